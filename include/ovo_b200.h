@@ -1,0 +1,212 @@
+/* ovo_b200 — C ABI of the B200-native hot path of tberriel/OVO
+ * (CLIP/ViT region encoder -> 3D association/fusion into the point map -> text-vs-map cosine query).
+ *
+ * The reference has no FFI on this path: its seam is the Python class surface of `OVO`,
+ * `CLIPGenerator`, `MaskGenerator`, `Instance3D` (ovo/entities/*.py).  ovo_b200/ mirrors those classes in
+ * Python and calls the entry points below through ctypes; INTEGRATION.md shows the binding.
+ * Each entry point cites the reference lines it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *   - every pointer named *_dev is a CUDA device pointer owned by the caller (PyTorch); *_host is host memory;
+ *   - all calls return 0 on success or a negative OVO_E_* code; ovo_last_error() gives the message
+ *     (thread-local); no C++ exception crosses the boundary;
+ *   - kernels are enqueued on the caller's stream (`stream` is a cudaStream_t passed as void*);
+ *     calls are asynchronous except where a host result is documented;
+ *   - a handle is not thread-safe; distinct handles are.  One handle per GPU.
+ */
+#ifndef OVO_B200_H
+#define OVO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OVO_OK 0
+#define OVO_E_INVALID (-1)  /* bad argument / unsupported shape */
+#define OVO_E_CUDA (-2)     /* CUDA runtime / driver error */
+#define OVO_E_NOMEM (-3)    /* workspace allocation failed */
+#define OVO_E_STATE (-4)    /* call sequence error (e.g. fuse before associate) */
+
+typedef struct ovo_encoder ovo_encoder_t;
+typedef struct ovo_map ovo_map_t;
+
+const char* ovo_last_error(void);
+int ovo_version(void);
+/* Number of kernels launched by this library on the calling thread since the last reset
+ * (bench.py reports it as `gpu_launches`). */
+long long ovo_launch_count(int reset);
+
+/* ------------------------------------------------------------------------------------------------
+ * Encoder: PE ViT (vision tower + text tower)
+ *   thirdParty/perception_models/core/vision_encoder/pe.py:293-533 (VisionTransformer),
+ *   pe.py:552-695 (TextTransformer), config.py:101-118 (PE-Core-L14-336).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  int image_size; /* 336 */
+  int patch_size; /* 14 */
+  int width;      /* 1024; head_dim = width/heads must be 64 */
+  int layers;     /* 24 */
+  int heads;      /* 16 */
+  int mlp_width;  /* 4096 */
+  int output_dim; /* 1024 */
+  float ln_eps;   /* 1e-5 (pe.py:302) */
+  /* text tower (0 layers = no text tower) */
+  int text_ctx;   /* 32 */
+  int text_width; /* 1024 */
+  int text_heads; /* 16 */
+  int text_layers;
+  int text_mlp_width;
+  int vocab_size; /* 49408 */
+  int text_output_dim;
+} ovo_vit_cfg;
+
+/* Device pointers to one transformer block's parameters (reference state_dict names):
+ *   ln_1.{weight,bias}, attn.in_proj_{weight [3W,W], bias}, attn.out_proj.{weight [W,W], bias},
+ *   ln_2.{weight,bias}, mlp.c_fc.{weight [F,W], bias}, mlp.c_proj.{weight [W,F], bias}.
+ * Matrices are bf16 row-major exactly as nn.Linear stores them ([out,in]); vectors are f32. */
+typedef struct {
+  const float* ln1_w; const float* ln1_b;
+  const void* qkv_w;  const float* qkv_b;
+  const void* out_w;  const float* out_b;
+  const float* ln2_w; const float* ln2_b;
+  const void* fc_w;   const float* fc_b;
+  const void* proj_w; const float* proj_b;
+} ovo_block_weights;
+
+typedef struct {
+  /* vision tower */
+  const void* patch_w;      /* bf16 [width, kpad]: conv1.weight flattened (c,ky,kx) and zero padded to kpad */
+  int patch_kpad;           /* 3*patch*patch rounded up to a multiple of 64 (640 for 14x14) */
+  const float* cls_pos0;    /* f32 [width]: class_embedding + positional_embedding[0] (pe.py:512-519) */
+  const float* pos;         /* f32 [1+grid^2, width] positional_embedding */
+  const float* ln_pre_w; const float* ln_pre_b;
+  const float* ln_post_w; const float* ln_post_b;
+  const ovo_block_weights* blocks;          /* host array [layers] of device-pointer structs */
+  /* region pooling (textregion.py:163-195 closed form): r = normalize(mean . pool_w^T + pool_b),
+   * pool_w = (W_v^T W_o^T proj)^T as bf16 [output_dim, width], pool_b f32 [output_dim] */
+  const void* pool_w; const float* pool_b;
+  /* text tower */
+  const float* tok_emb;     /* f32 [vocab, text_width] token_embedding.weight */
+  const float* text_pos;    /* f32 [ctx, text_width] */
+  const ovo_block_weights* text_blocks;     /* host array [text_layers] */
+  const float* ln_final_w; const float* ln_final_b;
+  const void* text_proj_w;  /* bf16 [text_output_dim, text_width] = text_projection^T */
+} ovo_vit_weights;
+
+/* Creates an encoder able to process up to max_images 336x336 crops per call (activations are
+ * pre-allocated), frames of at most max_h x max_w and max_masks masks per call. */
+int ovo_encoder_create(const ovo_vit_cfg* cfg, const ovo_vit_weights* w, int max_images, int max_h, int max_w,
+                       int max_masks, ovo_encoder_t** out);
+void ovo_encoder_destroy(ovo_encoder_t* enc);
+
+/* E1: PETextRegion.get_img_features crops + T.Resize(antialias) + Normalize (textregion.py:104-134,
+ * transforms.py:19-26).  rgb uint8 [n_frames,H,W,3] -> im2col'd patches inside the encoder.  Returns the
+ * number of 336x336 images per frame in *n_img_per_frame (1 + floor(H/336)*floor(W/336)). */
+int ovo_encoder_preprocess(ovo_encoder_t* enc, const uint8_t* rgb_dev, int n_frames, int H, int W,
+                           int* n_img_per_frame, void* stream);
+/* Test tap: same as above but from already normalised float pixels [n_img,3,S,S] (skips the resize). */
+int ovo_encoder_load_pixels(ovo_encoder_t* enc, const float* pixels_dev, int n_img, void* stream);
+/* E2: VisionTransformer.forward_features(norm=True) (pe.py:499-533) on the images loaded by
+ * preprocess/load_pixels.  n_layers < 0 = all.  tokens_out_dev (optional, may be NULL) receives f32
+ * [n_img, 1+grid^2, width]; apply_ln_post selects the final ln_post. */
+int ovo_encoder_forward(ovo_encoder_t* enc, int n_img, int n_layers, int apply_ln_post, float* tokens_out_dev,
+                        void* stream);
+/* E3-E5: resize_features + get_features_mask + pe_value_with_sam2_attn (textregion.py:9-28,145-195) for
+ * ONE frame whose n_img images start at image index img0 of the last forward.
+ * masks uint8 [M,H,W] (non-zero = set) -> out f32 [M, output_dim], unit norm (NaN rows for masks that
+ * cover no token, as the reference). */
+int ovo_encoder_pool_regions(ovo_encoder_t* enc, int img0, int H, int W, const uint8_t* masks_dev, int M,
+                             float* out_dev, void* stream);
+/* CLIPGenerator.extract_clip, TextRegion branch (clip_generator.py:125-135): E1..E5 for a batch of
+ * frames.  masks are concatenated over frames, masks_per_frame_host[f] of them belong to frame f. */
+int ovo_encode_regions(ovo_encoder_t* enc, const uint8_t* rgb_dev, int n_frames, int H, int W,
+                       const uint8_t* masks_dev, const int* masks_per_frame_host, float* out_dev, void* stream);
+/* Q1: CLIP.encode_text (pe.py:671-695,725): tokens int32 [T, ctx] -> f32 [T, text_output_dim], NOT
+ * normalised (the caller applies clip_generator.py:170-173,193-196). */
+int ovo_encode_text(ovo_encoder_t* enc, const int32_t* tokens_dev, int T, float* out_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Map: 3D association, instance vote, fusion, query
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t n_matched;    /* points matched into this mask                        (ovo.py:257) */
+  int32_t n_assigned;   /* of those, points that already carry an instance id   (ovo.py:260) */
+  int32_t n_unassigned;
+  int32_t mode_id;      /* torch.mode of the assigned ids, ties -> smallest     (ovo.py:264); -1 if none */
+  int32_t ins_id;       /* instance id given to the mask, -1 if none            (ovo.py:263-276) */
+  int32_t is_new;       /* 1 if ins_id was newly allocated from next_ins_id     (ovo.py:271-276) */
+  int32_t area;         /* (seg_map == mask).sum()                              (ovo.py:259) */
+  int32_t reserved;
+} ovo_vote_row;
+
+typedef struct {
+  const float* depth_dev;   /* [h,w] f32 metres, 0 = invalid */
+  int h, w;
+  const int32_t* seg_map_dev; /* [H,W] i32, -1 = no mask */
+  int H, W;
+  int n_masks;              /* seg_map.max()+1 */
+  float c2w[16];            /* camera-to-world, row major */
+  float w2c[16];            /* its inverse (torch.linalg.inv(c2w), ovo.py:216) */
+  float K[9];               /* intrinsics, row major */
+  float match_th;           /* semantic.match_distance_th (0.05) */
+  int track_th;             /* semantic.track_th (100) */
+  int depth_filter;         /* semantic.depth_filter */
+  /* rgb/depth resolution fix-up (ovo.py:218-221): 0 = none, else u' = int((u+crop_edge)*ratio_w) */
+  int has_ratio; float ratio_h, ratio_w; int crop_edge;
+} ovo_frame;
+
+int ovo_map_create(ovo_map_t** out);
+void ovo_map_destroy(ovo_map_t* map);
+
+/* geometry_utils.depth_filter (geometry_utils.py:92-96): 7x7 gaussian (sigma 2.5, reflect) high-pass;
+ * |d - blur| > 0.05 -> -1. */
+int ovo_depth_filter(const float* depth_dev, int h, int w, float* out_dev, void* stream);
+
+/* OVO._match_and_track_instances minus the Python bookkeeping (ovo.py:204-229, 240-282):
+ * frustum cull (geometry_utils.py:99-129,252-277) + projection/depth match (:26-89) + seg lookup +
+ * per-mask instance vote + id assignment to unassigned points, in two streaming passes over the map.
+ *   xyz_dev [N,3] f32, ins_ids_dev [N] i32 updated IN PLACE (-1 = unassigned),
+ *   next_ins_id: in = OVO.next_ins_id, out = advanced by the number of new instances,
+ *   votes_host [n_masks] filled on return (this call synchronises `stream` once),
+ *   n_matched_host = len(matched_points_idxs).
+ * The matched (point, mask) list of this keyframe is kept inside the handle in slot `kf_slot`
+ * (0 <= kf_slot < 64) for a later ovo_map_fuse_dense. */
+int ovo_map_associate(ovo_map_t* map, const float* xyz_dev, int32_t* ins_ids_dev, int64_t N, const ovo_frame* frame,
+                      int* next_ins_id, ovo_vote_row* votes_host, int* n_matched_host, int kf_slot, void* stream);
+/* Copies the matched list of a slot to the caller: pairs (point index, mask index), n from associate. */
+int ovo_map_get_matches(ovo_map_t* map, int kf_slot, int32_t* pairs_dev, int max_pairs, void* stream);
+
+/* Dense per-point running mean (north-star F6; per-point analogue of instance3d.py:19-21):
+ * for every matched point p of slot kf_slot whose mask m has mask_row_dev[m] = r >= 0:
+ *   bank[p] += (feats[r] - bank[p]) / (count[p] + 1); count[p] += 1.
+ * bank_dev bf16 [N, D], counts_dev i32 [N], feats_dev f32 [R, D], mask_row_dev i32 [n_masks]. */
+int ovo_map_fuse_dense(ovo_map_t* map, int kf_slot, void* bank_dev, int32_t* counts_dev, int64_t N, int D,
+                       const float* feats_dev, const int32_t* mask_row_dev, int n_masks, void* stream);
+
+/* Instance-bank running mean, fusion 'avg_pooling' (instance3d.py:19-21,157-189):
+ * bank[row[i]] = (bank[row[i]]*cnt + feats[i]) / (cnt+1), not re-normalised. bank f32 [I,D]. */
+int ovo_bank_update_mean(float* bank_dev, int32_t* counts_dev, int D, const float* feats_dev,
+                         const int32_t* rows_dev, int n, void* stream);
+
+/* clip_cosine_similarity (clip_utils.py:16-19) on the DENSE map: bank bf16 [N,D] x text f32 [Q,D]^T ->
+ * out f32 [N,Q].  tcgen05 GEMM streaming the bank once from HBM. */
+int ovo_query_dense(ovo_map_t* map, const void* bank_dev, int64_t N, int D, const float* text_dev, int Q,
+                    float* out_dev, void* stream);
+/* Same, instance bank: bank f32 [I,D] x text f32 [Q,D]^T -> out f32 [I,Q] in f32 arithmetic. */
+int ovo_query_instances(const float* bank_dev, int I, int D, const float* text_dev, int Q, float* out_dev,
+                        void* stream);
+/* OVO.classify_instances (ovo.py:486-491): argmax over queries + threshold. sim f32 [n,Q] ->
+ * cls i32 [n] (-1 if max <= th), conf f32 [n] (0 if max <= th). */
+int ovo_classify(const float* sim_dev, int64_t n, int Q, float th, int32_t* cls_dev, float* conf_dev, void* stream);
+
+/* Test tap for the GEMM machinery: C[M,N] f32 = A[M,K] bf16 . B[N,K]^T bf16 (+bias f32 [N]). */
+int ovo_gemm_bf16(const void* A_dev, int lda, const void* B_dev, int ldb, int M, int N, int K,
+                  const float* bias_dev, float* C_dev, int ldc, int force_bn, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OVO_B200_H */

@@ -1,0 +1,204 @@
+"""TEST INFRASTRUCTURE — CPU restatement (numpy, float32, fixed operation order) of the reference's
+3D association + fusion path.  Not part of the product; see oracle/encoder.py header for the rules.
+
+  gu  = ovo/utils/geometry_utils.py      ovo = ovo/entities/ovo.py      i3d = ovo/entities/instance3d.py
+
+Floating point feeds integer decisions here (pixel rounding, plane tests, depth threshold).  The
+reference evaluates them with torch.einsum / matmul / conv2d whose accumulation order is BLAS-defined;
+this restatement FIXES one order (left-to-right, every product and sum rounded to float32, no FMA) and
+the CUDA kernels use the same order with __fmul_rn/__fadd_rn, so CUDA == oracle bit-for-bit, and
+oracle == reference is pinned on the golden fixtures (tests/golden/assoc_*.npz, generated from the
+reference with oracle/gen_golden.py; mismatches counted there).
+"""
+import numpy as np
+
+f32 = np.float32
+
+
+def _dot4(m_row, x, y, z, w=None):
+    """((m0*x + m1*y) + m2*z) + m3*w  in float32, left to right."""
+    acc = f32(m_row[0]) * x
+    acc = acc + f32(m_row[1]) * y
+    acc = acc + f32(m_row[2]) * z
+    if w is None:
+        acc = acc + f32(m_row[3])
+    else:
+        acc = acc + f32(m_row[3]) * w
+    return acc.astype(f32) if isinstance(acc, np.ndarray) else f32(acc)
+
+
+def frustum_corners(depth: np.ndarray, c2w: np.ndarray, K: np.ndarray) -> np.ndarray:
+    """gu:99-129.  depth [h,w] f32, c2w [4,4] f32, K [3,3] f32 -> corners [8,3] f32."""
+    h, w = depth.shape
+    valid = depth[depth > 0]
+    dmin, dmax = f32(valid.min()), f32(valid.max())
+    px = np.array([0, w, 0, w, 0, w, 0, w], f32)
+    py = np.array([0, 0, h, h, 0, 0, h, h], f32)
+    pz = np.array([dmin] * 4 + [dmax] * 4, f32)
+    x = ((px - f32(K[0, 2])) * pz / f32(K[0, 0])).astype(f32)
+    y = ((py - f32(K[1, 2])) * pz / f32(K[1, 1])).astype(f32)
+    out = np.zeros((8, 3), f32)
+    for r in range(3):
+        out[:, r] = _dot4(c2w[r].astype(f32), x, y, pz)
+    return out
+
+
+def _cross(a, b):
+    return np.array([a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]], f32)
+
+
+def frustum_planes(c: np.ndarray) -> np.ndarray:
+    """gu:163-207.  corners [8,3] -> planes [6,4] (near, far, left, right, top, bottom), inside iff n.p+d<=0."""
+    pairs = [(2, 0, 1, 0), (6, 4, 5, 4), (4, 0, 2, 0), (7, 3, 1, 3), (5, 1, 3, 1), (6, 2, 0, 2)]
+    planes = np.zeros((6, 4), f32)
+    for i, (a, b, cc, d) in enumerate(pairs):
+        n = _cross((c[a] - c[b]).astype(f32), (c[cc] - c[d]).astype(f32))
+        dd = -f32(f32(f32(n[0] * c[i][0]) + f32(n[1] * c[i][1])) + f32(n[2] * c[i][2]))
+        planes[i, :3], planes[i, 3] = n, dd
+    return planes
+
+
+def frustum_mask(xyz: np.ndarray, corners: np.ndarray, planes: np.ndarray) -> np.ndarray:
+    """gu:252-277: AABB broad phase then 6 half-space tests.  xyz [N,3] f32 -> bool [N]."""
+    lo, hi = corners.min(0), corners.max(0)
+    x, y, z = xyz[:, 0], xyz[:, 1], xyz[:, 2]
+    m = (x >= lo[0]) & (x <= hi[0]) & (y >= lo[1]) & (y <= hi[1]) & (z >= lo[2]) & (z <= hi[2])
+    for p in planes:
+        m &= _dot4(p, x, y, z) <= 0
+    return m
+
+
+# torchvision _get_gaussian_kernel1d(7, 2.5, float32) bit patterns (torch.exp differs from np.exp by 1-2 ulp,
+# so the reference's values are pinned here and in ovo_b200/csrc/map.cu; checked in tests/test_oracle_pin.py)
+_K1D_7_25_BITS = np.array([1035802123, 1041042090, 1043549328, 1044527997, 1043549328, 1041042090, 1035802123],
+                          np.uint32)
+
+
+def gaussian_kernel1d(k: int = 7, sigma: float = 2.5) -> np.ndarray:
+    """torchvision _get_gaussian_kernel1d."""
+    if k == 7 and sigma == 2.5:
+        return _K1D_7_25_BITS.view(f32).copy()
+    half = (k - 1) * 0.5
+    x = np.linspace(-half, half, k, dtype=f32)
+    pdf = np.exp(-0.5 * (x / f32(sigma)) ** 2).astype(f32)
+    return (pdf / pdf.sum()).astype(f32)
+
+
+def depth_filter(depth: np.ndarray, k: int = 7, sigma: float = 2.5, th: float = 0.05) -> np.ndarray:
+    """gu:92-96: 7x7 gaussian blur (reflect padding, 2-D kernel = outer(k1d,k1d)), |d-blur|>th -> -1.
+    Accumulation order fixed: rows top to bottom, columns left to right."""
+    k1 = gaussian_kernel1d(k, sigma)
+    k2 = np.outer(k1, k1).astype(f32)
+    r = k // 2
+    pad = np.pad(depth.astype(f32), r, mode="reflect")
+    h, w = depth.shape
+    acc = np.zeros((h, w), f32)
+    for dy in range(k):
+        for dx in range(k):
+            acc = (acc + k2[dy, dx] * pad[dy:dy + h, dx:dx + w]).astype(f32)
+    hf = np.abs(depth.astype(f32) - acc)
+    return np.where(hf > f32(th), f32(-1), depth.astype(f32)).astype(f32)
+
+
+def project_match(xyz: np.ndarray, depth: np.ndarray, w2c: np.ndarray, K: np.ndarray, th: float):
+    """gu:26-89 on an already culled subset.  Returns (ok bool[n], u int32[n], v int32[n])."""
+    h, w = depth.shape
+    x, y, z = xyz[:, 0].astype(f32), xyz[:, 1].astype(f32), xyz[:, 2].astype(f32)
+    w2c = w2c.astype(f32)
+    lx, ly, lz, lw = (_dot4(w2c[r], x, y, z) for r in range(4))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        X, Y, Z = (lx / lw).astype(f32), (ly / lw).astype(f32), (lz / lw).astype(f32)
+        K = K.astype(f32)
+        ph = [((f32(K[r, 0]) * X + f32(K[r, 1]) * Y).astype(f32) + f32(K[r, 2]) * Z).astype(f32) for r in range(3)]
+        uf, vf = np.rint((ph[0] / ph[2]).astype(f32)), np.rint((ph[1] / ph[2]).astype(f32))
+    finite = np.isfinite(uf) & np.isfinite(vf) & (np.abs(uf) < 2e9) & (np.abs(vf) < 2e9)
+    u = np.where(finite, uf, -1).astype(np.int64).astype(np.int32)
+    v = np.where(finite, vf, -1).astype(np.int64).astype(np.int32)
+    inpl = finite & (u < w) & (v < h) & (u >= 0) & (v >= 0)
+    d = depth[np.clip(v, 0, h - 1), np.clip(u, 0, w - 1)].astype(f32)
+    ok = inpl & (np.abs(lz - d) < f32(th)) & (d != 0)
+    return ok, u, v
+
+
+def associate(xyz, ins_ids, depth, seg_map, c2w, w2c, K, match_th, use_depth_filter=True, rgb_depth_ratio=()):
+    """ovo:204-224: cull -> (depth filter) -> project/match -> seg lookup.
+    Returns seg_of_pt int32[N] (-2 = not matched, else seg_map value which may be -1)."""
+    N = xyz.shape[0]
+    seg_of_pt = np.full(N, -2, np.int32)
+    corners = frustum_corners(depth, c2w, K)
+    planes = frustum_planes(corners)
+    fm = frustum_mask(xyz, corners, planes)
+    d = depth_filter(depth) if use_depth_filter else depth
+    idx = np.nonzero(fm)[0]
+    ok, u, v = project_match(xyz[idx], d, w2c, K, match_th)
+    u, v = u[ok], v[ok]
+    if len(rgb_depth_ratio) > 0:                      # ovo:218-221
+        u = u + int(rgb_depth_ratio[-1]); v = v + int(rgb_depth_ratio[-1])
+        v = (v.astype(f32) * f32(rgb_depth_ratio[0])).astype(np.int32)   # int tensor * python float -> f32 in torch
+        u = (u.astype(f32) * f32(rgb_depth_ratio[1])).astype(np.int32)
+    seg_of_pt[idx[ok]] = seg_map[v, u]
+    return seg_of_pt, fm
+
+
+def track(ins_ids: np.ndarray, seg_of_pt: np.ndarray, seg_map: np.ndarray, track_th: int, next_ins_id: int):
+    """ovo:240-282 without the Instance3D side effects.
+    Returns (ins_ids_new int32[N], rows list of dict per mask, next_ins_id).
+    row: mask, n_matched, n_assigned, n_unassigned, mode_id, ins_id (-1 none), is_new, area."""
+    ins = ins_ids.copy()
+    n_masks = int(seg_map.max()) + 1
+    rows = []
+    for m in range(n_masks):
+        pts = np.nonzero(seg_of_pt == m)[0]
+        assigned = ins_ids[pts] > -1
+        row = dict(mask=m, n_matched=len(pts), n_assigned=int(assigned.sum()), n_unassigned=int((~assigned).sum()),
+                   mode_id=-1, ins_id=-1, is_new=0, area=int((seg_map == m).sum()))
+        if row["n_assigned"] > 0:
+            vals, cnt = np.unique(ins_ids[pts[assigned]], return_counts=True)
+            row["mode_id"] = int(vals[np.argmax(cnt)])           # ties -> smallest id (torch.mode on CPU)
+        if len(pts) > track_th:                                   # ovo:258
+            if row["n_assigned"] > track_th:                      # ovo:263-269
+                row["ins_id"] = row["mode_id"]
+            elif row["n_unassigned"] > track_th:                  # ovo:271-276
+                row["ins_id"] = next_ins_id; row["is_new"] = 1; next_ins_id += 1
+            if row["ins_id"] > -1:                                # ovo:278-280
+                ins[pts[~assigned]] = row["ins_id"]
+        rows.append(row)
+    return ins, rows, next_ins_id
+
+
+def fuse_masks(binary_maps: np.ndarray, rows: list):
+    """ovo:284-324 with n_top_views<=0 or every keyframe in the top-k (k_top_views=10000 default):
+    masks voted to the same instance are OR-ed into the first; order = first-vote order.
+    Returns (matched_ins_ids list, fused maps [M',H,W], mask_row int32[n_masks] (-1 = dropped))."""
+    order, groups = [], {}
+    for r in rows:
+        if r["ins_id"] > -1:
+            if r["ins_id"] not in groups:
+                groups[r["ins_id"]] = []; order.append(r["ins_id"])
+            groups[r["ins_id"]].append(r["mask"])
+    bm = binary_maps.copy()
+    mask_row = np.full(len(rows), -1, np.int32)
+    idxs = []
+    for j, ins in enumerate(order):
+        first = groups[ins][0]
+        for other in groups[ins][1:]:
+            bm[first] |= bm[other]
+        for mm in groups[ins]:
+            mask_row[mm] = j
+        idxs.append(first)
+    return order, bm[idxs] if len(idxs) else bm[:0], mask_row
+
+
+def avg_pooling(clips: np.ndarray) -> np.ndarray:
+    """i3d:19-21: mean over keyframe descriptors, NOT re-normalised."""
+    return clips.astype(f32).mean(axis=0, dtype=f32)
+
+
+def dense_running_mean(bank: np.ndarray, counts: np.ndarray, pt_idx: np.ndarray, feats: np.ndarray):
+    """Dense per-point analogue of i3d:19-21 (north-star F6): f_p += (e - f_p)/(c_p+1); c_p += 1.
+    bank [N,D] f32 (the CUDA bank is bf16: compare with bf16 rounding applied after each update)."""
+    for p, e in zip(pt_idx, feats):
+        c = counts[p] + 1
+        bank[p] = bank[p] + (e - bank[p]) / f32(c)
+        counts[p] = c
+    return bank, counts

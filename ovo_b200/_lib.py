@@ -1,0 +1,107 @@
+"""ctypes binding of libovo_b200.so (include/ovo_b200.h).  There is no CPU fallback: if the shared
+library is missing or a call fails, a RuntimeError is raised."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libovo_b200.so")
+
+c_void_p, c_int, c_float, c_int64 = C.c_void_p, C.c_int, C.c_float, C.c_int64
+
+
+class VitCfg(C.Structure):
+    _fields_ = [("image_size", c_int), ("patch_size", c_int), ("width", c_int), ("layers", c_int),
+                ("heads", c_int), ("mlp_width", c_int), ("output_dim", c_int), ("ln_eps", c_float),
+                ("text_ctx", c_int), ("text_width", c_int), ("text_heads", c_int), ("text_layers", c_int),
+                ("text_mlp_width", c_int), ("vocab_size", c_int), ("text_output_dim", c_int)]
+
+
+class BlockWeights(C.Structure):
+    _fields_ = [(n, c_void_p) for n in ("ln1_w", "ln1_b", "qkv_w", "qkv_b", "out_w", "out_b",
+                                        "ln2_w", "ln2_b", "fc_w", "fc_b", "proj_w", "proj_b")]
+
+
+class VitWeights(C.Structure):
+    _fields_ = [("patch_w", c_void_p), ("patch_kpad", c_int), ("cls_pos0", c_void_p), ("pos", c_void_p),
+                ("ln_pre_w", c_void_p), ("ln_pre_b", c_void_p), ("ln_post_w", c_void_p), ("ln_post_b", c_void_p),
+                ("blocks", C.POINTER(BlockWeights)), ("pool_w", c_void_p), ("pool_b", c_void_p),
+                ("tok_emb", c_void_p), ("text_pos", c_void_p), ("text_blocks", C.POINTER(BlockWeights)),
+                ("ln_final_w", c_void_p), ("ln_final_b", c_void_p), ("text_proj_w", c_void_p)]
+
+
+class VoteRow(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("n_matched", "n_assigned", "n_unassigned", "mode_id", "ins_id",
+                                         "is_new", "area", "reserved")]
+
+
+class Frame(C.Structure):
+    _fields_ = [("depth_dev", c_void_p), ("h", c_int), ("w", c_int), ("seg_map_dev", c_void_p), ("H", c_int),
+                ("W", c_int), ("n_masks", c_int), ("c2w", c_float * 16), ("w2c", c_float * 16), ("K", c_float * 9),
+                ("match_th", c_float), ("track_th", c_int), ("depth_filter", c_int), ("has_ratio", c_int),
+                ("ratio_h", c_float), ("ratio_w", c_float), ("crop_edge", c_int)]
+
+
+# name -> (restype, argtypes); mirrors include/ovo_b200.h one to one
+SIGNATURES = {
+    "ovo_last_error": (C.c_char_p, []),
+    "ovo_version": (c_int, []),
+    "ovo_launch_count": (C.c_longlong, [c_int]),
+    "ovo_encoder_create": (c_int, [C.POINTER(VitCfg), C.POINTER(VitWeights), c_int, c_int, c_int, c_int,
+                                   C.POINTER(c_void_p)]),
+    "ovo_encoder_destroy": (None, [c_void_p]),
+    "ovo_encoder_preprocess": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, C.POINTER(c_int), c_void_p]),
+    "ovo_encoder_load_pixels": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
+    "ovo_encoder_forward": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "ovo_encoder_pool_regions": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),
+    "ovo_encode_regions": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, C.POINTER(c_int), c_void_p,
+                                   c_void_p]),
+    "ovo_encode_text": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "ovo_map_create": (c_int, [C.POINTER(c_void_p)]),
+    "ovo_map_destroy": (None, [c_void_p]),
+    "ovo_depth_filter": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "ovo_map_associate": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, C.POINTER(Frame), C.POINTER(c_int),
+                                  C.POINTER(VoteRow), C.POINTER(c_int), c_int, c_void_p]),
+    "ovo_map_get_matches": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p]),
+    "ovo_map_fuse_dense": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int,
+                                   c_void_p]),
+    "ovo_bank_update_mean": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p]),
+    "ovo_query_dense": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_int, c_void_p, c_void_p]),
+    "ovo_query_instances": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),
+    "ovo_classify": (c_int, [c_void_p, c_int64, c_int, c_float, c_void_p, c_void_p, c_void_p]),
+    "ovo_gemm_bf16": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int,
+                              c_int, c_void_p]),
+}
+
+_lib = None
+
+
+def lib():
+    """The loaded library; raises if it has not been built (python -m ovo_b200.build)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} not found: build it with `python -m ovo_b200.build` "
+                               "(there is no CPU fallback)")
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = handle
+    return _lib
+
+
+def check(code: int, what: str = "") -> int:
+    if code < 0:
+        msg = lib().ovo_last_error()
+        raise RuntimeError(f"ovo_b200 {what} failed ({code}): {msg.decode() if msg else ''}")
+    return code
+
+
+def ptr(t):
+    """Device (or host) pointer of a torch tensor, or None."""
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)

@@ -1,0 +1,148 @@
+// Error state, TMA descriptor creation, GEMM dispatch, and the GEMM test tap of the C ABI.
+#include "common.cuh"
+#include "gemm.cuh"
+
+#include <cudaTypedefs.h>
+#include <mutex>
+
+namespace ovo {
+
+static thread_local char g_err[512] = "";
+static thread_local long long g_launches = 0;
+
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+void count_launch(int n) { g_launches += n; }
+
+int num_sms() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+// cuTensorMapEncodeTiled is fetched through the runtime so the library has no link-time libcuda dependency
+// (it must load on a machine without a driver for the symbol-export test).
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  });
+  return fn;
+}
+
+int make_tmap_bf16_2d(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld_elems,
+                      uint32_t box_rows, uint32_t box_cols) {
+  auto enc = get_encode();
+  if (!enc) return set_error(OVO_E_CUDA, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (ld_elems & 7) != 0)
+    return set_error(OVO_E_INVALID, "TMA operand must be 16-byte aligned with a row stride multiple of 8 elements");
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld_elems * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(OVO_E_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return OVO_OK;
+}
+
+template <int BN, int EPI>
+static int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const EpiParams& ep,
+                      cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  auto kern = gemm_bf16_tn_kernel<BN, EPI>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    OVO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  const int tiles = ceil_div(M, kBM) * ceil_div(N, BN);
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, M, N, K, ep);
+  OVO_CHECK_LAUNCH();
+  return OVO_OK;
+}
+
+template <int EPI>
+static int launch_bn(int bn, const __nv_bfloat16* A, int lda, const __nv_bfloat16* B, int ldb, int M, int N, int K,
+                     const EpiParams& ep, cudaStream_t stream) {
+  CUtensorMap ta, tb;
+  OVO_TRY(make_tmap_bf16_2d(&ta, A, M, K, lda, kBM, kBK));
+  OVO_TRY(make_tmap_bf16_2d(&tb, B, N, K, ldb, bn, kBK));
+  switch (bn) {
+    case 32: return launch_one<32, EPI>(ta, tb, M, N, K, ep, stream);
+    case 64: return launch_one<64, EPI>(ta, tb, M, N, K, ep, stream);
+    case 128: return launch_one<128, EPI>(ta, tb, M, N, K, ep, stream);
+    case 256: return launch_one<256, EPI>(ta, tb, M, N, K, ep, stream);
+  }
+  return set_error(OVO_E_INVALID, "unsupported BN %d", bn);
+}
+
+// Pick the N tile: the widest tile that does not waste more SM-rounds than a narrower one.
+static int pick_bn(int M, int N) {
+  if (N <= 32) return 32;
+  if (N <= 64) return 64;
+  if (N <= 128) return 128;
+  const int sms = num_sms();
+  const long long t256 = static_cast<long long>(ceil_div(M, kBM)) * ceil_div(N, 256);
+  const long long t128 = static_cast<long long>(ceil_div(M, kBM)) * ceil_div(N, 128);
+  const long long cost256 = 2LL * ceil_div(t256, sms);
+  const long long cost128 = 1LL * ceil_div(t128, sms);
+  return cost256 <= cost128 ? 256 : 128;
+}
+
+int launch_gemm(int epi, const __nv_bfloat16* A, int lda, const __nv_bfloat16* B, int ldb, int M, int N, int K,
+                const EpiParams& ep, cudaStream_t stream, int force_bn) {
+  if (M <= 0 || N <= 0 || K <= 0) return set_error(OVO_E_INVALID, "gemm: empty problem %dx%dx%d", M, N, K);
+  const int bn = force_bn > 0 ? force_bn : pick_bn(M, N);
+  switch (epi) {
+    case EPI_F32: return launch_bn<EPI_F32>(bn, A, lda, B, ldb, M, N, K, ep, stream);
+    case EPI_BF16: return launch_bn<EPI_BF16>(bn, A, lda, B, ldb, M, N, K, ep, stream);
+    case EPI_BF16_GELU: return launch_bn<EPI_BF16_GELU>(bn, A, lda, B, ldb, M, N, K, ep, stream);
+    case EPI_F32_RESID: return launch_bn<EPI_F32_RESID>(bn, A, lda, B, ldb, M, N, K, ep, stream);
+    case EPI_QKV: return launch_bn<EPI_QKV>(bn, A, lda, B, ldb, M, N, K, ep, stream);
+    case EPI_PATCH: return launch_bn<EPI_PATCH>(bn, A, lda, B, ldb, M, N, K, ep, stream);
+  }
+  return set_error(OVO_E_INVALID, "unknown epilogue %d", epi);
+}
+
+}  // namespace ovo
+
+extern "C" {
+
+const char* ovo_last_error(void) { return ovo::g_err; }
+int ovo_version(void) { return 100; }
+long long ovo_launch_count(int reset) {
+  long long v = ovo::g_launches;
+  if (reset) ovo::g_launches = 0;
+  return v;
+}
+
+int ovo_gemm_bf16(const void* A_dev, int lda, const void* B_dev, int ldb, int M, int N, int K, const float* bias_dev,
+                  float* C_dev, int ldc, int force_bn, void* stream) {
+  ovo::EpiParams ep;
+  ep.out = C_dev;
+  ep.ldo = ldc;
+  ep.bias = bias_dev;
+  return ovo::launch_gemm(ovo::EPI_F32, static_cast<const __nv_bfloat16*>(A_dev), lda,
+                          static_cast<const __nv_bfloat16*>(B_dev), ldb, M, N, K, ep,
+                          static_cast<cudaStream_t>(stream), force_bn);
+}
+
+}  // extern "C"

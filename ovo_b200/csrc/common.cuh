@@ -1,0 +1,42 @@
+// Shared host-side helpers: error reporting, launch counting, checked CUDA calls.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+
+#include "../../include/ovo_b200.h"
+
+namespace ovo {
+
+int set_error(int code, const char* fmt, ...);
+void count_launch(int n = 1);
+
+#define OVO_CUDA(expr)                                                                                    \
+  do {                                                                                                    \
+    cudaError_t _e = (expr);                                                                              \
+    if (_e != cudaSuccess)                                                                                \
+      return ::ovo::set_error(OVO_E_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+  } while (0)
+
+#define OVO_CHECK_LAUNCH()                                                                               \
+  do {                                                                                                   \
+    ::ovo::count_launch();                                                                               \
+    cudaError_t _e = cudaGetLastError();                                                                 \
+    if (_e != cudaSuccess)                                                                               \
+      return ::ovo::set_error(OVO_E_CUDA, "%s:%d kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \
+  } while (0)
+
+#define OVO_REQUIRE(cond, ...)                                    \
+  do {                                                            \
+    if (!(cond)) return ::ovo::set_error(OVO_E_INVALID, __VA_ARGS__); \
+  } while (0)
+
+#define OVO_TRY(expr)         \
+  do {                        \
+    int _r = (expr);          \
+    if (_r != OVO_OK) return _r; \
+  } while (0)
+
+inline int ceil_div(long long a, long long b) { return static_cast<int>((a + b - 1) / b); }
+
+}  // namespace ovo

@@ -1,0 +1,680 @@
+// PE ViT region encoder + text tower (reference: thirdParty/perception_models/core/vision_encoder/pe.py,
+// rope.py, transforms.py; ovo/entities/textregion.py) behind the C ABI of include/ovo_b200.h.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <vector>
+
+#include "attention.cuh"
+#include "common.cuh"
+#include "gemm.cuh"
+
+namespace ovo {
+
+// =========================================================================================== small kernels
+// LayerNorm over rows of `width` f32 (pe.py:183-184,347-348; eps 1e-5): one warp per row, two-pass in registers.
+// Writes bf16 (GEMM A operand) and/or f32.
+template <int kMaxPerLane>
+__global__ void __launch_bounds__(256)
+    layernorm_kernel(const float* __restrict__ x, int rows, int width, const float* __restrict__ g,
+                     const float* __restrict__ b, float eps, __nv_bfloat16* __restrict__ out_bf16,
+                     float* __restrict__ out_f32, const int* __restrict__ gather /* optional row indices */) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const int src = gather ? gather[row] : row;
+  const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(src) * width);
+  const int nvec = width >> 2;
+  float4 v[kMaxPerLane];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMaxPerLane; ++i) {
+    const int idx = lane + 32 * i;
+    if (idx < nvec) {
+      v[i] = xr[idx];
+      sum += v[i].x + v[i].y + v[i].z + v[i].w;
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum / width;
+  float var = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMaxPerLane; ++i) {
+    const int idx = lane + 32 * i;
+    if (idx < nvec) {
+      const float a = v[i].x - mean, bb = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      var += a * a + bb * bb + c * c + d * d;
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+  const float rstd = rsqrtf(var / width + eps);
+#pragma unroll
+  for (int i = 0; i < kMaxPerLane; ++i) {
+    const int idx = lane + 32 * i;
+    if (idx < nvec) {
+      const float4 gg = __ldg(reinterpret_cast<const float4*>(g) + idx);
+      const float4 bb = __ldg(reinterpret_cast<const float4*>(b) + idx);
+      float4 o;
+      o.x = (v[i].x - mean) * rstd * gg.x + bb.x;
+      o.y = (v[i].y - mean) * rstd * gg.y + bb.y;
+      o.z = (v[i].z - mean) * rstd * gg.z + bb.z;
+      o.w = (v[i].w - mean) * rstd * gg.w + bb.w;
+      if (out_f32) reinterpret_cast<float4*>(out_f32 + static_cast<size_t>(row) * width)[idx] = o;
+      if (out_bf16) {
+        uint2 u;
+        u.x = pack_bf16(o.x, o.y);
+        u.y = pack_bf16(o.z, o.w);
+        reinterpret_cast<uint2*>(out_bf16 + static_cast<size_t>(row) * width)[idx] = u;
+      }
+    }
+  }
+}
+
+// x[b*(P+1)] = class_embedding + positional_embedding[0]   (pe.py:512-519)
+__global__ void cls_rows_kernel(float* __restrict__ x, int n_img, int tokens, int width, const float* __restrict__ cls_pos0) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_img * width) return;
+  const int b = i / width, d = i - b * width;
+  x[static_cast<size_t>(b) * tokens * width + d] = cls_pos0[d];
+}
+
+// ------------------------------------------------------------------------------------------- E1 preprocess
+struct ImgJob {  // one 336x336 output image cut from a frame
+  int frame, y1, x1, h, w;   // source rectangle
+  int tab_x, tab_y;          // offsets (in entries) of the per-axis tables
+  int kx, ky;                // taps per output (table row length)
+};
+
+// horizontal anti-aliased pass: tmp[img][c][y][ox] = sum_k wx[ox][k] * src[y1+y][x1+xmin[ox]+k][c] / 255
+__global__ void aa_resize_h_kernel(const uint8_t* __restrict__ rgb, int H, int W, const ImgJob* __restrict__ jobs,
+                                   const int* __restrict__ tab_min, const int* __restrict__ tab_size,
+                                   const float* __restrict__ tab_w, int S, float* __restrict__ tmp, int tmp_h) {
+  const ImgJob j = jobs[blockIdx.z];
+  const int ox = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  if (ox >= S || y >= j.h) return;
+  const int xmin = tab_min[j.tab_x + ox], n = tab_size[j.tab_x + ox];
+  const float* w = tab_w + static_cast<size_t>(j.tab_x + ox) * j.kx;
+  const uint8_t* src = rgb + ((static_cast<size_t>(j.frame) * H + j.y1 + y) * W + j.x1 + xmin) * 3;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+  for (int k = 0; k < n; ++k) {
+    const float wk = w[k];
+    a0 += wk * (static_cast<float>(src[3 * k]) / 255.f);
+    a1 += wk * (static_cast<float>(src[3 * k + 1]) / 255.f);
+    a2 += wk * (static_cast<float>(src[3 * k + 2]) / 255.f);
+  }
+  float* dst = tmp + (static_cast<size_t>(blockIdx.z) * 3 * tmp_h + y) * S + ox;
+  dst[0] = a0;
+  dst[static_cast<size_t>(tmp_h) * S] = a1;
+  dst[static_cast<size_t>(2) * tmp_h * S] = a2;
+}
+
+// vertical pass + Normalize(0.5, 0.5) + im2col to patch-major bf16 rows [img*P + patch][c*p*p + ky*p + kx]
+__global__ void aa_resize_v_patch_kernel(const float* __restrict__ tmp, int tmp_h, const ImgJob* __restrict__ jobs,
+                                         const int* __restrict__ tab_min, const int* __restrict__ tab_size,
+                                         const float* __restrict__ tab_w, int S, int patch, int kpad,
+                                         __nv_bfloat16* __restrict__ patches) {
+  const ImgJob j = jobs[blockIdx.z];
+  const int ox = blockIdx.x * blockDim.x + threadIdx.x;
+  const int oy = blockIdx.y;
+  if (ox >= S) return;
+  const int ymin = tab_min[j.tab_y + oy], n = tab_size[j.tab_y + oy];
+  const float* w = tab_w + static_cast<size_t>(j.tab_y + oy) * j.ky;
+  const int grid = S / patch;
+  const int prow = blockIdx.z * grid * grid + (oy / patch) * grid + ox / patch;
+  const int pcol = (oy % patch) * patch + ox % patch;
+  for (int c = 0; c < 3; ++c) {
+    const float* src = tmp + ((static_cast<size_t>(blockIdx.z) * 3 + c) * tmp_h + ymin) * S + ox;
+    float a = 0.f;
+    for (int k = 0; k < n; ++k) a += w[k] * src[static_cast<size_t>(k) * S];
+    a = (a - 0.5f) / 0.5f;
+    patches[static_cast<size_t>(prow) * kpad + c * patch * patch + pcol] = __float2bfloat16_rn(a);
+  }
+}
+
+// test tap: normalised f32 pixels [n,3,S,S] -> patch-major bf16
+__global__ void pixels_to_patches_kernel(const float* __restrict__ px, int n_img, int S, int patch, int kpad,
+                                         __nv_bfloat16* __restrict__ patches) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t total = static_cast<size_t>(n_img) * 3 * S * S;
+  if (i >= total) return;
+  const int ox = i % S, oy = (i / S) % S, c = (i / (static_cast<size_t>(S) * S)) % 3, img = i / (static_cast<size_t>(3) * S * S);
+  const int grid = S / patch;
+  const size_t prow = static_cast<size_t>(img) * grid * grid + (oy / patch) * grid + ox / patch;
+  patches[prow * kpad + c * patch * patch + (oy % patch) * patch + ox % patch] = __float2bfloat16_rn(px[i]);
+}
+
+// ------------------------------------------------------------------------------------------- E3 canvas
+// resize_features (textregion.py:9-28): bilinear up-sample (align_corners=False) of the global image's
+// tokens to [ph,pw], then 0.5*up + tokens of the crop that owns the cell.  tokens: [n_img, 1+g*g, width].
+__global__ void token_canvas_kernel(const float* __restrict__ tokens, int g, int width, int nh, int nw,
+                                    float* __restrict__ canvas) {
+  const int ph = nh * g, pw = nw * g;
+  const int p = blockIdx.x;  // canvas cell
+  const int py = p / pw, px = p - py * pw;
+  const float sy = fmaxf((static_cast<float>(g) / ph) * (py + 0.5f) - 0.5f, 0.f);
+  const float sx = fmaxf((static_cast<float>(g) / pw) * (px + 0.5f) - 0.5f, 0.f);
+  const int y0 = min(static_cast<int>(sy), g - 1), x0 = min(static_cast<int>(sx), g - 1);
+  const int y1 = min(y0 + 1, g - 1), x1 = min(x0 + 1, g - 1);
+  const float ly = sy - y0, lx = sx - x0;
+  const size_t tstride = static_cast<size_t>(g) * g + 1;
+  const float* G = tokens + width;  // global image, skip cls row
+  const int crop = 1 + (py / g) * nw + (px / g);
+  const float* C = tokens + (crop * tstride + 1 + (py % g) * g + (px % g)) * width;
+  for (int d = threadIdx.x; d < width; d += blockDim.x) {
+    const float top = G[(static_cast<size_t>(y0) * g + x0) * width + d] * (1.f - lx) + G[(static_cast<size_t>(y0) * g + x1) * width + d] * lx;
+    const float bot = G[(static_cast<size_t>(y1) * g + x0) * width + d] * (1.f - lx) + G[(static_cast<size_t>(y1) * g + x1) * width + d] * lx;
+    const float up = top * (1.f - ly) + bot * ly;
+    canvas[static_cast<size_t>(p) * width + d] = 0.5f * up + C[d];
+  }
+}
+
+// ------------------------------------------------------------------------------------------- E4 feature masks
+// get_features_mask (textregion.py:145-161) as used at :187 (`<= 0` is padded): a token belongs to the mask
+// iff any bilinear tap with non-zero weight is set.
+__global__ void feature_mask_kernel(const uint8_t* __restrict__ masks, int M, int H, int W, int ph, int pw,
+                                    uint8_t* __restrict__ fmask, int* __restrict__ cnt) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  const int m = blockIdx.y;
+  if (p >= ph * pw) return;
+  const int py = p / pw, px = p - py * pw;
+  const float sy = fmaxf((static_cast<float>(H) / ph) * (py + 0.5f) - 0.5f, 0.f);
+  const float sx = fmaxf((static_cast<float>(W) / pw) * (px + 0.5f) - 0.5f, 0.f);
+  const int y0 = min(static_cast<int>(sy), H - 1), x0 = min(static_cast<int>(sx), W - 1);
+  const int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
+  const float ly = sy - y0, lx = sx - x0;
+  const uint8_t* mk = masks + static_cast<size_t>(m) * H * W;
+  bool on = false;
+  if ((1.f - ly) > 0.f && (1.f - lx) > 0.f) on |= mk[static_cast<size_t>(y0) * W + x0] != 0;
+  if ((1.f - ly) > 0.f && lx > 0.f) on |= mk[static_cast<size_t>(y0) * W + x1] != 0;
+  if (ly > 0.f && (1.f - lx) > 0.f) on |= mk[static_cast<size_t>(y1) * W + x0] != 0;
+  if (ly > 0.f && lx > 0.f) on |= mk[static_cast<size_t>(y1) * W + x1] != 0;
+  fmask[static_cast<size_t>(m) * ph * pw + p] = on ? 1 : 0;
+  if (on) atomicAdd(&cnt[m], 1);
+}
+
+// ------------------------------------------------------------------------------------------- E5 masked mean
+// mean[m] = sum_{p in mask m} canvas[p] / cnt[m]  (uniform softmax of textregion.py:183-189);
+// 8 masks per block share each canvas read.  0/0 -> NaN like the reference's all-padded attention.
+constexpr int kMeanMasks = 8;
+__global__ void __launch_bounds__(256)
+    masked_mean_kernel(const float* __restrict__ canvas, int P, int width, const uint8_t* __restrict__ fmask,
+                       const int* __restrict__ cnt, int M, __nv_bfloat16* __restrict__ mean) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  const int m0 = blockIdx.y * kMeanMasks;
+  __shared__ uint8_t s_f[kMeanMasks][64];
+  float acc[kMeanMasks];
+#pragma unroll
+  for (int i = 0; i < kMeanMasks; ++i) acc[i] = 0.f;
+  for (int p0 = 0; p0 < P; p0 += 64) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < kMeanMasks * 64; i += blockDim.x) {
+      const int mi = i >> 6, pi = i & 63;
+      s_f[mi][pi] = (m0 + mi < M && p0 + pi < P) ? fmask[static_cast<size_t>(m0 + mi) * P + p0 + pi] : 0;
+    }
+    __syncthreads();
+    if (d < width) {
+      const int pe = min(64, P - p0);
+      for (int pi = 0; pi < pe; ++pi) {
+        const float c = canvas[static_cast<size_t>(p0 + pi) * width + d];
+#pragma unroll
+        for (int i = 0; i < kMeanMasks; ++i)
+          if (s_f[i][pi]) acc[i] += c;
+      }
+    }
+  }
+  if (d < width) {
+#pragma unroll
+    for (int i = 0; i < kMeanMasks; ++i)
+      if (m0 + i < M) mean[static_cast<size_t>(m0 + i) * width + d] = __float2bfloat16_rn(acc[i] / static_cast<float>(cnt[m0 + i]));
+  }
+}
+
+// F.normalize(dim=-1) (textregion.py:194): one warp per row
+__global__ void l2_normalize_kernel(float* __restrict__ x, int rows, int dim) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float* r = x + static_cast<size_t>(row) * dim;
+  float ss = 0.f;
+  for (int d = lane; d < dim; d += 32) ss += r[d] * r[d];
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+  for (int d = lane; d < dim; d += 32) r[d] *= inv;
+}
+
+// ------------------------------------------------------------------------------------------- text tower
+// x[t*ctx+s] = token_embedding[tok] + positional_embedding[s] (pe.py:672-680); eot[t] = t*ctx + argmax_s tok
+__global__ void text_embed_kernel(const int32_t* __restrict__ tokens, int T, int ctx, int width,
+                                  const float* __restrict__ emb, const float* __restrict__ pos, float* __restrict__ x,
+                                  int* __restrict__ eot_rows) {
+  const int row = blockIdx.x;  // t*ctx + s
+  const int t = row / ctx, s = row - t * ctx;
+  const int tok = tokens[row];
+  for (int d = threadIdx.x; d < width; d += blockDim.x)
+    x[static_cast<size_t>(row) * width + d] = emb[static_cast<size_t>(tok) * width + d] + pos[static_cast<size_t>(s) * width + d];
+  if (s == 0 && threadIdx.x == 0) {
+    int best = tokens[row], bi = 0;
+    for (int i = 1; i < ctx; ++i)
+      if (tokens[row + i] > best) { best = tokens[row + i]; bi = i; }
+    eot_rows[t] = t * ctx + bi;
+  }
+}
+
+}  // namespace ovo
+
+// =============================================================================================== handle
+using namespace ovo;
+
+struct AaTable {
+  int offset;  // entry offset into the device tables
+  int k;       // taps per row
+};
+
+struct ovo_encoder {
+  ovo_vit_cfg cfg{};
+  ovo_vit_weights w{};
+  std::vector<ovo_block_weights> blocks, text_blocks;
+  int max_images = 0, max_h = 0, max_w = 0, max_masks = 0;
+  int grid = 0, patches = 0, seq = 0, seq_pad = 0;
+  size_t rows_cap = 0;  // activation rows
+  // activations
+  __nv_bfloat16 *patch_buf = nullptr, *xn = nullptr, *q = nullptr, *k = nullptr, *vt = nullptr, *attn = nullptr,
+                *hmid = nullptr, *mean = nullptr, *pooled_in = nullptr;
+  float *x = nullptr, *xfinal = nullptr, *rope_cos = nullptr, *rope_sin = nullptr, *canvas = nullptr,
+        *resize_tmp = nullptr;
+  uint8_t* fmask = nullptr;
+  int *fcnt = nullptr, *eot_rows = nullptr;
+  // AA resize tables
+  int *tab_min = nullptr, *tab_size = nullptr;
+  float* tab_w = nullptr;
+  int tab_entries = 0, tab_cap = 0, tab_wcap = 0, tab_wused = 0;
+  std::map<std::pair<int, int>, AaTable> tables;
+  ImgJob* jobs_dev = nullptr;
+  int jobs_cap = 0;
+  int loaded_images = 0;
+  // CUDA graphs of the transformer stack, keyed by (n_img, n_layers, ln_post)
+  struct GraphEntry { cudaGraphExec_t exec = nullptr; long long launches = 0; int warm = 0; };
+  std::map<long long, GraphEntry> graphs;
+  bool use_graphs = true;
+};
+
+namespace {
+
+template <typename T>
+int dmalloc(T** p, size_t n) {
+  if (cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(T)) != cudaSuccess) {
+    cudaGetLastError();
+    return set_error(OVO_E_NOMEM, "encoder workspace allocation of %zu bytes failed", n * sizeof(T));
+  }
+  if (cudaMemset(*p, 0, n * sizeof(T)) != cudaSuccess) return set_error(OVO_E_CUDA, "memset failed");
+  return OVO_OK;
+}
+
+int launch_ln(const float* x, int rows, int width, const float* g, const float* b, float eps, __nv_bfloat16* o16,
+              float* o32, const int* gather, cudaStream_t s) {
+  OVO_REQUIRE(width % 4 == 0 && width <= 32 * 4 * 16, "layernorm: unsupported width %d", width);
+  const int blocks = ceil_div(rows, 8);
+  if (width <= 1024)
+    layernorm_kernel<8><<<blocks, 256, 0, s>>>(x, rows, width, g, b, eps, o16, o32, gather);
+  else
+    layernorm_kernel<16><<<blocks, 256, 0, s>>>(x, rows, width, g, b, eps, o16, o32, gather);
+  OVO_CHECK_LAUNCH();
+  return OVO_OK;
+}
+
+int launch_attention(ovo_encoder* e, int n_seq, int seq, int seq_pad, int heads, int width, bool causal, cudaStream_t s) {
+  OVO_REQUIRE(seq_pad % 128 == 0 && seq_pad / 128 <= kAttnMaxBlocks, "attention: seq_pad %d unsupported", seq_pad);
+  CUtensorMap tq, tk, tv;
+  const uint64_t bh = static_cast<uint64_t>(n_seq) * heads;
+  OVO_TRY(make_tmap_bf16_2d(&tq, e->q, bh * seq_pad, 64, 64, 128, 64));
+  OVO_TRY(make_tmap_bf16_2d(&tk, e->k, bh * seq_pad, 64, 64, 128, 64));
+  OVO_TRY(make_tmap_bf16_2d(&tv, e->vt, bh * 64, seq_pad, seq_pad, 64, 64));
+  const int nblk = seq_pad / 128;
+  const int smem = AttnSmem::bytes(nblk);
+  static int attr_smem = 0;
+  if (smem > attr_smem) {
+    OVO_CUDA(cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_smem = smem;
+  }
+  const int qtiles = ceil_div(seq, 128);
+  const float scale_log2e = 0.125f * 1.4426950408889634f;  // head_dim 64
+  attention_fwd_kernel<<<dim3(qtiles, static_cast<unsigned>(bh)), kAttnThreads, smem, s>>>(
+      tq, tk, tv, e->attn, seq, seq_pad, heads, width, scale_log2e, causal ? 1 : 0);
+  OVO_CHECK_LAUNCH();
+  return OVO_OK;
+}
+
+// pe.py:216-225 for `n_layers` blocks over rows = n_seq * seq
+int run_blocks(ovo_encoder* e, const std::vector<ovo_block_weights>& blocks, int n_layers, int n_seq, int seq,
+               int seq_pad, int heads, int width, int mlp, bool rope, bool causal, cudaStream_t s) {
+  const int rows = n_seq * seq;
+  for (int l = 0; l < n_layers; ++l) {
+    const ovo_block_weights& b = blocks[l];
+    OVO_TRY(launch_ln(e->x, rows, width, b.ln1_w, b.ln1_b, e->cfg.ln_eps, e->xn, nullptr, nullptr, s));
+    EpiParams qkv;
+    qkv.bias = b.qkv_b; qkv.q = e->q; qkv.k = e->k; qkv.vt = e->vt;
+    qkv.rope_cos = rope ? e->rope_cos : nullptr; qkv.rope_sin = rope ? e->rope_sin : nullptr;
+    qkv.seq = seq; qkv.seq_pad = seq_pad; qkv.heads = heads; qkv.width = width;
+    OVO_TRY(launch_gemm(EPI_QKV, e->xn, width, static_cast<const __nv_bfloat16*>(b.qkv_w), width, rows, 3 * width, width, qkv, s));
+    OVO_TRY(launch_attention(e, n_seq, seq, seq_pad, heads, width, causal, s));
+    EpiParams op;
+    op.out = e->x; op.ldo = width; op.bias = b.out_b; op.resid = e->x; op.ldr = width;
+    OVO_TRY(launch_gemm(EPI_F32_RESID, e->attn, width, static_cast<const __nv_bfloat16*>(b.out_w), width, rows, width, width, op, s));
+    OVO_TRY(launch_ln(e->x, rows, width, b.ln2_w, b.ln2_b, e->cfg.ln_eps, e->xn, nullptr, nullptr, s));
+    EpiParams fc;
+    fc.out = e->hmid; fc.ldo = mlp; fc.bias = b.fc_b;
+    OVO_TRY(launch_gemm(EPI_BF16_GELU, e->xn, width, static_cast<const __nv_bfloat16*>(b.fc_w), width, rows, mlp, width, fc, s));
+    EpiParams pj;
+    pj.out = e->x; pj.ldo = width; pj.bias = b.proj_b; pj.resid = e->x; pj.ldr = width;
+    OVO_TRY(launch_gemm(EPI_F32_RESID, e->hmid, mlp, static_cast<const __nv_bfloat16*>(b.proj_w), mlp, rows, width, mlp, pj, s));
+  }
+  return OVO_OK;
+}
+
+// ATen _upsample_bilinear2d_aa weights for one axis: returns taps per output
+int aa_axis(int n_in, int n_out, std::vector<int>& mins, std::vector<int>& sizes, std::vector<float>& ws) {
+  const double scale = static_cast<double>(n_in) / n_out;
+  const double support = std::max(scale, 1.0), inv = 1.0 / std::max(scale, 1.0);
+  const int kmax = static_cast<int>(std::ceil(support)) * 2 + 1;
+  mins.resize(n_out); sizes.resize(n_out); ws.assign(static_cast<size_t>(n_out) * kmax, 0.f);
+  for (int i = 0; i < n_out; ++i) {
+    const double center = scale * (i + 0.5);
+    const int lo = std::max(0, static_cast<int>(center - support + 0.5));
+    const int hi = std::min(n_in, static_cast<int>(center + support + 0.5));
+    double total = 0;
+    std::vector<double> t(hi - lo);
+    for (int j = lo; j < hi; ++j) {
+      t[j - lo] = std::max(0.0, 1.0 - std::fabs((j - center + 0.5) * inv));
+      total += t[j - lo];
+    }
+    mins[i] = lo; sizes[i] = hi - lo;
+    for (int j = 0; j < hi - lo; ++j) ws[static_cast<size_t>(i) * kmax + j] = static_cast<float>(t[j] / total);
+  }
+  return kmax;
+}
+
+int get_table(ovo_encoder* e, int n_in, AaTable* out, cudaStream_t s) {
+  const int S = e->cfg.image_size;
+  auto it = e->tables.find({n_in, S});
+  if (it != e->tables.end()) { *out = it->second; return OVO_OK; }
+  std::vector<int> mins, sizes; std::vector<float> ws;
+  const int k = aa_axis(n_in, S, mins, sizes, ws);
+  OVO_REQUIRE(e->tab_entries + S <= e->tab_cap && e->tab_wused + S * k <= e->tab_wcap, "resize table space exhausted");
+  // the weight table of this axis starts at tab_wused; kernels index it as (offset_entries + o) * k, so keep
+  // the entry offset consistent by giving each table its own weight base = entry_offset * k.
+  const int entry_off = ceil_div(e->tab_wused, k) > e->tab_entries ? ceil_div(e->tab_wused, k) : e->tab_entries;
+  OVO_REQUIRE(entry_off + S <= e->tab_cap && static_cast<size_t>(entry_off + S) * k <= static_cast<size_t>(e->tab_wcap), "resize table space exhausted");
+  OVO_CUDA(cudaMemcpyAsync(e->tab_min + entry_off, mins.data(), S * sizeof(int), cudaMemcpyHostToDevice, s));
+  OVO_CUDA(cudaMemcpyAsync(e->tab_size + entry_off, sizes.data(), S * sizeof(int), cudaMemcpyHostToDevice, s));
+  OVO_CUDA(cudaMemcpyAsync(e->tab_w + static_cast<size_t>(entry_off) * k, ws.data(), static_cast<size_t>(S) * k * sizeof(float), cudaMemcpyHostToDevice, s));
+  OVO_CUDA(cudaStreamSynchronize(s));  // host vectors go out of scope; tables are built once per size
+  e->tab_entries = entry_off + S;
+  e->tab_wused = (entry_off + S) * k;
+  AaTable t{entry_off, k};
+  e->tables[{n_in, S}] = t;
+  *out = t;
+  return OVO_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ovo_encoder_create(const ovo_vit_cfg* cfg, const ovo_vit_weights* w, int max_images, int max_h, int max_w,
+                       int max_masks, ovo_encoder_t** out) {
+  OVO_REQUIRE(cfg && w && out, "ovo_encoder_create: null argument");
+  OVO_REQUIRE(cfg->width % 64 == 0 && cfg->heads > 0 && cfg->width / cfg->heads == 64, "head_dim must be 64 (width %d, heads %d)", cfg->width, cfg->heads);
+  OVO_REQUIRE(cfg->image_size % cfg->patch_size == 0, "image_size must be a multiple of patch_size");
+  OVO_REQUIRE(max_images > 0 && max_masks > 0 && max_h > 0 && max_w > 0, "ovo_encoder_create: bad limits");
+  OVO_REQUIRE(w->patch_kpad % 64 == 0 && w->patch_kpad >= 3 * cfg->patch_size * cfg->patch_size, "patch_kpad must be a multiple of 64");
+  if (cfg->text_layers > 0)
+    OVO_REQUIRE(cfg->text_heads > 0 && cfg->text_width / cfg->text_heads == 64 && cfg->text_ctx <= 128 && w->text_blocks,
+                "text tower: head_dim must be 64 and ctx <= 128");
+  OVO_REQUIRE(ovo::ceil_div(cfg->image_size / cfg->patch_size * (cfg->image_size / cfg->patch_size) + 1, 128) <= kAttnMaxBlocks,
+              "sequence too long for the attention kernel");
+  ovo_encoder* e = new ovo_encoder();
+  e->cfg = *cfg; e->w = *w;
+  e->blocks.assign(w->blocks, w->blocks + cfg->layers);
+  if (cfg->text_layers > 0) e->text_blocks.assign(w->text_blocks, w->text_blocks + cfg->text_layers);
+  e->max_images = max_images; e->max_h = max_h; e->max_w = max_w; e->max_masks = max_masks;
+  e->grid = cfg->image_size / cfg->patch_size; e->patches = e->grid * e->grid; e->seq = e->patches + 1;
+  e->seq_pad = ceil_div(e->seq, 128) * 128;
+  const char* env = getenv("OVO_B200_GRAPHS");
+  e->use_graphs = !(env && env[0] == '0');
+
+  const int W = std::max(cfg->width, cfg->text_width), F = std::max(cfg->mlp_width, cfg->text_mlp_width);
+  const int heads = std::max(cfg->heads, cfg->text_heads);
+  const size_t rows = static_cast<size_t>(max_images) * e->seq;   // text strings: up to max_images*seq/ctx
+  e->rows_cap = rows;
+  const size_t rows_pad = rows + 128;
+  const size_t qk_elems = static_cast<size_t>(max_images) * heads * e->seq_pad * 64 * 2;  // x2: text uses seq_pad 128 per string
+  const int nh_max = std::max(max_h / cfg->image_size, 1), nw_max = std::max(max_w / cfg->image_size, 1);
+  const size_t pmax = static_cast<size_t>(nh_max) * nw_max * e->patches;
+  int r = OVO_OK;
+  r |= dmalloc(&e->patch_buf, static_cast<size_t>(max_images) * e->patches * w->patch_kpad + 64);
+  r |= dmalloc(&e->x, rows_pad * W);
+  r |= dmalloc(&e->xfinal, rows_pad * W);
+  r |= dmalloc(&e->xn, rows_pad * W);
+  r |= dmalloc(&e->attn, rows_pad * W);
+  r |= dmalloc(&e->hmid, rows_pad * F);
+  r |= dmalloc(&e->q, qk_elems);
+  r |= dmalloc(&e->k, qk_elems);
+  r |= dmalloc(&e->vt, qk_elems);
+  r |= dmalloc(&e->rope_cos, static_cast<size_t>(e->seq) * 32);
+  r |= dmalloc(&e->rope_sin, static_cast<size_t>(e->seq) * 32);
+  r |= dmalloc(&e->canvas, pmax * cfg->width);
+  r |= dmalloc(&e->fmask, static_cast<size_t>(max_masks) * pmax);
+  r |= dmalloc(&e->fcnt, static_cast<size_t>(max_masks));
+  r |= dmalloc(&e->mean, static_cast<size_t>(max_masks + 128) * cfg->width);
+  r |= dmalloc(&e->resize_tmp, static_cast<size_t>(max_images) * 3 * max_h * cfg->image_size);
+  r |= dmalloc(&e->eot_rows, rows_pad);
+  r |= dmalloc(&e->pooled_in, rows_pad * static_cast<size_t>(W) / 8 + static_cast<size_t>(W) * 128);
+  e->tab_cap = 16 * cfg->image_size; e->tab_wcap = e->tab_cap * 64;
+  r |= dmalloc(&e->tab_min, static_cast<size_t>(e->tab_cap));
+  r |= dmalloc(&e->tab_size, static_cast<size_t>(e->tab_cap));
+  r |= dmalloc(&e->tab_w, static_cast<size_t>(e->tab_wcap));
+  e->jobs_cap = max_images;
+  r |= dmalloc(&e->jobs_dev, static_cast<size_t>(max_images));
+  if (r != OVO_OK) { ovo_encoder_destroy(e); return OVO_E_NOMEM; }
+
+  // 2D RoPE table with a cls token (rope.py:315-340): pairs 0..15 rotate by (x+1)*theta_i,
+  // pairs 16..31 by (y+1)*theta_i, theta_i = 10000^(-2i/32); cls row angle 0.
+  {
+    std::vector<float> c(static_cast<size_t>(e->seq) * 32), s(static_cast<size_t>(e->seq) * 32);
+    for (int t = 0; t < e->seq; ++t)
+      for (int p = 0; p < 32; ++p) {
+        float ang = 0.f;
+        if (t > 0) {
+          const int y = (t - 1) / e->grid, x = (t - 1) % e->grid;
+          const int i = p & 15;
+          const float theta = 1.0f / powf(10000.0f, static_cast<float>(2 * i) / 32.0f);
+          ang = static_cast<float>((p < 16 ? x : y) + 1) * theta;
+        }
+        c[static_cast<size_t>(t) * 32 + p] = cosf(ang);
+        s[static_cast<size_t>(t) * 32 + p] = sinf(ang);
+      }
+    if (cudaMemcpy(e->rope_cos, c.data(), c.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(e->rope_sin, s.data(), s.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
+      ovo_encoder_destroy(e);
+      return set_error(OVO_E_CUDA, "rope table upload failed");
+    }
+  }
+  *out = e;
+  return OVO_OK;
+}
+
+void ovo_encoder_destroy(ovo_encoder_t* e) {
+  if (!e) return;
+  for (auto& g : e->graphs) if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
+  cudaFree(e->patch_buf); cudaFree(e->x); cudaFree(e->xfinal); cudaFree(e->xn); cudaFree(e->attn); cudaFree(e->hmid);
+  cudaFree(e->q); cudaFree(e->k); cudaFree(e->vt); cudaFree(e->rope_cos); cudaFree(e->rope_sin); cudaFree(e->canvas);
+  cudaFree(e->fmask); cudaFree(e->fcnt); cudaFree(e->mean); cudaFree(e->resize_tmp); cudaFree(e->eot_rows);
+  cudaFree(e->pooled_in); cudaFree(e->tab_min); cudaFree(e->tab_size); cudaFree(e->tab_w); cudaFree(e->jobs_dev);
+  delete e;
+}
+
+int ovo_encoder_preprocess(ovo_encoder_t* e, const uint8_t* rgb_dev, int n_frames, int H, int W, int* n_img_per_frame,
+                           void* stream_) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream_);
+  OVO_REQUIRE(e && rgb_dev && n_frames > 0, "ovo_encoder_preprocess: bad arguments");
+  OVO_REQUIRE(H > 0 && W > 0 && H <= e->max_h && W <= e->max_w, "frame %dx%d exceeds encoder limits %dx%d", H, W, e->max_h, e->max_w);
+  const int S = e->cfg.image_size;
+  // crop boxes of the multi_resolution strategy (textregion.py:114-128)
+  const int nh = std::max(H / S, 1), nw = std::max(W / S, 1);
+  const int ch = ceil_div(H, nh), cw = ceil_div(W, nw);
+  const int per = 1 + nh * nw;
+  OVO_REQUIRE(n_frames * per <= e->max_images, "%d frames x %d images exceed max_images %d", n_frames, per, e->max_images);
+  AaTable tgx, tgy, tcx, tcy;
+  OVO_TRY(get_table(e, W, &tgx, s)); OVO_TRY(get_table(e, H, &tgy, s));
+  OVO_TRY(get_table(e, cw, &tcx, s)); OVO_TRY(get_table(e, ch, &tcy, s));
+  std::vector<ImgJob> jobs;
+  for (int f = 0; f < n_frames; ++f) {
+    jobs.push_back({f, 0, 0, H, W, tgx.offset, tgy.offset, tgx.k, tgy.k});
+    for (int hi = 0; hi < nh; ++hi)
+      for (int wi = 0; wi < nw; ++wi) {
+        int y1 = hi * ch, x1 = wi * cw;
+        const int y2 = std::min(y1 + ch, H), x2 = std::min(x1 + cw, W);
+        y1 = std::max(y2 - ch, 0); x1 = std::max(x2 - cw, 0);
+        jobs.push_back({f, y1, x1, y2 - y1, x2 - x1, tcx.offset, tcy.offset, tcx.k, tcy.k});
+      }
+  }
+  const int n_img = static_cast<int>(jobs.size());
+  OVO_CUDA(cudaMemcpyAsync(e->jobs_dev, jobs.data(), jobs.size() * sizeof(ImgJob), cudaMemcpyHostToDevice, s));
+  OVO_CUDA(cudaStreamSynchronize(s));  // jobs is a host temporary
+  aa_resize_h_kernel<<<dim3(ceil_div(S, 128), H, n_img), 128, 0, s>>>(rgb_dev, H, W, e->jobs_dev, e->tab_min, e->tab_size, e->tab_w, S, e->resize_tmp, e->max_h);
+  OVO_CHECK_LAUNCH();
+  aa_resize_v_patch_kernel<<<dim3(ceil_div(S, 128), S, n_img), 128, 0, s>>>(e->resize_tmp, e->max_h, e->jobs_dev, e->tab_min, e->tab_size, e->tab_w, S, e->cfg.patch_size, e->w.patch_kpad, e->patch_buf);
+  OVO_CHECK_LAUNCH();
+  e->loaded_images = n_img;
+  if (n_img_per_frame) *n_img_per_frame = per;
+  return OVO_OK;
+}
+
+int ovo_encoder_load_pixels(ovo_encoder_t* e, const float* pixels_dev, int n_img, void* stream_) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream_);
+  OVO_REQUIRE(e && pixels_dev && n_img > 0 && n_img <= e->max_images, "ovo_encoder_load_pixels: bad arguments");
+  const int S = e->cfg.image_size;
+  const size_t total = static_cast<size_t>(n_img) * 3 * S * S;
+  pixels_to_patches_kernel<<<ceil_div(total, 256), 256, 0, s>>>(pixels_dev, n_img, S, e->cfg.patch_size, e->w.patch_kpad, e->patch_buf);
+  OVO_CHECK_LAUNCH();
+  e->loaded_images = n_img;
+  return OVO_OK;
+}
+
+static int forward_eager(ovo_encoder* e, int n_img, int n_layers, int apply_ln_post, cudaStream_t s) {
+  const ovo_vit_cfg& c = e->cfg;
+  const int rows = n_img * e->seq;
+  // patch embed (pe.py:509-519) + cls row, then ln_pre (pe.py:524)
+  EpiParams pe;
+  pe.out = e->x; pe.ldo = c.width; pe.pos = e->w.pos; pe.patches = e->patches;
+  OVO_TRY(launch_gemm(EPI_PATCH, e->patch_buf, e->w.patch_kpad, static_cast<const __nv_bfloat16*>(e->w.patch_w), e->w.patch_kpad,
+                      n_img * e->patches, c.width, e->w.patch_kpad, pe, s));
+  cls_rows_kernel<<<ceil_div(n_img * c.width, 256), 256, 0, s>>>(e->x, n_img, e->seq, c.width, e->w.cls_pos0);
+  OVO_CHECK_LAUNCH();
+  OVO_TRY(launch_ln(e->x, rows, c.width, e->w.ln_pre_w, e->w.ln_pre_b, c.ln_eps, nullptr, e->x, nullptr, s));
+  OVO_TRY(run_blocks(e, e->blocks, n_layers, n_img, e->seq, e->seq_pad, c.heads, c.width, c.mlp_width, true, false, s));
+  if (apply_ln_post) {
+    OVO_TRY(launch_ln(e->x, rows, c.width, e->w.ln_post_w, e->w.ln_post_b, c.ln_eps, nullptr, e->xfinal, nullptr, s));
+  } else {
+    OVO_CUDA(cudaMemcpyAsync(e->xfinal, e->x, static_cast<size_t>(rows) * c.width * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  }
+  return OVO_OK;
+}
+
+int ovo_encoder_forward(ovo_encoder_t* e, int n_img, int n_layers, int apply_ln_post, float* tokens_out_dev, void* stream_) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream_);
+  OVO_REQUIRE(e && n_img > 0 && n_img <= e->max_images, "ovo_encoder_forward: bad n_img %d", n_img);
+  if (n_layers < 0 || n_layers > e->cfg.layers) n_layers = e->cfg.layers;
+  const long long key = (static_cast<long long>(n_img) << 16) | (n_layers << 1) | (apply_ln_post ? 1 : 0);
+  ovo_encoder::GraphEntry& ge = e->graphs[key];
+  if (!e->use_graphs || ge.warm == 0) {
+    // first call per shape runs eagerly (sets kernel attributes, validates), later calls replay a graph
+    OVO_TRY(forward_eager(e, n_img, n_layers, apply_ln_post, s));
+    ge.warm = 1;
+  } else {
+    if (ge.exec == nullptr) {
+      const long long before = ovo_launch_count(0);
+      cudaGraph_t graph = nullptr;
+      OVO_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+      const int r = forward_eager(e, n_img, n_layers, apply_ln_post, s);
+      const cudaError_t ce = cudaStreamEndCapture(s, &graph);
+      if (r != OVO_OK) { if (graph) cudaGraphDestroy(graph); return r; }
+      if (ce != cudaSuccess) return set_error(OVO_E_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
+      const cudaError_t ie = cudaGraphInstantiate(&ge.exec, graph, 0);
+      cudaGraphDestroy(graph);
+      if (ie != cudaSuccess) { ge.exec = nullptr; return set_error(OVO_E_CUDA, "graph instantiate failed: %s", cudaGetErrorString(ie)); }
+      ge.launches = ovo_launch_count(0) - before;
+      count_launch(-static_cast<int>(ge.launches));  // captured, not executed yet
+    }
+    OVO_CUDA(cudaGraphLaunch(ge.exec, s));
+    count_launch(static_cast<int>(ge.launches));
+  }
+  if (tokens_out_dev)
+    OVO_CUDA(cudaMemcpyAsync(tokens_out_dev, e->xfinal, static_cast<size_t>(n_img) * e->seq * e->cfg.width * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  return OVO_OK;
+}
+
+int ovo_encoder_pool_regions(ovo_encoder_t* e, int img0, int H, int W, const uint8_t* masks_dev, int M, float* out_dev,
+                             void* stream_) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream_);
+  OVO_REQUIRE(e && masks_dev && out_dev, "ovo_encoder_pool_regions: null argument");
+  OVO_REQUIRE(M > 0 && M <= e->max_masks, "ovo_encoder_pool_regions: M=%d outside (0, %d]", M, e->max_masks);
+  const ovo_vit_cfg& c = e->cfg;
+  const int S = c.image_size, g = e->grid;
+  const int nh = std::max(H / S, 1), nw = std::max(W / S, 1);
+  OVO_REQUIRE(H <= e->max_h && W <= e->max_w && img0 >= 0 && img0 + 1 + nh * nw <= e->max_images, "ovo_encoder_pool_regions: frame out of range");
+  const int ph = nh * g, pw = nw * g, P = ph * pw;
+  const float* tokens = e->xfinal + static_cast<size_t>(img0) * e->seq * c.width;
+  token_canvas_kernel<<<P, 256, 0, s>>>(tokens, g, c.width, nh, nw, e->canvas);
+  OVO_CHECK_LAUNCH();
+  OVO_CUDA(cudaMemsetAsync(e->fcnt, 0, M * sizeof(int), s));
+  feature_mask_kernel<<<dim3(ceil_div(P, 128), M), 128, 0, s>>>(masks_dev, M, H, W, ph, pw, e->fmask, e->fcnt);
+  OVO_CHECK_LAUNCH();
+  masked_mean_kernel<<<dim3(ceil_div(c.width, 256), ceil_div(M, kMeanMasks)), 256, 0, s>>>(e->canvas, P, c.width, e->fmask, e->fcnt, M, e->mean);
+  OVO_CHECK_LAUNCH();
+  EpiParams ep;
+  ep.out = out_dev; ep.ldo = c.output_dim; ep.bias = e->w.pool_b;
+  OVO_TRY(launch_gemm(EPI_F32, e->mean, c.width, static_cast<const __nv_bfloat16*>(e->w.pool_w), c.width, M, c.output_dim, c.width, ep, s));
+  l2_normalize_kernel<<<ceil_div(M, 8), 256, 0, s>>>(out_dev, M, c.output_dim);
+  OVO_CHECK_LAUNCH();
+  return OVO_OK;
+}
+
+int ovo_encode_regions(ovo_encoder_t* e, const uint8_t* rgb_dev, int n_frames, int H, int W, const uint8_t* masks_dev,
+                       const int* masks_per_frame_host, float* out_dev, void* stream) {
+  OVO_REQUIRE(e && masks_per_frame_host, "ovo_encode_regions: null argument");
+  int per = 0;
+  OVO_TRY(ovo_encoder_preprocess(e, rgb_dev, n_frames, H, W, &per, stream));
+  OVO_TRY(ovo_encoder_forward(e, n_frames * per, -1, 1, nullptr, stream));
+  size_t moff = 0;
+  for (int f = 0; f < n_frames; ++f) {
+    const int M = masks_per_frame_host[f];
+    if (M > 0)
+      OVO_TRY(ovo_encoder_pool_regions(e, f * per, H, W, masks_dev + moff * H * W, M, out_dev + moff * e->cfg.output_dim, stream));
+    moff += M;
+  }
+  return OVO_OK;
+}
+
+int ovo_encode_text(ovo_encoder_t* e, const int32_t* tokens_dev, int T, float* out_dev, void* stream_) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream_);
+  OVO_REQUIRE(e && tokens_dev && out_dev && T > 0, "ovo_encode_text: bad arguments");
+  const ovo_vit_cfg& c = e->cfg;
+  OVO_REQUIRE(c.text_layers > 0, "encoder was created without a text tower");
+  const int ctx = c.text_ctx, W = c.text_width;
+  OVO_REQUIRE(static_cast<size_t>(T) * ctx <= e->rows_cap && static_cast<size_t>(T) * 128 <= static_cast<size_t>(e->max_images) * e->seq_pad * 2,
+              "ovo_encode_text: %d strings exceed the encoder workspace", T);
+  text_embed_kernel<<<T * ctx, 256, 0, s>>>(tokens_dev, T, ctx, W, e->w.tok_emb, e->w.text_pos, e->x, e->eot_rows);
+  OVO_CHECK_LAUNCH();
+  OVO_TRY(run_blocks(e, e->text_blocks, c.text_layers, T, ctx, 128, c.text_heads, W, c.text_mlp_width, false, true, s));
+  // ln_final on the EOT rows only (LayerNorm is row-wise), then @ text_projection (pe.py:684-693)
+  OVO_TRY(launch_ln(e->x, T, W, e->w.ln_final_w, e->w.ln_final_b, c.ln_eps, e->pooled_in, nullptr, e->eot_rows, s));
+  EpiParams ep;
+  ep.out = out_dev; ep.ldo = c.text_output_dim;
+  OVO_TRY(launch_gemm(EPI_F32, e->pooled_in, W, static_cast<const __nv_bfloat16*>(e->w.text_proj_w), W, T, c.text_output_dim, W, ep, s));
+  return OVO_OK;
+}
+
+}  // extern "C"

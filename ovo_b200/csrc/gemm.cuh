@@ -1,0 +1,277 @@
+// Persistent, warp-specialised bf16 GEMM for sm_100a:  C[M,N] = A[M,K] . B[N,K]^T  (+ fused epilogue)
+//   warp 0      : TMA producer (cp.async.bulk.tensor, 128B-swizzled 128x64 / BNx64 tiles, mbarrier ring)
+//   warp 1      : tcgen05.mma issuer (one elected thread), accumulators double-buffered in TMEM
+//   warps 2..5  : epilogue (tcgen05.ld 32x32b -> registers -> fused epilogue -> global)
+// Both operands are K-major (row-major with K contiguous), which is how activations [tokens, width]
+// and nn.Linear weights [out, in] already sit in memory, so no transposes are ever materialised.
+//
+// Used for every linear layer of the ViT / text tower (reference pe.py:125,150,190-198,509), the region
+// projection (textregion.py:183-195) and the dense text-vs-map cosine query (clip_utils.py:16-19).
+#pragma once
+#include "ptx.cuh"
+
+namespace ovo {
+
+enum EpiKind : int {
+  EPI_F32 = 0,        // out_f32 = acc (+bias)
+  EPI_BF16 = 1,       // out_bf16 = acc (+bias)
+  EPI_BF16_GELU = 2,  // out_bf16 = gelu(acc + bias)            (pe.py:190-198)
+  EPI_F32_RESID = 3,  // out_f32 = acc + bias + resid            (pe.py:221-224)
+  EPI_QKV = 4,        // split q/k/v, 2D-RoPE on q,k, v written transposed (pe.py:125-143, rope.py:40-62)
+  EPI_PATCH = 5,      // out_f32[token row] = acc + pos_emb      (pe.py:509-519)
+};
+
+struct EpiParams {
+  void* out = nullptr;
+  int ldo = 0;
+  const float* bias = nullptr;
+  const float* resid = nullptr;
+  int ldr = 0;
+  // EPI_QKV
+  __nv_bfloat16* q = nullptr;
+  __nv_bfloat16* k = nullptr;
+  __nv_bfloat16* vt = nullptr;
+  const float* rope_cos = nullptr;  // [seq, head_dim/2] or nullptr (text tower: no RoPE)
+  const float* rope_sin = nullptr;
+  int seq = 0, seq_pad = 0, heads = 0, width = 0;
+  // EPI_PATCH
+  const float* pos = nullptr;  // [1 + patches, width]
+  int patches = 0;             // patches per image (576)
+};
+
+constexpr int kBM = 128;
+constexpr int kBK = 64;
+constexpr int kGemmThreads = 192;
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int kStages = BN >= 256 ? 4 : (BN >= 128 ? 6 : 8);
+  static constexpr int kBytesA = kBM * kBK * 2;
+  static constexpr int kBytesB = BN * kBK * 2;
+  static constexpr int kStageBytes = kBytesA + kBytesB;
+  static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+
+// One thread owns `row` and 32 consecutive accumulator columns starting at `col`.
+template <int EPI>
+__device__ __forceinline__ void epilogue_store(const EpiParams& ep, int row, int col, const uint32_t (&v)[32], int M,
+                                               int N) {
+  if (row >= M || col >= N) return;
+  const int ncol = min(32, N - col);
+  float acc[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(v[j]);
+  if (ep.bias != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j < ncol) acc[j] += __ldg(ep.bias + col + j);
+  }
+
+  if constexpr (EPI == EPI_F32 || EPI == EPI_F32_RESID) {
+    float* out = static_cast<float*>(ep.out) + static_cast<size_t>(row) * ep.ldo + col;
+    if constexpr (EPI == EPI_F32_RESID) {
+      const float* r = ep.resid + static_cast<size_t>(row) * ep.ldr + col;
+      if (ncol == 32 && (ep.ldr & 3) == 0) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float4 t = *reinterpret_cast<const float4*>(r + j);
+          acc[j] += t.x; acc[j + 1] += t.y; acc[j + 2] += t.z; acc[j + 3] += t.w;
+        }
+      } else {
+        for (int j = 0; j < ncol; ++j) acc[j] += r[j];
+      }
+    }
+    if (ncol == 32 && (ep.ldo & 3) == 0) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4)
+        *reinterpret_cast<float4*>(out + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+    } else {
+      for (int j = 0; j < ncol; ++j) out[j] = acc[j];
+    }
+  } else if constexpr (EPI == EPI_BF16 || EPI == EPI_BF16_GELU) {
+    if constexpr (EPI == EPI_BF16_GELU) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) acc[j] = gelu_erf(acc[j]);
+    }
+    __nv_bfloat16* out = static_cast<__nv_bfloat16*>(ep.out) + static_cast<size_t>(row) * ep.ldo + col;
+    if (ncol == 32 && (ep.ldo & 7) == 0) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        uint4 t;
+        t.x = pack_bf16(acc[j], acc[j + 1]); t.y = pack_bf16(acc[j + 2], acc[j + 3]);
+        t.z = pack_bf16(acc[j + 4], acc[j + 5]); t.w = pack_bf16(acc[j + 6], acc[j + 7]);
+        *reinterpret_cast<uint4*>(out + j) = t;
+      }
+    } else {
+      for (int j = 0; j < ncol; ++j) out[j] = __float2bfloat16_rn(acc[j]);
+    }
+  } else if constexpr (EPI == EPI_QKV) {
+    // column layout of in_proj: [q | k | v], each `width` wide, heads of 64 (pe.py:128-140)
+    const int which = col / ep.width;
+    const int within = col - which * ep.width;
+    const int head = within >> 6;
+    const int d0 = within & 63;  // 0 or 32
+    const int b = row / ep.seq;
+    const int t = row - b * ep.seq;
+    const size_t bh = static_cast<size_t>(b) * ep.heads + head;
+    if (which < 2) {
+      if (ep.rope_cos != nullptr) {
+        // interleaved pairs (2i, 2i+1); pair index p = (d0 + j) / 2 (rope.py:32-37,57)
+        const float* c = ep.rope_cos + static_cast<size_t>(t) * 32 + (d0 >> 1);
+        const float* s = ep.rope_sin + static_cast<size_t>(t) * 32 + (d0 >> 1);
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          const float cs = __ldg(c + (j >> 1)), sn = __ldg(s + (j >> 1));
+          const float a = acc[j], bb = acc[j + 1];
+          acc[j] = a * cs - bb * sn;
+          acc[j + 1] = bb * cs + a * sn;
+        }
+      }
+      __nv_bfloat16* dst = (which == 0 ? ep.q : ep.k) + (bh * ep.seq_pad + t) * 64 + d0;
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        uint4 u;
+        u.x = pack_bf16(acc[j], acc[j + 1]); u.y = pack_bf16(acc[j + 2], acc[j + 3]);
+        u.z = pack_bf16(acc[j + 4], acc[j + 5]); u.w = pack_bf16(acc[j + 6], acc[j + 7]);
+        *reinterpret_cast<uint4*>(dst + j) = u;
+      }
+    } else {
+      // V stored transposed [b, head, d, seq_pad] so that P.V sees a K-major B operand
+      __nv_bfloat16* dst = ep.vt + (bh * 64 + d0) * ep.seq_pad + t;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) dst[static_cast<size_t>(j) * ep.seq_pad] = __float2bfloat16_rn(acc[j]);
+    }
+  } else if constexpr (EPI == EPI_PATCH) {
+    const int b = row / ep.patches;
+    const int p = row - b * ep.patches;
+    const size_t orow = static_cast<size_t>(b) * (ep.patches + 1) + 1 + p;
+    float* out = static_cast<float*>(ep.out) + orow * ep.ldo + col;
+    const float* pos = ep.pos + static_cast<size_t>(1 + p) * ep.ldo + col;
+    for (int j = 0; j < ncol; ++j) out[j] = acc[j] + __ldg(pos + j);
+  }
+}
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+    gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N,
+                        int K, EpiParams ep) {
+  using Cfg = GemmCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + Cfg::kStages * Cfg::kBytesA;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + Cfg::kStages;
+  uint64_t* tmem_full = bars + 2 * Cfg::kStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int tiles_m = (M + kBM - 1) / kBM;
+  const int tiles_n = (N + BN - 1) / BN;
+  const int num_tiles = tiles_m * tiles_n;
+  const int num_kb = (K + kBK - 1) / kBK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < Cfg::kStages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0, phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int tm = tile % tiles_m, tn = tile / tiles_m;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
+          tma_load_2d(sA + stage * Cfg::kBytesA, &tmA, &full[stage], kb * kBK, tm * kBM);
+          tma_load_2d(sB + stage * Cfg::kBytesB, &tmB, &full[stage], kb * kBK, tn * BN);
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN);
+      int stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint64_t adesc = umma_desc_sw128(smem_u32(sA + stage * Cfg::kBytesA));
+          const uint64_t bdesc = umma_desc_sw128(smem_u32(sB + stage * Cfg::kBytesB));
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k)  // +32 B per K=16 step inside the 128 B swizzle row
+            umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          umma_commit(&empty[stage]);
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    int acc = 0, acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int tm = tile % tiles_m, tn = tile / tiles_m;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const int row = tm * kBM + quad * 32 + lane;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + c * 32, v);
+        tmem_ld_wait();
+        epilogue_store<EPI>(ep, row, tn * BN + c * 32, v, M, N);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- host
+int make_tmap_bf16_2d(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld_elems,
+                      uint32_t box_rows, uint32_t box_cols);
+int num_sms();
+
+// Launches C = A.B^T with the given epilogue.  lda/ldb in elements (multiples of 8), pointers 16 B aligned.
+int launch_gemm(int epi, const __nv_bfloat16* A, int lda, const __nv_bfloat16* B, int ldb, int M, int N, int K,
+                const EpiParams& ep, cudaStream_t stream, int force_bn = 0);
+
+}  // namespace ovo

@@ -1,0 +1,638 @@
+// 3D association, instance vote, dense/instance fusion and query kernels (HBM-bound streaming passes).
+//
+// Replaces, on device and without per-mask host syncs:
+//   geometry_utils.compute_camera_frustum_corners / compute_frustum_point_ids  (geometry_utils.py:99-129,252-277)
+//   geometry_utils.match_3d_points_to_2d_pixels / project_3d_points           (geometry_utils.py:26-89)
+//   geometry_utils.depth_filter                                               (geometry_utils.py:92-96)
+//   OVO._match_and_track_instances / _track_objects                          (ovo.py:204-229,240-282)
+//   Instance3D avg_pooling fusion                                            (instance3d.py:19-21)
+//   clip_utils.clip_cosine_similarity / OVO.classify_instances               (clip_utils.py:16-19, ovo.py:486-491)
+//
+// Floating point that feeds integer decisions uses __fmul_rn/__fadd_rn/__fdiv_rn in a fixed left-to-right
+// order (no FMA contraction) so the results are bit-identical to oracle/fusion.py.
+#include <vector>
+
+#include "common.cuh"
+#include "gemm.cuh"
+
+namespace ovo {
+
+struct FrameGeom {
+  float lo[3], hi[3];
+  float planes[6][4];
+  int dmin_bits, dmax_bits;  // depth>0 min / max as int bit patterns (positive floats order like ints)
+};
+
+struct FrameDev {
+  float c2w[16], w2c[16], K[9];
+  float match_th;
+  int h, w, H, W;
+  int has_ratio;
+  float ratio_h, ratio_w;
+  int crop_edge;
+};
+
+// ------------------------------------------------------------------------------------------ depth min/max
+__global__ void depth_minmax_kernel(const float* __restrict__ depth, int n, FrameGeom* g) {
+  int lmin = 0x7f800000, lmax = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float d = depth[i];
+    if (d > 0.f) {
+      const int b = __float_as_int(d);
+      lmin = min(lmin, b);
+      lmax = max(lmax, b);
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    lmin = min(lmin, __shfl_xor_sync(0xffffffffu, lmin, o));
+    lmax = max(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMin(&g->dmin_bits, lmin);
+    atomicMax(&g->dmax_bits, lmax);
+  }
+}
+
+__device__ __forceinline__ float dot4_rn(const float* m, float x, float y, float z) {
+  float acc = __fmul_rn(m[0], x);
+  acc = __fadd_rn(acc, __fmul_rn(m[1], y));
+  acc = __fadd_rn(acc, __fmul_rn(m[2], z));
+  return __fadd_rn(acc, m[3]);
+}
+
+// corners (geometry_utils.py:110-129), planes (:163-207), AABB (:210-221); one thread, fixed op order.
+__global__ void frustum_setup_kernel(FrameGeom* g, const FrameDev* f) {
+  const float dmin = __int_as_float(g->dmin_bits), dmax = __int_as_float(g->dmax_bits);
+  const float wf = static_cast<float>(f->w), hf = static_cast<float>(f->h);
+  const float px[8] = {0.f, wf, 0.f, wf, 0.f, wf, 0.f, wf};
+  const float py[8] = {0.f, 0.f, hf, hf, 0.f, 0.f, hf, hf};
+  float c[8][3];
+  for (int i = 0; i < 8; ++i) {
+    const float pz = i < 4 ? dmin : dmax;
+    const float x = __fdiv_rn(__fmul_rn(__fsub_rn(px[i], f->K[2]), pz), f->K[0]);
+    const float y = __fdiv_rn(__fmul_rn(__fsub_rn(py[i], f->K[5]), pz), f->K[4]);
+    for (int r = 0; r < 3; ++r) c[i][r] = dot4_rn(&f->c2w[4 * r], x, y, pz);
+  }
+  for (int r = 0; r < 3; ++r) {
+    float lo = c[0][r], hi = c[0][r];
+    for (int i = 1; i < 8; ++i) {
+      lo = fminf(lo, c[i][r]);
+      hi = fmaxf(hi, c[i][r]);
+    }
+    g->lo[r] = lo;
+    g->hi[r] = hi;
+  }
+  const int pairs[6][4] = {{2, 0, 1, 0}, {6, 4, 5, 4}, {4, 0, 2, 0}, {7, 3, 1, 3}, {5, 1, 3, 1}, {6, 2, 0, 2}};
+  for (int i = 0; i < 6; ++i) {
+    float a[3], b[3];
+    for (int r = 0; r < 3; ++r) {
+      a[r] = __fsub_rn(c[pairs[i][0]][r], c[pairs[i][1]][r]);
+      b[r] = __fsub_rn(c[pairs[i][2]][r], c[pairs[i][3]][r]);
+    }
+    const float n0 = __fsub_rn(__fmul_rn(a[1], b[2]), __fmul_rn(a[2], b[1]));
+    const float n1 = __fsub_rn(__fmul_rn(a[2], b[0]), __fmul_rn(a[0], b[2]));
+    const float n2 = __fsub_rn(__fmul_rn(a[0], b[1]), __fmul_rn(a[1], b[0]));
+    const float d =
+        -__fadd_rn(__fadd_rn(__fmul_rn(n0, c[i][0]), __fmul_rn(n1, c[i][1])), __fmul_rn(n2, c[i][2]));
+    g->planes[i][0] = n0; g->planes[i][1] = n1; g->planes[i][2] = n2; g->planes[i][3] = d;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ depth filter
+// torchvision _get_gaussian_kernel1d(7, 2.5, float32) bit patterns (see oracle/fusion.py)
+__constant__ uint32_t kGauss7Bits[7] = {1035802123u, 1041042090u, 1043549328u, 1044527997u,
+                                        1043549328u, 1041042090u, 1035802123u};
+
+__global__ void depth_filter_kernel(const float* __restrict__ depth, int h, int w, float* __restrict__ out) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= w || y >= h) return;
+  float acc = 0.f;
+#pragma unroll
+  for (int dy = 0; dy < 7; ++dy) {
+    int yy = y + dy - 3;
+    yy = yy < 0 ? -yy : (yy >= h ? 2 * h - 2 - yy : yy);  // reflect (no edge repeat)
+    const float ky = __uint_as_float(kGauss7Bits[dy]);
+#pragma unroll
+    for (int dx = 0; dx < 7; ++dx) {
+      int xx = x + dx - 3;
+      xx = xx < 0 ? -xx : (xx >= w ? 2 * w - 2 - xx : xx);
+      const float k2 = __fmul_rn(ky, __uint_as_float(kGauss7Bits[dx]));
+      acc = __fadd_rn(acc, __fmul_rn(k2, __ldg(depth + static_cast<size_t>(yy) * w + xx)));
+    }
+  }
+  const float d = depth[static_cast<size_t>(y) * w + x];
+  out[static_cast<size_t>(y) * w + x] = fabsf(__fsub_rn(d, acc)) > 0.05f ? -1.f : d;
+}
+
+// ------------------------------------------------------------------------------------------ mask areas
+__global__ void seg_area_kernel(const int32_t* __restrict__ seg, int n, int n_masks, int32_t* __restrict__ area) {
+  extern __shared__ int32_t hist[];
+  for (int i = threadIdx.x; i < n_masks; i += blockDim.x) hist[i] = 0;
+  __syncthreads();
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int s = seg[i];
+    if (s >= 0 && s < n_masks) atomicAdd(&hist[s], 1);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n_masks; i += blockDim.x)
+    if (hist[i]) atomicAdd(&area[i], hist[i]);
+}
+
+// ------------------------------------------------------------------------------------------ pass 1
+// One streaming pass over the map: cull + project + depth test + seg lookup + vote histogram + match list.
+// votes: [n_masks][n_ins + 1] (column 0 = unassigned points, column 1+id = points already carrying id).
+constexpr int kP1Threads = 256;
+
+__global__ void __launch_bounds__(kP1Threads)
+    associate_pass1_kernel(const float* __restrict__ xyz, const int32_t* __restrict__ ins_ids, long long N,
+                           const float* __restrict__ depth, const int32_t* __restrict__ seg_map,
+                           const FrameGeom* __restrict__ geom, const FrameDev* __restrict__ fr, int n_masks,
+                           int n_ins, int32_t* __restrict__ votes, int2* __restrict__ match_list,
+                           int32_t* __restrict__ counters /* [0]=list len, [1]=n_matched */) {
+  __shared__ float s_xyz[kP1Threads * 3];
+  __shared__ FrameGeom s_g;
+  __shared__ FrameDev s_f;
+  if (threadIdx.x < sizeof(FrameGeom) / 4) reinterpret_cast<int*>(&s_g)[threadIdx.x] = reinterpret_cast<const int*>(geom)[threadIdx.x];
+  for (int i = threadIdx.x; i < static_cast<int>(sizeof(FrameDev) / 4); i += blockDim.x)
+    reinterpret_cast<int*>(&s_f)[i] = reinterpret_cast<const int*>(fr)[i];
+  const int lane = threadIdx.x & 31;
+
+  for (long long base = static_cast<long long>(blockIdx.x) * kP1Threads; base < N;
+       base += static_cast<long long>(gridDim.x) * kP1Threads) {
+    __syncthreads();
+    // coalesced, vectorised stage of 256 points (3072 B) through shared memory
+    const long long fbase = base * 3;
+    const long long fend = min(N * 3, fbase + kP1Threads * 3);
+    if (fend - fbase == kP1Threads * 3) {  // fbase*4 is a multiple of 3072 B -> 16 B aligned
+      const float4* src = reinterpret_cast<const float4*>(xyz + fbase);
+      if (threadIdx.x < kP1Threads * 3 / 4) reinterpret_cast<float4*>(s_xyz)[threadIdx.x] = __ldg(src + threadIdx.x);
+    } else {
+      for (int i = threadIdx.x; i < fend - fbase; i += kP1Threads) s_xyz[i] = xyz[fbase + i];
+    }
+    __syncthreads();
+    const long long idx = base + threadIdx.x;
+    bool matched = false;
+    int seg = -1;
+    if (idx < N) {
+      const float x = s_xyz[threadIdx.x * 3], y = s_xyz[threadIdx.x * 3 + 1], z = s_xyz[threadIdx.x * 3 + 2];
+      bool in = x >= s_g.lo[0] && x <= s_g.hi[0] && y >= s_g.lo[1] && y <= s_g.hi[1] && z >= s_g.lo[2] &&
+                z <= s_g.hi[2];
+      if (in) {
+#pragma unroll
+        for (int p = 0; p < 6; ++p) in = in && (dot4_rn(s_g.planes[p], x, y, z) <= 0.f);
+      }
+      if (in) {
+        const float lx = dot4_rn(&s_f.w2c[0], x, y, z), ly = dot4_rn(&s_f.w2c[4], x, y, z);
+        const float lz = dot4_rn(&s_f.w2c[8], x, y, z), lw = dot4_rn(&s_f.w2c[12], x, y, z);
+        const float X = __fdiv_rn(lx, lw), Y = __fdiv_rn(ly, lw), Z = __fdiv_rn(lz, lw);
+        float ph[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+          ph[r] = __fadd_rn(__fadd_rn(__fmul_rn(s_f.K[3 * r], X), __fmul_rn(s_f.K[3 * r + 1], Y)),
+                            __fmul_rn(s_f.K[3 * r + 2], Z));
+        const float uf = rintf(__fdiv_rn(ph[0], ph[2])), vf = rintf(__fdiv_rn(ph[1], ph[2]));
+        if (fabsf(uf) < 2e9f && fabsf(vf) < 2e9f) {  // also rejects NaN/Inf
+          int u = static_cast<int>(uf), v = static_cast<int>(vf);
+          if (u >= 0 && v >= 0 && u < s_f.w && v < s_f.h) {
+            const float d = __ldg(depth + static_cast<size_t>(v) * s_f.w + u);
+            if (fabsf(__fsub_rn(lz, d)) < s_f.match_th && d != 0.f) {
+              matched = true;
+              if (s_f.has_ratio) {  // ovo.py:218-221
+                u += s_f.crop_edge;
+                v += s_f.crop_edge;
+                v = static_cast<int>(__fmul_rn(static_cast<float>(v), s_f.ratio_h));
+                u = static_cast<int>(__fmul_rn(static_cast<float>(u), s_f.ratio_w));
+              }
+              if (u >= 0 && v >= 0 && u < s_f.W && v < s_f.H) seg = __ldg(seg_map + static_cast<size_t>(v) * s_f.W + u);
+              if (seg >= n_masks) seg = -1;
+            }
+          }
+        }
+      }
+    }
+    // bookkeeping, warp aggregated
+    const unsigned m_all = __ballot_sync(0xffffffffu, matched);
+    if (lane == 0 && m_all) atomicAdd(&counters[1], __popc(m_all));
+    const bool listed = matched && seg >= 0;
+    const unsigned m_list = __ballot_sync(0xffffffffu, listed);
+    if (m_list) {
+      int pos = 0;
+      if (lane == 0) pos = atomicAdd(&counters[0], __popc(m_list));
+      pos = __shfl_sync(0xffffffffu, pos, 0);
+      if (listed) {
+        match_list[pos + __popc(m_list & ((1u << lane) - 1))] = make_int2(static_cast<int>(idx), seg);
+        int id = ins_ids[idx];
+        if (id >= n_ins) id = -1;  // ids the host does not know about count as unassigned
+        const int key = seg * (n_ins + 1) + (id + 1);
+        const unsigned peers = __match_any_sync(m_list, key);
+        if (lane == __ffs(peers) - 1) atomicAdd(&votes[key], __popc(peers));
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ vote reduce
+// One block per mask: n_unassigned, n_assigned, mode of assigned ids (ties -> smallest id = torch.mode on CPU).
+__global__ void vote_reduce_kernel(const int32_t* __restrict__ votes, int n_ins, const int32_t* __restrict__ area,
+                                   ovo_vote_row* __restrict__ rows) {
+  const int m = blockIdx.x;
+  const int32_t* row = votes + static_cast<size_t>(m) * (n_ins + 1);
+  int best_cnt = 0, best_id = 0x7fffffff, total = 0;
+  for (int i = threadIdx.x; i < n_ins; i += blockDim.x) {
+    const int c = row[1 + i];
+    total += c;
+    if (c > best_cnt || (c == best_cnt && c > 0 && i < best_id)) {
+      best_cnt = c;
+      best_id = i;
+    }
+  }
+  __shared__ int s_cnt[32], s_id[32], s_tot[32];
+  for (int o = 16; o > 0; o >>= 1) {
+    const int oc = __shfl_xor_sync(0xffffffffu, best_cnt, o), oi = __shfl_xor_sync(0xffffffffu, best_id, o);
+    total += __shfl_xor_sync(0xffffffffu, total, o);
+    if (oc > best_cnt || (oc == best_cnt && oi < best_id)) {
+      best_cnt = oc;
+      best_id = oi;
+    }
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) {
+    s_cnt[warp] = best_cnt; s_id[warp] = best_id; s_tot[warp] = total;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int nw = blockDim.x >> 5;
+    for (int i = 1; i < nw; ++i) {
+      total += s_tot[i];
+      if (s_cnt[i] > best_cnt || (s_cnt[i] == best_cnt && s_id[i] < best_id)) {
+        best_cnt = s_cnt[i];
+        best_id = s_id[i];
+      }
+    }
+    ovo_vote_row r;
+    r.n_unassigned = row[0];
+    r.n_assigned = total;
+    r.n_matched = total + row[0];
+    r.mode_id = best_cnt > 0 ? best_id : -1;
+    r.ins_id = -1;
+    r.is_new = 0;
+    r.area = area[m];
+    r.reserved = 0;
+    rows[m] = r;
+  }
+}
+
+// Sequential over masks (ids are allocated in mask order, ovo.py:255,271-273).
+__global__ void vote_decide_kernel(ovo_vote_row* rows, int n_masks, int track_th, int32_t* mask_ins,
+                                   int32_t* next_ins_id) {
+  int next = *next_ins_id;
+  for (int m = 0; m < n_masks; ++m) {
+    ovo_vote_row r = rows[m];
+    if (r.n_matched > track_th) {
+      if (r.n_assigned > track_th) {
+        r.ins_id = r.mode_id;
+      } else if (r.n_unassigned > track_th) {
+        r.ins_id = next++;
+        r.is_new = 1;
+      }
+    }
+    rows[m] = r;
+    mask_ins[m] = r.ins_id;
+  }
+  *next_ins_id = next;
+}
+
+// ------------------------------------------------------------------------------------------ pass 2
+__global__ void associate_pass2_kernel(const int2* __restrict__ match_list, const int32_t* __restrict__ counters,
+                                       const int32_t* __restrict__ mask_ins, int32_t* __restrict__ ins_ids) {
+  const int n = counters[0];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int2 e = match_list[i];
+    const int id = mask_ins[e.y];
+    if (id >= 0 && ins_ids[e.x] == -1) ins_ids[e.x] = id;  // assigned points never change (ovo.py:274,280)
+  }
+}
+
+// ------------------------------------------------------------------------------------------ dense fusion
+// One warp per matched point: 2 KB bf16 row read-modify-write, 16 B per lane per access.
+__global__ void __launch_bounds__(256)
+    fuse_dense_kernel(const int2* __restrict__ match_list, int n, __nv_bfloat16* __restrict__ bank,
+                      int32_t* __restrict__ counts, int D, const float* __restrict__ feats,
+                      const int32_t* __restrict__ mask_row) {
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  for (int e = blockIdx.x * warps_per_block + (threadIdx.x >> 5); e < n; e += gridDim.x * warps_per_block) {
+    const int2 m = match_list[e];
+    const int r = mask_row[m.y];
+    if (r < 0) continue;
+    const int c = counts[m.x] + 1;
+    __syncwarp();
+    if (lane == 0) counts[m.x] = c;
+    const float cf = static_cast<float>(c);
+    uint4* prow = reinterpret_cast<uint4*>(bank + static_cast<size_t>(m.x) * D);
+    const float4* frow = reinterpret_cast<const float4*>(feats + static_cast<size_t>(r) * D);
+    for (int v = lane; v < D / 8; v += 32) {
+      uint4 raw = prow[v];
+      const float4 e0 = __ldg(frow + 2 * v), e1 = __ldg(frow + 2 * v + 1);
+      const float ev[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+      uint32_t* w = reinterpret_cast<uint32_t*>(&raw);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        __nv_bfloat162 b2 = *reinterpret_cast<__nv_bfloat162*>(&w[j]);
+        float f0 = __bfloat162float(b2.x), f1 = __bfloat162float(b2.y);
+        f0 = __fadd_rn(f0, __fdiv_rn(__fsub_rn(ev[2 * j], f0), cf));
+        f1 = __fadd_rn(f1, __fdiv_rn(__fsub_rn(ev[2 * j + 1], f1), cf));
+        w[j] = pack_bf16(f0, f1);
+      }
+      prow[v] = raw;
+    }
+  }
+}
+
+__global__ void bank_update_mean_kernel(float* __restrict__ bank, int32_t* __restrict__ counts, int D,
+                                        const float* __restrict__ feats, const int32_t* __restrict__ rows, int n) {
+  const int i = blockIdx.x;
+  if (i >= n) return;
+  const int r = rows[i];
+  if (r < 0) return;
+  const int c = counts[r] + 1;
+  __syncthreads();
+  if (threadIdx.x == 0) counts[r] = c;
+  const float cf = static_cast<float>(c);
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    const float b = bank[static_cast<size_t>(r) * D + d];
+    bank[static_cast<size_t>(r) * D + d] = __fadd_rn(b, __fdiv_rn(__fsub_rn(feats[static_cast<size_t>(i) * D + d], b), cf));
+  }
+}
+
+// ------------------------------------------------------------------------------------------ query helpers
+__global__ void f32_to_bf16_pad_kernel(const float* __restrict__ src, int rows, int cols, __nv_bfloat16* __restrict__ dst,
+                                       int rows_pad) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows_pad * cols) return;
+  const int r = i / cols;
+  dst[i] = __float2bfloat16_rn(r < rows ? src[i] : 0.f);
+}
+
+// one warp per (instance, query) dot product in f32, lanes stride the feature dimension
+__global__ void query_instances_kernel(const float* __restrict__ bank, int I, int D, const float* __restrict__ text, int Q,
+                                       float* __restrict__ out) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= I * Q) return;
+  const int i = w / Q, q = w - i * Q;
+  float acc = 0.f;
+  for (int d = lane; d < D; d += 32) acc = fmaf(bank[static_cast<size_t>(i) * D + d], text[static_cast<size_t>(q) * D + d], acc);
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) out[w] = acc;
+}
+
+__global__ void classify_kernel(const float* __restrict__ sim, long long n, int Q, float th, int32_t* __restrict__ cls,
+                                float* __restrict__ conf) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* row = sim + i * Q;
+  float best = row[0];
+  int bi = 0;
+  for (int q = 1; q < Q; ++q) {
+    const float v = row[q];
+    if (v > best) {  // first maximum wins, like torch.argmax
+      best = v;
+      bi = q;
+    }
+  }
+  const bool keep = best > th;
+  cls[i] = keep ? bi : -1;
+  conf[i] = keep ? best : 0.f;
+}
+
+}  // namespace ovo
+
+// =============================================================================================== handle
+struct ovo_map {
+  static constexpr int kSlots = 64;
+  ovo::FrameGeom* geom = nullptr;
+  ovo::FrameDev* frame = nullptr;
+  int32_t* counters = nullptr;  // [0] list len, [1] n_matched, [2] next_ins_id
+  int32_t* votes = nullptr; size_t votes_cap = 0;
+  int32_t* area = nullptr; int32_t* mask_ins = nullptr; ovo_vote_row* rows = nullptr; int masks_cap = 0;
+  int2* scratch_list = nullptr; size_t scratch_cap = 0;
+  float* depth_f = nullptr; size_t depth_cap = 0;
+  int2* slot_list[kSlots] = {}; size_t slot_cap[kSlots] = {}; int slot_n[kSlots] = {};
+  __nv_bfloat16* text_bf16 = nullptr; size_t text_cap = 0;
+  // pinned host staging
+  ovo_vote_row* h_rows = nullptr; int32_t* h_counters = nullptr; ovo::FrameDev* h_frame = nullptr;
+};
+
+namespace {
+template <typename T>
+int grow(T** p, size_t* cap, size_t need) {
+  if (need <= *cap) return OVO_OK;
+  if (*p) cudaFree(*p);
+  *p = nullptr;
+  const size_t n = need + need / 4 + 64;
+  if (cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(T)) != cudaSuccess) {
+    *cap = 0;
+    cudaGetLastError();
+    return ovo::set_error(OVO_E_NOMEM, "workspace allocation of %zu bytes failed", n * sizeof(T));
+  }
+  *cap = n;
+  return OVO_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int ovo_map_create(ovo_map_t** out) {
+  OVO_REQUIRE(out != nullptr, "ovo_map_create: null out");
+  ovo_map* m = new ovo_map();
+  if (cudaMalloc(&m->geom, sizeof(ovo::FrameGeom)) != cudaSuccess || cudaMalloc(&m->frame, sizeof(ovo::FrameDev)) != cudaSuccess ||
+      cudaMalloc(&m->counters, 4 * sizeof(int32_t)) != cudaSuccess ||
+      cudaMallocHost(&m->h_counters, 4 * sizeof(int32_t)) != cudaSuccess ||
+      cudaMallocHost(&m->h_frame, sizeof(ovo::FrameDev)) != cudaSuccess) {
+    int r = ovo::set_error(OVO_E_CUDA, "ovo_map_create: %s", cudaGetErrorString(cudaGetLastError()));
+    ovo_map_destroy(m);
+    return r;
+  }
+  *out = m;
+  return OVO_OK;
+}
+
+void ovo_map_destroy(ovo_map_t* m) {
+  if (!m) return;
+  cudaFree(m->geom); cudaFree(m->frame); cudaFree(m->counters); cudaFree(m->votes); cudaFree(m->area);
+  cudaFree(m->mask_ins); cudaFree(m->rows); cudaFree(m->scratch_list); cudaFree(m->depth_f); cudaFree(m->text_bf16);
+  for (int i = 0; i < ovo_map::kSlots; ++i) cudaFree(m->slot_list[i]);
+  cudaFreeHost(m->h_rows); cudaFreeHost(m->h_counters); cudaFreeHost(m->h_frame);
+  delete m;
+}
+
+int ovo_depth_filter(const float* depth_dev, int h, int w, float* out_dev, void* stream) {
+  OVO_REQUIRE(depth_dev && out_dev && h >= 4 && w >= 4, "ovo_depth_filter: bad arguments");
+  dim3 b(32, 8), g(ovo::ceil_div(w, 32), ovo::ceil_div(h, 8));
+  ovo::depth_filter_kernel<<<g, b, 0, static_cast<cudaStream_t>(stream)>>>(depth_dev, h, w, out_dev);
+  OVO_CHECK_LAUNCH();
+  return OVO_OK;
+}
+
+int ovo_map_associate(ovo_map_t* m, const float* xyz_dev, int32_t* ins_ids_dev, int64_t N, const ovo_frame* f,
+                      int* next_ins_id, ovo_vote_row* votes_host, int* n_matched_host, int kf_slot, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  OVO_REQUIRE(m && f && next_ins_id && votes_host && n_matched_host, "ovo_map_associate: null argument");
+  OVO_REQUIRE(N >= 0 && N < (1LL << 31), "ovo_map_associate: N out of range");
+  OVO_REQUIRE(kf_slot >= 0 && kf_slot < ovo_map::kSlots, "ovo_map_associate: kf_slot out of range");
+  OVO_REQUIRE(f->n_masks >= 0 && f->n_masks <= 8192, "ovo_map_associate: n_masks out of range");
+  OVO_REQUIRE(f->depth_dev && f->seg_map_dev && f->h > 0 && f->w > 0 && f->H > 0 && f->W > 0, "ovo_map_associate: bad frame");
+  OVO_REQUIRE(N == 0 || (xyz_dev && ins_ids_dev), "ovo_map_associate: null map");
+  const int n_masks = f->n_masks, n_ins = *next_ins_id;
+  OVO_REQUIRE(n_ins >= 0, "ovo_map_associate: negative next_ins_id");
+  const size_t votes_need = static_cast<size_t>(n_masks > 0 ? n_masks : 1) * (n_ins + 1);
+  OVO_REQUIRE(votes_need < (1ull << 28), "ovo_map_associate: vote table too large (%d masks x %d instances)", n_masks, n_ins);
+
+  // workspaces
+  OVO_TRY(grow(&m->votes, &m->votes_cap, votes_need));
+  if (n_masks + 1 > m->masks_cap) {
+    cudaFree(m->area); cudaFree(m->mask_ins); cudaFree(m->rows); cudaFreeHost(m->h_rows);
+    m->masks_cap = n_masks + 64;
+    OVO_CUDA(cudaMalloc(&m->area, m->masks_cap * sizeof(int32_t)));
+    OVO_CUDA(cudaMalloc(&m->mask_ins, m->masks_cap * sizeof(int32_t)));
+    OVO_CUDA(cudaMalloc(&m->rows, m->masks_cap * sizeof(ovo_vote_row)));
+    OVO_CUDA(cudaMallocHost(&m->h_rows, m->masks_cap * sizeof(ovo_vote_row)));
+  }
+  OVO_TRY(grow(&m->scratch_list, &m->scratch_cap, static_cast<size_t>(N > 0 ? N : 1)));
+  const int npix = f->h * f->w;
+  OVO_TRY(grow(&m->depth_f, &m->depth_cap, static_cast<size_t>(npix)));
+
+  // frame constants
+  ovo::FrameDev* hf = m->h_frame;
+  memcpy(hf->c2w, f->c2w, sizeof(hf->c2w)); memcpy(hf->w2c, f->w2c, sizeof(hf->w2c)); memcpy(hf->K, f->K, sizeof(hf->K));
+  hf->match_th = f->match_th; hf->h = f->h; hf->w = f->w; hf->H = f->H; hf->W = f->W;
+  hf->has_ratio = f->has_ratio; hf->ratio_h = f->ratio_h; hf->ratio_w = f->ratio_w; hf->crop_edge = f->crop_edge;
+  OVO_CUDA(cudaMemcpyAsync(m->frame, hf, sizeof(ovo::FrameDev), cudaMemcpyHostToDevice, stream));
+  ovo::FrameGeom init{};
+  init.dmin_bits = 0x7f800000; init.dmax_bits = 0;
+  OVO_CUDA(cudaMemcpyAsync(m->geom, &init, sizeof(init), cudaMemcpyHostToDevice, stream));
+  m->h_counters[0] = 0; m->h_counters[1] = 0; m->h_counters[2] = n_ins; m->h_counters[3] = 0;
+  OVO_CUDA(cudaMemcpyAsync(m->counters, m->h_counters, 4 * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
+  OVO_CUDA(cudaMemsetAsync(m->votes, 0, votes_need * sizeof(int32_t), stream));
+  OVO_CUDA(cudaMemsetAsync(m->area, 0, (n_masks + 1) * sizeof(int32_t), stream));
+
+  const int sms = ovo::num_sms();
+  // frustum from the RAW depth (ovo.py:209), match against the filtered depth (ovo.py:213-216)
+  ovo::depth_minmax_kernel<<<sms, 256, 0, stream>>>(f->depth_dev, npix, m->geom);
+  OVO_CHECK_LAUNCH();
+  ovo::frustum_setup_kernel<<<1, 1, 0, stream>>>(m->geom, m->frame);
+  OVO_CHECK_LAUNCH();
+  const float* depth_used = f->depth_dev;
+  if (f->depth_filter) {
+    OVO_TRY(ovo_depth_filter(f->depth_dev, f->h, f->w, m->depth_f, stream));
+    depth_used = m->depth_f;
+  }
+  if (n_masks > 0) {
+    ovo::seg_area_kernel<<<sms, 256, n_masks * sizeof(int32_t), stream>>>(f->seg_map_dev, f->H * f->W, n_masks, m->area);
+    OVO_CHECK_LAUNCH();
+  }
+  if (N > 0) {
+    const int blocks = static_cast<int>(std::min<long long>((N + ovo::kP1Threads - 1) / ovo::kP1Threads, sms * 8LL));
+    ovo::associate_pass1_kernel<<<blocks, ovo::kP1Threads, 0, stream>>>(xyz_dev, ins_ids_dev, N, depth_used, f->seg_map_dev,
+                                                                        m->geom, m->frame, n_masks, n_ins, m->votes,
+                                                                        m->scratch_list, m->counters);
+    OVO_CHECK_LAUNCH();
+  }
+  if (n_masks > 0) {
+    ovo::vote_reduce_kernel<<<n_masks, 128, 0, stream>>>(m->votes, n_ins, m->area, m->rows);
+    OVO_CHECK_LAUNCH();
+    ovo::vote_decide_kernel<<<1, 1, 0, stream>>>(m->rows, n_masks, f->track_th, m->mask_ins, m->counters + 2);
+    OVO_CHECK_LAUNCH();
+    if (N > 0) {
+      ovo::associate_pass2_kernel<<<sms * 4, 256, 0, stream>>>(m->scratch_list, m->counters, m->mask_ins, ins_ids_dev);
+      OVO_CHECK_LAUNCH();
+    }
+    OVO_CUDA(cudaMemcpyAsync(m->h_rows, m->rows, n_masks * sizeof(ovo_vote_row), cudaMemcpyDeviceToHost, stream));
+  }
+  OVO_CUDA(cudaMemcpyAsync(m->h_counters, m->counters, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+  OVO_CUDA(cudaStreamSynchronize(stream));  // the one host sync of the association step
+  if (n_masks > 0) memcpy(votes_host, m->h_rows, n_masks * sizeof(ovo_vote_row));
+  *n_matched_host = m->h_counters[1];
+  *next_ins_id = m->h_counters[2];
+  // keep this keyframe's matched list for the (delayed) dense fusion
+  const int n_list = m->h_counters[0];
+  OVO_TRY(grow(&m->slot_list[kf_slot], &m->slot_cap[kf_slot], static_cast<size_t>(n_list > 0 ? n_list : 1)));
+  if (n_list > 0)
+    OVO_CUDA(cudaMemcpyAsync(m->slot_list[kf_slot], m->scratch_list, n_list * sizeof(int2), cudaMemcpyDeviceToDevice, stream));
+  m->slot_n[kf_slot] = n_list;
+  return OVO_OK;
+}
+
+int ovo_map_get_matches(ovo_map_t* m, int kf_slot, int32_t* pairs_dev, int max_pairs, void* stream) {
+  OVO_REQUIRE(m && kf_slot >= 0 && kf_slot < ovo_map::kSlots, "ovo_map_get_matches: bad slot");
+  const int n = m->slot_n[kf_slot];
+  OVO_REQUIRE(max_pairs >= n, "ovo_map_get_matches: buffer too small (%d < %d)", max_pairs, n);
+  if (n > 0)
+    OVO_CUDA(cudaMemcpyAsync(pairs_dev, m->slot_list[kf_slot], n * sizeof(int2), cudaMemcpyDeviceToDevice,
+                             static_cast<cudaStream_t>(stream)));
+  return n;
+}
+
+int ovo_map_fuse_dense(ovo_map_t* m, int kf_slot, void* bank_dev, int32_t* counts_dev, int64_t N, int D,
+                       const float* feats_dev, const int32_t* mask_row_dev, int n_masks, void* stream) {
+  OVO_REQUIRE(m && kf_slot >= 0 && kf_slot < ovo_map::kSlots, "ovo_map_fuse_dense: bad slot");
+  OVO_REQUIRE(bank_dev && counts_dev && feats_dev && mask_row_dev, "ovo_map_fuse_dense: null argument");
+  OVO_REQUIRE(D > 0 && D % 8 == 0, "ovo_map_fuse_dense: D must be a multiple of 8");
+  (void)N; (void)n_masks;
+  const int n = m->slot_n[kf_slot];
+  if (n == 0) return OVO_OK;
+  const int blocks = std::min(ovo::ceil_div(n, 8), ovo::num_sms() * 8);
+  ovo::fuse_dense_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      m->slot_list[kf_slot], n, static_cast<__nv_bfloat16*>(bank_dev), counts_dev, D, feats_dev, mask_row_dev);
+  OVO_CHECK_LAUNCH();
+  return OVO_OK;
+}
+
+int ovo_bank_update_mean(float* bank_dev, int32_t* counts_dev, int D, const float* feats_dev, const int32_t* rows_dev,
+                         int n, void* stream) {
+  OVO_REQUIRE(bank_dev && counts_dev && feats_dev && rows_dev && D > 0, "ovo_bank_update_mean: bad arguments");
+  if (n <= 0) return OVO_OK;
+  ovo::bank_update_mean_kernel<<<n, 256, 0, static_cast<cudaStream_t>(stream)>>>(bank_dev, counts_dev, D, feats_dev, rows_dev, n);
+  OVO_CHECK_LAUNCH();
+  return OVO_OK;
+}
+
+int ovo_query_dense(ovo_map_t* m, const void* bank_dev, int64_t N, int D, const float* text_dev, int Q, float* out_dev,
+                    void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  OVO_REQUIRE(m && bank_dev && text_dev && out_dev, "ovo_query_dense: null argument");
+  OVO_REQUIRE(N > 0 && N < (1LL << 31) && D > 0 && D % 8 == 0 && Q > 0, "ovo_query_dense: bad shape N=%lld D=%d Q=%d", (long long)N, D, Q);
+  for (int q0 = 0; q0 < Q; q0 += 256) {
+    const int qn = std::min(256, Q - q0);
+    const int qpad = qn <= 32 ? 32 : (qn <= 64 ? 64 : (qn <= 128 ? 128 : 256));
+    OVO_TRY(grow(&m->text_bf16, &m->text_cap, static_cast<size_t>(256) * D));
+    ovo::f32_to_bf16_pad_kernel<<<ovo::ceil_div(static_cast<long long>(qpad) * D, 256), 256, 0, stream>>>(
+        text_dev + static_cast<size_t>(q0) * D, qn, D, m->text_bf16, qpad);
+    OVO_CHECK_LAUNCH();
+    ovo::EpiParams ep;
+    ep.out = out_dev + q0;
+    ep.ldo = Q;
+    OVO_TRY(ovo::launch_gemm(ovo::EPI_F32, static_cast<const __nv_bfloat16*>(bank_dev), D, m->text_bf16, D,
+                             static_cast<int>(N), qn, D, ep, stream, qpad));
+  }
+  return OVO_OK;
+}
+
+int ovo_query_instances(const float* bank_dev, int I, int D, const float* text_dev, int Q, float* out_dev, void* stream) {
+  OVO_REQUIRE(bank_dev && text_dev && out_dev && I > 0 && D > 0 && Q > 0, "ovo_query_instances: bad arguments");
+  const long long threads = static_cast<long long>(I) * Q * 32;
+  ovo::query_instances_kernel<<<ovo::ceil_div(threads, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(bank_dev, I, D, text_dev, Q, out_dev);
+  OVO_CHECK_LAUNCH();
+  return OVO_OK;
+}
+
+int ovo_classify(const float* sim_dev, int64_t n, int Q, float th, int32_t* cls_dev, float* conf_dev, void* stream) {
+  OVO_REQUIRE(sim_dev && cls_dev && conf_dev && n > 0 && Q > 0, "ovo_classify: bad arguments");
+  ovo::classify_kernel<<<ovo::ceil_div(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(sim_dev, n, Q, th, cls_dev, conf_dev);
+  OVO_CHECK_LAUNCH();
+  return OVO_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,122 @@
+"""Host side of the 3D association / fusion / query kernels (libovo_b200 map entry points).
+
+`SemanticMap` replaces the body of `OVO._match_and_track_instances` + `_track_objects`
+(ovo/entities/ovo.py:182-282) and carries the two map modes of SURVEY §0: the instance bank (reference
+semantics) and the dense per-point bank (north-star running-mean / cosine kernels)."""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import Frame, VoteRow, check, ptr, stream_ptr
+
+VOTE_FIELDS = ("n_matched", "n_assigned", "n_unassigned", "mode_id", "ins_id", "is_new", "area")
+
+
+class SemanticMap:
+    def __init__(self, device="cuda"):
+        if not torch.cuda.is_available():
+            raise RuntimeError("ovo_b200.SemanticMap needs a CUDA device (no CPU fallback)")
+        self.device = torch.device(device)
+        self.lib = _lib.lib()
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            check(self.lib.ovo_map_create(C.byref(h)), "ovo_map_create")
+        self.handle = h
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                self.lib.ovo_map_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    # -------------------------------------------------------------------------------------------
+    def depth_filter(self, depth: torch.Tensor) -> torch.Tensor:
+        """geometry_utils.depth_filter (geometry_utils.py:92-96)."""
+        depth = depth.to(self.device, torch.float32).contiguous()
+        out = torch.empty_like(depth)
+        check(self.lib.ovo_depth_filter(ptr(depth), depth.shape[0], depth.shape[1], ptr(out), stream_ptr()), "ovo_depth_filter")
+        return out
+
+    def associate(self, xyz: torch.Tensor, ins_ids: torch.Tensor, depth: torch.Tensor, seg_map: torch.Tensor,
+                  c2w, K, next_ins_id: int, match_th: float = 0.05, track_th: int = 100, depth_filter: bool = True,
+                  rgb_depth_ratio=(), kf_slot: int = 0, n_masks: int | None = None, w2c=None):
+        """One keyframe of association.  xyz [N,3] f32, ins_ids [N] i32 (updated IN PLACE), depth [h,w] f32,
+        seg_map [H,W] i32, all on the device.  Returns (votes dict of np arrays [n_masks], n_matched,
+        next_ins_id)."""
+        assert xyz.is_cuda and ins_ids.is_cuda and depth.is_cuda and seg_map.is_cuda
+        assert xyz.dtype == torch.float32 and ins_ids.dtype == torch.int32 and seg_map.dtype == torch.int32
+        assert xyz.is_contiguous() and ins_ids.is_contiguous() and depth.is_contiguous() and seg_map.is_contiguous()
+        c2w = np.asarray(c2w, np.float32).reshape(4, 4)
+        if w2c is None:
+            w2c = torch.linalg.inv(torch.from_numpy(c2w)).numpy()      # ovo.py:216
+        K = np.asarray(K, np.float32).reshape(3, 3)
+        if n_masks is None:
+            n_masks = int(seg_map.max().item()) + 1                     # ovo.py:255
+        f = Frame()
+        f.depth_dev = ptr(depth); f.h, f.w = depth.shape
+        f.seg_map_dev = ptr(seg_map); f.H, f.W = seg_map.shape
+        f.n_masks = n_masks
+        f.c2w[:] = c2w.reshape(-1).tolist(); f.w2c[:] = np.asarray(w2c, np.float32).reshape(-1).tolist()
+        f.K[:] = K.reshape(-1).tolist()
+        f.match_th, f.track_th, f.depth_filter = float(match_th), int(track_th), int(bool(depth_filter))
+        if len(rgb_depth_ratio) > 0:
+            f.has_ratio, f.ratio_h, f.ratio_w, f.crop_edge = 1, float(rgb_depth_ratio[0]), float(rgb_depth_ratio[1]), int(rgb_depth_ratio[2])
+        rows = (VoteRow * max(n_masks, 1))()
+        nxt, nm = C.c_int(next_ins_id), C.c_int(0)
+        check(self.lib.ovo_map_associate(self.handle, ptr(xyz), ptr(ins_ids), xyz.shape[0], C.byref(f), C.byref(nxt), rows,
+                                         C.byref(nm), kf_slot, stream_ptr()), "ovo_map_associate")
+        arr = np.frombuffer(rows, dtype=np.int32).reshape(-1, 8)[:n_masks]
+        votes = {k: arr[:, i].copy() for i, k in enumerate(VOTE_FIELDS)}
+        return votes, nm.value, nxt.value
+
+    def matches(self, kf_slot: int, n_max: int) -> torch.Tensor:
+        """(point index, mask index) pairs of a keyframe slot, [n,2] i32 on the device (unordered)."""
+        buf = torch.empty(max(n_max, 1), 2, device=self.device, dtype=torch.int32)
+        n = check(self.lib.ovo_map_get_matches(self.handle, kf_slot, ptr(buf), n_max, stream_ptr()), "ovo_map_get_matches")
+        return buf[:n]
+
+    def fuse_dense(self, kf_slot: int, bank: torch.Tensor, counts: torch.Tensor, feats: torch.Tensor, mask_row: torch.Tensor):
+        """Per-point running mean: bank [N,D] bf16, counts [N] i32, feats [R,D] f32, mask_row [n_masks] i32."""
+        assert bank.dtype == torch.bfloat16 and counts.dtype == torch.int32 and feats.dtype == torch.float32
+        assert mask_row.dtype == torch.int32 and bank.is_contiguous() and feats.is_contiguous()
+        check(self.lib.ovo_map_fuse_dense(self.handle, kf_slot, ptr(bank), ptr(counts), bank.shape[0], bank.shape[1],
+                                          ptr(feats), ptr(mask_row), mask_row.shape[0], stream_ptr()), "ovo_map_fuse_dense")
+
+    def query_dense(self, bank: torch.Tensor, text: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+        """clip_cosine_similarity over the dense bank: [N,D] bf16 x [Q,D] f32 -> [N,Q] f32."""
+        assert bank.dtype == torch.bfloat16 and bank.is_contiguous()
+        text = text.to(self.device, torch.float32).contiguous()
+        N, D = bank.shape
+        Q = text.shape[0]
+        if out is None:
+            out = torch.empty(N, Q, device=self.device, dtype=torch.float32)
+        check(self.lib.ovo_query_dense(self.handle, ptr(bank), N, D, ptr(text), Q, ptr(out), stream_ptr()), "ovo_query_dense")
+        return out
+
+    def query_instances(self, bank: torch.Tensor, text: torch.Tensor) -> torch.Tensor:
+        """clip_cosine_similarity over the instance bank in f32: [I,D] x [Q,D] -> [I,Q]."""
+        bank = bank.to(self.device, torch.float32).contiguous()
+        text = text.to(self.device, torch.float32).contiguous()
+        out = torch.empty(bank.shape[0], text.shape[0], device=self.device, dtype=torch.float32)
+        check(self.lib.ovo_query_instances(ptr(bank), bank.shape[0], bank.shape[1], ptr(text), text.shape[0], ptr(out),
+                                           stream_ptr()), "ovo_query_instances")
+        return out
+
+    def classify(self, sim: torch.Tensor, th: float = 0.0):
+        """OVO.classify_instances' argmax + threshold (ovo.py:486-491)."""
+        sim = sim.contiguous()
+        cls = torch.empty(sim.shape[0], device=self.device, dtype=torch.int32)
+        conf = torch.empty(sim.shape[0], device=self.device, dtype=torch.float32)
+        check(self.lib.ovo_classify(ptr(sim), sim.shape[0], sim.shape[1], float(th), ptr(cls), ptr(conf), stream_ptr()), "ovo_classify")
+        return cls, conf
+
+    def bank_update_mean(self, bank: torch.Tensor, counts: torch.Tensor, feats: torch.Tensor, rows: torch.Tensor):
+        """avg_pooling running mean on the instance bank (instance3d.py:19-21)."""
+        assert bank.dtype == torch.float32 and counts.dtype == torch.int32 and rows.dtype == torch.int32
+        feats = feats.to(self.device, torch.float32).contiguous()
+        check(self.lib.ovo_bank_update_mean(ptr(bank), ptr(counts), bank.shape[1], ptr(feats), ptr(rows), rows.shape[0],
+                                            stream_ptr()), "ovo_bank_update_mean")
