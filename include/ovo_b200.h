@@ -88,6 +88,9 @@ typedef struct {
   /* region pooling (textregion.py:163-195 closed form): r = normalize(mean . pool_w^T + pool_b),
    * pool_w = (W_v^T W_o^T proj)^T as bf16 [output_dim, width], pool_b f32 [output_dim] */
   const void* pool_w; const float* pool_b;
+  const float* pool_b_empty; /* f32 [output_dim] = out_proj.bias @ proj: a mask that covers no token has every
+                              * key padded; torch's MHA (safe softmax, torch >= 2.5) then attends to nothing and
+                              * the region feature is normalize(out_proj.bias @ proj) */
   /* text tower */
   const float* tok_emb;     /* f32 [vocab, text_width] token_embedding.weight */
   const float* text_pos;    /* f32 [ctx, text_width] */
@@ -116,8 +119,8 @@ int ovo_encoder_forward(ovo_encoder_t* enc, int n_img, int n_layers, int apply_l
                         void* stream);
 /* E3-E5: resize_features + get_features_mask + pe_value_with_sam2_attn (textregion.py:9-28,145-195) for
  * ONE frame whose n_img images start at image index img0 of the last forward.
- * masks uint8 [M,H,W] (non-zero = set) -> out f32 [M, output_dim], unit norm (NaN rows for masks that
- * cover no token, as the reference). */
+ * masks uint8 [M,H,W] (non-zero = set) -> out f32 [M, output_dim], unit norm (a mask that covers no token
+ * gets normalize(pool_b_empty), as the reference does under torch >= 2.5). */
 int ovo_encoder_pool_regions(ovo_encoder_t* enc, int img0, int H, int W, const uint8_t* masks_dev, int M,
                              float* out_dev, void* stream);
 /* CLIPGenerator.extract_clip, TextRegion branch (clip_generator.py:125-135): E1..E5 for a batch of

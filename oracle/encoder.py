@@ -259,13 +259,17 @@ def region_pool(canvas: torch.Tensor, fmask: torch.Tensor, W: dict, cfg: VitCfg)
     """Closed form of tr:183-195: all keys are identical (tr:185-186), so the softmax over
     un-padded keys is uniform and every head sees the same weights:
         out = normalize( out_proj( W_v . mean_{p in mask} x_p + b_v ) @ proj ).
-    A mask with no token gives NaN in the reference (all keys padded); same here (0/0)."""
+    A mask with no token has every key padded; torch's MHA (safe softmax, torch >= 2.5: verified against the
+    reference in tests/golden/encoder_tiny.npz) then attends to nothing, the attention output is 0 and the
+    region feature is normalize(out_proj.bias @ proj)."""
     D = cfg.width
     Wv = W["visual.attn_pool.attn.in_proj_weight"][2 * D: 3 * D]
     bv = W["visual.attn_pool.attn.in_proj_bias"][2 * D: 3 * D]
     fm = fmask.float()
-    mean = (fm @ canvas) / fm.sum(dim=1, keepdim=True)
+    cnt = fm.sum(dim=1, keepdim=True)
+    mean = (fm @ canvas) / cnt.clamp_min(1.0)
     v = F.linear(mean, Wv, bv)
+    v = torch.where(cnt > 0, v, torch.zeros_like(v))
     o = F.linear(v, W["visual.attn_pool.attn.out_proj.weight"], W["visual.attn_pool.attn.out_proj.bias"])
     r = o @ W["visual.proj"]
     return r / r.norm(dim=-1, keepdim=True).clamp_min(1e-12)

@@ -1,0 +1,211 @@
+"""TEST INFRASTRUCTURE — generates tests/golden/*.npz by running the UNMODIFIED reference
+(/root/reference, imported through oracle/ref_harness.py) on seeded synthetic inputs.
+
+    python -m oracle.gen_golden          (build container only; the GPU box has no /root/reference)
+
+Inputs and weights are NOT stored: they are regenerated in the tests from seeds
+(ovo_b200.synth + ovo_b200.encoder.random_state_dict), only the reference's outputs are committed.
+The reference model is pe.CLIP built from a small PEConfig (same code path as PE-Core-L14-336: cls token,
+abs pos-emb, 2D RoPE, attention pooler; head_dim 64) with our seeded weights loaded into it.
+"""
+import os
+import sys
+import tempfile
+
+import numpy as np
+import torch
+
+from . import ref_harness as rh
+from . import encoder as OE
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+# the small encoder used by every fixture
+TINY = dict(width=128, layers=2, heads=2, mlp_width=512, output_dim=64, text_width=128, text_heads=2, text_layers=2,
+            text_mlp_width=512, text_output_dim=64, vocab_size=1024)
+TEXT_TOKENS = np.array([[1000, 5, 17, 1001] + [0] * 28,
+                        [1000, 900, 3, 44, 2, 1001] + [0] * 26,
+                        [1000, 7, 1001] + [0] * 29], np.int64)
+QUERIES_TOK = TEXT_TOKENS  # three "queries" expressed directly as token ids (tiny vocab)
+
+
+def tiny_cfg():
+    from ovo_b200.encoder import EncoderConfig
+    return EncoderConfig(**TINY)
+
+
+def build_reference_model(seed=0):
+    """Reference pe.CLIP (tiny config) carrying OUR seeded weights."""
+    from ovo_b200.encoder import random_state_dict
+    cfg = tiny_cfg()
+    rh.setup_paths()
+    from core.vision_encoder.config import PEConfig, PETextConfig
+    import core.vision_encoder.pe as pe
+    vc = PEConfig(image_size=cfg.image_size, patch_size=cfg.patch_size, width=cfg.width, layers=cfg.layers,
+                  heads=cfg.heads, mlp_ratio=cfg.mlp_width / cfg.width, pool_type="attn", output_dim=cfg.output_dim,
+                  use_cls_token=True, attn_pooler_heads=cfg.heads)
+    tc = PETextConfig(context_length=cfg.text_ctx, width=cfg.text_width, heads=cfg.text_heads, layers=cfg.text_layers,
+                      output_dim=cfg.text_output_dim, mlp_ratio=cfg.text_mlp_width / cfg.text_width,
+                      vocab_size=cfg.vocab_size)
+    torch.manual_seed(123)
+    model = pe.CLIP(vc, tc).eval()
+    sd = random_state_dict(cfg, seed=seed)
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    assert not unexpected, unexpected
+    # keys we do not set never influence the TextRegion / text outputs: pooler probe/ln/mlp/q,k
+    assert all(k.startswith("visual.attn_pool.") or k == "logit_scale" for k in missing), missing
+    return model, sd, cfg
+
+
+def masks_for(h, w):
+    from ovo_b200 import synth
+    seg, bm = synth.grid_masks(h, w, rows=3, cols=4)
+    bm = np.concatenate([bm, np.zeros((1, h, w), bool)])
+    bm[-1, h // 2: h // 2 + 3, 5:9] = True          # too small to touch a token -> NaN row in the reference
+    return bm
+
+
+def gen_encoder():
+    from ovo_b200 import synth
+    model, sd, cfg = build_reference_model()
+    tr = rh.build_textregion(model)
+    out = {}
+    for tag, (h, w) in {"a": (480, 640), "b": (968, 1296)}.items():
+        img = synth.rgb(h, w, seed=3)
+        bm = masks_for(h, w)
+        imt = torch.from_numpy(img.transpose(2, 0, 1).copy()).float()
+        with torch.no_grad():
+            feats = tr.predict(imt / 255.0, torch.from_numpy(bm))
+            if tag == "a":
+                px = torch.stack([tr.clip_preprocess(imt / 255.0), tr.clip_preprocess((imt / 255.0)[:, 0:480, 0:640])])
+                tok = model.visual.forward_features(px, norm=True)
+                out["px_a_sub"] = px[:, :, ::7, ::7].numpy()
+                out["tok_a_sub"] = tok[:, ::16].numpy()
+                fm = tr.get_features_mask(torch.from_numpy(bm)) > 0
+                out["fmask_a"] = np.packbits(fm.numpy(), axis=1)
+        out[f"regions_{tag}"] = feats.numpy()
+    with torch.no_grad():
+        out["text"] = model.encode_text(torch.from_numpy(TEXT_TOKENS)).numpy()
+    tok = rh.tokenizer(32)
+    out["tokenizer_a_chair"] = tok(["a chair"]).numpy()
+    np.savez_compressed(os.path.join(OUT, "encoder_tiny.npz"), **out)
+    print("encoder_tiny.npz", {k: v.shape for k, v in out.items()})
+
+
+ASSOC_CASES = [(0, 20000, 0.25), (3, 60000, 0.5), (7, 150000, 0.25)]
+
+
+def gen_assoc():
+    from ovo_b200 import synth
+    rh.setup_paths()
+    import ovo.utils.geometry_utils as gu
+    K = synth.intrinsics()
+    out = {}
+    for fid, N, fv in ASSOC_CASES:
+        c2w = synth.pose(fid); d = synth.depth_map(frame_id=fid)
+        seg, _ = synth.grid_masks()
+        xyz, ids, ins = synth.point_map(N, d, K, c2w, seed=fid, frac_visible=fv)
+        tK, tc2w, td, txyz = map(torch.from_numpy, (K, c2w, d, xyz))
+        corners = gu.compute_camera_frustum_corners(td, tc2w, tK)
+        fmask = gu.compute_frustum_point_ids(txyz, corners, device="cpu")
+        df = gu.depth_filter(td)
+        midx, matches = gu.match_3d_points_to_2d_pixels(df, torch.linalg.inv(tc2w), txyz[fmask], tK, 0.05)
+        seg_of_pt = np.full(N, -2, np.int16)
+        seg_of_pt[fmask[midx].numpy()] = seg[matches[:, 1].numpy(), matches[:, 0].numpy()]
+        out[f"seg_of_pt_{fid}"] = seg_of_pt
+        out[f"depth_rejected_{fid}"] = np.packbits(df.numpy() == -1)
+        out[f"corners_{fid}"] = corners.numpy()
+    np.savez_compressed(os.path.join(OUT, "assoc.npz"), **out)
+    print("assoc.npz", {k: v.shape for k, v in out.items()})
+
+
+OVO_RUN = dict(n_points=40000, frac_visible=0.6, n_kf=4, pose_step=6, track_th=100)
+
+
+def ovo_config(masks_dir):
+    return {"segment_every": 1, "match_distance_th": 0.05, "track_th": OVO_RUN["track_th"], "depth_filter": True,
+            "log": False, "kf_queue_delay": 1, "debug_info": False, "verbose": False,
+            "sam": {"precomputed": True, "masks_base_path": masks_dir},
+            "clip": {"embed_type": "TextRegion", "model_card": "PE-Core-L14-336", "k_top_views": 10000,
+                     "fusion": "avg_pooling"}}
+
+
+def ovo_inputs():
+    """The synthetic replay every OVO end-to-end fixture / test uses."""
+    from ovo_b200 import synth
+    K = synth.intrinsics()
+    d0 = synth.depth_map(frame_id=0)
+    xyz, ids, ins = synth.point_map(OVO_RUN["n_points"], d0, K, synth.pose(0), seed=11, frac_visible=OVO_RUN["frac_visible"])
+    frames = []
+    for i in range(OVO_RUN["n_kf"]):
+        fid = i * OVO_RUN["pose_step"]
+        rows, cols = (6, 8) if i % 2 == 0 else (4, 5)       # masks change between keyframes -> merges and new ids
+        seg, bm = synth.grid_masks(rows=rows, cols=cols)
+        frames.append(dict(frame_id=fid, image=synth.rgb(seed=100 + i), depth=synth.depth_map(frame_id=fid),
+                           c2w=synth.pose(fid), seg=seg, bm=bm))
+    return K, xyz, ids, ins, frames
+
+
+def gen_ovo():
+    """Runs the reference OVO class itself (ovo/entities/ovo.py) over 4 keyframes."""
+    rh.setup_paths()
+    model, sd, cfg = build_reference_model()
+    import ovo.utils.clip_utils as cu
+    from torchvision.transforms import Resize, Normalize, CenterCrop, Compose
+    import core.vision_encoder.transforms as transforms
+
+    class TokTokenizer:          # queries are given as token-id rows in this fixture (tiny vocab)
+        def __call__(self, phrase):
+            return torch.from_numpy(QUERIES_TOK[int(phrase)][None])
+
+    def fake_loader(model_card, ckpt_path=None):
+        pre = transforms.get_image_transform(model.image_size)
+        keep = [tf for tf in pre.transforms if isinstance(tf, (Resize, CenterCrop, Normalize))]
+        return model, TokTokenizer(), Compose(keep)
+
+    cu.load_perception_encoder = fake_loader
+    from ovo.entities.ovo import OVO
+    from ovo.entities.logger import Logger
+    K, xyz, ids, ins, frames = ovo_inputs()
+    out = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        mdir = os.path.join(tmp, "masks", "scene")
+        os.makedirs(mdir)
+        for f in frames:
+            np.save(os.path.join(mdir, f"{f['frame_id']:04d}_seg_map_default.npy"), f["seg"])
+            np.save(os.path.join(mdir, f"{f['frame_id']:04d}_bmap_default.npy"), f["bm"])
+        logger = Logger(os.path.join(tmp, "log"), os.getpid(), False)
+        ovo = OVO(ovo_config(os.path.join(tmp, "masks")), logger, scene_name="scene", cam_intrinsics=torch.from_numpy(K),
+                  device="cpu")
+        ovo.clip_generator.clip_dim = cfg.output_dim   # the reference hard-codes 1024 (clip_generator.py:41)
+        pts, pids, pins = torch.from_numpy(xyz), torch.from_numpy(ids), torch.from_numpy(ins)
+        for i, f in enumerate(frames):
+            upd = ovo.detect_and_track_objects((f["frame_id"], f["image"], f["depth"], ()), (pts, pids, pins),
+                                               torch.from_numpy(f["c2w"]))
+            pins = upd
+            out[f"ins_ids_{i}"] = upd.numpy().astype(np.int16)
+            out[f"matched_ins_{i}"] = np.array(ovo.keyframes_queue[-1][0], np.int32)
+            out[f"maps_area_{i}"] = ovo.keyframes_queue[-1][1].sum((1, 2)).numpy().astype(np.int32)
+            ovo.compute_semantic_info()
+        ovo.complete_semantic_info()
+        keys = list(ovo.objects.keys())
+        out["object_ids"] = np.array(keys, np.int32)
+        out["object_clips"] = ovo.get_objs_clips().numpy()
+        out["object_n_kfs"] = np.array([len(ovo.objects[k].kfs_ids) for k in keys], np.int32)
+        out["query"] = ovo.query(["0", "1", "2"]).numpy()
+        cls = ovo.classify_instances(["0", "1", "2"], template="{}", th=0.0)
+        out["classes"], out["conf"] = cls["classes"], cls["conf"]
+        cd = ovo.capture_dict(False)
+        out["capture_keys"] = np.array(sorted(cd.keys()))
+    np.savez_compressed(os.path.join(OUT, "ovo_run.npz"), **out)
+    print("ovo_run.npz", {k: v.shape for k, v in out.items()})
+    print("objects", keys, "n_kfs", out["object_n_kfs"])
+
+
+if __name__ == "__main__":
+    if not rh.available():
+        sys.exit("reference not available: fixtures can only be generated in the build container")
+    os.makedirs(OUT, exist_ok=True)
+    which = sys.argv[1:] or ["encoder", "assoc", "ovo"]
+    for w in which:
+        globals()["gen_" + w]()

@@ -24,7 +24,7 @@ class BlockWeights(C.Structure):
 class VitWeights(C.Structure):
     _fields_ = [("patch_w", c_void_p), ("patch_kpad", c_int), ("cls_pos0", c_void_p), ("pos", c_void_p),
                 ("ln_pre_w", c_void_p), ("ln_pre_b", c_void_p), ("ln_post_w", c_void_p), ("ln_post_b", c_void_p),
-                ("blocks", C.POINTER(BlockWeights)), ("pool_w", c_void_p), ("pool_b", c_void_p),
+                ("blocks", C.POINTER(BlockWeights)), ("pool_w", c_void_p), ("pool_b", c_void_p), ("pool_b_empty", c_void_p),
                 ("tok_emb", c_void_p), ("text_pos", c_void_p), ("text_blocks", C.POINTER(BlockWeights)),
                 ("ln_final_w", c_void_p), ("ln_final_b", c_void_p), ("text_proj_w", c_void_p)]
 

@@ -196,7 +196,8 @@ __global__ void feature_mask_kernel(const uint8_t* __restrict__ masks, int M, in
 
 // ------------------------------------------------------------------------------------------- E5 masked mean
 // mean[m] = sum_{p in mask m} canvas[p] / cnt[m]  (uniform softmax of textregion.py:183-189);
-// 8 masks per block share each canvas read.  0/0 -> NaN like the reference's all-padded attention.
+// 8 masks per block share each canvas read.  Empty masks (cnt 0) get a zero row and are fixed up in
+// l2_normalize_kernel.
 constexpr int kMeanMasks = 8;
 __global__ void __launch_bounds__(256)
     masked_mean_kernel(const float* __restrict__ canvas, int P, int width, const uint8_t* __restrict__ fmask,
@@ -227,16 +228,21 @@ __global__ void __launch_bounds__(256)
   if (d < width) {
 #pragma unroll
     for (int i = 0; i < kMeanMasks; ++i)
-      if (m0 + i < M) mean[static_cast<size_t>(m0 + i) * width + d] = __float2bfloat16_rn(acc[i] / static_cast<float>(cnt[m0 + i]));
+      if (m0 + i < M) mean[static_cast<size_t>(m0 + i) * width + d] = __float2bfloat16_rn(cnt[m0 + i] > 0 ? acc[i] / static_cast<float>(cnt[m0 + i]) : 0.f);
   }
 }
 
-// F.normalize(dim=-1) (textregion.py:194): one warp per row
-__global__ void l2_normalize_kernel(float* __restrict__ x, int rows, int dim) {
+// F.normalize(dim=-1) (textregion.py:194): one warp per row.  Rows whose mask covered no token (all keys
+// padded at textregion.py:187 -> the MHA attends to nothing) become normalize(out_proj.bias @ proj).
+__global__ void l2_normalize_kernel(float* __restrict__ x, int rows, int dim, const int* __restrict__ cnt,
+                                    const float* __restrict__ empty_vec) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
   float* r = x + static_cast<size_t>(row) * dim;
+  if (cnt != nullptr && cnt[row] == 0)
+    for (int d = lane; d < dim; d += 32) r[d] = empty_vec[d];
+  __syncwarp();
   float ss = 0.f;
   for (int d = lane; d < dim; d += 32) ss += r[d] * r[d];
   for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
@@ -298,6 +304,7 @@ struct ovo_encoder {
   struct GraphEntry { cudaGraphExec_t exec = nullptr; long long launches = 0; int warm = 0; };
   std::map<long long, GraphEntry> graphs;
   bool use_graphs = true;
+  cudaStream_t cap_stream = nullptr;  // capture happens here (the caller's stream may be the legacy stream)
 };
 
 namespace {
@@ -446,10 +453,11 @@ int ovo_encoder_create(const ovo_vit_cfg* cfg, const ovo_vit_weights* w, int max
 
   const int W = std::max(cfg->width, cfg->text_width), F = std::max(cfg->mlp_width, cfg->text_mlp_width);
   const int heads = std::max(cfg->heads, cfg->text_heads);
-  const size_t rows = static_cast<size_t>(max_images) * e->seq;   // text strings: up to max_images*seq/ctx
+  constexpr int kMaxText = 256;                                     // strings per ovo_encode_text call
+  const size_t rows = std::max(static_cast<size_t>(max_images) * e->seq, static_cast<size_t>(kMaxText) * std::max(cfg->text_ctx, 1));
   e->rows_cap = rows;
   const size_t rows_pad = rows + 128;
-  const size_t qk_elems = static_cast<size_t>(max_images) * heads * e->seq_pad * 64 * 2;  // x2: text uses seq_pad 128 per string
+  const size_t qk_elems = std::max(static_cast<size_t>(max_images) * e->seq_pad, static_cast<size_t>(kMaxText) * 128) * heads * 64;
   const int nh_max = std::max(max_h / cfg->image_size, 1), nw_max = std::max(max_w / cfg->image_size, 1);
   const size_t pmax = static_cast<size_t>(nh_max) * nw_max * e->patches;
   int r = OVO_OK;
@@ -508,6 +516,7 @@ int ovo_encoder_create(const ovo_vit_cfg* cfg, const ovo_vit_weights* w, int max
 void ovo_encoder_destroy(ovo_encoder_t* e) {
   if (!e) return;
   for (auto& g : e->graphs) if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
+  if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
   cudaFree(e->patch_buf); cudaFree(e->x); cudaFree(e->xfinal); cudaFree(e->xn); cudaFree(e->attn); cudaFree(e->hmid);
   cudaFree(e->q); cudaFree(e->k); cudaFree(e->vt); cudaFree(e->rope_cos); cudaFree(e->rope_sin); cudaFree(e->canvas);
   cudaFree(e->fmask); cudaFree(e->fcnt); cudaFree(e->mean); cudaFree(e->resize_tmp); cudaFree(e->eot_rows);
@@ -597,9 +606,10 @@ int ovo_encoder_forward(ovo_encoder_t* e, int n_img, int n_layers, int apply_ln_
     if (ge.exec == nullptr) {
       const long long before = ovo_launch_count(0);
       cudaGraph_t graph = nullptr;
-      OVO_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-      const int r = forward_eager(e, n_img, n_layers, apply_ln_post, s);
-      const cudaError_t ce = cudaStreamEndCapture(s, &graph);
+      if (!e->cap_stream) OVO_CUDA(cudaStreamCreateWithFlags(&e->cap_stream, cudaStreamNonBlocking));
+      OVO_CUDA(cudaStreamBeginCapture(e->cap_stream, cudaStreamCaptureModeThreadLocal));
+      const int r = forward_eager(e, n_img, n_layers, apply_ln_post, e->cap_stream);
+      const cudaError_t ce = cudaStreamEndCapture(e->cap_stream, &graph);
       if (r != OVO_OK) { if (graph) cudaGraphDestroy(graph); return r; }
       if (ce != cudaSuccess) return set_error(OVO_E_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
       const cudaError_t ie = cudaGraphInstantiate(&ge.exec, graph, 0);
@@ -637,7 +647,7 @@ int ovo_encoder_pool_regions(ovo_encoder_t* e, int img0, int H, int W, const uin
   EpiParams ep;
   ep.out = out_dev; ep.ldo = c.output_dim; ep.bias = e->w.pool_b;
   OVO_TRY(launch_gemm(EPI_F32, e->mean, c.width, static_cast<const __nv_bfloat16*>(e->w.pool_w), c.width, M, c.output_dim, c.width, ep, s));
-  l2_normalize_kernel<<<ceil_div(M, 8), 256, 0, s>>>(out_dev, M, c.output_dim);
+  l2_normalize_kernel<<<ceil_div(M, 8), 256, 0, s>>>(out_dev, M, c.output_dim, e->fcnt, e->w.pool_b_empty);
   OVO_CHECK_LAUNCH();
   return OVO_OK;
 }
@@ -664,8 +674,7 @@ int ovo_encode_text(ovo_encoder_t* e, const int32_t* tokens_dev, int T, float* o
   const ovo_vit_cfg& c = e->cfg;
   OVO_REQUIRE(c.text_layers > 0, "encoder was created without a text tower");
   const int ctx = c.text_ctx, W = c.text_width;
-  OVO_REQUIRE(static_cast<size_t>(T) * ctx <= e->rows_cap && static_cast<size_t>(T) * 128 <= static_cast<size_t>(e->max_images) * e->seq_pad * 2,
-              "ovo_encode_text: %d strings exceed the encoder workspace", T);
+  OVO_REQUIRE(T <= 256, "ovo_encode_text: at most 256 strings per call (got %d)", T);
   text_embed_kernel<<<T * ctx, 256, 0, s>>>(tokens_dev, T, ctx, W, e->w.tok_emb, e->w.text_pos, e->x, e->eot_rows);
   OVO_CHECK_LAUNCH();
   OVO_TRY(run_blocks(e, e->text_blocks, c.text_layers, T, ctx, 128, c.text_heads, W, c.text_mlp_width, false, true, s));

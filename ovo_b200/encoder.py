@@ -153,6 +153,7 @@ class RegionEncoder:
         w.ln_post_w = ptr(self._dev(sd["visual.ln_post.weight"], f32)); w.ln_post_b = ptr(self._dev(sd["visual.ln_post.bias"], f32))
         w.blocks = self._blocks(sd, "visual.transformer.resblocks.", cfg.layers)
         w.pool_w = ptr(self._dev(A.T.float(), bf)); w.pool_b = ptr(self._dev(cvec.float(), f32))
+        w.pool_b_empty = ptr(self._dev((bo @ proj).float(), f32))
         if self.has_text:
             w.tok_emb = ptr(self._dev(sd["token_embedding.weight"], f32))
             w.text_pos = ptr(self._dev(sd["positional_embedding"], f32))
