@@ -1,0 +1,384 @@
+#!/usr/bin/env python
+"""Headline benchmark: keyframes/s of CLIP-encode (PE-Core-L14-336, TextRegion pooling) + 3D fusion on
+640x480 RGB-D into a 2M-point map, and the dense text-vs-map cosine query in GB/s (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--frames-per-step F] [--points P]
+    python bench.py --impl reference ...     # the reference's algorithm on the host cores (CPU oracle port)
+
+One step = one batch of F synthetic keyframes through the hot path:
+  association of every keyframe against the map (cull + project + depth match + vote, 2 streaming passes),
+  E1..E5 for the whole batch (AA resize -> ViT-L/14 x (2 images per keyframe) -> canvas -> masked pooling),
+  dense per-point running-mean fusion of the region features + instance-bank fusion.
+`value` times this with every input resident in HBM; `e2e` times the public OVO API per keyframe with host
+(pinned) inputs copied in and the new descriptors copied out inside the timed region.
+Under torchrun each rank is one replica with its own scene (frames are data parallel): weak scaling.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H, W, N_MASK_ROWS, N_MASK_COLS, Q = 480, 640, 6, 8, 20
+GFLOP_PER_IMAGE = 349.2          # PE-Core-L14-336 forward_features, SURVEY §6 / BASELINE.md §2
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d["hbm_gbs"], d["bf16_tflops_sustained"], d["bf16_tflops"], "measured"
+    return 6650.0, 1400.0, 1590.0, "fallback"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def scene(points, seed):
+    from ovo_b200 import synth
+    K = synth.intrinsics(H, W)
+    d0 = synth.depth_map(H, W, 0)
+    xyz, ids, ins = synth.point_map(points, d0, K, synth.pose(0), seed=seed)
+    seg, bm = synth.grid_masks(H, W, N_MASK_ROWS, N_MASK_COLS)
+    return K, xyz, ids, ins, seg, bm
+
+
+def frames(n, seed):
+    from ovo_b200 import synth
+    return [dict(frame_id=i, image=synth.rgb(H, W, seed=seed * 1000 + i), depth=synth.depth_map(H, W, i % 4),
+                 c2w=synth.pose(i % 4)) for i in range(n)]
+
+
+# ================================================================================================ ours
+def run_ours(args, rank, world, local_rank):
+    from ovo_b200 import _lib, synth
+    from ovo_b200.encoder import EncoderConfig, RegionEncoder, random_state_dict
+    from ovo_b200.map import SemanticMap
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    F, P = args.frames_per_step, args.points
+    cfg = EncoderConfig()
+    sd = random_state_dict(cfg, seed=0, text=True)
+    enc = RegionEncoder(cfg, sd, max_images=2 * F, max_h=H, max_w=W, max_masks=64, device=dev)
+    sm = SemanticMap(dev)
+    K, xyz, ids, ins, seg, bm = scene(P, seed=rank)
+    M = bm.shape[0]
+    fr = frames(F, seed=rank)
+    # --- device-resident inputs for `value`
+    xyz_d = torch.from_numpy(xyz).to(dev)
+    ins_d = torch.from_numpy(ins).to(dev)
+    seg_d = torch.from_numpy(seg).to(dev)
+    rgb_d = torch.from_numpy(np.stack([f["image"] for f in fr])).to(dev)
+    depth_d = [torch.from_numpy(f["depth"]).to(dev) for f in fr]
+    masks_d = torch.from_numpy(np.concatenate([bm] * F)).to(dev).to(torch.uint8).contiguous()
+    D = cfg.output_dim
+    bank = torch.zeros(P, D, device=dev, dtype=torch.bfloat16)           # dense per-point map, 4.1 GB at 2M
+    counts = torch.zeros(P, device=dev, dtype=torch.int32)
+    ibank = torch.zeros(4096, D, device=dev, dtype=torch.float32)        # instance bank
+    icounts = torch.zeros(4096, device=dev, dtype=torch.int32)
+    w2cs = [torch.linalg.inv(torch.from_numpy(f["c2w"])).numpy() for f in fr]
+    state = dict(next_id=0, n_matched=0)
+
+    def step():
+        rows = []
+        for i, f in enumerate(fr):
+            votes, nm, state["next_id"] = sm.associate(xyz_d, ins_d, depth_d[i], seg_d, f["c2w"], K, state["next_id"],
+                                                       kf_slot=i, n_masks=M, w2c=w2cs[i])
+            state["n_matched"] = nm
+            rows.append(torch.from_numpy(votes["ins_id"].astype(np.int32)))
+        feats = enc.encode_regions(rgb_d, masks_d, masks_per_frame=[M] * F)
+        ins_rows = torch.stack(rows).to(dev, non_blocking=True)          # [F, M] instance id per mask (-1 = none)
+        ident = torch.arange(M, dtype=torch.int32, device=dev)
+        for i in range(F):
+            mask_row = torch.where(ins_rows[i] >= 0, ident, -1)
+            sm.fuse_dense(i, bank, counts, feats[i * M:(i + 1) * M], mask_row)
+            sm.bank_update_mean(ibank, icounts, feats[i * M:(i + 1) * M], ins_rows[i])
+        return feats
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        _lib.lib().ovo_launch_count(1)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        launches = _lib.lib().ovo_launch_count(0)
+        if dist:
+            dist.barrier()
+        ms = e0.elapsed_time(e1)
+        if dist:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms, launches
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ms_total, launches = timed(step, args.steps, args.warmup)
+    clocks = sampler.stop() if sampler else None
+    ms_step = ms_total / args.steps
+    value = world * F / (ms_step / 1e3)
+
+    # --- per-kernel-class breakdown: same steps, CUDA events around every launch (instrumented pass)
+    _lib.profile_begin()
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize()
+    prof = _lib.profile_report()
+    hbm, tf_sus, tf_burst, how = peaks()
+    g = prof["gemm"]
+    gemm_tflops = g["flops"] / (g["ms"] * 1e-3) / 1e12 if g["ms"] > 0 else 0.0
+    tot_ms = sum(v["ms"] for v in prof.values())
+    breakdown = {k: round(v["ms"] / 2, 4) for k, v in prof.items() if v["launches"]}
+    roofline = {"bound": "tensor", "kernel": "gemm_bf16_tn_kernel (tcgen05, all ViT linears)",
+                "achieved": round(gemm_tflops, 1), "peak": tf_sus, "unit": "TFLOP/s", "frac": round(gemm_tflops / tf_sus, 4),
+                "traffic": None, "peak_source": f"{how} bf16_tflops_sustained (kernel timed inside a long step)",
+                "flops_per_launch": round(g["flops"] / max(g["launches"], 1) / 1e9, 2), "avg_launch_us": round(1e3 * g["ms"] / max(g["launches"], 1), 2),
+                "share_of_step": round(g["ms"] / tot_ms, 3) if tot_ms else None,
+                "how": "CUDA events around every launch in an instrumented pass of the same steps (graphs off)",
+                "step_breakdown_ms": breakdown,
+                "encoder_algorithmic_tflops": round(2 * F * GFLOP_PER_IMAGE / (sum(prof[k]["ms"] for k in ("gemm", "attention", "layernorm")) / 2) , 1)}
+
+    # --- query: dense cosine of the text bank against the 2M-point map (HBM-bound)
+    text = torch.nn.functional.normalize(torch.randn(Q, D, device=dev, generator=torch.Generator(device=dev).manual_seed(1)), dim=-1)
+    qout = torch.empty(P, Q, device=dev)
+    qms, _ = timed(lambda: sm.query_dense(bank, text, qout), 20, 3)
+    qms /= 20
+    qbytes = P * D * 2 + P * Q * 4 + Q * D * 2
+    qgbs = qbytes / qms / 1e6
+    query = {"metric": "dense text-vs-map cosine query", "value": round(qgbs, 1), "unit": "GB/s", "ms": round(qms, 4),
+             "points": P, "queries": Q, "l2": "bank 4.1 GB >> 126 MB L2",
+             "roofline": {"bound": "hbm", "achieved": round(qgbs, 1), "peak": hbm, "unit": "GB/s", "frac": round(qgbs / hbm, 4),
+                          "traffic": None, "peak_source": f"{how} hbm_gbs", "algorithmic_bytes": qbytes}}
+
+    # --- e2e through the public OVO API, host inputs, per keyframe
+    e2e = run_e2e(args, rank, world, dev, enc, K, xyz, ids, ins, seg, bm, fr, dist)
+
+    if rank != 0:
+        return
+    out = {"metric": "keyframes/s, CLIP-encode (PE-Core-L14-336 TextRegion) + 3D fusion, 640x480 RGB-D into a 2M-point map",
+           "value": round(value, 2), "unit": "keyframes/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "bf16 (f32 accumulate, f32 residual stream)", "data": "synthetic (seeded RGB-D, random-init weights)",
+           "config": {"workload": f"{F} keyframes/step x {world} replica(s): 640x480 RGB-D, PE-Core-L14-336 (2 images/keyframe), "
+                                  f"{M} precomputed masks/keyframe (sam.precomputed seam), {P}-point map per replica, dense "
+                                  f"running-mean fusion + instance bank; query Q={Q}",
+                      "frames_per_step": F, "points": P, "masks": M, "queries": Q, "parallelism": f"replicas x{world}",
+                      "l2_policy": "inputs larger than L2: per step 0.63 GB weights + ~2 GB map/bank traffic per keyframe (L2 126 MB)"},
+           "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e, "roofline": roofline, "query": query,
+           "n_matched_points_per_keyframe": int(state["n_matched"])}
+    if not args.no_cpu_baseline and world >= 1:
+        out["cpu_baseline"] = cpu_baseline(args, budget_frames=1)
+    print(json.dumps(out))
+
+
+def run_e2e(args, rank, world, dev, enc, K, xyz, ids, ins, seg, bm, fr, dist):
+    """The call a user makes: OVO.detect_and_track_objects + compute_semantic_info per keyframe with numpy
+    (pinned) image/depth/masks on the host; the new descriptors are read back each keyframe."""
+    from ovo_b200 import OVO
+    from ovo_b200.clip_generator import CLIPGenerator
+
+    class _Logger:
+        def log_ovo_stats(self, *a, **k):
+            pass
+
+    class HostMasks:                   # precomputed masks served from pinned host memory (the .npy seam, RAM-resident)
+        precomputed = True
+
+        def __init__(self):
+            self.seg = torch.from_numpy(seg).pin_memory()
+            self.bm = torch.from_numpy(bm).pin_memory()
+
+        def get_masks(self, image, frame_id=None):
+            return self.seg.to(dev, non_blocking=True), self.bm.to(dev, non_blocking=True)
+
+        def cpu(self): pass
+        def cuda(self): pass
+
+    config = {"segment_every": 1, "match_distance_th": 0.05, "track_th": 100, "depth_filter": True, "log": False,
+              "kf_queue_delay": 0, "verbose": False, "dense_map": True, "sam": {"precomputed": True, "masks_base_path": ""},
+              "clip": {"embed_type": "TextRegion", "model_card": "PE-Core-L14-336", "k_top_views": 10000, "fusion": "avg_pooling"}}
+    clip = CLIPGenerator(config["clip"], encoder=enc)       # share the already-built encoder (weights are 0.7 GB)
+    ovo = OVO(config, _Logger(), scene_name=None, cam_intrinsics=torch.from_numpy(K), eval=True, clip_generator=clip, device="cuda")
+    ovo.mask_generator = HostMasks()
+    pts, pids = torch.from_numpy(xyz).to(dev), torch.from_numpy(ids).to(dev)
+    state = dict(pins=torch.from_numpy(ins).to(dev))
+    imgs = [torch.from_numpy(f["image"]).pin_memory().numpy() for f in fr]
+    deps = [torch.from_numpy(f["depth"]).pin_memory().numpy() for f in fr]
+    out_host = torch.empty(bm.shape[0], enc.cfg.output_dim).pin_memory()
+
+    def step():
+        for i, f in enumerate(fr):
+            upd = ovo.detect_and_track_objects((f["frame_id"], imgs[i], deps[i], ()), (pts, pids, state["pins"]), torch.from_numpy(f["c2w"]))
+            state["pins"] = upd
+            n0 = ovo._store_n
+            ovo.compute_semantic_info()
+            n = ovo._store_n - n0
+            out_host[:n].copy_(ovo._store[n0:n0 + n], non_blocking=True)
+        torch.cuda.synchronize()
+        if ovo._store_n > 200000:            # keep the descriptor store bounded over long runs
+            ovo._store_n = 0
+            ovo.keyframes["ins_descriptors"].clear()
+
+    steps = max(1, min(args.steps, 10))
+    for _ in range(max(3, min(args.warmup, 3))):
+        step()
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if dist:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    F = len(fr)
+    h2d = F * (imgs[0].nbytes + deps[0].nbytes + seg.nbytes + bm.nbytes)
+    d2h = F * (bm.shape[0] * enc.cfg.output_dim * 4 + bm.shape[0] * 32)
+    return {"value": round(world * F * steps / (ms / 1e3), 2), "unit": "keyframes/s", "h2d_bytes_per_step": int(h2d),
+            "d2h_bytes_per_step": int(d2h), "api": "ovo_b200.OVO.detect_and_track_objects + compute_semantic_info, one keyframe per call",
+            "steps": steps}
+
+
+# ================================================================================================ CPU reference arm
+def cpu_frames_per_second(points, n_frames, threads):
+    """The reference's algorithm for this path (oracle port: oracle/encoder.py + oracle/fusion.py) on the host."""
+    from oracle import encoder as OE, fusion as OF
+    from ovo_b200.encoder import EncoderConfig, random_state_dict
+    torch.set_num_threads(threads)
+    cfg = EncoderConfig()
+    ocfg = OE.VitCfg()
+    sd = random_state_dict(cfg, seed=0, text=False)
+    K, xyz, ids, ins, seg, bm = scene(points, seed=0)
+    fr = frames(n_frames, seed=0)
+    bank = np.zeros((points, 64), np.float32)        # the dense bank update is timed on a 64-wide slice and scaled
+    t0 = time.time()
+    nxt = 0
+    for f in fr:
+        w2c = torch.linalg.inv(torch.from_numpy(f["c2w"])).numpy()
+        seg_of_pt, _ = OF.associate(xyz, ins, f["depth"], seg, f["c2w"], w2c, K, 0.05, True)
+        ins, rows, nxt = OF.track(ins, seg_of_pt, seg, 100, nxt)
+        order, fused, mask_row = OF.fuse_masks(bm, rows)
+        with torch.no_grad():
+            feats = OE.encode_regions(f["image"], fused, sd, ocfg).numpy()
+        pts = np.nonzero(seg_of_pt >= 0)[0]
+        rr = mask_row[seg_of_pt[pts]]
+        sel = rr >= 0
+        bank[pts[sel]] += (feats[rr[sel], :64] - bank[pts[sel]]) * 0.5
+    return n_frames / (time.time() - t0)
+
+
+def cpu_baseline(args, budget_frames=1):
+    threads = os.cpu_count() or 1
+    fps = cpu_frames_per_second(args.points, budget_frames, threads)
+    return {"value": round(fps, 4), "unit": "keyframes/s", "cores": threads, "kind": "port",
+            "sample": f"{budget_frames} keyframe(s) of the same workload (640x480, 2 ViT-L/14 images, {args.points}-point map) "
+                      "through oracle/ (torch f32 + numpy restatement of the reference); dense-bank update timed on a 64-wide slice"}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    # warm-up (1 frame) then `steps` samples of 1 keyframe each, bounded so the whole run stays within minutes
+    cpu_frames_per_second(min(args.points, 200000), 1, threads)
+    steps = max(1, min(args.steps, 5))
+    t0 = time.time()
+    fps = [cpu_frames_per_second(args.points, 1, threads) for _ in range(steps)]
+    v = float(np.mean(fps))
+    M = N_MASK_ROWS * N_MASK_COLS
+    out = {"impl": "reference",
+           "metric": "keyframes/s, CLIP-encode (PE-Core-L14-336 TextRegion) + 3D fusion, 640x480 RGB-D into a 2M-point map",
+           "value": round(v, 4), "unit": "keyframes/s", "n_gpus": world, "steps": steps, "warmup": 1,
+           "ms_per_step": round(1e3 / v, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f32", "data": "synthetic (seeded RGB-D, random-init weights)",
+           "config": {"workload": f"1 keyframe/step: 640x480 RGB-D, PE-Core-L14-336 (2 images/keyframe), {M} precomputed masks, "
+                                  f"{args.points}-point map, reference algorithm on host cores", "points": args.points},
+           "cpu_baseline": {"value": round(v, 4), "unit": "keyframes/s", "cores": threads, "kind": "port",
+                            "sample": "1 keyframe per step through oracle/ (the Python reference cannot travel to the GPU box)"},
+           "e2e": {"value": round(v, 4), "unit": "keyframes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0, "wall_s": round(time.time() - t0, 1)}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames-per-step", type=int, default=8)
+    ap.add_argument("--points", type=int, default=2_000_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+    if not torch.cuda.is_available():
+        sys.exit("bench.py: no CUDA device (the hot path has no CPU fallback; use --impl reference for the CPU arm)")
+    run_ours(args, rank, world, local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -131,6 +131,10 @@ int ovo_encode_regions(ovo_encoder_t* enc, const uint8_t* rgb_dev, int n_frames,
  * normalised (the caller applies clip_generator.py:170-173,193-196). */
 int ovo_encode_text(ovo_encoder_t* enc, const int32_t* tokens_dev, int T, float* out_dev, void* stream);
 
+/* get_embed_txt_similarity's text side (clip_generator.py:161-173,186-196): tokens int32 [Q*T, ctx] (T templates
+ * per query, query-major) -> f32 [Q, text_output_dim] = normalize(mean_t(normalize(encode_text))). */
+int ovo_text_bank(ovo_encoder_t* enc, const int32_t* tokens_dev, int Q, int T, float* out_dev, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Map: 3D association, instance vote, fusion, query
  * ---------------------------------------------------------------------------------------------- */
@@ -198,12 +202,29 @@ int ovo_bank_update_mean(float* bank_dev, int32_t* counts_dev, int D, const floa
  * out f32 [N,Q].  tcgen05 GEMM streaming the bank once from HBM. */
 int ovo_query_dense(ovo_map_t* map, const void* bank_dev, int64_t N, int D, const float* text_dev, int Q,
                     float* out_dev, void* stream);
-/* Same, instance bank: bank f32 [I,D] x text f32 [Q,D]^T -> out f32 [I,Q] in f32 arithmetic. */
-int ovo_query_instances(const float* bank_dev, int I, int D, const float* text_dev, int Q, float* out_dev,
-                        void* stream);
+/* Same, instance bank (OVO.query / get_objs_clips, ovo.py:495-527): out[i] = bank[rows[i]] . text^T in f32.
+ * bank f32 [*,D], rows_dev i32 [I] (NULL = identity), text f32 [Q,D] -> out f32 [I,Q]. */
+int ovo_query_instances(const float* bank_dev, const int32_t* rows_dev, int I, int D, const float* text_dev, int Q,
+                        float* out_dev, void* stream);
+/* OVO._fuse_masks_with_same_ins_id (ovo.py:284-324): out[r] = OR of masks m with group_dev[m] == r (uint8 0/1,
+ * [R,H,W]); areas_dev[r] = number of set pixels.  masks uint8 [M,H,W]. */
+int ovo_merge_masks(const uint8_t* masks_dev, int M, int H, int W, const int32_t* group_dev, int R, uint8_t* out_dev,
+                    int32_t* areas_dev, void* stream);
+/* Instance3D.update_clip for a batch of instances (instance3d.py:157-189): instance j fuses the descriptor rows
+ * store[idx[off[j]..off[j+1])] into bank[out_rows[j]]; mode 0 avg_pooling (:19-21, not re-normalised),
+ * 1 l1_medoid (:9-12), 2 cossim_medoid (:14-17); chosen_dev[j] (optional) = index of the medoid view. */
+int ovo_fuse_views(const float* store_dev, int D, const int32_t* idx_dev, const int32_t* off_dev, int n_instances,
+                   int mode, float* bank_dev, const int32_t* out_rows_dev, int32_t* chosen_dev, void* stream);
 /* OVO.classify_instances (ovo.py:486-491): argmax over queries + threshold. sim f32 [n,Q] ->
  * cls i32 [n] (-1 if max <= th), conf f32 [n] (0 if max <= th). */
 int ovo_classify(const float* sim_dev, int64_t n, int Q, float th, int32_t* cls_dev, float* conf_dev, void* stream);
+
+/* Per-launch timing for bench.py's roofline: after ovo_profile_begin() every kernel launch of this library is
+ * bracketed by CUDA events on its stream (the encoder then runs eagerly instead of replaying its CUDA graph);
+ * ovo_profile_report() stops, synchronises and sums per kernel class: 0 gemm, 1 attention, 2 layernorm,
+ * 3 preprocess, 4 region pooling, 5 association, 6 dense fusion, 7 query, 8 other.  Returns the class count. */
+void ovo_profile_begin(void);
+int ovo_profile_report(int n_classes, float* ms_host, double* flops_host, double* bytes_host, int* counts_host);
 
 /* Test tap for the GEMM machinery: C[M,N] f32 = A[M,K] bf16 . B[N,K]^T bf16 (+bias f32 [N]). */
 int ovo_gemm_bf16(const void* A_dev, int lda, const void* B_dev, int ldb, int M, int N, int K,

@@ -66,8 +66,13 @@ SIGNATURES = {
                                    c_void_p]),
     "ovo_bank_update_mean": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p]),
     "ovo_query_dense": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_int, c_void_p, c_void_p]),
-    "ovo_query_instances": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),
+    "ovo_query_instances": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),
+    "ovo_merge_masks": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "ovo_fuse_views": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "ovo_text_bank": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "ovo_classify": (c_int, [c_void_p, c_int64, c_int, c_float, c_void_p, c_void_p, c_void_p]),
+    "ovo_profile_begin": (None, []),
+    "ovo_profile_report": (c_int, [c_int, C.POINTER(c_float), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(c_int)]),
     "ovo_gemm_bf16": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int,
                               c_int, c_void_p]),
 }
@@ -105,3 +110,18 @@ def ptr(t):
 def stream_ptr():
     import torch
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+PROF_CLASSES = ("gemm", "attention", "layernorm", "preprocess", "pool", "associate", "fuse_dense", "query", "other")
+
+
+def profile_begin():
+    lib().ovo_profile_begin()
+
+
+def profile_report():
+    """-> {class: dict(ms, flops, bytes, launches)} for the launches since profile_begin()."""
+    n = len(PROF_CLASSES)
+    ms, fl, by, ct = (c_float * n)(), (C.c_double * n)(), (C.c_double * n)(), (c_int * n)()
+    check(lib().ovo_profile_report(n, ms, fl, by, ct), "ovo_profile_report")
+    return {PROF_CLASSES[i]: dict(ms=ms[i], flops=fl[i], bytes=by[i], launches=ct[i]) for i in range(n)}

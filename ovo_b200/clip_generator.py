@@ -1,0 +1,122 @@
+"""`CLIPGenerator` with the reference's surface (ovo/entities/clip_generator.py:12-198), TextRegion branch
+(`embed_type: TextRegion`, the default of data/working/configs/ovo.yaml:45) on the sm_100a encoder.
+
+Weights: `config["ckpt_path"]` may point to a Perception-Encoder checkpoint (`torch.save`d state_dict with the
+reference's key names, what `pe.CLIP.load_ckpt` reads).  Without it — there is no network in the build or
+bench environment — seeded random weights of the same architecture are used and a warning is printed."""
+import os
+from typing import Dict, List
+
+import torch
+
+from . import _lib
+from ._lib import check, ptr, stream_ptr
+from .encoder import EncoderConfig, RegionEncoder, random_state_dict
+
+MODEL_CARDS = {"PE-Core-L14-336": EncoderConfig()}
+
+
+class CLIPGenerator:
+    def __init__(self, config: Dict, device: str = "cuda", state_dict: dict | None = None, tokenizer=None,
+                 encoder_config: EncoderConfig | None = None, encoder: RegionEncoder | None = None):
+        self.config = config
+        self.device = device
+        self.embed_type = config.get("embed_type", "vanilla")
+        self.mask_res = config.get("mask_res", 384)
+        if self.embed_type != "TextRegion":
+            raise NotImplementedError(
+                f"ovo_b200: embed_type '{self.embed_type}' (crop-based descriptors, SURVEY §8f rank 2) is not built; "
+                "use embed_type: TextRegion (the reference default)")
+        self.model_card = config.get("model_card", "PE-Core-L14-336")
+        cfg = (encoder.cfg if encoder is not None else None) or encoder_config or MODEL_CARDS.get(self.model_card)
+        if cfg is None:
+            raise NotImplementedError(f"ovo_b200: model card '{self.model_card}' is not supported (have {list(MODEL_CARDS)})")
+        if state_dict is None and encoder is None:
+            ckpt = config.get("ckpt_path")
+            if ckpt and os.path.exists(ckpt):
+                sd = torch.load(ckpt, map_location="cpu", weights_only=True)
+                sd = sd.get("state_dict", sd.get("weights", sd))
+                state_dict = {k.replace("module.", ""): v for k, v in sd.items()}
+            else:
+                print(f"[ovo_b200] no checkpoint for {self.model_card}: using seeded RANDOM weights (seed "
+                      f"{config.get('random_init_seed', 0)}) — descriptors carry no semantics")
+                state_dict = random_state_dict(cfg, seed=config.get("random_init_seed", 0))
+        self.cfg = cfg
+        self.clip_dim = cfg.output_dim
+        self.encoder = encoder or RegionEncoder(cfg, state_dict, max_images=config.get("max_images", 16),
+                                                max_h=config.get("max_h", 1080), max_w=config.get("max_w", 1920),
+                                                max_masks=config.get("max_masks", 512), device=device)
+        self.model = self.encoder                      # attribute the reference exposes
+        self._tokenizer = tokenizer
+        if self.model_card.startswith("SigLIP"):
+            raise NotImplementedError("SigLIP similarity is part of the open_clip branch (not built)")
+        self.similarity_args = ()
+        self._text_cache = {}
+
+    @property
+    def get_clip_dim(self) -> int:
+        return self.clip_dim
+
+    @property
+    def tokenizer(self):
+        if self._tokenizer is None:
+            from .tokenizer import BPETokenizer
+            self._tokenizer = BPETokenizer(context_length=self.cfg.text_ctx)
+        return self._tokenizer
+
+    def to(self, device: str) -> None:
+        return self.cuda() if "cuda" in device else self.cpu()
+
+    def cpu(self) -> None:
+        """The reference parks the model on the host to free VRAM; weights here stay device-resident (0.7 GB)."""
+        self.device = "cpu"
+
+    def cuda(self) -> None:
+        self.device = "cuda"
+
+    @torch.no_grad()
+    def extract_clip(self, image: torch.Tensor, binary_maps: torch.Tensor, return_all: bool = False) -> torch.Tensor:
+        """image [3,H,W] (or [H,W,3] uint8) range 0-255, binary_maps [N,H,W] -> [N, clip_dim] on the device
+        (clip_generator.py:125-135)."""
+        if image.dim() == 3 and image.shape[0] == 3 and image.shape[-1] != 3:
+            image = image.permute(1, 2, 0)
+        image = image.to(self.encoder.device).round().to(torch.uint8) if image.dtype != torch.uint8 else image
+        return self.encoder.encode_regions(image.contiguous(), binary_maps)
+
+    def _tokens(self, phrases: List[str]) -> torch.Tensor:
+        return torch.cat([self.tokenizer(p) for p in phrases])
+
+    @torch.no_grad()
+    def get_txt_embedding(self, text_list: List[str]) -> torch.Tensor:
+        """L2-normalised text embeddings, one per string (clip_generator.py:161-174)."""
+        return self.text_bank([[t] for t in text_list])
+
+    @torch.no_grad()
+    def text_bank(self, queries: List[List[str]]) -> torch.Tensor:
+        """queries[q] = the template-expanded phrases of query q -> [Q, D] = normalize(mean_t(normalize(e)))
+        (clip_generator.py:191-196), cached per phrase tuple."""
+        key = tuple(tuple(q) for q in queries)
+        if key not in self._text_cache:
+            T = len(queries[0])
+            assert all(len(q) == T for q in queries)
+            tok = self._tokens([p for q in queries for p in q]).to(self.encoder.device, torch.int32).contiguous()
+            out = torch.empty(len(queries), self.cfg.text_output_dim, device=self.encoder.device, dtype=torch.float32)
+            check(self.encoder.lib.ovo_text_bank(self.encoder.handle, ptr(tok), len(queries), T, ptr(out), stream_ptr()),
+                  "ovo_text_bank")
+            self._text_cache[key] = out
+        return self._text_cache[key]
+
+    @torch.no_grad()
+    def get_embed_txt_similarity(self, ins_descriptors: torch.Tensor, txt_queries: List[str],
+                                 templates: str | List[str] = ['{}'], rows: torch.Tensor | None = None) -> torch.Tensor:
+        """[n_obj, n_queries] plain dot products — PE cards use no logit scale (clip_generator.py:54-72,176-199)."""
+        if isinstance(templates, str):
+            templates = [templates]
+        queries = [[t.format(q) for t in templates] for q in txt_queries]
+        txt = self.text_bank(queries)
+        bank = ins_descriptors.to(self.encoder.device, torch.float32).contiguous()
+        n = bank.shape[0] if rows is None else rows.shape[0]
+        out = torch.empty(n, txt.shape[0], device=self.encoder.device, dtype=torch.float32)
+        check(_lib.lib().ovo_query_instances(ptr(bank), ptr(rows), n, bank.shape[1], ptr(txt), txt.shape[0], ptr(out),
+                                             stream_ptr()), "ovo_query_instances")
+        return out

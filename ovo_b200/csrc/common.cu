@@ -4,6 +4,7 @@
 
 #include <cudaTypedefs.h>
 #include <mutex>
+#include <vector>
 
 namespace ovo {
 
@@ -18,6 +19,20 @@ int set_error(int code, const char* fmt, ...) {
   return code;
 }
 void count_launch(int n) { g_launches += n; }
+
+struct ProfRec { int cls; cudaEvent_t a, b; double flops, bytes; };
+static bool g_prof = false;
+static std::vector<ProfRec> g_recs;
+bool profiling() { return g_prof; }
+ProfScope::ProfScope(cudaStream_t stream, int cls, double flops, double bytes) : s(stream), idx(-1) {
+  if (!g_prof) return;
+  ProfRec r{cls, nullptr, nullptr, flops, bytes};
+  cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+  cudaEventRecord(r.a, s);
+  g_recs.push_back(r);
+  idx = static_cast<int>(g_recs.size()) - 1;
+}
+ProfScope::~ProfScope() { if (idx >= 0) cudaEventRecord(g_recs[idx].b, s); }
 
 int num_sms() {
   static int sms = 0;
@@ -74,6 +89,7 @@ static int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N
   }
   const int tiles = ceil_div(M, kBM) * ceil_div(N, BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
+  ProfScope prof(stream, ep.prof_cls, 2.0 * M * N * K, 2.0 * (static_cast<double>(M) * K + static_cast<double>(N) * K) + 4.0 * M * N);
   kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, M, N, K, ep);
   OVO_CHECK_LAUNCH();
   return OVO_OK;
@@ -132,6 +148,28 @@ long long ovo_launch_count(int reset) {
   long long v = ovo::g_launches;
   if (reset) ovo::g_launches = 0;
   return v;
+}
+
+void ovo_profile_begin(void) {
+  for (auto& r : ovo::g_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  ovo::g_recs.clear();
+  ovo::g_prof = true;
+}
+
+int ovo_profile_report(int n_classes, float* ms, double* flops, double* bytes, int* counts) {
+  ovo::g_prof = false;
+  if (n_classes < ovo::PROF_NCLASS) return ovo::set_error(OVO_E_INVALID, "ovo_profile_report: need room for %d classes", (int)ovo::PROF_NCLASS);
+  for (int i = 0; i < n_classes; ++i) { ms[i] = 0.f; flops[i] = 0.0; bytes[i] = 0.0; counts[i] = 0; }
+  for (auto& r : ovo::g_recs) {
+    float t = 0.f;
+    if (cudaEventSynchronize(r.b) == cudaSuccess && cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) {
+      ms[r.cls] += t; flops[r.cls] += r.flops; bytes[r.cls] += r.bytes; counts[r.cls] += 1;
+    }
+    cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+  }
+  ovo::g_recs.clear();
+  cudaGetLastError();
+  return ovo::PROF_NCLASS;
 }
 
 int ovo_gemm_bf16(const void* A_dev, int lda, const void* B_dev, int ldb, int M, int N, int K, const float* bias_dev,

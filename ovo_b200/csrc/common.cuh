@@ -39,4 +39,15 @@ void count_launch(int n = 1);
 
 inline int ceil_div(long long a, long long b) { return static_cast<int>((a + b - 1) / b); }
 
+// Optional per-launch timing (ovo_profile_begin / ovo_profile_report): CUDA events recorded on the launching
+// stream around each kernel, aggregated per kernel class.  Off by default; when on, the encoder runs eagerly.
+enum ProfClass : int { PROF_GEMM = 0, PROF_ATTN, PROF_LN, PROF_PRE, PROF_POOL, PROF_ASSOC, PROF_FUSE, PROF_QUERY, PROF_OTHER, PROF_NCLASS };
+bool profiling();
+struct ProfScope {
+  cudaStream_t s;
+  int idx;
+  ProfScope(cudaStream_t stream, int cls, double flops, double bytes);
+  ~ProfScope();
+};
+
 }  // namespace ovo

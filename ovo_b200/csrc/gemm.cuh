@@ -37,6 +37,7 @@ struct EpiParams {
   // EPI_PATCH
   const float* pos = nullptr;  // [1 + patches, width]
   int patches = 0;             // patches per image (576)
+  int prof_cls = 0;            // profiling class of this launch (common.cuh ProfClass; host side only)
 };
 
 constexpr int kBM = 128;

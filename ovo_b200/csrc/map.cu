@@ -376,14 +376,15 @@ __global__ void f32_to_bf16_pad_kernel(const float* __restrict__ src, int rows, 
 }
 
 // one warp per (instance, query) dot product in f32, lanes stride the feature dimension
-__global__ void query_instances_kernel(const float* __restrict__ bank, int I, int D, const float* __restrict__ text, int Q,
-                                       float* __restrict__ out) {
+__global__ void query_instances_kernel(const float* __restrict__ bank, const int32_t* __restrict__ rows, int I, int D,
+                                       const float* __restrict__ text, int Q, float* __restrict__ out) {
   const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (w >= I * Q) return;
   const int i = w / Q, q = w - i * Q;
+  const size_t br = rows ? static_cast<size_t>(rows[i]) : static_cast<size_t>(i);
   float acc = 0.f;
-  for (int d = lane; d < D; d += 32) acc = fmaf(bank[static_cast<size_t>(i) * D + d], text[static_cast<size_t>(q) * D + d], acc);
+  for (int d = lane; d < D; d += 32) acc = fmaf(bank[br * D + d], text[static_cast<size_t>(q) * D + d], acc);
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
   if (lane == 0) out[w] = acc;
 }
@@ -405,6 +406,87 @@ __global__ void classify_kernel(const float* __restrict__ sim, long long n, int 
   const bool keep = best > th;
   cls[i] = keep ? bi : -1;
   conf[i] = keep ? best : 0.f;
+}
+
+
+// ------------------------------------------------------------------------------------------ mask merge
+// OVO._fuse_masks_with_same_ins_id (ovo.py:284-324): masks voted to the same instance are OR-ed into one row;
+// out[r] = OR of the masks m with group[m] == r; areas[r] = popcount(out[r]).  One thread per 4 pixels.
+__global__ void merge_masks_kernel(const uint8_t* __restrict__ masks, int M, int npix4, const int32_t* __restrict__ group,
+                                   int R, uint8_t* __restrict__ out, int32_t* __restrict__ areas) {
+  const int r = blockIdx.y;
+  int local = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < npix4; i += gridDim.x * blockDim.x) {
+    uint32_t acc = 0;
+    for (int m = 0; m < M; ++m)
+      if (group[m] == r) acc |= reinterpret_cast<const uint32_t*>(masks + static_cast<size_t>(m) * npix4 * 4)[i];
+    // normalise every non-zero byte to 1
+    acc = ((acc | (acc >> 1) | (acc >> 2) | (acc >> 3) | (acc >> 4) | (acc >> 5) | (acc >> 6) | (acc >> 7)) & 0x01010101u);
+    reinterpret_cast<uint32_t*>(out + static_cast<size_t>(r) * npix4 * 4)[i] = acc;
+    local += __popc(acc);
+  }
+  for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+  if ((threadIdx.x & 31) == 0 && local) atomicAdd(&areas[r], local);
+}
+
+// ------------------------------------------------------------------------------------------ view fusion
+// Instance3D.update_clip (instance3d.py:157-189) for a batch of instances: instance j fuses the descriptor rows
+// store[idx[off[j] .. off[j+1])] with mode 0 = avg_pooling (:19-21), 1 = l1_medoid (:9-12), 2 = cossim_medoid
+// (:14-17) into bank[out_rows[j]]; chosen[j] = medoid index (0 for avg).  One block per instance.
+__global__ void __launch_bounds__(256)
+    fuse_views_kernel(const float* __restrict__ store, int D, const int32_t* __restrict__ idx, const int32_t* __restrict__ off,
+                      int mode, float* __restrict__ bank, const int32_t* __restrict__ out_rows, int32_t* __restrict__ chosen) {
+  const int j = blockIdx.x;
+  const int beg = off[j], n = off[j + 1] - beg;
+  if (n <= 0) return;
+  float* dst = bank + static_cast<size_t>(out_rows[j]) * D;
+  __shared__ float s_red[8];
+  __shared__ float s_best;
+  __shared__ int s_besti;
+  if (mode == 0 || n == 1) {
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+      float acc = 0.f;
+      for (int i = 0; i < n; ++i) acc += store[static_cast<size_t>(idx[beg + i]) * D + d];
+      dst[d] = n == 1 ? acc : acc / static_cast<float>(n);
+    }
+    if (threadIdx.x == 0 && chosen) chosen[j] = 0;
+    return;
+  }
+  if (threadIdx.x == 0) { s_best = mode == 1 ? INFINITY : -INFINITY; s_besti = 0; }
+  __syncthreads();
+  for (int a = 0; a < n; ++a) {
+    const float* ra = store + static_cast<size_t>(idx[beg + a]) * D;
+    float score = 0.f;  // sum over b of L1(a,b)  or  sum over b of cos(a,b)
+    for (int b = 0; b < n; ++b) {
+      const float* rb = store + static_cast<size_t>(idx[beg + b]) * D;
+      float p0 = 0.f, p1 = 0.f, p2 = 0.f;
+      for (int d = threadIdx.x; d < D; d += blockDim.x) {
+        const float x = ra[d], y = rb[d];
+        if (mode == 1) p0 += fabsf(x - y);
+        else { p0 += x * y; p1 += x * x; p2 += y * y; }
+      }
+      float v[3] = {p0, p1, p2};
+      for (int t = 0; t < 3; ++t) {
+        float r = v[t];
+        for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = r;
+        __syncthreads();
+        r = 0.f;
+        for (int w = 0; w < (blockDim.x >> 5); ++w) r += s_red[w];
+        v[t] = r;
+      }
+      score += mode == 1 ? v[0] : v[0] / fmaxf(sqrtf(v[1]) * sqrtf(v[2]), 1e-8f);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      if ((mode == 1 && score < s_best) || (mode == 2 && score > s_best)) { s_best = score; s_besti = a; }
+    }
+    __syncthreads();
+  }
+  const float* src = store + static_cast<size_t>(idx[beg + s_besti]) * D;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) dst[d] = src[d];
+  if (threadIdx.x == 0 && chosen) chosen[j] = s_besti;
 }
 
 }  // namespace ovo
@@ -518,6 +600,7 @@ int ovo_map_associate(ovo_map_t* m, const float* xyz_dev, int32_t* ins_ids_dev, 
   OVO_CUDA(cudaMemsetAsync(m->votes, 0, votes_need * sizeof(int32_t), stream));
   OVO_CUDA(cudaMemsetAsync(m->area, 0, (n_masks + 1) * sizeof(int32_t), stream));
 
+  ovo::ProfScope prof(stream, ovo::PROF_ASSOC, 0.0, static_cast<double>(N) * 20 + static_cast<double>(f->h) * f->w * 8);
   const int sms = ovo::num_sms();
   // frustum from the RAW depth (ovo.py:209), match against the filtered depth (ovo.py:213-216)
   ovo::depth_minmax_kernel<<<sms, 256, 0, stream>>>(f->depth_dev, npix, m->geom);
@@ -584,6 +667,7 @@ int ovo_map_fuse_dense(ovo_map_t* m, int kf_slot, void* bank_dev, int32_t* count
   const int n = m->slot_n[kf_slot];
   if (n == 0) return OVO_OK;
   const int blocks = std::min(ovo::ceil_div(n, 8), ovo::num_sms() * 8);
+  ovo::ProfScope prof(static_cast<cudaStream_t>(stream), ovo::PROF_FUSE, 0.0, static_cast<double>(n) * (4.0 * D + 12));
   ovo::fuse_dense_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       m->slot_list[kf_slot], n, static_cast<__nv_bfloat16*>(bank_dev), counts_dev, D, feats_dev, mask_row_dev);
   OVO_CHECK_LAUNCH();
@@ -614,16 +698,40 @@ int ovo_query_dense(ovo_map_t* m, const void* bank_dev, int64_t N, int D, const 
     ovo::EpiParams ep;
     ep.out = out_dev + q0;
     ep.ldo = Q;
+    ep.prof_cls = ovo::PROF_QUERY;
     OVO_TRY(ovo::launch_gemm(ovo::EPI_F32, static_cast<const __nv_bfloat16*>(bank_dev), D, m->text_bf16, D,
                              static_cast<int>(N), qn, D, ep, stream, qpad));
   }
   return OVO_OK;
 }
 
-int ovo_query_instances(const float* bank_dev, int I, int D, const float* text_dev, int Q, float* out_dev, void* stream) {
+int ovo_query_instances(const float* bank_dev, const int32_t* rows_dev, int I, int D, const float* text_dev, int Q,
+                        float* out_dev, void* stream) {
   OVO_REQUIRE(bank_dev && text_dev && out_dev && I > 0 && D > 0 && Q > 0, "ovo_query_instances: bad arguments");
   const long long threads = static_cast<long long>(I) * Q * 32;
-  ovo::query_instances_kernel<<<ovo::ceil_div(threads, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(bank_dev, I, D, text_dev, Q, out_dev);
+  ovo::query_instances_kernel<<<ovo::ceil_div(threads, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(bank_dev, rows_dev, I, D, text_dev, Q, out_dev);
+  OVO_CHECK_LAUNCH();
+  return OVO_OK;
+}
+
+int ovo_merge_masks(const uint8_t* masks_dev, int M, int H, int W, const int32_t* group_dev, int R, uint8_t* out_dev,
+                    int32_t* areas_dev, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  OVO_REQUIRE(masks_dev && group_dev && out_dev && areas_dev && M > 0 && R > 0, "ovo_merge_masks: bad arguments");
+  OVO_REQUIRE((static_cast<long long>(H) * W) % 4 == 0 && (reinterpret_cast<uintptr_t>(masks_dev) & 3) == 0 &&
+                  (reinterpret_cast<uintptr_t>(out_dev) & 3) == 0, "ovo_merge_masks: H*W must be a multiple of 4 and buffers 4-byte aligned");
+  const int npix4 = H * W / 4;
+  OVO_CUDA(cudaMemsetAsync(areas_dev, 0, R * sizeof(int32_t), stream));
+  ovo::merge_masks_kernel<<<dim3(std::min(ovo::ceil_div(npix4, 256), 64), R), 256, 0, stream>>>(masks_dev, M, npix4, group_dev, R, out_dev, areas_dev);
+  OVO_CHECK_LAUNCH();
+  return OVO_OK;
+}
+
+int ovo_fuse_views(const float* store_dev, int D, const int32_t* idx_dev, const int32_t* off_dev, int n_instances, int mode,
+                   float* bank_dev, const int32_t* out_rows_dev, int32_t* chosen_dev, void* stream) {
+  OVO_REQUIRE(store_dev && idx_dev && off_dev && bank_dev && out_rows_dev && D > 0 && mode >= 0 && mode <= 2, "ovo_fuse_views: bad arguments");
+  if (n_instances <= 0) return OVO_OK;
+  ovo::fuse_views_kernel<<<n_instances, 256, 0, static_cast<cudaStream_t>(stream)>>>(store_dev, D, idx_dev, off_dev, mode, bank_dev, out_rows_dev, chosen_dev);
   OVO_CHECK_LAUNCH();
   return OVO_OK;
 }

@@ -97,14 +97,31 @@ class SemanticMap:
         check(self.lib.ovo_query_dense(self.handle, ptr(bank), N, D, ptr(text), Q, ptr(out), stream_ptr()), "ovo_query_dense")
         return out
 
-    def query_instances(self, bank: torch.Tensor, text: torch.Tensor) -> torch.Tensor:
-        """clip_cosine_similarity over the instance bank in f32: [I,D] x [Q,D] -> [I,Q]."""
+    def query_instances(self, bank: torch.Tensor, text: torch.Tensor, rows: torch.Tensor | None = None) -> torch.Tensor:
+        """clip_cosine_similarity over the instance bank in f32: bank[rows] [I,D] x [Q,D] -> [I,Q]."""
         bank = bank.to(self.device, torch.float32).contiguous()
         text = text.to(self.device, torch.float32).contiguous()
-        out = torch.empty(bank.shape[0], text.shape[0], device=self.device, dtype=torch.float32)
-        check(self.lib.ovo_query_instances(ptr(bank), bank.shape[0], bank.shape[1], ptr(text), text.shape[0], ptr(out),
+        n = bank.shape[0] if rows is None else rows.shape[0]
+        out = torch.empty(n, text.shape[0], device=self.device, dtype=torch.float32)
+        check(self.lib.ovo_query_instances(ptr(bank), ptr(rows), n, bank.shape[1], ptr(text), text.shape[0], ptr(out),
                                            stream_ptr()), "ovo_query_instances")
         return out
+
+    def merge_masks(self, masks: torch.Tensor, group: torch.Tensor, n_out: int):
+        """_fuse_masks_with_same_ins_id: masks uint8 [M,H,W], group i32 [M] -> (out uint8 [R,H,W], areas i32 [R])."""
+        assert masks.dtype == torch.uint8 and masks.is_contiguous() and group.dtype == torch.int32
+        M, H, W = masks.shape
+        out = torch.empty(n_out, H, W, device=self.device, dtype=torch.uint8)
+        areas = torch.empty(n_out, device=self.device, dtype=torch.int32)
+        check(self.lib.ovo_merge_masks(ptr(masks), M, H, W, ptr(group), n_out, ptr(out), ptr(areas), stream_ptr()), "ovo_merge_masks")
+        return out, areas
+
+    def fuse_views(self, store: torch.Tensor, idx: torch.Tensor, off: torch.Tensor, mode: int, bank: torch.Tensor,
+                   out_rows: torch.Tensor, chosen: torch.Tensor | None = None):
+        """Instance3D.update_clip batched: see ovo_fuse_views in include/ovo_b200.h."""
+        assert store.dtype == torch.float32 and bank.dtype == torch.float32 and idx.dtype == torch.int32
+        check(self.lib.ovo_fuse_views(ptr(store), store.shape[1], ptr(idx), ptr(off), out_rows.shape[0], mode, ptr(bank),
+                                      ptr(out_rows), ptr(chosen), stream_ptr()), "ovo_fuse_views")
 
     def classify(self, sim: torch.Tensor, th: float = 0.0):
         """OVO.classify_instances' argmax + threshold (ovo.py:486-491)."""

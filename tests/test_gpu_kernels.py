@@ -1,0 +1,187 @@
+"""GPU parity of the map / query kernels against the CPU oracle and the reference's golden vectors.
+Everything goes through the C ABI (ovo_b200._lib -> libovo_b200.so)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import fusion as OF, gen_golden as GG
+from ovo_b200 import synth
+
+
+@pytest.fixture(scope="module")
+def sm():
+    from ovo_b200.map import SemanticMap
+    return SemanticMap()
+
+
+def _dev(*arrs):
+    return [torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in arrs]
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (300, 200, 192), (1154, 3072, 1024), (77, 1024, 4096), (5000, 20, 1024)])
+def test_gemm_matches_f32(M, N, K):
+    """tcgen05 GEMM (every N-tile width) vs an f32 matmul of the same bf16 operands; tolerance 1e-5 relative-L2."""
+    from ovo_b200.encoder import gemm_bf16
+    torch.manual_seed(0)
+    A = torch.randn(M, K, device="cuda").bfloat16()
+    B = torch.randn(N, K, device="cuda").bfloat16()
+    bias = torch.randn(N, device="cuda")
+    ref = A.float() @ B.float().T + bias
+    for bn in (0, 32, 64, 128, 256):
+        out = gemm_bf16(A, B, bias, force_bn=bn)
+        assert ((out - ref).norm() / ref.norm()).item() < 1e-5, bn
+
+
+@pytest.mark.parametrize("N,Q", [(1, 1), (129, 20), (70000, 21), (20000, 200), (3000, 300)])
+def test_query_dense(sm, N, Q):
+    """Dense cosine query == f32 matmul of the bf16 bank with the bf16-rounded text bank (tolerance 1e-5 rel-L2),
+    and within 1e-3 absolute of the unrounded f32 text bank."""
+    torch.manual_seed(1)
+    bank = torch.nn.functional.normalize(torch.randn(N, 1024, device="cuda"), dim=-1).bfloat16()
+    text = torch.nn.functional.normalize(torch.randn(Q, 1024, device="cuda"), dim=-1)
+    out = sm.query_dense(bank, text)
+    ref = bank.float() @ text.bfloat16().float().T
+    assert ((out - ref).norm() / ref.norm()).item() < 1e-5
+    assert (out - bank.float() @ text.T).abs().max().item() < 1e-3
+    cls, conf = sm.classify(out, 0.0)
+    mx, am = out.max(1)
+    assert (cls.long() == torch.where(mx > 0, am, -1)).all()
+    assert torch.equal(conf, torch.where(mx > 0, mx, torch.zeros_like(mx)))
+
+
+def test_query_linearity_full_size(sm):
+    """Size-independent property at BASELINE size (2M points, Q=20): the query is linear in the text bank."""
+    N = 2_000_000
+    g = torch.Generator(device="cuda").manual_seed(2)
+    bank = torch.randn(N, 1024, device="cuda", generator=g).bfloat16()
+    t1 = torch.randn(20, 1024, device="cuda", generator=g).bfloat16().float()
+    t2 = torch.randn(20, 1024, device="cuda", generator=g).bfloat16().float()
+    a, b = sm.query_dense(bank, t1), sm.query_dense(bank, t2)
+    c = sm.query_dense(bank, (t1 + t2) / 2)        # exactly representable? no -> compare with tolerance
+    ref = (a + b) / 2
+    assert ((c - ref).norm() / ref.norm()).item() < 5e-3
+    idx = torch.randint(0, N, (4096,), device="cuda")
+    assert ((a[idx] - bank[idx].float() @ t1.T).abs().max().item()) < 2e-2 * 32   # spot check against f32
+
+
+def test_query_instances_and_fuse_views(sm):
+    torch.manual_seed(3)
+    store = torch.randn(40, 256, device="cuda")
+    bank = torch.zeros(8, 256, device="cuda")
+    idx = torch.tensor([0, 5, 9, 3, 7, 7, 8, 2, 1], dtype=torch.int32, device="cuda")
+    off = torch.tensor([0, 3, 4, 9], dtype=torch.int32, device="cuda")
+    rows = torch.tensor([2, 0, 5], dtype=torch.int32, device="cuda")
+    for mode in (0, 1, 2):
+        chosen = torch.zeros(3, dtype=torch.int32, device="cuda")
+        sm.fuse_views(store, idx, off, mode, bank, rows, chosen)
+        for j in range(3):
+            clips = store[idx[off[j]:off[j + 1]].long()]
+            if mode == 0 or clips.shape[0] == 1:
+                ref = clips.mean(0)
+            elif mode == 1:
+                ref = clips[torch.abs(clips[None] - clips[:, None]).sum((1, 2)).argmin()]
+            else:
+                ref = clips[torch.cosine_similarity(clips[None], clips[:, None], dim=-1).sum(-1).argmax()]
+            assert (bank[rows[j]] - ref).abs().max().item() < 1e-5, (mode, j)
+    text = torch.randn(5, 256, device="cuda")
+    out = sm.query_instances(bank, text, rows)
+    assert (out - bank[rows.long()] @ text.T).abs().max().item() < 1e-4
+
+
+def test_merge_masks(sm):
+    rng = np.random.default_rng(0)
+    masks = (rng.random((6, 48, 64)) > 0.7)
+    group = np.array([0, 1, 0, -1, 2, 1], np.int32)
+    out, areas = sm.merge_masks(*_dev(masks.astype(np.uint8), group), 3)
+    for r in range(3):
+        ref = np.any(masks[group == r], axis=0)
+        assert (out[r].cpu().numpy().astype(bool) == ref).all() and int(areas[r]) == ref.sum()
+
+
+@pytest.mark.parametrize("fid,N,fv", GG.ASSOC_CASES)
+def test_association_matches_reference_golden(sm, golden_dir, fid, N, fv):
+    """CUDA association == the reference's own geometry functions (golden) bit for bit."""
+    g = np.load(os.path.join(golden_dir, "assoc.npz"))
+    K = synth.intrinsics(); c2w = synth.pose(fid); d = synth.depth_map(frame_id=fid)
+    seg, _ = synth.grid_masks()
+    xyz, ids, ins = synth.point_map(N, d, K, c2w, seed=fid, frac_visible=fv)
+    xyz_d, ins_d, d_d, seg_d = _dev(xyz, ins, d, seg)
+    assert (np.packbits(sm.depth_filter(d_d).cpu().numpy() == -1) == g[f"depth_rejected_{fid}"]).all()
+    votes, n_matched, nxt = sm.associate(xyz_d, ins_d, d_d, seg_d, c2w, K, 0, kf_slot=1)
+    ref_seg = g[f"seg_of_pt_{fid}"].astype(np.int32)
+    assert n_matched == (ref_seg > -2).sum()
+    pairs = sm.matches(1, int(votes["n_matched"].sum())).cpu().numpy()
+    mine = np.full(N, -2, np.int32)
+    mine[ref_seg == -1] = -1                         # matched but outside every mask: not listed
+    mine[pairs[:, 0]] = pairs[:, 1]
+    assert (mine == ref_seg).all()
+    new, rows, nxt_o = OF.track(ins, ref_seg, seg, 100, 0)
+    assert nxt == nxt_o and (ins_d.cpu().numpy() == new).all()
+    for k in votes:
+        assert (votes[k] == np.array([r[k] for r in rows])).all(), k
+
+
+@pytest.mark.parametrize("N,track_th,ratio", [(0, 100, ()), (1, 0, ()), (257, 3, ()), (150000, 100, ()),
+                                              (90000, 50, (1.0, 1.0, 0)), (60000, 100, (2.0, 2.0, 4))])
+def test_association_multi_keyframe_vs_oracle(sm, N, track_th, ratio):
+    """Four keyframes with changing masks/poses: votes, new ids, ties and the dense running mean are
+    bit-exact against oracle/fusion.py, including empty / tiny maps and the rgb-depth ratio fix-up."""
+    K = synth.intrinsics()
+    h, w = 480, 640
+    H, W = (h, w) if not ratio else (int((h + 2 * ratio[2]) * ratio[0]), int((w + 2 * ratio[2]) * ratio[1]))
+    d0 = synth.depth_map(frame_id=0)
+    xyz, ids, ins = synth.point_map(max(N, 1), d0, K, synth.pose(0), seed=5, frac_visible=0.6)
+    xyz, ins = xyz[:N], ins[:N]
+    xyz_d, ins_d = _dev(xyz, ins)
+    D = 64
+    bank = torch.zeros(max(N, 1), D, device="cuda", dtype=torch.bfloat16)
+    counts = torch.zeros(max(N, 1), device="cuda", dtype=torch.int32)
+    bank_o = np.zeros((max(N, 1), D), np.float32); counts_o = np.zeros(max(N, 1), np.int32)
+    next_id = 0
+    for i in range(4):
+        fid = 4 * i
+        c2w = synth.pose(fid); d = synth.depth_map(frame_id=fid)
+        seg, bm = synth.grid_masks(H, W, rows=(6 if i % 2 == 0 else 3), cols=(8 if i % 2 == 0 else 5))
+        d_d, seg_d = _dev(d, seg)
+        votes, nm, nxt = sm.associate(xyz_d, ins_d, d_d, seg_d, c2w, K, next_id, track_th=track_th,
+                                      rgb_depth_ratio=ratio, kf_slot=i)
+        w2c = torch.linalg.inv(torch.from_numpy(c2w)).numpy()
+        seg_of_pt, _ = OF.associate(xyz, ins, d, seg, c2w, w2c, K, 0.05, True, ratio) if N else (np.zeros(0, np.int32), None)
+        new, rows, nxt_o = OF.track(ins, seg_of_pt, seg, track_th, next_id)
+        assert nm == (seg_of_pt > -2).sum() and nxt == nxt_o
+        assert (ins_d.cpu().numpy() == new).all()
+        for k in votes:
+            assert (votes[k] == np.array([r[k] for r in rows])).all(), (i, k)
+        order, fused, mask_row = OF.fuse_masks(bm, rows)
+        feats = torch.randn(max(len(order), 1), D, generator=torch.Generator().manual_seed(i))
+        sm.fuse_dense(i, bank, counts, feats.cuda(), torch.from_numpy(mask_row).cuda())
+        pts = np.nonzero(seg_of_pt >= 0)[0]
+        rr = mask_row[seg_of_pt[pts]]
+        for p, r_ in zip(pts[rr >= 0], rr[rr >= 0]):
+            c = counts_o[p] + 1
+            upd = bank_o[p] + (feats[r_].numpy() - bank_o[p]) / np.float32(c)
+            bank_o[p] = torch.from_numpy(upd).bfloat16().float().numpy()
+            counts_o[p] = c
+        assert (counts.cpu().numpy() == counts_o).all()
+        assert (bank.float().cpu().numpy() == bank_o).all()
+        ins, next_id = new, nxt_o
+
+
+def test_association_idempotent_at_full_size(sm):
+    """BASELINE-size property (2M points): a second pass over the same keyframe creates no instance, moves no
+    point, and every mask now votes for the instance it created."""
+    K = synth.intrinsics(); d = synth.depth_map(); N = 2_000_000
+    xyz, ids, ins = synth.point_map(N, d, K, synth.pose(0), seed=0)
+    seg, _ = synth.grid_masks()
+    xyz_d, ins_d, d_d, seg_d = _dev(xyz, ins, d, seg)
+    v1, n1, nxt1 = sm.associate(xyz_d, ins_d, d_d, seg_d, synth.pose(0), K, 0, kf_slot=0)
+    after1 = ins_d.clone()
+    v2, n2, nxt2 = sm.associate(xyz_d, ins_d, d_d, seg_d, synth.pose(0), K, nxt1, kf_slot=1)
+    assert n1 == n2 and nxt2 == nxt1 and torch.equal(after1, ins_d)
+    assert (v2["n_unassigned"] == 0).all() and (v2["is_new"] == 0).all()
+    assert (v2["ins_id"] == v1["ins_id"]).all() and (v2["n_assigned"] == v1["n_matched"]).all()
+    assert int((ins_d >= 0).sum()) == int(v1["n_matched"][v1["ins_id"] >= 0].sum())

@@ -1,0 +1,133 @@
+"""The drop-in `OVO` class on the GPU reproduces what the reference's OVO class produced on the same
+4-keyframe replay (tests/golden/ovo_run.npz): integer outputs exactly, descriptors within tolerance."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import gen_golden as GG
+
+
+class _Logger:
+    def log_ovo_stats(self, *a, **k):
+        pass
+
+
+class _TokTokenizer:            # the fixture's queries are token-id rows (tiny vocabulary)
+    def __call__(self, phrase):
+        return torch.from_numpy(GG.QUERIES_TOK[int(phrase)][None])
+
+
+def _build(tmp_path, dense=False, fusion="avg_pooling"):
+    from ovo_b200 import OVO, CLIPGenerator
+    from ovo_b200.encoder import random_state_dict
+    K, xyz, ids, ins, frames = GG.ovo_inputs()
+    mdir = tmp_path / "masks" / "scene"
+    mdir.mkdir(parents=True)
+    for f in frames:
+        np.save(mdir / f"{f['frame_id']:04d}_seg_map_default.npy", f["seg"])
+        np.save(mdir / f"{f['frame_id']:04d}_bmap_default.npy", f["bm"])
+    cfg = GG.tiny_cfg()
+    config = GG.ovo_config(str(tmp_path / "masks"))
+    config["clip"]["fusion"] = fusion
+    config["dense_map"] = dense
+    clip = CLIPGenerator(config["clip"], state_dict=random_state_dict(cfg, seed=0), tokenizer=_TokTokenizer(), encoder_config=cfg)
+    ovo = OVO(config, _Logger(), scene_name="scene", cam_intrinsics=torch.from_numpy(K), clip_generator=clip)
+    return ovo, K, xyz, ids, ins, frames
+
+
+def _replay(ovo, xyz, ids, ins, frames, check=None):
+    pts, pids, pins = (torch.from_numpy(a).cuda() for a in (xyz, ids, ins))
+    for i, f in enumerate(frames):
+        upd = ovo.detect_and_track_objects((f["frame_id"], f["image"], f["depth"], ()), (pts, pids, pins), torch.from_numpy(f["c2w"]))
+        assert upd is not None and upd.dtype == torch.int32 and upd.shape == pins.shape
+        if check:
+            check(i, upd, ovo)
+        pins = upd
+        ovo.compute_semantic_info()
+    ovo.complete_semantic_info()
+    return pins
+
+
+def test_ovo_matches_reference_run(tmp_path, golden_dir):
+    g = np.load(os.path.join(golden_dir, "ovo_run.npz"))
+    ovo, K, xyz, ids, ins, frames = _build(tmp_path)
+
+    def check(i, upd, o):
+        assert (upd.cpu().numpy() == g[f"ins_ids_{i}"]).all()                       # bit-exact ids
+        assert o.keyframes_queue[-1][0] == g[f"matched_ins_{i}"].tolist()            # first-vote order
+        assert (o.keyframes_queue[-1][1].sum((1, 2)).cpu().numpy() == g[f"maps_area_{i}"]).all()
+
+    _replay(ovo, xyz, ids, ins, frames, check)
+    assert list(ovo.objects.keys()) == g["object_ids"].tolist()
+    assert [len(o.kfs_ids) for o in ovo.objects.values()] == g["object_n_kfs"].tolist()
+    clips = ovo.get_objs_clips().cpu()
+    ref = torch.from_numpy(g["object_clips"])
+    assert ((clips - ref).norm() / ref.norm()).item() < 1e-2
+    assert (1 - torch.nn.functional.cosine_similarity(clips, ref, dim=-1)).max().item() < 1e-3
+    q = ovo.query(["0", "1", "2"]).cpu().numpy()
+    assert q.shape == g["query"].shape                                              # [n_obj, n_query]
+    assert np.abs(q - g["query"]).max() < 2e-2
+    cls = ovo.classify_instances(["0", "1", "2"], template="{}", th=0.0)
+    agree = (cls["classes"] == g["classes"]).mean()
+    margin = np.sort(g["query"], axis=1)
+    confident = (margin[:, -1] - margin[:, -2]) > 4e-2
+    assert (cls["classes"][confident] == g["classes"][confident]).all() and agree > 0.8
+    # checkpoint keys are the reference's
+    assert sorted(ovo.capture_dict(False).keys()) == g["capture_keys"].tolist()
+    for o in ovo.objects.values():                                                  # shape quirk kept
+        assert o.clip_feature.shape in [(1, 64), (64,)] and (o.clip_feature.dim() == 2) == (len(o.kfs_ids) > 1 and o.clip_feature_kf is None)
+
+
+def test_capture_restore_roundtrip(tmp_path):
+    ovo, K, xyz, ids, ins, frames = _build(tmp_path)
+    _replay(ovo, xyz, ids, ins, frames)
+    d = ovo.capture_dict(False)
+    q0 = ovo.query(["0", "1"]).cpu()
+    from ovo_b200 import OVO
+    other = OVO(ovo.config, _Logger(), eval=True, clip_generator=ovo.clip_generator)
+    other.restore_dict(d, False)
+    assert list(other.objects.keys()) == list(ovo.objects.keys())
+    assert torch.equal(other.query(["0", "1"]).cpu(), q0)
+
+
+def test_dense_mode_consistent_with_instance_mode(tmp_path):
+    """SURVEY §0 consistency rule: a point's dense feature is the running mean of the descriptors of the masks it
+    fell into; for a point seen in exactly the keyframes that formed its instance's descriptor, the two agree."""
+    ovo, K, xyz, ids, ins, frames = _build(tmp_path, dense=True)
+    final = _replay(ovo, xyz, ids, ins, frames)
+    counts = ovo._dense_counts[: xyz.shape[0]]
+    assert int(counts.max()) <= len(frames) and int((counts > 0).sum()) > 1000
+    sim_pts = ovo.query_points(["0", "1", "2"], n_points=xyz.shape[0])
+    assert sim_pts.shape == (xyz.shape[0], 3)
+    assert (sim_pts[counts == 0] == 0).all()                     # unseen points carry a zero feature
+    # a point observed once carries exactly (bf16-rounded) the descriptor of the mask it fell into
+    once = torch.nonzero(counts == 1).flatten()[:200]
+    store = ovo._store[: ovo._store_n]
+    d = torch.cdist(ovo._dense_bank[once].float(), store.bfloat16().float())
+    assert d.min(dim=1).values.max().item() < 1e-6
+    # points seen in every keyframe of a two-view instance whose descriptor used both views
+    bank = ovo.get_objs_clips()
+    checked = 0
+    for j, o in enumerate(ovo.objects.values()):
+        used = [kf for kf in o.kfs_ids if kf in ovo.keyframes["ins_descriptors"] and o.id in ovo.keyframes["ins_descriptors"][kf]]
+        mean_all = torch.stack([ovo._store[ovo.keyframes["ins_descriptors"][kf][o.id]] for kf in used]).mean(0)
+        pts = torch.nonzero((final == o.id) & (counts == len(used))).flatten()[:50]
+        if len(pts) == 0:
+            continue
+        close = (ovo._dense_bank[pts].float() - mean_all).abs().max(dim=1).values < 2e-2
+        checked += int(close.sum())
+    assert checked > 50
+
+
+@pytest.mark.parametrize("fusion", ["l1_medoid", "cossim_medoid"])
+def test_medoid_fusions_pick_a_view(tmp_path, fusion):
+    ovo, K, xyz, ids, ins, frames = _build(tmp_path, fusion=fusion)
+    _replay(ovo, xyz, ids, ins, frames)
+    store = ovo._store[: ovo._store_n]
+    for o in list(ovo.objects.values())[:10]:
+        f = o.clip_feature.reshape(-1)
+        assert (store - f).abs().sum(1).min().item() == 0.0         # the fused descriptor IS one of the views

@@ -1,0 +1,66 @@
+"""Host-side logic that needs no GPU: Instance3D view selection, tokenizer, synthetic scenes, sharding."""
+import numpy as np
+import pytest
+import torch
+
+from ovo_b200.instance3d import Instance3D
+from ovo_b200 import synth
+
+
+def test_instance3d_topk_and_to_update():
+    Instance3D.n_top_kf = 2
+    o = Instance3D(3, kf_id=0, points_ids=[1, 2], mask_area=50)
+    assert o.to_update and o.top_kf == [(50, 0)] and o.kfs_ids == [0] and o.points_ids == [1, 2]
+    o.to_update = False
+    o.update([], 1, 80)
+    assert o.to_update and sorted(o.top_kf) == [(50, 0), (80, 1)]
+    o.to_update = False
+    o.update([], 2, 10)                       # smaller than both: pushed and popped straight away
+    assert not o.to_update and not o.is_top_kf(2) and o.kfs_ids == [0, 1, 2]
+    o.update([], 3, 60)                       # evicts keyframe 0
+    assert o.to_update and not o.is_top_kf(0) and o.is_top_kf(3)
+    o.to_update = False
+    o.add_top_kf(3, 55)                       # known keyframe, smaller area: nothing changes
+    assert not o.to_update
+    o.add_top_kf(3, 99)
+    assert o.to_update and (99, 3) in o.top_kf
+    descs = {1: {3: "d1"}, 3: {3: "d3"}}
+    assert o.views_to_fuse(descs) == ["d3", "d1"]          # area-descending (heapq.nlargest)
+    assert not o.to_update and o.views_to_fuse(descs) is None
+    assert o.views_to_fuse(descs, force_update=True) == ["d3", "d1"]
+    Instance3D.n_top_kf = 0
+    p = Instance3D(4, kf_id=0, points_ids=[], mask_area=5)
+    assert p.to_update and p.top_kf == []                  # n_top_kf <= 0: heap stays empty, flag raised
+    assert p.views_to_fuse({0: {4: "x"}}) == ["x"]
+    Instance3D.n_top_kf = 10000
+
+
+def test_instance3d_export_restore_keys():
+    o = Instance3D(7, kf_id=2, points_ids=[5], mask_area=9)
+    o.clip_feature = torch.ones(4)
+    d = o.export(True)
+    assert set(d) == {"ins3d_7_clip_feature", "ins3d_7_clip_feature_kf", "ins3d_7_keyframes_ids", "ins3d_7_points_ids", "ins3d_7_top_kfs"}
+    q = Instance3D(7)
+    q.restore(d, True)
+    assert q.kfs_ids == [2] and q.points_ids == [5] and not q.to_update
+
+
+def test_tokenizer_matches_known_answer():
+    from ovo_b200.tokenizer import BPETokenizer, find_vocab
+    if find_vocab() is None:
+        pytest.skip("CLIP BPE vocabulary not reachable (ships with the reference)")
+    t = BPETokenizer(context_length=32)
+    ids = t(["a chair"])[0]
+    assert ids[:4].tolist() == [49406, 320, 4269, 49407] and int(ids[4:].sum()) == 0
+    long = t(["word " * 100])[0]
+    assert long[-1].item() == 49407 and long[0].item() == 49406
+
+
+def test_synth_scene_is_well_formed():
+    K = synth.intrinsics()
+    d = synth.depth_map()
+    assert d.min() == 0 and d[d > 0].min() < d.max()            # non-degenerate frustum
+    seg, bm = synth.grid_masks()
+    assert seg.max() + 1 == bm.shape[0] == 48 and (seg == -1).any()
+    xyz, ids, ins = synth.point_map(1000, d, K, synth.pose(0))
+    assert xyz.shape == (1000, 3) and xyz.dtype == np.float32 and (ins == -1).all()
