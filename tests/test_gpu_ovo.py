@@ -107,7 +107,7 @@ def test_dense_mode_consistent_with_instance_mode(tmp_path):
     # a point observed once carries exactly (bf16-rounded) the descriptor of the mask it fell into
     once = torch.nonzero(counts == 1).flatten()[:200]
     store = ovo._store[: ovo._store_n]
-    d = torch.cdist(ovo._dense_bank[once].float(), store.bfloat16().float())
+    d = torch.cdist(ovo._dense_bank[once].float(), store.bfloat16().float(), compute_mode="donot_use_mm_for_euclid_dist")
     assert d.min(dim=1).values.max().item() < 1e-6
     # points seen in every keyframe of a two-view instance whose descriptor used both views
     bank = ovo.get_objs_clips()
