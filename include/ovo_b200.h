@@ -226,6 +226,10 @@ int ovo_classify(const float* sim_dev, int64_t n, int Q, float th, int32_t* cls_
 void ovo_profile_begin(void);
 int ovo_profile_report(int n_classes, float* ms_host, double* flops_host, double* bytes_host, int* counts_host);
 
+/* Tuning aid: thread-block cluster size (TMA multicast of the weight tile) used by the wide GEMM tiles:
+ * 0 = automatic (default), 1, 2 or 4. */
+void ovo_set_gemm_cluster(int cluster_size);
+
 /* Test tap for the GEMM machinery: C[M,N] f32 = A[M,K] bf16 . B[N,K]^T bf16 (+bias f32 [N]). */
 int ovo_gemm_bf16(const void* A_dev, int lda, const void* B_dev, int ldb, int M, int N, int K,
                   const float* bias_dev, float* C_dev, int ldc, int force_bn, void* stream);

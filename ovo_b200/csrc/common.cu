@@ -3,6 +3,7 @@
 #include "gemm.cuh"
 
 #include <cudaTypedefs.h>
+#include <cstdlib>
 #include <mutex>
 #include <vector>
 
@@ -77,37 +78,68 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t
   return OVO_OK;
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, int CS>
 static int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const EpiParams& ep,
                       cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
-  auto kern = gemm_bf16_tn_kernel<BN, EPI>;
+  auto kern = gemm_bf16_tn_kernel<BN, EPI, CS>;
   static bool attr_set = false;
   if (!attr_set) {
     OVO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
-  const int tiles = ceil_div(M, kBM) * ceil_div(N, BN);
-  const int grid = tiles < num_sms() ? tiles : num_sms();
+  const int ctiles = ceil_div(ceil_div(M, kBM), CS) * ceil_div(N, BN);   // cluster tiles
+  const int max_clusters = num_sms() / CS;
+  const int grid = (ctiles < max_clusters ? ctiles : max_clusters) * CS;
   ProfScope prof(stream, ep.prof_cls, 2.0 * M * N * K, 2.0 * (static_cast<double>(M) * K + static_cast<double>(N) * K) + 4.0 * M * N);
-  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, M, N, K, ep);
+  if constexpr (CS == 1) {
+    kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, M, N, K, ep);
+  } else {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CS;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    OVO_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, M, N, K, ep));
+  }
   OVO_CHECK_LAUNCH();
   return OVO_OK;
 }
 
+static int g_gemm_cluster = -1;   // -1 = auto; OVO_B200_GEMM_CLUSTER=1|2|4 forces a cluster size (tuning aid)
+
 template <int EPI>
 static int launch_bn(int bn, const __nv_bfloat16* A, int lda, const __nv_bfloat16* B, int ldb, int M, int N, int K,
                      const EpiParams& ep, cudaStream_t stream) {
+  if (g_gemm_cluster == -1) {
+    const char* e = getenv("OVO_B200_GEMM_CLUSTER");
+    g_gemm_cluster = e ? atoi(e) : 0;
+  }
+  // clusters pay off when there are enough M tiles to share a B tile; the narrow tiles (query, pooling) stay 1-CTA
+  int cs = 1;
+  if (bn >= 128 && ceil_div(M, kBM) >= 2) cs = g_gemm_cluster > 0 ? g_gemm_cluster : 2;
+  if (bn < 128 || ceil_div(M, kBM) < cs) cs = 1;
   CUtensorMap ta, tb;
   OVO_TRY(make_tmap_bf16_2d(&ta, A, M, K, lda, kBM, kBK));
-  OVO_TRY(make_tmap_bf16_2d(&tb, B, N, K, ldb, bn, kBK));
-  switch (bn) {
-    case 32: return launch_one<32, EPI>(ta, tb, M, N, K, ep, stream);
-    case 64: return launch_one<64, EPI>(ta, tb, M, N, K, ep, stream);
-    case 128: return launch_one<128, EPI>(ta, tb, M, N, K, ep, stream);
-    case 256: return launch_one<256, EPI>(ta, tb, M, N, K, ep, stream);
+  OVO_TRY(make_tmap_bf16_2d(&tb, B, N, K, ldb, bn / cs, kBK));
+  switch (bn * 10 + cs) {
+    case 321: return launch_one<32, EPI, 1>(ta, tb, M, N, K, ep, stream);
+    case 641: return launch_one<64, EPI, 1>(ta, tb, M, N, K, ep, stream);
+    case 1281: return launch_one<128, EPI, 1>(ta, tb, M, N, K, ep, stream);
+    case 1282: return launch_one<128, EPI, 2>(ta, tb, M, N, K, ep, stream);
+    case 1284: return launch_one<128, EPI, 4>(ta, tb, M, N, K, ep, stream);
+    case 2561: return launch_one<256, EPI, 1>(ta, tb, M, N, K, ep, stream);
+    case 2562: return launch_one<256, EPI, 2>(ta, tb, M, N, K, ep, stream);
+    case 2564: return launch_one<256, EPI, 4>(ta, tb, M, N, K, ep, stream);
   }
-  return set_error(OVO_E_INVALID, "unsupported BN %d", bn);
+  return set_error(OVO_E_INVALID, "unsupported BN %d / cluster %d", bn, cs);
 }
 
 // Pick the N tile: the widest tile that does not waste more SM-rounds than a narrower one.
@@ -171,6 +203,8 @@ int ovo_profile_report(int n_classes, float* ms, double* flops, double* bytes, i
   cudaGetLastError();
   return ovo::PROF_NCLASS;
 }
+
+void ovo_set_gemm_cluster(int cluster_size) { ovo::g_gemm_cluster = cluster_size; }
 
 int ovo_gemm_bf16(const void* A_dev, int lda, const void* B_dev, int ldb, int M, int N, int K, const float* bias_dev,
                   float* C_dev, int ldc, int force_bn, void* stream) {

@@ -155,7 +155,12 @@ __device__ __forceinline__ void epilogue_store(const EpiParams& ep, int row, int
   }
 }
 
-template <int BN, int EPI>
+// CS = thread-block cluster size along M.  The CS CTAs of a cluster work on CS consecutive M tiles of the SAME
+// N tile; each loads 1/CS of the B tile and TMA-multicasts it to all of them, so L2 operand traffic per CTA and
+// k-block drops from 16 KB + BN*128 B to 16 KB + BN*128/CS B (the kernel is otherwise L2-bandwidth bound).
+// A smem stage may only be refilled when EVERY CTA of the cluster has consumed it: the MMA warp's
+// tcgen05.commit arrives (multicast) on the `empty` barrier of all CTAs, which therefore counts CS arrivals.
+template <int BN, int EPI, int CS>
 __global__ void __launch_bounds__(kGemmThreads, 1)
     gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N,
                         int K, EpiParams ep) {
@@ -175,15 +180,20 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
   const int lane = threadIdx.x & 31;
   const int tiles_m = (M + kBM - 1) / kBM;
   const int tiles_n = (N + BN - 1) / BN;
-  const int num_tiles = tiles_m * tiles_n;
+  const int groups_m = (tiles_m + CS - 1) / CS;      // cluster tiles along M
+  const int num_ctiles = groups_m * tiles_n;
   const int num_kb = (K + kBK - 1) / kBK;
+  const int crank = CS > 1 ? static_cast<int>(cluster_ctarank()) : 0;
+  const int cluster_id = blockIdx.x / CS;
+  const int num_clusters = gridDim.x / CS;
+  constexpr uint16_t kMask = static_cast<uint16_t>((1u << CS) - 1);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int i = 0; i < Cfg::kStages; ++i) {
       mbar_init(&full[i], 1);
-      mbar_init(&empty[i], 1);
+      mbar_init(&empty[i], CS);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
@@ -194,19 +204,26 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
   if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
   tc_fence_before();
   __syncthreads();
+  if constexpr (CS > 1) cluster_sync_all();   // peers' barriers are initialised before anyone signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0, phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int tm = tile % tiles_m, tn = tile / tiles_m;
+      for (int ct = cluster_id; ct < num_ctiles; ct += num_clusters) {
+        const int tm = (ct % groups_m) * CS + crank, tn = ct / groups_m;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
           tma_load_2d(sA + stage * Cfg::kBytesA, &tmA, &full[stage], kb * kBK, tm * kBM);
-          tma_load_2d(sB + stage * Cfg::kBytesB, &tmB, &full[stage], kb * kBK, tn * BN);
+          if constexpr (CS == 1) {
+            tma_load_2d(sB + stage * Cfg::kBytesB, &tmB, &full[stage], kb * kBK, tn * BN);
+          } else {
+            constexpr int kSliceRows = BN / CS;
+            tma_load_2d_multicast(sB + stage * Cfg::kBytesB + crank * kSliceRows * 128, &tmB, &full[stage], kb * kBK,
+                                  tn * BN + crank * kSliceRows, kMask);
+          }
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -215,7 +232,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN);
       int stage = 0, phase = 0, acc = 0, acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int ct = cluster_id; ct < num_ctiles; ct += num_clusters) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
@@ -227,7 +244,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 #pragma unroll
           for (int k = 0; k < kBK / 16; ++k)  // +32 B per K=16 step inside the 128 B swizzle row
             umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
-          umma_commit(&empty[stage]);
+          if constexpr (CS == 1) umma_commit(&empty[stage]);
+          else umma_commit_multicast(&empty[stage], kMask);
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tmem_full[acc]);
@@ -238,8 +256,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
   } else {
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
     int acc = 0, acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int tm = tile % tiles_m, tn = tile / tiles_m;
+    for (int ct = cluster_id; ct < num_ctiles; ct += num_clusters) {
+      const int tm = (ct % groups_m) * CS + crank, tn = ct / groups_m;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const int row = tm * kBM + quad * 32 + lane;
@@ -260,6 +278,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (CS > 1) cluster_sync_all();   // no CTA leaves while a peer may still multicast into it / signal it
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<Cfg::kTmemCols>(tmem_base);
