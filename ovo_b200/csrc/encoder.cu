@@ -148,10 +148,12 @@ __global__ void pixels_to_patches_kernel(const float* __restrict__ px, int n_img
 // ------------------------------------------------------------------------------------------- E3 canvas
 // resize_features (textregion.py:9-28): bilinear up-sample (align_corners=False) of the global image's
 // tokens to [ph,pw], then 0.5*up + tokens of the crop that owns the cell.  tokens: [n_img, 1+g*g, width].
-__global__ void token_canvas_kernel(const float* __restrict__ tokens, int g, int width, int nh, int nw,
-                                    float* __restrict__ canvas) {
+__global__ void token_canvas_kernel(const float* __restrict__ tokens_all, int g, int width, int nh, int nw,
+                                    float* __restrict__ canvas_all, int imgs_per_frame) {
   const int ph = nh * g, pw = nw * g;
-  const int p = blockIdx.x;  // canvas cell
+  const int p = blockIdx.x;  // canvas cell; blockIdx.y = frame
+  const float* tokens = tokens_all + static_cast<size_t>(blockIdx.y) * imgs_per_frame * (g * g + 1) * width;
+  float* canvas = canvas_all + static_cast<size_t>(blockIdx.y) * ph * pw * width;
   const int py = p / pw, px = p - py * pw;
   const float sy = fmaxf((static_cast<float>(g) / ph) * (py + 0.5f) - 0.5f, 0.f);
   const float sx = fmaxf((static_cast<float>(g) / pw) * (px + 0.5f) - 0.5f, 0.f);
@@ -195,30 +197,39 @@ __global__ void feature_mask_kernel(const uint8_t* __restrict__ masks, int M, in
 }
 
 // ------------------------------------------------------------------------------------------- E5 masked mean
-// mean[m] = sum_{p in mask m} canvas[p] / cnt[m]  (uniform softmax of textregion.py:183-189);
-// 8 masks per block share each canvas read.  Empty masks (cnt 0) get a zero row and are fixed up in
-// l2_normalize_kernel.
+// mean[m] = sum_{p in mask m} canvas[frame(m)][p] / cnt[m]  (uniform softmax of textregion.py:183-189).
+// Work unit = (256 feature columns) x (group of <= 8 masks of one frame) x (64-token slice): the 8 masks share
+// every canvas read, the loads of a thread are independent (unrolled); per-slice partial sums are written to
+// acc[slice][mask][column] and added in slice order by mean_finalize_kernel (deterministic, no atomics).
+// Empty masks (cnt 0) get a zero row, fixed up in l2_normalize_kernel.
 constexpr int kMeanMasks = 8;
+constexpr int kMeanSlice = 64;      // tokens staged per shared-memory refill
+constexpr int kMeanMaxSplits = 16;  // token slices per mask (bounds the partial-sum buffer)
+struct MaskGroup { int frame, m0, n, pad; };
+
 __global__ void __launch_bounds__(256)
-    masked_mean_kernel(const float* __restrict__ canvas, int P, int width, const uint8_t* __restrict__ fmask,
-                       const int* __restrict__ cnt, int M, __nv_bfloat16* __restrict__ mean) {
+    masked_sum_kernel(const float* __restrict__ canvas_all, int P, int width, const uint8_t* __restrict__ fmask,
+                      const MaskGroup* __restrict__ groups, float* __restrict__ partial, int M, int tokens_per_split) {
+  const MaskGroup gr = groups[blockIdx.y];
   const int d = blockIdx.x * blockDim.x + threadIdx.x;
-  const int m0 = blockIdx.y * kMeanMasks;
-  __shared__ uint8_t s_f[kMeanMasks][64];
+  const int pbeg = blockIdx.z * tokens_per_split, pend = min(P, pbeg + tokens_per_split);
+  __shared__ uint8_t s_f[kMeanMasks][kMeanSlice];
   float acc[kMeanMasks];
 #pragma unroll
   for (int i = 0; i < kMeanMasks; ++i) acc[i] = 0.f;
-  for (int p0 = 0; p0 < P; p0 += 64) {
+  for (int p0 = pbeg; p0 < pend; p0 += kMeanSlice) {
+    const int pe = min(kMeanSlice, pend - p0);
     __syncthreads();
-    for (int i = threadIdx.x; i < kMeanMasks * 64; i += blockDim.x) {
-      const int mi = i >> 6, pi = i & 63;
-      s_f[mi][pi] = (m0 + mi < M && p0 + pi < P) ? fmask[static_cast<size_t>(m0 + mi) * P + p0 + pi] : 0;
+    for (int i = threadIdx.x; i < kMeanMasks * kMeanSlice; i += blockDim.x) {
+      const int mi = i / kMeanSlice, pi = i % kMeanSlice;
+      s_f[mi][pi] = (mi < gr.n && pi < pe) ? fmask[static_cast<size_t>(gr.m0 + mi) * P + p0 + pi] : 0;
     }
     __syncthreads();
     if (d < width) {
-      const int pe = min(64, P - p0);
+      const float* canvas = canvas_all + (static_cast<size_t>(gr.frame) * P + p0) * width + d;
+#pragma unroll 8
       for (int pi = 0; pi < pe; ++pi) {
-        const float c = canvas[static_cast<size_t>(p0 + pi) * width + d];
+        const float c = canvas[static_cast<size_t>(pi) * width];
 #pragma unroll
         for (int i = 0; i < kMeanMasks; ++i)
           if (s_f[i][pi]) acc[i] += c;
@@ -228,8 +239,19 @@ __global__ void __launch_bounds__(256)
   if (d < width) {
 #pragma unroll
     for (int i = 0; i < kMeanMasks; ++i)
-      if (m0 + i < M) mean[static_cast<size_t>(m0 + i) * width + d] = __float2bfloat16_rn(cnt[m0 + i] > 0 ? acc[i] / static_cast<float>(cnt[m0 + i]) : 0.f);
+      if (i < gr.n) partial[(static_cast<size_t>(blockIdx.z) * M + gr.m0 + i) * width + d] = acc[i];
   }
+}
+
+__global__ void mean_finalize_kernel(const float* __restrict__ partial, int splits, const int* __restrict__ cnt, int M,
+                                     int width, __nv_bfloat16* __restrict__ mean) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t n = static_cast<size_t>(M) * width;
+  if (i >= n) return;
+  float acc = 0.f;
+  for (int z = 0; z < splits; ++z) acc += partial[z * n + i];
+  const int c = cnt[i / width];
+  mean[i] = __float2bfloat16_rn(c > 0 ? acc / static_cast<float>(c) : 0.f);
 }
 
 // F.normalize(dim=-1) (textregion.py:194): one warp per row.  Rows whose mask covered no token (all keys
@@ -311,9 +333,12 @@ struct ovo_encoder {
   // activations
   __nv_bfloat16 *patch_buf = nullptr, *xn = nullptr, *q = nullptr, *k = nullptr, *vt = nullptr, *attn = nullptr,
                 *hmid = nullptr, *mean = nullptr, *pooled_in = nullptr;
-  float *x = nullptr, *xfinal = nullptr, *rope_cos = nullptr, *rope_sin = nullptr, *canvas = nullptr,
+  float2* rope_tab = nullptr;
+  float *x = nullptr, *xfinal = nullptr, *canvas = nullptr,
         *resize_tmp = nullptr;
   uint8_t* fmask = nullptr;
+  float* mean_acc = nullptr;
+  MaskGroup* groups_dev = nullptr;
   int *fcnt = nullptr, *eot_rows = nullptr;
   // AA resize tables
   int *tab_min = nullptr, *tab_size = nullptr;
@@ -387,7 +412,7 @@ int run_blocks(ovo_encoder* e, const std::vector<ovo_block_weights>& blocks, int
     OVO_TRY(launch_ln(e->x, rows, width, b.ln1_w, b.ln1_b, e->cfg.ln_eps, e->xn, nullptr, nullptr, s));
     EpiParams qkv;
     qkv.bias = b.qkv_b; qkv.q = e->q; qkv.k = e->k; qkv.vt = e->vt;
-    qkv.rope_cos = rope ? e->rope_cos : nullptr; qkv.rope_sin = rope ? e->rope_sin : nullptr;
+    qkv.rope_tab = rope ? e->rope_tab : nullptr; qkv.rope_grid = e->grid;
     qkv.seq = seq; qkv.seq_pad = seq_pad; qkv.heads = heads; qkv.width = width;
     OVO_TRY(launch_gemm(EPI_QKV, e->xn, width, static_cast<const __nv_bfloat16*>(b.qkv_w), width, rows, 3 * width, width, qkv, s));
     OVO_TRY(launch_attention(e, n_seq, seq, seq_pad, heads, width, causal, s));
@@ -458,7 +483,7 @@ int ovo_encoder_create(const ovo_vit_cfg* cfg, const ovo_vit_weights* w, int max
                        int max_masks, ovo_encoder_t** out) {
   OVO_REQUIRE(cfg && w && out, "ovo_encoder_create: null argument");
   OVO_REQUIRE(cfg->width % 64 == 0 && cfg->heads > 0 && cfg->width / cfg->heads == 64, "head_dim must be 64 (width %d, heads %d)", cfg->width, cfg->heads);
-  OVO_REQUIRE(cfg->image_size % cfg->patch_size == 0, "image_size must be a multiple of patch_size");
+  OVO_REQUIRE(cfg->image_size % cfg->patch_size == 0 && cfg->image_size / cfg->patch_size < kRopeRowsMax, "image_size must be a multiple of patch_size (grid < 40)");
   OVO_REQUIRE(max_images > 0 && max_masks > 0 && max_h > 0 && max_w > 0, "ovo_encoder_create: bad limits");
   OVO_REQUIRE(w->patch_kpad % 64 == 0 && w->patch_kpad >= 3 * cfg->patch_size * cfg->patch_size, "patch_kpad must be a multiple of 64");
   if (cfg->text_layers > 0)
@@ -495,12 +520,13 @@ int ovo_encoder_create(const ovo_vit_cfg* cfg, const ovo_vit_weights* w, int max
   r |= dmalloc(&e->q, qk_elems);
   r |= dmalloc(&e->k, qk_elems);
   r |= dmalloc(&e->vt, qk_elems);
-  r |= dmalloc(&e->rope_cos, static_cast<size_t>(e->seq) * 32);
-  r |= dmalloc(&e->rope_sin, static_cast<size_t>(e->seq) * 32);
-  r |= dmalloc(&e->canvas, pmax * cfg->width);
+  r |= dmalloc(&e->rope_tab, static_cast<size_t>(e->grid + 1) * 16);
+  r |= dmalloc(&e->canvas, std::max(pmax, static_cast<size_t>(max_images) * e->patches) * cfg->width);
   r |= dmalloc(&e->fmask, static_cast<size_t>(max_masks) * pmax);
   r |= dmalloc(&e->fcnt, static_cast<size_t>(max_masks));
   r |= dmalloc(&e->mean, static_cast<size_t>(max_masks + 128) * cfg->width);
+  r |= dmalloc(&e->mean_acc, static_cast<size_t>(kMeanMaxSplits) * max_masks * cfg->width);
+  r |= dmalloc(&e->groups_dev, static_cast<size_t>(max_masks) + static_cast<size_t>(max_images));
   r |= dmalloc(&e->resize_tmp, static_cast<size_t>(max_images) * 3 * max_h * cfg->image_size);
   r |= dmalloc(&e->eot_rows, rows_pad);
   r |= dmalloc(&e->pooled_in, rows_pad * static_cast<size_t>(W) / 8 + static_cast<size_t>(W) * 128);
@@ -512,24 +538,17 @@ int ovo_encoder_create(const ovo_vit_cfg* cfg, const ovo_vit_weights* w, int max
   r |= dmalloc(&e->jobs_dev, static_cast<size_t>(max_images));
   if (r != OVO_OK) { ovo_encoder_destroy(e); return OVO_E_NOMEM; }
 
-  // 2D RoPE table with a cls token (rope.py:315-340): pairs 0..15 rotate by (x+1)*theta_i,
-  // pairs 16..31 by (y+1)*theta_i, theta_i = 10000^(-2i/32); cls row angle 0.
+  // 2D RoPE table (rope.py:315-340): both axes share theta_i = 10000^(-2i/32); row r holds
+  // (cos, sin)(r * theta_i) for r = coordinate + 1 (r = 0 is the cls token's zero angle).
   {
-    std::vector<float> c(static_cast<size_t>(e->seq) * 32), s(static_cast<size_t>(e->seq) * 32);
-    for (int t = 0; t < e->seq; ++t)
-      for (int p = 0; p < 32; ++p) {
-        float ang = 0.f;
-        if (t > 0) {
-          const int y = (t - 1) / e->grid, x = (t - 1) % e->grid;
-          const int i = p & 15;
-          const float theta = 1.0f / powf(10000.0f, static_cast<float>(2 * i) / 32.0f);
-          ang = static_cast<float>((p < 16 ? x : y) + 1) * theta;
-        }
-        c[static_cast<size_t>(t) * 32 + p] = cosf(ang);
-        s[static_cast<size_t>(t) * 32 + p] = sinf(ang);
+    std::vector<float2> tab(static_cast<size_t>(e->grid + 1) * 16);
+    for (int r = 0; r <= e->grid; ++r)
+      for (int i = 0; i < 16; ++i) {
+        const float theta = 1.0f / powf(10000.0f, static_cast<float>(2 * i) / 32.0f);
+        const float ang = static_cast<float>(r) * theta;
+        tab[static_cast<size_t>(r) * 16 + i] = make_float2(cosf(ang), sinf(ang));
       }
-    if (cudaMemcpy(e->rope_cos, c.data(), c.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess ||
-        cudaMemcpy(e->rope_sin, s.data(), s.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
+    if (cudaMemcpy(e->rope_tab, tab.data(), tab.size() * sizeof(float2), cudaMemcpyHostToDevice) != cudaSuccess) {
       ovo_encoder_destroy(e);
       return set_error(OVO_E_CUDA, "rope table upload failed");
     }
@@ -543,8 +562,8 @@ void ovo_encoder_destroy(ovo_encoder_t* e) {
   for (auto& g : e->graphs) if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
   if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
   cudaFree(e->patch_buf); cudaFree(e->x); cudaFree(e->xfinal); cudaFree(e->xn); cudaFree(e->attn); cudaFree(e->hmid);
-  cudaFree(e->q); cudaFree(e->k); cudaFree(e->vt); cudaFree(e->rope_cos); cudaFree(e->rope_sin); cudaFree(e->canvas);
-  cudaFree(e->fmask); cudaFree(e->fcnt); cudaFree(e->mean); cudaFree(e->resize_tmp); cudaFree(e->eot_rows);
+  cudaFree(e->q); cudaFree(e->k); cudaFree(e->vt); cudaFree(e->rope_tab); cudaFree(e->canvas);
+  cudaFree(e->fmask); cudaFree(e->mean_acc); cudaFree(e->groups_dev); cudaFree(e->fcnt); cudaFree(e->mean); cudaFree(e->resize_tmp); cudaFree(e->eot_rows);
   cudaFree(e->pooled_in); cudaFree(e->tab_min); cudaFree(e->tab_size); cudaFree(e->tab_w); cudaFree(e->jobs_dev);
   delete e;
 }
@@ -652,24 +671,38 @@ int ovo_encoder_forward(ovo_encoder_t* e, int n_img, int n_layers, int apply_ln_
   return OVO_OK;
 }
 
-int ovo_encoder_pool_regions(ovo_encoder_t* e, int img0, int H, int W, const uint8_t* masks_dev, int M, float* out_dev,
-                             void* stream_) {
-  cudaStream_t s = static_cast<cudaStream_t>(stream_);
-  OVO_REQUIRE(e && masks_dev && out_dev, "ovo_encoder_pool_regions: null argument");
-  OVO_REQUIRE(M > 0 && M <= e->max_masks, "ovo_encoder_pool_regions: M=%d outside (0, %d]", M, e->max_masks);
+// E3-E5 for n_frames frames whose images start at img0 (imgs_per_frame each); masks concatenated over frames.
+static int pool_regions_batch(ovo_encoder* e, int img0, int n_frames, int H, int W, const uint8_t* masks_dev,
+                              const int* masks_per_frame, float* out_dev, cudaStream_t s) {
   const ovo_vit_cfg& c = e->cfg;
   const int S = c.image_size, g = e->grid;
-  const int nh = std::max(H / S, 1), nw = std::max(W / S, 1);
-  OVO_REQUIRE(H <= e->max_h && W <= e->max_w && img0 >= 0 && img0 + 1 + nh * nw <= e->max_images, "ovo_encoder_pool_regions: frame out of range");
+  const int nh = std::max(H / S, 1), nw = std::max(W / S, 1), per = 1 + nh * nw;
+  OVO_REQUIRE(H <= e->max_h && W <= e->max_w && img0 >= 0 && img0 + n_frames * per <= e->max_images, "pool_regions: frames out of range");
   const int ph = nh * g, pw = nw * g, P = ph * pw;
+  std::vector<MaskGroup> groups;
+  int M = 0;
+  for (int f = 0; f < n_frames; ++f) {
+    OVO_REQUIRE(masks_per_frame[f] >= 0, "pool_regions: negative mask count");
+    for (int m = 0; m < masks_per_frame[f]; m += kMeanMasks)
+      groups.push_back({f, M + m, std::min(kMeanMasks, masks_per_frame[f] - m), 0});
+    M += masks_per_frame[f];
+  }
+  if (M == 0) return OVO_OK;
+  OVO_REQUIRE(M <= e->max_masks, "pool_regions: %d masks exceed max_masks %d", M, e->max_masks);
   const float* tokens = e->xfinal + static_cast<size_t>(img0) * e->seq * c.width;
-  ProfScope prof(s, PROF_POOL, 0.0, static_cast<double>(P) * c.width * 8 + static_cast<double>(M) * H * W);
-  token_canvas_kernel<<<P, 256, 0, s>>>(tokens, g, c.width, nh, nw, e->canvas);
+  ProfScope prof(s, PROF_POOL, 0.0, static_cast<double>(n_frames) * P * c.width * 8 + static_cast<double>(M) * H * W);
+  OVO_CUDA(cudaMemcpyAsync(e->groups_dev, groups.data(), groups.size() * sizeof(MaskGroup), cudaMemcpyHostToDevice, s));
+  token_canvas_kernel<<<dim3(P, n_frames), 256, 0, s>>>(tokens, g, c.width, nh, nw, e->canvas, per);
   OVO_CHECK_LAUNCH();
   OVO_CUDA(cudaMemsetAsync(e->fcnt, 0, M * sizeof(int), s));
   feature_mask_kernel<<<dim3(ceil_div(P, 128), M), 128, 0, s>>>(masks_dev, M, H, W, ph, pw, e->fmask, e->fcnt);
   OVO_CHECK_LAUNCH();
-  masked_mean_kernel<<<dim3(ceil_div(c.width, 256), ceil_div(M, kMeanMasks)), 256, 0, s>>>(e->canvas, P, c.width, e->fmask, e->fcnt, M, e->mean);
+  const int tokens_per_split = std::max(kMeanSlice, ceil_div(ceil_div(P, kMeanMaxSplits), kMeanSlice) * kMeanSlice);
+  const int splits = ceil_div(P, tokens_per_split);
+  masked_sum_kernel<<<dim3(ceil_div(c.width, 256), static_cast<unsigned>(groups.size()), splits), 256, 0, s>>>(
+      e->canvas, P, c.width, e->fmask, e->groups_dev, e->mean_acc, M, tokens_per_split);
+  OVO_CHECK_LAUNCH();
+  mean_finalize_kernel<<<ceil_div(static_cast<long long>(M) * c.width, 256), 256, 0, s>>>(e->mean_acc, splits, e->fcnt, M, c.width, e->mean);
   OVO_CHECK_LAUNCH();
   EpiParams ep;
   ep.out = out_dev; ep.ldo = c.output_dim; ep.bias = e->w.pool_b;
@@ -679,20 +712,20 @@ int ovo_encoder_pool_regions(ovo_encoder_t* e, int img0, int H, int W, const uin
   return OVO_OK;
 }
 
+int ovo_encoder_pool_regions(ovo_encoder_t* e, int img0, int H, int W, const uint8_t* masks_dev, int M, float* out_dev,
+                             void* stream_) {
+  OVO_REQUIRE(e && masks_dev && out_dev, "ovo_encoder_pool_regions: null argument");
+  OVO_REQUIRE(M > 0 && M <= e->max_masks, "ovo_encoder_pool_regions: M=%d outside (0, %d]", M, e->max_masks);
+  return pool_regions_batch(e, img0, 1, H, W, masks_dev, &M, out_dev, static_cast<cudaStream_t>(stream_));
+}
+
 int ovo_encode_regions(ovo_encoder_t* e, const uint8_t* rgb_dev, int n_frames, int H, int W, const uint8_t* masks_dev,
                        const int* masks_per_frame_host, float* out_dev, void* stream) {
-  OVO_REQUIRE(e && masks_per_frame_host, "ovo_encode_regions: null argument");
+  OVO_REQUIRE(e && masks_per_frame_host && masks_dev && out_dev, "ovo_encode_regions: null argument");
   int per = 0;
   OVO_TRY(ovo_encoder_preprocess(e, rgb_dev, n_frames, H, W, &per, stream));
   OVO_TRY(ovo_encoder_forward(e, n_frames * per, -1, 1, nullptr, stream));
-  size_t moff = 0;
-  for (int f = 0; f < n_frames; ++f) {
-    const int M = masks_per_frame_host[f];
-    if (M > 0)
-      OVO_TRY(ovo_encoder_pool_regions(e, f * per, H, W, masks_dev + moff * H * W, M, out_dev + moff * e->cfg.output_dim, stream));
-    moff += M;
-  }
-  return OVO_OK;
+  return pool_regions_batch(e, 0, n_frames, H, W, masks_dev, masks_per_frame_host, out_dev, static_cast<cudaStream_t>(stream));
 }
 
 int ovo_encode_text(ovo_encoder_t* e, const int32_t* tokens_dev, int T, float* out_dev, void* stream_) {

@@ -1,7 +1,8 @@
 // Persistent, warp-specialised bf16 GEMM for sm_100a:  C[M,N] = A[M,K] . B[N,K]^T  (+ fused epilogue)
 //   warp 0      : TMA producer (cp.async.bulk.tensor, 128B-swizzled 128x64 / BNx64 tiles, mbarrier ring)
 //   warp 1      : tcgen05.mma issuer (one elected thread), accumulators double-buffered in TMEM
-//   warps 2..5  : epilogue (tcgen05.ld 32x32b -> registers -> fused epilogue -> global)
+//   warps 2..9  : epilogue (tcgen05.ld 32x32b -> registers -> fused epilogue -> global); two warps per TMEM
+//                 lane quadrant, each taking every other 32-column chunk
 // Both operands are K-major (row-major with K contiguous), which is how activations [tokens, width]
 // and nn.Linear weights [out, in] already sit in memory, so no transposes are ever materialised.
 //
@@ -31,8 +32,8 @@ struct EpiParams {
   __nv_bfloat16* q = nullptr;
   __nv_bfloat16* k = nullptr;
   __nv_bfloat16* vt = nullptr;
-  const float* rope_cos = nullptr;  // [seq, head_dim/2] or nullptr (text tower: no RoPE)
-  const float* rope_sin = nullptr;
+  const float2* rope_tab = nullptr;  // [grid+1][16] (cos, sin) of r*theta_i, or nullptr (text tower: no RoPE)
+  int rope_grid = 0;                 // patch grid side (24); token t>0 sits at (y,x) = divmod(t-1, grid)
   int seq = 0, seq_pad = 0, heads = 0, width = 0;
   // EPI_PATCH
   const float* pos = nullptr;  // [1 + patches, width]
@@ -42,7 +43,8 @@ struct EpiParams {
 
 constexpr int kBM = 128;
 constexpr int kBK = 64;
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 320;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quadrant)
+constexpr int kRopeRowsMax = 40;     // rows of the per-axis RoPE table staged in shared memory (grid+1 <= 40)
 
 template <int BN>
 struct GemmCfg {
@@ -51,15 +53,26 @@ struct GemmCfg {
   static constexpr int kBytesB = BN * kBK * 2;
   static constexpr int kStageBytes = kBytesA + kBytesB;
   static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kRopeRowsMax * 17 * 8 /*rope table*/;
 };
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// Exact (erf) GELU of nn.GELU (pe.py:301).  erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, far below the bf16
+// rounding of the output): ~14 instructions instead of erff's ~25 — the fc epilogue is issue-bound otherwise.
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float e = 1.0f - p * t * exp2f(-1.4426950408889634f * z * z);   // erf(|x|/sqrt2)
+  return 0.5f * x * (1.0f + copysignf(e, x));
+}
 
 // One thread owns `row` and 32 consecutive accumulator columns starting at `col`.
 template <int EPI>
 __device__ __forceinline__ void epilogue_store(const EpiParams& ep, int row, int col, const uint32_t (&v)[32], int M,
-                                               int N) {
+                                               int N, const float2* s_rope) {
   if (row >= M || col >= N) return;
   const int ncol = min(32, N - col);
   float acc[32];
@@ -119,16 +132,18 @@ __device__ __forceinline__ void epilogue_store(const EpiParams& ep, int row, int
     const int t = row - b * ep.seq;
     const size_t bh = static_cast<size_t>(b) * ep.heads + head;
     if (which < 2) {
-      if (ep.rope_cos != nullptr) {
-        // interleaved pairs (2i, 2i+1); pair index p = (d0 + j) / 2 (rope.py:32-37,57)
-        const float* c = ep.rope_cos + static_cast<size_t>(t) * 32 + (d0 >> 1);
-        const float* s = ep.rope_sin + static_cast<size_t>(t) * 32 + (d0 >> 1);
+      if (ep.rope_tab != nullptr) {
+        // 2D RoPE with a cls token (rope.py:315-347): interleaved pairs (2i, 2i+1); pairs 0..15 of a head
+        // (d0 == 0) rotate by (x+1)*theta_i, pairs 16..31 (d0 == 32) by (y+1)*theta_i, the cls token by 0.
+        int r = 0;
+        if (t > 0) r = (d0 == 0 ? (t - 1) % ep.rope_grid : (t - 1) / ep.rope_grid) + 1;
+        const float2* tab = s_rope + r * 17;
 #pragma unroll
         for (int j = 0; j < 32; j += 2) {
-          const float cs = __ldg(c + (j >> 1)), sn = __ldg(s + (j >> 1));
+          const float2 cs = tab[j >> 1];
           const float a = acc[j], bb = acc[j + 1];
-          acc[j] = a * cs - bb * sn;
-          acc[j + 1] = bb * cs + a * sn;
+          acc[j] = a * cs.x - bb * cs.y;
+          acc[j + 1] = bb * cs.x + a * cs.y;
         }
       }
       __nv_bfloat16* dst = (which == 0 ? ep.q : ep.k) + (bh * ep.seq_pad + t) * 64 + d0;
@@ -175,6 +190,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
   uint64_t* tmem_full = bars + 2 * Cfg::kStages;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float2* s_rope = reinterpret_cast<float2*>(smem + Cfg::kStages * Cfg::kStageBytes + 256);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -197,11 +213,15 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 4);
+      mbar_init(&tmem_empty[i], 8);
     }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  if constexpr (EPI == EPI_QKV) {
+    if (ep.rope_tab != nullptr)
+      for (int i = threadIdx.x; i < (ep.rope_grid + 1) * 16; i += blockDim.x) s_rope[(i >> 4) * 17 + (i & 15)] = ep.rope_tab[i];
+  }
   tc_fence_before();
   __syncthreads();
   if constexpr (CS > 1) cluster_sync_all();   // peers' barriers are initialised before anyone signals them
@@ -212,7 +232,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     if (lane == 0) {
       int stage = 0, phase = 0;
       for (int ct = cluster_id; ct < num_ctiles; ct += num_clusters) {
-        const int tm = (ct % groups_m) * CS + crank, tn = ct / groups_m;
+        const int tm = (ct / tiles_n) * CS + crank, tn = ct % tiles_n;   // N fastest: concurrent CTAs spread over the weight tiles
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
@@ -254,19 +274,20 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
       }
     }
   } else {
-    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    const int quad = warp & 3;         // TMEM lane quadrant this warp may access
+    const int half = (warp - 2) >> 2;  // which of the two warps of that quadrant: takes chunks half, half+2, ...
     int acc = 0, acc_phase = 0;
     for (int ct = cluster_id; ct < num_ctiles; ct += num_clusters) {
-      const int tm = (ct % groups_m) * CS + crank, tn = ct / groups_m;
+      const int tm = (ct / tiles_n) * CS + crank, tn = ct % tiles_n;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const int row = tm * kBM + quad * 32 + lane;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = half; c < BN / 32; c += 2) {
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + c * 32, v);
         tmem_ld_wait();
-        epilogue_store<EPI>(ep, row, tn * BN + c * 32, v, M, N);
+        epilogue_store<EPI>(ep, row, tn * BN + c * 32, v, M, N, s_rope);
       }
       tc_fence_before();
       __syncwarp();

@@ -149,7 +149,13 @@ __global__ void __launch_bounds__(kP1Threads)
                            const float* __restrict__ depth, const int32_t* __restrict__ seg_map,
                            const FrameGeom* __restrict__ geom, const FrameDev* __restrict__ fr, int n_masks,
                            int n_ins, int32_t* __restrict__ votes, int2* __restrict__ match_list,
-                           int32_t* __restrict__ counters /* [0]=list len, [1]=n_matched */) {
+                           int32_t* __restrict__ counters /* [0]=list len, [1]=n_matched */, int smem_votes) {
+  // when the vote table fits, votes are first accumulated per block in shared memory (few hot global addresses
+  // otherwise: every matched point of a mask hits the same counter)
+  extern __shared__ int32_t s_votes[];
+  const int n_votes = n_masks * (n_ins + 1);
+  if (smem_votes)
+    for (int i = threadIdx.x; i < n_votes; i += blockDim.x) s_votes[i] = 0;
   __shared__ float s_xyz[kP1Threads * 3];
   __shared__ FrameGeom s_g;
   __shared__ FrameDev s_f;
@@ -226,9 +232,14 @@ __global__ void __launch_bounds__(kP1Threads)
         if (id >= n_ins) id = -1;  // ids the host does not know about count as unassigned
         const int key = seg * (n_ins + 1) + (id + 1);
         const unsigned peers = __match_any_sync(m_list, key);
-        if (lane == __ffs(peers) - 1) atomicAdd(&votes[key], __popc(peers));
+        if (lane == __ffs(peers) - 1) atomicAdd(smem_votes ? &s_votes[key] : &votes[key], __popc(peers));
       }
     }
+  }
+  if (smem_votes) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_votes; i += blockDim.x)
+      if (s_votes[i]) atomicAdd(&votes[i], s_votes[i]);
   }
 }
 
@@ -283,24 +294,47 @@ __global__ void vote_reduce_kernel(const int32_t* __restrict__ votes, int n_ins,
   }
 }
 
-// Sequential over masks (ids are allocated in mask order, ovo.py:255,271-273).
-__global__ void vote_decide_kernel(ovo_vote_row* rows, int n_masks, int track_th, int32_t* mask_ins,
-                                   int32_t* next_ins_id) {
-  int next = *next_ins_id;
-  for (int m = 0; m < n_masks; ++m) {
-    ovo_vote_row r = rows[m];
-    if (r.n_matched > track_th) {
-      if (r.n_assigned > track_th) {
-        r.ins_id = r.mode_id;
-      } else if (r.n_unassigned > track_th) {
-        r.ins_id = next++;
-        r.is_new = 1;
+// New ids are allocated in mask order (ovo.py:255,271-273): every mask decides in parallel, then an ordered
+// prefix sum over the "wants a new instance" flags hands out next_ins_id, next_ins_id+1, ...  One block.
+__global__ void __launch_bounds__(256)
+    vote_decide_kernel(ovo_vote_row* rows, int n_masks, int track_th, int32_t* mask_ins, int32_t* next_ins_id) {
+  __shared__ int s_warp[8];
+  __shared__ int s_base;
+  if (threadIdx.x == 0) s_base = *next_ins_id;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int m0 = 0; m0 < n_masks; m0 += blockDim.x) {
+    const int m = m0 + threadIdx.x;
+    ovo_vote_row r;
+    int want_new = 0, ins = -1;
+    if (m < n_masks) {
+      r = rows[m];
+      if (r.n_matched > track_th) {
+        if (r.n_assigned > track_th) ins = r.mode_id;
+        else if (r.n_unassigned > track_th) want_new = 1;
       }
     }
-    rows[m] = r;
-    mask_ins[m] = r.ins_id;
+    // ordered exclusive prefix of want_new over the block
+    const unsigned bal = __ballot_sync(0xffffffffu, want_new);
+    const int in_warp = __popc(bal & ((1u << lane) - 1));
+    if (lane == 0) s_warp[warp] = __popc(bal);
+    __syncthreads();
+    int before = 0, total = 0;
+    for (int w = 0; w < 8; ++w) {
+      if (w < warp) before += s_warp[w];
+      total += s_warp[w];
+    }
+    if (m < n_masks) {
+      if (want_new) { ins = s_base + before + in_warp; r.is_new = 1; }
+      r.ins_id = ins;
+      rows[m] = r;
+      mask_ins[m] = ins;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) s_base += total;
+    __syncthreads();
   }
-  *next_ins_id = next;
+  if (threadIdx.x == 0) *next_ins_id = s_base;
 }
 
 // ------------------------------------------------------------------------------------------ pass 2
@@ -315,13 +349,16 @@ __global__ void associate_pass2_kernel(const int2* __restrict__ match_list, cons
 }
 
 // ------------------------------------------------------------------------------------------ dense fusion
-// One warp per matched point: 2 KB bf16 row read-modify-write, 16 B per lane per access.
+// One warp per matched point: 2 KB bf16 row read-modify-write, 16 B per lane per access; every lane issues all
+// of its loads for the row before the arithmetic so several KB per warp are in flight (HBM latency hiding).
+template <int kVecPerLane>
 __global__ void __launch_bounds__(256)
     fuse_dense_kernel(const int2* __restrict__ match_list, int n, __nv_bfloat16* __restrict__ bank,
                       int32_t* __restrict__ counts, int D, const float* __restrict__ feats,
                       const int32_t* __restrict__ mask_row) {
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
+  const int nvec = D >> 3;
   for (int e = blockIdx.x * warps_per_block + (threadIdx.x >> 5); e < n; e += gridDim.x * warps_per_block) {
     const int2 m = match_list[e];
     const int r = mask_row[m.y];
@@ -332,20 +369,29 @@ __global__ void __launch_bounds__(256)
     const float cf = static_cast<float>(c);
     uint4* prow = reinterpret_cast<uint4*>(bank + static_cast<size_t>(m.x) * D);
     const float4* frow = reinterpret_cast<const float4*>(feats + static_cast<size_t>(r) * D);
-    for (int v = lane; v < D / 8; v += 32) {
-      uint4 raw = prow[v];
-      const float4 e0 = __ldg(frow + 2 * v), e1 = __ldg(frow + 2 * v + 1);
-      const float ev[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
-      uint32_t* w = reinterpret_cast<uint32_t*>(&raw);
+    uint4 raw[kVecPerLane];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        __nv_bfloat162 b2 = *reinterpret_cast<__nv_bfloat162*>(&w[j]);
-        float f0 = __bfloat162float(b2.x), f1 = __bfloat162float(b2.y);
-        f0 = __fadd_rn(f0, __fdiv_rn(__fsub_rn(ev[2 * j], f0), cf));
-        f1 = __fadd_rn(f1, __fdiv_rn(__fsub_rn(ev[2 * j + 1], f1), cf));
-        w[j] = pack_bf16(f0, f1);
+    for (int i = 0; i < kVecPerLane; ++i) {
+      const int v = lane + 32 * i;
+      if (v < nvec) raw[i] = prow[v];
+    }
+#pragma unroll
+    for (int i = 0; i < kVecPerLane; ++i) {
+      const int v = lane + 32 * i;
+      if (v < nvec) {
+        const float4 e0 = __ldg(frow + 2 * v), e1 = __ldg(frow + 2 * v + 1);
+        const float ev[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+        uint32_t* w = reinterpret_cast<uint32_t*>(&raw[i]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          __nv_bfloat162 b2 = *reinterpret_cast<__nv_bfloat162*>(&w[j]);
+          float f0 = __bfloat162float(b2.x), f1 = __bfloat162float(b2.y);
+          f0 = __fadd_rn(f0, __fdiv_rn(__fsub_rn(ev[2 * j], f0), cf));
+          f1 = __fadd_rn(f1, __fdiv_rn(__fsub_rn(ev[2 * j + 1], f1), cf));
+          w[j] = pack_bf16(f0, f1);
+        }
+        prow[v] = raw[i];
       }
-      prow[v] = raw;
     }
   }
 }
@@ -618,15 +664,17 @@ int ovo_map_associate(ovo_map_t* m, const float* xyz_dev, int32_t* ins_ids_dev, 
   }
   if (N > 0) {
     const int blocks = static_cast<int>(std::min<long long>((N + ovo::kP1Threads - 1) / ovo::kP1Threads, sms * 8LL));
-    ovo::associate_pass1_kernel<<<blocks, ovo::kP1Threads, 0, stream>>>(xyz_dev, ins_ids_dev, N, depth_used, f->seg_map_dev,
-                                                                        m->geom, m->frame, n_masks, n_ins, m->votes,
-                                                                        m->scratch_list, m->counters);
+    const size_t vbytes = votes_need * sizeof(int32_t);
+    const int smem_votes = vbytes <= 32 * 1024 ? 1 : 0;
+    ovo::associate_pass1_kernel<<<blocks, ovo::kP1Threads, smem_votes ? vbytes : 0, stream>>>(
+        xyz_dev, ins_ids_dev, N, depth_used, f->seg_map_dev, m->geom, m->frame, n_masks, n_ins, m->votes, m->scratch_list,
+        m->counters, smem_votes);
     OVO_CHECK_LAUNCH();
   }
   if (n_masks > 0) {
     ovo::vote_reduce_kernel<<<n_masks, 128, 0, stream>>>(m->votes, n_ins, m->area, m->rows);
     OVO_CHECK_LAUNCH();
-    ovo::vote_decide_kernel<<<1, 1, 0, stream>>>(m->rows, n_masks, f->track_th, m->mask_ins, m->counters + 2);
+    ovo::vote_decide_kernel<<<1, 256, 0, stream>>>(m->rows, n_masks, f->track_th, m->mask_ins, m->counters + 2);
     OVO_CHECK_LAUNCH();
     if (N > 0) {
       ovo::associate_pass2_kernel<<<sms * 4, 256, 0, stream>>>(m->scratch_list, m->counters, m->mask_ins, ins_ids_dev);
@@ -666,10 +714,15 @@ int ovo_map_fuse_dense(ovo_map_t* m, int kf_slot, void* bank_dev, int32_t* count
   (void)N; (void)n_masks;
   const int n = m->slot_n[kf_slot];
   if (n == 0) return OVO_OK;
+  OVO_REQUIRE(D <= 8 * 32 * 8, "ovo_map_fuse_dense: D > 2048 unsupported");
   const int blocks = std::min(ovo::ceil_div(n, 8), ovo::num_sms() * 8);
   ovo::ProfScope prof(static_cast<cudaStream_t>(stream), ovo::PROF_FUSE, 0.0, static_cast<double>(n) * (4.0 * D + 12));
-  ovo::fuse_dense_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      m->slot_list[kf_slot], n, static_cast<__nv_bfloat16*>(bank_dev), counts_dev, D, feats_dev, mask_row_dev);
+  if (D <= 1024)
+    ovo::fuse_dense_kernel<4><<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        m->slot_list[kf_slot], n, static_cast<__nv_bfloat16*>(bank_dev), counts_dev, D, feats_dev, mask_row_dev);
+  else
+    ovo::fuse_dense_kernel<8><<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        m->slot_list[kf_slot], n, static_cast<__nv_bfloat16*>(bank_dev), counts_dev, D, feats_dev, mask_row_dev);
   OVO_CHECK_LAUNCH();
   return OVO_OK;
 }

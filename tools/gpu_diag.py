@@ -221,6 +221,45 @@ def stage_timing():
     print(f"associate N={N}: {ms:.3f} ms", flush=True)
 
 
+def stage_clusters():
+    """GEMM correctness + speed per thread-block-cluster size (TMA multicast of the weight tile)."""
+    from ovo_b200 import _lib
+    torch.manual_seed(0)
+    for cs in (1, 2, 4):
+        _lib.lib().ovo_set_gemm_cluster(cs)
+        for (M, N, K) in [(300, 512, 192), (1154, 3072, 1024), (9232, 1024, 4096), (9232, 4096, 1024), (9232, 3072, 1024), (9232, 1024, 1024)]:
+            A = torch.randn(M, K, device=dev).bfloat16(); B = torch.randn(N, K, device=dev).bfloat16()
+            bias = torch.randn(N, device=dev)
+            ref = A.float() @ B.float().T + bias
+            for bn in (128, 256):
+                out = gemm_bf16(A, B, bias, force_bn=bn)
+                torch.cuda.synchronize()
+                r, m = relerr(out, ref)
+                ms = _time(lambda: gemm_bf16(A, B, bias, force_bn=bn), n=20)
+                print(f"cs={cs} gemm {M}x{N}x{K} bn={bn}: rel {r:.2e}  {ms * 1e3:.1f} us  {2 * M * N * K / ms / 1e9:.0f} TFLOP/s", flush=True)
+    cfg = EncoderConfig(text_layers=0)
+    enc, sd, ocfg = _enc(cfg, n_img=16, text=False)
+    px = torch.randn(16, 3, 336, 336, device=dev)
+    for cs in (1, 2, 4, 0):
+        _lib.lib().ovo_set_gemm_cluster(cs)
+        os.environ["X"] = "1"
+        enc.lib.ovo_profile_begin()
+        for _ in range(2):
+            enc.forward_features_from_pixels(px)
+        torch.cuda.synchronize()
+        prof = _lib.profile_report()
+        print(f"cs={cs} vit16 profiled: " + ", ".join(f"{k} {v['ms'] / 2:.3f} ms" for k, v in prof.items() if v['launches']), flush=True)
+    _lib.lib().ovo_set_gemm_cluster(0)
+    out = enc.forward_features_from_pixels(px[:2])
+    with torch.no_grad():
+        ref = OE.vit_forward_features(px[:2].cpu(), sd, ocfg)
+    r, m = relerr(out, ref)
+    print(f"vit parity after cluster runs: rel-L2 {r:.3e}", flush=True)
+    for n_img in (2, 16):
+        ms = _time(lambda: enc.forward_features_from_pixels(px[:n_img]), n=10)
+        print(f"vit forward (graph) n_img={n_img}: {ms:.3f} ms  {n_img * 349.2 / ms:.1f} TFLOP/s", flush=True)
+
+
 if __name__ == "__main__":
     for st in sys.argv[1:]:
         print(f"===== {st}", flush=True)
