@@ -102,7 +102,7 @@ def run_ours(args, rank, world, local_rank):
     F, P = args.frames_per_step, args.points
     cfg = EncoderConfig()
     sd = random_state_dict(cfg, seed=0, text=True)
-    enc = RegionEncoder(cfg, sd, max_images=2 * F, max_h=H, max_w=W, max_masks=64, device=dev)
+    enc = RegionEncoder(cfg, sd, max_images=2 * F, max_h=H, max_w=W, max_masks=64 * F, device=dev)
     sm = SemanticMap(dev)
     K, xyz, ids, ins, seg, bm = scene(P, seed=rank)
     M = bm.shape[0]

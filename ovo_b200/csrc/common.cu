@@ -113,6 +113,7 @@ static int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N
   return OVO_OK;
 }
 
+static int g_gemm_debug = 0;
 static int g_gemm_cluster = -1;   // -1 = auto; OVO_B200_GEMM_CLUSTER=1|2|4 forces a cluster size (tuning aid)
 
 template <int EPI>
@@ -156,7 +157,9 @@ static int pick_bn(int M, int N) {
 }
 
 int launch_gemm(int epi, const __nv_bfloat16* A, int lda, const __nv_bfloat16* B, int ldb, int M, int N, int K,
-                const EpiParams& ep, cudaStream_t stream, int force_bn) {
+                const EpiParams& ep_in, cudaStream_t stream, int force_bn) {
+  EpiParams ep = ep_in;
+  ep.debug = g_gemm_debug;
   if (M <= 0 || N <= 0 || K <= 0) return set_error(OVO_E_INVALID, "gemm: empty problem %dx%dx%d", M, N, K);
   const int bn = force_bn > 0 ? force_bn : pick_bn(M, N);
   switch (epi) {
@@ -204,7 +207,10 @@ int ovo_profile_report(int n_classes, float* ms, double* flops, double* bytes, i
   return ovo::PROF_NCLASS;
 }
 
-void ovo_set_gemm_cluster(int cluster_size) { ovo::g_gemm_cluster = cluster_size; }
+void ovo_set_gemm_cluster(int cluster_size) {
+  ovo::g_gemm_cluster = cluster_size & 0xff;
+  ovo::g_gemm_debug = (cluster_size >> 8) & 0xff;   // bits 8..15: tuning experiments (EpiParams::debug)
+}
 
 int ovo_gemm_bf16(const void* A_dev, int lda, const void* B_dev, int ldb, int M, int N, int K, const float* bias_dev,
                   float* C_dev, int ldc, int force_bn, void* stream) {

@@ -387,12 +387,11 @@ int launch_attention(ovo_encoder* e, int n_seq, int seq, int seq_pad, int heads,
   OVO_TRY(make_tmap_bf16_2d(&tq, e->q, bh * seq_pad, 64, 64, 128, 64));
   OVO_TRY(make_tmap_bf16_2d(&tk, e->k, bh * seq_pad, 64, 64, 128, 64));
   OVO_TRY(make_tmap_bf16_2d(&tv, e->vt, bh * 64, seq_pad, seq_pad, 64, 64));
-  const int nblk = seq_pad / 128;
-  const int smem = AttnSmem::bytes(nblk);
-  static int attr_smem = 0;
-  if (smem > attr_smem) {
+  const int smem = AttnSmem::kBytes;
+  static bool attr_set = false;
+  if (!attr_set) {
     OVO_CUDA(cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_smem = smem;
+    attr_set = true;
   }
   const int qtiles = ceil_div(seq, 128);
   const float scale_log2e = 0.125f * 1.4426950408889634f;  // head_dim 64

@@ -39,6 +39,7 @@ struct EpiParams {
   const float* pos = nullptr;  // [1 + patches, width]
   int patches = 0;             // patches per image (576)
   int prof_cls = 0;            // profiling class of this launch (common.cuh ProfClass; host side only)
+  int debug = 0;               // tuning experiments: 1 = no epilogue stores, 2 = no MMA, 4 = no TMA loads
 };
 
 constexpr int kBM = 128;
@@ -235,6 +236,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
         const int tm = (ct / tiles_n) * CS + crank, tn = ct % tiles_n;   // N fastest: concurrent CTAs spread over the weight tiles
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
+          if (ep.debug & 4) { mbar_arrive(&full[stage]); if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; } continue; }
           mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
           tma_load_2d(sA + stage * Cfg::kBytesA, &tmA, &full[stage], kb * kBK, tm * kBM);
           if constexpr (CS == 1) {
@@ -261,9 +263,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
           tc_fence_after();
           const uint64_t adesc = umma_desc_sw128(smem_u32(sA + stage * Cfg::kBytesA));
           const uint64_t bdesc = umma_desc_sw128(smem_u32(sB + stage * Cfg::kBytesB));
+          if (!(ep.debug & 2)) {
 #pragma unroll
-          for (int k = 0; k < kBK / 16; ++k)  // +32 B per K=16 step inside the 128 B swizzle row
-            umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            for (int k = 0; k < kBK / 16; ++k)  // +32 B per K=16 step inside the 128 B swizzle row
+              umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          }
           if constexpr (CS == 1) umma_commit(&empty[stage]);
           else umma_commit_multicast(&empty[stage], kMask);
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
@@ -287,7 +291,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + c * 32, v);
         tmem_ld_wait();
-        epilogue_store<EPI>(ep, row, tn * BN + c * 32, v, M, N, s_rope);
+        if (!(ep.debug & 1)) epilogue_store<EPI>(ep, row, tn * BN + c * 32, v, M, N, s_rope);
       }
       tc_fence_before();
       __syncwarp();

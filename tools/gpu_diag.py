@@ -260,6 +260,27 @@ def stage_clusters():
         print(f"vit forward (graph) n_img={n_img}: {ms:.3f} ms  {n_img * 349.2 / ms:.1f} TFLOP/s", flush=True)
 
 
+def stage_gemmdbg():
+    """Which part bounds the GEMM: full vs no-epilogue-stores vs no-MMA vs no-TMA (EpiParams::debug bits)."""
+    from ovo_b200 import _lib
+    cfg = EncoderConfig(text_layers=0, layers=4)
+    enc, sd, ocfg = _enc(cfg, n_img=16, text=False)
+    px = torch.randn(16, 3, 336, 336, device=dev)
+    for dbg, name in ((0, "full"), (1, "no-epilogue-stores"), (2, "no-mma"), (4, "no-tma"), (6, "no-mma,no-tma"), (7, "nothing")):
+        _lib.lib().ovo_set_gemm_cluster((dbg << 8) | 1)
+        _lib.profile_begin()
+        for _ in range(2):
+            enc.forward_features_from_pixels(px)
+        torch.cuda.synchronize()
+        prof = _lib.profile_report()
+        print(f"{name:22s} 4 layers x16 img: gemm {prof['gemm']['ms'] / 2:.3f} ms ({prof['gemm']['launches'] // 2} launches)", flush=True)
+        for (M, N, K) in [(9232, 4096, 1024), (9232, 1024, 4096), (9232, 1024, 1024)]:
+            A = torch.randn(M, K, device=dev).bfloat16(); B = torch.randn(N, K, device=dev).bfloat16()
+            ms = _time(lambda: gemm_bf16(A, B, None, force_bn=256), n=10)
+            print(f"    f32-out gemm {M}x{N}x{K}: {ms * 1e3:.1f} us  {2 * M * N * K / ms / 1e9:.0f} TFLOP/s", flush=True)
+    _lib.lib().ovo_set_gemm_cluster(0)
+
+
 if __name__ == "__main__":
     for st in sys.argv[1:]:
         print(f"===== {st}", flush=True)
