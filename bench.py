@@ -122,14 +122,22 @@ def run_ours(args, rank, world, local_rank):
     w2cs = [torch.linalg.inv(torch.from_numpy(f["c2w"])).numpy() for f in fr]
     state = dict(next_id=0, n_matched=0)
 
+    side = torch.cuda.Stream(device=dev)
+
     def step():
-        rows = []
-        for i, f in enumerate(fr):
-            votes, nm, state["next_id"] = sm.associate(xyz_d, ins_d, depth_d[i], seg_d, f["c2w"], K, state["next_id"],
-                                                       kf_slot=i, n_masks=M, w2c=w2cs[i])
-            state["n_matched"] = nm
-            rows.append(torch.from_numpy(votes["ins_id"].astype(np.int32)))
+        # the encoder does not depend on the association: enqueue it first, then run the (host-synchronising)
+        # association of the batch on a second stream so its launch/sync latency hides under the ViT
+        main = torch.cuda.current_stream()
+        side.wait_stream(main)
         feats = enc.encode_regions(rgb_d, masks_d, masks_per_frame=[M] * F)
+        rows = []
+        with torch.cuda.stream(side):
+            for i, f in enumerate(fr):
+                votes, nm, state["next_id"] = sm.associate(xyz_d, ins_d, depth_d[i], seg_d, f["c2w"], K, state["next_id"],
+                                                           kf_slot=i, n_masks=M, w2c=w2cs[i])
+                state["n_matched"] = nm
+                rows.append(torch.from_numpy(votes["ins_id"].astype(np.int32)))
+        main.wait_stream(side)
         ins_rows = torch.stack(rows).to(dev, non_blocking=True)          # [F, M] instance id per mask (-1 = none)
         ident = torch.arange(M, dtype=torch.int32, device=dev)
         for i in range(F):

@@ -183,6 +183,14 @@ int ovo_depth_filter(const float* depth_dev, int h, int w, float* out_dev, void*
  * (0 <= kf_slot < 64) for a later ovo_map_fuse_dense. */
 int ovo_map_associate(ovo_map_t* map, const float* xyz_dev, int32_t* ins_ids_dev, int64_t N, const ovo_frame* frame,
                       int* next_ins_id, ovo_vote_row* votes_host, int* n_matched_host, int kf_slot, void* stream);
+/* The same association split in two for a map SHARDED over several GPUs: every rank calls
+ * ovo_map_vote on its own points (no host sync), the ranks sum the returned table (n_masks*(n_ins+1) vote counts
+ * followed by one n_matched counter; the call returns that length) with an all-reduce, then every rank calls
+ * ovo_map_apply with the summed table: all ranks take identical decisions and update their own points. */
+int ovo_map_vote(ovo_map_t* map, const float* xyz_dev, const int32_t* ins_ids_dev, int64_t N, const ovo_frame* frame,
+                 int n_ins, int32_t* table_out_dev, int kf_slot, void* stream);
+int ovo_map_apply(ovo_map_t* map, const int32_t* table_in_dev, int32_t* ins_ids_dev, int* next_ins_id,
+                  ovo_vote_row* votes_host, int* n_matched_host, void* stream);
 /* Copies the matched list of a slot to the caller: pairs (point index, mask index), n from associate. */
 int ovo_map_get_matches(ovo_map_t* map, int kf_slot, int32_t* pairs_dev, int max_pairs, void* stream);
 

@@ -202,3 +202,43 @@ def dense_running_mean(bank: np.ndarray, counts: np.ndarray, pt_idx: np.ndarray,
         bank[p] = bank[p] + (e - bank[p]) / f32(c)
         counts[p] = c
     return bank, counts
+
+
+# ---------------------------------------------------------------------------------------------------
+# The same vote (ovo:240-282) decomposed for a map sharded over several ranks (SURVEY 8e): every rank builds
+# the vote table of its own points, the tables are summed, and every rank takes the same decisions.
+# ---------------------------------------------------------------------------------------------------
+def vote_table(ins_ids: np.ndarray, seg_of_pt: np.ndarray, n_masks: int, n_ins: int) -> np.ndarray:
+    """[n_masks, n_ins+1] int32: column 0 = matched points without an instance, column 1+id = points carrying id."""
+    t = np.zeros((n_masks, n_ins + 1), np.int32)
+    sel = seg_of_pt >= 0
+    np.add.at(t, (seg_of_pt[sel], np.where(ins_ids[sel] >= 0, ins_ids[sel] + 1, 0)), 1)
+    return t
+
+
+def decide_from_table(table: np.ndarray, areas: np.ndarray, track_th: int, next_ins_id: int):
+    """rows (same dicts as track()) and the new next_ins_id from a (summed) vote table."""
+    rows = []
+    for m in range(table.shape[0]):
+        n_un, assigned = int(table[m, 0]), table[m, 1:]
+        n_as = int(assigned.sum())
+        row = dict(mask=m, n_matched=n_un + n_as, n_assigned=n_as, n_unassigned=n_un, mode_id=-1, ins_id=-1, is_new=0,
+                   area=int(areas[m]))
+        if n_as > 0:
+            row["mode_id"] = int(np.argmax(assigned))            # first maximum = smallest id on ties
+        if row["n_matched"] > track_th:
+            if n_as > track_th:
+                row["ins_id"] = row["mode_id"]
+            elif n_un > track_th:
+                row["ins_id"] = next_ins_id; row["is_new"] = 1; next_ins_id += 1
+        rows.append(row)
+    return rows, next_ins_id
+
+
+def apply_decisions(ins_ids: np.ndarray, seg_of_pt: np.ndarray, rows: list) -> np.ndarray:
+    out = ins_ids.copy()
+    mask_ins = np.array([r["ins_id"] for r in rows] + [-1], np.int32)
+    sel = (seg_of_pt >= 0) & (ins_ids == -1)
+    new = mask_ins[seg_of_pt[sel]]
+    out[sel] = np.where(new >= 0, new, -1)
+    return out

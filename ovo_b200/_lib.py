@@ -61,6 +61,8 @@ SIGNATURES = {
     "ovo_depth_filter": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "ovo_map_associate": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, C.POINTER(Frame), C.POINTER(c_int),
                                   C.POINTER(VoteRow), C.POINTER(c_int), c_int, c_void_p]),
+    "ovo_map_vote": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, C.POINTER(Frame), c_int, c_void_p, c_int, c_void_p]),
+    "ovo_map_apply": (c_int, [c_void_p, c_void_p, c_void_p, C.POINTER(c_int), C.POINTER(VoteRow), C.POINTER(c_int), c_void_p]),
     "ovo_map_get_matches": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p]),
     "ovo_map_fuse_dense": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int,
                                    c_void_p]),

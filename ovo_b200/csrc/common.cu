@@ -125,7 +125,8 @@ static int launch_bn(int bn, const __nv_bfloat16* A, int lda, const __nv_bfloat1
   }
   // clusters pay off when there are enough M tiles to share a B tile; the narrow tiles (query, pooling) stay 1-CTA
   int cs = 1;
-  if (bn >= 128 && ceil_div(M, kBM) >= 2) cs = g_gemm_cluster > 0 ? g_gemm_cluster : 2;
+  // measured on B200: the GEMM was epilogue-bound, not L2-bound, and multicast brought nothing -> default 1
+  if (bn >= 128 && ceil_div(M, kBM) >= 2) cs = g_gemm_cluster > 0 ? g_gemm_cluster : 1;
   if (bn < 128 || ceil_div(M, kBM) < cs) cs = 1;
   CUtensorMap ta, tb;
   OVO_TRY(make_tmap_bf16_2d(&ta, A, M, K, lda, kBM, kBK));

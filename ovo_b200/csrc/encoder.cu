@@ -347,6 +347,7 @@ struct ovo_encoder {
   std::map<std::pair<int, int>, AaTable> tables;
   ImgJob* jobs_dev = nullptr;
   int jobs_cap = 0;
+  std::vector<ImgJob> jobs_host;   // last uploaded job list (re-uploaded only when the frame geometry changes)
   int loaded_images = 0;
   // CUDA graphs of the transformer stack, keyed by (n_img, n_layers, ln_post)
   struct GraphEntry { cudaGraphExec_t exec = nullptr; long long launches = 0; int warm = 0; };
@@ -593,8 +594,11 @@ int ovo_encoder_preprocess(ovo_encoder_t* e, const uint8_t* rgb_dev, int n_frame
       }
   }
   const int n_img = static_cast<int>(jobs.size());
-  OVO_CUDA(cudaMemcpyAsync(e->jobs_dev, jobs.data(), jobs.size() * sizeof(ImgJob), cudaMemcpyHostToDevice, s));
-  OVO_CUDA(cudaStreamSynchronize(s));  // jobs is a host temporary
+  if (jobs.size() != e->jobs_host.size() || memcmp(jobs.data(), e->jobs_host.data(), jobs.size() * sizeof(ImgJob)) != 0) {
+    e->jobs_host = jobs;  // persistent host copy: the async upload may outlive this call
+    OVO_CUDA(cudaMemcpyAsync(e->jobs_dev, e->jobs_host.data(), jobs.size() * sizeof(ImgJob), cudaMemcpyHostToDevice, s));
+    OVO_CUDA(cudaStreamSynchronize(s));
+  }
   ProfScope prof(s, PROF_PRE, 0.0, static_cast<double>(n_frames) * H * W * 3 + static_cast<double>(n_img) * e->patches * e->w.patch_kpad * 2);
   aa_resize_h_kernel<<<dim3(ceil_div(S, 128), H, n_img), 128, 0, s>>>(rgb_dev, H, W, e->jobs_dev, e->tab_min, e->tab_size, e->tab_w, S, e->resize_tmp, e->max_h);
   OVO_CHECK_LAUNCH();

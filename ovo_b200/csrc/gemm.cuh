@@ -54,7 +54,8 @@ struct GemmCfg {
   static constexpr int kBytesB = BN * kBK * 2;
   static constexpr int kStageBytes = kBytesA + kBytesB;
   static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kRopeRowsMax * 17 * 8 /*rope table*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kRopeRowsMax * 17 * 8 /*rope table*/ +
+                                    8 * 2048 /*epilogue staging, 32 rows x 64 B per warp*/;
 };
 
 // Exact (erf) GELU of nn.GELU (pe.py:301).  erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, far below the bf16
@@ -171,6 +172,135 @@ __device__ __forceinline__ void epilogue_store(const EpiParams& ep, int row, int
   }
 }
 
+// ---- coalesced epilogue -----------------------------------------------------------------------------------------
+// After tcgen05.ld a thread owns one output ROW (32 columns): storing that directly makes every warp instruction
+// touch 32 different cache lines (measured: the epilogue, not the MMA, bounded the GEMM).  Instead each epilogue
+// warp exchanges 32 rows x 64 B through a private, XOR-swizzled (bank-conflict-free) shared-memory tile so that
+// afterwards lane l holds, for i = 0..3, the 16-byte piece (l & 3) of row 8*i + (l >> 2): a warp store instruction
+// then writes 8 rows x 64 contiguous bytes (full 32-byte sectors).
+__device__ __forceinline__ void stage_exchange(uint8_t* st, int lane, const uint32_t (&in)[16], uint4 (&out)[4]) {
+  __syncwarp();  // the previous exchange has been read by everyone
+  const int sw = (lane >> 1) & 3;
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    *reinterpret_cast<uint4*>(st + lane * 64 + ((j ^ sw) << 4)) = make_uint4(in[4 * j], in[4 * j + 1], in[4 * j + 2], in[4 * j + 3]);
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = 8 * i + (lane >> 2);
+    out[i] = *reinterpret_cast<const uint4*>(st + r * 64 + (((lane & 3) ^ ((r >> 1) & 3)) << 4));
+  }
+}
+
+// One warp handles rows row0..row0+31 (lane = row) x columns col..col+31.  Every lane of the warp must call this.
+template <int EPI>
+__device__ __forceinline__ void epilogue_chunk(const EpiParams& ep, int row0, int lane, int col, const uint32_t (&v)[32],
+                                               int M, int N, const float2* s_rope, uint8_t* st) {
+  if (col >= N) return;  // warp uniform
+  bool fast = (col + 32 <= N);
+  if constexpr (EPI == EPI_F32 || EPI == EPI_F32_RESID)
+    fast = fast && (ep.ldo & 3) == 0 && (reinterpret_cast<uintptr_t>(ep.out) & 15) == 0 &&
+           (EPI != EPI_F32_RESID || ((ep.ldr & 3) == 0 && (reinterpret_cast<uintptr_t>(ep.resid) & 15) == 0));
+  if constexpr (EPI == EPI_BF16 || EPI == EPI_BF16_GELU) fast = fast && (ep.ldo & 7) == 0 && (reinterpret_cast<uintptr_t>(ep.out) & 15) == 0;
+  if constexpr (EPI == EPI_PATCH) fast = false;
+  if (!fast) {  // ragged N / unaligned output (e.g. the [N_points, 20] query result): per-thread row stores
+    epilogue_store<EPI>(ep, row0 + lane, col, v, M, N, s_rope);
+    return;
+  }
+  float acc[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(v[j]);
+  if (ep.bias != nullptr) {
+    const float4* b4 = reinterpret_cast<const float4*>(ep.bias + col);  // col % 32 == 0 -> 128-byte aligned
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 t = __ldg(b4 + j);
+      acc[4 * j] += t.x; acc[4 * j + 1] += t.y; acc[4 * j + 2] += t.z; acc[4 * j + 3] += t.w;
+    }
+  }
+  const int sub = lane & 3, rsub = lane >> 2;
+
+  if constexpr (EPI == EPI_F32 || EPI == EPI_F32_RESID) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {  // two halves of 16 f32 columns = 64 B per row
+      uint32_t in[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) in[j] = __float_as_uint(acc[16 * h + j]);
+      uint4 o[4];
+      stage_exchange(st, lane, in, o);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = row0 + 8 * i + rsub;
+        if (r >= M) continue;
+        const int c = col + 16 * h + 4 * sub;
+        float4 val = make_float4(__uint_as_float(o[i].x), __uint_as_float(o[i].y), __uint_as_float(o[i].z), __uint_as_float(o[i].w));
+        if constexpr (EPI == EPI_F32_RESID) {
+          const float4 rr = *reinterpret_cast<const float4*>(ep.resid + static_cast<size_t>(r) * ep.ldr + c);
+          val.x += rr.x; val.y += rr.y; val.z += rr.z; val.w += rr.w;
+        }
+        *reinterpret_cast<float4*>(static_cast<float*>(ep.out) + static_cast<size_t>(r) * ep.ldo + c) = val;
+      }
+    }
+  } else if constexpr (EPI == EPI_BF16 || EPI == EPI_BF16_GELU) {
+    if constexpr (EPI == EPI_BF16_GELU) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) acc[j] = gelu_erf(acc[j]);
+    }
+    uint32_t in[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) in[j] = pack_bf16(acc[2 * j], acc[2 * j + 1]);
+    uint4 o[4];
+    stage_exchange(st, lane, in, o);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = row0 + 8 * i + rsub;
+      if (r < M) *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(ep.out) + static_cast<size_t>(r) * ep.ldo + col + 8 * sub) = o[i];
+    }
+  } else if constexpr (EPI == EPI_QKV) {
+    const int which = col / ep.width;  // warp uniform: 0 q, 1 k, 2 v
+    const int within = col - which * ep.width;
+    const int head = within >> 6, d0 = within & 63;
+    const int row = row0 + lane;
+    if (which == 2) {  // V^T [b, head, d, seq_pad]: consecutive lanes = consecutive tokens -> 64-byte runs per d
+      if (row < M) {
+        const int b = row / ep.seq, t = row - b * ep.seq;
+        __nv_bfloat16* dst = ep.vt + ((static_cast<size_t>(b) * ep.heads + head) * 64 + d0) * ep.seq_pad + t;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) dst[static_cast<size_t>(j) * ep.seq_pad] = __float2bfloat16_rn(acc[j]);
+      }
+      return;
+    }
+    if (ep.rope_tab != nullptr) {
+      // 2D RoPE with a cls token (rope.py:315-347): interleaved pairs (2i, 2i+1); pairs 0..15 of a head
+      // (d0 == 0) rotate by (x+1)*theta_i, pairs 16..31 (d0 == 32) by (y+1)*theta_i, the cls token by 0.
+      const int t = row % ep.seq;
+      int r = 0;
+      if (t > 0) r = (d0 == 0 ? (t - 1) % ep.rope_grid : (t - 1) / ep.rope_grid) + 1;
+      const float2* tab = s_rope + r * 17;
+#pragma unroll
+      for (int j = 0; j < 32; j += 2) {
+        const float2 cs = tab[j >> 1];
+        const float a = acc[j], bb = acc[j + 1];
+        acc[j] = a * cs.x - bb * cs.y;
+        acc[j + 1] = bb * cs.x + a * cs.y;
+      }
+    }
+    uint32_t in[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) in[j] = pack_bf16(acc[2 * j], acc[2 * j + 1]);
+    uint4 o[4];
+    stage_exchange(st, lane, in, o);
+    __nv_bfloat16* base = which == 0 ? ep.q : ep.k;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = row0 + 8 * i + rsub;
+      if (r >= M) continue;
+      const int b = r / ep.seq, t = r - b * ep.seq;
+      *reinterpret_cast<uint4*>(base + ((static_cast<size_t>(b) * ep.heads + head) * ep.seq_pad + t) * 64 + d0 + 8 * sub) = o[i];
+    }
+  }
+}
+
 // CS = thread-block cluster size along M.  The CS CTAs of a cluster work on CS consecutive M tiles of the SAME
 // N tile; each loads 1/CS of the B tile and TMA-multicasts it to all of them, so L2 operand traffic per CTA and
 // k-block drops from 16 KB + BN*128 B to 16 KB + BN*128/CS B (the kernel is otherwise L2-bandwidth bound).
@@ -192,6 +322,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
   float2* s_rope = reinterpret_cast<float2*>(smem + Cfg::kStages * Cfg::kStageBytes + 256);
+  uint8_t* s_stage = reinterpret_cast<uint8_t*>(s_rope) + kRopeRowsMax * 17 * 8;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -291,7 +422,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + c * 32, v);
         tmem_ld_wait();
-        if (!(ep.debug & 1)) epilogue_store<EPI>(ep, row, tn * BN + c * 32, v, M, N, s_rope);
+        if (!(ep.debug & 1)) epilogue_chunk<EPI>(ep, tm * kBM + quad * 32, lane, tn * BN + c * 32, v, M, N, s_rope, s_stage + (warp - 2) * 2048);
       }
       tc_fence_before();
       __syncwarp();

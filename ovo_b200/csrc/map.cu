@@ -551,6 +551,8 @@ struct ovo_map {
   __nv_bfloat16* text_bf16 = nullptr; size_t text_cap = 0;
   // pinned host staging
   ovo_vote_row* h_rows = nullptr; int32_t* h_counters = nullptr; ovo::FrameDev* h_frame = nullptr;
+  // association split in two calls (ovo_map_vote / ovo_map_apply): state of the pending keyframe
+  bool pend_valid = false; int64_t pend_N = 0; int pend_n_ins = 0, pend_n_masks = 0, pend_slot = 0, pend_track_th = 0;
 };
 
 namespace {
@@ -604,10 +606,12 @@ int ovo_depth_filter(const float* depth_dev, int h, int w, float* out_dev, void*
   return OVO_OK;
 }
 
-int ovo_map_associate(ovo_map_t* m, const float* xyz_dev, int32_t* ins_ids_dev, int64_t N, const ovo_frame* f,
-                      int* next_ins_id, ovo_vote_row* votes_host, int* n_matched_host, int kf_slot, void* stream_) {
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  OVO_REQUIRE(m && f && next_ins_id && votes_host && n_matched_host, "ovo_map_associate: null argument");
+// Phase 1 of the association: frustum, depth filter, mask areas, pass 1 (votes + match list).  No host sync.
+static int associate_vote(ovo_map_t* m, const float* xyz_dev, const int32_t* ins_ids_dev, int64_t N, const ovo_frame* f,
+                          int n_ins_in, int kf_slot, cudaStream_t stream) {
+  OVO_REQUIRE(m && f, "ovo_map_associate: null argument");
+  const int next_ins_id_v = n_ins_in;
+  const int* next_ins_id = &next_ins_id_v;
   OVO_REQUIRE(N >= 0 && N < (1LL << 31), "ovo_map_associate: N out of range");
   OVO_REQUIRE(kf_slot >= 0 && kf_slot < ovo_map::kSlots, "ovo_map_associate: kf_slot out of range");
   OVO_REQUIRE(f->n_masks >= 0 && f->n_masks <= 8192, "ovo_map_associate: n_masks out of range");
@@ -646,7 +650,6 @@ int ovo_map_associate(ovo_map_t* m, const float* xyz_dev, int32_t* ins_ids_dev, 
   OVO_CUDA(cudaMemsetAsync(m->votes, 0, votes_need * sizeof(int32_t), stream));
   OVO_CUDA(cudaMemsetAsync(m->area, 0, (n_masks + 1) * sizeof(int32_t), stream));
 
-  ovo::ProfScope prof(stream, ovo::PROF_ASSOC, 0.0, static_cast<double>(N) * 20 + static_cast<double>(f->h) * f->w * 8);
   const int sms = ovo::num_sms();
   // frustum from the RAW depth (ovo.py:209), match against the filtered depth (ovo.py:213-216)
   ovo::depth_minmax_kernel<<<sms, 256, 0, stream>>>(f->depth_dev, npix, m->geom);
@@ -671,10 +674,24 @@ int ovo_map_associate(ovo_map_t* m, const float* xyz_dev, int32_t* ins_ids_dev, 
         m->counters, smem_votes);
     OVO_CHECK_LAUNCH();
   }
+  m->pend_N = N; m->pend_n_ins = n_ins; m->pend_n_masks = n_masks; m->pend_slot = kf_slot; m->pend_track_th = f->track_th;
+  m->pend_valid = true;
+  return OVO_OK;
+}
+
+// Phase 2: per-mask reduce of the (possibly all-reduced) vote table, id decisions, pass 2, one host sync.
+static int associate_apply(ovo_map_t* m, int32_t* ins_ids_dev, int* next_ins_id, ovo_vote_row* votes_host,
+                           int* n_matched_host, cudaStream_t stream) {
+  OVO_REQUIRE(m && next_ins_id && votes_host && n_matched_host, "ovo_map_associate: null argument");
+  if (!m->pend_valid) return ovo::set_error(OVO_E_STATE, "ovo_map_apply called without a pending ovo_map_vote");
+  m->pend_valid = false;
+  const int64_t N = m->pend_N;
+  const int n_masks = m->pend_n_masks, n_ins = m->pend_n_ins, kf_slot = m->pend_slot, track_th = m->pend_track_th;
+  const int sms = ovo::num_sms();
   if (n_masks > 0) {
     ovo::vote_reduce_kernel<<<n_masks, 128, 0, stream>>>(m->votes, n_ins, m->area, m->rows);
     OVO_CHECK_LAUNCH();
-    ovo::vote_decide_kernel<<<1, 256, 0, stream>>>(m->rows, n_masks, f->track_th, m->mask_ins, m->counters + 2);
+    ovo::vote_decide_kernel<<<1, 256, 0, stream>>>(m->rows, n_masks, track_th, m->mask_ins, m->counters + 2);
     OVO_CHECK_LAUNCH();
     if (N > 0) {
       ovo::associate_pass2_kernel<<<sms * 4, 256, 0, stream>>>(m->scratch_list, m->counters, m->mask_ins, ins_ids_dev);
@@ -694,6 +711,38 @@ int ovo_map_associate(ovo_map_t* m, const float* xyz_dev, int32_t* ins_ids_dev, 
     OVO_CUDA(cudaMemcpyAsync(m->slot_list[kf_slot], m->scratch_list, n_list * sizeof(int2), cudaMemcpyDeviceToDevice, stream));
   m->slot_n[kf_slot] = n_list;
   return OVO_OK;
+}
+
+
+int ovo_map_associate(ovo_map_t* m, const float* xyz_dev, int32_t* ins_ids_dev, int64_t N, const ovo_frame* f,
+                      int* next_ins_id, ovo_vote_row* votes_host, int* n_matched_host, int kf_slot, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  OVO_REQUIRE(next_ins_id && votes_host && n_matched_host, "ovo_map_associate: null argument");
+  ovo::ProfScope prof(stream, ovo::PROF_ASSOC, 0.0, static_cast<double>(N) * 20 + (f ? static_cast<double>(f->h) * f->w * 8 : 0.0));
+  OVO_TRY(associate_vote(m, xyz_dev, ins_ids_dev, N, f, *next_ins_id, kf_slot, stream));
+  return associate_apply(m, ins_ids_dev, next_ins_id, votes_host, n_matched_host, stream);
+}
+
+int ovo_map_vote(ovo_map_t* m, const float* xyz_dev, const int32_t* ins_ids_dev, int64_t N, const ovo_frame* f, int n_ins,
+                 int32_t* table_out_dev, int kf_slot, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  OVO_REQUIRE(table_out_dev != nullptr, "ovo_map_vote: null table");
+  OVO_TRY(associate_vote(m, xyz_dev, ins_ids_dev, N, f, n_ins, kf_slot, stream));
+  const size_t n = static_cast<size_t>(m->pend_n_masks > 0 ? m->pend_n_masks : 1) * (n_ins + 1);
+  OVO_CUDA(cudaMemcpyAsync(table_out_dev, m->votes, n * sizeof(int32_t), cudaMemcpyDeviceToDevice, stream));
+  OVO_CUDA(cudaMemcpyAsync(table_out_dev + n, m->counters + 1, sizeof(int32_t), cudaMemcpyDeviceToDevice, stream));
+  return static_cast<int>(n + 1);
+}
+
+int ovo_map_apply(ovo_map_t* m, const int32_t* table_in_dev, int32_t* ins_ids_dev, int* next_ins_id,
+                  ovo_vote_row* votes_host, int* n_matched_host, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  OVO_REQUIRE(m && table_in_dev, "ovo_map_apply: null argument");
+  if (!m->pend_valid) return ovo::set_error(OVO_E_STATE, "ovo_map_apply called without a pending ovo_map_vote");
+  const size_t n = static_cast<size_t>(m->pend_n_masks > 0 ? m->pend_n_masks : 1) * (m->pend_n_ins + 1);
+  OVO_CUDA(cudaMemcpyAsync(m->votes, table_in_dev, n * sizeof(int32_t), cudaMemcpyDeviceToDevice, stream));
+  OVO_CUDA(cudaMemcpyAsync(m->counters + 1, table_in_dev + n, sizeof(int32_t), cudaMemcpyDeviceToDevice, stream));
+  return associate_apply(m, ins_ids_dev, next_ins_id, votes_host, n_matched_host, stream);
 }
 
 int ovo_map_get_matches(ovo_map_t* m, int kf_slot, int32_t* pairs_dev, int max_pairs, void* stream) {

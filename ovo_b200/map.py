@@ -73,6 +73,42 @@ class SemanticMap:
         votes = {k: arr[:, i].copy() for i, k in enumerate(VOTE_FIELDS)}
         return votes, nm.value, nxt.value
 
+    # ---- the same association in two halves, for a map sharded over ranks (ovo_b200/sharding.py)
+    def _frame(self, depth, seg_map, c2w, K, match_th, track_th, depth_filter, rgb_depth_ratio, n_masks, w2c):
+        c2w = np.asarray(c2w, np.float32).reshape(4, 4)
+        if w2c is None:
+            w2c = torch.linalg.inv(torch.from_numpy(c2w)).numpy()
+        K = np.asarray(K, np.float32).reshape(3, 3)
+        f = Frame()
+        f.depth_dev = ptr(depth); f.h, f.w = depth.shape
+        f.seg_map_dev = ptr(seg_map); f.H, f.W = seg_map.shape
+        f.n_masks = n_masks
+        f.c2w[:] = c2w.reshape(-1).tolist(); f.w2c[:] = np.asarray(w2c, np.float32).reshape(-1).tolist()
+        f.K[:] = K.reshape(-1).tolist()
+        f.match_th, f.track_th, f.depth_filter = float(match_th), int(track_th), int(bool(depth_filter))
+        if len(rgb_depth_ratio) > 0:
+            f.has_ratio, f.ratio_h, f.ratio_w, f.crop_edge = 1, float(rgb_depth_ratio[0]), float(rgb_depth_ratio[1]), int(rgb_depth_ratio[2])
+        return f
+
+    def vote(self, xyz, ins_ids, depth, seg_map, c2w, K, n_ins: int, n_masks: int, match_th=0.05, track_th=100,
+             depth_filter=True, rgb_depth_ratio=(), kf_slot=0, w2c=None) -> torch.Tensor:
+        """Pass 1 on this rank's points: returns the device table [n_masks*(n_ins+1) + 1] i32 (votes, n_matched)."""
+        f = self._frame(depth, seg_map, c2w, K, match_th, track_th, depth_filter, rgb_depth_ratio, n_masks, w2c)
+        table = torch.empty(max(n_masks, 1) * (n_ins + 1) + 1, device=self.device, dtype=torch.int32)
+        self._pending = (ins_ids, n_masks)
+        check(self.lib.ovo_map_vote(self.handle, ptr(xyz), ptr(ins_ids), xyz.shape[0], C.byref(f), n_ins, ptr(table), kf_slot,
+                                    stream_ptr()), "ovo_map_vote")
+        return table
+
+    def apply(self, table: torch.Tensor, next_ins_id: int):
+        """Decisions from the (all-reduced) table + pass 2 on this rank's points -> (votes, n_matched, next_ins_id)."""
+        ins_ids, n_masks = self._pending
+        rows = (VoteRow * max(n_masks, 1))()
+        nxt, nm = C.c_int(next_ins_id), C.c_int(0)
+        check(self.lib.ovo_map_apply(self.handle, ptr(table), ptr(ins_ids), C.byref(nxt), rows, C.byref(nm), stream_ptr()), "ovo_map_apply")
+        arr = np.frombuffer(rows, dtype=np.int32).reshape(-1, 8)[:n_masks]
+        return {k: arr[:, i].copy() for i, k in enumerate(VOTE_FIELDS)}, nm.value, nxt.value
+
     def matches(self, kf_slot: int, n_max: int) -> torch.Tensor:
         """(point index, mask index) pairs of a keyframe slot, [n,2] i32 on the device (unordered)."""
         buf = torch.empty(max(n_max, 1), 2, device=self.device, dtype=torch.int32)
