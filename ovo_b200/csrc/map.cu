@@ -538,7 +538,16 @@ __global__ void __launch_bounds__(256)
 }  // namespace ovo
 
 // =============================================================================================== handle
+// Control block of one association: uploaded with ONE pinned H2D copy (frame constants, geometry init, counters)
+// and read back with ONE D2H copy (counters + per-mask rows, which follow the header in the same allocation).
+struct CtlHeader {
+  ovo::FrameDev frame;
+  ovo::FrameGeom geom;
+  int32_t counters[4];  // [0] match-list length, [1] n_matched, [2] next_ins_id
+};
+
 struct ovo_map {
+  uint8_t* ctl = nullptr; uint8_t* h_ctl = nullptr;
   static constexpr int kSlots = 64;
   ovo::FrameGeom* geom = nullptr;
   ovo::FrameDev* frame = nullptr;
@@ -572,18 +581,32 @@ int grow(T** p, size_t* cap, size_t need) {
 }
 }  // namespace
 
+static int ctl_alloc(ovo_map* m, int masks_cap) {
+  cudaFree(m->ctl); cudaFreeHost(m->h_ctl); cudaFree(m->area); cudaFree(m->mask_ins);
+  m->ctl = nullptr; m->h_ctl = nullptr; m->area = nullptr; m->mask_ins = nullptr;
+  const size_t bytes = sizeof(CtlHeader) + static_cast<size_t>(masks_cap) * sizeof(ovo_vote_row);
+  if (cudaMalloc(&m->ctl, bytes) != cudaSuccess || cudaMallocHost(&m->h_ctl, bytes) != cudaSuccess ||
+      cudaMalloc(&m->area, 2 * static_cast<size_t>(masks_cap) * sizeof(int32_t)) != cudaSuccess)
+    return ovo::set_error(OVO_E_CUDA, "ovo_map: control block allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+  m->mask_ins = m->area + masks_cap;
+  m->masks_cap = masks_cap;
+  CtlHeader* h = reinterpret_cast<CtlHeader*>(m->ctl);
+  m->frame = &h->frame; m->geom = &h->geom; m->counters = h->counters;
+  m->rows = reinterpret_cast<ovo_vote_row*>(m->ctl + sizeof(CtlHeader));
+  CtlHeader* hh = reinterpret_cast<CtlHeader*>(m->h_ctl);
+  m->h_frame = &hh->frame; m->h_counters = hh->counters;
+  m->h_rows = reinterpret_cast<ovo_vote_row*>(m->h_ctl + sizeof(CtlHeader));
+  return OVO_OK;
+}
+
 extern "C" {
 
 int ovo_map_create(ovo_map_t** out) {
   OVO_REQUIRE(out != nullptr, "ovo_map_create: null out");
   ovo_map* m = new ovo_map();
-  if (cudaMalloc(&m->geom, sizeof(ovo::FrameGeom)) != cudaSuccess || cudaMalloc(&m->frame, sizeof(ovo::FrameDev)) != cudaSuccess ||
-      cudaMalloc(&m->counters, 4 * sizeof(int32_t)) != cudaSuccess ||
-      cudaMallocHost(&m->h_counters, 4 * sizeof(int32_t)) != cudaSuccess ||
-      cudaMallocHost(&m->h_frame, sizeof(ovo::FrameDev)) != cudaSuccess) {
-    int r = ovo::set_error(OVO_E_CUDA, "ovo_map_create: %s", cudaGetErrorString(cudaGetLastError()));
+  if (ctl_alloc(m, 256) != OVO_OK) {
     ovo_map_destroy(m);
-    return r;
+    return OVO_E_CUDA;
   }
   *out = m;
   return OVO_OK;
@@ -591,10 +614,9 @@ int ovo_map_create(ovo_map_t** out) {
 
 void ovo_map_destroy(ovo_map_t* m) {
   if (!m) return;
-  cudaFree(m->geom); cudaFree(m->frame); cudaFree(m->counters); cudaFree(m->votes); cudaFree(m->area);
-  cudaFree(m->mask_ins); cudaFree(m->rows); cudaFree(m->scratch_list); cudaFree(m->depth_f); cudaFree(m->text_bf16);
+  cudaFree(m->ctl); cudaFreeHost(m->h_ctl); cudaFree(m->votes); cudaFree(m->area);
+  cudaFree(m->scratch_list); cudaFree(m->depth_f); cudaFree(m->text_bf16);
   for (int i = 0; i < ovo_map::kSlots; ++i) cudaFree(m->slot_list[i]);
-  cudaFreeHost(m->h_rows); cudaFreeHost(m->h_counters); cudaFreeHost(m->h_frame);
   delete m;
 }
 
@@ -624,14 +646,7 @@ static int associate_vote(ovo_map_t* m, const float* xyz_dev, const int32_t* ins
 
   // workspaces
   OVO_TRY(grow(&m->votes, &m->votes_cap, votes_need));
-  if (n_masks + 1 > m->masks_cap) {
-    cudaFree(m->area); cudaFree(m->mask_ins); cudaFree(m->rows); cudaFreeHost(m->h_rows);
-    m->masks_cap = n_masks + 64;
-    OVO_CUDA(cudaMalloc(&m->area, m->masks_cap * sizeof(int32_t)));
-    OVO_CUDA(cudaMalloc(&m->mask_ins, m->masks_cap * sizeof(int32_t)));
-    OVO_CUDA(cudaMalloc(&m->rows, m->masks_cap * sizeof(ovo_vote_row)));
-    OVO_CUDA(cudaMallocHost(&m->h_rows, m->masks_cap * sizeof(ovo_vote_row)));
-  }
+  if (n_masks + 1 > m->masks_cap) OVO_TRY(ctl_alloc(m, n_masks + 64));
   OVO_TRY(grow(&m->scratch_list, &m->scratch_cap, static_cast<size_t>(N > 0 ? N : 1)));
   const int npix = f->h * f->w;
   OVO_TRY(grow(&m->depth_f, &m->depth_cap, static_cast<size_t>(npix)));
@@ -641,14 +656,13 @@ static int associate_vote(ovo_map_t* m, const float* xyz_dev, const int32_t* ins
   memcpy(hf->c2w, f->c2w, sizeof(hf->c2w)); memcpy(hf->w2c, f->w2c, sizeof(hf->w2c)); memcpy(hf->K, f->K, sizeof(hf->K));
   hf->match_th = f->match_th; hf->h = f->h; hf->w = f->w; hf->H = f->H; hf->W = f->W;
   hf->has_ratio = f->has_ratio; hf->ratio_h = f->ratio_h; hf->ratio_w = f->ratio_w; hf->crop_edge = f->crop_edge;
-  OVO_CUDA(cudaMemcpyAsync(m->frame, hf, sizeof(ovo::FrameDev), cudaMemcpyHostToDevice, stream));
-  ovo::FrameGeom init{};
-  init.dmin_bits = 0x7f800000; init.dmax_bits = 0;
-  OVO_CUDA(cudaMemcpyAsync(m->geom, &init, sizeof(init), cudaMemcpyHostToDevice, stream));
+  CtlHeader* hh = reinterpret_cast<CtlHeader*>(m->h_ctl);
+  memset(&hh->geom, 0, sizeof(hh->geom));
+  hh->geom.dmin_bits = 0x7f800000; hh->geom.dmax_bits = 0;
   m->h_counters[0] = 0; m->h_counters[1] = 0; m->h_counters[2] = n_ins; m->h_counters[3] = 0;
-  OVO_CUDA(cudaMemcpyAsync(m->counters, m->h_counters, 4 * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
+  OVO_CUDA(cudaMemcpyAsync(m->ctl, m->h_ctl, sizeof(CtlHeader), cudaMemcpyHostToDevice, stream));   // one pinned upload
   OVO_CUDA(cudaMemsetAsync(m->votes, 0, votes_need * sizeof(int32_t), stream));
-  OVO_CUDA(cudaMemsetAsync(m->area, 0, (n_masks + 1) * sizeof(int32_t), stream));
+  OVO_CUDA(cudaMemsetAsync(m->area, 0, static_cast<size_t>(n_masks + 1) * sizeof(int32_t), stream));
 
   const int sms = ovo::num_sms();
   // frustum from the RAW depth (ovo.py:209), match against the filtered depth (ovo.py:213-216)
@@ -697,9 +711,9 @@ static int associate_apply(ovo_map_t* m, int32_t* ins_ids_dev, int* next_ins_id,
       ovo::associate_pass2_kernel<<<sms * 4, 256, 0, stream>>>(m->scratch_list, m->counters, m->mask_ins, ins_ids_dev);
       OVO_CHECK_LAUNCH();
     }
-    OVO_CUDA(cudaMemcpyAsync(m->h_rows, m->rows, n_masks * sizeof(ovo_vote_row), cudaMemcpyDeviceToHost, stream));
   }
-  OVO_CUDA(cudaMemcpyAsync(m->h_counters, m->counters, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+  OVO_CUDA(cudaMemcpyAsync(m->h_counters, m->counters, 4 * sizeof(int32_t) + static_cast<size_t>(n_masks) * sizeof(ovo_vote_row),
+                           cudaMemcpyDeviceToHost, stream));   // counters + rows are contiguous: one read-back
   OVO_CUDA(cudaStreamSynchronize(stream));  // the one host sync of the association step
   if (n_masks > 0) memcpy(votes_host, m->h_rows, n_masks * sizeof(ovo_vote_row));
   *n_matched_host = m->h_counters[1];
