@@ -255,7 +255,8 @@ def run_e2e(args, rank, world, dev, enc, K, xyz, ids, ins, seg, bm, fr, dist):
 
     config = {"segment_every": 1, "match_distance_th": 0.05, "track_th": 100, "depth_filter": True, "log": False,
               "kf_queue_delay": 0, "verbose": False, "dense_map": True, "sam": {"precomputed": True, "masks_base_path": ""},
-              "clip": {"embed_type": "TextRegion", "model_card": "PE-Core-L14-336", "k_top_views": 10000, "fusion": "avg_pooling"}}
+              "clip": {"embed_type": "TextRegion", "model_card": "PE-Core-L14-336", "k_top_views": 10000, "fusion": "avg_pooling",
+                       "batch_keyframes": len(fr)}}
     clip = CLIPGenerator(config["clip"], encoder=enc)       # share the already-built encoder (weights are 0.7 GB)
     ovo = OVO(config, _Logger(), scene_name=None, cam_intrinsics=torch.from_numpy(K), eval=True, clip_generator=clip, device="cuda")
     ovo.mask_generator = HostMasks()
@@ -263,16 +264,16 @@ def run_e2e(args, rank, world, dev, enc, K, xyz, ids, ins, seg, bm, fr, dist):
     state = dict(pins=torch.from_numpy(ins).to(dev))
     imgs = [torch.from_numpy(f["image"]).pin_memory().numpy() for f in fr]
     deps = [torch.from_numpy(f["depth"]).pin_memory().numpy() for f in fr]
-    out_host = torch.empty(bm.shape[0], enc.cfg.output_dim).pin_memory()
+    out_host = torch.empty(len(fr) * bm.shape[0], enc.cfg.output_dim).pin_memory()
 
     def step():
+        n0 = ovo._store_n
         for i, f in enumerate(fr):
             upd = ovo.detect_and_track_objects((f["frame_id"], imgs[i], deps[i], ()), (pts, pids, state["pins"]), torch.from_numpy(f["c2w"]))
             state["pins"] = upd
-            n0 = ovo._store_n
-            ovo.compute_semantic_info()
-            n = ovo._store_n - n0
-            out_host[:n].copy_(ovo._store[n0:n0 + n], non_blocking=True)
+            ovo.compute_semantic_info()          # encodes when `batch_keyframes` keyframes are queued
+        n = ovo._store_n - n0
+        out_host[:n].copy_(ovo._store[n0:n0 + n], non_blocking=True)     # the step's new descriptors, read back
         torch.cuda.synchronize()
         if ovo._store_n > 200000:            # keep the descriptor store bounded over long runs
             ovo._store_n = 0
@@ -299,7 +300,7 @@ def run_e2e(args, rank, world, dev, enc, K, xyz, ids, ins, seg, bm, fr, dist):
     h2d = F * (imgs[0].nbytes + deps[0].nbytes + seg.nbytes + bm.nbytes)
     d2h = F * (bm.shape[0] * enc.cfg.output_dim * 4 + bm.shape[0] * 32)
     return {"value": round(world * F * steps / (ms / 1e3), 2), "unit": "keyframes/s", "h2d_bytes_per_step": int(h2d),
-            "d2h_bytes_per_step": int(d2h), "api": "ovo_b200.OVO.detect_and_track_objects + compute_semantic_info, one keyframe per call",
+            "d2h_bytes_per_step": int(d2h), "api": "ovo_b200.OVO.detect_and_track_objects + compute_semantic_info per keyframe (clip.batch_keyframes = frames/step)",
             "steps": steps}
 
 

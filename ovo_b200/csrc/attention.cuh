@@ -114,6 +114,9 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
     const int kv0 = j * 128;
     int kv_hi = seq - kv0;                           // keys >= seq are padding
     if (causal) kv_hi = min(kv_hi, qrow - kv0 + 1);  // keys > query are masked
+    // blocks that are entirely valid (all but the last one, and no causal diagonal) skip the per-element masking:
+    // the softmax is instruction-issue bound, every instruction per score counts
+    const bool full = !causal && (kv0 + 128 <= seq);   // CTA uniform
     // pass 1: row max
     float m_blk = -INFINITY;
 #pragma unroll 1
@@ -121,13 +124,18 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
       uint32_t v[32];
       tmem_ld_32x32(tmem_S + lane_off + c * 32, v);
       tmem_ld_wait();
+      if (full) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i)
-        if (c * 32 + i < kv_hi) m_blk = fmaxf(m_blk, __uint_as_float(v[i]));
+        for (int i = 0; i < 32; ++i) m_blk = fmaxf(m_blk, __uint_as_float(v[i]));
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (c * 32 + i < kv_hi) m_blk = fmaxf(m_blk, __uint_as_float(v[i]));
+      }
     }
     const float m_new = fmaxf(m_run, m_blk);
     const float m_scaled = (m_new == -INFINITY) ? 0.f : m_new * scale_log2e;
-    const float alpha = (m_run == -INFINITY) ? 0.f : exp2f(m_run * scale_log2e - m_scaled);
+    const float alpha = (m_run == -INFINITY) ? 0.f : fast_ex2(m_run * scale_log2e - m_scaled);
     // pass 2: p = exp2(s*scale - m), row sum, P -> swizzled smem (bf16)
     float l_blk = 0.f;
 #pragma unroll 1
@@ -136,10 +144,15 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
       tmem_ld_32x32(tmem_S + lane_off + c * 32, v);
       tmem_ld_wait();
       float p[32];
+      if (full) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const float e = exp2f(__uint_as_float(v[i]) * scale_log2e - m_scaled);
-        p[i] = (c * 32 + i < kv_hi) ? e : 0.f;
+        for (int i = 0; i < 32; ++i) p[i] = fast_ex2(fmaf(__uint_as_float(v[i]), scale_log2e, -m_scaled));
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float e = fast_ex2(fmaf(__uint_as_float(v[i]), scale_log2e, -m_scaled));
+          p[i] = (c * 32 + i < kv_hi) ? e : 0.f;
+        }
       }
       uint8_t* tile = p_row + (c >> 1) * (128 * 128);  // keys 0-63 -> tile 0, 64-127 -> tile 1
 #pragma unroll

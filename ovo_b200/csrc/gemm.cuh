@@ -62,12 +62,12 @@ struct GemmCfg {
 // rounding of the output): ~14 instructions instead of erff's ~25 — the fc epilogue is issue-bound otherwise.
 __device__ __forceinline__ float gelu_erf(float x) {
   const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  const float t = fast_rcp(fmaf(0.3275911f, z, 1.0f));
   float p = fmaf(1.061405429f, t, -1.453152027f);
   p = fmaf(p, t, 1.421413741f);
   p = fmaf(p, t, -0.284496736f);
   p = fmaf(p, t, 0.254829592f);
-  const float e = 1.0f - p * t * exp2f(-1.4426950408889634f * z * z);   // erf(|x|/sqrt2)
+  const float e = 1.0f - p * t * fast_ex2(-1.4426950408889634f * z * z);   // erf(|x|/sqrt2)
   return 0.5f * x * (1.0f + copysignf(e, x));
 }
 

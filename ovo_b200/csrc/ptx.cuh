@@ -163,6 +163,18 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
          (static_cast<uint32_t>(M >> 4) << 24);
 }
 
+// single-instruction MUFU approximations (2 ulp): exp2 and reciprocal without the range fix-ups of exp2f / 1.f/x
+__device__ __forceinline__ float fast_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float fast_rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);

@@ -229,41 +229,81 @@ class OVO:
 
     # ------------------------------------------------------------------------------------------ keyframe: descriptors
     def compute_semantic_info(self) -> None:
-        if len(self.keyframes_queue) > self.config.get("kf_queue_delay", 0):
-            self._compute_semantic_info()
+        """ovo.py:326-328.  With `clip.batch_keyframes: B` (default 1 = the reference's cadence) descriptors are
+        computed for B queued keyframes at a time: one ViT pass over 2B images instead of B passes over 2."""
+        delay, B = self.config.get("kf_queue_delay", 0), max(1, int(self.config["clip"].get("batch_keyframes", 1)))
+        if B == 1:
+            if len(self.keyframes_queue) > delay:
+                self._compute_semantic_batch(1)
+        else:
+            while len(self.keyframes_queue) - delay >= B:
+                self._compute_semantic_batch(B)
 
     def complete_semantic_info(self) -> None:
+        B = max(1, int(self.config["clip"].get("batch_keyframes", 1)))
         while len(self.keyframes_queue) > 0:
-            self._compute_semantic_info()
+            self._compute_semantic_batch(min(B, len(self.keyframes_queue)))
 
     def _compute_semantic_info(self) -> None:
-        """ovo.py:334-364."""
-        matched_ins_ids, binary_maps, image, kf_id, extra = self.keyframes_queue.popleft()
-        if len(matched_ins_ids) == 0:
+        self._compute_semantic_batch(1)
+
+    def _compute_semantic_batch(self, n: int) -> None:
+        """ovo.py:334-364 for the first n keyframes of the queue (encoded together, bookkeeping in queue order)."""
+        items = []
+        for _ in range(n):
+            matched_ins_ids, binary_maps, image, kf_id, extra = self.keyframes_queue.popleft()
+            if len(matched_ins_ids) == 0:
+                continue
+            mask_row = extra["mask_row"]
+            if self.n_top_views > 0:
+                sel = [j for j, ins in enumerate(matched_ins_ids) if self.objects[ins].is_top_kf(kf_id)]
+                if len(sel) == 0:
+                    continue
+                if len(sel) != len(matched_ins_ids):
+                    remap = np.full(len(matched_ins_ids), -1, np.int32)
+                    remap[sel] = np.arange(len(sel), dtype=np.int32)
+                    remap_d = torch.from_numpy(remap).to(self._dev)
+                    mask_row = torch.where(mask_row >= 0, remap_d[mask_row.clamp_min(0).long()], mask_row)
+                    matched_ins_ids = [matched_ins_ids[j] for j in sel]
+                    binary_maps = binary_maps[torch.as_tensor(sel, device=self._dev, dtype=torch.long)]
+            items.append((matched_ins_ids, binary_maps, image, kf_id, extra["slot"], mask_row))
+        if not items:
             return
-        mask_row = extra["mask_row"]
-        if self.n_top_views > 0:
-            sel = [j for j, ins in enumerate(matched_ins_ids) if self.objects[ins].is_top_kf(kf_id)]
-            if len(sel) == 0:
-                return
-            if len(sel) != len(matched_ins_ids):
-                remap = np.full(len(matched_ins_ids), -1, np.int32)
-                remap[sel] = np.arange(len(sel), dtype=np.int32)
-                remap_d = torch.from_numpy(remap).to(self._dev)
-                mask_row = torch.where(mask_row >= 0, remap_d[mask_row.clamp_min(0).long()], mask_row)
-                matched_ins_ids = [matched_ins_ids[j] for j in sel]
-                binary_maps = binary_maps[torch.as_tensor(sel, device=self._dev, dtype=torch.long)]
-        rows = self._extract_clip(image, binary_maps)
-        self._update_matched_objects_clip(rows, matched_ins_ids, kf_id)
-        if self.dense:
-            n = len(matched_ins_ids)
-            self.semmap.fuse_dense(extra["slot"], self._dense_bank, self._dense_counts,
-                                   self._store[rows[0]: rows[0] + n], mask_row.contiguous())
-        if self.config.get("log", False):
-            frame_id = self.keyframes["frame_id"][kf_id]
-            self.logger.log_ovo_stats({"frame_id": frame_id, "t_clip": round(self._time_cache[0], 2),
-                                       "t_up": round(self._time_cache[1], 3)}, print_output=True)
+        same_shape = all(it[2].shape == items[0][2].shape for it in items)
+        groups = [items] if same_shape else [[it] for it in items]
+        for group in groups:
+            rows_per_kf = self._extract_clip_batch([it[2] for it in group], [it[1] for it in group])
+            for (ids, _, _, kf_id, slot, mask_row), rows in zip(group, rows_per_kf):
+                self._update_matched_objects_clip(rows, ids, kf_id)
+                if self.dense:
+                    self.semmap.fuse_dense(slot, self._dense_bank, self._dense_counts,
+                                           self._store[rows[0]: rows[0] + len(ids)], mask_row.contiguous())
+                if self.config.get("log", False):
+                    frame_id = self.keyframes["frame_id"][kf_id]
+                    self.logger.log_ovo_stats({"frame_id": frame_id, "t_clip": round(self._time_cache[0], 2),
+                                               "t_up": round(self._time_cache[-1], 3)}, print_output=True)
             self._time_cache = []
+
+    @profil
+    def _extract_clip_batch(self, images: List[np.ndarray], maps: List[torch.Tensor]) -> List[List[int]]:
+        """ovo.py:426-437 for a batch of keyframes: descriptors are written straight into the device descriptor
+        store; returns the store rows per keyframe."""
+        counts = [int(m.shape[0]) for m in maps]
+        M = sum(counts)
+        self._grow_store(self._store_n + M)
+        if len(images) == 1:
+            img = torch.from_numpy(np.ascontiguousarray(images[0])).to(self._dev, non_blocking=True)[None]
+        else:
+            img = torch.stack([torch.from_numpy(np.ascontiguousarray(im)) for im in images]).to(self._dev, non_blocking=True)
+        masks = maps[0] if len(maps) == 1 else torch.cat(maps)
+        feats = self.clip_generator.encoder.encode_regions(img, masks, masks_per_frame=counts)
+        self._store[self._store_n: self._store_n + M].copy_(feats)
+        out, r0 = [], self._store_n
+        for c in counts:
+            out.append(list(range(r0, r0 + c)))
+            r0 += c
+        self._store_n += M
+        return out
 
     @profil
     def _extract_clip(self, image: np.ndarray, binary_maps: torch.Tensor) -> List[int]:
