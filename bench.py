@@ -123,6 +123,7 @@ def run_ours(args, rank, world, local_rank):
     state = dict(next_id=0, n_matched=0)
 
     side = torch.cuda.Stream(device=dev)
+    ident_all = torch.arange(F * M, dtype=torch.int32, device=dev).reshape(F, M)
 
     def step():
         # the encoder does not depend on the association: enqueue it first, then run the (host-synchronising)
@@ -139,10 +140,11 @@ def run_ours(args, rank, world, local_rank):
                 rows.append(torch.from_numpy(votes["ins_id"].astype(np.int32)))
         main.wait_stream(side)
         ins_rows = torch.stack(rows).to(dev, non_blocking=True)          # [F, M] instance id per mask (-1 = none)
-        ident = torch.arange(M, dtype=torch.int32, device=dev)
+        # dense per-point fusion of all F keyframes in one pass over the bank (bit-identical to F passes), then the
+        # instance bank
+        mask_row = torch.where(ins_rows >= 0, ident_all, -1)
+        sm.fuse_dense_batch(list(range(F)), bank, counts, feats, mask_row)
         for i in range(F):
-            mask_row = torch.where(ins_rows[i] >= 0, ident, -1)
-            sm.fuse_dense(i, bank, counts, feats[i * M:(i + 1) * M], mask_row)
             sm.bank_update_mean(ibank, icounts, feats[i * M:(i + 1) * M], ins_rows[i])
         return feats
 
@@ -264,7 +266,8 @@ def run_e2e(args, rank, world, dev, enc, K, xyz, ids, ins, seg, bm, fr, dist):
     state = dict(pins=torch.from_numpy(ins).to(dev))
     imgs = [torch.from_numpy(f["image"]).pin_memory().numpy() for f in fr]
     deps = [torch.from_numpy(f["depth"]).pin_memory().numpy() for f in fr]
-    out_host = torch.empty(len(fr) * bm.shape[0], enc.cfg.output_dim).pin_memory()
+    out_host = [torch.empty(len(fr) * bm.shape[0], enc.cfg.output_dim).pin_memory() for _ in range(2)]
+    state["k"] = 0
 
     def step():
         n0 = ovo._store_n
@@ -272,10 +275,12 @@ def run_e2e(args, rank, world, dev, enc, K, xyz, ids, ins, seg, bm, fr, dist):
             upd = ovo.detect_and_track_objects((f["frame_id"], imgs[i], deps[i], ()), (pts, pids, state["pins"]), torch.from_numpy(f["c2w"]))
             state["pins"] = upd
             ovo.compute_semantic_info()          # encodes when `batch_keyframes` keyframes are queued
-        n = ovo._store_n - n0
-        out_host[:n].copy_(ovo._store[n0:n0 + n], non_blocking=True)     # the step's new descriptors, read back
-        torch.cuda.synchronize()
+        # the step's new descriptors are read back to pinned host memory (asynchronously, behind the encoder: the
+        # host goes on with the next keyframes' association while the ViT of this batch runs)
+        ovo.descriptors_since(n0, out_host[state["k"] & 1])
+        state["k"] += 1
         if ovo._store_n > 200000:            # keep the descriptor store bounded over long runs
+            torch.cuda.synchronize()
             ovo._store_n = 0
             ovo.keyframes["ins_descriptors"].clear()
 

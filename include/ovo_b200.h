@@ -201,6 +201,14 @@ int ovo_map_get_matches(ovo_map_t* map, int kf_slot, int32_t* pairs_dev, int max
 int ovo_map_fuse_dense(ovo_map_t* map, int kf_slot, void* bank_dev, int32_t* counts_dev, int64_t N, int D,
                        const float* feats_dev, const int32_t* mask_row_dev, int n_masks, void* stream);
 
+/* The same update for SEVERAL keyframes in one pass over the bank (keyframe order preserved, bit-identical to
+ * n_slots consecutive ovo_map_fuse_dense calls): a point matched in k keyframes has its row read and written once
+ * instead of k times.  feats_dev f32 [R, D] holds the descriptors of all keyframes; mask_row_dev i32
+ * [n_slots, n_masks] maps (keyframe, mask) to a row of feats_dev or -1. */
+int ovo_map_fuse_dense_batch(ovo_map_t* map, const int* kf_slots_host, int n_slots, void* bank_dev, int32_t* counts_dev,
+                             int64_t N, int D, const float* feats_dev, const int32_t* mask_row_dev, int n_masks,
+                             void* stream);
+
 /* Instance-bank running mean, fusion 'avg_pooling' (instance3d.py:19-21,157-189):
  * bank[row[i]] = (bank[row[i]]*cnt + feats[i]) / (cnt+1), not re-normalised. bank f32 [I,D]. */
 int ovo_bank_update_mean(float* bank_dev, int32_t* counts_dev, int D, const float* feats_dev,

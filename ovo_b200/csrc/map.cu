@@ -396,6 +396,85 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// ------------------------------------------------------------------------------------------ batched dense fusion
+// Several keyframes fused in ONE pass over the bank: a point matched in k keyframes of the batch has its 2 KB row
+// read once and written once instead of k times.  The arithmetic per point is the same sequence of updates
+// (keyframe order, bf16 rounding after every update), so the result is bit-identical to k fuse_dense_kernel calls.
+__global__ void scatter_matches_kernel(const int2* __restrict__ list, int n, int16_t* __restrict__ seg_of_pt) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int2 e = list[i];
+    seg_of_pt[e.x] = static_cast<int16_t>(e.y);
+  }
+}
+
+template <int kVecPerLane>
+__global__ void __launch_bounds__(256)
+    fuse_dense_batch_kernel(const int16_t* __restrict__ seg_of_pt /* [F][N] */, int F, long long N,
+                            __nv_bfloat16* __restrict__ bank, int32_t* __restrict__ counts, int D,
+                            const float* __restrict__ feats, const int32_t* __restrict__ mask_row /* [F][n_masks] */,
+                            int n_masks) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const long long n_warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  const int nvec = D >> 3;
+  for (long long p0 = warp * 32; p0 < N; p0 += n_warps * 32) {
+    // lane l looks at point p0+l: which keyframes of the batch matched it into a mask that produced a descriptor?
+    const long long pl = p0 + lane;
+    unsigned fmask = 0;  // bit f set -> keyframe f updates this point
+    if (pl < N) {
+      for (int f = 0; f < F; ++f) {
+        const int m = seg_of_pt[static_cast<size_t>(f) * N + pl];
+        if (m >= 0 && m < n_masks && mask_row[f * n_masks + m] >= 0) fmask |= 1u << f;
+      }
+    }
+    unsigned todo = __ballot_sync(0xffffffffu, fmask != 0);
+    while (todo) {
+      const int src = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const long long p = p0 + src;
+      const unsigned fm = __shfl_sync(0xffffffffu, fmask, src);
+      int c = counts[p];
+      uint4* prow = reinterpret_cast<uint4*>(bank + static_cast<size_t>(p) * D);
+      uint4 raw[kVecPerLane];
+#pragma unroll
+      for (int i = 0; i < kVecPerLane; ++i) {
+        const int v = lane + 32 * i;
+        if (v < nvec) raw[i] = prow[v];
+      }
+      for (int f = 0; f < F; ++f) {
+        if (!((fm >> f) & 1u)) continue;
+        const int r = mask_row[f * n_masks + seg_of_pt[static_cast<size_t>(f) * N + p]];
+        ++c;
+        const float cf = static_cast<float>(c);
+        const float4* frow = reinterpret_cast<const float4*>(feats + static_cast<size_t>(r) * D);
+#pragma unroll
+        for (int i = 0; i < kVecPerLane; ++i) {
+          const int v = lane + 32 * i;
+          if (v < nvec) {
+            const float4 e0 = __ldg(frow + 2 * v), e1 = __ldg(frow + 2 * v + 1);
+            const float ev[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+            uint32_t* w = reinterpret_cast<uint32_t*>(&raw[i]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              __nv_bfloat162 b2 = *reinterpret_cast<__nv_bfloat162*>(&w[j]);
+              float f0 = __bfloat162float(b2.x), f1 = __bfloat162float(b2.y);
+              f0 = __fadd_rn(f0, __fdiv_rn(__fsub_rn(ev[2 * j], f0), cf));
+              f1 = __fadd_rn(f1, __fdiv_rn(__fsub_rn(ev[2 * j + 1], f1), cf));
+              w[j] = pack_bf16(f0, f1);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < kVecPerLane; ++i) {
+        const int v = lane + 32 * i;
+        if (v < nvec) prow[v] = raw[i];
+      }
+      if (lane == 0) counts[p] = c;
+    }
+  }
+}
+
 __global__ void bank_update_mean_kernel(float* __restrict__ bank, int32_t* __restrict__ counts, int D,
                                         const float* __restrict__ feats, const int32_t* __restrict__ rows, int n) {
   const int i = blockIdx.x;
@@ -556,6 +635,7 @@ struct ovo_map {
   int32_t* area = nullptr; int32_t* mask_ins = nullptr; ovo_vote_row* rows = nullptr; int masks_cap = 0;
   int2* scratch_list = nullptr; size_t scratch_cap = 0;
   float* depth_f = nullptr; size_t depth_cap = 0;
+  int16_t* seg_dense = nullptr; size_t seg_dense_cap = 0;   // [F][N] scratch of ovo_map_fuse_dense_batch
   int2* slot_list[kSlots] = {}; size_t slot_cap[kSlots] = {}; int slot_n[kSlots] = {};
   __nv_bfloat16* text_bf16 = nullptr; size_t text_cap = 0;
   // pinned host staging
@@ -615,7 +695,7 @@ int ovo_map_create(ovo_map_t** out) {
 void ovo_map_destroy(ovo_map_t* m) {
   if (!m) return;
   cudaFree(m->ctl); cudaFreeHost(m->h_ctl); cudaFree(m->votes); cudaFree(m->area);
-  cudaFree(m->scratch_list); cudaFree(m->depth_f); cudaFree(m->text_bf16);
+  cudaFree(m->scratch_list); cudaFree(m->depth_f); cudaFree(m->seg_dense); cudaFree(m->text_bf16);
   for (int i = 0; i < ovo_map::kSlots; ++i) cudaFree(m->slot_list[i]);
   delete m;
 }
@@ -786,6 +866,39 @@ int ovo_map_fuse_dense(ovo_map_t* m, int kf_slot, void* bank_dev, int32_t* count
   else
     ovo::fuse_dense_kernel<8><<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
         m->slot_list[kf_slot], n, static_cast<__nv_bfloat16*>(bank_dev), counts_dev, D, feats_dev, mask_row_dev);
+  OVO_CHECK_LAUNCH();
+  return OVO_OK;
+}
+
+int ovo_map_fuse_dense_batch(ovo_map_t* m, const int* kf_slots_host, int n_slots, void* bank_dev, int32_t* counts_dev,
+                             int64_t N, int D, const float* feats_dev, const int32_t* mask_row_dev, int n_masks,
+                             void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  OVO_REQUIRE(m && kf_slots_host && bank_dev && counts_dev && feats_dev && mask_row_dev, "ovo_map_fuse_dense_batch: null argument");
+  OVO_REQUIRE(n_slots > 0 && n_slots <= 32 && N > 0 && N < (1LL << 31) && D > 0 && D % 8 == 0 && D <= 2048 && n_masks > 0 && n_masks < 32768,
+              "ovo_map_fuse_dense_batch: bad shape (slots %d, N %lld, D %d, masks %d)", n_slots, (long long)N, D, n_masks);
+  long long total = 0;
+  for (int i = 0; i < n_slots; ++i) {
+    OVO_REQUIRE(kf_slots_host[i] >= 0 && kf_slots_host[i] < ovo_map::kSlots, "ovo_map_fuse_dense_batch: bad slot");
+    total += m->slot_n[kf_slots_host[i]];
+  }
+  if (total == 0) return OVO_OK;
+  const size_t need = static_cast<size_t>(n_slots) * N;
+  OVO_TRY(grow(&m->seg_dense, &m->seg_dense_cap, need));
+  ovo::ProfScope prof(stream, ovo::PROF_FUSE, 0.0, static_cast<double>(total) * (4.0 * D + 12));
+  OVO_CUDA(cudaMemsetAsync(m->seg_dense, 0xff, need * sizeof(int16_t), stream));   // -1 everywhere
+  const int sms = ovo::num_sms();
+  for (int i = 0; i < n_slots; ++i) {
+    const int s = kf_slots_host[i], n = m->slot_n[s];
+    if (n == 0) continue;
+    ovo::scatter_matches_kernel<<<std::min(ovo::ceil_div(n, 256), sms * 4), 256, 0, stream>>>(m->slot_list[s], n, m->seg_dense + static_cast<size_t>(i) * N);
+    OVO_CHECK_LAUNCH();
+  }
+  const int blocks = static_cast<int>(std::min<long long>((N + 255) / 256, sms * 8LL));
+  if (D <= 1024)
+    ovo::fuse_dense_batch_kernel<4><<<blocks, 256, 0, stream>>>(m->seg_dense, n_slots, N, static_cast<__nv_bfloat16*>(bank_dev), counts_dev, D, feats_dev, mask_row_dev, n_masks);
+  else
+    ovo::fuse_dense_batch_kernel<8><<<blocks, 256, 0, stream>>>(m->seg_dense, n_slots, N, static_cast<__nv_bfloat16*>(bank_dev), counts_dev, D, feats_dev, mask_row_dev, n_masks);
   OVO_CHECK_LAUNCH();
   return OVO_OK;
 }

@@ -122,6 +122,15 @@ class SemanticMap:
         check(self.lib.ovo_map_fuse_dense(self.handle, kf_slot, ptr(bank), ptr(counts), bank.shape[0], bank.shape[1],
                                           ptr(feats), ptr(mask_row), mask_row.shape[0], stream_ptr()), "ovo_map_fuse_dense")
 
+    def fuse_dense_batch(self, kf_slots, bank: torch.Tensor, counts: torch.Tensor, feats: torch.Tensor, mask_row: torch.Tensor):
+        """Several keyframes in one pass over the bank (bit-identical to consecutive fuse_dense calls in that order).
+        feats [R,D] f32 = descriptors of all keyframes, mask_row [len(kf_slots), n_masks] i32 -> row of feats or -1."""
+        assert bank.dtype == torch.bfloat16 and counts.dtype == torch.int32 and feats.dtype == torch.float32
+        assert mask_row.dtype == torch.int32 and mask_row.dim() == 2 and mask_row.shape[0] == len(kf_slots) and mask_row.is_contiguous()
+        arr = (C.c_int * len(kf_slots))(*[int(s) for s in kf_slots])
+        check(self.lib.ovo_map_fuse_dense_batch(self.handle, arr, len(kf_slots), ptr(bank), ptr(counts), bank.shape[0], bank.shape[1],
+                                                ptr(feats), ptr(mask_row), mask_row.shape[1], stream_ptr()), "ovo_map_fuse_dense_batch")
+
     def query_dense(self, bank: torch.Tensor, text: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
         """clip_cosine_similarity over the dense bank: [N,D] bf16 x [Q,D] f32 -> [N,Q] f32."""
         assert bank.dtype == torch.bfloat16 and bank.is_contiguous()

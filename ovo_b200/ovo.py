@@ -61,10 +61,14 @@ class OVO:
         # device-resident tables
         self._dev = self.clip_generator.encoder.device
         self.semmap = SemanticMap(self._dev)
+        # Descriptor work (ViT, pooling, fusion) is enqueued on its own stream: association synchronises the host once
+        # per keyframe, and that wait must not include the encoder of earlier keyframes.  Readers of descriptors
+        # (query, get_objs_clips, capture_dict, ...) first make the current stream wait for this one.
+        self._enc_stream = torch.cuda.Stream(device=self._dev)
         D = self.clip_generator.clip_dim
-        self._store = torch.zeros(1024, D, device=self._dev, dtype=torch.float32)   # per-keyframe descriptors
+        self._store = torch.zeros(4096, D, device=self._dev, dtype=torch.float32)   # per-keyframe descriptors
         self._store_n = 0
-        self._bank = torch.zeros(256, D, device=self._dev, dtype=torch.float32)     # fused instance descriptors
+        self._bank = torch.zeros(4096, D, device=self._dev, dtype=torch.float32)    # fused instance descriptors
         self._bank_n = 0
         self._rows_cache = None
         # dense per-point mode
@@ -139,7 +143,7 @@ class OVO:
         image, depth, rgb_depth_ratio = frame_data
         points_3d, points_ids, points_ins_ids = map_data
         dev = self._dev
-        depth_d = torch.as_tensor(depth, dtype=torch.float32).to(dev).contiguous()
+        depth_d = torch.as_tensor(depth, dtype=torch.float32).to(dev, non_blocking=True).contiguous()
         seg_d = seg_map.to(dev, torch.int32).contiguous()
         xyz = points_3d.to(dev, torch.float32).contiguous()
         updated = points_ins_ids.to(dev, torch.int32).reshape(-1).clone()        # ovo.py:228
@@ -149,7 +153,9 @@ class OVO:
         votes, n_matched, self.next_ins_id = self.semmap.associate(
             xyz, updated, depth_d, seg_d, c2w_np, K_np, self.next_ins_id, match_th=self.config["match_distance_th"],
             track_th=int(self.config["track_th"]), depth_filter=self.config.get("depth_filter", False),
-            rgb_depth_ratio=rgb_depth_ratio, kf_slot=slot)
+            rgb_depth_ratio=rgb_depth_ratio, kf_slot=slot, n_masks=int(binary_maps.shape[0]))
+        # (the reference loops to seg_map.max()+1 <= len(binary_maps); masks absent from seg_map get no votes, so
+        # using the mask count instead saves a device->host sync without changing any result)
         n_masks = len(votes["ins_id"])
 
         # points that received an id in this keyframe, per mask (only materialised when someone will read it)
@@ -271,11 +277,28 @@ class OVO:
             return
         same_shape = all(it[2].shape == items[0][2].shape for it in items)
         groups = [items] if same_shape else [[it] for it in items]
+        self._enc_stream.wait_stream(torch.cuda.current_stream(self._dev))     # masks / match lists are ready
+        with torch.cuda.stream(self._enc_stream):
+            self._compute_groups(groups)
+
+    def _compute_groups(self, groups) -> None:
         for group in groups:
+            for it in group:
+                it[1].record_stream(self._enc_stream)
             rows_per_kf = self._extract_clip_batch([it[2] for it in group], [it[1] for it in group])
+            if self.dense and len(group) > 1:
+                # all keyframes of the batch in ONE pass over the dense bank (bit-identical to one pass per keyframe)
+                base, total = rows_per_kf[0][0], sum(len(r) for r in rows_per_kf)
+                nm = max(int(it[5].shape[0]) for it in group)
+                mr = torch.full((len(group), nm), -1, dtype=torch.int32, device=self._dev)
+                for k, (it, rows) in enumerate(zip(group, rows_per_kf)):
+                    loc = it[5]
+                    mr[k, : loc.shape[0]] = torch.where(loc >= 0, loc + (rows[0] - base), loc)
+                self.semmap.fuse_dense_batch([it[4] for it in group], self._dense_bank, self._dense_counts,
+                                             self._store[base: base + total], mr)
             for (ids, _, _, kf_id, slot, mask_row), rows in zip(group, rows_per_kf):
                 self._update_matched_objects_clip(rows, ids, kf_id)
-                if self.dense:
+                if self.dense and len(group) == 1:
                     self.semmap.fuse_dense(slot, self._dense_bank, self._dense_counts,
                                            self._store[rows[0]: rows[0] + len(ids)], mask_row.contiguous())
                 if self.config.get("log", False):
@@ -372,6 +395,7 @@ class OVO:
 
     def _alloc_bank_row(self) -> int:
         if self._bank_n == self._bank.shape[0]:
+            self._sync_descriptors()
             new = torch.zeros(2 * self._bank.shape[0], self._bank.shape[1], device=self._dev)
             new[: self._bank_n] = self._bank
             self._bank = new
@@ -395,6 +419,20 @@ class OVO:
             nc[: self._dense_counts.shape[0]] = self._dense_counts
             self._dense_bank, self._dense_counts = nb, nc
 
+    def _sync_descriptors(self) -> None:
+        """Make the current stream wait for the descriptor stream (no host sync)."""
+        torch.cuda.current_stream(self._dev).wait_stream(self._enc_stream)
+
+    def descriptors_since(self, row0: int, out: torch.Tensor | None = None) -> torch.Tensor:
+        """Per-keyframe region descriptors appended to the device store since `row0` (see `_store_n`); with a pinned
+        `out` the read-back is enqueued asynchronously behind the work that produces them."""
+        n = self._store_n - row0
+        with torch.cuda.stream(self._enc_stream):
+            if out is None:
+                return self._store[row0: row0 + n].clone()
+            out[:n].copy_(self._store[row0: row0 + n], non_blocking=True)
+            return out[:n]
+
     def _object_rows(self) -> torch.Tensor:
         if self._rows_cache is None or self._rows_cache.shape[0] != len(self.objects):
             self._rows_cache = torch.tensor([o.bank_row for o in self.objects.values()], dtype=torch.int32, device=self._dev)
@@ -405,6 +443,7 @@ class OVO:
     def query(self, queries: List[str], templates: List[str] = ['{}'], ensemble: bool = False) -> torch.Tensor:
         """ovo.py:495-510: [n_obj, n_queries] similarity (objects in dict order)."""
         assert len(self.objects) > 0, "No 3D instances to query!"
+        self._sync_descriptors()
         self._refresh_missing_clips()
         return self.clip_generator.get_embed_txt_similarity(self._bank, queries, templates=templates, rows=self._object_rows())
 
@@ -412,6 +451,7 @@ class OVO:
     def query_points(self, queries: List[str], templates: List[str] = ['{}'], n_points: int | None = None) -> torch.Tensor:
         """Dense mode: [n_points, n_queries] similarity of every map point's running-mean feature."""
         assert self.dense and self._dense_bank is not None, "dense_map mode is off or no keyframe has been fused yet"
+        self._sync_descriptors()
         if isinstance(templates, str):
             templates = [templates]
         txt = self.clip_generator.text_bank([[t.format(q) for t in templates] for q in queries])
@@ -438,6 +478,7 @@ class OVO:
     @torch.no_grad()
     def get_objs_clips(self) -> torch.Tensor:
         """ovo.py:512-527: [n_obj, clip_dim] on the device."""
+        self._sync_descriptors()
         self._refresh_missing_clips()
         return self._bank.index_select(0, self._object_rows().long())
 
@@ -447,6 +488,7 @@ class OVO:
         keyframes, drop instances without points, merge instances that pass the centroid / cosine / point-distance
         test of instance_utils.same_instance (instance_utils.py:5-24), re-fuse descriptors."""
         self.complete_semantic_info()
+        self._sync_descriptors()
         points_3d, _, points_ins_ids = map_data
         for i, kf in enumerate(self.keyframes["frame_id"]):
             if kf not in kfs:
@@ -503,6 +545,7 @@ class OVO:
     # ------------------------------------------------------------------------------------------ checkpoint
     def capture_dict(self, debug_info: bool) -> Dict[str, Any]:
         """ovo.py:529-549: same flat keys (`ins_3d_ids`, `ins3d_{id}_clip_feature`, ...), tensors on the host."""
+        self._sync_descriptors()
         scene = {"ins_3d_ids": np.asarray(list(self.objects.keys()))}
         for obj in self.objects.values():
             d = obj.export(debug_info)

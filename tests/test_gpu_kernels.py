@@ -185,3 +185,34 @@ def test_association_idempotent_at_full_size(sm):
     assert (v2["n_unassigned"] == 0).all() and (v2["is_new"] == 0).all()
     assert (v2["ins_id"] == v1["ins_id"]).all() and (v2["n_assigned"] == v1["n_matched"]).all()
     assert int((ins_d >= 0).sum()) == int(v1["n_matched"][v1["ins_id"] >= 0].sum())
+
+
+def test_fuse_dense_batch_equals_sequential(sm):
+    """One pass over the bank for several keyframes == one pass per keyframe, bit for bit."""
+    K = synth.intrinsics(); N, D, F = 120000, 128, 5
+    d0 = synth.depth_map(frame_id=0)
+    xyz, ids, ins = synth.point_map(N, d0, K, synth.pose(0), seed=9, frac_visible=0.6)
+    xyz_d, ins_d = _dev(xyz, ins)
+    feats_all, rows_all, nm = [], [], 48
+    base = 0
+    for i in range(F):
+        seg, bm = synth.grid_masks(rows=(6 if i % 2 == 0 else 3), cols=(8 if i % 2 == 0 else 5))
+        d_d, seg_d = _dev(synth.depth_map(frame_id=3 * i), seg)
+        votes, _, _ = sm.associate(xyz_d, ins_d, d_d, seg_d, synth.pose(3 * i), K, 0 if i == 0 else 48, kf_slot=i)
+        n_m = len(votes["ins_id"])
+        local = np.where(votes["ins_id"] >= 0, np.arange(n_m), -1).astype(np.int32)
+        local[::7] = -1                                   # some masks produce no descriptor
+        feats_all.append(torch.randn(n_m, D, generator=torch.Generator().manual_seed(i)))
+        row = np.full(nm, -1, np.int32); row[:n_m] = np.where(local >= 0, local + base, -1)
+        rows_all.append((local, row)); base += n_m
+    feats = torch.cat(feats_all).cuda()
+    bank_a = torch.zeros(N, D, device="cuda", dtype=torch.bfloat16); cnt_a = torch.zeros(N, device="cuda", dtype=torch.int32)
+    bank_b, cnt_b = bank_a.clone(), cnt_a.clone()
+    off = 0
+    for i in range(F):
+        n_m = feats_all[i].shape[0]
+        sm.fuse_dense(i, bank_a, cnt_a, feats[off:off + n_m].contiguous(), torch.from_numpy(rows_all[i][0]).cuda())
+        off += n_m
+    sm.fuse_dense_batch(list(range(F)), bank_b, cnt_b, feats, torch.from_numpy(np.stack([r[1] for r in rows_all])).cuda())
+    assert torch.equal(cnt_a, cnt_b) and int(cnt_a.max()) >= 3
+    assert torch.equal(bank_a, bank_b)
