@@ -196,7 +196,7 @@ int ovo_map_get_matches(ovo_map_t* map, int kf_slot, int32_t* pairs_dev, int max
 
 /* Dense per-point running mean (north-star F6; per-point analogue of instance3d.py:19-21):
  * for every matched point p of slot kf_slot whose mask m has mask_row_dev[m] = r >= 0:
- *   bank[p] += (feats[r] - bank[p]) / (count[p] + 1); count[p] += 1.
+ *   count[p] += 1; bank[p] += (feats[r] - bank[p]) * (1 / count[p])   (f32, result rounded to bf16).
  * bank_dev bf16 [N, D], counts_dev i32 [N], feats_dev f32 [R, D], mask_row_dev i32 [n_masks]. */
 int ovo_map_fuse_dense(ovo_map_t* map, int kf_slot, void* bank_dev, int32_t* counts_dev, int64_t N, int D,
                        const float* feats_dev, const int32_t* mask_row_dev, int n_masks, void* stream);
@@ -206,7 +206,7 @@ int ovo_map_fuse_dense(ovo_map_t* map, int kf_slot, void* bank_dev, int32_t* cou
  * instead of k times.  feats_dev f32 [R, D] holds the descriptors of all keyframes; mask_row_dev i32
  * [n_slots, n_masks] maps (keyframe, mask) to a row of feats_dev or -1. */
 int ovo_map_fuse_dense_batch(ovo_map_t* map, const int* kf_slots_host, int n_slots, void* bank_dev, int32_t* counts_dev,
-                             int64_t N, int D, const float* feats_dev, const int32_t* mask_row_dev, int n_masks,
+                             int64_t N, int D, const float* feats_dev, int n_rows, const int32_t* mask_row_dev, int n_masks,
                              void* stream);
 
 /* Instance-bank running mean, fusion 'avg_pooling' (instance3d.py:19-21,157-189):

@@ -195,11 +195,12 @@ def avg_pooling(clips: np.ndarray) -> np.ndarray:
 
 
 def dense_running_mean(bank: np.ndarray, counts: np.ndarray, pt_idx: np.ndarray, feats: np.ndarray):
-    """Dense per-point analogue of i3d:19-21 (north-star F6): f_p += (e - f_p)/(c_p+1); c_p += 1.
-    bank [N,D] f32 (the CUDA bank is bf16: compare with bf16 rounding applied after each update)."""
+    """Dense per-point analogue of i3d:19-21 (north-star F6): c_p += 1; f_p += (e - f_p) * (1/c_p), every operation
+    rounded to f32 (one division per point).  bank [N,D] f32 (the CUDA bank is bf16: compare with bf16 rounding
+    applied after each update)."""
     for p, e in zip(pt_idx, feats):
         c = counts[p] + 1
-        bank[p] = bank[p] + (e - bank[p]) / f32(c)
+        bank[p] = bank[p] + ((e - bank[p]).astype(f32) * (f32(1) / f32(c))).astype(f32)
         counts[p] = c
     return bank, counts
 

@@ -39,7 +39,8 @@ struct EpiParams {
   const float* pos = nullptr;  // [1 + patches, width]
   int patches = 0;             // patches per image (576)
   int prof_cls = 0;            // profiling class of this launch (common.cuh ProfClass; host side only)
-  int debug = 0;               // tuning experiments: 1 = no epilogue stores, 2 = no MMA, 4 = no TMA loads
+  int debug = 0;               // tuning experiments: 1 = no epilogue, 2 = no MMA, 4 = no TMA loads, 8 = no GELU math,
+                               // 16 = no global stores, 32 = no bias loads
 };
 
 constexpr int kBM = 128;
@@ -210,7 +211,7 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& ep, int row0, in
   float acc[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(v[j]);
-  if (ep.bias != nullptr) {
+  if (ep.bias != nullptr && !(ep.debug & 32)) {
     const float4* b4 = reinterpret_cast<const float4*>(ep.bias + col);  // col % 32 == 0 -> 128-byte aligned
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -243,8 +244,10 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& ep, int row0, in
     }
   } else if constexpr (EPI == EPI_BF16 || EPI == EPI_BF16_GELU) {
     if constexpr (EPI == EPI_BF16_GELU) {
+      if (!(ep.debug & 8)) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) acc[j] = gelu_erf(acc[j]);
+        for (int j = 0; j < 32; ++j) acc[j] = gelu_erf(acc[j]);
+      }
     }
     uint32_t in[16];
 #pragma unroll
@@ -254,7 +257,7 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& ep, int row0, in
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int r = row0 + 8 * i + rsub;
-      if (r < M) *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(ep.out) + static_cast<size_t>(r) * ep.ldo + col + 8 * sub) = o[i];
+      if (r < M && !(ep.debug & 16)) *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(ep.out) + static_cast<size_t>(r) * ep.ldo + col + 8 * sub) = o[i];
     }
   } else if constexpr (EPI == EPI_QKV) {
     const int which = col / ep.width;  // warp uniform: 0 q, 1 k, 2 v

@@ -128,8 +128,10 @@ class SemanticMap:
         assert bank.dtype == torch.bfloat16 and counts.dtype == torch.int32 and feats.dtype == torch.float32
         assert mask_row.dtype == torch.int32 and mask_row.dim() == 2 and mask_row.shape[0] == len(kf_slots) and mask_row.is_contiguous()
         arr = (C.c_int * len(kf_slots))(*[int(s) for s in kf_slots])
+        assert feats.is_contiguous() and feats.shape[1] == bank.shape[1]
         check(self.lib.ovo_map_fuse_dense_batch(self.handle, arr, len(kf_slots), ptr(bank), ptr(counts), bank.shape[0], bank.shape[1],
-                                                ptr(feats), ptr(mask_row), mask_row.shape[1], stream_ptr()), "ovo_map_fuse_dense_batch")
+                                                ptr(feats), feats.shape[0], ptr(mask_row), mask_row.shape[1], stream_ptr()),
+              "ovo_map_fuse_dense_batch")
 
     def query_dense(self, bank: torch.Tensor, text: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
         """clip_cosine_similarity over the dense bank: [N,D] bf16 x [Q,D] f32 -> [N,Q] f32."""

@@ -163,7 +163,7 @@ def test_association_multi_keyframe_vs_oracle(sm, N, track_th, ratio):
         rr = mask_row[seg_of_pt[pts]]
         for p, r_ in zip(pts[rr >= 0], rr[rr >= 0]):
             c = counts_o[p] + 1
-            upd = bank_o[p] + (feats[r_].numpy() - bank_o[p]) / np.float32(c)
+            upd = bank_o[p] + (feats[r_].numpy() - bank_o[p]) * (np.float32(1) / np.float32(c))
             bank_o[p] = torch.from_numpy(upd).bfloat16().float().numpy()
             counts_o[p] = c
         assert (counts.cpu().numpy() == counts_o).all()

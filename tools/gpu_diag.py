@@ -103,7 +103,7 @@ def stage_map():
         sel = rr >= 0
         for p, r_ in zip(pts[sel], rr[sel]):
             c = counts_o[p] + 1
-            bank_o[p] = (torch.from_numpy(bank_o[p] + (feats[r_].numpy() - bank_o[p]) / np.float32(c)).bfloat16().float().numpy())
+            bank_o[p] = (torch.from_numpy(bank_o[p] + (feats[r_].numpy() - bank_o[p]) * (np.float32(1) / np.float32(c))).bfloat16().float().numpy())
             counts_o[p] = c
         print("  dense bank mismatches", int((bank.float().cpu().numpy() != bank_o).sum()), "count mismatches",
               int((counts.cpu().numpy() != counts_o).sum()), flush=True)
@@ -266,7 +266,7 @@ def stage_gemmdbg():
     cfg = EncoderConfig(text_layers=0, layers=4)
     enc, sd, ocfg = _enc(cfg, n_img=16, text=False)
     px = torch.randn(16, 3, 336, 336, device=dev)
-    for dbg, name in ((0, "full"), (1, "no-epilogue-stores"), (2, "no-mma"), (4, "no-tma"), (6, "no-mma,no-tma"), (7, "nothing")):
+    for dbg, name in ((0, "full"), (1, "no-epilogue"), (8, "no-gelu-math"), (16, "no-bf16-stores"), (32, "no-bias"), (56, "no gelu/stores/bias"), (2, "no-mma"), (4, "no-tma")):
         _lib.lib().ovo_set_gemm_cluster((dbg << 8) | 1)
         _lib.profile_begin()
         for _ in range(2):
