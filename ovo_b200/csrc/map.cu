@@ -407,101 +407,74 @@ __global__ void scatter_matches_kernel(const int2* __restrict__ list, int n, int
   }
 }
 
-// Slab design: a block owns 64 feature columns.  The descriptors of ALL keyframes of the batch for that slab
-// ([R, 64] f32, <= ~100 KB) sit in shared memory, so the only HBM traffic is one read + one write of each touched
-// 128-byte bank piece (the per-keyframe kernel re-reads a 4 KB descriptor row from L2 for every point update).
-// 8 lanes handle one point (16 B each), 4 points per warp.  counts[] is only read here (all slabs need the old
-// value); dense_counts_kernel adds the number of updates afterwards.
-constexpr int kSlab = 64;
-constexpr int kSlabPad = 68;  // floats per shared row: 16-byte aligned, staggers banks between rows
-
-constexpr int kFuseThreads = 512;
-constexpr int kFuseUnroll = 4;   // points per 8-lane group and iteration: 4 independent 16-byte loads in flight per lane
-
-__global__ void __launch_bounds__(kFuseThreads)
+// One warp per touched point, all keyframes of the batch applied to the row while it sits in registers.  Descriptor
+// rows come from L2 (the batch's descriptors are ~1.5 MB).  (A variant that kept 64-column descriptor slabs in
+// shared memory was 4x slower on B200: 128-byte strided bank accesses waste DRAM pages.)
+template <int kVecPerLane>
+__global__ void __launch_bounds__(256)
     fuse_dense_batch_kernel(const int16_t* __restrict__ seg_of_pt /* [F][N] */, int F, long long N,
-                            __nv_bfloat16* __restrict__ bank, const int32_t* __restrict__ counts, int D,
-                            const float* __restrict__ feats, int R, const int32_t* __restrict__ mask_row /* [F][n_masks] */,
-                            int n_masks, int pts_per_block) {
-  extern __shared__ float s_feats[];  // [R][kSlabPad]
-  const int slab = blockIdx.y;
-  for (int i = threadIdx.x; i < R * (kSlab / 4); i += blockDim.x) {
-    const int r = i / (kSlab / 4), q = i % (kSlab / 4);
-    *reinterpret_cast<float4*>(s_feats + r * kSlabPad + 4 * q) =
-        __ldg(reinterpret_cast<const float4*>(feats + static_cast<size_t>(r) * D + slab * kSlab) + q);
-  }
-  __syncthreads();
-  const int group = threadIdx.x >> 3, q = threadIdx.x & 7;
-  const long long pbeg = static_cast<long long>(blockIdx.x) * pts_per_block;
-  const long long pend = min(N, pbeg + pts_per_block);
-  constexpr int U = kFuseUnroll;
-  for (long long p0 = pbeg + static_cast<long long>(group) * U; p0 < pend; p0 += (kFuseThreads / 8) * U) {
-    int rows[U][8];
-    bool any[U];
+                            __nv_bfloat16* __restrict__ bank, int32_t* __restrict__ counts, int D,
+                            const float* __restrict__ feats, const int32_t* __restrict__ mask_row /* [F][n_masks] */,
+                            int n_masks) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const long long n_warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  const int nvec = D >> 3;
+  for (long long p0 = warp * 32; p0 < N; p0 += n_warps * 32) {
+    // lane l looks at point p0+l: which keyframes of the batch matched it into a mask that produced a descriptor?
+    const long long pl = p0 + lane;
+    unsigned fmask = 0;  // bit f set -> keyframe f updates this point
+    if (pl < N) {
+      for (int f = 0; f < F; ++f) {
+        const int m = seg_of_pt[static_cast<size_t>(f) * N + pl];
+        if (m >= 0 && m < n_masks && mask_row[f * n_masks + m] >= 0) fmask |= 1u << f;
+      }
+    }
+    unsigned todo = __ballot_sync(0xffffffffu, fmask != 0);
+    while (todo) {
+      const int src = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const long long p = p0 + src;
+      const unsigned fm = __shfl_sync(0xffffffffu, fmask, src);
+      int c = counts[p];
+      uint4* prow = reinterpret_cast<uint4*>(bank + static_cast<size_t>(p) * D);
+      uint4 raw[kVecPerLane];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      any[u] = false;
+      for (int i = 0; i < kVecPerLane; ++i) {
+        const int v = lane + 32 * i;
+        if (v < nvec) raw[i] = prow[v];
+      }
+      for (int f = 0; f < F; ++f) {
+        if (!((fm >> f) & 1u)) continue;
+        const int r = mask_row[f * n_masks + seg_of_pt[static_cast<size_t>(f) * N + p]];
+        ++c;
+        const float inv = __fdiv_rn(1.0f, static_cast<float>(c));
+        const float4* frow = reinterpret_cast<const float4*>(feats + static_cast<size_t>(r) * D);
 #pragma unroll
-      for (int f = 0; f < 8; ++f) {
-        int r = -1;
-        if (f < F && p0 + u < pend) {
-          const int m = seg_of_pt[static_cast<size_t>(f) * N + p0 + u];
-          if (m >= 0 && m < n_masks) r = mask_row[f * n_masks + m];
+        for (int i = 0; i < kVecPerLane; ++i) {
+          const int v = lane + 32 * i;
+          if (v < nvec) {
+            const float4 e0 = __ldg(frow + 2 * v), e1 = __ldg(frow + 2 * v + 1);
+            const float ev[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+            uint32_t* w = reinterpret_cast<uint32_t*>(&raw[i]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              __nv_bfloat162 b2 = *reinterpret_cast<__nv_bfloat162*>(&w[j]);
+              float f0 = __bfloat162float(b2.x), f1 = __bfloat162float(b2.y);
+              f0 = __fadd_rn(f0, __fmul_rn(__fsub_rn(ev[2 * j], f0), inv));
+              f1 = __fadd_rn(f1, __fmul_rn(__fsub_rn(ev[2 * j + 1], f1), inv));
+              w[j] = pack_bf16(f0, f1);
+            }
+          }
         }
-        rows[u][f] = r;
-        any[u] = any[u] || r >= 0;
-      }
-    }
-    uint4 raw[U];
-    int c[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      if (any[u]) {
-        raw[u] = *(reinterpret_cast<const uint4*>(bank + static_cast<size_t>(p0 + u) * D + slab * kSlab) + q);
-        c[u] = counts[p0 + u];
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      if (!any[u]) continue;
-      uint32_t* w = reinterpret_cast<uint32_t*>(&raw[u]);
-      float fv[8];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const __nv_bfloat162 b2 = *reinterpret_cast<__nv_bfloat162*>(&w[j]);
-        fv[2 * j] = __bfloat162float(b2.x);
-        fv[2 * j + 1] = __bfloat162float(b2.y);
-      }
-      int cc = c[u];
-#pragma unroll
-      for (int f = 0; f < 8; ++f) {
-        if (rows[u][f] < 0) continue;
-        ++cc;
-        const float inv = __fdiv_rn(1.0f, static_cast<float>(cc));
-        const float* e = s_feats + rows[u][f] * kSlabPad + 8 * q;
-        const float4 e0 = *reinterpret_cast<const float4*>(e), e1 = *reinterpret_cast<const float4*>(e + 4);
-        const float ev[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
-#pragma unroll
-        for (int j = 0; j < 8; ++j)  // same op sequence as fuse_dense_kernel, bf16 rounding after every update
-          fv[j] = __bfloat162float(__float2bfloat16_rn(__fadd_rn(fv[j], __fmul_rn(__fsub_rn(ev[j], fv[j]), inv))));
       }
 #pragma unroll
-      for (int j = 0; j < 4; ++j) w[j] = pack_bf16(fv[2 * j], fv[2 * j + 1]);
-      *(reinterpret_cast<uint4*>(bank + static_cast<size_t>(p0 + u) * D + slab * kSlab) + q) = raw[u];
+      for (int i = 0; i < kVecPerLane; ++i) {
+        const int v = lane + 32 * i;
+        if (v < nvec) prow[v] = raw[i];
+      }
+      if (lane == 0) counts[p] = c;
     }
-  }
-}
-
-__global__ void dense_counts_kernel(const int16_t* __restrict__ seg_of_pt, int F, long long N, int32_t* __restrict__ counts,
-                                    const int32_t* __restrict__ mask_row, int n_masks) {
-  for (long long p = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; p < N;
-       p += static_cast<long long>(gridDim.x) * blockDim.x) {
-    int nup = 0;
-    for (int f = 0; f < F; ++f) {
-      const int m = seg_of_pt[static_cast<size_t>(f) * N + p];
-      if (m >= 0 && m < n_masks && mask_row[f * n_masks + m] >= 0) ++nup;
-    }
-    if (nup) counts[p] += nup;
   }
 }
 
@@ -924,24 +897,12 @@ int ovo_map_fuse_dense_batch(ovo_map_t* m, const int* kf_slots_host, int n_slots
     ovo::scatter_matches_kernel<<<std::min(ovo::ceil_div(n, 256), sms * 4), 256, 0, stream>>>(m->slot_list[s], n, m->seg_dense + static_cast<size_t>(i) * N);
     OVO_CHECK_LAUNCH();
   }
-  OVO_REQUIRE(D % ovo::kSlab == 0 && n_slots <= 8, "ovo_map_fuse_dense_batch: D must be a multiple of 64 and at most 8 keyframes per batch");
-  OVO_REQUIRE(n_rows > 0 && static_cast<size_t>(n_rows) * ovo::kSlabPad * sizeof(float) <= 200 * 1024,
-              "ovo_map_fuse_dense_batch: %d descriptor rows do not fit the shared-memory slab", n_rows);
-  const size_t smem = static_cast<size_t>(n_rows) * ovo::kSlabPad * sizeof(float);
-  static size_t attr_smem = 0;
-  if (smem > attr_smem) {
-    OVO_CUDA(cudaFuncSetAttribute(ovo::fuse_dense_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    attr_smem = smem;
-  }
-  const int slabs = D / ovo::kSlab;
-  // ~2 waves of blocks over (point chunks x slabs); chunk a multiple of 32 points
-  int pts_per_block = static_cast<int>(((N * slabs / (2LL * sms * (smem > 100 * 1024 ? 1 : 2))) + 31) / 32 * 32);
-  pts_per_block = std::max(pts_per_block, 1024);
-  const int chunks = static_cast<int>((N + pts_per_block - 1) / pts_per_block);
-  ovo::fuse_dense_batch_kernel<<<dim3(chunks, slabs), ovo::kFuseThreads, smem, stream>>>(m->seg_dense, n_slots, N, static_cast<__nv_bfloat16*>(bank_dev),
-                                                                         counts_dev, D, feats_dev, n_rows, mask_row_dev, n_masks, pts_per_block);
-  OVO_CHECK_LAUNCH();
-  ovo::dense_counts_kernel<<<sms * 4, 256, 0, stream>>>(m->seg_dense, n_slots, N, counts_dev, mask_row_dev, n_masks);
+  (void)n_rows;
+  const int blocks = static_cast<int>(std::min<long long>((N + 255) / 256, sms * 8LL));
+  if (D <= 1024)
+    ovo::fuse_dense_batch_kernel<4><<<blocks, 256, 0, stream>>>(m->seg_dense, n_slots, N, static_cast<__nv_bfloat16*>(bank_dev), counts_dev, D, feats_dev, mask_row_dev, n_masks);
+  else
+    ovo::fuse_dense_batch_kernel<8><<<blocks, 256, 0, stream>>>(m->seg_dense, n_slots, N, static_cast<__nv_bfloat16*>(bank_dev), counts_dev, D, feats_dev, mask_row_dev, n_masks);
   OVO_CHECK_LAUNCH();
   return OVO_OK;
 }
