@@ -231,6 +231,18 @@ int ovo_merge_masks(const uint8_t* masks_dev, int M, int H, int W, const int32_t
  * 1 l1_medoid (:9-12), 2 cossim_medoid (:14-17); chosen_dev[j] (optional) = index of the medoid view. */
 int ovo_fuse_views(const float* store_dev, int D, const int32_t* idx_dev, const int32_t* off_dev, int n_instances,
                    int mode, float* bank_dev, const int32_t* out_rows_dev, int32_t* chosen_dev, void* stream);
+/* S2 — mask post-processing of the proposals (ovo/utils/segment_utils.py).
+ * ovo_mask_nms = masks_update + mask_nms + filter (:173-259): masks uint8 [M,H,W], scores f32 [M] (= stability *
+ * predicted_iou) -> keep_dev uint8 [M] in the ORIGINAL mask order.  OVO passes iou_thr 0.8, score_thr 0.7, inner_thr 0.5
+ * (mask_generator.py:25-27).
+ * ovo_mask2segmap = mask2segmap (:12-27): masks painted in descending stability, earlier masks win overlaps:
+ * seg_map_dev i32 [H,W] (-1 = none), maps_out_dev uint8 [M,H,W] = masks in painted order, order_dev i32 [M] = painted
+ * position -> input index. */
+int ovo_mask_nms(const uint8_t* masks_dev, const float* scores_dev, int M, int H, int W, float iou_thr, float score_thr,
+                 float inner_thr, uint8_t* keep_dev, void* stream);
+int ovo_mask2segmap(const uint8_t* masks_dev, const float* stability_dev, int M, int H, int W, int32_t* seg_map_dev,
+                    uint8_t* maps_out_dev, int32_t* order_dev, void* stream);
+
 /* OVO.classify_instances (ovo.py:486-491): argmax over queries + threshold. sim f32 [n,Q] ->
  * cls i32 [n] (-1 if max <= th), conf f32 [n] (0 if max <= th). */
 int ovo_classify(const float* sim_dev, int64_t n, int Q, float th, int32_t* cls_dev, float* conf_dev, void* stream);

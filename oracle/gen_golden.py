@@ -202,10 +202,28 @@ def gen_ovo():
     print("objects", keys, "n_kfs", out["object_n_kfs"])
 
 
+def gen_masks():
+    """Reference masks_update / mask2segmap (ovo/utils/segment_utils.py) on synthetic proposals."""
+    rh.setup_paths()
+    import ovo.utils.segment_utils as su
+    from . import masks as OM
+    out = {}
+    for seed in (0, 1, 2):
+        masks, iou, stab = OM.synth_masks(seed=seed)
+        lst = [dict(segmentation=masks[i], predicted_iou=iou[i], stability_score=stab[i]) for i in range(len(masks))]
+        kept, = su.masks_update(lst, iou_thr=0.8, score_thr=0.7, inner_thr=0.5)
+        out[f"kept_{seed}"] = np.array([next(i for i in range(len(lst)) if lst[i] is k) for k in kept], np.int64)
+        seg, bm = su.mask2segmap(kept, np.zeros(masks.shape[1:] + (3,)))
+        out[f"seg_{seed}"] = seg.astype(np.int16)
+        out[f"bm_{seed}"] = np.packbits(bm)
+    np.savez_compressed(os.path.join(OUT, "masks.npz"), **out)
+    print("masks.npz", {k: v.shape for k, v in out.items()})
+
+
 if __name__ == "__main__":
     if not rh.available():
         sys.exit("reference not available: fixtures can only be generated in the build container")
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["encoder", "assoc", "ovo"]
+    which = sys.argv[1:] or ["encoder", "assoc", "ovo", "masks"]
     for w in which:
         globals()["gen_" + w]()

@@ -74,6 +74,8 @@ SIGNATURES = {
     "ovo_merge_masks": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "ovo_fuse_views": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "ovo_text_bank": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "ovo_mask_nms": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_float, c_float, c_void_p, c_void_p]),
+    "ovo_mask2segmap": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "ovo_classify": (c_int, [c_void_p, c_int64, c_int, c_float, c_void_p, c_void_p, c_void_p]),
     "ovo_profile_begin": (None, []),
     "ovo_profile_report": (c_int, [c_int, C.POINTER(c_float), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(c_int)]),

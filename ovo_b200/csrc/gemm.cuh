@@ -203,7 +203,7 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& ep, int row0, in
     fast = fast && (ep.ldo & 3) == 0 && (reinterpret_cast<uintptr_t>(ep.out) & 15) == 0 &&
            (EPI != EPI_F32_RESID || ((ep.ldr & 3) == 0 && (reinterpret_cast<uintptr_t>(ep.resid) & 15) == 0));
   if constexpr (EPI == EPI_BF16 || EPI == EPI_BF16_GELU) fast = fast && (ep.ldo & 7) == 0 && (reinterpret_cast<uintptr_t>(ep.out) & 15) == 0;
-  if constexpr (EPI == EPI_PATCH) fast = false;
+  if constexpr (EPI == EPI_PATCH) fast = fast && (ep.ldo & 3) == 0 && (reinterpret_cast<uintptr_t>(ep.out) & 15) == 0 && (reinterpret_cast<uintptr_t>(ep.pos) & 15) == 0;
   if (!fast) {  // ragged N / unaligned output (e.g. the [N_points, 20] query result): per-thread row stores
     epilogue_store<EPI>(ep, row0 + lane, col, v, M, N, s_rope);
     return;
@@ -221,7 +221,28 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& ep, int row0, in
   }
   const int sub = lane & 3, rsub = lane >> 2;
 
-  if constexpr (EPI == EPI_F32 || EPI == EPI_F32_RESID) {
+  if constexpr (EPI == EPI_PATCH) {
+    // patch-embed rows -> token rows (skip the cls slot of every image) + absolute position embedding (pe.py:509-519)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      uint32_t in[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) in[j] = __float_as_uint(acc[16 * h + j]);
+      uint4 o[4];
+      stage_exchange(st, lane, in, o);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = row0 + 8 * i + rsub;
+        if (r >= M) continue;
+        const int c = col + 16 * h + 4 * sub;
+        const int b = r / ep.patches, p = r - b * ep.patches;
+        const float4 pe = __ldg(reinterpret_cast<const float4*>(ep.pos + static_cast<size_t>(1 + p) * ep.ldo + c));
+        const float4 val = make_float4(__uint_as_float(o[i].x) + pe.x, __uint_as_float(o[i].y) + pe.y,
+                                       __uint_as_float(o[i].z) + pe.z, __uint_as_float(o[i].w) + pe.w);
+        *reinterpret_cast<float4*>(static_cast<float*>(ep.out) + (static_cast<size_t>(b) * (ep.patches + 1) + 1 + p) * ep.ldo + c) = val;
+      }
+    }
+  } else if constexpr (EPI == EPI_F32 || EPI == EPI_F32_RESID) {
 #pragma unroll
     for (int h = 0; h < 2; ++h) {  // two halves of 16 f32 columns = 64 B per row
       uint32_t in[16];

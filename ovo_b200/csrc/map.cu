@@ -617,6 +617,104 @@ __global__ void __launch_bounds__(256)
   if (threadIdx.x == 0 && chosen) chosen[j] = s_besti;
 }
 
+
+// ------------------------------------------------------------------------------------------ S2: mask NMS + seg-map
+// masks_update / mask_nms / mask2segmap (ovo/utils/segment_utils.py:173-259,12-27) on the device: masks are
+// bit-packed, pairwise intersections are popcounts, the keep rules and the paint order follow the reference
+// (including tril(diagonal=1) keeping the first super-diagonal, segment_utils.py:236).
+__global__ void bitpack_masks_kernel(const uint8_t* __restrict__ masks, int M, int npix, int nwords, uint32_t* __restrict__ bits) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  const int m = blockIdx.y;
+  if (w >= nwords) return;
+  const uint8_t* src = masks + static_cast<size_t>(m) * npix + static_cast<size_t>(w) * 32;
+  uint32_t v = 0;
+  const int n = min(32, npix - w * 32);
+  for (int i = 0; i < n; ++i) v |= (src[i] != 0 ? 1u : 0u) << i;
+  bits[static_cast<size_t>(m) * nwords + w] = v;
+}
+
+// rank[i] = position of mask i when sorted by descending key (ties: lower index first = stable sort)
+__global__ void rank_desc_kernel(const float* __restrict__ key, int M, int32_t* __restrict__ rank, int32_t* __restrict__ order) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M) return;
+  const float k = key[i];
+  int r = 0;
+  for (int j = 0; j < M; ++j) {
+    const float kj = key[j];
+    r += (kj > k) || (kj == k && j < i);
+  }
+  rank[i] = r;
+  order[r] = i;
+}
+
+// inter[a][b] = |mask(order[a]) & mask(order[b])| for a <= b (sorted order); one block per pair
+__global__ void mask_intersections_kernel(const uint32_t* __restrict__ bits, int nwords, const int32_t* __restrict__ order,
+                                          int M, int32_t* __restrict__ inter) {
+  const int a = blockIdx.y, b = blockIdx.x;
+  if (b < a) return;
+  const uint32_t* ba = bits + static_cast<size_t>(order[a]) * nwords;
+  const uint32_t* bb = bits + static_cast<size_t>(order[b]) * nwords;
+  int acc = 0;
+  for (int w = threadIdx.x; w < nwords; w += blockDim.x) acc += __popc(ba[w] & bb[w]);
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  __shared__ int s[8];
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int i = 0; i < (blockDim.x >> 5); ++i) t += s[i];
+    inter[a * M + b] = t;
+    inter[b * M + a] = t;
+  }
+}
+
+// keep rules of mask_nms (segment_utils.py:225-257), one thread per column j of the sorted order
+__global__ void mask_nms_decide_kernel(const int32_t* __restrict__ inter, const float* __restrict__ scores,
+                                       const int32_t* __restrict__ order, int M, float iou_thr, float score_thr, float inner_lim,
+                                       uint8_t* __restrict__ keep_sorted) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= M) return;
+  const float area_j = static_cast<float>(inter[j * M + j]);
+  float iou_max = 0.f, inner_u = 0.f, inner_l = 0.f;
+  // inner[r][c] is written for pairs (i<=j'): [i][j'] when ri<0.5 && rj>=0.85, [j'][i] when ri>=0.85 && rj<0.5
+  for (int i = 0; i < M; ++i) {
+    const float it = static_cast<float>(inter[i * M + j]);
+    const float area_i = static_cast<float>(inter[i * M + i]);
+    if (i < j) {  // pair (i, j), i < j: column j of the upper triangle
+      const float uni = __fsub_rn(__fadd_rn(area_i, area_j), it);
+      iou_max = fmaxf(iou_max, __fdiv_rn(it, uni));
+      const float ri = __fdiv_rn(it, area_i), rj = __fdiv_rn(it, area_j);
+      if (ri < 0.5f && rj >= 0.85f) inner_u = fmaxf(inner_u, __fsub_rn(1.f, __fmul_rn(rj, ri)));   // inner[i][j], upper
+      // tril(diagonal=1) also keeps inner[j-1][j]
+      if (i == j - 1 && ri < 0.5f && rj >= 0.85f) inner_l = fmaxf(inner_l, __fsub_rn(1.f, __fmul_rn(rj, ri)));
+    } else if (i > j) {  // pair (j, i) with j < i: entry [i][j] (lower triangle) set when r_j >= 0.85 && r_i < 0.5
+      const float rjj = __fdiv_rn(it, area_j), rii = __fdiv_rn(it, area_i);
+      if (rjj >= 0.85f && rii < 0.5f) inner_l = fmaxf(inner_l, __fsub_rn(1.f, __fmul_rn(rii, rjj)));
+    }
+  }
+  const bool keep = iou_max <= iou_thr && scores[order[j]] > score_thr && inner_u <= inner_lim && inner_l <= inner_lim;
+  keep_sorted[j] = keep ? 1 : 0;
+}
+
+__global__ void gather_u8_kernel(const uint8_t* __restrict__ src, const int32_t* __restrict__ idx, int n, uint8_t* __restrict__ dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[idx[i]];
+}
+
+// mask2segmap: pixel gets the position (in descending-stability order) of the first mask that contains it
+__global__ void paint_segmap_kernel(const uint8_t* __restrict__ masks, const int32_t* __restrict__ order, int M, int npix,
+                                    int32_t* __restrict__ seg, uint8_t* __restrict__ maps_out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npix) return;
+  int s = -1;
+  for (int k = 0; k < M; ++k) {
+    const uint8_t v = masks[static_cast<size_t>(order[k]) * npix + i] != 0;
+    maps_out[static_cast<size_t>(k) * npix + i] = v;
+    if (v && s < 0) s = k;
+  }
+  seg[i] = s;
+}
+
 }  // namespace ovo
 
 // =============================================================================================== handle
@@ -966,6 +1064,49 @@ int ovo_fuse_views(const float* store_dev, int D, const int32_t* idx_dev, const 
   if (n_instances <= 0) return OVO_OK;
   ovo::fuse_views_kernel<<<n_instances, 256, 0, static_cast<cudaStream_t>(stream)>>>(store_dev, D, idx_dev, off_dev, mode, bank_dev, out_rows_dev, chosen_dev);
   OVO_CHECK_LAUNCH();
+  return OVO_OK;
+}
+
+int ovo_mask_nms(const uint8_t* masks_dev, const float* scores_dev, int M, int H, int W, float iou_thr, float score_thr,
+                 float inner_thr, uint8_t* keep_dev, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  OVO_REQUIRE(masks_dev && scores_dev && keep_dev && M > 0 && M <= 4096 && H > 0 && W > 0, "ovo_mask_nms: bad arguments");
+  const int npix = H * W, nwords = ovo::ceil_div(npix, 32);
+  uint32_t* bits = nullptr; int32_t *rank = nullptr, *order = nullptr, *inter = nullptr; uint8_t* keep_sorted = nullptr;
+  // small, rare call (once per keyframe at most): stream-ordered temporaries
+  OVO_CUDA(cudaMallocAsync(&bits, static_cast<size_t>(M) * nwords * 4, stream));
+  OVO_CUDA(cudaMallocAsync(&rank, M * 4, stream));
+  OVO_CUDA(cudaMallocAsync(&order, M * 4, stream));
+  OVO_CUDA(cudaMallocAsync(&inter, static_cast<size_t>(M) * M * 4, stream));
+  OVO_CUDA(cudaMallocAsync(&keep_sorted, M, stream));
+  ovo::bitpack_masks_kernel<<<dim3(ovo::ceil_div(nwords, 256), M), 256, 0, stream>>>(masks_dev, M, npix, nwords, bits);
+  OVO_CHECK_LAUNCH();
+  ovo::rank_desc_kernel<<<ovo::ceil_div(M, 128), 128, 0, stream>>>(scores_dev, M, rank, order);
+  OVO_CHECK_LAUNCH();
+  ovo::mask_intersections_kernel<<<dim3(M, M), 256, 0, stream>>>(bits, nwords, order, M, inter);
+  OVO_CHECK_LAUNCH();
+  ovo::mask_nms_decide_kernel<<<ovo::ceil_div(M, 128), 128, 0, stream>>>(inter, scores_dev, order, M, iou_thr, score_thr,
+                                                                              static_cast<float>(1.0 - static_cast<double>(inner_thr)), keep_sorted);
+  OVO_CHECK_LAUNCH();
+  // keep flags back in ORIGINAL mask order (masks_update/filter keep the original order, segment_utils.py:188-193)
+  ovo::gather_u8_kernel<<<ovo::ceil_div(M, 128), 128, 0, stream>>>(keep_sorted, rank, M, keep_dev);
+  OVO_CHECK_LAUNCH();
+  cudaFreeAsync(bits, stream); cudaFreeAsync(rank, stream); cudaFreeAsync(order, stream); cudaFreeAsync(inter, stream);
+  cudaFreeAsync(keep_sorted, stream);
+  return OVO_OK;
+}
+
+int ovo_mask2segmap(const uint8_t* masks_dev, const float* stability_dev, int M, int H, int W, int32_t* seg_map_dev,
+                    uint8_t* maps_out_dev, int32_t* order_dev, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  OVO_REQUIRE(masks_dev && stability_dev && seg_map_dev && maps_out_dev && order_dev && M > 0 && H > 0 && W > 0, "ovo_mask2segmap: bad arguments");
+  int32_t* rank = nullptr;
+  OVO_CUDA(cudaMallocAsync(&rank, M * 4, stream));
+  ovo::rank_desc_kernel<<<ovo::ceil_div(M, 128), 128, 0, stream>>>(stability_dev, M, rank, order_dev);
+  OVO_CHECK_LAUNCH();
+  ovo::paint_segmap_kernel<<<ovo::ceil_div(H * W, 256), 256, 0, stream>>>(masks_dev, order_dev, M, H * W, seg_map_dev, maps_out_dev);
+  OVO_CHECK_LAUNCH();
+  cudaFreeAsync(rank, stream);
   return OVO_OK;
 }
 

@@ -170,6 +170,27 @@ class SemanticMap:
         check(self.lib.ovo_fuse_views(ptr(store), store.shape[1], ptr(idx), ptr(off), out_rows.shape[0], mode, ptr(bank),
                                       ptr(out_rows), ptr(chosen), stream_ptr()), "ovo_fuse_views")
 
+    def mask_nms(self, masks: torch.Tensor, scores: torch.Tensor, iou_thr=0.8, score_thr=0.7, inner_thr=0.5) -> torch.Tensor:
+        """masks_update/mask_nms/filter (segment_utils.py:173-259): masks [M,H,W] bool/uint8, scores [M] f32 ->
+        keep [M] bool in the original order."""
+        m8 = masks.to(self.device).to(torch.uint8).contiguous()
+        sc = scores.to(self.device, torch.float32).contiguous()
+        keep = torch.empty(m8.shape[0], device=self.device, dtype=torch.uint8)
+        check(self.lib.ovo_mask_nms(ptr(m8), ptr(sc), m8.shape[0], m8.shape[1], m8.shape[2], float(iou_thr), float(score_thr),
+                                    float(inner_thr), ptr(keep), stream_ptr()), "ovo_mask_nms")
+        return keep.bool()
+
+    def mask2segmap(self, masks: torch.Tensor, stability: torch.Tensor):
+        """mask2segmap (segment_utils.py:12-27) -> (seg_map [H,W] i32, binary_maps [M,H,W] bool in painted order, order)."""
+        m8 = masks.to(self.device).to(torch.uint8).contiguous()
+        st = stability.to(self.device, torch.float32).contiguous()
+        M, H, W = m8.shape
+        seg = torch.empty(H, W, device=self.device, dtype=torch.int32)
+        maps = torch.empty_like(m8)
+        order = torch.empty(M, device=self.device, dtype=torch.int32)
+        check(self.lib.ovo_mask2segmap(ptr(m8), ptr(st), M, H, W, ptr(seg), ptr(maps), ptr(order), stream_ptr()), "ovo_mask2segmap")
+        return seg, maps.bool(), order
+
     def classify(self, sim: torch.Tensor, th: float = 0.0):
         """OVO.classify_instances' argmax + threshold (ovo.py:486-491)."""
         sim = sim.contiguous()

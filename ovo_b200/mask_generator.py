@@ -46,7 +46,35 @@ class MaskGenerator:
         return torch.from_numpy(seg_map).to(self.device), torch.from_numpy(binary_maps).to(self.device)
 
     def segment(self, image: np.ndarray):
-        raise NotImplementedError("ovo_b200: SAM-2 mask proposal is not built yet")
+        """mask_generator.py:101-120.  The proposal network (SAM-2 automatic mask generator) is not built here; when a
+        `proposal_fn(image) -> list of {segmentation, predicted_iou, stability_score}` is attached (e.g. the
+        reference's own SAM2AutomaticMaskGenerator.generate), its output goes through the native post-processing."""
+        fn = getattr(self, "proposal_fn", None)
+        if fn is None:
+            raise NotImplementedError("ovo_b200: SAM-2 mask proposal is not built yet (attach MaskGenerator.proposal_fn)")
+        masks = fn(image)
+        if len(masks) == 0:
+            return np.array([]), np.array([])
+        seg, maps = self.postprocess(masks)
+        return seg.cpu().numpy(), maps.cpu().numpy()
+
+    def postprocess(self, masks):
+        """masks_update + mask2segmap (segment_utils.py:173-259,12-27) on the device.
+        masks: list of dicts with 'segmentation' [H,W] bool, 'predicted_iou', 'stability_score'.
+        Returns (seg_map [H,W] i32, binary_maps [M,H,W] bool) as device tensors."""
+        from .map import SemanticMap
+        if getattr(self, "_sm", None) is None:
+            self._sm = SemanticMap(self.device if "cuda" in str(self.device) else "cuda")
+        seg = torch.from_numpy(np.stack([m["segmentation"] for m in masks]))
+        iou = torch.tensor([float(m["predicted_iou"]) for m in masks], dtype=torch.float32)
+        stab = torch.tensor([float(m["stability_score"]) for m in masks], dtype=torch.float32)
+        seg_d = seg.to(self._sm.device)
+        keep = self._sm.mask_nms(seg_d, stab * iou, self.nms_iou_th, self.nms_score_th, self.nms_inner_th)
+        idx = torch.nonzero(keep).flatten()
+        if idx.numel() == 0:
+            return torch.full(seg.shape[1:], -1, dtype=torch.int32, device=self._sm.device), seg_d[:0]
+        seg_map, maps, _ = self._sm.mask2segmap(seg_d[idx], stab.to(self._sm.device)[idx])
+        return seg_map, maps
 
     def precompute(self, dataset, segment_every: int) -> None:
         """With every mask already on disk this is the reference's no-op path (mask_generator.py:141-152)."""

@@ -216,3 +216,19 @@ def test_fuse_dense_batch_equals_sequential(sm):
     sm.fuse_dense_batch(list(range(F)), bank_b, cnt_b, feats, torch.from_numpy(np.stack([r[1] for r in rows_all])).cuda())
     assert torch.equal(cnt_a, cnt_b) and int(cnt_a.max()) >= 3
     assert torch.equal(bank_a, bank_b)
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_mask_nms_and_segmap_match_oracle(sm, golden_dir, seed):
+    """S2: GPU mask NMS + seg-map painting == oracle/masks.py (pinned to the reference in tests/golden/masks.npz)."""
+    from oracle import masks as OM
+    masks, iou, stab = OM.synth_masks(seed=seed)
+    keep = sm.mask_nms(torch.from_numpy(masks), torch.from_numpy(stab * iou)).cpu().numpy()
+    ref = OM.masks_update(masks, iou, stab)
+    assert np.nonzero(keep)[0].tolist() == ref.tolist() and 0 < len(ref) < len(masks)
+    g = np.load(os.path.join(golden_dir, "masks.npz"))
+    if f"kept_{seed}" in g:
+        assert np.nonzero(keep)[0].tolist() == g[f"kept_{seed}"].tolist()
+    seg, maps, order = sm.mask2segmap(torch.from_numpy(masks[ref]), torch.from_numpy(stab[ref]))
+    seg_o, maps_o, order_o = OM.mask2segmap(masks[ref], stab[ref])
+    assert (seg.cpu().numpy() == seg_o).all() and (maps.cpu().numpy() == maps_o).all() and order.cpu().tolist() == order_o.tolist()
