@@ -118,7 +118,8 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
     // the softmax is instruction-issue bound, every instruction per score counts
     const bool full = !causal && (kv0 + 128 <= seq);   // CTA uniform
     // pass 1: row max
-    float m_blk = -INFINITY;
+    // (four independent partial maxima / sums: a single dependent chain of 128 FMNMX or FADD costs ~4 clk per element)
+    float mp[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll 1
     for (int c = 0; c < 4; ++c) {
       uint32_t v[32];
@@ -126,18 +127,19 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
       tmem_ld_wait();
       if (full) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) m_blk = fmaxf(m_blk, __uint_as_float(v[i]));
+        for (int i = 0; i < 32; ++i) mp[i & 3] = fmaxf(mp[i & 3], __uint_as_float(v[i]));
       } else {
 #pragma unroll
         for (int i = 0; i < 32; ++i)
-          if (c * 32 + i < kv_hi) m_blk = fmaxf(m_blk, __uint_as_float(v[i]));
+          if (c * 32 + i < kv_hi) mp[i & 3] = fmaxf(mp[i & 3], __uint_as_float(v[i]));
       }
     }
+    const float m_blk = fmaxf(fmaxf(mp[0], mp[1]), fmaxf(mp[2], mp[3]));
     const float m_new = fmaxf(m_run, m_blk);
     const float m_scaled = (m_new == -INFINITY) ? 0.f : m_new * scale_log2e;
     const float alpha = (m_run == -INFINITY) ? 0.f : fast_ex2(m_run * scale_log2e - m_scaled);
     // pass 2: p = exp2(s*scale - m), row sum, P -> swizzled smem (bf16)
-    float l_blk = 0.f;
+    float lp[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
     for (int c = 0; c < 4; ++c) {
       uint32_t v[32];
@@ -164,8 +166,9 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
         *reinterpret_cast<uint4*>(tile + ((chunk ^ r8) << 4)) = u;
       }
 #pragma unroll
-      for (int i = 0; i < 32; ++i) l_blk += p[i];
+      for (int i = 0; i < 32; ++i) lp[i & 3] += p[i];
     }
+    const float l_blk = (lp[0] + lp[1]) + (lp[2] + lp[3]);
     l_run = l_run * alpha + l_blk;
     m_run = m_new;
 #pragma unroll
