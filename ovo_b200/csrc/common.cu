@@ -114,6 +114,7 @@ static int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N
 }
 
 static int g_gemm_debug = 0;
+static int g_query_cluster = 1;   // cluster size of the wide (Q > 64) dense query: the text tile is multicast (set by tuning)
 static int g_gemm_cluster = -1;   // -1 = auto; OVO_B200_GEMM_CLUSTER=1|2|4 forces a cluster size (tuning aid)
 
 template <int EPI>
@@ -126,7 +127,7 @@ static int launch_bn(int bn, const __nv_bfloat16* A, int lda, const __nv_bfloat1
   // clusters pay off when there are enough M tiles to share a B tile; the narrow tiles (query, pooling) stay 1-CTA
   int cs = 1;
   // measured on B200: the GEMM was epilogue-bound, not L2-bound, and multicast brought nothing -> default 1
-  if (bn >= 128 && ceil_div(M, kBM) >= 2) cs = g_gemm_cluster > 0 ? g_gemm_cluster : 1;
+  if (bn >= 128 && ceil_div(M, kBM) >= 2) cs = g_gemm_cluster > 0 ? g_gemm_cluster : (ep.prof_cls == PROF_QUERY ? g_query_cluster : 1);
   if (bn < 128 || ceil_div(M, kBM) < cs) cs = 1;
   CUtensorMap ta, tb;
   OVO_TRY(make_tmap_bf16_2d(&ta, A, M, K, lda, kBM, kBK));
@@ -211,6 +212,7 @@ int ovo_profile_report(int n_classes, float* ms, double* flops, double* bytes, i
 void ovo_set_gemm_cluster(int cluster_size) {
   ovo::g_gemm_cluster = cluster_size & 0xff;
   ovo::g_gemm_debug = (cluster_size >> 8) & 0xff;   // bits 8..15: tuning experiments (EpiParams::debug)
+  if ((cluster_size >> 16) & 0xff) ovo::g_query_cluster = (cluster_size >> 16) & 0xff;   // bits 16..23: query cluster
 }
 
 int ovo_gemm_bf16(const void* A_dev, int lda, const void* B_dev, int ldb, int M, int N, int K, const float* bias_dev,

@@ -260,6 +260,29 @@ def stage_clusters():
         print(f"vit forward (graph) n_img={n_img}: {ms:.3f} ms  {n_img * 349.2 / ms:.1f} TFLOP/s", flush=True)
 
 
+def stage_querycs():
+    """Dense query at Q=200 with the text tile multicast over clusters of 1/2/4 CTAs."""
+    from ovo_b200 import _lib
+    sm = SemanticMap()
+    N = 2_000_000
+    bank = torch.randn(N, 1024, device=dev).bfloat16()
+    for Q in (200, 64, 128):
+        text = torch.randn(Q, 1024, device=dev)
+        out = torch.empty(N, Q, device=dev)
+        ref = None
+        for cs in (1, 2, 4):
+            _lib.lib().ovo_set_gemm_cluster(cs << 16)
+            sm.query_dense(bank, text, out)
+            torch.cuda.synchronize()
+            if ref is None:
+                ref = out[:4096].clone()
+            same = torch.equal(ref, out[:4096])
+            ms = _time(lambda: sm.query_dense(bank, text, out), n=10)
+            gb = (N * 1024 * 2 + N * Q * 4 + Q * 1024 * 2) / 1e9
+            print(f"query Q={Q} cluster={cs}: {ms:.3f} ms  {gb / ms * 1e3:.0f} GB/s  same={same}", flush=True)
+    _lib.lib().ovo_set_gemm_cluster(1 << 16)
+
+
 def stage_gemmdbg():
     """Which part bounds the GEMM: full vs no-epilogue-stores vs no-MMA vs no-TMA (EpiParams::debug bits)."""
     from ovo_b200 import _lib
