@@ -1,8 +1,9 @@
 // Flash-style softmax attention forward for head_dim 64 on tcgen05 (reference: F.scaled_dot_product_attention
 // at pe.py:145-147 for the vision tower, nn.MultiheadAttention with the causal mask pe.py:621-627 for text).
 //
-// One CTA = one (image, head, 128-query tile), 128 threads, TWO CTAs resident per SM (112 KB smem, 256 TMEM
-// columns each) so that one CTA's softmax overlaps the other's tensor-core work.
+// One CTA = one (image, head, 128-query tile), 256 threads: two threads per query row, each owning half of the keys
+// of a block and half of the output columns (the softmax is issue/latency bound, so warps per SM matter).  TWO CTAs
+// are resident per SM (112 KB smem, 256 TMEM columns each): one CTA's softmax overlaps the other's tensor-core work.
 // Q (128x64) is TMA-loaded once; K (128x64) and V^T (64x128) blocks stream through 2-slot rings of 128B-swizzled
 // shared memory.  Per 128-key block: S = Q.K^T (tcgen05, accumulator in TMEM) -> tcgen05.ld -> online softmax in
 // registers (one thread per query row, exp2f) -> P (bf16) written to swizzled smem -> O_j = P.V_j (tcgen05,
@@ -13,7 +14,7 @@
 
 namespace ovo {
 
-constexpr int kAttnThreads = 128;
+constexpr int kAttnThreads = 256;
 constexpr int kAttnMaxBlocks = 5;  // seq_pad <= 640
 
 struct AttnSmem {
@@ -21,7 +22,7 @@ struct AttnSmem {
   static constexpr int kKBlock = 128 * 64 * 2;  // 16 KB per 128 keys
   static constexpr int kVBlock = 64 * 64 * 2;   // 8 KB per 64 keys (V^T tile: 64 d-rows x 64 keys); 2 per block
   static constexpr int kP = 2 * 128 * 64 * 2;   // 32 KB: P as two K-major 128x64 tiles
-  static constexpr int kBytes = kQ + 2 * kKBlock + 4 * kVBlock + kP + 256;  // 112 KB + barriers
+  static constexpr int kBytes = kQ + 2 * kKBlock + 4 * kVBlock + kP + 256 + 512;  // 112 KB + barriers + row exchange
 };
 
 __global__ void __launch_bounds__(kAttnThreads, 2)
@@ -41,6 +42,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
   uint64_t* bar_s = bars + 4;   // S ready
   uint64_t* bar_o = bars + 5;   // P.V ready
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+  float* s_x = reinterpret_cast<float*>(sP + AttnSmem::kP + 256);  // [128] per-row exchange between the two halves
 
   const int tid = threadIdx.x, warp = tid >> 5;
   const int qt = blockIdx.x;  // query tile
@@ -95,15 +97,17 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
     issue_qk(0);
   }
 
-  // per-thread state: one query row each
-  const int qrow = q0 + tid;
-  float m_run = -INFINITY, l_run = 0.f;
-  float o_acc[64];
+  // per-thread state: thread (row, half) owns query row `row`, keys [64*half, 64*half+64) of every block and output
+  // columns [32*half, 32*half+32)
+  const int row = tid & 127, half = tid >> 7;
+  const int qrow = q0 + row;
+  float m_run = -INFINITY, l_run = 0.f;  // l_run: partial row sum over this thread's keys (same m for both halves)
+  float o_acc[32];
 #pragma unroll
-  for (int i = 0; i < 64; ++i) o_acc[i] = 0.f;
-  const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
-  const int r8 = tid & 7;
-  uint8_t* p_row = sP + (tid >> 3) * 1024 + r8 * 128;
+  for (int i = 0; i < 32; ++i) o_acc[i] = 0.f;
+  const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
+  const int r8 = row & 7;
+  uint8_t* p_row = sP + half * (128 * 128) + (row >> 3) * 1024 + r8 * 128;  // P tile `half` = this thread's 64 keys
 
   for (int j = 0; j < nb; ++j) {
     mbar_wait(bar_s, j & 1);
@@ -111,19 +115,17 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
     // K slot j&1 has been consumed by Q.K_j^T: refill it with block j+2
     if (tid == 0 && j + 2 < nb) load_k(j + 2);
 
-    const int kv0 = j * 128;
+    const int kv0 = j * 128 + half * 64;             // first key of this thread's half
     int kv_hi = seq - kv0;                           // keys >= seq are padding
     if (causal) kv_hi = min(kv_hi, qrow - kv0 + 1);  // keys > query are masked
-    // blocks that are entirely valid (all but the last one, and no causal diagonal) skip the per-element masking:
-    // the softmax is instruction-issue bound, every instruction per score counts
-    const bool full = !causal && (kv0 + 128 <= seq);   // CTA uniform
-    // pass 1: row max
-    // (four independent partial maxima / sums: a single dependent chain of 128 FMNMX or FADD costs ~4 clk per element)
+    // blocks that are entirely valid (all but the last one, and no causal diagonal) skip the per-element masking
+    const bool full = !causal && (j * 128 + 128 <= seq);   // CTA uniform
+    // pass 1: row max over this thread's 64 keys (independent partial maxima: no long dependent chain)
     float mp[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < 2; ++c) {
       uint32_t v[32];
-      tmem_ld_32x32(tmem_S + lane_off + c * 32, v);
+      tmem_ld_32x32(tmem_S + lane_off + half * 64 + c * 32, v);
       tmem_ld_wait();
       if (full) {
 #pragma unroll
@@ -134,16 +136,22 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
           if (c * 32 + i < kv_hi) mp[i & 3] = fmaxf(mp[i & 3], __uint_as_float(v[i]));
       }
     }
-    const float m_blk = fmaxf(fmaxf(mp[0], mp[1]), fmaxf(mp[2], mp[3]));
+    float m_blk = fmaxf(fmaxf(mp[0], mp[1]), fmaxf(mp[2], mp[3]));
+    // both halves of a row must use the same maximum: half 1 publishes, half 0 combines and publishes back
+    if (half == 1) s_x[row] = m_blk;
+    __syncthreads();
+    if (half == 0) { m_blk = fmaxf(m_blk, s_x[row]); s_x[row] = m_blk; }
+    __syncthreads();
+    if (half == 1) m_blk = s_x[row];
     const float m_new = fmaxf(m_run, m_blk);
     const float m_scaled = (m_new == -INFINITY) ? 0.f : m_new * scale_log2e;
     const float alpha = (m_run == -INFINITY) ? 0.f : fast_ex2(m_run * scale_log2e - m_scaled);
-    // pass 2: p = exp2(s*scale - m), row sum, P -> swizzled smem (bf16)
+    // pass 2: p = exp2(s*scale - m), partial row sum, P -> swizzled smem (bf16)
     float lp[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < 2; ++c) {
       uint32_t v[32];
-      tmem_ld_32x32(tmem_S + lane_off + c * 32, v);
+      tmem_ld_32x32(tmem_S + lane_off + half * 64 + c * 32, v);
       tmem_ld_wait();
       float p[32];
       if (full) {
@@ -156,23 +164,21 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
           p[i] = (c * 32 + i < kv_hi) ? e : 0.f;
         }
       }
-      uint8_t* tile = p_row + (c >> 1) * (128 * 128);  // keys 0-63 -> tile 0, 64-127 -> tile 1
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         uint4 u;
         u.x = pack_bf16(p[8 * g], p[8 * g + 1]); u.y = pack_bf16(p[8 * g + 2], p[8 * g + 3]);
         u.z = pack_bf16(p[8 * g + 4], p[8 * g + 5]); u.w = pack_bf16(p[8 * g + 6], p[8 * g + 7]);
-        const int chunk = (c & 1) * 4 + g;  // 16-byte chunk index inside the 128-byte row
-        *reinterpret_cast<uint4*>(tile + ((chunk ^ r8) << 4)) = u;
+        const int chunk = c * 4 + g;  // 16-byte chunk index inside the 128-byte row
+        *reinterpret_cast<uint4*>(p_row + ((chunk ^ r8) << 4)) = u;
       }
 #pragma unroll
       for (int i = 0; i < 32; ++i) lp[i & 3] += p[i];
     }
-    const float l_blk = (lp[0] + lp[1]) + (lp[2] + lp[3]);
-    l_run = l_run * alpha + l_blk;
+    l_run = l_run * alpha + ((lp[0] + lp[1]) + (lp[2] + lp[3]));
     m_run = m_new;
 #pragma unroll
-    for (int i = 0; i < 64; ++i) o_acc[i] *= alpha;
+    for (int i = 0; i < 32; ++i) o_acc[i] *= alpha;
 
     // P visible to the async proxy and every thread done reading S; then O_j = P.V_j and S_{j+1} = Q.K_{j+1}^T
     fence_proxy_async_smem();
@@ -197,22 +203,27 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
     tc_fence_after();
     // V slot j&1 has been consumed by P.V_j: refill it with block j+2
     if (tid == 0 && j + 2 < nb) load_v(j + 2);
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
+    {
       uint32_t v[32];
-      tmem_ld_32x32(tmem_O + lane_off + c * 32, v);
+      tmem_ld_32x32(tmem_O + lane_off + half * 32, v);
       tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] += __uint_as_float(v[i]);
+      for (int i = 0; i < 32; ++i) o_acc[i] += __uint_as_float(v[i]);
     }
     tc_fence_before();  // these TMEM reads are ordered before the next P.V (issued after the next __syncthreads)
   }
 
+  // total row sum = sum of the two halves' partial sums
+  if (half == 1) s_x[row] = l_run;
+  __syncthreads();
+  if (half == 0) { l_run += s_x[row]; s_x[row] = l_run; }
+  __syncthreads();
+  if (half == 1) l_run = s_x[row];
   if (qrow < seq) {
     const float inv = 1.f / l_run;
-    __nv_bfloat16* dst = out + (static_cast<size_t>(b) * seq + qrow) * ld_out + head * 64;
+    __nv_bfloat16* dst = out + (static_cast<size_t>(b) * seq + qrow) * ld_out + head * 64 + half * 32;
 #pragma unroll
-    for (int g = 0; g < 8; ++g) {
+    for (int g = 0; g < 4; ++g) {
       uint4 u;
       u.x = pack_bf16(o_acc[8 * g] * inv, o_acc[8 * g + 1] * inv);
       u.y = pack_bf16(o_acc[8 * g + 2] * inv, o_acc[8 * g + 3] * inv);

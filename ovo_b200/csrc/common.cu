@@ -114,7 +114,7 @@ static int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N
 }
 
 static int g_gemm_debug = 0;
-static int g_query_cluster = 1;   // cluster size of the wide (Q > 64) dense query: the text tile is multicast (set by tuning)
+static int g_query_cluster = 2;   // cluster size of the wide (Q > 64) dense query: the text tile is multicast (set by tuning)
 static int g_gemm_cluster = -1;   // -1 = auto; OVO_B200_GEMM_CLUSTER=1|2|4 forces a cluster size (tuning aid)
 
 template <int EPI>
