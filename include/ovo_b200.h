@@ -231,6 +231,16 @@ int ovo_merge_masks(const uint8_t* masks_dev, int M, int H, int W, const int32_t
  * 1 l1_medoid (:9-12), 2 cossim_medoid (:14-17); chosen_dev[j] (optional) = index of the medoid view. */
 int ovo_fuse_views(const float* store_dev, int D, const int32_t* idx_dev, const int32_t* off_dev, int n_instances,
                    int mode, float* bank_dev, const int32_t* out_rows_dev, int32_t* chosen_dev, void* stream);
+/* Map producer, VanillaMapper.map (ovo/slam/vanilla_mapper.py:46-85): depth pixels not yet explained
+ * by a map point (same cull/project/depth test as the association, match_th 0.03, 3x3 erosion of the free mask,
+ * every `downscale`-th pixel) are un-projected with c2w and APPENDED at row N of the caller's pre-reserved buffers
+ * (xyz f32 [capacity,3], ids i32, ins_ids i32 = -1, colors u8 [capacity,3] optional) — no vstack re-allocation.
+ * Synchronises `stream` once to return the number of new points. */
+int ovo_map_integrate(ovo_map_t* map, float* xyz_dev, int32_t* ids_dev, int32_t* ins_ids_dev, uint8_t* colors_dev, int64_t N,
+                      int64_t capacity, const float* depth_dev, const uint8_t* rgb_dev, int h, int w, const float* c2w,
+                      const float* w2c, const float* K, float match_th, int downscale, int k_pool, int next_point_id,
+                      int* n_new_host, void* stream);
+
 /* S2 — mask post-processing of the proposals (ovo/utils/segment_utils.py).
  * ovo_mask_nms = masks_update + mask_nms + filter (:173-259): masks uint8 [M,H,W], scores f32 [M] (= stability *
  * predicted_iou) -> keep_dev uint8 [M] in the ORIGINAL mask order.  OVO passes iou_thr 0.8, score_thr 0.7, inner_thr 0.5

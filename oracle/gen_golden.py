@@ -202,6 +202,28 @@ def gen_ovo():
     print("objects", keys, "n_kfs", out["object_n_kfs"])
 
 
+MAPPER_FRAMES = [(fid, 3 * fid, 0.0123 * fid) for fid in range(5)]       # (depth frame, pose frame, yaw)
+
+
+def gen_mapper():
+    """Reference VanillaMapper.map (ovo/slam/vanilla_mapper.py:46-85) over 5 frames."""
+    from ovo_b200 import synth
+    rh.setup_paths()
+    from ovo.slam.vanilla_mapper import VanillaMapper
+    K = synth.intrinsics()
+    vm = VanillaMapper({"device": "cpu", "mapping": {"k_pooling": 3}}, torch.from_numpy(K))
+    out = {}
+    for i, (fid, pf, yaw) in enumerate(MAPPER_FRAMES):
+        d, c2w, img = synth.depth_map(frame_id=fid), synth.pose(pf, yaw=yaw), synth.rgb(seed=fid)
+        n0 = vm.pcd.shape[0]
+        vm.map([fid, img, d, c2w], torch.from_numpy(c2w))
+        out[f"n_{i}"] = np.array(vm.pcd.shape[0] - n0)
+        out[f"xyz_{i}"] = vm.pcd[n0:].numpy()[::37]
+        out[f"col_{i}"] = vm.pcd_colors[n0:].numpy()[::37]
+    np.savez_compressed(os.path.join(OUT, "mapper.npz"), **out)
+    print("mapper.npz", {k: v.shape for k, v in out.items()})
+
+
 def gen_masks():
     """Reference masks_update / mask2segmap (ovo/utils/segment_utils.py) on synthetic proposals."""
     rh.setup_paths()
@@ -224,6 +246,6 @@ if __name__ == "__main__":
     if not rh.available():
         sys.exit("reference not available: fixtures can only be generated in the build container")
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["encoder", "assoc", "ovo", "masks"]
+    which = sys.argv[1:] or ["encoder", "assoc", "ovo", "masks", "mapper"]
     for w in which:
         globals()["gen_" + w]()

@@ -74,6 +74,9 @@ SIGNATURES = {
     "ovo_merge_masks": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "ovo_fuse_views": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "ovo_text_bank": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "ovo_map_integrate": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int, c_int,
+                                  C.POINTER(c_float), C.POINTER(c_float), C.POINTER(c_float), c_float, c_int, c_int, c_int,
+                                  C.POINTER(c_int), c_void_p]),
     "ovo_mask_nms": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_float, c_float, c_void_p, c_void_p]),
     "ovo_mask2segmap": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "ovo_classify": (c_int, [c_void_p, c_int64, c_int, c_float, c_void_p, c_void_p, c_void_p]),

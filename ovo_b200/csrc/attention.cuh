@@ -28,7 +28,7 @@ struct AttnSmem {
 __global__ void __launch_bounds__(kAttnThreads, 2)
     attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                          const __grid_constant__ CUtensorMap tmVt, __nv_bfloat16* __restrict__ out, int seq,
-                         int seq_pad, int heads, int ld_out, float scale_log2e, int causal) {
+                         int seq_pad, int heads, int ld_out, float scale_log2e, int causal, int dbg) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();  // the 128B swizzle needs 1024-byte aligned tiles
   const int nblk = seq_pad / 128;
@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
     // pass 1: row max over this thread's 64 keys (independent partial maxima: no long dependent chain)
     float mp[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll 1
-    for (int c = 0; c < 2; ++c) {
+    for (int c = 0; c < ((dbg & 1) ? 0 : 2); ++c) {
       uint32_t v[32];
       tmem_ld_32x32(tmem_S + lane_off + half * 64 + c * 32, v);
       tmem_ld_wait();
@@ -138,18 +138,20 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
     }
     float m_blk = fmaxf(fmaxf(mp[0], mp[1]), fmaxf(mp[2], mp[3]));
     // both halves of a row must use the same maximum: half 1 publishes, half 0 combines and publishes back
-    if (half == 1) s_x[row] = m_blk;
-    __syncthreads();
-    if (half == 0) { m_blk = fmaxf(m_blk, s_x[row]); s_x[row] = m_blk; }
-    __syncthreads();
-    if (half == 1) m_blk = s_x[row];
+    if (!(dbg & 8)) {
+      if (half == 1) s_x[row] = m_blk;
+      __syncthreads();
+      if (half == 0) { m_blk = fmaxf(m_blk, s_x[row]); s_x[row] = m_blk; }
+      __syncthreads();
+      if (half == 1) m_blk = s_x[row];
+    }
     const float m_new = fmaxf(m_run, m_blk);
     const float m_scaled = (m_new == -INFINITY) ? 0.f : m_new * scale_log2e;
     const float alpha = (m_run == -INFINITY) ? 0.f : fast_ex2(m_run * scale_log2e - m_scaled);
     // pass 2: p = exp2(s*scale - m), partial row sum, P -> swizzled smem (bf16)
     float lp[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
-    for (int c = 0; c < 2; ++c) {
+    for (int c = 0; c < ((dbg & 1) ? 0 : 2); ++c) {
       uint32_t v[32];
       tmem_ld_32x32(tmem_S + lane_off + half * 64 + c * 32, v);
       tmem_ld_wait();
@@ -181,7 +183,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
     for (int i = 0; i < 32; ++i) o_acc[i] *= alpha;
 
     // P visible to the async proxy and every thread done reading S; then O_j = P.V_j and S_{j+1} = Q.K_{j+1}^T
-    fence_proxy_async_smem();
+    if (!(dbg & 4)) fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
     if (tid == 0) {
@@ -203,7 +205,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
     tc_fence_after();
     // V slot j&1 has been consumed by P.V_j: refill it with block j+2
     if (tid == 0 && j + 2 < nb) load_v(j + 2);
-    {
+    if (!(dbg & 2)) {
       uint32_t v[32];
       tmem_ld_32x32(tmem_O + lane_off + half * 32, v);
       tmem_ld_wait();

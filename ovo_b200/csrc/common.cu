@@ -7,6 +7,8 @@
 #include <mutex>
 #include <vector>
 
+extern int g_attn_debug;
+
 namespace ovo {
 
 static thread_local char g_err[512] = "";
@@ -213,6 +215,7 @@ void ovo_set_gemm_cluster(int cluster_size) {
   ovo::g_gemm_cluster = cluster_size & 0xff;
   ovo::g_gemm_debug = (cluster_size >> 8) & 0xff;   // bits 8..15: tuning experiments (EpiParams::debug)
   if ((cluster_size >> 16) & 0xff) ovo::g_query_cluster = (cluster_size >> 16) & 0xff;   // bits 16..23: query cluster
+  g_attn_debug = (cluster_size >> 24) & 0x7f;                                            // bits 24..30: attention experiments
 }
 
 int ovo_gemm_bf16(const void* A_dev, int lda, const void* B_dev, int ldb, int M, int N, int K, const float* bias_dev,

@@ -356,6 +356,8 @@ struct ovo_encoder {
   cudaStream_t cap_stream = nullptr;  // capture happens here (the caller's stream may be the legacy stream)
 };
 
+int g_attn_debug = 0;   // tuning experiments (attention.cuh dbg bits), set through ovo_set_gemm_cluster bits 24..31
+
 namespace {
 
 template <typename T>
@@ -398,7 +400,7 @@ int launch_attention(ovo_encoder* e, int n_seq, int seq, int seq_pad, int heads,
   const float scale_log2e = 0.125f * 1.4426950408889634f;  // head_dim 64
   ProfScope prof(s, PROF_ATTN, 4.0 * static_cast<double>(bh) * seq * (causal ? 0.5 * seq : seq) * 64, 4.0 * static_cast<double>(bh) * seq * 64 * 2);
   attention_fwd_kernel<<<dim3(qtiles, static_cast<unsigned>(bh)), kAttnThreads, smem, s>>>(
-      tq, tk, tv, e->attn, seq, seq_pad, heads, width, scale_log2e, causal ? 1 : 0);
+      tq, tk, tv, e->attn, seq, seq_pad, heads, width, scale_log2e, causal ? 1 : 0, g_attn_debug);
   OVO_CHECK_LAUNCH();
   return OVO_OK;
 }

@@ -715,6 +715,130 @@ __global__ void paint_segmap_kernel(const uint8_t* __restrict__ masks, const int
   seg[i] = s;
 }
 
+
+// ------------------------------------------------------------------------------------------ map producer
+// VanillaMapper.map (ovo/slam/vanilla_mapper.py:46-85): depth pixels that are not explained by a map point yet are
+// un-projected and appended.  Same cull + project + depth test as the association (match_th 0.03, raw depth).
+__device__ __forceinline__ bool match_point_rn(float x, float y, float z, const FrameGeom& g, const FrameDev& f,
+                                               const float* __restrict__ depth, int& u, int& v) {
+  bool in = x >= g.lo[0] && x <= g.hi[0] && y >= g.lo[1] && y <= g.hi[1] && z >= g.lo[2] && z <= g.hi[2];
+  if (!in) return false;
+#pragma unroll
+  for (int p = 0; p < 6; ++p) in = in && (dot4_rn(g.planes[p], x, y, z) <= 0.f);
+  if (!in) return false;
+  const float lx = dot4_rn(&f.w2c[0], x, y, z), ly = dot4_rn(&f.w2c[4], x, y, z);
+  const float lz = dot4_rn(&f.w2c[8], x, y, z), lw = dot4_rn(&f.w2c[12], x, y, z);
+  const float X = __fdiv_rn(lx, lw), Y = __fdiv_rn(ly, lw), Z = __fdiv_rn(lz, lw);
+  float ph[3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+    ph[r] = __fadd_rn(__fadd_rn(__fmul_rn(f.K[3 * r], X), __fmul_rn(f.K[3 * r + 1], Y)), __fmul_rn(f.K[3 * r + 2], Z));
+  const float uf = rintf(__fdiv_rn(ph[0], ph[2])), vf = rintf(__fdiv_rn(ph[1], ph[2]));
+  if (!(fabsf(uf) < 2e9f && fabsf(vf) < 2e9f)) return false;
+  u = static_cast<int>(uf);
+  v = static_cast<int>(vf);
+  if (u < 0 || v < 0 || u >= f.w || v >= f.h) return false;
+  const float d = __ldg(depth + static_cast<size_t>(v) * f.w + u);
+  return fabsf(__fsub_rn(lz, d)) < f.match_th && d != 0.f;
+}
+
+__global__ void mark_mapped_pixels_kernel(const float* __restrict__ xyz, long long N, const float* __restrict__ depth,
+                                          const FrameGeom* __restrict__ geom, const FrameDev* __restrict__ fr,
+                                          uint8_t* __restrict__ mapped) {
+  __shared__ FrameGeom s_g;
+  __shared__ FrameDev s_f;
+  if (threadIdx.x < sizeof(FrameGeom) / 4) reinterpret_cast<int*>(&s_g)[threadIdx.x] = reinterpret_cast<const int*>(geom)[threadIdx.x];
+  for (int i = threadIdx.x; i < static_cast<int>(sizeof(FrameDev) / 4); i += blockDim.x)
+    reinterpret_cast<int*>(&s_f)[i] = reinterpret_cast<const int*>(fr)[i];
+  __syncthreads();
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < N;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    int u, v;
+    if (match_point_rn(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], s_g, s_f, depth, u, v)) mapped[static_cast<size_t>(v) * s_f.w + u] = 1;
+  }
+}
+
+// flag[(y/ds)*(wd)+(x/ds)] = 1 iff pixel (y,x) (y,x multiples of ds) yields a new point: depth > 0 and, when the map
+// is not empty, the whole k x k neighbourhood is valid and unmapped (~maxpool(~mask), padding counts as valid)
+__global__ void new_point_flags_kernel(const float* __restrict__ depth, const uint8_t* __restrict__ mapped, int h, int w,
+                                       int ds, int kpool, int erode, int hd, int wd, int32_t* __restrict__ flags) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= hd * wd) return;
+  const int y = (i / wd) * ds, x = (i % wd) * ds;
+  bool ok = depth[static_cast<size_t>(y) * w + x] > 0.f;
+  if (erode) {
+    ok = ok && !mapped[static_cast<size_t>(y) * w + x];
+    const int r = kpool / 2;
+    for (int dy = -r; dy <= r && ok; ++dy)
+      for (int dx = -r; dx <= r; ++dx) {
+        const int yy = y + dy, xx = x + dx;
+        if (yy < 0 || xx < 0 || yy >= h || xx >= w) continue;
+        if (!(depth[static_cast<size_t>(yy) * w + xx] > 0.f) || mapped[static_cast<size_t>(yy) * w + xx]) { ok = false; break; }
+      }
+  }
+  flags[i] = ok ? 1 : 0;
+}
+
+// single-block exclusive scan (n <= a few 100k): flags -> positions, total in *count
+__global__ void __launch_bounds__(1024) scan_flags_kernel(const int32_t* __restrict__ flags, int n, int32_t* __restrict__ pos,
+                                                          int32_t* __restrict__ count) {
+  __shared__ int s_warp[32];
+  __shared__ int s_carry;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int base = 0; base < n; base += 1024) {
+    const int i = base + threadIdx.x;
+    const int f = i < n ? flags[i] : 0;
+    int incl = f;
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      int w = s_warp[lane];
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += t;
+      }
+      s_warp[lane] = w;
+    }
+    __syncthreads();
+    const int before = s_carry + (warp ? s_warp[warp - 1] : 0) + incl - f;
+    if (i < n) pos[i] = before;
+    __syncthreads();
+    if (threadIdx.x == 1023) s_carry = before + f;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *count = s_carry;
+}
+
+__global__ void emit_points_kernel(const int32_t* __restrict__ flags, const int32_t* __restrict__ pos, int hd, int wd, int ds,
+                                   const float* __restrict__ depth, const uint8_t* __restrict__ rgb, int w,
+                                   const FrameDev* __restrict__ fr, long long capacity_left, float* __restrict__ xyz_out,
+                                   int32_t* __restrict__ ids_out, int32_t* __restrict__ ins_out, uint8_t* __restrict__ col_out,
+                                   int base_id) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= hd * wd || !flags[i]) return;
+  const int k = pos[i];
+  if (k >= capacity_left) return;
+  const int y = (i / wd) * ds, x = (i % wd) * ds;
+  const float d = depth[static_cast<size_t>(y) * w + x];
+  // vanilla_mapper.py:73-79 in a fixed f32 order
+  const float X = __fdiv_rn(__fmul_rn(__fsub_rn(static_cast<float>(x), fr->K[2]), d), fr->K[0]);
+  const float Y = __fdiv_rn(__fmul_rn(__fsub_rn(static_cast<float>(y), fr->K[5]), d), fr->K[4]);
+#pragma unroll
+  for (int r = 0; r < 3; ++r) xyz_out[3 * static_cast<size_t>(k) + r] = dot4_rn(&fr->c2w[4 * r], X, Y, d);
+  ids_out[k] = base_id + k;
+  ins_out[k] = -1;
+  if (col_out != nullptr && rgb != nullptr) {
+    const uint8_t* c = rgb + (static_cast<size_t>(y) * w + x) * 3;
+    col_out[3 * static_cast<size_t>(k)] = c[0]; col_out[3 * static_cast<size_t>(k) + 1] = c[1]; col_out[3 * static_cast<size_t>(k) + 2] = c[2];
+  }
+}
+
 }  // namespace ovo
 
 // =============================================================================================== handle
@@ -736,7 +860,8 @@ struct ovo_map {
   int32_t* area = nullptr; int32_t* mask_ins = nullptr; ovo_vote_row* rows = nullptr; int masks_cap = 0;
   int2* scratch_list = nullptr; size_t scratch_cap = 0;
   float* depth_f = nullptr; size_t depth_cap = 0;
-  int16_t* seg_dense = nullptr; size_t seg_dense_cap = 0;   // [F][N] scratch of ovo_map_fuse_dense_batch
+  int16_t* seg_dense = nullptr; size_t seg_dense_cap = 0;
+  uint8_t* mapped = nullptr; size_t mapped_cap = 0; int32_t* pix_flags = nullptr; size_t pix_cap = 0;   // map producer scratch   // [F][N] scratch of ovo_map_fuse_dense_batch
   int2* slot_list[kSlots] = {}; size_t slot_cap[kSlots] = {}; int slot_n[kSlots] = {};
   __nv_bfloat16* text_bf16 = nullptr; size_t text_cap = 0;
   // pinned host staging
@@ -796,7 +921,7 @@ int ovo_map_create(ovo_map_t** out) {
 void ovo_map_destroy(ovo_map_t* m) {
   if (!m) return;
   cudaFree(m->ctl); cudaFreeHost(m->h_ctl); cudaFree(m->votes); cudaFree(m->area);
-  cudaFree(m->scratch_list); cudaFree(m->depth_f); cudaFree(m->seg_dense); cudaFree(m->text_bf16);
+  cudaFree(m->scratch_list); cudaFree(m->depth_f); cudaFree(m->seg_dense); cudaFree(m->mapped); cudaFree(m->pix_flags); cudaFree(m->text_bf16);
   for (int i = 0; i < ovo_map::kSlots; ++i) cudaFree(m->slot_list[i]);
   delete m;
 }
@@ -1064,6 +1189,55 @@ int ovo_fuse_views(const float* store_dev, int D, const int32_t* idx_dev, const 
   if (n_instances <= 0) return OVO_OK;
   ovo::fuse_views_kernel<<<n_instances, 256, 0, static_cast<cudaStream_t>(stream)>>>(store_dev, D, idx_dev, off_dev, mode, bank_dev, out_rows_dev, chosen_dev);
   OVO_CHECK_LAUNCH();
+  return OVO_OK;
+}
+
+int ovo_map_integrate(ovo_map_t* m, float* xyz_dev, int32_t* ids_dev, int32_t* ins_ids_dev, uint8_t* colors_dev, int64_t N,
+                      int64_t capacity, const float* depth_dev, const uint8_t* rgb_dev, int h, int w, const float* c2w,
+                      const float* w2c, const float* K, float match_th, int downscale, int k_pool, int next_point_id,
+                      int* n_new_host, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  OVO_REQUIRE(m && xyz_dev && ids_dev && ins_ids_dev && depth_dev && c2w && w2c && K && n_new_host, "ovo_map_integrate: null argument");
+  OVO_REQUIRE(N >= 0 && capacity >= N && h > 0 && w > 0 && downscale >= 1 && k_pool >= 1 && (k_pool & 1), "ovo_map_integrate: bad arguments");
+  const int npix = h * w, hd = (h + downscale - 1) / downscale, wd = (w + downscale - 1) / downscale;
+  OVO_TRY(grow(&m->mapped, &m->mapped_cap, static_cast<size_t>(npix)));
+  OVO_TRY(grow(&m->pix_flags, &m->pix_cap, 2 * static_cast<size_t>(hd) * wd));
+  ovo::FrameDev* hf = m->h_frame;
+  memset(hf, 0, sizeof(*hf));
+  memcpy(hf->c2w, c2w, sizeof(hf->c2w)); memcpy(hf->w2c, w2c, sizeof(hf->w2c)); memcpy(hf->K, K, sizeof(hf->K));
+  hf->match_th = match_th; hf->h = h; hf->w = w; hf->H = h; hf->W = w;
+  CtlHeader* hh = reinterpret_cast<CtlHeader*>(m->h_ctl);
+  memset(&hh->geom, 0, sizeof(hh->geom));
+  hh->geom.dmin_bits = 0x7f800000; hh->geom.dmax_bits = 0;
+  m->h_counters[0] = m->h_counters[1] = m->h_counters[2] = m->h_counters[3] = 0;
+  OVO_CUDA(cudaMemcpyAsync(m->ctl, m->h_ctl, sizeof(CtlHeader), cudaMemcpyHostToDevice, stream));
+  const int sms = ovo::num_sms();
+  const int erode = N > 0 ? 1 : 0;   // vanilla_mapper.py:58: suppression + pooling only once the map is not empty
+  if (N > 0) {
+    OVO_CUDA(cudaMemsetAsync(m->mapped, 0, npix, stream));
+    ovo::depth_minmax_kernel<<<sms, 256, 0, stream>>>(depth_dev, npix, m->geom);
+    OVO_CHECK_LAUNCH();
+    ovo::frustum_setup_kernel<<<1, 1, 0, stream>>>(m->geom, m->frame);
+    OVO_CHECK_LAUNCH();
+    ovo::mark_mapped_pixels_kernel<<<static_cast<int>(std::min<long long>((N + 255) / 256, sms * 8LL)), 256, 0, stream>>>(
+        xyz_dev, N, depth_dev, m->geom, m->frame, m->mapped);
+    OVO_CHECK_LAUNCH();
+  }
+  int32_t* flags = m->pix_flags;
+  int32_t* pos = m->pix_flags + static_cast<size_t>(hd) * wd;
+  ovo::new_point_flags_kernel<<<ovo::ceil_div(hd * wd, 256), 256, 0, stream>>>(depth_dev, m->mapped, h, w, downscale, k_pool > 1 ? k_pool : 1,
+                                                                             erode && true, hd, wd, flags);
+  OVO_CHECK_LAUNCH();
+  ovo::scan_flags_kernel<<<1, 1024, 0, stream>>>(flags, hd * wd, pos, m->counters);
+  OVO_CHECK_LAUNCH();
+  ovo::emit_points_kernel<<<ovo::ceil_div(hd * wd, 256), 256, 0, stream>>>(flags, pos, hd, wd, downscale, depth_dev, rgb_dev, w, m->frame,
+                                                                         capacity - N, xyz_dev + 3 * N, ids_dev + N, ins_ids_dev + N,
+                                                                         colors_dev ? colors_dev + 3 * N : nullptr, next_point_id);
+  OVO_CHECK_LAUNCH();
+  OVO_CUDA(cudaMemcpyAsync(m->h_counters, m->counters, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+  OVO_CUDA(cudaStreamSynchronize(stream));
+  *n_new_host = m->h_counters[0];
+  if (N + *n_new_host > capacity) return ovo::set_error(OVO_E_NOMEM, "ovo_map_integrate: %d new points exceed the capacity (%lld + %d > %lld)", *n_new_host, (long long)N, *n_new_host, (long long)capacity);
   return OVO_OK;
 }
 

@@ -14,9 +14,13 @@ def intrinsics(h=480, w=640):
     return K
 
 
-def pose(frame_id: int) -> np.ndarray:
+def pose(frame_id: int, yaw: float = 0.0) -> np.ndarray:
+    """Camera-to-world: translation 0.01*frame_id along x, optional yaw (rad) about the camera's y axis."""
     c2w = np.eye(4, dtype=np.float32)
     c2w[0, 3] = 0.01 * frame_id
+    if yaw != 0.0:
+        c, s = np.float32(np.cos(yaw)), np.float32(np.sin(yaw))
+        c2w[0, 0], c2w[0, 2], c2w[2, 0], c2w[2, 2] = c, s, -s, c
     return c2w
 
 

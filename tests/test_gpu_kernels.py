@@ -232,3 +232,25 @@ def test_mask_nms_and_segmap_match_oracle(sm, golden_dir, seed):
     seg, maps, order = sm.mask2segmap(torch.from_numpy(masks[ref]), torch.from_numpy(stab[ref]))
     seg_o, maps_o, order_o = OM.mask2segmap(masks[ref], stab[ref])
     assert (seg.cpu().numpy() == seg_o).all() and (maps.cpu().numpy() == maps_o).all() and order.cpu().tolist() == order_o.tolist()
+
+
+def test_map_producer_matches_oracle(sm):
+    """PointMapper (ovo_map_integrate) == oracle/mapper.py point for point (bit-exact f32), colours included, with
+    geometric buffer growth."""
+    from oracle import mapper as OMp, gen_golden as GG2
+    from ovo_b200.mapper import PointMapper
+    K = synth.intrinsics()
+    pm = PointMapper({"device": "cuda", "mapping": {"k_pooling": 3, "reserve_points": 100000}}, torch.from_numpy(K), semmap=sm)
+    xyz = np.zeros((0, 3), np.float32)
+    for i, (fid, pf, yaw) in enumerate(GG2.MAPPER_FRAMES):
+        d, c2w, img = synth.depth_map(frame_id=fid), synth.pose(pf, yaw=yaw), synth.rgb(seed=fid)
+        n_new = pm.map([fid, img, d, c2w], torch.from_numpy(c2w))
+        new, pix = OMp.integrate_frame(xyz, d, c2w, K)
+        assert n_new == len(new)
+        got = pm.pcd[len(xyz):].cpu().numpy()
+        assert (got == new).all()
+        assert (pm.pcd_colors[len(xyz):].cpu().numpy() == img[pix[:, 0], pix[:, 1]]).all()
+        xyz = np.concatenate([xyz, new])
+    pts, pids, obj = pm.get_map()
+    assert pts.shape[0] == len(xyz) and (pids.reshape(-1).cpu().numpy() == np.arange(len(xyz))).all() and int(obj.max()) == -1
+    assert pm.capacity >= len(xyz) > 100000          # grew past the initial reservation

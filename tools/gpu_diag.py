@@ -283,6 +283,23 @@ def stage_querycs():
     _lib.lib().ovo_set_gemm_cluster(1 << 16)
 
 
+def stage_attndbg():
+    """Where the attention kernel's time goes (attention.cuh dbg bits); results are wrong in the dbg modes."""
+    from ovo_b200 import _lib
+    cfg = EncoderConfig(text_layers=0, layers=4)
+    enc, sd, ocfg = _enc(cfg, n_img=16, text=False)
+    px = torch.randn(16, 3, 336, 336, device=dev)
+    for dbg, name in ((0, "full"), (1, "no softmax (no S loads, no P)"), (2, "no O accumulate"), (4, "no proxy fence"), (8, "no max exchange"), (15, "none of them")):
+        _lib.lib().ovo_set_gemm_cluster((dbg << 24) | 1)
+        _lib.profile_begin()
+        for _ in range(2):
+            enc.forward_features_from_pixels(px)
+        torch.cuda.synchronize()
+        prof = _lib.profile_report()
+        print(f"{name:32s} 4 layers x16 img: attention {prof['attention']['ms'] / 2:.3f} ms", flush=True)
+    _lib.lib().ovo_set_gemm_cluster(1)
+
+
 def stage_gemmdbg():
     """Which part bounds the GEMM: full vs no-epilogue-stores vs no-MMA vs no-TMA (EpiParams::debug bits)."""
     from ovo_b200 import _lib
