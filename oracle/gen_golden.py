@@ -242,10 +242,77 @@ def gen_masks():
     print("masks.npz", {k: v.shape for k, v in out.items()})
 
 
+SAM_THR = dict(pred_iou_thresh=0.5, stability_score_thresh=0.5, box_nms_thresh=1.0)
+SAM_AMG_HW = (240, 320)   # the AMG fixture uses a small frame so that the stored masks stay small   # random weights: the stock 0.8 / 0.95 would reject everything
+
+
+SAM_OVO_SCORE_THR = 0.22
+
+
+def sam_image(h=480, w=640, seed=5):
+    """A blocky colour image with noise (something for the AA resize and the masks to bite on)."""
+    rng = np.random.default_rng(seed)
+    coarse = rng.integers(0, 256, (h // 40, w // 40, 3))
+    img = np.kron(coarse, np.ones((40, 40, 1))) + rng.normal(0, 12, (h, w, 3))
+    return np.clip(img, 0, 255).astype(np.uint8)
+
+
+def gen_sam():
+    """Reference SAM-2 image path (SAM2Base + SAM2ImagePredictor + SAM2AutomaticMaskGenerator, tiny Hiera geometry,
+    our seeded weights) and OVO's MaskGenerator.segment post-processing on one 640x480 image."""
+    from ovo_b200.sam_config import tiny_sam_config, random_state_dict
+    rh.setup_paths()
+    import ovo.utils.segment_utils as su
+    cfg = tiny_sam_config()
+    sd = random_state_dict(cfg, seed=0)
+    model = rh.build_sam2_reference(cfg, sd)
+    amg = rh.build_sam2_amg(model, **SAM_THR)
+    img = sam_image()
+    out = {}
+    with torch.no_grad():
+        pred = amg.predictor
+        px = pred._transforms(img)[None]
+        out["px_sub"] = px[0, :, ::16, ::16].numpy()
+        pred.set_image(img)
+        emb = pred._features["image_embed"]
+        s0, s1 = pred._features["high_res_feats"]
+        out["embed_sub"] = emb[0, :, ::4, ::4].numpy()
+        out["s0_sub"] = s0[0, :, ::16, ::16].numpy()
+        out["s1_sub"] = s1[0, :, ::8, ::8].numpy()
+        from sam2.utils.amg import build_point_grid
+        pts = torch.as_tensor(build_point_grid(16) * np.array([[640, 480]]), dtype=torch.float32)
+        in_pts = pred._transforms.transform_coords(pts, normalize=True, orig_hw=(480, 640))
+        masks, iou, low = pred._predict(in_pts[:64, None, :], torch.ones(64, 1, dtype=torch.int), multimask_output=True,
+                                        return_logits=True)
+        out["iou64"] = iou.numpy()
+        out["low_sub"] = low[:, :, ::16, ::16].numpy()
+        out["low_full1"] = low[0, 0].numpy().astype(np.float16)
+        out["mask_logit_sub"] = masks[:16, :, ::16, ::16].numpy()
+        img = sam_image(*SAM_AMG_HW, seed=6)
+        anns = amg.generate(img)
+    out["n"] = np.array(len(anns))
+    segs = np.stack([a["segmentation"] for a in anns])
+    out["seg_bits_every8"] = np.packbits(segs[::8])
+    out["seg_checksum"] = np.array([np.flatnonzero(m).sum() for m in segs], np.int64)   # sum of the set pixels' flat indices
+    out["pred_iou"] = np.array([a["predicted_iou"] for a in anns], np.float32)
+    out["stability"] = np.array([a["stability_score"] for a in anns], np.float32)
+    out["bbox"] = np.array([a["bbox"] for a in anns], np.float32)
+    out["area"] = np.array([a["area"] for a in anns], np.int64)
+    out["points"] = np.array([a["point_coords"][0] for a in anns], np.float32)
+    # OVO's second stage exactly as MaskGenerator.segment does it (mask_generator.py:113-119)
+    kept, = su.masks_update(anns, iou_thr=0.8, score_thr=SAM_OVO_SCORE_THR, inner_thr=0.5)
+    seg_map, bmaps = su.mask2segmap(kept, img)
+    out["ovo_seg_map"] = seg_map.astype(np.int16)
+    out["ovo_n"] = np.array(len(kept))
+    out["ovo_bits"] = np.packbits(bmaps)
+    np.savez_compressed(os.path.join(OUT, "sam_tiny.npz"), **out)
+    print("sam_tiny.npz", {k: v.shape for k, v in out.items()}, "n", len(anns), "kept", len(kept))
+
+
 if __name__ == "__main__":
     if not rh.available():
         sys.exit("reference not available: fixtures can only be generated in the build container")
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["encoder", "assoc", "ovo", "masks", "mapper"]
+    which = sys.argv[1:] or ["encoder", "assoc", "ovo", "masks", "mapper", "sam"]
     for w in which:
         globals()["gen_" + w]()

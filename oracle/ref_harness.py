@@ -94,3 +94,57 @@ def tokenizer(context_length=32):
     setup_paths()
     import core.vision_encoder.transforms as transforms
     return transforms.get_text_tokenizer(context_length)
+
+
+def build_sam2_reference(cfg, state_dict):
+    """The reference's SAM2Base (image path) instantiated from ITS OWN yaml (sam2.1_hiera_l.yaml) with the trunk
+    geometry of `cfg` (ovo_b200.sam_config.SamConfig) and the given state_dict loaded.  hydra is absent here, so the
+    `_target_` tree is instantiated by the 12-line importer below.  The memory modules the
+    image path never calls keep their default initialisation (strict=False)."""
+    setup_paths()
+    import importlib
+    import yaml
+
+    path = os.path.join(REF_ROOT, "thirdParty/segment-anything-2/sam2/configs/sam2.1/sam2.1_hiera_l.yaml")
+    with open(path) as f:
+        y = yaml.safe_load(f)["model"]
+    tr = y["image_encoder"]["trunk"]
+    tr["embed_dim"], tr["num_heads"] = cfg.embed_dim, cfg.num_heads
+    tr["stages"], tr["global_att_blocks"] = list(cfg.stages), list(cfg.global_att_blocks)
+    tr["window_spec"] = list(cfg.window_spec)
+    y["image_encoder"]["neck"]["backbone_channel_list"] = cfg.channel_list()
+    y["image_size"] = cfg.image_size
+
+    def inst(node):
+        if isinstance(node, dict):
+            kw = {k: inst(v) for k, v in node.items() if k != "_target_"}
+            if "_target_" in node:
+                mod, name = node["_target_"].rsplit(".", 1)
+                return getattr(importlib.import_module(mod), name)(**kw)
+            return kw
+        if isinstance(node, list):
+            return [inst(v) for v in node]
+        if isinstance(node, str):
+            try:
+                return float(node) if any(c in node for c in "eE.") and node.replace(".", "").replace("e", "").replace("E", "").replace("-", "").replace("+", "").isdigit() else node
+            except ValueError:
+                return node
+        return node
+
+    model = inst(y).eval()
+    missing, unexpected = model.load_state_dict(state_dict, strict=False)
+    assert not unexpected, unexpected
+    used = ("image_encoder.", "sam_prompt_encoder.pe_layer", "sam_prompt_encoder.point_embeddings",
+            "sam_prompt_encoder.not_a_point", "sam_prompt_encoder.no_mask", "sam_mask_decoder.", "no_mem_embed")
+    bad = [k for k in missing if k.startswith(used)]
+    assert not bad, f"image-path parameters missing from the state_dict: {bad[:5]}"
+    return model
+
+
+def build_sam2_amg(model, **kw):
+    """SAM2AutomaticMaskGenerator wired as ovo/utils/segment_utils.py:296-307 does (points_per_side 16 from ovo.yaml:32)."""
+    setup_paths()
+    from sam2.automatic_mask_generator import SAM2AutomaticMaskGenerator
+    args = dict(points_per_side=16, pred_iou_thresh=0.8, stability_score_thresh=0.95, min_mask_region_area=0, use_m2m=False)
+    args.update(kw)
+    return SAM2AutomaticMaskGenerator(model=model, **args)
