@@ -253,6 +253,118 @@ int ovo_mask_nms(const uint8_t* masks_dev, const float* scores_dev, int M, int H
 int ovo_mask2segmap(const uint8_t* masks_dev, const float* stability_dev, int M, int H, int W, int32_t* seg_map_dev,
                     uint8_t* maps_out_dev, int32_t* order_dev, void* stream);
 
+
+/* ------------------------------------------------------------------------------------------------
+ * S1 — SAM-2 mask proposal (image path): thirdParty/segment-anything-2/sam2/
+ *   utils/transforms.py:15-40 (resize 1024 + normalize), modeling/backbones/hieradet.py:39-291 (Hiera trunk),
+ *   modeling/backbones/image_encoder.py:45-134 (FPN neck), modeling/sam2_base.py:467-479 (conv_s0/s1),
+ *   sam2_image_predictor.py:86-127,337-432 (set_image / _predict), modeling/sam/prompt_encoder.py:81-182,
+ *   modeling/sam/transformer.py:44-286, modeling/sam/mask_decoder.py:110-245,
+ *   automatic_mask_generator.py:170-375 + utils/amg.py (grid prompts, filters, box NMS),
+ *   and OVO's wrapper ovo/entities/mask_generator.py:102-120 (segment).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct ovo_sam ovo_sam_t;
+
+/* One Hiera block (MultiScaleBlock, hieradet.py:84-166).  Matrices bf16 [out,in] as nn.Linear stores them, vectors f32. */
+typedef struct {
+  int dim, dim_out, heads, window /* 0 = global */, q_pool /* MaxPool2d(2,2) on q + shortcut */, grid_in;
+  const float* norm1_w; const float* norm1_b;
+  const void* qkv_w;    const float* qkv_b;     /* [3*dim_out, dim] rows [q;k;v], each head-major */
+  const void* proj_w;   const float* proj_b;    /* [dim_out, dim_out] */
+  const float* norm2_w; const float* norm2_b;
+  const void* fc1_w;    const float* fc1_b;     /* [4*dim_out, dim_out] */
+  const void* fc2_w;    const float* fc2_b;     /* [dim_out, 4*dim_out] */
+  const void* short_w;  const float* short_b;   /* [dim_out, dim] shortcut projection of transition blocks, else NULL */
+} ovo_hiera_block;
+
+/* sam/transformer.py Attention: q/k/v/out projections, bf16 [out,in] + f32 bias */
+typedef struct {
+  const void* q_w; const float* q_b; const void* k_w; const float* k_b;
+  const void* v_w; const float* v_b; const void* o_w; const float* o_b;
+} ovo_sam_attn;
+
+/* TwoWayAttentionBlock (sam/transformer.py:137-212) */
+typedef struct {
+  ovo_sam_attn self_attn, t2i, i2t;
+  const float* norm_w[4]; const float* norm_b[4];
+  const void* mlp0_w; const float* mlp0_b; const void* mlp1_w; const float* mlp1_b;
+} ovo_sam_dec_layer;
+
+typedef struct {
+  int image_size;          /* 1024 */
+  int n_blocks;
+  int embed_dim;           /* 144 */
+  int stage_end[4];        /* block index closing each stage (hieradet.py:193) */
+  int decoder_depth;       /* 2 */
+  float trunk_ln_eps;      /* 1e-6 */
+} ovo_sam_cfg;
+
+typedef struct {
+  /* trunk */
+  const void* patch_w; int patch_kpad; const float* patch_b;   /* bf16 [embed, kpad]: conv 7x7 s4 p3 flattened (c,ky,kx), zero padded */
+  const float* pos;                  /* f32 [g*g, embed]: Hiera._get_pos_embed (bicubic bkg + tiled window), weights only */
+  const ovo_hiera_block* blocks;     /* host array [n_blocks] */
+  /* neck (image_encoder.py:102-134) with conv_s0/conv_s1 (sam2_base.py:467-479) folded into the two lateral convs that feed
+   * them, and no_mem_embed (sam2_image_predictor.py:118-121) folded into the bias of the 64x64 level */
+  const void* neck3_w; const float* neck3_b;   /* [256, C_stage4]  (top level, only feeds the top-down path) */
+  const void* neck2_w; const float* neck2_b;   /* [256, C_stage3]  -> image_embed */
+  const void* s1_w;    const float* s1_b;      /* [64,  C_stage2]  -> feat_s1 */
+  const void* s0_w;    const float* s0_b;      /* [32,  C_stage1]  -> feat_s0 */
+  /* prompt encoder (prompt_encoder.py) */
+  const float* gauss;          /* f32 [2,128] positional_encoding_gaussian_matrix */
+  const float* point_embed;    /* f32 [256] point_embeddings[1] (foreground point) */
+  const float* not_a_point;    /* f32 [256] */
+  const float* dense_pe;       /* f32 [64*64, 256] get_dense_pe(), weights only */
+  const float* no_mask_embed;  /* f32 [256] */
+  /* mask decoder (mask_decoder.py) */
+  const float* out_tokens;     /* f32 [6,256]: obj_score_token, iou_token, mask_tokens[0..3] */
+  const ovo_sam_dec_layer* layers;   /* host array [decoder_depth] */
+  ovo_sam_attn final_attn; const float* norm_final_w; const float* norm_final_b;
+  const void* up0_w; const float* up0_b;       /* ConvTranspose2d 256->64 k2 s2 as bf16 [(ky*2+kx)*64+o, 256]; bias tiled [256] */
+  const float* up_ln_w; const float* up_ln_b;  /* LayerNorm2d(64), eps 1e-6 */
+  const void* up1_w; const float* up1_b;       /* ConvTranspose2d 64->32 k2 s2 as bf16 [(ky*2+kx)*32+o, 64]; bias tiled [128] */
+  const void* hyper_w[4][3]; const float* hyper_b[4][3];   /* output_hypernetworks_mlps[i].layers[j] */
+  const void* iou_w[3]; const float* iou_b[3];             /* iou_prediction_head (sigmoid output) */
+} ovo_sam_weights;
+
+typedef struct {
+  int points_per_side;        /* ovo.yaml:32 -> 16 */
+  float pred_iou_thresh;      /* segment_utils.py:298 <- sam.nms_iou_th (0.8) */
+  float stability_thresh;     /* :299 <- sam.stability_score_th (0.95) */
+  float stability_offset;     /* 1.0 (automatic_mask_generator.py:44) */
+  float box_nms_thresh;       /* 0.7 (:46) */
+  float nms_iou_th, nms_score_th, nms_inner_th;   /* OVO's second NMS, mask_generator.py:25-27 (0.8, 0.7, 0.5) */
+} ovo_amg_params;
+
+int ovo_sam_create(const ovo_sam_cfg* cfg, const ovo_sam_weights* w, int max_h, int max_w, int max_prompts, ovo_sam_t** out);
+void ovo_sam_destroy(ovo_sam_t* sam);
+/* SAM2ImagePredictor.set_image: rgb uint8 [H,W,3] -> image embedding + high-res features kept inside the handle.
+ * Optional taps (may be NULL): pixels f32 [3,S,S]; embed f32 [g*g,256] (token major); feat_s0 f32 [16*g*g,32];
+ * feat_s1 f32 [4*g*g,64], g = image_size/16.  n_blocks < 0 = all; block_out (optional) receives the f32 token grid
+ * [grid^2, dim] after the last executed block (layer-by-layer parity tests). */
+int ovo_sam_set_image(ovo_sam_t* sam, const uint8_t* rgb_dev, int H, int W, float* pixels_out_dev, float* embed_out_dev,
+                      float* feat_s0_out_dev, float* feat_s1_out_dev, int n_blocks, float* block_out_dev, void* stream);
+/* Test tap: run the trunk from already normalised pixels f32 [3,S,S] instead of the resize. */
+int ovo_sam_set_pixels(ovo_sam_t* sam, const float* pixels_dev, float* embed_out_dev, float* feat_s0_out_dev,
+                       float* feat_s1_out_dev, int n_blocks, float* block_out_dev, void* stream);
+/* SAM2ImagePredictor._predict, one foreground point per prompt, multimask_output=True: points f32 [P,2] in model-frame
+ * pixels (transforms.py:59-65) -> low_res f32 [P,3,4g,4g] mask logits (not clamped), iou f32 [P,3]. */
+int ovo_sam_predict(ovo_sam_t* sam, const float* points_dev, int P, float* low_res_out_dev, float* iou_out_dev, void* stream);
+/* SAM2AutomaticMaskGenerator._process_batch/_process_crop filters for the whole-image crop
+ * (automatic_mask_generator.py:251-375) on given logits: bilinear up-sampling to HxW (transforms.py:117), predicted-IoU
+ * filter, stability score (utils/amg.py:158-178), threshold, boxes (:305-348), box NMS (torchvision batched_nms).
+ *   low_res f32 [P,3,h,w], iou f32 [P,3]  ->  masks_out uint8 [K,H,W] (0/1) in the reference's order (descending predicted
+ *   IoU), iou_out/stab_out f32 [K], boxes_out i32 [K,4] XYXY, src_out i32 [K] = index into the flattened [P*3] list.
+ * Synchronises `stream` once; returns K in *n_out (K <= max_out, else OVO_E_INVALID). */
+int ovo_sam_postprocess(ovo_sam_t* sam, const float* low_res_dev, const float* iou_dev, int P, int h, int w, int H, int W,
+                        const ovo_amg_params* prm, uint8_t* masks_out_dev, float* iou_out_dev, float* stab_out_dev,
+                        int32_t* boxes_out_dev, int32_t* src_out_dev, int max_out, int* n_out, void* stream);
+/* MaskGenerator.segment (ovo/entities/mask_generator.py:102-120) end to end: set_image, grid prompts, decoder, AMG filters,
+ * OVO's masks_update (segment_utils.py:173-259) and mask2segmap (:12-27).
+ *   -> seg_map i32 [H,W] (-1 = none), masks_out uint8 [M,H,W] in painted order, M in *n_masks (M <= max_masks). */
+int ovo_sam_generate(ovo_sam_t* sam, const uint8_t* rgb_dev, int H, int W, const ovo_amg_params* prm, int32_t* seg_map_dev,
+                     uint8_t* masks_out_dev, int max_masks, int* n_masks, void* stream);
+
 /* OVO.classify_instances (ovo.py:486-491): argmax over queries + threshold. sim f32 [n,Q] ->
  * cls i32 [n] (-1 if max <= th), conf f32 [n] (0 if max <= th). */
 int ovo_classify(const float* sim_dev, int64_t n, int Q, float th, int32_t* cls_dev, float* conf_dev, void* stream);

@@ -303,6 +303,36 @@ def mask_boxes(masks: np.ndarray) -> np.ndarray:
     return out
 
 
+def upsample_bilinear(low: np.ndarray, H: int, W: int) -> np.ndarray:
+    """F.interpolate(mode="bilinear", align_corners=False) (utils/transforms.py:117) restated with a fixed f32 operation
+    order (ATen upsample_bilinear2d: src = scale*(dst+0.5)-0.5 clamped at 0, i0 = int(src), lambda = src - i0,
+    out = (1-ly)*((1-lx)*a + lx*b) + ly*((1-lx)*c + lx*d)); ATen's own CPU kernel may contract some of these into FMAs, so the
+    two can differ in the last bit — the thresholded masks are pinned to the reference within a few pixels instead."""
+    f = np.float32
+    h, w = low.shape[-2:]
+
+    def axis(n_out, n_in):
+        scale = f(n_in) / f(n_out)
+        src = (scale * (np.arange(n_out, dtype=f) + f(0.5))).astype(f) - f(0.5)
+        src = np.maximum(src, f(0)).astype(f)
+        i0 = np.minimum(src.astype(np.int64), n_in - 1)
+        i1 = i0 + (i0 < n_in - 1)
+        lam = (src - i0.astype(f)).astype(f)
+        return i0, i1, lam, (f(1) - lam).astype(f)
+
+    y0, y1, ly, hy = axis(H, h)
+    x0, x1, lx, hx = axis(W, w)
+    low = low.astype(f, copy=False)
+    out = np.empty(low.shape[:-2] + (H, W), f)
+    flat, oflat = low.reshape(-1, h, w), out.reshape(-1, H, W)
+    for i in range(flat.shape[0]):
+        m = flat[i]
+        top = (hx * m[y0][:, x0]).astype(f) + (lx * m[y0][:, x1]).astype(f)
+        bot = (hx * m[y1][:, x0]).astype(f) + (lx * m[y1][:, x1]).astype(f)
+        oflat[i] = (hy[:, None] * top).astype(f) + (ly[:, None] * bot).astype(f)
+    return out
+
+
 def amg_postprocess(low_res, iou, H, W, pred_iou_thresh=0.8, stability_thresh=0.95, offset=1.0, box_nms_thresh=0.7):
     """SAM2AutomaticMaskGenerator._process_batch/_process_crop for a single full-image crop
     (automatic_mask_generator.py:251-292, 294-375) applied to ALL prompts at once (the per-64-prompt batching of the
@@ -310,11 +340,12 @@ def amg_postprocess(low_res, iou, H, W, pred_iou_thresh=0.8, stability_thresh=0.
     -> dict(masks bool [K,H,W], iou [K], stability [K], boxes [K,4], src [K] = index into the flattened P*3 list),
     in the order the reference returns them (descending predicted IoU after box NMS)."""
     P = low_res.shape[0]
-    masks = F.interpolate(low_res.float(), (H, W), mode="bilinear", align_corners=False).flatten(0, 1)   # transforms.py:117
     iou = iou.flatten().float()
     src = torch.arange(P * 3)
     keep = iou > pred_iou_thresh
-    masks, iou, src = masks[keep], iou[keep], src[keep]
+    iou, src = iou[keep], src[keep]
+    # (the reference up-samples every mask before the IoU filter; per-mask results are the same)
+    masks = torch.from_numpy(upsample_bilinear(low_res.float().flatten(0, 1)[keep].numpy(), H, W))
     inter = (masks > offset).flatten(1).sum(1).to(torch.int32)
     union = (masks > -offset).flatten(1).sum(1).to(torch.int32)
     stab = inter / union

@@ -41,6 +41,45 @@ class Frame(C.Structure):
                 ("ratio_h", c_float), ("ratio_w", c_float), ("crop_edge", c_int)]
 
 
+class HieraBlock(C.Structure):
+    _fields_ = [(n, c_int) for n in ("dim", "dim_out", "heads", "window", "q_pool", "grid_in")] + \
+               [(n, c_void_p) for n in ("norm1_w", "norm1_b", "qkv_w", "qkv_b", "proj_w", "proj_b", "norm2_w", "norm2_b",
+                                        "fc1_w", "fc1_b", "fc2_w", "fc2_b", "short_w", "short_b")]
+
+
+class SamAttn(C.Structure):
+    _fields_ = [(n, c_void_p) for n in ("q_w", "q_b", "k_w", "k_b", "v_w", "v_b", "o_w", "o_b")]
+
+
+class SamDecLayer(C.Structure):
+    _fields_ = [("self_attn", SamAttn), ("t2i", SamAttn), ("i2t", SamAttn), ("norm_w", c_void_p * 4), ("norm_b", c_void_p * 4),
+                ("mlp0_w", c_void_p), ("mlp0_b", c_void_p), ("mlp1_w", c_void_p), ("mlp1_b", c_void_p)]
+
+
+class SamCfg(C.Structure):
+    _fields_ = [("image_size", c_int), ("n_blocks", c_int), ("embed_dim", c_int), ("stage_end", c_int * 4),
+                ("decoder_depth", c_int), ("trunk_ln_eps", c_float)]
+
+
+class SamWeights(C.Structure):
+    _fields_ = [("patch_w", c_void_p), ("patch_kpad", c_int), ("patch_b", c_void_p), ("pos", c_void_p),
+                ("blocks", C.POINTER(HieraBlock)),
+                ("neck3_w", c_void_p), ("neck3_b", c_void_p), ("neck2_w", c_void_p), ("neck2_b", c_void_p),
+                ("s1_w", c_void_p), ("s1_b", c_void_p), ("s0_w", c_void_p), ("s0_b", c_void_p),
+                ("gauss", c_void_p), ("point_embed", c_void_p), ("not_a_point", c_void_p), ("dense_pe", c_void_p),
+                ("no_mask_embed", c_void_p), ("out_tokens", c_void_p), ("layers", C.POINTER(SamDecLayer)),
+                ("final_attn", SamAttn), ("norm_final_w", c_void_p), ("norm_final_b", c_void_p),
+                ("up0_w", c_void_p), ("up0_b", c_void_p), ("up_ln_w", c_void_p), ("up_ln_b", c_void_p),
+                ("up1_w", c_void_p), ("up1_b", c_void_p),
+                ("hyper_w", (c_void_p * 3) * 4), ("hyper_b", (c_void_p * 3) * 4), ("iou_w", c_void_p * 3), ("iou_b", c_void_p * 3)]
+
+
+class AmgParams(C.Structure):
+    _fields_ = [("points_per_side", c_int), ("pred_iou_thresh", c_float), ("stability_thresh", c_float),
+                ("stability_offset", c_float), ("box_nms_thresh", c_float), ("nms_iou_th", c_float),
+                ("nms_score_th", c_float), ("nms_inner_th", c_float)]
+
+
 # name -> (restype, argtypes); mirrors include/ovo_b200.h one to one
 SIGNATURES = {
     "ovo_last_error": (C.c_char_p, []),
@@ -79,6 +118,15 @@ SIGNATURES = {
                                   C.POINTER(c_int), c_void_p]),
     "ovo_mask_nms": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_float, c_float, c_void_p, c_void_p]),
     "ovo_mask2segmap": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "ovo_sam_create": (c_int, [C.POINTER(SamCfg), C.POINTER(SamWeights), c_int, c_int, c_int, C.POINTER(c_void_p)]),
+    "ovo_sam_destroy": (None, [c_void_p]),
+    "ovo_sam_set_image": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "ovo_sam_set_pixels": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "ovo_sam_predict": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "ovo_sam_postprocess": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, C.POINTER(AmgParams), c_void_p,
+                                    c_void_p, c_void_p, c_void_p, c_void_p, c_int, C.POINTER(c_int), c_void_p]),
+    "ovo_sam_generate": (c_int, [c_void_p, c_void_p, c_int, c_int, C.POINTER(AmgParams), c_void_p, c_void_p, c_int, C.POINTER(c_int),
+                                 c_void_p]),
     "ovo_classify": (c_int, [c_void_p, c_int64, c_int, c_float, c_void_p, c_void_p, c_void_p]),
     "ovo_profile_begin": (None, []),
     "ovo_profile_report": (c_int, [c_int, C.POINTER(c_float), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(c_int)]),

@@ -20,6 +20,7 @@ enum EpiKind : int {
   EPI_F32_RESID = 3,  // out_f32 = acc + bias + resid            (pe.py:221-224)
   EPI_QKV = 4,        // split q/k/v, 2D-RoPE on q,k, v written transposed (pe.py:125-143, rope.py:40-62)
   EPI_PATCH = 5,      // out_f32[token row] = acc + pos_emb      (pe.py:509-519)
+  EPI_BF16_RELU = 6,  // out_bf16 = relu(acc + bias)            (SAM-2 two-way transformer MLP, sam/transformer.py:161-163)
 };
 
 struct EpiParams {
@@ -28,6 +29,9 @@ struct EpiParams {
   const float* bias = nullptr;
   const float* resid = nullptr;
   int ldr = 0;
+  int resid_mod = 0;           // > 0: the residual row is (row % resid_mod) — one [resid_mod, N] table shared by every batch
+                               // item (SAM-2 mask decoder: image embedding / high-res features broadcast over the prompts).
+                               // EPI_F32_RESID adds it after the bias; EPI_BF16_GELU adds it BEFORE the GELU when resid != nullptr
   // EPI_QKV
   __nv_bfloat16* q = nullptr;
   __nv_bfloat16* k = nullptr;
@@ -90,7 +94,7 @@ __device__ __forceinline__ void epilogue_store(const EpiParams& ep, int row, int
   if constexpr (EPI == EPI_F32 || EPI == EPI_F32_RESID) {
     float* out = static_cast<float*>(ep.out) + static_cast<size_t>(row) * ep.ldo + col;
     if constexpr (EPI == EPI_F32_RESID) {
-      const float* r = ep.resid + static_cast<size_t>(row) * ep.ldr + col;
+      const float* r = ep.resid + static_cast<size_t>(ep.resid_mod > 0 ? row % ep.resid_mod : row) * ep.ldr + col;
       if (ncol == 32 && (ep.ldr & 3) == 0) {
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
@@ -108,10 +112,18 @@ __device__ __forceinline__ void epilogue_store(const EpiParams& ep, int row, int
     } else {
       for (int j = 0; j < ncol; ++j) out[j] = acc[j];
     }
-  } else if constexpr (EPI == EPI_BF16 || EPI == EPI_BF16_GELU) {
+  } else if constexpr (EPI == EPI_BF16 || EPI == EPI_BF16_GELU || EPI == EPI_BF16_RELU) {
     if constexpr (EPI == EPI_BF16_GELU) {
+      if (ep.resid != nullptr) {
+        const float* r = ep.resid + static_cast<size_t>(ep.resid_mod > 0 ? row % ep.resid_mod : row) * ep.ldr + col;
+        for (int j = 0; j < ncol; ++j) acc[j] += r[j];
+      }
 #pragma unroll
       for (int j = 0; j < 32; ++j) acc[j] = gelu_erf(acc[j]);
+    }
+    if constexpr (EPI == EPI_BF16_RELU) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) acc[j] = fmaxf(acc[j], 0.f);
     }
     __nv_bfloat16* out = static_cast<__nv_bfloat16*>(ep.out) + static_cast<size_t>(row) * ep.ldo + col;
     if (ncol == 32 && (ep.ldo & 7) == 0) {
@@ -202,7 +214,8 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& ep, int row0, in
   if constexpr (EPI == EPI_F32 || EPI == EPI_F32_RESID)
     fast = fast && (ep.ldo & 3) == 0 && (reinterpret_cast<uintptr_t>(ep.out) & 15) == 0 &&
            (EPI != EPI_F32_RESID || ((ep.ldr & 3) == 0 && (reinterpret_cast<uintptr_t>(ep.resid) & 15) == 0));
-  if constexpr (EPI == EPI_BF16 || EPI == EPI_BF16_GELU) fast = fast && (ep.ldo & 7) == 0 && (reinterpret_cast<uintptr_t>(ep.out) & 15) == 0;
+  if constexpr (EPI == EPI_BF16 || EPI == EPI_BF16_GELU || EPI == EPI_BF16_RELU) fast = fast && (ep.ldo & 7) == 0 && (reinterpret_cast<uintptr_t>(ep.out) & 15) == 0;
+  if constexpr (EPI == EPI_BF16_GELU) fast = fast && (ep.resid == nullptr || ((ep.ldr & 3) == 0 && (reinterpret_cast<uintptr_t>(ep.resid) & 15) == 0));
   if constexpr (EPI == EPI_PATCH) fast = fast && (ep.ldo & 3) == 0 && (reinterpret_cast<uintptr_t>(ep.out) & 15) == 0 && (reinterpret_cast<uintptr_t>(ep.pos) & 15) == 0;
   if (!fast) {  // ragged N / unaligned output (e.g. the [N_points, 20] query result): per-thread row stores
     epilogue_store<EPI>(ep, row0 + lane, col, v, M, N, s_rope);
@@ -257,18 +270,31 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& ep, int row0, in
         const int c = col + 16 * h + 4 * sub;
         float4 val = make_float4(__uint_as_float(o[i].x), __uint_as_float(o[i].y), __uint_as_float(o[i].z), __uint_as_float(o[i].w));
         if constexpr (EPI == EPI_F32_RESID) {
-          const float4 rr = *reinterpret_cast<const float4*>(ep.resid + static_cast<size_t>(r) * ep.ldr + c);
+          const float4 rr = *reinterpret_cast<const float4*>(ep.resid + static_cast<size_t>(ep.resid_mod > 0 ? r % ep.resid_mod : r) * ep.ldr + c);
           val.x += rr.x; val.y += rr.y; val.z += rr.z; val.w += rr.w;
         }
         *reinterpret_cast<float4*>(static_cast<float*>(ep.out) + static_cast<size_t>(r) * ep.ldo + c) = val;
       }
     }
-  } else if constexpr (EPI == EPI_BF16 || EPI == EPI_BF16_GELU) {
+  } else if constexpr (EPI == EPI_BF16 || EPI == EPI_BF16_GELU || EPI == EPI_BF16_RELU) {
     if constexpr (EPI == EPI_BF16_GELU) {
+      if (ep.resid != nullptr && row0 + lane < M) {   // lane = row: 128 contiguous bytes of its residual row
+        const int rr = row0 + lane;
+        const float4* r4 = reinterpret_cast<const float4*>(ep.resid + static_cast<size_t>(ep.resid_mod > 0 ? rr % ep.resid_mod : rr) * ep.ldr + col);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 t = __ldg(r4 + j);
+          acc[4 * j] += t.x; acc[4 * j + 1] += t.y; acc[4 * j + 2] += t.z; acc[4 * j + 3] += t.w;
+        }
+      }
       if (!(ep.debug & 8)) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) acc[j] = gelu_erf(acc[j]);
       }
+    }
+    if constexpr (EPI == EPI_BF16_RELU) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) acc[j] = fmaxf(acc[j], 0.f);
     }
     uint32_t in[16];
 #pragma unroll

@@ -1,0 +1,1157 @@
+// SAM-2 mask proposal, image path behind the C ABI of include/ovo_b200.h.
+// Reference: thirdParty/segment-anything-2/sam2/ — utils/transforms.py, modeling/backbones/{hieradet,image_encoder,utils}.py,
+// modeling/sam2_base.py:467-479, sam2_image_predictor.py, modeling/sam/{prompt_encoder,transformer,mask_decoder}.py,
+// automatic_mask_generator.py, utils/amg.py; and ovo/entities/mask_generator.py:102-120.
+//
+// Every linear layer / 1x1 conv / transposed conv runs on the tcgen05 GEMM of gemm.cuh; attention inside the Hiera
+// windows runs on sam_attention.cuh; the decoder's tiny attentions (8 tokens, head_dim 16/32) and the mask
+// post-processing are plain CUDA-core kernels (HBM / latency bound).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+#include "gemm.cuh"
+#include "sam_attention.cuh"
+
+namespace ovo {
+namespace {
+
+constexpr int kC = 256;        // d_model of neck / prompt encoder / mask decoder (sam2_base.py:207-243)
+constexpr int kTok = 8;        // obj_score + iou + 4 mask tokens + point + padding point (mask_decoder.py:186-204)
+constexpr int kInt = 128;      // internal dim of the cross attentions (attention_downsample_rate 2)
+
+// ------------------------------------------------------------------------------------------- small kernels
+// LayerNorm over rows of `width` (any multiple of 4 up to 2048), optional row-modulo additive table written as a second
+// bf16 output: out16 = bf16(y), out16b = bf16(y + add[row % add_mod]).
+__global__ void __launch_bounds__(256)
+    sam_ln_kernel(const float* __restrict__ x, int rows, int width, const float* __restrict__ g, const float* __restrict__ b,
+                  float eps, float* __restrict__ out32, __nv_bfloat16* __restrict__ out16, __nv_bfloat16* __restrict__ out16b,
+                  const float* __restrict__ add, int add_mod) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * width);
+  const int nvec = width >> 2;
+  float4 v[16];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int idx = lane + 32 * i;
+    if (idx < nvec) { v[i] = xr[idx]; sum += v[i].x + v[i].y + v[i].z + v[i].w; }
+  }
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum / width;
+  float var = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int idx = lane + 32 * i;
+    if (idx < nvec) {
+      const float a = v[i].x - mean, bb = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      var += a * a + bb * bb + c * c + d * d;
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+  const float rstd = rsqrtf(var / width + eps);
+  const float4* ar = add ? reinterpret_cast<const float4*>(add + static_cast<size_t>(row % add_mod) * width) : nullptr;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int idx = lane + 32 * i;
+    if (idx < nvec) {
+      const float4 gg = __ldg(reinterpret_cast<const float4*>(g) + idx);
+      const float4 bb = __ldg(reinterpret_cast<const float4*>(b) + idx);
+      float4 o;
+      o.x = (v[i].x - mean) * rstd * gg.x + bb.x; o.y = (v[i].y - mean) * rstd * gg.y + bb.y;
+      o.z = (v[i].z - mean) * rstd * gg.z + bb.z; o.w = (v[i].w - mean) * rstd * gg.w + bb.w;
+      if (out32) reinterpret_cast<float4*>(out32 + static_cast<size_t>(row) * width)[idx] = o;
+      if (out16) reinterpret_cast<uint2*>(out16 + static_cast<size_t>(row) * width)[idx] = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
+      if (out16b) {
+        const float4 a = __ldg(ar + idx);
+        reinterpret_cast<uint2*>(out16b + static_cast<size_t>(row) * width)[idx] = make_uint2(pack_bf16(o.x + a.x, o.y + a.y), pack_bf16(o.z + a.z, o.w + a.w));
+      }
+    }
+  }
+}
+
+// out16[i] = bf16(a[i] + b[(i / width % b_mod) * width + i % width])   (b optional): f32 -> bf16 GEMM operands
+__global__ void add_cast_kernel(const float* __restrict__ a, const float* __restrict__ b, int b_mod, int width, size_t n4,
+                                __nv_bfloat16* __restrict__ out16, float* __restrict__ out32) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  float4 v = reinterpret_cast<const float4*>(a)[i];
+  if (b) {
+    const size_t e = i * 4;
+    const size_t row = e / width, col = e - row * width;
+    const float4 w = *reinterpret_cast<const float4*>(b + (row % b_mod) * width + col);
+    v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+  }
+  if (out16) reinterpret_cast<uint2*>(out16)[i] = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+  if (out32) reinterpret_cast<float4*>(out32)[i] = v;
+}
+
+// ---- image transform (utils/transforms.py:15-40): ToTensor, Resize (bilinear, antialias), Normalize
+__global__ void sam_resize_h_kernel(const uint8_t* __restrict__ rgb, int H, int W, const int* __restrict__ xmin,
+                                    const int* __restrict__ xsize, const float* __restrict__ xw, int kx, int S,
+                                    float* __restrict__ tmp) {
+  const int ox = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (ox >= S) return;
+  const int x0 = xmin[ox], n = xsize[ox];
+  const float* w = xw + static_cast<size_t>(ox) * kx;
+  const uint8_t* src = rgb + (static_cast<size_t>(y) * W + x0) * 3;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+  for (int k = 0; k < n; ++k) {
+    const float wk = w[k];
+    a0 += wk * (static_cast<float>(src[3 * k]) / 255.f);
+    a1 += wk * (static_cast<float>(src[3 * k + 1]) / 255.f);
+    a2 += wk * (static_cast<float>(src[3 * k + 2]) / 255.f);
+  }
+  float* dst = tmp + static_cast<size_t>(y) * S + ox;
+  dst[0] = a0; dst[static_cast<size_t>(H) * S] = a1; dst[static_cast<size_t>(2) * H * S] = a2;
+}
+__global__ void sam_resize_v_kernel(const float* __restrict__ tmp, int H, const int* __restrict__ ymin,
+                                    const int* __restrict__ ysize, const float* __restrict__ yw, int ky, int S,
+                                    float* __restrict__ px) {
+  const int ox = blockIdx.x * blockDim.x + threadIdx.x, oy = blockIdx.y, c = blockIdx.z;
+  if (ox >= S) return;
+  const int y0 = ymin[oy], n = ysize[oy];
+  const float* w = yw + static_cast<size_t>(oy) * ky;
+  const float* src = tmp + (static_cast<size_t>(c) * H + y0) * S + ox;
+  float a = 0.f;
+  for (int k = 0; k < n; ++k) a += w[k] * src[static_cast<size_t>(k) * S];
+  const float mean = c == 0 ? 0.485f : (c == 1 ? 0.456f : 0.406f);
+  const float sd = c == 0 ? 0.229f : (c == 1 ? 0.224f : 0.225f);
+  px[(static_cast<size_t>(c) * S + oy) * S + ox] = (a - mean) / sd;
+}
+// PatchEmbed conv 7x7 stride 4 pad 3 (backbones/utils.py:65-95) as im2col rows [g*g, kpad] bf16, column = c*49 + ky*7 + kx
+__global__ void sam_im2col_kernel(const float* __restrict__ px, int S, int g, int kpad, __nv_bfloat16* __restrict__ out) {
+  const int t = blockIdx.x;
+  const int ty = t / g, tx = t - ty * g;
+  for (int j = threadIdx.x; j < kpad; j += blockDim.x) {
+    float v = 0.f;
+    if (j < 147) {
+      const int c = j / 49, r = j - c * 49, ky = r / 7, kx = r - ky * 7;
+      const int y = 4 * ty - 3 + ky, x = 4 * tx - 3 + kx;
+      if (y >= 0 && y < S && x >= 0 && x < S) v = px[(static_cast<size_t>(c) * S + y) * S + x];
+    }
+    out[static_cast<size_t>(t) * kpad + j] = __float2bfloat16_rn(v);
+  }
+}
+// MaxPool2d(2,2) on a [g,g,C] f32 token grid -> [g/2,g/2,C]  (hieradet.py:25-37, the shortcut of a transition block)
+__global__ void sam_maxpool_kernel(const float* __restrict__ in, int g, int C, float* __restrict__ out) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int c4 = C >> 2, go = g >> 1;
+  if (i >= static_cast<size_t>(go) * go * c4) return;
+  const int c = i % c4;
+  const size_t t = i / c4;
+  const int y = t / go, x = t - static_cast<size_t>(y) * go;
+  const float4* p = reinterpret_cast<const float4*>(in);
+  const size_t r0 = (static_cast<size_t>(2 * y) * g + 2 * x) * c4 + c;
+  const float4 a = p[r0], b = p[r0 + c4], d = p[r0 + static_cast<size_t>(g) * c4], e = p[r0 + static_cast<size_t>(g) * c4 + c4];
+  reinterpret_cast<float4*>(out)[i] = make_float4(fmaxf(fmaxf(a.x, b.x), fmaxf(d.x, e.x)), fmaxf(fmaxf(a.y, b.y), fmaxf(d.y, e.y)),
+                                                  fmaxf(fmaxf(a.z, b.z), fmaxf(d.z, e.z)), fmaxf(fmaxf(a.w, b.w), fmaxf(d.w, e.w)));
+}
+// FPN top-down (image_encoder.py:117-128, nearest x2) + decoder-side constants:
+//   embed = lat2 + up(lat3)   (no_mem_embed is already in lat2's bias);  src = embed + no_mask_embed
+//   src_bf = bf16(src), srcpe_bf = bf16(src + dense_pe)
+__global__ void sam_embed_kernel(const float* __restrict__ lat2, const float* __restrict__ lat3, int g, const float* __restrict__ no_mask,
+                                 const float* __restrict__ dense_pe, float* __restrict__ embed, float* __restrict__ src,
+                                 __nv_bfloat16* __restrict__ src_bf, __nv_bfloat16* __restrict__ srcpe_bf) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= g * g * kC) return;
+  const int c = i % kC, t = i / kC, y = t / g, x = t - y * g;
+  const float e = lat2[i] + lat3[((y >> 1) * (g >> 1) + (x >> 1)) * kC + c];
+  embed[i] = e;
+  const float s = e + no_mask[c];
+  src[i] = s;
+  src_bf[i] = __float2bfloat16_rn(s);
+  srcpe_bf[i] = __float2bfloat16_rn(s + dense_pe[i]);
+}
+// feature map [2g,2g,C] -> [g*g, (ky*2+kx)*C + c]: the layout in which a k2 s2 transposed conv (a GEMM with N = 4*C_out)
+// meets its high-resolution skip feature (mask_decoder.py:214-217)
+__global__ void sam_subpixel_kernel(const float* __restrict__ in, int g, int C, float* __restrict__ out) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<size_t>(g) * g * 4 * C) return;
+  const int c = i % C, sub = (i / C) & 3;
+  const size_t t = i / (4 * C);
+  const int y = t / g, x = t - static_cast<size_t>(y) * g;
+  out[i] = in[((static_cast<size_t>(2 * y + (sub >> 1)) * 2 * g) + 2 * x + (sub & 1)) * C + c];
+}
+
+// feat_s0 [4g,4g,32] in the order the SECOND transposed conv's GEMM rows come in: up1 pixels are stored as
+// (y, x, sub1) over the g x g grid, so row = (y*g + x)*4 + sub1 is up1 pixel (2y+ky1, 2x+kx1) and column
+// sub2*32 + c is final pixel (2Y+ky2, 2X+kx2).
+__global__ void sam_subpixel2_kernel(const float* __restrict__ in, int g, float* __restrict__ out) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<size_t>(g) * g * 16 * 32) return;
+  const int c = i & 31, sub2 = (i >> 5) & 3, sub1 = (i >> 7) & 3;
+  const size_t t = i >> 9;
+  const int y = t / g, x = t - static_cast<size_t>(y) * g;
+  const int Y = 2 * (2 * y + (sub1 >> 1)) + (sub2 >> 1), X = 2 * (2 * x + (sub1 & 1)) + (sub2 & 1);
+  out[i] = in[(static_cast<size_t>(Y) * 4 * g + X) * 32 + c];
+}
+
+// ---- prompt encoder (prompt_encoder.py:81-104, position_encoding.py:129-158): tokens [P,8,256] =
+// [out_tokens(6); pe(point + 0.5) + point_embeddings[1]; not_a_point_embed]
+__global__ void sam_tokens_kernel(const float* __restrict__ pts, int P, float image_size, const float* __restrict__ gauss,
+                                  const float* __restrict__ point_embed, const float* __restrict__ not_a_point,
+                                  const float* __restrict__ out_tokens, float* __restrict__ tokens) {
+  const int p = blockIdx.x, c = threadIdx.x;   // 256 threads
+  float* t = tokens + static_cast<size_t>(p) * kTok * kC;
+#pragma unroll
+  for (int j = 0; j < 6; ++j) t[j * kC + c] = out_tokens[j * kC + c];
+  const float x = (pts[2 * p] + 0.5f) / image_size, y = (pts[2 * p + 1] + 0.5f) / image_size;
+  const int f = c & 127;
+  float v = (2.f * x - 1.f) * gauss[f] + (2.f * y - 1.f) * gauss[128 + f];
+  v = 2.f * 3.14159265358979323846f * v;
+  t[6 * kC + c] = (c < 128 ? sinf(v) : cosf(v)) + point_embed[c];
+  t[7 * kC + c] = not_a_point[c];
+}
+
+// ---- decoder attentions (sam/transformer.py:255-286); all operands bf16, f32 math
+// token self-attention: 8 tokens, 8 heads of 32.  q,k,v [P*8, 256] -> out [P*8, 256].  One CTA (256 threads) per prompt.
+__global__ void __launch_bounds__(256) sam_self_attn_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k,
+                                                            const __nv_bfloat16* __restrict__ v, __nv_bfloat16* __restrict__ out) {
+  __shared__ float sq[kTok][kC], sk[kTok][kC], sv[kTok][kC];
+  __shared__ float sp[8][kTok][kTok];
+  const size_t base = static_cast<size_t>(blockIdx.x) * kTok * kC;
+  for (int i = threadIdx.x; i < kTok * kC; i += 256) {
+    sq[0][i] = __bfloat162float(q[base + i]); sk[0][i] = __bfloat162float(k[base + i]); sv[0][i] = __bfloat162float(v[base + i]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 8 * kTok * kTok; i += 256) {
+    const int h = i >> 6, a = (i >> 3) & 7, b = i & 7;
+    float s = 0.f;
+#pragma unroll
+    for (int d = 0; d < 32; ++d) s += sq[a][h * 32 + d] * sk[b][h * 32 + d];
+    sp[h][a][b] = s * 0.17677669529663687f;   // 32^-0.5
+  }
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    const int h = threadIdx.x >> 3, a = threadIdx.x & 7;
+    float m = -INFINITY;
+    for (int b = 0; b < kTok; ++b) m = fmaxf(m, sp[h][a][b]);
+    float l = 0.f;
+    for (int b = 0; b < kTok; ++b) { const float e = expf(sp[h][a][b] - m); sp[h][a][b] = e; l += e; }
+    for (int b = 0; b < kTok; ++b) sp[h][a][b] /= l;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kTok * kC; i += 256) {
+    const int a = i >> 8, c = i & 255, h = c >> 5;
+    float acc = 0.f;
+#pragma unroll
+    for (int b = 0; b < kTok; ++b) acc += sp[h][a][b] * sv[b][c];
+    out[base + i] = __float2bfloat16_rn(acc);
+  }
+}
+
+// token -> image cross attention: 8 queries x n_keys keys, 8 heads of 16.  q [P*8,128]; k,v [kv_batch * n_keys, 128]
+// (kv_stride = 0: the same keys for every prompt, layer 0).  One CTA per (prompt, head); 256 threads stripe the keys,
+// each keeps an online-softmax state per query; states merge through shared memory.
+__global__ void __launch_bounds__(256) sam_t2i_attn_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k,
+                                                           const __nv_bfloat16* __restrict__ v, size_t kv_stride, int n_keys,
+                                                           __nv_bfloat16* __restrict__ out) {
+  const int p = blockIdx.x, h = blockIdx.y, tid = threadIdx.x;
+  __shared__ float sq[kTok][16];
+  __shared__ float red_m[8][kTok], red_l[8][kTok], red_o[8][kTok][16];
+  if (tid < kTok * 16) sq[tid >> 4][tid & 15] = __bfloat162float(q[(static_cast<size_t>(p) * kTok + (tid >> 4)) * kInt + h * 16 + (tid & 15)]) * 0.25f;
+  __syncthreads();
+  float m[kTok], l[kTok], o[kTok][16];
+#pragma unroll
+  for (int a = 0; a < kTok; ++a) {
+    m[a] = -INFINITY; l[a] = 0.f;
+#pragma unroll
+    for (int d = 0; d < 16; ++d) o[a][d] = 0.f;
+  }
+  const __nv_bfloat16* kb = k + static_cast<size_t>(p) * kv_stride + h * 16;
+  const __nv_bfloat16* vb = v + static_cast<size_t>(p) * kv_stride + h * 16;
+  for (int j = tid; j < n_keys; j += 256) {
+    float kf[16], vf[16];
+    {
+      const uint4* kp = reinterpret_cast<const uint4*>(kb + static_cast<size_t>(j) * kInt);
+      const uint4* vp = reinterpret_cast<const uint4*>(vb + static_cast<size_t>(j) * kInt);
+      uint4 t[2] = {kp[0], kp[1]}, u[2] = {vp[0], vp[1]};
+      const __nv_bfloat16* tk = reinterpret_cast<const __nv_bfloat16*>(t);
+      const __nv_bfloat16* tv = reinterpret_cast<const __nv_bfloat16*>(u);
+#pragma unroll
+      for (int d = 0; d < 16; ++d) { kf[d] = __bfloat162float(tk[d]); vf[d] = __bfloat162float(tv[d]); }
+    }
+#pragma unroll
+    for (int a = 0; a < kTok; ++a) {
+      float s = 0.f;
+#pragma unroll
+      for (int d = 0; d < 16; ++d) s += sq[a][d] * kf[d];
+      const float nm = fmaxf(m[a], s);
+      const float c = __expf(m[a] - nm), e = __expf(s - nm);
+      m[a] = nm; l[a] = l[a] * c + e;
+#pragma unroll
+      for (int d = 0; d < 16; ++d) o[a][d] = o[a][d] * c + e * vf[d];
+    }
+  }
+  // merge the 32 lanes of each warp, then the 8 warps
+  const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+  for (int a = 0; a < kTok; ++a) {
+    float wm = m[a];
+    for (int s = 16; s > 0; s >>= 1) wm = fmaxf(wm, __shfl_xor_sync(0xffffffffu, wm, s));
+    const float c = (m[a] == -INFINITY) ? 0.f : __expf(m[a] - wm);
+    float wl = l[a] * c;
+    for (int s = 16; s > 0; s >>= 1) wl += __shfl_xor_sync(0xffffffffu, wl, s);
+#pragma unroll
+    for (int d = 0; d < 16; ++d) {
+      float x = o[a][d] * c;
+      for (int s = 16; s > 0; s >>= 1) x += __shfl_xor_sync(0xffffffffu, x, s);
+      if (lane == 0) red_o[warp][a][d] = x;
+    }
+    if (lane == 0) { red_m[warp][a] = wm; red_l[warp][a] = wl; }
+  }
+  __syncthreads();
+  if (tid < kTok * 16) {
+    const int a = tid >> 4, d = tid & 15;
+    float gm = -INFINITY;
+    for (int w = 0; w < 8; ++w) gm = fmaxf(gm, red_m[w][a]);
+    float gl = 0.f, go = 0.f;
+    for (int w = 0; w < 8; ++w) {
+      const float c = (red_m[w][a] == -INFINITY) ? 0.f : __expf(red_m[w][a] - gm);
+      gl += red_l[w][a] * c; go += red_o[w][a][d] * c;
+    }
+    out[(static_cast<size_t>(p) * kTok + a) * kInt + h * 16 + d] = __float2bfloat16_rn(go / gl);
+  }
+}
+
+// image -> token cross attention: every image token attends to the 8 prompt tokens, 8 heads of 16.
+// q [q_batch * n_img, 128] (q_stride = 0: shared queries, layer 0); k,v [P*8,128]; out [P*n_img,128].
+// One thread per (prompt, image token, head).
+__global__ void __launch_bounds__(256) sam_i2t_attn_kernel(const __nv_bfloat16* __restrict__ q, size_t q_stride, const __nv_bfloat16* __restrict__ k,
+                                                           const __nv_bfloat16* __restrict__ v, int n_img, __nv_bfloat16* __restrict__ out) {
+  __shared__ float sk[kTok][kInt], sv[kTok][kInt];
+  const int p = blockIdx.y;
+  for (int i = threadIdx.x; i < kTok * kInt; i += 256) {
+    sk[0][i] = __bfloat162float(k[static_cast<size_t>(p) * kTok * kInt + i]);
+    sv[0][i] = __bfloat162float(v[static_cast<size_t>(p) * kTok * kInt + i]);
+  }
+  __syncthreads();
+  const int idx = blockIdx.x * 256 + threadIdx.x;   // (token, head)
+  const int t = idx >> 3, h = idx & 7;
+  if (t >= n_img) return;
+  const uint4* qp = reinterpret_cast<const uint4*>(q + static_cast<size_t>(p) * q_stride + static_cast<size_t>(t) * kInt + h * 16);
+  uint4 raw[2] = {qp[0], qp[1]};
+  const __nv_bfloat16* qb = reinterpret_cast<const __nv_bfloat16*>(raw);
+  float qf[16];
+#pragma unroll
+  for (int d = 0; d < 16; ++d) qf[d] = __bfloat162float(qb[d]) * 0.25f;
+  float s[kTok], m = -INFINITY;
+#pragma unroll
+  for (int a = 0; a < kTok; ++a) {
+    float x = 0.f;
+#pragma unroll
+    for (int d = 0; d < 16; ++d) x += qf[d] * sk[a][h * 16 + d];
+    s[a] = x; m = fmaxf(m, x);
+  }
+  float l = 0.f;
+#pragma unroll
+  for (int a = 0; a < kTok; ++a) { s[a] = __expf(s[a] - m); l += s[a]; }
+  const float inv = 1.f / l;
+  float o[16];
+#pragma unroll
+  for (int d = 0; d < 16; ++d) {
+    float x = 0.f;
+#pragma unroll
+    for (int a = 0; a < kTok; ++a) x += s[a] * sv[a][h * 16 + d];
+    o[d] = x * inv;
+  }
+  uint4 w[2];
+  uint32_t* wp = reinterpret_cast<uint32_t*>(w);
+#pragma unroll
+  for (int d = 0; d < 8; ++d) wp[d] = pack_bf16(o[2 * d], o[2 * d + 1]);
+  uint4* op = reinterpret_cast<uint4*>(out + (static_cast<size_t>(p) * n_img + t) * kInt + h * 16);
+  op[0] = w[0]; op[1] = w[1];
+}
+
+// ---- output upscaling (mask_decoder.py:214-217): rows of dc1 [P*g*g, 4*64] (transposed conv + bias + feat_s1 already added
+// by the GEMM epilogue) -> LayerNorm2d over the 64 channels of each sub-pixel (eps 1e-6) -> GELU -> up1 bf16
+// [P, (2g)^2 pixels in (y,x,sub) order, 64].  One warp per (row, sub-pixel).
+__global__ void __launch_bounds__(256) sam_up1_kernel(const float* __restrict__ dc1, size_t n_items, const float* __restrict__ lw,
+                                                      const float* __restrict__ lb, __nv_bfloat16* __restrict__ up1) {
+  const size_t item = static_cast<size_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (item >= n_items) return;
+  const float2 v = *reinterpret_cast<const float2*>(dc1 + item * 64 + 2 * lane);
+  float s = v.x + v.y;
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float u = s / 64.f;
+  const float a = v.x - u, b = v.y - u;
+  float q = a * a + b * b;
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float r = 1.f / sqrtf(q / 64.f + 1e-6f);
+  const float y0 = lw[2 * lane] * (a * r) + lb[2 * lane], y1 = lw[2 * lane + 1] * (b * r) + lb[2 * lane + 1];
+  *reinterpret_cast<uint32_t*>(up1 + item * 64 + 2 * lane) = pack_bf16(gelu_erf(y0), gelu_erf(y1));
+}
+
+// masks = hyper_in @ upscaled (mask_decoder.py:225-226) for mask tokens 1..3 (multimask_output, :141-143):
+// up2 bf16 [P, g*g, sub1, sub2, 32] (nested sub-pixel order, see sam_subpixel2_kernel) -> low_res f32 [P,3,4g,4g].
+// One thread per (prompt, output pixel).
+__global__ void __launch_bounds__(256) sam_mask_dot_kernel(const __nv_bfloat16* __restrict__ up2, const float* __restrict__ hyper /*[P,4,32]*/,
+                                                           int g, float* __restrict__ low) {
+  __shared__ float sh[3][32];
+  const int p = blockIdx.y;
+  if (threadIdx.x < 96) sh[0][threadIdx.x] = hyper[static_cast<size_t>(p) * 128 + 32 + threadIdx.x];
+  __syncthreads();
+  const int S = 4 * g;
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= S * S) return;
+  const int y = i / S, x = i - y * S;
+  const int sub2 = (y & 1) * 2 + (x & 1), sub1 = ((y >> 1) & 1) * 2 + ((x >> 1) & 1);
+  const size_t src = (((static_cast<size_t>(p) * g * g + static_cast<size_t>(y >> 2) * g + (x >> 2)) * 4 + sub1) * 4 + sub2) * 32;
+  const uint4* up = reinterpret_cast<const uint4*>(up2 + src);
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint4 raw = up[j];
+    const __nv_bfloat16* e = reinterpret_cast<const __nv_bfloat16*>(&raw);
+#pragma unroll
+    for (int d = 0; d < 8; ++d) {
+      const float f = __bfloat162float(e[d]);
+      a0 += sh[0][8 * j + d] * f; a1 += sh[1][8 * j + d] * f; a2 += sh[2][8 * j + d] * f;
+    }
+  }
+  float* o = low + static_cast<size_t>(p) * 3 * S * S + i;
+  o[0] = a0; o[static_cast<size_t>(S) * S] = a1; o[static_cast<size_t>(2) * S * S] = a2;
+}
+
+// gathers rows (token index `tok` of every prompt) of hs [P,8,256] f32 as bf16 [P,256]
+__global__ void sam_pick_token_kernel(const float* __restrict__ hs, int P, int tok, __nv_bfloat16* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P * kC) return;
+  out[i] = __float2bfloat16_rn(hs[(static_cast<size_t>(i / kC) * kTok + tok) * kC + (i % kC)]);
+}
+// iou = sigmoid(head)[:, 1:4]   (mask_decoder.py:229, sam2_utils.py:134-135, multimask slice :141-143)
+__global__ void sam_iou_kernel(const float* __restrict__ head /*[P,4]*/, int P, float* __restrict__ iou /*[P,3]*/) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P * 3) return;
+  const float x = head[(i / 3) * 4 + 1 + i % 3];
+  iou[i] = 1.f / (1.f + expf(-x));
+}
+
+// ------------------------------------------------------------------------------------------- AMG post-processing
+// F.interpolate(bilinear, align_corners=False) sample of a [h,w] logit map at output pixel (y,x) of [H,W]
+// (ATen upsample_bilinear2d: src = scale*(dst+0.5)-0.5 clamped at 0, lambda in f32)
+struct Bilin { int y0, y1, x0, x1; float ly, lx; };
+__device__ __forceinline__ void bilin_axis(int d, float scale, int n, int& i0, int& i1, float& l) {
+  float s = __fadd_rn(__fmul_rn(scale, __fadd_rn(static_cast<float>(d), 0.5f)), -0.5f);
+  if (s < 0.f) s = 0.f;
+  i0 = static_cast<int>(s);
+  if (i0 > n - 1) i0 = n - 1;
+  i1 = i0 + (i0 < n - 1 ? 1 : 0);
+  l = __fadd_rn(s, -static_cast<float>(i0));
+}
+__device__ __forceinline__ float bilin_sample(const float* __restrict__ m, int w, int y0, int y1, int x0, int x1, float ly, float lx) {
+  const float hy = __fadd_rn(1.f, -ly), hx = __fadd_rn(1.f, -lx);
+  // ATen: w0y * (w0x * a + w1x * b) + w1y * (w0x * c + w1x * d)
+  const float top = __fadd_rn(__fmul_rn(hx, m[y0 * w + x0]), __fmul_rn(lx, m[y0 * w + x1]));
+  const float bot = __fadd_rn(__fmul_rn(hx, m[y1 * w + x0]), __fmul_rn(lx, m[y1 * w + x1]));
+  return __fadd_rn(__fmul_rn(hy, top), __fmul_rn(ly, bot));
+}
+
+struct MaskStat { int hi, lo, area, x0, y0, x1, y1, pad; };   // counts of logit > +off, > -off, > 0; bbox of > 0
+
+// candidates = masks with iou > pred_iou_thresh (cand[j] = flattened index).  grid (tiles, n_cand)
+__global__ void __launch_bounds__(256) amg_stats_kernel(const float* __restrict__ low, const int* __restrict__ cand, int h, int w, int H, int W,
+                                                        float off, MaskStat* __restrict__ stats) {
+  const int j = blockIdx.y;
+  const float* m = low + static_cast<size_t>(cand[j]) * h * w;
+  const float sy = static_cast<float>(h) / H, sx = static_cast<float>(w) / W;
+  int hi = 0, lo = 0, area = 0, x0 = W, y0 = H, x1 = -1, y1 = -1;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < H * W; i += gridDim.x * 256) {
+    const int y = i / W, x = i - y * W;
+    int ya, yb, xa, xb; float ly, lx;
+    bilin_axis(y, sy, h, ya, yb, ly);
+    bilin_axis(x, sx, w, xa, xb, lx);
+    const float v = bilin_sample(m, w, ya, yb, xa, xb, ly, lx);
+    hi += v > off; lo += v > -off;
+    if (v > 0.f) { ++area; x0 = min(x0, x); x1 = max(x1, x); y0 = min(y0, y); y1 = max(y1, y); }
+  }
+  for (int s = 16; s > 0; s >>= 1) {
+    hi += __shfl_xor_sync(0xffffffffu, hi, s); lo += __shfl_xor_sync(0xffffffffu, lo, s); area += __shfl_xor_sync(0xffffffffu, area, s);
+    x0 = min(x0, __shfl_xor_sync(0xffffffffu, x0, s)); y0 = min(y0, __shfl_xor_sync(0xffffffffu, y0, s));
+    x1 = max(x1, __shfl_xor_sync(0xffffffffu, x1, s)); y1 = max(y1, __shfl_xor_sync(0xffffffffu, y1, s));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    MaskStat* st = stats + j;
+    atomicAdd(&st->hi, hi); atomicAdd(&st->lo, lo); atomicAdd(&st->area, area);
+    atomicMin(&st->x0, x0); atomicMin(&st->y0, y0); atomicMax(&st->x1, x1); atomicMax(&st->y1, y1);
+  }
+}
+__global__ void amg_stats_init_kernel(MaskStat* st, int n, int H, int W) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) st[i] = MaskStat{0, 0, 0, W, H, -1, -1, 0};
+}
+// binarise the kept masks in their final order: out[k] = upsample(low[sel[k]]) > 0
+__global__ void __launch_bounds__(256) amg_write_masks_kernel(const float* __restrict__ low, const int* __restrict__ sel, int h, int w, int H, int W,
+                                                              uint8_t* __restrict__ out) {
+  const int k = blockIdx.y;
+  const float* m = low + static_cast<size_t>(sel[k]) * h * w;
+  const float sy = static_cast<float>(h) / H, sx = static_cast<float>(w) / W;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < H * W; i += gridDim.x * 256) {
+    const int y = i / W, x = i - y * W;
+    int ya, yb, xa, xb; float ly, lx;
+    bilin_axis(y, sy, h, ya, yb, ly);
+    bilin_axis(x, sx, w, xa, xb, lx);
+    out[static_cast<size_t>(k) * H * W + i] = bilin_sample(m, w, ya, yb, xa, xb, ly, lx) > 0.f ? 1 : 0;
+  }
+}
+
+// counters: [0] n_cand, [1] K (final)
+// predicted-IoU filter (automatic_mask_generator.py:331-334): ordered compaction of the flattened [P*3] list
+__global__ void amg_candidates_kernel(const float* __restrict__ iou, int n, float thr, int* __restrict__ cand, int* __restrict__ counters) {
+  __shared__ int s_off;
+  if (threadIdx.x == 0) s_off = 0;
+  __syncthreads();
+  for (int base = 0; base < n; base += blockDim.x) {   // blockDim.x == 1024, one block
+    const int i = base + threadIdx.x;
+    const bool keep = i < n && iou[i] > thr;
+    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+    __shared__ int s_warp[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) s_warp[warp] = __popc(bal);
+    __syncthreads();
+    int before = 0;
+    for (int w = 0; w < warp; ++w) before += s_warp[w];
+    int total = 0;
+    for (int w = 0; w < 32; ++w) total += s_warp[w];
+    if (keep) cand[s_off + before + __popc(bal & ((1u << lane) - 1))] = i;
+    __syncthreads();
+    if (threadIdx.x == 0) s_off += total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) counters[0] = s_off;
+}
+
+// stability filter (:337-342, utils/amg.py:158-178), boxes (:305-348), box NMS (torchvision nms: stable descending sort by
+// predicted IoU, greedy, IoU = inter / (a_i + a_j - inter) > thr suppresses).  One block of 1024 threads, n_cand <= 1024.
+__global__ void __launch_bounds__(1024) amg_decide_kernel(const MaskStat* __restrict__ stats, const int* __restrict__ cand, const float* __restrict__ iou,
+                                                          float stab_thr, float nms_thr, int* __restrict__ counters, int* __restrict__ sel,
+                                                          float* __restrict__ iou_out, float* __restrict__ stab_out, int32_t* __restrict__ boxes_out,
+                                                          int32_t* __restrict__ src_out, int max_out) {
+  __shared__ float s_score[1024], s_stab[1024];
+  __shared__ int s_box[1024][4];
+  __shared__ int s_idx[1024];      // candidate slot in sorted position
+  __shared__ unsigned char s_dead[1024];
+  __shared__ int s_n;
+  const int n_cand = counters[0];
+  const int t = threadIdx.x;
+  // 1. stability filter, ordered compaction into shared arrays (slot order = flattened index order)
+  if (t == 0) {
+    int n = 0;
+    for (int j = 0; j < n_cand && j < 1024; ++j) {
+      const MaskStat st = stats[j];
+      const float stab = __fdiv_rn(static_cast<float>(st.hi), static_cast<float>(st.lo));   // 0/0 -> NaN -> rejected
+      if (stab >= stab_thr) {
+        s_score[n] = iou[cand[j]]; s_stab[n] = stab; s_idx[n] = cand[j];
+        const bool empty = st.area == 0;
+        s_box[n][0] = empty ? 0 : st.x0; s_box[n][1] = empty ? 0 : st.y0; s_box[n][2] = empty ? 0 : st.x1; s_box[n][3] = empty ? 0 : st.y1;
+        ++n;
+      }
+    }
+    s_n = n;
+  }
+  __syncthreads();
+  const int n = s_n;
+  // 2. stable descending rank
+  int rank = 0;
+  if (t < n) {
+    const float my = s_score[t];
+    for (int j = 0; j < n; ++j) rank += (s_score[j] > my) || (s_score[j] == my && j < t);
+  }
+  __shared__ int s_order[1024];
+  if (t < n) s_order[rank] = t;
+  if (t < 1024) s_dead[t] = 0;
+  __syncthreads();
+  // 3. greedy suppression in sorted order
+  for (int a = 0; a < n; ++a) {
+    if (!s_dead[a]) {
+      const int ia = s_order[a];
+      const float ax0 = s_box[ia][0], ay0 = s_box[ia][1], ax1 = s_box[ia][2], ay1 = s_box[ia][3];
+      const float aa = __fmul_rn(ax1 - ax0, ay1 - ay0);
+      const int b = a + 1 + t;
+      if (b < n && !s_dead[b]) {
+        const int ib = s_order[b];
+        const float bx0 = s_box[ib][0], by0 = s_box[ib][1], bx1 = s_box[ib][2], by1 = s_box[ib][3];
+        const float ab = __fmul_rn(bx1 - bx0, by1 - by0);
+        const float w = fmaxf(0.f, fminf(ax1, bx1) - fmaxf(ax0, bx0)), h = fmaxf(0.f, fminf(ay1, by1) - fmaxf(ay0, by0));
+        const float inter = __fmul_rn(w, h);
+        if (__fdiv_rn(inter, __fadd_rn(__fadd_rn(aa, ab), -inter)) > nms_thr) s_dead[b] = 1;
+      }
+    }
+    __syncthreads();
+  }
+  // 4. survivors in sorted order
+  if (t == 0) {
+    int k = 0;
+    for (int a = 0; a < n; ++a) {
+      if (s_dead[a]) continue;
+      if (k < max_out) {
+        const int i = s_order[a];
+        sel[k] = s_idx[i]; iou_out[k] = s_score[i]; stab_out[k] = s_stab[i]; src_out[k] = s_idx[i];
+        for (int c = 0; c < 4; ++c) boxes_out[4 * k + c] = s_box[i][c];
+      }
+      ++k;
+    }
+    counters[1] = k;
+  }
+}
+__global__ void mul_kernel(const float* a, const float* b, int n, float* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = a[i] * b[i];
+}
+// compaction of the masks kept by OVO's NMS: dst[k] = src[idx[k]]
+__global__ void gather_masks_kernel(const uint8_t* __restrict__ src, const int* __restrict__ idx, size_t npix16, uint8_t* __restrict__ dst) {
+  const uint4* s4 = reinterpret_cast<const uint4*>(src) + static_cast<size_t>(idx[blockIdx.y]) * npix16;
+  uint4* d4 = reinterpret_cast<uint4*>(dst) + static_cast<size_t>(blockIdx.y) * npix16;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < npix16; i += static_cast<size_t>(gridDim.x) * blockDim.x) d4[i] = s4[i];
+}
+// AMG point grid (utils/amg.py:181-189) in model-frame pixels the way the reference's f32 arithmetic produces them
+// (automatic_mask_generator.py:264-265,308-310; utils/transforms.py:59-65): f32(grid*W) / W * S
+__global__ void amg_points_kernel(int n, int H, int W, float S, float* __restrict__ pts) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * n) return;
+  const int iy = i / n, ix = i - iy * n;
+  // np.linspace(offset, 1 - offset, n) in f64: start + k * step, step = (stop - start) / (n - 1)
+  const double off = 1.0 / (2.0 * n), step = n > 1 ? ((1.0 - off) - off) / (n - 1) : 0.0;
+  const double gx = (n > 1 && ix == n - 1) ? 1.0 - off : off + ix * step, gy = (n > 1 && iy == n - 1) ? 1.0 - off : off + iy * step;
+  const float px = static_cast<float>(gx * W), py = static_cast<float>(gy * H);
+  pts[2 * i] = __fmul_rn(__fdiv_rn(px, static_cast<float>(W)), S);
+  pts[2 * i + 1] = __fmul_rn(__fdiv_rn(py, static_cast<float>(H)), S);
+}
+
+template <typename T>
+int dalloc(T** p, size_t n) {
+  if (cudaMalloc(reinterpret_cast<void**>(p), std::max<size_t>(n, 1) * sizeof(T)) != cudaSuccess) {
+    cudaGetLastError();
+    return set_error(OVO_E_NOMEM, "sam workspace allocation of %zu bytes failed", n * sizeof(T));
+  }
+  return OVO_OK;
+}
+
+// ATen _upsample_bilinear2d_aa weights for one axis (aten/src/ATen/native/cpu/UpSampleKernel.cpp)
+void aa_axis(int n_in, int n_out, std::vector<int>& mins, std::vector<int>& sizes, std::vector<float>& ws, int* kmax) {
+  const float scale = static_cast<float>(n_in) / n_out;
+  const float support = scale >= 1.f ? scale : 1.f;
+  const float inv = scale >= 1.f ? 1.f / scale : 1.f;
+  const int k = static_cast<int>(std::ceil(support)) * 2 + 1;
+  *kmax = k;
+  mins.assign(n_out, 0); sizes.assign(n_out, 0); ws.assign(static_cast<size_t>(n_out) * k, 0.f);
+  for (int i = 0; i < n_out; ++i) {
+    const float center = scale * (i + 0.5f);
+    const int xmin = std::max(0, static_cast<int>(center - support + 0.5f));
+    const int xmax = std::min(n_in, static_cast<int>(center + support + 0.5f));
+    float total = 0.f;
+    for (int j = 0; j < xmax - xmin; ++j) {
+      const float w = std::max(0.f, 1.f - std::fabs((j + xmin - center + 0.5f) * inv));
+      ws[static_cast<size_t>(i) * k + j] = w; total += w;
+    }
+    for (int j = 0; j < xmax - xmin; ++j) ws[static_cast<size_t>(i) * k + j] /= total;
+    mins[i] = xmin; sizes[i] = xmax - xmin;
+  }
+}
+
+}  // namespace
+}  // namespace ovo
+
+using namespace ovo;
+
+struct ovo_sam {
+  ovo_sam_cfg cfg{};
+  ovo_sam_weights w{};
+  std::vector<ovo_hiera_block> blocks;
+  std::vector<ovo_sam_dec_layer> layers;
+  int S = 0, g = 0;            // image size, embedding grid (S/16)
+  int max_h = 0, max_w = 0, max_p = 0;
+  // transform
+  int tab_h = -1, tab_w = -1, kx = 0, ky = 0;
+  int *xmin = nullptr, *xsize = nullptr, *ymin = nullptr, *ysize = nullptr;
+  float *xw = nullptr, *yw = nullptr, *tmp = nullptr, *pixels = nullptr;
+  __nv_bfloat16* patches = nullptr;
+  // trunk
+  float *xa = nullptr, *xb = nullptr, *tshort = nullptr;
+  __nv_bfloat16 *xn = nullptr, *qkv = nullptr, *att = nullptr, *hid = nullptr;
+  __nv_bfloat16* stage_bf[4] = {nullptr, nullptr, nullptr, nullptr};
+  int stage_grid[4] = {0, 0, 0, 0}, stage_dim[4] = {0, 0, 0, 0};
+  // neck / image features
+  float *lat3 = nullptr, *lat2 = nullptr, *embed = nullptr, *feat_s0 = nullptr, *feat_s1 = nullptr, *s0_sub = nullptr, *s1_sub = nullptr;
+  float* src = nullptr;
+  __nv_bfloat16 *src_bf = nullptr, *srcpe_bf = nullptr, *k0 = nullptr, *v0 = nullptr, *qi0 = nullptr;
+  // decoder (sized for max_p prompts)
+  float *tokens = nullptr, *queries = nullptr, *tq_tmp = nullptr, *keys = nullptr, *keys_pre = nullptr, *dc1 = nullptr, *hyper = nullptr, *iou_head = nullptr;
+  __nv_bfloat16 *tq_bf = nullptr, *tqpe_bf = nullptr, *t_q = nullptr, *t_k = nullptr, *t_v = nullptr, *t_o = nullptr, *t_mlp = nullptr;
+  __nv_bfloat16 *keys_bf = nullptr, *keyspe_bf = nullptr, *big_q = nullptr, *big_k = nullptr, *big_v = nullptr, *up1 = nullptr, *up2 = nullptr;
+  __nv_bfloat16 *tok_a = nullptr, *tok_b = nullptr;
+  // post-processing
+  MaskStat* stats = nullptr;
+  int *cand = nullptr, *sel = nullptr;
+  float* low_all = nullptr; float* iou_all = nullptr; float* points = nullptr;
+  uint8_t* masks_tmp = nullptr; float* score_tmp = nullptr; uint8_t* keep_tmp = nullptr; float* stab_tmp = nullptr; float* iou_tmp = nullptr;
+  int32_t* box_tmp = nullptr; int32_t* src_tmp = nullptr; int32_t* order_tmp = nullptr;
+  int* counters = nullptr;
+  size_t masks_tmp_bytes = 0; uint8_t* masks_tmp2 = nullptr;
+  std::vector<void*> owned;
+};
+
+namespace {
+
+template <typename T>
+int salloc(ovo_sam* s, T** p, size_t n) {
+  OVO_TRY(dalloc(p, n));
+  s->owned.push_back(*p);
+  return OVO_OK;
+}
+
+int gemm(int epi, const __nv_bfloat16* A, int lda, const void* W, int ldw, int M, int N, int K, const float* bias, void* out, int ldo,
+         const float* resid, int ldr, int resid_mod, cudaStream_t st) {
+  EpiParams ep;
+  ep.out = out; ep.ldo = ldo; ep.bias = bias; ep.resid = resid; ep.ldr = ldr; ep.resid_mod = resid_mod;
+  return launch_gemm(epi, A, lda, static_cast<const __nv_bfloat16*>(W), ldw, M, N, K, ep, st);
+}
+
+int ln(const float* x, int rows, int width, const float* g, const float* b, float eps, float* o32, __nv_bfloat16* o16,
+       __nv_bfloat16* o16b, const float* add, int add_mod, cudaStream_t st) {
+  OVO_REQUIRE(width % 4 == 0 && width <= 2048, "sam layernorm: unsupported width %d", width);
+  ProfScope prof(st, PROF_LN, 0.0, static_cast<double>(rows) * width * 8.0);
+  sam_ln_kernel<<<ceil_div(rows, 8), 256, 0, st>>>(x, rows, width, g, b, eps, o32, o16, o16b, add, add_mod);
+  OVO_CHECK_LAUNCH();
+  return OVO_OK;
+}
+
+int add_cast(const float* a, const float* b, int b_mod, int width, size_t n, __nv_bfloat16* o16, float* o32, cudaStream_t st) {
+  ProfScope prof(st, PROF_OTHER, 0.0, static_cast<double>(n) * 6.0);
+  add_cast_kernel<<<ceil_div(static_cast<long long>(n / 4), 256), 256, 0, st>>>(a, b, b_mod, width, n / 4, o16, o32);
+  OVO_CHECK_LAUNCH();
+  return OVO_OK;
+}
+
+// Hiera trunk from the im2col'd patches (hieradet.py:274-291) + neck + decoder-side per-image constants
+int run_trunk(ovo_sam* s, int n_blocks, float* block_out, cudaStream_t st) {
+  const ovo_sam_cfg& c = s->cfg;
+  int grid = s->S / 4;
+  const int T0 = grid * grid;
+  float* x = s->xa;
+  float* xo = s->xb;
+  // patch embed + bias + pos embed
+  OVO_TRY(gemm(EPI_F32_RESID, s->patches, s->w.patch_kpad, s->w.patch_w, s->w.patch_kpad, T0, c.embed_dim, s->w.patch_kpad, s->w.patch_b,
+               x, c.embed_dim, s->w.pos, c.embed_dim, 0, st));
+  const int nb = n_blocks < 0 ? c.n_blocks : std::min(n_blocks, c.n_blocks);
+  int stage = 0, last_dim = c.embed_dim;
+  for (int i = 0; i < nb; ++i) {
+    const ovo_hiera_block& b = s->blocks[i];
+    OVO_REQUIRE(b.grid_in == grid, "sam block %d: grid mismatch", i);
+    const int T = grid * grid;
+    const int ws = b.window > 0 ? b.window : grid;
+    OVO_REQUIRE(grid % ws == 0 && (ws * ws) % 16 == 0 && (!b.q_pool || ((ws / 2) * (ws / 2)) % 16 == 0), "sam block %d: unsupported window %d on grid %d", i, ws, grid);
+    OVO_REQUIRE(b.dim_out == b.heads * kSamHd, "sam block %d: head_dim must be 72", i);
+    OVO_TRY(ln(x, T, b.dim, b.norm1_w, b.norm1_b, c.trunk_ln_eps, nullptr, s->xn, nullptr, nullptr, 1, st));
+    const float* resid = x;
+    float* dst = x;
+    int grid_out = grid;
+    if (b.short_w != nullptr) {   // transition: shortcut = maxpool(proj(norm1(x)))  (hieradet.py:139-141)
+      OVO_TRY(gemm(EPI_F32, s->xn, b.dim, b.short_w, b.dim, T, b.dim_out, b.dim, b.short_b, s->tshort, b.dim_out, nullptr, 0, 0, st));
+      if (b.q_pool) {
+        grid_out = grid / 2;
+        sam_maxpool_kernel<<<ceil_div(static_cast<long long>(grid_out) * grid_out * (b.dim_out / 4), 256), 256, 0, st>>>(s->tshort, grid, b.dim_out, xo);
+        OVO_CHECK_LAUNCH();
+      } else {
+        OVO_CUDA(cudaMemcpyAsync(xo, s->tshort, sizeof(float) * T * b.dim_out, cudaMemcpyDeviceToDevice, st));
+      }
+      resid = xo; dst = xo;
+    }
+    OVO_TRY(gemm(EPI_BF16, s->xn, b.dim, b.qkv_w, b.dim, T, 3 * b.dim_out, b.dim, b.qkv_b, s->qkv, 3 * b.dim_out, nullptr, 0, 0, st));
+    {
+      WinAttnParams p;
+      p.qkv = s->qkv; p.out = s->att; p.grid = grid; p.ws = ws; p.heads = b.heads; p.dim_out = b.dim_out; p.q_pool = b.q_pool;
+      p.scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(kSamHd));
+      const int nq = b.q_pool ? ws * ws / 4 : ws * ws;
+      const int wins = (grid / ws) * (grid / ws);
+      ProfScope prof(st, PROF_ATTN, 4.0 * wins * b.heads * static_cast<double>(nq) * ws * ws * kSamHd, 0.0);
+      hiera_attention_kernel<<<dim3(ceil_div(nq, kSamQB), wins, b.heads), 128, 0, st>>>(p);
+      OVO_CHECK_LAUNCH();
+    }
+    const int To = grid_out * grid_out;
+    OVO_TRY(gemm(EPI_F32_RESID, s->att, b.dim_out, b.proj_w, b.dim_out, To, b.dim_out, b.dim_out, b.proj_b, dst, b.dim_out, resid, b.dim_out, 0, st));
+    if (dst != x) std::swap(x, xo);
+    grid = grid_out;
+    OVO_TRY(ln(x, To, b.dim_out, b.norm2_w, b.norm2_b, c.trunk_ln_eps, nullptr, s->xn, nullptr, nullptr, 1, st));
+    OVO_TRY(gemm(EPI_BF16_GELU, s->xn, b.dim_out, b.fc1_w, b.dim_out, To, 4 * b.dim_out, b.dim_out, b.fc1_b, s->hid, 4 * b.dim_out, nullptr, 0, 0, st));
+    OVO_TRY(gemm(EPI_F32_RESID, s->hid, 4 * b.dim_out, b.fc2_w, 4 * b.dim_out, To, b.dim_out, 4 * b.dim_out, b.fc2_b, x, b.dim_out, x, b.dim_out, 0, st));
+    last_dim = b.dim_out;
+    if (stage < 4 && i == c.stage_end[stage]) {
+      OVO_REQUIRE(s->stage_grid[stage] == grid && s->stage_dim[stage] == b.dim_out, "sam: stage %d geometry mismatch", stage);
+      OVO_TRY(add_cast(x, nullptr, 1, b.dim_out, static_cast<size_t>(To) * b.dim_out, s->stage_bf[stage], nullptr, st));
+      ++stage;
+    }
+  }
+  if (block_out) OVO_CUDA(cudaMemcpyAsync(block_out, x, sizeof(float) * grid * grid * last_dim, cudaMemcpyDeviceToDevice, st));
+  if (nb < c.n_blocks) return OVO_OK;
+  // ---- neck (image_encoder.py:102-134) with conv_s0/conv_s1 folded (sam2_base.py:467-479)
+  const int g = s->g;
+  OVO_TRY(gemm(EPI_F32, s->stage_bf[3], s->stage_dim[3], s->w.neck3_w, s->stage_dim[3], (g / 2) * (g / 2), kC, s->stage_dim[3], s->w.neck3_b, s->lat3, kC, nullptr, 0, 0, st));
+  OVO_TRY(gemm(EPI_F32, s->stage_bf[2], s->stage_dim[2], s->w.neck2_w, s->stage_dim[2], g * g, kC, s->stage_dim[2], s->w.neck2_b, s->lat2, kC, nullptr, 0, 0, st));
+  OVO_TRY(gemm(EPI_F32, s->stage_bf[1], s->stage_dim[1], s->w.s1_w, s->stage_dim[1], 4 * g * g, 64, s->stage_dim[1], s->w.s1_b, s->feat_s1, 64, nullptr, 0, 0, st));
+  OVO_TRY(gemm(EPI_F32, s->stage_bf[0], s->stage_dim[0], s->w.s0_w, s->stage_dim[0], 16 * g * g, 32, s->stage_dim[0], s->w.s0_b, s->feat_s0, 32, nullptr, 0, 0, st));
+  sam_embed_kernel<<<ceil_div(g * g * kC, 256), 256, 0, st>>>(s->lat2, s->lat3, g, s->w.no_mask_embed, s->w.dense_pe, s->embed, s->src, s->src_bf, s->srcpe_bf);
+  OVO_CHECK_LAUNCH();
+  sam_subpixel_kernel<<<ceil_div(static_cast<long long>(g) * g * 4 * 64, 256), 256, 0, st>>>(s->feat_s1, g, 64, s->s1_sub);
+  OVO_CHECK_LAUNCH();
+  sam_subpixel2_kernel<<<ceil_div(static_cast<long long>(g) * g * 16 * 32, 256), 256, 0, st>>>(s->feat_s0, g, s->s0_sub);
+  OVO_CHECK_LAUNCH();
+  // layer-0 projections of the (prompt independent) image side: k, v of token->image and q of image->token
+  const ovo_sam_dec_layer& L0 = s->layers[0];
+  const int HW = g * g;
+  OVO_TRY(gemm(EPI_BF16, s->srcpe_bf, kC, L0.t2i.k_w, kC, HW, kInt, kC, L0.t2i.k_b, s->k0, kInt, nullptr, 0, 0, st));
+  OVO_TRY(gemm(EPI_BF16, s->src_bf, kC, L0.t2i.v_w, kC, HW, kInt, kC, L0.t2i.v_b, s->v0, kInt, nullptr, 0, 0, st));
+  OVO_TRY(gemm(EPI_BF16, s->srcpe_bf, kC, L0.i2t.q_w, kC, HW, kInt, kC, L0.i2t.q_b, s->qi0, kInt, nullptr, 0, 0, st));
+  return OVO_OK;
+}
+
+int copy_taps(ovo_sam* s, float* embed, float* s0, float* s1, cudaStream_t st) {
+  const int g = s->g;
+  if (embed) OVO_CUDA(cudaMemcpyAsync(embed, s->embed, sizeof(float) * g * g * kC, cudaMemcpyDeviceToDevice, st));
+  if (s0) OVO_CUDA(cudaMemcpyAsync(s0, s->feat_s0, sizeof(float) * 16 * g * g * 32, cudaMemcpyDeviceToDevice, st));
+  if (s1) OVO_CUDA(cudaMemcpyAsync(s1, s->feat_s1, sizeof(float) * 4 * g * g * 64, cudaMemcpyDeviceToDevice, st));
+  return OVO_OK;
+}
+
+int patches_from_pixels(ovo_sam* s, cudaStream_t st) {
+  ProfScope prof(st, PROF_PRE, 0.0, 0.0);
+  sam_im2col_kernel<<<(s->S / 4) * (s->S / 4), 160, 0, st>>>(s->pixels, s->S, s->S / 4, s->w.patch_kpad, s->patches);
+  OVO_CHECK_LAUNCH();
+  return OVO_OK;
+}
+
+// Attention.forward on the token side: out_proj(attn(...)) handled by the caller; this projects q/k/v of tokens.
+int tok_lin(ovo_sam* s, const __nv_bfloat16* a, const void* w, const float* b, int rows, int n, int k, __nv_bfloat16* out, cudaStream_t st) {
+  return gemm(EPI_BF16, a, k, w, k, rows, n, k, b, out, n, nullptr, 0, 0, st);
+}
+
+// token -> image attention block: queries = LN(queries + out_proj(attn(q = queries+pe, k, v)))
+int t2i_block(ovo_sam* s, const ovo_sam_attn& A, const __nv_bfloat16* kbuf, const __nv_bfloat16* vbuf, size_t kv_stride, int P,
+              const float* nw, const float* nb, cudaStream_t st) {
+  const int R = P * kTok, HW = s->g * s->g;
+  OVO_TRY(add_cast(s->queries, s->tokens, R, kC, static_cast<size_t>(R) * kC, s->tqpe_bf, nullptr, st));
+  OVO_TRY(tok_lin(s, s->tqpe_bf, A.q_w, A.q_b, R, kInt, kC, s->t_q, st));
+  {
+    ProfScope prof(st, PROF_ATTN, 4.0 * P * 8 * kTok * static_cast<double>(HW) * 16, 0.0);
+    sam_t2i_attn_kernel<<<dim3(P, 8), 256, 0, st>>>(s->t_q, kbuf, vbuf, kv_stride, HW, s->t_o);
+    OVO_CHECK_LAUNCH();
+  }
+  OVO_TRY(gemm(EPI_F32_RESID, s->t_o, kInt, A.o_w, kInt, R, kC, kInt, A.o_b, s->tq_tmp, kC, s->queries, kC, 0, st));
+  return ln(s->tq_tmp, R, kC, nw, nb, 1e-5f, s->queries, s->tq_bf, nullptr, nullptr, 1, st);
+}
+
+}  // namespace
+
+extern "C" {
+
+int ovo_sam_create(const ovo_sam_cfg* cfg, const ovo_sam_weights* w, int max_h, int max_w, int max_prompts, ovo_sam_t** out) {
+  OVO_REQUIRE(cfg && w && out, "ovo_sam_create: null argument");
+  OVO_REQUIRE(cfg->image_size % 64 == 0 && cfg->n_blocks > 0 && cfg->decoder_depth >= 1, "ovo_sam_create: bad config");
+  OVO_REQUIRE(w->patch_kpad % 8 == 0 && w->patch_kpad >= 147, "ovo_sam_create: patch_kpad must be a multiple of 8 >= 147");
+  ovo_sam* s = new ovo_sam();
+  s->cfg = *cfg; s->w = *w;
+  s->blocks.assign(w->blocks, w->blocks + cfg->n_blocks);
+  s->layers.assign(w->layers, w->layers + cfg->decoder_depth);
+  s->w.blocks = s->blocks.data(); s->w.layers = s->layers.data();
+  s->S = cfg->image_size; s->g = cfg->image_size / 16;
+  s->max_h = max_h; s->max_w = max_w; s->max_p = max_prompts;
+  const int S = s->S, g = s->g, g0 = S / 4;
+  // geometry walk: buffer sizes and the stage outputs
+  size_t max_x = 0, max_qkv = 0, max_hid = 0, max_short = 0, max_xn = 0, max_att = 0;
+  {
+    int grid = g0, stage = 0;
+    for (int i = 0; i < cfg->n_blocks; ++i) {
+      const ovo_hiera_block& b = s->blocks[i];
+      const size_t T = static_cast<size_t>(grid) * grid;
+      const int go = b.q_pool ? grid / 2 : grid;
+      const size_t To = static_cast<size_t>(go) * go;
+      max_x = std::max({max_x, T * b.dim, To * b.dim_out});
+      max_xn = std::max({max_xn, T * b.dim, To * b.dim_out});
+      max_qkv = std::max(max_qkv, T * 3 * b.dim_out);
+      max_att = std::max(max_att, To * b.dim_out);
+      max_hid = std::max(max_hid, To * 4 * b.dim_out);
+      if (b.short_w) max_short = std::max(max_short, T * b.dim_out);
+      grid = go;
+      if (stage < 4 && i == cfg->stage_end[stage]) { s->stage_grid[stage] = grid; s->stage_dim[stage] = b.dim_out; ++stage; }
+    }
+    if (stage != 4 || s->stage_grid[2] != g || s->stage_grid[3] != g / 2 || s->stage_grid[1] != 2 * g || s->stage_grid[0] != 4 * g) {
+      delete s;
+      return set_error(OVO_E_INVALID, "ovo_sam_create: the trunk must have four stages at strides 4/8/16/32");
+    }
+  }
+  int r = OVO_OK;
+  auto A = [&](auto** p, size_t n) { if (r == OVO_OK) r = salloc(s, p, n); };
+  A(&s->tmp, static_cast<size_t>(3) * max_h * S); A(&s->pixels, static_cast<size_t>(3) * S * S);
+  A(&s->patches, static_cast<size_t>(g0) * g0 * w->patch_kpad);
+  A(&s->xa, max_x); A(&s->xb, max_x); A(&s->tshort, max_short); A(&s->xn, max_xn); A(&s->qkv, max_qkv); A(&s->att, max_att); A(&s->hid, max_hid);
+  for (int k = 0; k < 4; ++k) A(&s->stage_bf[k], static_cast<size_t>(s->stage_grid[k]) * s->stage_grid[k] * s->stage_dim[k]);
+  const size_t HW = static_cast<size_t>(g) * g;
+  A(&s->lat3, HW / 4 * kC); A(&s->lat2, HW * kC); A(&s->embed, HW * kC); A(&s->feat_s0, 16 * HW * 32); A(&s->feat_s1, 4 * HW * 64);
+  A(&s->s0_sub, 16 * HW * 32); A(&s->s1_sub, 4 * HW * 64); A(&s->src, HW * kC); A(&s->src_bf, HW * kC); A(&s->srcpe_bf, HW * kC);
+  A(&s->k0, HW * kInt); A(&s->v0, HW * kInt); A(&s->qi0, HW * kInt);
+  const size_t P = max_prompts, R = P * kTok;
+  A(&s->tokens, R * kC); A(&s->queries, R * kC); A(&s->tq_tmp, R * kC); A(&s->tq_bf, R * kC); A(&s->tqpe_bf, R * kC);
+  A(&s->t_q, R * kC); A(&s->t_k, R * kC); A(&s->t_v, R * kC); A(&s->t_o, R * kC); A(&s->t_mlp, R * 2048);
+  A(&s->keys, P * HW * kC); A(&s->keys_pre, P * HW * kC); A(&s->keys_bf, P * HW * kC); A(&s->keyspe_bf, P * HW * kC);
+  A(&s->big_q, P * HW * kInt); A(&s->big_k, P * HW * kInt); A(&s->big_v, P * HW * kInt);
+  A(&s->up1, P * HW * 4 * 64); A(&s->up2, P * HW * 16 * 32);
+  A(&s->hyper, P * 4 * 32); A(&s->iou_head, P * 4); A(&s->tok_a, P * kC); A(&s->tok_b, P * kC);
+  A(&s->stats, P * 3); A(&s->cand, P * 3); A(&s->sel, P * 3);
+  A(&s->low_all, P * 3 * 16 * HW); A(&s->iou_all, P * 3); A(&s->points, P * 2);
+  A(&s->score_tmp, P * 3); A(&s->keep_tmp, P * 3); A(&s->stab_tmp, P * 3); A(&s->iou_tmp, P * 3); A(&s->box_tmp, P * 3 * 4);
+  A(&s->src_tmp, P * 3); A(&s->order_tmp, P * 3); A(&s->counters, 4);
+  if (r != OVO_OK) { ovo_sam_destroy(s); return r; }
+  s->dc1 = s->keys_pre;   // [P*HW, 256] f32: the transposed-conv output reuses the pre-LayerNorm key buffer
+  *out = s;
+  return OVO_OK;
+}
+
+void ovo_sam_destroy(ovo_sam_t* s) {
+  if (!s) return;
+  for (void* p : s->owned) cudaFree(p);
+  for (void* p : {static_cast<void*>(s->xmin), static_cast<void*>(s->xsize), static_cast<void*>(s->ymin), static_cast<void*>(s->ysize),
+                  static_cast<void*>(s->xw), static_cast<void*>(s->yw), static_cast<void*>(s->masks_tmp), static_cast<void*>(s->masks_tmp2)})
+    if (p) cudaFree(p);
+  delete s;
+}
+
+int ovo_sam_set_pixels(ovo_sam_t* s, const float* pixels_dev, float* embed_out, float* s0_out, float* s1_out, int n_blocks,
+                       float* block_out, void* stream_) {
+  OVO_REQUIRE(s && pixels_dev, "ovo_sam_set_pixels: null argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  OVO_CUDA(cudaMemcpyAsync(s->pixels, pixels_dev, sizeof(float) * 3 * s->S * s->S, cudaMemcpyDeviceToDevice, st));
+  OVO_TRY(patches_from_pixels(s, st));
+  OVO_TRY(run_trunk(s, n_blocks, block_out, st));
+  if (n_blocks < 0 || n_blocks >= s->cfg.n_blocks) OVO_TRY(copy_taps(s, embed_out, s0_out, s1_out, st));
+  return OVO_OK;
+}
+
+int ovo_sam_set_image(ovo_sam_t* s, const uint8_t* rgb_dev, int H, int W, float* pixels_out, float* embed_out, float* s0_out,
+                      float* s1_out, int n_blocks, float* block_out, void* stream_) {
+  OVO_REQUIRE(s && rgb_dev, "ovo_sam_set_image: null argument");
+  OVO_REQUIRE(H > 0 && W > 0 && H <= s->max_h && W <= s->max_w, "ovo_sam_set_image: frame %dx%d exceeds the %dx%d the handle was created for", H, W, s->max_h, s->max_w);
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  const int S = s->S;
+  if (s->tab_h != H || s->tab_w != W) {   // resize tables for this frame size (host, once per size)
+    OVO_CUDA(cudaStreamSynchronize(st));
+    for (void* p : {static_cast<void*>(s->xmin), static_cast<void*>(s->xsize), static_cast<void*>(s->ymin), static_cast<void*>(s->ysize),
+                    static_cast<void*>(s->xw), static_cast<void*>(s->yw)})
+      if (p) cudaFree(p);
+    std::vector<int> mn, sz; std::vector<float> ws;
+    aa_axis(W, S, mn, sz, ws, &s->kx);
+    OVO_TRY(dalloc(&s->xmin, S)); OVO_TRY(dalloc(&s->xsize, S)); OVO_TRY(dalloc(&s->xw, ws.size()));
+    OVO_CUDA(cudaMemcpy(s->xmin, mn.data(), sizeof(int) * S, cudaMemcpyHostToDevice));
+    OVO_CUDA(cudaMemcpy(s->xsize, sz.data(), sizeof(int) * S, cudaMemcpyHostToDevice));
+    OVO_CUDA(cudaMemcpy(s->xw, ws.data(), sizeof(float) * ws.size(), cudaMemcpyHostToDevice));
+    aa_axis(H, S, mn, sz, ws, &s->ky);
+    OVO_TRY(dalloc(&s->ymin, S)); OVO_TRY(dalloc(&s->ysize, S)); OVO_TRY(dalloc(&s->yw, ws.size()));
+    OVO_CUDA(cudaMemcpy(s->ymin, mn.data(), sizeof(int) * S, cudaMemcpyHostToDevice));
+    OVO_CUDA(cudaMemcpy(s->ysize, sz.data(), sizeof(int) * S, cudaMemcpyHostToDevice));
+    OVO_CUDA(cudaMemcpy(s->yw, ws.data(), sizeof(float) * ws.size(), cudaMemcpyHostToDevice));
+    s->tab_h = H; s->tab_w = W;
+  }
+  {
+    ProfScope prof(st, PROF_PRE, 0.0, static_cast<double>(H) * W * 3 + 3.0 * S * S * 4);
+    sam_resize_h_kernel<<<dim3(ceil_div(S, 128), H), 128, 0, st>>>(rgb_dev, H, W, s->xmin, s->xsize, s->xw, s->kx, S, s->tmp);
+    OVO_CHECK_LAUNCH();
+    sam_resize_v_kernel<<<dim3(ceil_div(S, 128), S, 3), 128, 0, st>>>(s->tmp, H, s->ymin, s->ysize, s->yw, s->ky, S, s->pixels);
+    OVO_CHECK_LAUNCH();
+  }
+  if (pixels_out) OVO_CUDA(cudaMemcpyAsync(pixels_out, s->pixels, sizeof(float) * 3 * S * S, cudaMemcpyDeviceToDevice, st));
+  OVO_TRY(patches_from_pixels(s, st));
+  OVO_TRY(run_trunk(s, n_blocks, block_out, st));
+  if (n_blocks < 0 || n_blocks >= s->cfg.n_blocks) OVO_TRY(copy_taps(s, embed_out, s0_out, s1_out, st));
+  return OVO_OK;
+}
+
+int ovo_sam_predict(ovo_sam_t* s, const float* points_dev, int P, float* low_out, float* iou_out, void* stream_) {
+  OVO_REQUIRE(s && points_dev, "ovo_sam_predict: null argument");
+  OVO_REQUIRE(P > 0 && P <= s->max_p, "ovo_sam_predict: %d prompts, handle sized for %d", P, s->max_p);
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  const int g = s->g, HW = g * g, R = P * kTok;
+  const size_t PHW = static_cast<size_t>(P) * HW;
+  OVO_REQUIRE(PHW * 4 < (1ull << 31), "ovo_sam_predict: too many prompts for 32-bit GEMM row indices");
+  sam_tokens_kernel<<<P, 256, 0, st>>>(points_dev, P, static_cast<float>(s->S), s->w.gauss, s->w.point_embed, s->w.not_a_point, s->w.out_tokens, s->tokens);
+  OVO_CHECK_LAUNCH();
+  const int depth = s->cfg.decoder_depth;
+  for (int l = 0; l < depth; ++l) {
+    const ovo_sam_dec_layer& L = s->layers[l];
+    // (1) token self attention (sam/transformer.py:183-190)
+    if (l == 0) {
+      OVO_TRY(add_cast(s->tokens, nullptr, 1, kC, static_cast<size_t>(R) * kC, s->tq_bf, nullptr, st));
+      OVO_TRY(tok_lin(s, s->tq_bf, L.self_attn.q_w, L.self_attn.q_b, R, kC, kC, s->t_q, st));
+      OVO_TRY(tok_lin(s, s->tq_bf, L.self_attn.k_w, L.self_attn.k_b, R, kC, kC, s->t_k, st));
+    } else {
+      OVO_TRY(add_cast(s->queries, s->tokens, R, kC, static_cast<size_t>(R) * kC, s->tqpe_bf, nullptr, st));
+      OVO_TRY(tok_lin(s, s->tqpe_bf, L.self_attn.q_w, L.self_attn.q_b, R, kC, kC, s->t_q, st));
+      OVO_TRY(tok_lin(s, s->tqpe_bf, L.self_attn.k_w, L.self_attn.k_b, R, kC, kC, s->t_k, st));
+    }
+    OVO_TRY(tok_lin(s, s->tq_bf, L.self_attn.v_w, L.self_attn.v_b, R, kC, kC, s->t_v, st));
+    sam_self_attn_kernel<<<P, 256, 0, st>>>(s->t_q, s->t_k, s->t_v, s->t_o);
+    OVO_CHECK_LAUNCH();
+    OVO_TRY(gemm(l == 0 ? EPI_F32 : EPI_F32_RESID, s->t_o, kC, L.self_attn.o_w, kC, R, kC, kC, L.self_attn.o_b, s->tq_tmp, kC,
+                 l == 0 ? nullptr : s->queries, kC, 0, st));
+    OVO_TRY(ln(s->tq_tmp, R, kC, L.norm_w[0], L.norm_b[0], 1e-5f, s->queries, s->tq_bf, nullptr, nullptr, 1, st));
+    // (2) token -> image cross attention (:192-197)
+    if (l == 0) {
+      OVO_TRY(t2i_block(s, L.t2i, s->k0, s->v0, 0, P, L.norm_w[1], L.norm_b[1], st));
+    } else {
+      OVO_TRY(gemm(EPI_BF16, s->keyspe_bf, kC, L.t2i.k_w, kC, static_cast<int>(PHW), kInt, kC, L.t2i.k_b, s->big_k, kInt, nullptr, 0, 0, st));
+      OVO_TRY(gemm(EPI_BF16, s->keys_bf, kC, L.t2i.v_w, kC, static_cast<int>(PHW), kInt, kC, L.t2i.v_b, s->big_v, kInt, nullptr, 0, 0, st));
+      OVO_TRY(t2i_block(s, L.t2i, s->big_k, s->big_v, static_cast<size_t>(HW) * kInt, P, L.norm_w[1], L.norm_b[1], st));
+    }
+    // (3) MLP on the tokens (:199-202)
+    OVO_TRY(gemm(EPI_BF16_RELU, s->tq_bf, kC, L.mlp0_w, kC, R, 2048, kC, L.mlp0_b, s->t_mlp, 2048, nullptr, 0, 0, st));
+    OVO_TRY(gemm(EPI_F32_RESID, s->t_mlp, 2048, L.mlp1_w, 2048, R, kC, 2048, L.mlp1_b, s->tq_tmp, kC, s->queries, kC, 0, st));
+    OVO_TRY(ln(s->tq_tmp, R, kC, L.norm_w[2], L.norm_b[2], 1e-5f, s->queries, s->tq_bf, nullptr, nullptr, 1, st));
+    // (4) image -> token cross attention (:204-210)
+    OVO_TRY(add_cast(s->queries, s->tokens, R, kC, static_cast<size_t>(R) * kC, s->tqpe_bf, nullptr, st));
+    OVO_TRY(tok_lin(s, s->tqpe_bf, L.i2t.k_w, L.i2t.k_b, R, kInt, kC, s->t_k, st));
+    OVO_TRY(tok_lin(s, s->tq_bf, L.i2t.v_w, L.i2t.v_b, R, kInt, kC, s->t_v, st));
+    const __nv_bfloat16* qsrc = s->qi0;
+    size_t qstride = 0;
+    if (l > 0) {
+      OVO_TRY(gemm(EPI_BF16, s->keyspe_bf, kC, L.i2t.q_w, kC, static_cast<int>(PHW), kInt, kC, L.i2t.q_b, s->big_q, kInt, nullptr, 0, 0, st));
+      qsrc = s->big_q; qstride = static_cast<size_t>(HW) * kInt;
+    }
+    {
+      ProfScope prof(st, PROF_ATTN, 4.0 * static_cast<double>(PHW) * 8 * kTok * 16, 0.0);
+      sam_i2t_attn_kernel<<<dim3(ceil_div(HW * 8, 256), P), 256, 0, st>>>(qsrc, qstride, s->t_k, s->t_v, HW, s->big_k /* out */);
+      OVO_CHECK_LAUNCH();
+    }
+    OVO_TRY(gemm(EPI_F32_RESID, s->big_k, kInt, L.i2t.o_w, kInt, static_cast<int>(PHW), kC, kInt, L.i2t.o_b, s->keys_pre, kC,
+                 l == 0 ? s->src : s->keys, kC, l == 0 ? HW : 0, st));
+    OVO_TRY(ln(s->keys_pre, static_cast<int>(PHW), kC, L.norm_w[3], L.norm_b[3], 1e-5f, s->keys, s->keys_bf, s->keyspe_bf, s->w.dense_pe, HW, st));
+  }
+  // final token -> image attention + norm (sam/transformer.py:124-132)
+  OVO_TRY(gemm(EPI_BF16, s->keyspe_bf, kC, s->w.final_attn.k_w, kC, static_cast<int>(PHW), kInt, kC, s->w.final_attn.k_b, s->big_k, kInt, nullptr, 0, 0, st));
+  OVO_TRY(gemm(EPI_BF16, s->keys_bf, kC, s->w.final_attn.v_w, kC, static_cast<int>(PHW), kInt, kC, s->w.final_attn.v_b, s->big_v, kInt, nullptr, 0, 0, st));
+  OVO_TRY(t2i_block(s, s->w.final_attn, s->big_k, s->big_v, static_cast<size_t>(HW) * kInt, P, s->w.norm_final_w, s->w.norm_final_b, st));
+  // hs = s->queries.  Upscaling (mask_decoder.py:210-217): two k2 s2 transposed convs as GEMMs with N = 4*C_out
+  OVO_TRY(gemm(EPI_F32_RESID, s->keys_bf, kC, s->w.up0_w, kC, static_cast<int>(PHW), 256, kC, s->w.up0_b, s->dc1, 256, s->s1_sub, 256, HW, st));
+  sam_up1_kernel<<<ceil_div(static_cast<long long>(PHW) * 4, 8), 256, 0, st>>>(s->dc1, PHW * 4, s->w.up_ln_w, s->w.up_ln_b, s->up1);
+  OVO_CHECK_LAUNCH();
+  OVO_TRY(gemm(EPI_BF16_GELU, s->up1, 64, s->w.up1_w, 64, static_cast<int>(PHW * 4), 128, 64, s->w.up1_b, s->up2, 128, s->s0_sub, 128, 4 * HW, st));
+  // hypernetwork MLPs on the 4 mask tokens (:219-224) and the IoU head (:229)
+  for (int i = 0; i < 4; ++i) {
+    sam_pick_token_kernel<<<ceil_div(P * kC, 256), 256, 0, st>>>(s->queries, P, 2 + i, s->tok_a);
+    OVO_CHECK_LAUNCH();
+    OVO_TRY(gemm(EPI_BF16_RELU, s->tok_a, kC, s->w.hyper_w[i][0], kC, P, kC, kC, s->w.hyper_b[i][0], s->tok_b, kC, nullptr, 0, 0, st));
+    OVO_TRY(gemm(EPI_BF16_RELU, s->tok_b, kC, s->w.hyper_w[i][1], kC, P, kC, kC, s->w.hyper_b[i][1], s->tok_a, kC, nullptr, 0, 0, st));
+    OVO_TRY(gemm(EPI_F32, s->tok_a, kC, s->w.hyper_w[i][2], kC, P, 32, kC, s->w.hyper_b[i][2], s->hyper + i * 32, 128, nullptr, 0, 0, st));
+  }
+  sam_pick_token_kernel<<<ceil_div(P * kC, 256), 256, 0, st>>>(s->queries, P, 1, s->tok_a);
+  OVO_CHECK_LAUNCH();
+  OVO_TRY(gemm(EPI_BF16_RELU, s->tok_a, kC, s->w.iou_w[0], kC, P, 256, kC, s->w.iou_b[0], s->tok_b, 256, nullptr, 0, 0, st));
+  OVO_TRY(gemm(EPI_BF16_RELU, s->tok_b, 256, s->w.iou_w[1], 256, P, 256, 256, s->w.iou_b[1], s->tok_a, 256, nullptr, 0, 0, st));
+  OVO_TRY(gemm(EPI_F32, s->tok_a, 256, s->w.iou_w[2], 256, P, 4, 256, s->w.iou_b[2], s->iou_head, 4, nullptr, 0, 0, st));
+  float* low = low_out ? low_out : s->low_all;
+  float* iou = iou_out ? iou_out : s->iou_all;
+  {
+    ProfScope prof(st, PROF_OTHER, 0.0, 0.0);
+    sam_mask_dot_kernel<<<dim3(ceil_div(16 * HW, 256), P), 256, 0, st>>>(s->up2, s->hyper, g, low);
+    OVO_CHECK_LAUNCH();
+    sam_iou_kernel<<<ceil_div(P * 3, 256), 256, 0, st>>>(s->iou_head, P, iou);
+    OVO_CHECK_LAUNCH();
+  }
+  return OVO_OK;
+}
+
+
+int ovo_sam_postprocess(ovo_sam_t* s, const float* low_dev, const float* iou_dev, int P, int h, int w, int H, int W,
+                        const ovo_amg_params* prm, uint8_t* masks_out, float* iou_out, float* stab_out, int32_t* boxes_out,
+                        int32_t* src_out, int max_out, int* n_out, void* stream_) {
+  OVO_REQUIRE(s && low_dev && iou_dev && prm && masks_out && iou_out && stab_out && boxes_out && src_out && n_out, "ovo_sam_postprocess: null argument");
+  OVO_REQUIRE(P > 0 && P <= s->max_p && P * 3 <= 1024, "ovo_sam_postprocess: %d prompts unsupported (at most %d and 341)", P, s->max_p);
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  const int n = P * 3;
+  ProfScope prof(st, PROF_OTHER, 0.0, 0.0);
+  amg_candidates_kernel<<<1, 1024, 0, st>>>(iou_dev, n, prm->pred_iou_thresh, s->cand, s->counters);
+  OVO_CHECK_LAUNCH();
+  int counts[2] = {0, 0};
+  OVO_CUDA(cudaMemcpyAsync(counts, s->counters, sizeof(int), cudaMemcpyDeviceToHost, st));
+  OVO_CUDA(cudaStreamSynchronize(st));
+  const int n_cand = counts[0];
+  if (n_cand == 0) { *n_out = 0; return OVO_OK; }
+  amg_stats_init_kernel<<<ceil_div(n_cand, 256), 256, 0, st>>>(s->stats, n_cand, H, W);
+  OVO_CHECK_LAUNCH();
+  const int tiles = std::max(1, std::min(ceil_div(H * W, 256 * 8), 64));
+  amg_stats_kernel<<<dim3(tiles, n_cand), 256, 0, st>>>(low_dev, s->cand, h, w, H, W, prm->stability_offset, s->stats);
+  OVO_CHECK_LAUNCH();
+  amg_decide_kernel<<<1, 1024, 0, st>>>(s->stats, s->cand, iou_dev, prm->stability_thresh, prm->box_nms_thresh, s->counters, s->sel,
+                                       iou_out, stab_out, boxes_out, src_out, max_out);
+  OVO_CHECK_LAUNCH();
+  OVO_CUDA(cudaMemcpyAsync(counts, s->counters, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  OVO_CUDA(cudaStreamSynchronize(st));
+  const int K = counts[1];
+  OVO_REQUIRE(K <= max_out, "ovo_sam_postprocess: %d masks survive, room for %d", K, max_out);
+  *n_out = K;
+  if (K == 0) return OVO_OK;
+  amg_write_masks_kernel<<<dim3(tiles, K), 256, 0, st>>>(low_dev, s->sel, h, w, H, W, masks_out);
+  OVO_CHECK_LAUNCH();
+  return OVO_OK;
+}
+
+int ovo_sam_generate(ovo_sam_t* s, const uint8_t* rgb_dev, int H, int W, const ovo_amg_params* prm, int32_t* seg_map_dev,
+                     uint8_t* masks_out_dev, int max_masks, int* n_masks, void* stream_) {
+  OVO_REQUIRE(s && rgb_dev && prm && seg_map_dev && masks_out_dev && n_masks, "ovo_sam_generate: null argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  const int n = prm->points_per_side, P = n * n;
+  OVO_REQUIRE(n > 0 && P <= s->max_p && P * 3 <= 1024, "ovo_sam_generate: points_per_side %d unsupported (handle sized for %d prompts)", n, s->max_p);
+  OVO_REQUIRE((static_cast<size_t>(H) * W) % 16 == 0, "ovo_sam_generate: H*W must be a multiple of 16");
+  OVO_TRY(ovo_sam_set_image(s, rgb_dev, H, W, nullptr, nullptr, nullptr, nullptr, -1, nullptr, stream_));
+  amg_points_kernel<<<ceil_div(P, 128), 128, 0, st>>>(n, H, W, static_cast<float>(s->S), s->points);
+  OVO_CHECK_LAUNCH();
+  // every filter of the AMG is per mask, so all prompts go through the decoder in one batch (the reference's batches of 64
+  // only bound its memory, automatic_mask_generator.py:270-276)
+  OVO_TRY(ovo_sam_predict(s, s->points, P, s->low_all, s->iou_all, stream_));
+  const size_t need = static_cast<size_t>(P) * 3 * H * W;
+  if (s->masks_tmp_bytes < need) {
+    OVO_CUDA(cudaStreamSynchronize(st));
+    if (s->masks_tmp) cudaFree(s->masks_tmp);
+    if (s->masks_tmp2) cudaFree(s->masks_tmp2);
+    s->masks_tmp = nullptr; s->masks_tmp2 = nullptr; s->masks_tmp_bytes = 0;
+    OVO_TRY(dalloc(&s->masks_tmp, need)); OVO_TRY(dalloc(&s->masks_tmp2, need));
+    s->masks_tmp_bytes = need;
+  }
+  int K = 0;
+  OVO_TRY(ovo_sam_postprocess(s, s->low_all, s->iou_all, P, 4 * s->g, 4 * s->g, H, W, prm, s->masks_tmp, s->iou_tmp, s->stab_tmp, s->box_tmp,
+                              s->src_tmp, P * 3, &K, stream_));
+  *n_masks = 0;
+  if (K == 0) return OVO_OK;
+  // OVO's second stage (mask_generator.py:113-119): masks_update (score = stability * predicted_iou) then mask2segmap
+  mul_kernel<<<ceil_div(K, 256), 256, 0, st>>>(s->stab_tmp, s->iou_tmp, K, s->score_tmp);
+  OVO_CHECK_LAUNCH();
+  OVO_TRY(ovo_mask_nms(s->masks_tmp, s->score_tmp, K, H, W, prm->nms_iou_th, prm->nms_score_th, prm->nms_inner_th, s->keep_tmp, stream_));
+  std::vector<uint8_t> keep(K);
+  OVO_CUDA(cudaMemcpyAsync(keep.data(), s->keep_tmp, K, cudaMemcpyDeviceToHost, st));
+  OVO_CUDA(cudaStreamSynchronize(st));
+  std::vector<int> idx;
+  for (int i = 0; i < K; ++i) if (keep[i]) idx.push_back(i);
+  const int M = static_cast<int>(idx.size());
+  OVO_REQUIRE(M <= max_masks, "ovo_sam_generate: %d masks, room for %d", M, max_masks);
+  if (M == 0) return OVO_OK;
+  OVO_CUDA(cudaMemcpyAsync(s->order_tmp, idx.data(), sizeof(int) * M, cudaMemcpyHostToDevice, st));
+  const size_t npix16 = static_cast<size_t>(H) * W / 16;
+  gather_masks_kernel<<<dim3(std::min<int>(64, ceil_div(static_cast<long long>(npix16), 256)), M), 256, 0, st>>>(s->masks_tmp, s->order_tmp, npix16, s->masks_tmp2);
+  OVO_CHECK_LAUNCH();
+  // stability of the kept masks, same order
+  std::vector<float> stab(K);
+  OVO_CUDA(cudaMemcpyAsync(stab.data(), s->stab_tmp, sizeof(float) * K, cudaMemcpyDeviceToHost, st));
+  OVO_CUDA(cudaStreamSynchronize(st));
+  std::vector<float> stab_kept(M);
+  for (int i = 0; i < M; ++i) stab_kept[i] = stab[idx[i]];
+  OVO_CUDA(cudaMemcpyAsync(s->score_tmp, stab_kept.data(), sizeof(float) * M, cudaMemcpyHostToDevice, st));
+  OVO_TRY(ovo_mask2segmap(s->masks_tmp2, s->score_tmp, M, H, W, seg_map_dev, masks_out_dev, s->src_tmp, stream_));
+  OVO_CUDA(cudaStreamSynchronize(st));   // idx / stab_kept are host temporaries of this call
+  *n_masks = M;
+  return OVO_OK;
+}
+
+}  // extern "C"
