@@ -746,7 +746,7 @@ int run_trunk(ovo_sam* s, int n_blocks, float* block_out, cudaStream_t st) {
     OVO_REQUIRE(b.grid_in == grid, "sam block %d: grid mismatch", i);
     const int T = grid * grid;
     const int ws = b.window > 0 ? b.window : grid;
-    OVO_REQUIRE(grid % ws == 0 && (ws * ws) % 16 == 0 && (!b.q_pool || ((ws / 2) * (ws / 2)) % 16 == 0), "sam block %d: unsupported window %d on grid %d", i, ws, grid);
+    OVO_REQUIRE(grid % ws == 0 && (ws * ws) % 16 == 0 && (!b.q_pool || ws % 2 == 0), "sam block %d: unsupported window %d on grid %d", i, ws, grid);
     OVO_REQUIRE(b.dim_out == b.heads * kSamHd, "sam block %d: head_dim must be 72", i);
     OVO_TRY(ln(x, T, b.dim, b.norm1_w, b.norm1_b, c.trunk_ln_eps, nullptr, s->xn, nullptr, nullptr, 1, st));
     const float* resid = x;

@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(128) hiera_attention_kernel(WinAttnParams p) {
   }
   __syncthreads();
 
-  const bool active = q0 + warp * 16 < nq;   // warp uniform; nq is a multiple of 16
+  const bool active = q0 + warp * 16 < nq;   // warp uniform; rows >= nq of the last tile are zero padding
   uint32_t qf[5][4];
   if (active) {
 #pragma unroll
@@ -192,6 +192,7 @@ __global__ void __launch_bounds__(128) hiera_attention_kernel(WinAttnParams p) {
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     const int qi = q0 + warp * 16 + g + 8 * h;
+    if (qi >= nq) continue;
     const int qy = qi / wsq, qx = qi - qy * wsq;
     const size_t row = static_cast<size_t>(wy * wsq + qy) * grid_out + wx * wsq + qx;
     __nv_bfloat16* dst = p.out + row * p.dim_out + head * kSamHd + 2 * t4;
