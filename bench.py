@@ -30,6 +30,8 @@ sys.path.insert(0, ROOT)
 
 H, W, N_MASK_ROWS, N_MASK_COLS, Q = 480, 640, 6, 8, 20
 GFLOP_PER_IMAGE = 349.2          # PE-Core-L14-336 forward_features, SURVEY §6 / BASELINE.md §2
+SAM_GFLOP_ENCODER = 1619.7       # SAM-2.1 Hiera-L forward_image @1024^2, SURVEY §6
+SAM_GFLOP_DECODER = 4 * 232.9    # 256 point prompts (4 batches of 64 in the reference), SURVEY §6
 
 
 def peaks():
@@ -211,6 +213,9 @@ def run_ours(args, rank, world, local_rank):
              "roofline": {"bound": "hbm", "achieved": round(qgbs, 1), "peak": hbm, "unit": "GB/s", "frac": round(qgbs / hbm, 4),
                           "traffic": None, "peak_source": f"{how} hbm_gbs", "algorithmic_bytes": qbytes}}
 
+    # --- SAM-2 mask proposal stage (reported as a separate stage; the headline uses the precomputed-mask seam)
+    sam = None if args.no_sam else run_sam_stage(args, dev, ms_step / F, tf_sus, how)
+
     # --- e2e through the public OVO API, host inputs, per keyframe
     e2e = run_e2e(args, rank, world, dev, enc, K, xyz, ids, ins, seg, bm, fr, dist)
 
@@ -227,9 +232,63 @@ def run_ours(args, rank, world, local_rank):
                       "l2_policy": "inputs larger than L2: per step 0.63 GB weights + ~2 GB map/bank traffic per keyframe (L2 126 MB)"},
            "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e, "roofline": roofline, "query": query,
            "n_matched_points_per_keyframe": int(state["n_matched"])}
+    if sam is not None:
+        out["sam"] = sam
     if not args.no_cpu_baseline and world >= 1:
         out["cpu_baseline"] = cpu_baseline(args, budget_frames=1)
     print(json.dumps(out))
+
+
+def run_sam_stage(args, dev, clip_fusion_ms_per_keyframe, tf_sus, how):
+    """SAM-2.1 Hiera-L automatic mask generation (16x16 point grid, ovo.yaml:32) on one 640x480 frame: image resident in
+    HBM, CUDA events, per-kernel-class breakdown.  Random-init weights, so the AMG thresholds are set where a few dozen
+    masks survive (the stock 0.8 / 0.95 reject everything a random network proposes); the network work is unchanged."""
+    from ovo_b200 import _lib
+    from ovo_b200.sam import Sam2
+    from ovo_b200.sam_config import SamConfig, random_state_dict
+    cfg = SamConfig()
+    sam = Sam2(cfg, random_state_dict(cfg, seed=0), max_h=H, max_w=W, max_prompts=256, device=dev)
+    rng = np.random.default_rng(5)
+    coarse = rng.integers(0, 256, (H // 40, W // 40, 3))
+    img = torch.from_numpy(np.clip(np.kron(coarse, np.ones((40, 40, 1))) + rng.normal(0, 12, (H, W, 3)), 0, 255).astype(np.uint8)).to(dev)
+    prm = sam.amg_params(points_per_side=16, pred_iou_thresh=0.45, stability_score_thresh=0.4, box_nms_thresh=0.9999, nms_score_th=0.2)
+
+    def t(fn, n=10):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / n
+
+    pts = torch.empty(256, 2, device=dev)
+    g = torch.linspace(1 / 32, 1 - 1 / 32, 16, device=dev) * cfg.image_size
+    pts[:, 0], pts[:, 1] = g.repeat(16), g.repeat_interleave(16)
+    ms_img = t(lambda: sam.set_image(img))
+    ms_dec = t(lambda: sam.predict(pts))
+    ms_gen = t(lambda: sam.generate(img, prm))
+    seg, maps = sam.generate(img, prm)
+    _lib.profile_begin()
+    sam.generate(img, prm)
+    torch.cuda.synchronize()
+    prof = _lib.profile_report()
+    gf = SAM_GFLOP_ENCODER + SAM_GFLOP_DECODER
+    g_ = prof["gemm"]
+    del sam
+    torch.cuda.empty_cache()
+    return {"metric": "SAM-2.1 Hiera-L automatic mask generation, 640x480, 16x16 point prompts", "ms_per_frame": round(ms_gen, 3),
+            "frames_per_s": round(1e3 / ms_gen, 2), "set_image_ms": round(ms_img, 3), "decoder_256_prompts_ms": round(ms_dec, 3),
+            "algorithmic_gflop": gf, "algorithmic_tflops": round(gf / ms_gen, 1), "masks_kept": int(maps.shape[0]),
+            "breakdown_ms": {k: round(v["ms"], 4) for k, v in prof.items() if v["launches"]},
+            "gemm_tflops": round(g_["flops"] / max(g_["ms"], 1e-9) / 1e9, 1), "launches": int(sum(v["launches"] for v in prof.values())),
+            "roofline": {"bound": "tensor", "achieved": round(gf / ms_gen, 1), "peak": tf_sus, "unit": "TFLOP/s",
+                         "frac": round(gf / ms_gen / tf_sus, 4), "peak_source": f"{how} bf16_tflops_sustained",
+                         "note": "whole stage (GEMMs + windowed attention + HBM-bound decoder tensors) against the tensor peak"},
+            "keyframes_per_s_with_online_sam": round(1e3 / (clip_fusion_ms_per_keyframe + ms_gen), 2)}
 
 
 def run_e2e(args, rank, world, dev, enc, K, xyz, ids, ins, seg, bm, fr, dist):
@@ -379,6 +438,7 @@ def main():
     ap.add_argument("--frames-per-step", type=int, default=8)
     ap.add_argument("--points", type=int, default=2_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sam", action="store_true", help="skip the SAM-2 stage report")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", 0))

@@ -384,6 +384,10 @@ void ovo_set_gemm_cluster(int cluster_size);
 int ovo_gemm_bf16(const void* A_dev, int lda, const void* B_dev, int ldb, int M, int N, int K,
                   const float* bias_dev, float* C_dev, int ldc, int force_bn, void* stream);
 
+/* Measurement tap: average time of `iters` launches of the GEMM with a fused epilogue (0 f32, 1 bf16, 2 bf16+GELU,
+ * 3 f32+residual, 6 bf16+ReLU) on synthetic operands, CUDA events on `stream`. */
+int ovo_gemm_bench(int epi, int M, int N, int K, int force_bn, int iters, float* ms_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

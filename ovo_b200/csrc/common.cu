@@ -230,4 +230,37 @@ int ovo_gemm_bf16(const void* A_dev, int lda, const void* B_dev, int ldb, int M,
                           static_cast<cudaStream_t>(stream), force_bn);
 }
 
+
+// Tuning / measurement tap: times `iters` launches of C = A.B^T with the given fused epilogue on synthetic operands
+// (0 f32, 1 bf16, 2 bf16+GELU, 3 f32+residual, 6 bf16+ReLU) with CUDA events on `stream`; *ms_out = average per launch.
+int ovo_gemm_bench(int epi, int M, int N, int K, int force_bn, int iters, float* ms_out, void* stream_) {
+  using namespace ovo;
+  OVO_REQUIRE(M > 0 && N > 0 && K > 0 && K % 8 == 0 && iters > 0 && ms_out, "ovo_gemm_bench: bad arguments");
+  OVO_REQUIRE(epi == EPI_F32 || epi == EPI_BF16 || epi == EPI_BF16_GELU || epi == EPI_F32_RESID || epi == EPI_BF16_RELU, "ovo_gemm_bench: epilogue %d unsupported", epi);
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  __nv_bfloat16 *A = nullptr, *B = nullptr; float *bias = nullptr, *resid = nullptr; void* out = nullptr;
+  const int ldo = (N + 7) / 8 * 8;
+  OVO_CUDA(cudaMalloc(&A, sizeof(__nv_bfloat16) * M * (size_t)K)); OVO_CUDA(cudaMalloc(&B, sizeof(__nv_bfloat16) * N * (size_t)K));
+  OVO_CUDA(cudaMalloc(&bias, sizeof(float) * ldo)); OVO_CUDA(cudaMalloc(&resid, sizeof(float) * M * (size_t)ldo)); OVO_CUDA(cudaMalloc(&out, sizeof(float) * M * (size_t)ldo));
+  OVO_CUDA(cudaMemsetAsync(A, 0x3c, sizeof(__nv_bfloat16) * M * (size_t)K, st)); OVO_CUDA(cudaMemsetAsync(B, 0x3c, sizeof(__nv_bfloat16) * N * (size_t)K, st));
+  OVO_CUDA(cudaMemsetAsync(bias, 0, sizeof(float) * ldo, st)); OVO_CUDA(cudaMemsetAsync(resid, 0, sizeof(float) * M * (size_t)ldo, st));
+  EpiParams ep;
+  ep.out = out; ep.ldo = ldo; ep.bias = bias; ep.prof_cls = PROF_GEMM;
+  if (epi == EPI_F32_RESID) { ep.resid = resid; ep.ldr = ldo; }
+  int rc = OVO_OK;
+  for (int i = 0; i < 3 && rc == OVO_OK; ++i) rc = launch_gemm(epi, A, K, B, K, M, N, K, ep, st, force_bn);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  cudaEventRecord(e0, st);
+  for (int i = 0; i < iters && rc == OVO_OK; ++i) rc = launch_gemm(epi, A, K, B, K, M, N, K, ep, st, force_bn);
+  cudaEventRecord(e1, st);
+  cudaEventSynchronize(e1);
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  *ms_out = ms / iters;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(A); cudaFree(B); cudaFree(bias); cudaFree(resid); cudaFree(out);
+  return rc;
+}
+
 }  // extern "C"

@@ -44,7 +44,7 @@ struct EpiParams {
   int patches = 0;             // patches per image (576)
   int prof_cls = 0;            // profiling class of this launch (common.cuh ProfClass; host side only)
   int debug = 0;               // tuning experiments: 1 = no epilogue, 2 = no MMA, 4 = no TMA loads, 8 = no GELU math,
-                               // 16 = no global stores, 32 = no bias loads
+                               // 16 = no global stores, 32 = no bias loads, 64 = no residual prefetch
 };
 
 constexpr int kBM = 128;
@@ -206,9 +206,34 @@ __device__ __forceinline__ void stage_exchange(uint8_t* st, int lane, const uint
 }
 
 // One warp handles rows row0..row0+31 (lane = row) x columns col..col+31.  Every lane of the warp must call this.
+// Residual prefetch (EPI_F32_RESID): the 8 float4 a lane adds AFTER the shared-memory exchange (rows row0 + 8i + lane/4,
+// columns col + 16h + 4*(lane&3)) are requested one chunk ahead — the first chunk of a tile while the epilogue warps still
+// wait for the accumulator — so the DRAM/L2 latency of the f32 residual stream hides behind the MMA main loop.
+struct ResidPrefetch {
+  float4 v[8];
+  bool valid;
+};
+__device__ __forceinline__ bool resid_fast_ok(const EpiParams& ep) {
+  return ep.resid != nullptr && (ep.ldo & 3) == 0 && (reinterpret_cast<uintptr_t>(ep.out) & 15) == 0 && (ep.ldr & 3) == 0 &&
+         (reinterpret_cast<uintptr_t>(ep.resid) & 15) == 0;
+}
+__device__ __forceinline__ void resid_prefetch(const EpiParams& ep, int row0, int lane, int col, int M, int N, ResidPrefetch& pf) {
+  pf.valid = (col + 32 <= N);
+  if (!pf.valid) return;
+  const int sub = lane & 3, rsub = lane >> 2;
+#pragma unroll
+  for (int h = 0; h < 2; ++h)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = row0 + 8 * i + rsub;
+      if (r < M)
+        pf.v[h * 4 + i] = *reinterpret_cast<const float4*>(ep.resid + static_cast<size_t>(ep.resid_mod > 0 ? r % ep.resid_mod : r) * ep.ldr + col + 16 * h + 4 * sub);
+    }
+}
+
 template <int EPI>
 __device__ __forceinline__ void epilogue_chunk(const EpiParams& ep, int row0, int lane, int col, const uint32_t (&v)[32],
-                                               int M, int N, const float2* s_rope, uint8_t* st) {
+                                               int M, int N, const float2* s_rope, uint8_t* st, const ResidPrefetch* pf = nullptr) {
   if (col >= N) return;  // warp uniform
   bool fast = (col + 32 <= N);
   if constexpr (EPI == EPI_F32 || EPI == EPI_F32_RESID)
@@ -270,7 +295,8 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& ep, int row0, in
         const int c = col + 16 * h + 4 * sub;
         float4 val = make_float4(__uint_as_float(o[i].x), __uint_as_float(o[i].y), __uint_as_float(o[i].z), __uint_as_float(o[i].w));
         if constexpr (EPI == EPI_F32_RESID) {
-          const float4 rr = *reinterpret_cast<const float4*>(ep.resid + static_cast<size_t>(ep.resid_mod > 0 ? r % ep.resid_mod : r) * ep.ldr + c);
+          const float4 rr = (pf != nullptr && pf->valid) ? pf->v[h * 4 + i]
+                                                         : *reinterpret_cast<const float4*>(ep.resid + static_cast<size_t>(ep.resid_mod > 0 ? r % ep.resid_mod : r) * ep.ldr + c);
           val.x += rr.x; val.y += rr.y; val.z += rr.z; val.w += rr.w;
         }
         *reinterpret_cast<float4*>(static_cast<float*>(ep.out) + static_cast<size_t>(r) * ep.ldo + c) = val;
@@ -464,15 +490,33 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     int acc = 0, acc_phase = 0;
     for (int ct = cluster_id; ct < num_ctiles; ct += num_clusters) {
       const int tm = (ct / tiles_n) * CS + crank, tn = ct % tiles_n;
+      if constexpr (EPI == EPI_F32_RESID) {
+        const bool pre_ok = resid_fast_ok(ep) && !(ep.debug & 64);
+        ResidPrefetch nxt;
+        nxt.valid = false;
+        if (pre_ok) resid_prefetch(ep, tm * kBM + quad * 32, lane, tn * BN + half * 32, M, N, nxt);   // before the accumulator is ready
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = half; c < BN / 32; c += 2) {
+          uint32_t v[32];
+          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + c * 32, v);
+          ResidPrefetch cur = nxt;
+          nxt.valid = false;
+          if (pre_ok && c + 2 < BN / 32) resid_prefetch(ep, tm * kBM + quad * 32, lane, tn * BN + (c + 2) * 32, M, N, nxt);
+          tmem_ld_wait();
+          if (!(ep.debug & 1)) epilogue_chunk<EPI>(ep, tm * kBM + quad * 32, lane, tn * BN + c * 32, v, M, N, s_rope, s_stage + (warp - 2) * 2048, &cur);
+        }
+      } else {
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      const int row = tm * kBM + quad * 32 + lane;
 #pragma unroll 1
       for (int c = half; c < BN / 32; c += 2) {
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + c * 32, v);
         tmem_ld_wait();
         if (!(ep.debug & 1)) epilogue_chunk<EPI>(ep, tm * kBM + quad * 32, lane, tn * BN + c * 32, v, M, N, s_rope, s_stage + (warp - 2) * 2048);
+      }
       }
       tc_fence_before();
       __syncwarp();

@@ -1,9 +1,13 @@
 """`MaskGenerator` with the reference's surface (ovo/entities/mask_generator.py:9-195).
 
-Round-1 scope: the reference's own `sam.precomputed: True` seam (mask_generator.py:94-95,170-195) — masks are
-read from `{frame_id:04d}_seg_map_default.npy` / `_bmap_default.npy` and uploaded.  The SAM-2 Hiera-L mask
-proposal is not built yet; asking for it fails loudly instead of silently doing something
-else."""
+Two sources of masks, as in the reference: the `sam.precomputed: True` seam (mask_generator.py:94-95,170-195) — masks
+read from `{frame_id:04d}_seg_map_default.npy` / `_bmap_default.npy` and uploaded — and the on-line SAM-2 automatic mask
+generator (mask_generator.py:37-53,102-120) running on the device through `ovo_b200.sam.Sam2` (ovo_sam_generate).
+
+Weights: the reference loads `sam{version}_{hiera_large}.pt` from `sam_ckpt_path` (segment_utils.py:269-295).  Here the
+state_dict comes from `config["sam_state_dict"]` (a dict with the reference's key names), from that checkpoint file if it
+exists, or — when `config["sam_random_init"]` is set (benchmarks, tests: no checkpoints are available offline) — from
+seeded random weights of the configured geometry."""
 import os
 from typing import Any, Dict, Tuple
 
@@ -26,10 +30,35 @@ class MaskGenerator:
         self.multi_crop = config.get("multi_crop", False)
         self.device = device
         self.mask_generator = None
-        if not self.precomputed:
-            raise NotImplementedError(
-                "ovo_b200: on-line SAM-2 mask proposal is not built yet (SURVEY K22-K25); run with "
-                "semantic.sam.precomputed: True and masks produced by the reference's MaskGenerator.precompute")
+        if (self.precomputed or config.get("precompute", False)) and os.path.isdir(self.masks_path):
+            pass      # mask_generator.py:31-33: masks already on disk, no network needed
+        elif not self.precomputed:
+            self.load_mask_generator(config)
+
+    def load_mask_generator(self, config: Dict[str, Any]) -> None:
+        """mask_generator.py:37-53 + segment_utils.load_sam (:269-309): SAM-2.1 Hiera-L + the AMG thresholds OVO wires."""
+        from .sam import Sam2
+        from .sam_config import SamConfig, random_state_dict
+        if config.get("sam_version", "2.1") == "":
+            raise NotImplementedError("ovo_b200: SAM-1 (segment_anything, un-vendored in the reference) is not built; use sam_version 2.1")
+        cfg = config.get("sam_config") or SamConfig()
+        sd = config.get("sam_state_dict")
+        if sd is None:
+            ckpt = os.path.join(config.get("sam_ckpt_path", ""), f"sam{config.get('sam_version', '2.1')}_hiera_large.pt")
+            if os.path.exists(ckpt):
+                sd = torch.load(ckpt, map_location="cpu", weights_only=True)
+                sd = sd.get("model", sd)
+            elif config.get("sam_random_init", False):
+                sd = random_state_dict(cfg, seed=int(config.get("sam_seed", 0)))
+            else:
+                raise FileNotFoundError(f"ovo_b200: SAM-2 checkpoint {ckpt} not found (pass sam_state_dict, or sam_random_init for benchmarks)")
+        n = int(config.get("points_per_side", 32))
+        self.mask_generator = Sam2(cfg, sd, max_h=int(config.get("max_h", 968)), max_w=int(config.get("max_w", 1296)),
+                                   max_prompts=n * n, device=self.device)
+        self.amg_params = Sam2.amg_params(points_per_side=n, pred_iou_thresh=config.get("nms_iou_th", 0.8),
+                                          stability_score_thresh=config.get("stability_score_th", 0.95),
+                                          box_nms_thresh=config.get("box_nms_thresh", 0.7),
+                                          nms_iou_th=self.nms_iou_th, nms_score_th=self.nms_score_th, nms_inner_th=self.nms_inner_th)
 
     def to(self, device: str) -> None:
         self.device = device
@@ -42,16 +71,32 @@ class MaskGenerator:
 
     def get_masks(self, image: np.ndarray, frame_id: int | None = None) -> Tuple[torch.Tensor, torch.Tensor]:
         """-> (seg_map [H,W] i32 with -1 = none, binary_maps [N,H,W] bool) on self.device (mask_generator.py:81-99)."""
-        seg_map, binary_maps = self._load_masks(frame_id)
-        return torch.from_numpy(seg_map).to(self.device), torch.from_numpy(binary_maps).to(self.device)
+        if self.precomputed:
+            seg_map, binary_maps = self._load_masks(frame_id)
+            return torch.from_numpy(seg_map).to(self.device), torch.from_numpy(binary_maps).to(self.device)
+        return self.segment_device(image)
+
+    def segment_device(self, image) -> Tuple[torch.Tensor, torch.Tensor]:
+        """segment() without the round trip through host numpy: image HxWx3 uint8 (numpy or device tensor) ->
+        (seg_map [H,W] i32, binary_maps [M,H,W] bool) on the device; empty tensors when no mask survives."""
+        if self.mask_generator is None:
+            raise RuntimeError("ovo_b200: MaskGenerator has no SAM-2 loaded (precomputed masks were configured)")
+        img = image if torch.is_tensor(image) else torch.from_numpy(np.ascontiguousarray(image))
+        if img.dtype != torch.uint8:      # the reference's ToTensor only rescales uint8 input (transforms.py:37-39)
+            raise TypeError("ovo_b200: SAM-2 expects a uint8 HxWx3 image")
+        seg, maps = self.mask_generator.generate(img, self.amg_params, max_masks=int(self.config.get("max_masks", 256)))
+        if maps.shape[0] == 0:
+            return torch.zeros(0, device=maps.device), torch.zeros(0, device=maps.device)
+        return seg, maps
 
     def segment(self, image: np.ndarray):
-        """mask_generator.py:101-120.  The proposal network (SAM-2 automatic mask generator) is not built here; when a
-        `proposal_fn(image) -> list of {segmentation, predicted_iou, stability_score}` is attached (e.g. the
-        reference's own SAM2AutomaticMaskGenerator.generate), its output goes through the native post-processing."""
+        """mask_generator.py:101-120 -> (seg_map, binary_maps) as numpy.  When a `proposal_fn(image) -> list of
+        {segmentation, predicted_iou, stability_score}` is attached (e.g. masks from another proposal network), its output
+        goes through the native post-processing instead of the built-in SAM-2."""
         fn = getattr(self, "proposal_fn", None)
         if fn is None:
-            raise NotImplementedError("ovo_b200: SAM-2 mask proposal is not built yet (attach MaskGenerator.proposal_fn)")
+            seg, maps = self.segment_device(image)
+            return seg.cpu().numpy(), maps.cpu().numpy()
         masks = fn(image)
         if len(masks) == 0:
             return np.array([]), np.array([])

@@ -321,6 +321,37 @@ def stage_gemmdbg():
     _lib.lib().ovo_set_gemm_cluster(0)
 
 
+def stage_gemmshapes():
+    """Per-shape GEMM throughput with the fused epilogues (ovo_gemm_bench): ViT-L/14 x16 images and the SAM-2 shapes."""
+    import ctypes as C
+    from ovo_b200 import _lib
+    lib = _lib.lib()
+    names = {0: "f32", 1: "bf16", 2: "gelu", 3: "resid", 6: "relu"}
+    shapes = [("vit out-proj", 3, 9232, 1024, 1024), ("vit fc2", 3, 9232, 1024, 4096), ("vit fc1", 2, 9232, 4096, 1024),
+              ("vit qkv~bf16", 1, 9232, 3072, 1024),
+              ("sam s3 qkv", 1, 4096, 1728, 576), ("sam s3 proj", 3, 4096, 576, 576), ("sam s3 fc1", 2, 4096, 2304, 576),
+              ("sam s3 fc2", 3, 4096, 576, 2304), ("sam s1 qkv", 1, 65536, 432, 144), ("sam s1 fc1", 2, 65536, 576, 144),
+              ("sam s2 fc1", 2, 16384, 1152, 288), ("sam dec kproj", 1, 1048576, 128, 256), ("sam dec oproj", 3, 1048576, 256, 128),
+              ("sam dec up0", 3, 1048576, 256, 256), ("sam dec up1", 2, 4194304, 128, 64)]
+    dbgs = [(0, "")]
+    if os.environ.get("OVO_DIAG_NOPREFETCH"):
+        dbgs.append((64, " no-prefetch"))
+    for name, epi, M, N, K in shapes:
+        for dbg, tag in dbgs:
+            if dbg and epi != 3:
+                continue
+            lib.ovo_set_gemm_cluster((dbg << 8) | 1)
+            row = []
+            for bn in (0, 64, 128, 256):
+                if bn and bn > max(32, N):
+                    continue
+                ms = C.c_float(0)
+                _lib.check(lib.ovo_gemm_bench(epi, M, N, K, bn, 20, C.byref(ms), _lib.stream_ptr()), "gemm_bench")
+                row.append(f"bn{bn or 'auto'} {ms.value * 1e3:7.1f} us {2.0 * M * N * K / ms.value / 1e9:6.0f} TF/s")
+            print(f"{name:14s} {names[epi]:5s}{tag} {M}x{N}x{K}: " + " | ".join(row), flush=True)
+    lib.ovo_set_gemm_cluster(0)
+
+
 if __name__ == "__main__":
     for st in sys.argv[1:]:
         print(f"===== {st}", flush=True)
