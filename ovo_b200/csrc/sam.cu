@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <map>
 #include <vector>
 
 #include "common.cuh"
@@ -245,90 +246,18 @@ __global__ void __launch_bounds__(256) sam_self_attn_kernel(const __nv_bfloat16*
   }
 }
 
-// token -> image cross attention: 8 queries x n_keys keys, 8 heads of 16.  q [P*8,128]; k,v [kv_batch * n_keys, 128]
-// (kv_stride = 0: the same keys for every prompt, layer 0).  One CTA per (prompt, head); 256 threads stripe the keys,
-// each keeps an online-softmax state per query; states merge through shared memory.
-__global__ void __launch_bounds__(256) sam_t2i_attn_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k,
-                                                           const __nv_bfloat16* __restrict__ v, size_t kv_stride, int n_keys,
-                                                           __nv_bfloat16* __restrict__ out) {
-  const int p = blockIdx.x, h = blockIdx.y, tid = threadIdx.x;
-  __shared__ float sq[kTok][16];
-  __shared__ float red_m[8][kTok], red_l[8][kTok], red_o[8][kTok][16];
-  if (tid < kTok * 16) sq[tid >> 4][tid & 15] = __bfloat162float(q[(static_cast<size_t>(p) * kTok + (tid >> 4)) * kInt + h * 16 + (tid & 15)]) * 0.25f;
-  __syncthreads();
-  float m[kTok], l[kTok], o[kTok][16];
-#pragma unroll
-  for (int a = 0; a < kTok; ++a) {
-    m[a] = -INFINITY; l[a] = 0.f;
-#pragma unroll
-    for (int d = 0; d < 16; ++d) o[a][d] = 0.f;
-  }
-  const __nv_bfloat16* kb = k + static_cast<size_t>(p) * kv_stride + h * 16;
-  const __nv_bfloat16* vb = v + static_cast<size_t>(p) * kv_stride + h * 16;
-  for (int j = tid; j < n_keys; j += 256) {
-    float kf[16], vf[16];
-    {
-      const uint4* kp = reinterpret_cast<const uint4*>(kb + static_cast<size_t>(j) * kInt);
-      const uint4* vp = reinterpret_cast<const uint4*>(vb + static_cast<size_t>(j) * kInt);
-      uint4 t[2] = {kp[0], kp[1]}, u[2] = {vp[0], vp[1]};
-      const __nv_bfloat16* tk = reinterpret_cast<const __nv_bfloat16*>(t);
-      const __nv_bfloat16* tv = reinterpret_cast<const __nv_bfloat16*>(u);
-#pragma unroll
-      for (int d = 0; d < 16; ++d) { kf[d] = __bfloat162float(tk[d]); vf[d] = __bfloat162float(tv[d]); }
-    }
-#pragma unroll
-    for (int a = 0; a < kTok; ++a) {
-      float s = 0.f;
-#pragma unroll
-      for (int d = 0; d < 16; ++d) s += sq[a][d] * kf[d];
-      const float nm = fmaxf(m[a], s);
-      const float c = __expf(m[a] - nm), e = __expf(s - nm);
-      m[a] = nm; l[a] = l[a] * c + e;
-#pragma unroll
-      for (int d = 0; d < 16; ++d) o[a][d] = o[a][d] * c + e * vf[d];
-    }
-  }
-  // merge the 32 lanes of each warp, then the 8 warps
-  const int lane = tid & 31, warp = tid >> 5;
-#pragma unroll
-  for (int a = 0; a < kTok; ++a) {
-    float wm = m[a];
-    for (int s = 16; s > 0; s >>= 1) wm = fmaxf(wm, __shfl_xor_sync(0xffffffffu, wm, s));
-    const float c = (m[a] == -INFINITY) ? 0.f : __expf(m[a] - wm);
-    float wl = l[a] * c;
-    for (int s = 16; s > 0; s >>= 1) wl += __shfl_xor_sync(0xffffffffu, wl, s);
-#pragma unroll
-    for (int d = 0; d < 16; ++d) {
-      float x = o[a][d] * c;
-      for (int s = 16; s > 0; s >>= 1) x += __shfl_xor_sync(0xffffffffu, x, s);
-      if (lane == 0) red_o[warp][a][d] = x;
-    }
-    if (lane == 0) { red_m[warp][a] = wm; red_l[warp][a] = wl; }
-  }
-  __syncthreads();
-  if (tid < kTok * 16) {
-    const int a = tid >> 4, d = tid & 15;
-    float gm = -INFINITY;
-    for (int w = 0; w < 8; ++w) gm = fmaxf(gm, red_m[w][a]);
-    float gl = 0.f, go = 0.f;
-    for (int w = 0; w < 8; ++w) {
-      const float c = (red_m[w][a] == -INFINITY) ? 0.f : __expf(red_m[w][a] - gm);
-      gl += red_l[w][a] * c; go += red_o[w][a][d] * c;
-    }
-    out[(static_cast<size_t>(p) * kTok + a) * kInt + h * 16 + d] = __float2bfloat16_rn(go / gl);
-  }
-}
-
 // image -> token cross attention: every image token attends to the 8 prompt tokens, 8 heads of 16.
 // q [q_batch * n_img, 128] (q_stride = 0: shared queries, layer 0); k,v [P*8,128]; out [P*n_img,128].
 // One thread per (prompt, image token, head).
 __global__ void __launch_bounds__(256) sam_i2t_attn_kernel(const __nv_bfloat16* __restrict__ q, size_t q_stride, const __nv_bfloat16* __restrict__ k,
                                                            const __nv_bfloat16* __restrict__ v, int n_img, __nv_bfloat16* __restrict__ out) {
-  __shared__ float sk[kTok][kInt], sv[kTok][kInt];
+  // [token][head][20 floats]: the 8 heads a quarter-warp reads with one float4 request land in 8 distinct bank groups
+  __shared__ __align__(16) float sk[kTok][8][20], sv[kTok][8][20];
   const int p = blockIdx.y;
   for (int i = threadIdx.x; i < kTok * kInt; i += 256) {
-    sk[0][i] = __bfloat162float(k[static_cast<size_t>(p) * kTok * kInt + i]);
-    sv[0][i] = __bfloat162float(v[static_cast<size_t>(p) * kTok * kInt + i]);
+    const int a = i >> 7, h = (i >> 4) & 7, d = i & 15;
+    sk[a][h][d] = __bfloat162float(k[static_cast<size_t>(p) * kTok * kInt + i]) * 0.25f;   // 16^-0.5 folded into k
+    sv[a][h][d] = __bfloat162float(v[static_cast<size_t>(p) * kTok * kInt + i]);
   }
   __syncthreads();
   const int idx = blockIdx.x * 256 + threadIdx.x;   // (token, head)
@@ -339,13 +268,16 @@ __global__ void __launch_bounds__(256) sam_i2t_attn_kernel(const __nv_bfloat16* 
   const __nv_bfloat16* qb = reinterpret_cast<const __nv_bfloat16*>(raw);
   float qf[16];
 #pragma unroll
-  for (int d = 0; d < 16; ++d) qf[d] = __bfloat162float(qb[d]) * 0.25f;
+  for (int d = 0; d < 16; ++d) qf[d] = __bfloat162float(qb[d]);
   float s[kTok], m = -INFINITY;
 #pragma unroll
   for (int a = 0; a < kTok; ++a) {
     float x = 0.f;
 #pragma unroll
-    for (int d = 0; d < 16; ++d) x += qf[d] * sk[a][h * 16 + d];
+    for (int d4 = 0; d4 < 4; ++d4) {
+      const float4 kk = *reinterpret_cast<const float4*>(&sk[a][h][4 * d4]);
+      x += qf[4 * d4] * kk.x + qf[4 * d4 + 1] * kk.y + qf[4 * d4 + 2] * kk.z + qf[4 * d4 + 3] * kk.w;
+    }
     s[a] = x; m = fmaxf(m, x);
   }
   float l = 0.f;
@@ -354,16 +286,18 @@ __global__ void __launch_bounds__(256) sam_i2t_attn_kernel(const __nv_bfloat16* 
   const float inv = 1.f / l;
   float o[16];
 #pragma unroll
-  for (int d = 0; d < 16; ++d) {
-    float x = 0.f;
+  for (int d = 0; d < 16; ++d) o[d] = 0.f;
 #pragma unroll
-    for (int a = 0; a < kTok; ++a) x += s[a] * sv[a][h * 16 + d];
-    o[d] = x * inv;
-  }
+  for (int a = 0; a < kTok; ++a)
+#pragma unroll
+    for (int d4 = 0; d4 < 4; ++d4) {
+      const float4 vv = *reinterpret_cast<const float4*>(&sv[a][h][4 * d4]);
+      o[4 * d4] += s[a] * vv.x; o[4 * d4 + 1] += s[a] * vv.y; o[4 * d4 + 2] += s[a] * vv.z; o[4 * d4 + 3] += s[a] * vv.w;
+    }
   uint4 w[2];
   uint32_t* wp = reinterpret_cast<uint32_t*>(w);
 #pragma unroll
-  for (int d = 0; d < 8; ++d) wp[d] = pack_bf16(o[2 * d], o[2 * d + 1]);
+  for (int d = 0; d < 8; ++d) wp[d] = pack_bf16(o[2 * d] * inv, o[2 * d + 1] * inv);
   uint4* op = reinterpret_cast<uint4*>(out + (static_cast<size_t>(p) * n_img + t) * kInt + h * 16);
   op[0] = w[0]; op[1] = w[1];
 }
@@ -694,6 +628,12 @@ struct ovo_sam {
   int32_t* box_tmp = nullptr; int32_t* src_tmp = nullptr; int32_t* order_tmp = nullptr;
   int* counters = nullptr;
   size_t masks_tmp_bytes = 0; uint8_t* masks_tmp2 = nullptr;
+  // CUDA graphs of the static-shape launch sequences (trunk + neck: ~350 launches of 5-20 us each; decoder on the handle's
+  // own buffers: ~75 launches): the first call per key runs eagerly, the second captures, later calls replay
+  struct GraphEntry { cudaGraphExec_t exec = nullptr; long long launches = 0; int warm = 0; };
+  std::map<long long, GraphEntry> graphs;
+  cudaStream_t cap_stream = nullptr;
+  bool use_graphs = true;
   std::vector<void*> owned;
 };
 
@@ -726,6 +666,34 @@ int add_cast(const float* a, const float* b, int b_mod, int width, size_t n, __n
   ProfScope prof(st, PROF_OTHER, 0.0, static_cast<double>(n) * 6.0);
   add_cast_kernel<<<ceil_div(static_cast<long long>(n / 4), 256), 256, 0, st>>>(a, b, b_mod, width, n / 4, o16, o32);
   OVO_CHECK_LAUNCH();
+  return OVO_OK;
+}
+
+template <typename F>
+int graphed(ovo_sam* s, long long key, cudaStream_t st, F&& fn) {
+  ovo_sam::GraphEntry& ge = s->graphs[key];
+  if (!s->use_graphs || ge.warm == 0 || profiling()) {
+    OVO_TRY(fn(st));
+    if (!profiling()) ge.warm = 1;
+    return OVO_OK;
+  }
+  if (ge.exec == nullptr) {
+    const long long before = ovo_launch_count(0);
+    cudaGraph_t graph = nullptr;
+    if (!s->cap_stream) OVO_CUDA(cudaStreamCreateWithFlags(&s->cap_stream, cudaStreamNonBlocking));
+    OVO_CUDA(cudaStreamBeginCapture(s->cap_stream, cudaStreamCaptureModeThreadLocal));
+    const int r = fn(s->cap_stream);
+    const cudaError_t ce = cudaStreamEndCapture(s->cap_stream, &graph);
+    if (r != OVO_OK) { if (graph) cudaGraphDestroy(graph); return r; }
+    if (ce != cudaSuccess) return set_error(OVO_E_CUDA, "sam graph capture failed: %s", cudaGetErrorString(ce));
+    const cudaError_t ie = cudaGraphInstantiate(&ge.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ie != cudaSuccess) { ge.exec = nullptr; return set_error(OVO_E_CUDA, "sam graph instantiate failed: %s", cudaGetErrorString(ie)); }
+    ge.launches = ovo_launch_count(0) - before;
+    count_launch(-static_cast<int>(ge.launches));   // captured, not executed yet
+  }
+  OVO_CUDA(cudaGraphLaunch(ge.exec, st));
+  count_launch(static_cast<int>(ge.launches));
   return OVO_OK;
 }
 
@@ -771,7 +739,11 @@ int run_trunk(ovo_sam* s, int n_blocks, float* block_out, cudaStream_t st) {
       const int nq = b.q_pool ? ws * ws / 4 : ws * ws;
       const int wins = (grid / ws) * (grid / ws);
       ProfScope prof(st, PROF_ATTN, 4.0 * wins * b.heads * static_cast<double>(nq) * ws * ws * kSamHd, 0.0);
-      hiera_attention_kernel<<<dim3(ceil_div(nq, kSamQB), wins, b.heads), 128, 0, st>>>(p);
+      if (nq >= 128) {
+        hiera_attention_kernel<128><<<dim3(ceil_div(nq, 128), wins, b.heads), 256, hiera_attn_smem_bytes<128>(), st>>>(p);
+      } else {
+        hiera_attention_kernel<64><<<dim3(ceil_div(nq, 64), wins, b.heads), 128, hiera_attn_smem_bytes<64>(), st>>>(p);
+      }
       OVO_CHECK_LAUNCH();
     }
     const int To = grid_out * grid_out;
@@ -826,6 +798,16 @@ int patches_from_pixels(ovo_sam* s, cudaStream_t st) {
   return OVO_OK;
 }
 
+int trunk_from_pixels(ovo_sam* s, int n_blocks, float* block_out, cudaStream_t st) {
+  if ((n_blocks < 0 || n_blocks >= s->cfg.n_blocks) && block_out == nullptr)
+    return graphed(s, 1, st, [&](cudaStream_t cs) {
+      OVO_TRY(patches_from_pixels(s, cs));
+      return run_trunk(s, -1, nullptr, cs);
+    });
+  OVO_TRY(patches_from_pixels(s, st));
+  return run_trunk(s, n_blocks, block_out, st);
+}
+
 // Attention.forward on the token side: out_proj(attn(...)) handled by the caller; this projects q/k/v of tokens.
 int tok_lin(ovo_sam* s, const __nv_bfloat16* a, const void* w, const float* b, int rows, int n, int k, __nv_bfloat16* out, cudaStream_t st) {
   return gemm(EPI_BF16, a, k, w, k, rows, n, k, b, out, n, nullptr, 0, 0, st);
@@ -839,7 +821,8 @@ int t2i_block(ovo_sam* s, const ovo_sam_attn& A, const __nv_bfloat16* kbuf, cons
   OVO_TRY(tok_lin(s, s->tqpe_bf, A.q_w, A.q_b, R, kInt, kC, s->t_q, st));
   {
     ProfScope prof(st, PROF_ATTN, 4.0 * P * 8 * kTok * static_cast<double>(HW) * 16, 0.0);
-    sam_t2i_attn_kernel<<<dim3(P, 8), 256, 0, st>>>(s->t_q, kbuf, vbuf, kv_stride, HW, s->t_o);
+    OVO_REQUIRE(HW % 64 == 0, "sam decoder: image token count %d must be a multiple of 64", HW);
+    sam_t2i_attn_mma_kernel<<<P, 256, kT2iSmemBytes, st>>>(s->t_q, kbuf, vbuf, kv_stride, HW, s->t_o);
     OVO_CHECK_LAUNCH();
   }
   OVO_TRY(gemm(EPI_F32_RESID, s->t_o, kInt, A.o_w, kInt, R, kC, kInt, A.o_b, s->tq_tmp, kC, s->queries, kC, 0, st));
@@ -861,6 +844,10 @@ int ovo_sam_create(const ovo_sam_cfg* cfg, const ovo_sam_weights* w, int max_h, 
   s->w.blocks = s->blocks.data(); s->w.layers = s->layers.data();
   s->S = cfg->image_size; s->g = cfg->image_size / 16;
   s->max_h = max_h; s->max_w = max_w; s->max_p = max_prompts;
+  {
+    const char* env = getenv("OVO_B200_GRAPHS");
+    s->use_graphs = !(env && env[0] == '0');
+  }
   const int S = s->S, g = s->g, g0 = S / 4;
   // geometry walk: buffer sizes and the stage outputs
   size_t max_x = 0, max_qkv = 0, max_hid = 0, max_short = 0, max_xn = 0, max_att = 0;
@@ -907,6 +894,12 @@ int ovo_sam_create(const ovo_sam_cfg* cfg, const ovo_sam_weights* w, int max_h, 
   A(&s->score_tmp, P * 3); A(&s->keep_tmp, P * 3); A(&s->stab_tmp, P * 3); A(&s->iou_tmp, P * 3); A(&s->box_tmp, P * 3 * 4);
   A(&s->src_tmp, P * 3); A(&s->order_tmp, P * 3); A(&s->counters, 4);
   if (r != OVO_OK) { ovo_sam_destroy(s); return r; }
+  if (cudaFuncSetAttribute(hiera_attention_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, hiera_attn_smem_bytes<128>()) != cudaSuccess ||
+      cudaFuncSetAttribute(hiera_attention_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, hiera_attn_smem_bytes<64>()) != cudaSuccess ||
+      cudaFuncSetAttribute(sam_t2i_attn_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kT2iSmemBytes) != cudaSuccess) {
+    ovo_sam_destroy(s);
+    return set_error(OVO_E_CUDA, "ovo_sam_create: cudaFuncSetAttribute(shared memory) failed: %s", cudaGetErrorString(cudaGetLastError()));
+  }
   s->dc1 = s->keys_pre;   // [P*HW, 256] f32: the transposed-conv output reuses the pre-LayerNorm key buffer
   *out = s;
   return OVO_OK;
@@ -914,6 +907,8 @@ int ovo_sam_create(const ovo_sam_cfg* cfg, const ovo_sam_weights* w, int max_h, 
 
 void ovo_sam_destroy(ovo_sam_t* s) {
   if (!s) return;
+  for (auto& ge : s->graphs) if (ge.second.exec) cudaGraphExecDestroy(ge.second.exec);
+  if (s->cap_stream) cudaStreamDestroy(s->cap_stream);
   for (void* p : s->owned) cudaFree(p);
   for (void* p : {static_cast<void*>(s->xmin), static_cast<void*>(s->xsize), static_cast<void*>(s->ymin), static_cast<void*>(s->ysize),
                   static_cast<void*>(s->xw), static_cast<void*>(s->yw), static_cast<void*>(s->masks_tmp), static_cast<void*>(s->masks_tmp2)})
@@ -926,8 +921,7 @@ int ovo_sam_set_pixels(ovo_sam_t* s, const float* pixels_dev, float* embed_out, 
   OVO_REQUIRE(s && pixels_dev, "ovo_sam_set_pixels: null argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
   OVO_CUDA(cudaMemcpyAsync(s->pixels, pixels_dev, sizeof(float) * 3 * s->S * s->S, cudaMemcpyDeviceToDevice, st));
-  OVO_TRY(patches_from_pixels(s, st));
-  OVO_TRY(run_trunk(s, n_blocks, block_out, st));
+  OVO_TRY(trunk_from_pixels(s, n_blocks, block_out, st));
   if (n_blocks < 0 || n_blocks >= s->cfg.n_blocks) OVO_TRY(copy_taps(s, embed_out, s0_out, s1_out, st));
   return OVO_OK;
 }
@@ -964,16 +958,23 @@ int ovo_sam_set_image(ovo_sam_t* s, const uint8_t* rgb_dev, int H, int W, float*
     OVO_CHECK_LAUNCH();
   }
   if (pixels_out) OVO_CUDA(cudaMemcpyAsync(pixels_out, s->pixels, sizeof(float) * 3 * S * S, cudaMemcpyDeviceToDevice, st));
-  OVO_TRY(patches_from_pixels(s, st));
-  OVO_TRY(run_trunk(s, n_blocks, block_out, st));
+  OVO_TRY(trunk_from_pixels(s, n_blocks, block_out, st));
   if (n_blocks < 0 || n_blocks >= s->cfg.n_blocks) OVO_TRY(copy_taps(s, embed_out, s0_out, s1_out, st));
   return OVO_OK;
 }
+
+static int sam_predict_impl(ovo_sam_t* s, const float* points_dev, int P, float* low_out, float* iou_out, cudaStream_t st);
 
 int ovo_sam_predict(ovo_sam_t* s, const float* points_dev, int P, float* low_out, float* iou_out, void* stream_) {
   OVO_REQUIRE(s && points_dev, "ovo_sam_predict: null argument");
   OVO_REQUIRE(P > 0 && P <= s->max_p, "ovo_sam_predict: %d prompts, handle sized for %d", P, s->max_p);
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  if (points_dev == s->points && low_out == s->low_all && iou_out == s->iou_all)   // the handle's own buffers: static launch sequence
+    return graphed(s, (2ll << 32) | P, st, [&](cudaStream_t cs) { return sam_predict_impl(s, points_dev, P, low_out, iou_out, cs); });
+  return sam_predict_impl(s, points_dev, P, low_out, iou_out, st);
+}
+
+static int sam_predict_impl(ovo_sam_t* s, const float* points_dev, int P, float* low_out, float* iou_out, cudaStream_t st) {
   const int g = s->g, HW = g * g, R = P * kTok;
   const size_t PHW = static_cast<size_t>(P) * HW;
   OVO_REQUIRE(PHW * 4 < (1ull << 31), "ovo_sam_predict: too many prompts for 32-bit GEMM row indices");

@@ -56,10 +56,24 @@ __device__ __forceinline__ uint4 bf16x8_max(uint4 a, uint4 b) {
   return r;
 }
 
-__global__ void __launch_bounds__(128) hiera_attention_kernel(WinAttnParams p) {
-  __shared__ __align__(16) __nv_bfloat16 sQ[kSamQB * kSamRow];
-  __shared__ __align__(16) __nv_bfloat16 sK[kSamKB * kSamRow];
-  __shared__ __align__(16) __nv_bfloat16 sV[kSamKB * kSamRow];
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+// QB queries per CTA (QB/16 warps); K/V blocks of 64 keys double-buffered with cp.async so the next block's global loads
+// overlap this block's MMAs.  Dynamic shared memory: Q [QB] + 2 stages x (K [64] + V [64]) rows of kSamRow bf16.
+template <int QB>
+constexpr int hiera_attn_smem_bytes() { return (QB + 4 * kSamKB) * kSamRow * 2; }
+
+template <int QB>
+__global__ void __launch_bounds__(QB * 2) hiera_attention_kernel(WinAttnParams p) {
+  extern __shared__ __align__(16) uint8_t hiera_smem[];
+  __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(hiera_smem);
+  __nv_bfloat16* sKV = sQ + QB * kSamRow;                 // stage s: K at sKV + s*2*64*row, V right after K
+  constexpr int kThreads = QB * 2;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int head = blockIdx.z;
@@ -69,14 +83,37 @@ __global__ void __launch_bounds__(128) hiera_attention_kernel(WinAttnParams p) {
   const int wsq = p.q_pool ? p.ws >> 1 : p.ws;        // window side on the query / output grid
   const int nq = wsq * wsq;
   const int grid_out = p.q_pool ? p.grid >> 1 : p.grid;
-  const int q0 = blockIdx.x * kSamQB;
+  const int q0 = blockIdx.x * QB;
   const int ld = 3 * p.dim_out;
   const __nv_bfloat16* qbase = p.qkv + head * kSamHd;
   const __nv_bfloat16* kbase = qbase + p.dim_out;
   const __nv_bfloat16* vbase = kbase + p.dim_out;
+  const int nblocks = (nk + kSamKB - 1) / kSamKB;
 
-  // ---- stage Q (64 rows x 10 chunks of 8 bf16; chunk 9 is the zero pad 72..79)
-  for (int it = tid; it < kSamQB * 10; it += 128) {
+  auto prefetch = [&](int blk, int stage) {
+    __nv_bfloat16* sK = sKV + stage * 2 * kSamKB * kSamRow;
+    __nv_bfloat16* sV = sK + kSamKB * kSamRow;
+    for (int it = tid; it < kSamKB * 9; it += kThreads) {
+      const int r = it / 9, c = it - r * 9;
+      const int ki = blk * kSamKB + r;
+      if (ki < nk) {
+        const int ky = ki / p.ws, kx = ki - ky * p.ws;
+        const size_t t = static_cast<size_t>(wy * p.ws + ky) * p.grid + wx * p.ws + kx;
+        cp_async16(sK + r * kSamRow + c * 8, kbase + t * ld + c * 8);
+        cp_async16(sV + r * kSamRow + c * 8, vbase + t * ld + c * 8);
+      } else {   // rows past the window: zeros (P is 0 there, but 0 * garbage could be NaN)
+        *reinterpret_cast<uint4*>(sK + r * kSamRow + c * 8) = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4*>(sV + r * kSamRow + c * 8) = make_uint4(0, 0, 0, 0);
+      }
+    }
+  };
+  prefetch(0, 0);
+  cp_async_commit();
+  // zero pad columns 72..79 of every K/V row (never touched by cp.async) while block 0 is in flight
+  for (int r = tid; r < 4 * kSamKB; r += kThreads) *reinterpret_cast<uint4*>(sKV + r * kSamRow + 72) = make_uint4(0, 0, 0, 0);
+
+  // ---- stage Q (QB rows x 10 chunks of 8 bf16; chunk 9 is the zero pad 72..79)
+  for (int it = tid; it < QB * 10; it += kThreads) {
     const int r = it / 10, c = it - r * 10;
     uint4 v = make_uint4(0, 0, 0, 0);
     const int qi = q0 + r;
@@ -110,23 +147,19 @@ __global__ void __launch_bounds__(128) hiera_attention_kernel(WinAttnParams p) {
   for (int i = 0; i < 9; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
   float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
 
-  for (int kb = 0; kb < nk; kb += kSamKB) {
-    __syncthreads();   // previous block fully consumed
-    for (int it = tid; it < kSamKB * 10; it += 128) {
-      const int r = it / 10, c = it - r * 10;
-      uint4 kv = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
-      const int ki = kb + r;
-      if (c < 9 && ki < nk) {
-        const int ky = ki / p.ws, kx = ki - ky * p.ws;
-        const size_t t = static_cast<size_t>(wy * p.ws + ky) * p.grid + wx * p.ws + kx;
-        kv = *reinterpret_cast<const uint4*>(kbase + t * ld + c * 8);
-        vv = *reinterpret_cast<const uint4*>(vbase + t * ld + c * 8);
-      }
-      *reinterpret_cast<uint4*>(sK + r * kSamRow + c * 8) = kv;
-      *reinterpret_cast<uint4*>(sV + r * kSamRow + c * 8) = vv;
+  for (int blk = 0; blk < nblocks; ++blk) {
+    const int kb = blk * kSamKB;
+    if (blk + 1 < nblocks) {
+      prefetch(blk + 1, (blk + 1) & 1);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
     }
-    __syncthreads();
-    if (!active) continue;
+    __syncthreads();   // block `blk` has landed for every thread
+    const __nv_bfloat16* sK = sKV + (blk & 1) * 2 * kSamKB * kSamRow;
+    const __nv_bfloat16* sV = sK + kSamKB * kSamRow;
+    if (active) {
     const int nvalid = min(kSamKB, nk - kb);     // multiple of 16
     const int ntiles = nvalid >> 3;
 
@@ -154,16 +187,17 @@ __global__ void __launch_bounds__(128) hiera_attention_kernel(WinAttnParams p) {
     bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 1)); bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 2));
     bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 1)); bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 2));
     const float nm0 = fmaxf(m0, bm0), nm1 = fmaxf(m1, bm1);
-    const float c0 = exp2f((m0 - nm0) * p.scale_log2e), c1 = exp2f((m1 - nm1) * p.scale_log2e);
+    const float c0 = fast_ex2((m0 - nm0) * p.scale_log2e), c1 = fast_ex2((m1 - nm1) * p.scale_log2e);
     m0 = nm0; m1 = nm1;
+    const float ms0 = m0 * p.scale_log2e, ms1 = m1 * p.scale_log2e;
     float rs0 = 0.f, rs1 = 0.f;
     uint32_t pf[4][4];
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
       float e0 = 0.f, e1 = 0.f, e2 = 0.f, e3 = 0.f;
       if (nt < ntiles) {
-        e0 = exp2f((s[nt][0] - m0) * p.scale_log2e); e1 = exp2f((s[nt][1] - m0) * p.scale_log2e);
-        e2 = exp2f((s[nt][2] - m1) * p.scale_log2e); e3 = exp2f((s[nt][3] - m1) * p.scale_log2e);
+        e0 = fast_ex2(fmaf(s[nt][0], p.scale_log2e, -ms0)); e1 = fast_ex2(fmaf(s[nt][1], p.scale_log2e, -ms0));
+        e2 = fast_ex2(fmaf(s[nt][2], p.scale_log2e, -ms1)); e3 = fast_ex2(fmaf(s[nt][3], p.scale_log2e, -ms1));
       }
       rs0 += e0 + e1; rs1 += e2 + e3;
       pf[nt >> 1][(nt & 1) * 2] = pack_bf16(e0, e1);
@@ -183,6 +217,8 @@ __global__ void __launch_bounds__(128) hiera_attention_kernel(WinAttnParams p) {
         }
       }
     }
+    }
+    __syncthreads();   // everyone is done with this stage before the prefetch two blocks ahead overwrites it
   }
   if (!active) return;
   l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
@@ -201,6 +237,105 @@ __global__ void __launch_bounds__(128) hiera_attention_kernel(WinAttnParams p) {
     for (int nt = 0; nt < 9; ++nt)
       *reinterpret_cast<uint32_t*>(dst + nt * 8) = pack_bf16(o[nt][2 * h] * inv, o[nt][2 * h + 1] * inv);
   }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// SAM-2 mask decoder, token -> image cross attention (sam/transformer.py:192-197,124-130): 8 query tokens per prompt
+// against n_keys image tokens, 8 heads of 16.  One CTA per prompt, one warp per head; K/V tiles of 64 keys x 8 heads
+// (256-byte rows: fully coalesced) double-buffered with cp.async; S^T = Q K^T and O = P V on mma.sync.m16n8k16 (the 8
+// queries fill half of the 16-row tile).  q [P*8,128] bf16; k,v [kv_batch * n_keys, 128] bf16 (kv_stride = 0: the same
+// keys for every prompt, layer 0); out [P*8,128] bf16.
+constexpr int kT2iRow = 136;   // 128 + 8 bf16: 272-byte rows, 8 consecutive rows hit distinct 16-B bank groups
+constexpr int kT2iSmemBytes = 2 * 2 * 64 * kT2iRow * 2;
+
+__global__ void __launch_bounds__(256) sam_t2i_attn_mma_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k,
+                                                               const __nv_bfloat16* __restrict__ v, size_t kv_stride, int n_keys,
+                                                               __nv_bfloat16* __restrict__ out) {
+  extern __shared__ __align__(16) uint8_t t2i_smem[];
+  __nv_bfloat16* sKV = reinterpret_cast<__nv_bfloat16*>(t2i_smem);
+  const int prompt = blockIdx.x, tid = threadIdx.x, head = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t4 = lane & 3;
+  const __nv_bfloat16* kb = k + static_cast<size_t>(prompt) * kv_stride;
+  const __nv_bfloat16* vb = v + static_cast<size_t>(prompt) * kv_stride;
+  const int nblocks = n_keys / 64;
+
+  auto prefetch = [&](int blk, int stage) {
+    __nv_bfloat16* sK = sKV + stage * 2 * 64 * kT2iRow;
+    __nv_bfloat16* sV = sK + 64 * kT2iRow;
+    for (int it = tid; it < 64 * 16; it += 256) {
+      const int r = it >> 4, c = it & 15;
+      const size_t src = (static_cast<size_t>(blk) * 64 + r) * 128 + c * 8;
+      cp_async16(sK + r * kT2iRow + c * 8, kb + src);
+      cp_async16(sV + r * kT2iRow + c * 8, vb + src);
+    }
+  };
+  prefetch(0, 0);
+  cp_async_commit();
+  // A fragment of Q (rows 0..7 = the 8 tokens, rows 8..15 zero), head_dim 16 = one k-step
+  uint32_t qf[4];
+  {
+    const __nv_bfloat16* qp = q + (static_cast<size_t>(prompt) * 8 + g) * 128 + head * 16 + 2 * t4;
+    qf[0] = *reinterpret_cast<const uint32_t*>(qp);
+    qf[2] = *reinterpret_cast<const uint32_t*>(qp + 8);
+    qf[1] = 0; qf[3] = 0;
+  }
+  const float sc = 0.25f * 1.4426950408889634f;   // 16^-0.5 * log2(e)
+  float o[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+  float m0 = -INFINITY, l0 = 0.f;
+  for (int blk = 0; blk < nblocks; ++blk) {
+    if (blk + 1 < nblocks) {
+      prefetch(blk + 1, (blk + 1) & 1);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    const __nv_bfloat16* sK = sKV + (blk & 1) * 2 * 64 * kT2iRow;
+    const __nv_bfloat16* sV = sK + 64 * kT2iRow;
+    float s[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+      uint32_t bf[2];
+      ldsm_x2(bf, sK + (nt * 8 + (lane & 7)) * kT2iRow + head * 16 + (((lane >> 3) & 1) << 3));
+      mma_bf16_16816(s[nt], qf, bf);
+    }
+    float bm = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) bm = fmaxf(bm, fmaxf(s[nt][0], s[nt][1]));
+    bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 1)); bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 2));
+    const float nm = fmaxf(m0, bm);
+    const float c0 = fast_ex2((m0 - nm) * sc);
+    m0 = nm;
+    const float ms = m0 * sc;
+    float rs = 0.f;
+    uint32_t pf[4][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const float e0 = fast_ex2(fmaf(s[nt][0], sc, -ms)), e1 = fast_ex2(fmaf(s[nt][1], sc, -ms));
+      rs += e0 + e1;
+      pf[nt >> 1][(nt & 1) * 2] = pack_bf16(e0, e1);
+      pf[nt >> 1][(nt & 1) * 2 + 1] = 0;            // rows 8..15 are padding
+    }
+    l0 = l0 * c0 + rs;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) { o[i][0] *= c0; o[i][1] *= c0; }
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        uint32_t bf[2];
+        ldsm_x2_trans(bf, sV + (kk * 16 + (lane & 15)) * kT2iRow + head * 16 + nt * 8);
+        mma_bf16_16816(o[nt], pf[kk], bf);
+      }
+    __syncthreads();
+  }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  const float inv = 1.f / l0;
+  __nv_bfloat16* dst = out + (static_cast<size_t>(prompt) * 8 + g) * 128 + head * 16 + 2 * t4;
+  *reinterpret_cast<uint32_t*>(dst) = pack_bf16(o[0][0] * inv, o[0][1] * inv);
+  *reinterpret_cast<uint32_t*>(dst + 8) = pack_bf16(o[1][0] * inv, o[1][1] * inv);
 }
 
 }  // namespace ovo

@@ -47,7 +47,17 @@ def main():
     out["generate_ms"] = timed(lambda: sam.generate(img, prm), args.iters)
     seg, maps = sam.generate(img, prm)
     out["masks"] = int(maps.shape[0])
-    for name, fn in (("set_image", lambda: sam.set_image(img)), ("predict", lambda: sam.predict(pts))):
+    import time
+    torch.cuda.synchronize(); t0 = time.time()
+    for _ in range(5):
+        sam.generate(img, prm)
+    torch.cuda.synchronize(); out["generate_wall_ms"] = (time.time() - t0) / 5 * 1e3
+    low, iou = sam.predict(pts)
+    torch.cuda.synchronize(); t0 = time.time()
+    for _ in range(5):
+        sam.postprocess(low, iou, 480, 640, prm)
+    torch.cuda.synchronize(); out["postprocess_wall_ms"] = (time.time() - t0) / 5 * 1e3
+    for name, fn in (("set_image", lambda: sam.set_image(img)), ("predict", lambda: sam.predict(pts)), ("generate", lambda: sam.generate(img, prm))):
         _lib.profile_begin()
         fn()
         rep = _lib.profile_report()
