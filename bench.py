@@ -128,11 +128,14 @@ def run_ours(args, rank, world, local_rank):
     ident_all = torch.arange(F * M, dtype=torch.int32, device=dev).reshape(F, M)
 
     def step():
-        # the encoder does not depend on the association: enqueue it first, then run the (host-synchronising)
-        # association of the batch on a second stream so its launch/sync latency hides under the ViT
+        # The encoder does not depend on the association: it is enqueued first on the main stream; the (host-synchronising)
+        # association of the batch runs on a second stream under it.  The HBM-bound fusion of this step's descriptors is
+        # enqueued on that second stream as well, so it overlaps the tensor-bound encoder of the NEXT step (software
+        # pipelining across steps; the timed region ends with a full device synchronise, so every step's fusion is inside it).
         main = torch.cuda.current_stream()
         side.wait_stream(main)
         feats = enc.encode_regions(rgb_d, masks_d, masks_per_frame=[M] * F)
+        enc_done = main.record_event()
         rows = []
         with torch.cuda.stream(side):
             for i, f in enumerate(fr):
@@ -140,14 +143,17 @@ def run_ours(args, rank, world, local_rank):
                                                            kf_slot=i, n_masks=M, w2c=w2cs[i])
                 state["n_matched"] = nm
                 rows.append(torch.from_numpy(votes["ins_id"].astype(np.int32)))
-        main.wait_stream(side)
-        ins_rows = torch.stack(rows).to(dev, non_blocking=True)          # [F, M] instance id per mask (-1 = none)
-        # dense per-point fusion of all F keyframes in one pass over the bank (bit-identical to F passes), then the
-        # instance bank
-        mask_row = torch.where(ins_rows >= 0, ident_all, -1)
-        sm.fuse_dense_batch(list(range(F)), bank, counts, feats, mask_row)
-        for i in range(F):
-            sm.bank_update_mean(ibank, icounts, feats[i * M:(i + 1) * M], ins_rows[i])
+            side.wait_event(enc_done)
+            ins_rows = torch.stack(rows).to(dev, non_blocking=True)      # [F, M] instance id per mask (-1 = none)
+            # dense per-point fusion of all F keyframes in one pass over the bank (bit-identical to F passes), then the
+            # instance bank
+            mask_row = torch.where(ins_rows >= 0, ident_all, -1)
+            sm.fuse_dense_batch(list(range(F)), bank, counts, feats, mask_row)
+            for i in range(F):
+                sm.bank_update_mean(ibank, icounts, feats[i * M:(i + 1) * M], ins_rows[i])
+            feats.record_stream(side)
+        if args.no_pipeline:
+            main.wait_stream(side)
         return feats
 
     def timed(fn, steps, warmup):
@@ -439,6 +445,7 @@ def main():
     ap.add_argument("--points", type=int, default=2_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sam", action="store_true", help="skip the SAM-2 stage report")
+    ap.add_argument("--no-pipeline", action="store_true", help="do not overlap a step's fusion with the next step's encoder")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", 0))

@@ -4,11 +4,11 @@
 // One CTA = one (image, head, 128-query tile), 256 threads: two threads per query row, each owning half of the keys
 // of a block and half of the output columns (the softmax is issue/latency bound, so warps per SM matter).  TWO CTAs
 // are resident per SM (112 KB smem, 256 TMEM columns each): one CTA's softmax overlaps the other's tensor-core work.
-// Q (128x64) is TMA-loaded once; K (128x64) and V^T (64x128) blocks stream through 2-slot rings of 128B-swizzled
-// shared memory.  Per 128-key block: S = Q.K^T (tcgen05, accumulator in TMEM) -> tcgen05.ld -> online softmax in
+// Q (128x64) is TMA-loaded once; K (128x64) and V (128x64, used as an MN-major B operand: no transposed copy of V is
+// ever made) blocks stream through 2-slot rings of 128B-swizzled shared memory.  Per 128-key block: S = Q.K^T (tcgen05, accumulator in TMEM) -> tcgen05.ld -> online softmax in
 // registers (one thread per query row, exp2f) -> P (bf16) written to swizzled smem -> O_j = P.V_j (tcgen05,
 // issued together with the next block's Q.K^T) -> tcgen05.ld -> rescale-and-accumulate in registers.
-// q/k/v^T are produced in exactly this layout by the QKV GEMM epilogue (gemm.cuh EPI_QKV).
+// q/k/v are produced in exactly this layout by the QKV GEMM epilogue (gemm.cuh EPI_QKV).
 #pragma once
 #include "ptx.cuh"
 
@@ -20,14 +20,14 @@ constexpr int kAttnMaxBlocks = 5;  // seq_pad <= 640
 struct AttnSmem {
   static constexpr int kQ = 128 * 64 * 2;       // 16 KB
   static constexpr int kKBlock = 128 * 64 * 2;  // 16 KB per 128 keys
-  static constexpr int kVBlock = 64 * 64 * 2;   // 8 KB per 64 keys (V^T tile: 64 d-rows x 64 keys); 2 per block
+  static constexpr int kVBlock = 64 * 64 * 2;   // 8 KB per 64 keys (V rows of 128 B); one 128-key block = 2 of them, one TMA
   static constexpr int kP = 2 * 128 * 64 * 2;   // 32 KB: P as two K-major 128x64 tiles
   static constexpr int kBytes = kQ + 2 * kKBlock + 4 * kVBlock + kP + 256 + 512;  // 112 KB + barriers + row exchange
 };
 
 __global__ void __launch_bounds__(kAttnThreads, 2)
     attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                         const __grid_constant__ CUtensorMap tmVt, __nv_bfloat16* __restrict__ out, int seq,
+                         const __grid_constant__ CUtensorMap tmV, __nv_bfloat16* __restrict__ out, int seq,
                          int seq_pad, int heads, int ld_out, float scale_log2e, int causal, int dbg) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();  // the 128B swizzle needs 1024-byte aligned tiles
@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
   const int nb = causal ? min(nblk, qt + 1) : nblk;
 
   if (tid == 0) {
-    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmVt);
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
     for (int i = 0; i < 6; ++i) mbar_init(&bars[i], 1);
     fence_barrier_init();
   }
@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
   const uint32_t tmem_O = tmem_S + 128;
 
   constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128);
-  constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64);
+  constexpr uint32_t idesc_o = umma_idesc_bf16_bmn(128, 64);
   const uint64_t qdesc = umma_desc_sw128(smem_u32(sQ));
 
   auto load_k = [&](int j) {  // K block j -> slot j&1
@@ -74,11 +74,10 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
     if (j == 0) tma_load_2d(sQ, &tmQ, &bar_k[0], 0, bh * seq_pad + q0);
     tma_load_2d(sK + s * AttnSmem::kKBlock, &tmK, &bar_k[s], 0, bh * seq_pad + j * 128);
   };
-  auto load_v = [&](int j) {  // V^T block j (two 64-key tiles) -> slot j&1
+  auto load_v = [&](int j) {  // V block j (128 keys x 64) -> slot j&1
     const int s = j & 1;
     mbar_arrive_expect_tx(&bar_v[s], 2 * AttnSmem::kVBlock);
-    tma_load_2d(sV + (2 * s) * AttnSmem::kVBlock, &tmVt, &bar_v[s], j * 128, bh * 64);
-    tma_load_2d(sV + (2 * s + 1) * AttnSmem::kVBlock, &tmVt, &bar_v[s], j * 128 + 64, bh * 64);
+    tma_load_2d(sV + (2 * s) * AttnSmem::kVBlock, &tmV, &bar_v[s], 0, bh * seq_pad + j * 128);
   };
   auto issue_qk = [&](int j) {  // S = Q . K_j^T
     mbar_wait(&bar_k[j & 1], (j >> 1) & 1);
@@ -193,9 +192,10 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
 #pragma unroll
       for (int t = 0; t < 2; ++t) {
         const uint64_t pdesc = umma_desc_sw128(smem_u32(sP + t * (128 * 128)));
+        // keys 64t + 16k .. +15 of the block: 16 rows of 128 B = 2048 B per K=16 step
         const uint64_t vdesc = umma_desc_sw128(smem_u32(sV + (2 * (j & 1) + t) * AttnSmem::kVBlock));
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(tmem_O, pdesc + 2 * k, vdesc + 2 * k, idesc_o, (t | k) != 0);
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem_O, pdesc + 2 * k, vdesc + 128 * k, idesc_o, (t | k) != 0);
       }
       umma_commit(bar_o);
       if (j + 1 < nb) issue_qk(j + 1);

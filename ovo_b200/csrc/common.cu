@@ -236,7 +236,8 @@ int ovo_gemm_bf16(const void* A_dev, int lda, const void* B_dev, int ldb, int M,
 int ovo_gemm_bench(int epi, int M, int N, int K, int force_bn, int iters, float* ms_out, void* stream_) {
   using namespace ovo;
   OVO_REQUIRE(M > 0 && N > 0 && K > 0 && K % 8 == 0 && iters > 0 && ms_out, "ovo_gemm_bench: bad arguments");
-  OVO_REQUIRE(epi == EPI_F32 || epi == EPI_BF16 || epi == EPI_BF16_GELU || epi == EPI_F32_RESID || epi == EPI_BF16_RELU, "ovo_gemm_bench: epilogue %d unsupported", epi);
+  OVO_REQUIRE(epi == EPI_F32 || epi == EPI_BF16 || epi == EPI_BF16_GELU || epi == EPI_F32_RESID || epi == EPI_BF16_RELU || epi == EPI_QKV, "ovo_gemm_bench: epilogue %d unsupported", epi);
+  OVO_REQUIRE(epi != EPI_QKV || (M % 577 == 0 && N % 192 == 0), "ovo_gemm_bench: the QKV epilogue is timed at ViT shapes (M = images*577, N = 3*width, heads of 64)");
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
   __nv_bfloat16 *A = nullptr, *B = nullptr; float *bias = nullptr, *resid = nullptr; void* out = nullptr;
   const int ldo = (N + 7) / 8 * 8;
@@ -247,6 +248,13 @@ int ovo_gemm_bench(int epi, int M, int N, int K, int force_bn, int iters, float*
   EpiParams ep;
   ep.out = out; ep.ldo = ldo; ep.bias = bias; ep.prof_cls = PROF_GEMM;
   if (epi == EPI_F32_RESID) { ep.resid = resid; ep.ldr = ldo; }
+  __nv_bfloat16* qkv = nullptr;
+  if (epi == EPI_QKV) {   // head-major q/k/v [images, heads, 640, 64], no RoPE table (the rotation math is not timed)
+    const size_t per = static_cast<size_t>(M / 577) * (N / 192) * 640 * 64;
+    OVO_CUDA(cudaMalloc(&qkv, sizeof(__nv_bfloat16) * 3 * per));
+    ep.q = qkv; ep.k = qkv + per; ep.vt = qkv + 2 * per;
+    ep.seq = 577; ep.seq_pad = 640; ep.heads = N / 192; ep.width = N / 3;
+  }
   int rc = OVO_OK;
   for (int i = 0; i < 3 && rc == OVO_OK; ++i) rc = launch_gemm(epi, A, K, B, K, M, N, K, ep, st, force_bn);
   cudaEvent_t e0, e1;
@@ -259,7 +267,7 @@ int ovo_gemm_bench(int epi, int M, int N, int K, int force_bn, int iters, float*
   cudaEventElapsedTime(&ms, e0, e1);
   *ms_out = ms / iters;
   cudaEventDestroy(e0); cudaEventDestroy(e1);
-  cudaFree(A); cudaFree(B); cudaFree(bias); cudaFree(resid); cudaFree(out);
+  cudaFree(A); cudaFree(B); cudaFree(bias); cudaFree(resid); cudaFree(out); cudaFree(qkv);
   return rc;
 }
 

@@ -389,7 +389,7 @@ int launch_attention(ovo_encoder* e, int n_seq, int seq, int seq_pad, int heads,
   const uint64_t bh = static_cast<uint64_t>(n_seq) * heads;
   OVO_TRY(make_tmap_bf16_2d(&tq, e->q, bh * seq_pad, 64, 64, 128, 64));
   OVO_TRY(make_tmap_bf16_2d(&tk, e->k, bh * seq_pad, 64, 64, 128, 64));
-  OVO_TRY(make_tmap_bf16_2d(&tv, e->vt, bh * 64, seq_pad, seq_pad, 64, 64));
+  OVO_TRY(make_tmap_bf16_2d(&tv, e->vt, bh * seq_pad, 64, 64, 128, 64));   // V [b,h,seq_pad,64]: MN-major B operand of P.V
   const int smem = AttnSmem::kBytes;
   static bool attr_set = false;
   if (!attr_set) {

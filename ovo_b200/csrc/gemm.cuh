@@ -18,7 +18,7 @@ enum EpiKind : int {
   EPI_BF16 = 1,       // out_bf16 = acc (+bias)
   EPI_BF16_GELU = 2,  // out_bf16 = gelu(acc + bias)            (pe.py:190-198)
   EPI_F32_RESID = 3,  // out_f32 = acc + bias + resid            (pe.py:221-224)
-  EPI_QKV = 4,        // split q/k/v, 2D-RoPE on q,k, v written transposed (pe.py:125-143, rope.py:40-62)
+  EPI_QKV = 4,        // split q/k/v head-major [b,h,seq_pad,64], 2D-RoPE on q,k (pe.py:125-143, rope.py:40-62)
   EPI_PATCH = 5,      // out_f32[token row] = acc + pos_emb      (pe.py:509-519)
   EPI_BF16_RELU = 6,  // out_bf16 = relu(acc + bias)            (SAM-2 two-way transformer MLP, sam/transformer.py:161-163)
 };
@@ -146,8 +146,8 @@ __device__ __forceinline__ void epilogue_store(const EpiParams& ep, int row, int
     const int b = row / ep.seq;
     const int t = row - b * ep.seq;
     const size_t bh = static_cast<size_t>(b) * ep.heads + head;
-    if (which < 2) {
-      if (ep.rope_tab != nullptr) {
+    {
+      if (ep.rope_tab != nullptr && which < 2) {
         // 2D RoPE with a cls token (rope.py:315-347): interleaved pairs (2i, 2i+1); pairs 0..15 of a head
         // (d0 == 0) rotate by (x+1)*theta_i, pairs 16..31 (d0 == 32) by (y+1)*theta_i, the cls token by 0.
         int r = 0;
@@ -161,7 +161,7 @@ __device__ __forceinline__ void epilogue_store(const EpiParams& ep, int row, int
           acc[j + 1] = bb * cs.x + a * cs.y;
         }
       }
-      __nv_bfloat16* dst = (which == 0 ? ep.q : ep.k) + (bh * ep.seq_pad + t) * 64 + d0;
+      __nv_bfloat16* dst = (which == 0 ? ep.q : (which == 1 ? ep.k : ep.vt)) + (bh * ep.seq_pad + t) * 64 + d0;
 #pragma unroll
       for (int j = 0; j < 32; j += 8) {
         uint4 u;
@@ -169,11 +169,6 @@ __device__ __forceinline__ void epilogue_store(const EpiParams& ep, int row, int
         u.z = pack_bf16(acc[j + 4], acc[j + 5]); u.w = pack_bf16(acc[j + 6], acc[j + 7]);
         *reinterpret_cast<uint4*>(dst + j) = u;
       }
-    } else {
-      // V stored transposed [b, head, d, seq_pad] so that P.V sees a K-major B operand
-      __nv_bfloat16* dst = ep.vt + (bh * 64 + d0) * ep.seq_pad + t;
-#pragma unroll
-      for (int j = 0; j < 32; ++j) dst[static_cast<size_t>(j) * ep.seq_pad] = __float2bfloat16_rn(acc[j]);
     }
   } else if constexpr (EPI == EPI_PATCH) {
     const int b = row / ep.patches;
@@ -337,16 +332,7 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& ep, int row0, in
     const int within = col - which * ep.width;
     const int head = within >> 6, d0 = within & 63;
     const int row = row0 + lane;
-    if (which == 2) {  // V^T [b, head, d, seq_pad]: consecutive lanes = consecutive tokens -> 64-byte runs per d
-      if (row < M) {
-        const int b = row / ep.seq, t = row - b * ep.seq;
-        __nv_bfloat16* dst = ep.vt + ((static_cast<size_t>(b) * ep.heads + head) * 64 + d0) * ep.seq_pad + t;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) dst[static_cast<size_t>(j) * ep.seq_pad] = __float2bfloat16_rn(acc[j]);
-      }
-      return;
-    }
-    if (ep.rope_tab != nullptr) {
+    if (ep.rope_tab != nullptr && which < 2) {
       // 2D RoPE with a cls token (rope.py:315-347): interleaved pairs (2i, 2i+1); pairs 0..15 of a head
       // (d0 == 0) rotate by (x+1)*theta_i, pairs 16..31 (d0 == 32) by (y+1)*theta_i, the cls token by 0.
       const int t = row % ep.seq;
@@ -366,7 +352,7 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& ep, int row0, in
     for (int j = 0; j < 16; ++j) in[j] = pack_bf16(acc[2 * j], acc[2 * j + 1]);
     uint4 o[4];
     stage_exchange(st, lane, in, o);
-    __nv_bfloat16* base = which == 0 ? ep.q : ep.k;
+    __nv_bfloat16* base = which == 0 ? ep.q : (which == 1 ? ep.k : ep.vt);   // V is [b, head, seq_pad, 64] like K (MN-major B operand of P.V)
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int r = row0 + 8 * i + rsub;

@@ -163,6 +163,13 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
          (static_cast<uint32_t>(M >> 4) << 24);
 }
 
+// Same with the B operand MN-major (bit 16): B tile stored [k][n] with n contiguous — e.g. V [keys, head_dim] as the
+// B operand of P.V, loaded by TMA as 128-byte rows (one row per key) under the 128B swizzle.  Canonical layout
+// (cute/atom/mma_traits_sm100.hpp, make_umma_desc<Major::MN>, B128): ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units, so
+// the same descriptor fields as the K-major tile apply (SBO = 1024 B between groups of 8 k-rows); one K=16 step = 2 groups
+// = +2048 B on the start address.
+__host__ __device__ constexpr uint32_t umma_idesc_bf16_bmn(int M, int N) { return umma_idesc_bf16(M, N) | (1u << 16); }
+
 // single-instruction MUFU approximations (2 ulp): exp2 and reciprocal without the range fix-ups of exp2f / 1.f/x
 __device__ __forceinline__ float fast_ex2(float x) {
   float y;

@@ -75,6 +75,58 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// The decoder's image-side LayerNorm (norm4, sam/transformer.py:209-210) over [prompts*4096, 256] is pure HBM streaming
+// (3 GB per call at 256 prompts): one warp normalises 4 rows per iteration and issues all of their loads (8 float4 per
+// lane + the positional table) before the first reduction, so enough bytes are in flight to cover the DRAM latency.
+__global__ void __launch_bounds__(256)
+    sam_ln256_kernel(const float* __restrict__ x, int rows, const float* __restrict__ g, const float* __restrict__ b, float eps,
+                     float* __restrict__ out32, __nv_bfloat16* __restrict__ out16, __nv_bfloat16* __restrict__ out16b,
+                     const float* __restrict__ add, int add_mod) {
+  const int lane = threadIdx.x & 31;
+  const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int nwarps = gridDim.x * (blockDim.x >> 5);
+  const float4 g0 = __ldg(reinterpret_cast<const float4*>(g) + lane), g1 = __ldg(reinterpret_cast<const float4*>(g) + 32 + lane);
+  const float4 b0 = __ldg(reinterpret_cast<const float4*>(b) + lane), b1 = __ldg(reinterpret_cast<const float4*>(b) + 32 + lane);
+  for (int r0 = warp * 4; r0 < rows; r0 += nwarps * 4) {
+    float4 v[4][2], a[4][2];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int r = min(r0 + j, rows - 1);
+      const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(r) * 256);
+      v[j][0] = xr[lane]; v[j][1] = xr[32 + lane];
+      if (out16b) {
+        const float4* ar = reinterpret_cast<const float4*>(add + static_cast<size_t>(r % add_mod) * 256);
+        a[j][0] = __ldg(ar + lane); a[j][1] = __ldg(ar + 32 + lane);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float sum = v[j][0].x + v[j][0].y + v[j][0].z + v[j][0].w + v[j][1].x + v[j][1].y + v[j][1].z + v[j][1].w;
+      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      const float mean = sum * (1.f / 256.f);
+      float4 d0 = make_float4(v[j][0].x - mean, v[j][0].y - mean, v[j][0].z - mean, v[j][0].w - mean);
+      float4 d1 = make_float4(v[j][1].x - mean, v[j][1].y - mean, v[j][1].z - mean, v[j][1].w - mean);
+      float var = d0.x * d0.x + d0.y * d0.y + d0.z * d0.z + d0.w * d0.w + d1.x * d1.x + d1.y * d1.y + d1.z * d1.z + d1.w * d1.w;
+      for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+      const float rstd = rsqrtf(var * (1.f / 256.f) + eps);
+      const int r = r0 + j;
+      if (r >= rows) continue;
+      const float4 y0 = make_float4(d0.x * rstd * g0.x + b0.x, d0.y * rstd * g0.y + b0.y, d0.z * rstd * g0.z + b0.z, d0.w * rstd * g0.w + b0.w);
+      const float4 y1 = make_float4(d1.x * rstd * g1.x + b1.x, d1.y * rstd * g1.y + b1.y, d1.z * rstd * g1.z + b1.z, d1.w * rstd * g1.w + b1.w);
+      const size_t base = static_cast<size_t>(r) * 64;   // in float4 / uint2 units
+      if (out32) { reinterpret_cast<float4*>(out32)[base + lane] = y0; reinterpret_cast<float4*>(out32)[base + 32 + lane] = y1; }
+      if (out16) {
+        reinterpret_cast<uint2*>(out16)[base + lane] = make_uint2(pack_bf16(y0.x, y0.y), pack_bf16(y0.z, y0.w));
+        reinterpret_cast<uint2*>(out16)[base + 32 + lane] = make_uint2(pack_bf16(y1.x, y1.y), pack_bf16(y1.z, y1.w));
+      }
+      if (out16b) {
+        reinterpret_cast<uint2*>(out16b)[base + lane] = make_uint2(pack_bf16(y0.x + a[j][0].x, y0.y + a[j][0].y), pack_bf16(y0.z + a[j][0].z, y0.w + a[j][0].w));
+        reinterpret_cast<uint2*>(out16b)[base + 32 + lane] = make_uint2(pack_bf16(y1.x + a[j][1].x, y1.y + a[j][1].y), pack_bf16(y1.z + a[j][1].z, y1.w + a[j][1].w));
+      }
+    }
+  }
+}
+
 // out16[i] = bf16(a[i] + b[(i / width % b_mod) * width + i % width])   (b optional): f32 -> bf16 GEMM operands
 __global__ void add_cast_kernel(const float* __restrict__ a, const float* __restrict__ b, int b_mod, int width, size_t n4,
                                 __nv_bfloat16* __restrict__ out16, float* __restrict__ out32) {
@@ -307,19 +359,27 @@ __global__ void __launch_bounds__(256) sam_i2t_attn_kernel(const __nv_bfloat16* 
 // [P, (2g)^2 pixels in (y,x,sub) order, 64].  One warp per (row, sub-pixel).
 __global__ void __launch_bounds__(256) sam_up1_kernel(const float* __restrict__ dc1, size_t n_items, const float* __restrict__ lw,
                                                       const float* __restrict__ lb, __nv_bfloat16* __restrict__ up1) {
-  const size_t item = static_cast<size_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
-  if (item >= n_items) return;
-  const float2 v = *reinterpret_cast<const float2*>(dc1 + item * 64 + 2 * lane);
-  float s = v.x + v.y;
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  const float u = s / 64.f;
-  const float a = v.x - u, b = v.y - u;
-  float q = a * a + b * b;
-  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-  const float r = 1.f / sqrtf(q / 64.f + 1e-6f);
-  const float y0 = lw[2 * lane] * (a * r) + lb[2 * lane], y1 = lw[2 * lane + 1] * (b * r) + lb[2 * lane + 1];
-  *reinterpret_cast<uint32_t*>(up1 + item * 64 + 2 * lane) = pack_bf16(gelu_erf(y0), gelu_erf(y1));
+  const size_t warp = static_cast<size_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  const size_t nwarps = static_cast<size_t>(gridDim.x) * 8;
+  const float w0 = lw[2 * lane], w1 = lw[2 * lane + 1], c0 = lb[2 * lane], c1 = lb[2 * lane + 1];
+  for (size_t i0 = warp * 8; i0 < n_items; i0 += nwarps * 8) {   // 8 items (64 channels each) per warp: 8 loads in flight
+    float2 v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = *reinterpret_cast<const float2*>(dc1 + min(i0 + j, n_items - 1) * 64 + 2 * lane);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float s = v[j].x + v[j].y;
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      const float u = s / 64.f;
+      const float a = v[j].x - u, b = v[j].y - u;
+      float q = a * a + b * b;
+      for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+      const float r = 1.f / sqrtf(q / 64.f + 1e-6f);
+      if (i0 + j < n_items)
+        *reinterpret_cast<uint32_t*>(up1 + (i0 + j) * 64 + 2 * lane) = pack_bf16(gelu_erf(w0 * (a * r) + c0), gelu_erf(w1 * (b * r) + c1));
+    }
+  }
 }
 
 // masks = hyper_in @ upscaled (mask_decoder.py:225-226) for mask tokens 1..3 (multimask_output, :141-143):
@@ -657,6 +717,11 @@ int ln(const float* x, int rows, int width, const float* g, const float* b, floa
        __nv_bfloat16* o16b, const float* add, int add_mod, cudaStream_t st) {
   OVO_REQUIRE(width % 4 == 0 && width <= 2048, "sam layernorm: unsupported width %d", width);
   ProfScope prof(st, PROF_LN, 0.0, static_cast<double>(rows) * width * 8.0);
+  if (width == 256 && rows >= 65536) {
+    sam_ln256_kernel<<<num_sms() * 8, 256, 0, st>>>(x, rows, g, b, eps, o32, o16, o16b, add, add_mod);
+    OVO_CHECK_LAUNCH();
+    return OVO_OK;
+  }
   sam_ln_kernel<<<ceil_div(rows, 8), 256, 0, st>>>(x, rows, width, g, b, eps, o32, o16, o16b, add, add_mod);
   OVO_CHECK_LAUNCH();
   return OVO_OK;
@@ -1036,7 +1101,7 @@ static int sam_predict_impl(ovo_sam_t* s, const float* points_dev, int P, float*
   OVO_TRY(t2i_block(s, s->w.final_attn, s->big_k, s->big_v, static_cast<size_t>(HW) * kInt, P, s->w.norm_final_w, s->w.norm_final_b, st));
   // hs = s->queries.  Upscaling (mask_decoder.py:210-217): two k2 s2 transposed convs as GEMMs with N = 4*C_out
   OVO_TRY(gemm(EPI_F32_RESID, s->keys_bf, kC, s->w.up0_w, kC, static_cast<int>(PHW), 256, kC, s->w.up0_b, s->dc1, 256, s->s1_sub, 256, HW, st));
-  sam_up1_kernel<<<ceil_div(static_cast<long long>(PHW) * 4, 8), 256, 0, st>>>(s->dc1, PHW * 4, s->w.up_ln_w, s->w.up_ln_b, s->up1);
+  sam_up1_kernel<<<num_sms() * 8, 256, 0, st>>>(s->dc1, PHW * 4, s->w.up_ln_w, s->w.up_ln_b, s->up1);
   OVO_CHECK_LAUNCH();
   OVO_TRY(gemm(EPI_BF16_GELU, s->up1, 64, s->w.up1_w, 64, static_cast<int>(PHW * 4), 128, 64, s->w.up1_b, s->up2, 128, s->s0_sub, 128, 4 * HW, st));
   // hypernetwork MLPs on the 4 mask tokens (:219-224) and the IoU head (:229)

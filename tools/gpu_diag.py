@@ -326,9 +326,9 @@ def stage_gemmshapes():
     import ctypes as C
     from ovo_b200 import _lib
     lib = _lib.lib()
-    names = {0: "f32", 1: "bf16", 2: "gelu", 3: "resid", 6: "relu"}
+    names = {0: "f32", 1: "bf16", 2: "gelu", 3: "resid", 4: "qkv", 6: "relu"}
     shapes = [("vit out-proj", 3, 9232, 1024, 1024), ("vit fc2", 3, 9232, 1024, 4096), ("vit fc1", 2, 9232, 4096, 1024),
-              ("vit qkv~bf16", 1, 9232, 3072, 1024),
+              ("vit qkv~bf16", 1, 9232, 3072, 1024), ("vit qkv", 4, 9232, 3072, 1024),
               ("sam s3 qkv", 1, 4096, 1728, 576), ("sam s3 proj", 3, 4096, 576, 576), ("sam s3 fc1", 2, 4096, 2304, 576),
               ("sam s3 fc2", 3, 4096, 576, 2304), ("sam s1 qkv", 1, 65536, 432, 144), ("sam s1 fc1", 2, 65536, 576, 144),
               ("sam s2 fc1", 2, 16384, 1152, 288), ("sam dec kproj", 1, 1048576, 128, 256), ("sam dec oproj", 3, 1048576, 256, 128),
