@@ -300,20 +300,20 @@ __global__ void __launch_bounds__(256) sam_self_attn_kernel(const __nv_bfloat16*
 
 // image -> token cross attention: every image token attends to the 8 prompt tokens, 8 heads of 16.
 // q [q_batch * n_img, 128] (q_stride = 0: shared queries, layer 0); k,v [P*8,128]; out [P*n_img,128].
-// One thread per (prompt, image token, head).
+// One thread per (prompt, image token, head); a warp = one head x 32 consecutive tokens, so every k/v read from shared
+// memory is a warp-wide broadcast (one wavefront) and a block (8 warps = 8 heads) covers 32 whole 256-byte token rows.
 __global__ void __launch_bounds__(256) sam_i2t_attn_kernel(const __nv_bfloat16* __restrict__ q, size_t q_stride, const __nv_bfloat16* __restrict__ k,
                                                            const __nv_bfloat16* __restrict__ v, int n_img, __nv_bfloat16* __restrict__ out) {
-  // [token][head][20 floats]: the 8 heads a quarter-warp reads with one float4 request land in 8 distinct bank groups
-  __shared__ __align__(16) float sk[kTok][8][20], sv[kTok][8][20];
+  __shared__ __align__(16) float sk[8][kTok][16], sv[8][kTok][16];   // [head][token][dim]
   const int p = blockIdx.y;
   for (int i = threadIdx.x; i < kTok * kInt; i += 256) {
     const int a = i >> 7, h = (i >> 4) & 7, d = i & 15;
-    sk[a][h][d] = __bfloat162float(k[static_cast<size_t>(p) * kTok * kInt + i]) * 0.25f;   // 16^-0.5 folded into k
-    sv[a][h][d] = __bfloat162float(v[static_cast<size_t>(p) * kTok * kInt + i]);
+    sk[h][a][d] = __bfloat162float(k[static_cast<size_t>(p) * kTok * kInt + i]) * 0.25f;   // 16^-0.5 folded into k
+    sv[h][a][d] = __bfloat162float(v[static_cast<size_t>(p) * kTok * kInt + i]);
   }
   __syncthreads();
-  const int idx = blockIdx.x * 256 + threadIdx.x;   // (token, head)
-  const int t = idx >> 3, h = idx & 7;
+  const int h = threadIdx.x >> 5;
+  const int t = blockIdx.x * 32 + (threadIdx.x & 31);
   if (t >= n_img) return;
   const uint4* qp = reinterpret_cast<const uint4*>(q + static_cast<size_t>(p) * q_stride + static_cast<size_t>(t) * kInt + h * 16);
   uint4 raw[2] = {qp[0], qp[1]};
@@ -327,7 +327,7 @@ __global__ void __launch_bounds__(256) sam_i2t_attn_kernel(const __nv_bfloat16* 
     float x = 0.f;
 #pragma unroll
     for (int d4 = 0; d4 < 4; ++d4) {
-      const float4 kk = *reinterpret_cast<const float4*>(&sk[a][h][4 * d4]);
+      const float4 kk = *reinterpret_cast<const float4*>(&sk[h][a][4 * d4]);
       x += qf[4 * d4] * kk.x + qf[4 * d4 + 1] * kk.y + qf[4 * d4 + 2] * kk.z + qf[4 * d4 + 3] * kk.w;
     }
     s[a] = x; m = fmaxf(m, x);
@@ -343,7 +343,7 @@ __global__ void __launch_bounds__(256) sam_i2t_attn_kernel(const __nv_bfloat16* 
   for (int a = 0; a < kTok; ++a)
 #pragma unroll
     for (int d4 = 0; d4 < 4; ++d4) {
-      const float4 vv = *reinterpret_cast<const float4*>(&sv[a][h][4 * d4]);
+      const float4 vv = *reinterpret_cast<const float4*>(&sv[h][a][4 * d4]);
       o[4 * d4] += s[a] * vv.x; o[4 * d4 + 1] += s[a] * vv.y; o[4 * d4 + 2] += s[a] * vv.z; o[4 * d4 + 3] += s[a] * vv.w;
     }
   uint4 w[2];
@@ -359,25 +359,28 @@ __global__ void __launch_bounds__(256) sam_i2t_attn_kernel(const __nv_bfloat16* 
 // [P, (2g)^2 pixels in (y,x,sub) order, 64].  One warp per (row, sub-pixel).
 __global__ void __launch_bounds__(256) sam_up1_kernel(const float* __restrict__ dc1, size_t n_items, const float* __restrict__ lw,
                                                       const float* __restrict__ lb, __nv_bfloat16* __restrict__ up1) {
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, sub = lane & 15, hw = lane >> 4;   // 16 lanes x float4 = one item of 64 channels
   const size_t warp = static_cast<size_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   const size_t nwarps = static_cast<size_t>(gridDim.x) * 8;
-  const float w0 = lw[2 * lane], w1 = lw[2 * lane + 1], c0 = lb[2 * lane], c1 = lb[2 * lane + 1];
-  for (size_t i0 = warp * 8; i0 < n_items; i0 += nwarps * 8) {   // 8 items (64 channels each) per warp: 8 loads in flight
-    float2 v[8];
+  const float4 w = __ldg(reinterpret_cast<const float4*>(lw) + sub), c = __ldg(reinterpret_cast<const float4*>(lb) + sub);
+  for (size_t i0 = warp * 16; i0 < n_items; i0 += nwarps * 16) {   // 16 items per warp iteration: 8 x 16-byte loads in flight per lane
+    float4 v[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = *reinterpret_cast<const float2*>(dc1 + min(i0 + j, n_items - 1) * 64 + 2 * lane);
+    for (int j = 0; j < 8; ++j) v[j] = *reinterpret_cast<const float4*>(dc1 + min(i0 + 2 * j + hw, n_items - 1) * 64 + 4 * sub);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      float s = v[j].x + v[j].y;
-      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      float s = (v[j].x + v[j].y) + (v[j].z + v[j].w);
+      for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
       const float u = s / 64.f;
-      const float a = v[j].x - u, b = v[j].y - u;
-      float q = a * a + b * b;
-      for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+      const float a0 = v[j].x - u, a1 = v[j].y - u, a2 = v[j].z - u, a3 = v[j].w - u;
+      float q = (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+      for (int o = 8; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
       const float r = 1.f / sqrtf(q / 64.f + 1e-6f);
-      if (i0 + j < n_items)
-        *reinterpret_cast<uint32_t*>(up1 + (i0 + j) * 64 + 2 * lane) = pack_bf16(gelu_erf(w0 * (a * r) + c0), gelu_erf(w1 * (b * r) + c1));
+      const size_t item = i0 + 2 * j + hw;
+      if (item < n_items)
+        *reinterpret_cast<uint2*>(up1 + item * 64 + 4 * sub) =
+            make_uint2(pack_bf16(gelu_erf(w.x * (a0 * r) + c.x), gelu_erf(w.y * (a1 * r) + c.y)),
+                       pack_bf16(gelu_erf(w.z * (a2 * r) + c.z), gelu_erf(w.w * (a3 * r) + c.w)));
     }
   }
 }
@@ -449,21 +452,40 @@ __device__ __forceinline__ float bilin_sample(const float* __restrict__ m, int w
 
 struct MaskStat { int hi, lo, area, x0, y0, x1, y1, pad; };   // counts of logit > +off, > -off, > 0; bbox of > 0
 
-// candidates = masks with iou > pred_iou_thresh (cand[j] = flattened index).  grid (tiles, n_cand)
+// candidates = masks with iou > pred_iou_thresh (cand[j] = flattened index).  grid (row bands, n_cand); the per-column
+// interpolation table (x0, x1, lambda) is staged once per block in shared memory, the per-row one lives in registers.
+constexpr int kAmgMaxW = 2048;
 __global__ void __launch_bounds__(256) amg_stats_kernel(const float* __restrict__ low, const int* __restrict__ cand, int h, int w, int H, int W,
                                                         float off, MaskStat* __restrict__ stats) {
+  __shared__ short s_x0[kAmgMaxW], s_x1[kAmgMaxW];
+  __shared__ float s_lx[kAmgMaxW];
   const int j = blockIdx.y;
   const float* m = low + static_cast<size_t>(cand[j]) * h * w;
   const float sy = static_cast<float>(h) / H, sx = static_cast<float>(w) / W;
-  int hi = 0, lo = 0, area = 0, x0 = W, y0 = H, x1 = -1, y1 = -1;
-  for (int i = blockIdx.x * 256 + threadIdx.x; i < H * W; i += gridDim.x * 256) {
-    const int y = i / W, x = i - y * W;
-    int ya, yb, xa, xb; float ly, lx;
-    bilin_axis(y, sy, h, ya, yb, ly);
+  for (int x = threadIdx.x; x < W; x += 256) {
+    int xa, xb; float lx;
     bilin_axis(x, sx, w, xa, xb, lx);
-    const float v = bilin_sample(m, w, ya, yb, xa, xb, ly, lx);
-    hi += v > off; lo += v > -off;
-    if (v > 0.f) { ++area; x0 = min(x0, x); x1 = max(x1, x); y0 = min(y0, y); y1 = max(y1, y); }
+    s_x0[x] = static_cast<short>(xa); s_x1[x] = static_cast<short>(xb); s_lx[x] = lx;
+  }
+  __syncthreads();
+  const int rows_per = (H + gridDim.x - 1) / gridDim.x;
+  const int r_lo = blockIdx.x * rows_per, r_hi = min(H, r_lo + rows_per);
+  int hi = 0, lo = 0, area = 0, x0 = W, y0 = H, x1 = -1, y1 = -1;
+  for (int y = r_lo; y < r_hi; ++y) {
+    int ya, yb; float ly;
+    bilin_axis(y, sy, h, ya, yb, ly);
+    const float hy = __fadd_rn(1.f, -ly);
+    const float* ra = m + ya * w;
+    const float* rb = m + yb * w;
+    for (int x = threadIdx.x; x < W; x += 256) {
+      const int xa = s_x0[x], xb = s_x1[x];
+      const float lx = s_lx[x], hx = __fadd_rn(1.f, -lx);
+      const float top = __fadd_rn(__fmul_rn(hx, ra[xa]), __fmul_rn(lx, ra[xb]));
+      const float bot = __fadd_rn(__fmul_rn(hx, rb[xa]), __fmul_rn(lx, rb[xb]));
+      const float v = __fadd_rn(__fmul_rn(hy, top), __fmul_rn(ly, bot));
+      hi += v > off; lo += v > -off;
+      if (v > 0.f) { ++area; x0 = min(x0, x); x1 = max(x1, x); y0 = min(y0, y); y1 = max(y1, y); }
+    }
   }
   for (int s = 16; s > 0; s >>= 1) {
     hi += __shfl_xor_sync(0xffffffffu, hi, s); lo += __shfl_xor_sync(0xffffffffu, lo, s); area += __shfl_xor_sync(0xffffffffu, area, s);
@@ -1088,7 +1110,7 @@ static int sam_predict_impl(ovo_sam_t* s, const float* points_dev, int P, float*
     }
     {
       ProfScope prof(st, PROF_ATTN, 4.0 * static_cast<double>(PHW) * 8 * kTok * 16, 0.0);
-      sam_i2t_attn_kernel<<<dim3(ceil_div(HW * 8, 256), P), 256, 0, st>>>(qsrc, qstride, s->t_k, s->t_v, HW, s->big_k /* out */);
+      sam_i2t_attn_kernel<<<dim3(ceil_div(HW, 32), P), 256, 0, st>>>(qsrc, qstride, s->t_k, s->t_v, HW, s->big_k /* out */);
       OVO_CHECK_LAUNCH();
     }
     OVO_TRY(gemm(EPI_F32_RESID, s->big_k, kInt, L.i2t.o_w, kInt, static_cast<int>(PHW), kC, kInt, L.i2t.o_b, s->keys_pre, kC,
@@ -1147,8 +1169,9 @@ int ovo_sam_postprocess(ovo_sam_t* s, const float* low_dev, const float* iou_dev
   if (n_cand == 0) { *n_out = 0; return OVO_OK; }
   amg_stats_init_kernel<<<ceil_div(n_cand, 256), 256, 0, st>>>(s->stats, n_cand, H, W);
   OVO_CHECK_LAUNCH();
+  OVO_REQUIRE(W <= kAmgMaxW && h < 32768 && w < 32768, "ovo_sam_postprocess: frame width %d unsupported (max %d)", W, kAmgMaxW);
   const int tiles = std::max(1, std::min(ceil_div(H * W, 256 * 8), 64));
-  amg_stats_kernel<<<dim3(tiles, n_cand), 256, 0, st>>>(low_dev, s->cand, h, w, H, W, prm->stability_offset, s->stats);
+  amg_stats_kernel<<<dim3(std::min(H, 16), n_cand), 256, 0, st>>>(low_dev, s->cand, h, w, H, W, prm->stability_offset, s->stats);
   OVO_CHECK_LAUNCH();
   amg_decide_kernel<<<1, 1024, 0, st>>>(s->stats, s->cand, iou_dev, prm->stability_thresh, prm->box_nms_thresh, s->counters, s->sel,
                                        iou_out, stab_out, boxes_out, src_out, max_out);
