@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libovo_b200.so")
+LIB_PATH = os.environ.get("OVO_B200_LIB") or os.path.join(_HERE, "libovo_b200.so")   # the override is an A/B measurement aid
 
 c_void_p, c_int, c_float, c_int64 = C.c_void_p, C.c_int, C.c_float, C.c_int64
 

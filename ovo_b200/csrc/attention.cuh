@@ -2,12 +2,18 @@
 // at pe.py:145-147 for the vision tower, nn.MultiheadAttention with the causal mask pe.py:621-627 for text).
 //
 // One CTA = one (image, head, 128-query tile), 256 threads: two threads per query row, each owning half of the keys
-// of a block and half of the output columns (the softmax is issue/latency bound, so warps per SM matter).  TWO CTAs
-// are resident per SM (112 KB smem, 256 TMEM columns each): one CTA's softmax overlaps the other's tensor-core work.
-// Q (128x64) is TMA-loaded once; K (128x64) and V (128x64, used as an MN-major B operand: no transposed copy of V is
-// ever made) blocks stream through 2-slot rings of 128B-swizzled shared memory.  Per 128-key block: S = Q.K^T (tcgen05, accumulator in TMEM) -> tcgen05.ld -> online softmax in
-// registers (one thread per query row, exp2f) -> P (bf16) written to swizzled smem -> O_j = P.V_j (tcgen05,
-// issued together with the next block's Q.K^T) -> tcgen05.ld -> rescale-and-accumulate in registers.
+// of a block and half of the output columns.  TWO CTAs are resident per SM (114 KB smem, 256 TMEM columns each): one
+// CTA's softmax overlaps the other's tensor-core work.  Q (128x64) is TMA-loaded once; K (128x64) and V (128x64, used
+// as an MN-major B operand: no transposed copy of V is ever made) blocks stream through 2-slot rings of 128B-swizzled
+// shared memory.
+//
+// Per 128-key block: S = Q.K^T (tcgen05, accumulator in TMEM) -> ONE pass over S: tcgen05.ld, p = exp2(s*scale - m),
+// P (bf16) -> swizzled smem -> O += P.V accumulated IN TMEM across all blocks (issued together with the next block's
+// Q.K^T).  The reference maximum m of a row is fixed after the first block (the only block that needs a separate max
+// pass) and only raised — with a rescale of the TMEM accumulator by tcgen05.ld/st — if a later block's maximum exceeds
+// it by more than 2^kRescaleLog2: f32/bf16 carry an 8-bit exponent, so p up to 2^32 is exact enough and the final
+// O / l division cancels the common factor.  Per block this removes a second pass over S, the per-block read-back of O
+// and the cross-half maximum exchange (two block-wide barriers) of the textbook online softmax.
 // q/k/v are produced in exactly this layout by the QKV GEMM epilogue (gemm.cuh EPI_QKV).
 #pragma once
 #include "ptx.cuh"
@@ -22,8 +28,13 @@ struct AttnSmem {
   static constexpr int kKBlock = 128 * 64 * 2;  // 16 KB per 128 keys
   static constexpr int kVBlock = 64 * 64 * 2;   // 8 KB per 64 keys (V rows of 128 B); one 128-key block = 2 of them, one TMA
   static constexpr int kP = 2 * 128 * 64 * 2;   // 32 KB: P as two K-major 128x64 tiles
-  static constexpr int kBytes = kQ + 2 * kKBlock + 4 * kVBlock + kP + 256 + 512;  // 112 KB + barriers + row exchange
+  // 112 KB + barriers.  Two CTAs per SM need 2 * (kBytes + 1 KB) <= 228 KB, so there is no room for a dedicated row-exchange
+  // buffer: the rare cross-half exchanges (first block's maximum, a rescale, the final row sum) borrow the P tile while no
+  // MMA reads it.
+  static constexpr int kBytes = kQ + 2 * kKBlock + 4 * kVBlock + kP + 256;
 };
+
+constexpr float kRescaleLog2 = 32.f;   // raise a row's reference maximum only when a block exceeds it by 2^32
 
 __global__ void __launch_bounds__(kAttnThreads, 2)
     attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -40,9 +51,9 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
   uint64_t* bar_k = bars;       // [2]  (bar_k[0] also covers Q on its first use)
   uint64_t* bar_v = bars + 2;   // [2]
   uint64_t* bar_s = bars + 4;   // S ready
-  uint64_t* bar_o = bars + 5;   // P.V ready
+  uint64_t* bar_o = bars + 5;   // P.V done
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
-  float* s_x = reinterpret_cast<float*>(sP + AttnSmem::kP + 256);  // [128] per-row exchange between the two halves
+  float* s_x = reinterpret_cast<float*>(sP);   // [half][128] scratch inside the P tile (only while no P.V is in flight)
 
   const int tid = threadIdx.x, warp = tid >> 5;
   const int qt = blockIdx.x;  // query tile
@@ -96,14 +107,14 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
     issue_qk(0);
   }
 
-  // per-thread state: thread (row, half) owns query row `row`, keys [64*half, 64*half+64) of every block and output
-  // columns [32*half, 32*half+32)
+  // thread (row, half) owns query row `row`, keys [64*half, 64*half+64) of every block and output columns
+  // [32*half, 32*half+32) of the accumulator in TMEM
   const int row = tid & 127, half = tid >> 7;
   const int qrow = q0 + row;
-  float m_run = -INFINITY, l_run = 0.f;  // l_run: partial row sum over this thread's keys (same m for both halves)
-  float o_acc[32];
-#pragma unroll
-  for (int i = 0; i < 32; ++i) o_acc[i] = 0.f;
+  float m_used = -INFINITY;      // the row's reference maximum (raw score units), identical in both halves
+  float l_run = 0.f;             // partial row sum over this thread's keys
+  float m_loc = -INFINITY;       // maximum this thread has seen over its keys so far
+  int rescale = 0;               // CTA-uniform: some row's maximum outgrew its reference by 2^kRescaleLog2 in the last block
   const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
   const int r8 = row & 7;
   uint8_t* p_row = sP + half * (128 * 128) + (row >> 3) * 1024 + r8 * 128;  // P tile `half` = this thread's 64 keys
@@ -119,50 +130,77 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
     if (causal) kv_hi = min(kv_hi, qrow - kv0 + 1);  // keys > query are masked
     // blocks that are entirely valid (all but the last one, and no causal diagonal) skip the per-element masking
     const bool full = !causal && (j * 128 + 128 <= seq);   // CTA uniform
-    // pass 1: row max over this thread's 64 keys (independent partial maxima: no long dependent chain)
-    float mp[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+
+    if (j == 0) {
+      // first block: the reference maximum of the row = its maximum over block 0 (both halves)
+      float mp[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll 1
-    for (int c = 0; c < ((dbg & 1) ? 0 : 2); ++c) {
-      uint32_t v[32];
-      tmem_ld_32x32(tmem_S + lane_off + half * 64 + c * 32, v);
-      tmem_ld_wait();
-      if (full) {
+      for (int c = 0; c < 2; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_S + lane_off + half * 64 + c * 32, v);
+        tmem_ld_wait();
+        if (full) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) mp[i & 3] = fmaxf(mp[i & 3], __uint_as_float(v[i]));
-      } else {
+          for (int i = 0; i < 32; ++i) mp[i & 3] = fmaxf(mp[i & 3], __uint_as_float(v[i]));
+        } else {
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (c * 32 + i < kv_hi) mp[i & 3] = fmaxf(mp[i & 3], __uint_as_float(v[i]));
+          for (int i = 0; i < 32; ++i)
+            if (c * 32 + i < kv_hi) mp[i & 3] = fmaxf(mp[i & 3], __uint_as_float(v[i]));
+        }
+      }
+      const float mine = fmaxf(fmaxf(mp[0], mp[1]), fmaxf(mp[2], mp[3]));
+      s_x[half * 128 + row] = mine;
+      __syncthreads();
+      m_used = fmaxf(mine, s_x[(1 - half) * 128 + row]);
+      m_loc = mine;
+      __syncthreads();                               // the scratch lives in the P tile that is written next
+    } else {
+      // P.V_{j-1} has completed (it was issued before Q.K_j^T): the P tile, V slot (j-1)&1 and the accumulator are free
+      mbar_wait(bar_o, (j - 1) & 1);
+      tc_fence_after();
+      if (tid == 0 && j + 1 < nb) load_v(j + 1);
+      if (rescale) {   // rare, CTA-uniform (dbg 16: whenever a maximum grows, for the tests)
+        s_x[half * 128 + row] = m_loc;
+        __syncthreads();
+        const float m_new = fmaxf(m_used, fmaxf(m_loc, s_x[(1 - half) * 128 + row]));   // the same in both halves of the row
+        const float alpha = (m_new > m_used) ? fast_ex2((m_used - m_new) * scale_log2e) : 1.f;
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_O + lane_off + half * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+        tmem_st_32x32(tmem_O + lane_off + half * 32, v);
+        tmem_st_wait();
+        l_run *= alpha;
+        m_used = m_new;
+        __syncthreads();                             // scratch reads done before P is written again
       }
     }
-    float m_blk = fmaxf(fmaxf(mp[0], mp[1]), fmaxf(mp[2], mp[3]));
-    // both halves of a row must use the same maximum: half 1 publishes, half 0 combines and publishes back
-    if (!(dbg & 8)) {
-      if (half == 1) s_x[row] = m_blk;
-      __syncthreads();
-      if (half == 0) { m_blk = fmaxf(m_blk, s_x[row]); s_x[row] = m_blk; }
-      __syncthreads();
-      if (half == 1) m_blk = s_x[row];
-    }
-    const float m_new = fmaxf(m_run, m_blk);
-    const float m_scaled = (m_new == -INFINITY) ? 0.f : m_new * scale_log2e;
-    const float alpha = (m_run == -INFINITY) ? 0.f : fast_ex2(m_run * scale_log2e - m_scaled);
-    // pass 2: p = exp2(s*scale - m), partial row sum, P -> swizzled smem (bf16)
+    const float m_scaled = (m_used == -INFINITY) ? 0.f : m_used * scale_log2e;
+
+    // single pass: p = exp2(s*scale - m), partial row sum, block maximum, P -> swizzled smem (bf16)
     float lp[4] = {0.f, 0.f, 0.f, 0.f};
+    float mp[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll 1
-    for (int c = 0; c < ((dbg & 1) ? 0 : 2); ++c) {
+    for (int c = 0; c < 2; ++c) {
       uint32_t v[32];
       tmem_ld_32x32(tmem_S + lane_off + half * 64 + c * 32, v);
       tmem_ld_wait();
       float p[32];
       if (full) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) p[i] = fast_ex2(fmaf(__uint_as_float(v[i]), scale_log2e, -m_scaled));
+        for (int i = 0; i < 32; ++i) {
+          const float sv = __uint_as_float(v[i]);
+          p[i] = fast_ex2(fmaf(sv, scale_log2e, -m_scaled));
+          mp[i & 3] = fmaxf(mp[i & 3], sv);
+        }
       } else {
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          const float e = fast_ex2(fmaf(__uint_as_float(v[i]), scale_log2e, -m_scaled));
-          p[i] = (c * 32 + i < kv_hi) ? e : 0.f;
+          const float sv = __uint_as_float(v[i]);
+          const bool ok = c * 32 + i < kv_hi;
+          p[i] = ok ? fast_ex2(fmaf(sv, scale_log2e, -m_scaled)) : 0.f;
+          if (ok) mp[i & 3] = fmaxf(mp[i & 3], sv);
         }
       }
 #pragma unroll
@@ -176,15 +214,14 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
 #pragma unroll
       for (int i = 0; i < 32; ++i) lp[i & 3] += p[i];
     }
-    l_run = l_run * alpha + ((lp[0] + lp[1]) + (lp[2] + lp[3]));
-    m_run = m_new;
-#pragma unroll
-    for (int i = 0; i < 32; ++i) o_acc[i] *= alpha;
+    l_run += (lp[0] + lp[1]) + (lp[2] + lp[3]);
+    m_loc = fmaxf(m_loc, fmaxf(fmaxf(mp[0], mp[1]), fmaxf(mp[2], mp[3])));
+    const int need = m_loc > m_used + ((dbg & 16) ? 0.f : kRescaleLog2 / scale_log2e);
 
-    // P visible to the async proxy and every thread done reading S; then O_j = P.V_j and S_{j+1} = Q.K_{j+1}^T
-    if (!(dbg & 4)) fence_proxy_async_smem();
+    // P visible to the async proxy and every thread done reading S; then O += P.V_j and S_{j+1} = Q.K_{j+1}^T
+    fence_proxy_async_smem();
     tc_fence_before();
-    __syncthreads();
+    rescale = __syncthreads_or(need);
     if (tid == 0) {
       tc_fence_after();
       mbar_wait(&bar_v[j & 1], (j >> 1) & 1);
@@ -195,42 +232,32 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
         // keys 64t + 16k .. +15 of the block: 16 rows of 128 B = 2048 B per K=16 step
         const uint64_t vdesc = umma_desc_sw128(smem_u32(sV + (2 * (j & 1) + t) * AttnSmem::kVBlock));
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(tmem_O, pdesc + 2 * k, vdesc + 128 * k, idesc_o, (t | k) != 0);
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem_O, pdesc + 2 * k, vdesc + 128 * k, idesc_o, (j | t | k) != 0);
       }
       umma_commit(bar_o);
       if (j + 1 < nb) issue_qk(j + 1);
     }
-    __syncwarp();
-    mbar_wait(bar_o, j & 1);
-    tc_fence_after();
-    // V slot j&1 has been consumed by P.V_j: refill it with block j+2
-    if (tid == 0 && j + 2 < nb) load_v(j + 2);
-    if (!(dbg & 2)) {
-      uint32_t v[32];
-      tmem_ld_32x32(tmem_O + lane_off + half * 32, v);
-      tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < 32; ++i) o_acc[i] += __uint_as_float(v[i]);
-    }
-    tc_fence_before();  // these TMEM reads are ordered before the next P.V (issued after the next __syncthreads)
   }
 
-  // total row sum = sum of the two halves' partial sums
-  if (half == 1) s_x[row] = l_run;
+  // total row sum = sum of the two halves' partial sums; the accumulator is complete once the last P.V has landed
+  mbar_wait(bar_o, (nb - 1) & 1);                    // ... and the P tile is free to serve as scratch
+  tc_fence_after();
+  s_x[half * 128 + row] = l_run;
   __syncthreads();
-  if (half == 0) { l_run += s_x[row]; s_x[row] = l_run; }
-  __syncthreads();
-  if (half == 1) l_run = s_x[row];
+  l_run += s_x[(1 - half) * 128 + row];
+  uint32_t v[32];
+  tmem_ld_32x32(tmem_O + lane_off + half * 32, v);   // warp-collective: every lane, also the padding rows
+  tmem_ld_wait();
   if (qrow < seq) {
     const float inv = 1.f / l_run;
     __nv_bfloat16* dst = out + (static_cast<size_t>(b) * seq + qrow) * ld_out + head * 64 + half * 32;
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
       uint4 u;
-      u.x = pack_bf16(o_acc[8 * g] * inv, o_acc[8 * g + 1] * inv);
-      u.y = pack_bf16(o_acc[8 * g + 2] * inv, o_acc[8 * g + 3] * inv);
-      u.z = pack_bf16(o_acc[8 * g + 4] * inv, o_acc[8 * g + 5] * inv);
-      u.w = pack_bf16(o_acc[8 * g + 6] * inv, o_acc[8 * g + 7] * inv);
+      u.x = pack_bf16(__uint_as_float(v[8 * g]) * inv, __uint_as_float(v[8 * g + 1]) * inv);
+      u.y = pack_bf16(__uint_as_float(v[8 * g + 2]) * inv, __uint_as_float(v[8 * g + 3]) * inv);
+      u.z = pack_bf16(__uint_as_float(v[8 * g + 4]) * inv, __uint_as_float(v[8 * g + 5]) * inv);
+      u.w = pack_bf16(__uint_as_float(v[8 * g + 6]) * inv, __uint_as_float(v[8 * g + 7]) * inv);
       *reinterpret_cast<uint4*>(dst + 8 * g) = u;
     }
   }

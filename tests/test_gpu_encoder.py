@@ -87,6 +87,28 @@ def test_layer_by_layer_vs_oracle(tiny):
     assert torch.equal(a, b) and torch.equal(b, c)
 
 
+def test_attention_rescale_path(tiny):
+    """The attention kernel keeps a row's reference maximum fixed after the first key block and only rescales its TMEM
+    accumulator when a later block exceeds it by 2^32 (attention.cuh).  Debug bit 16 forces the rescale whenever the
+    maximum grows, so the tcgen05.ld/st rescale path is exercised; both modes must agree with the oracle."""
+    from ovo_b200 import _lib
+    enc, cfg, ocfg, sd = tiny
+    torch.manual_seed(2)
+    px = torch.randn(2, 3, 336, 336) * 0.5
+    with torch.no_grad():
+        ref = OE.vit_forward_features(px, sd, ocfg, n_layers=cfg.layers, norm=True)
+        ref1 = OE.vit_forward_features(px[:1], sd, ocfg, n_layers=1, norm=False)
+    try:
+        _lib.lib().ovo_set_gemm_cluster(16 << 24)
+        # (1 image, 1 layer) is a shape no other test uses: its first call runs eagerly with the debug bit
+        out = enc.forward_features_from_pixels(px.cuda()[:1], n_layers=1, ln_post=False)
+        _check(out, ref1, "forced rescale")
+    finally:
+        _lib.lib().ovo_set_gemm_cluster(0)
+    out2 = enc.forward_features_from_pixels(px.cuda())
+    _check(out2, ref, "lazy rescale")
+
+
 def test_batched_frames_equal_single_frames(tiny):
     """Batching keyframes changes nothing: features of frame f in a batch == features of frame f alone."""
     enc, cfg, ocfg, sd = tiny
