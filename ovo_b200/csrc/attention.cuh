@@ -2,18 +2,22 @@
 // at pe.py:145-147 for the vision tower, nn.MultiheadAttention with the causal mask pe.py:621-627 for text).
 //
 // One CTA = one (image, head, 128-query tile), 256 threads: two threads per query row, each owning half of the keys
-// of a block and half of the output columns.  TWO CTAs are resident per SM (114 KB smem, 256 TMEM columns each): one
-// CTA's softmax overlaps the other's tensor-core work.  Q (128x64) is TMA-loaded once; K (128x64) and V (128x64, used
-// as an MN-major B operand: no transposed copy of V is ever made) blocks stream through 2-slot rings of 128B-swizzled
-// shared memory.
+// of a block and half of the output columns.  TWO CTAs are resident per SM (112 KB smem, 256 TMEM columns each).
+// Q (128x64) is TMA-loaded once; K and V stream in 64-key blocks through 4-slot rings of 128B-swizzled shared memory
+// (V is consumed as an MN-major B operand: no transposed copy of V is ever made).
 //
-// Per 128-key block: S = Q.K^T (tcgen05, accumulator in TMEM) -> ONE pass over S: tcgen05.ld, p = exp2(s*scale - m),
-// P (bf16) -> swizzled smem -> O += P.V accumulated IN TMEM across all blocks (issued together with the next block's
-// Q.K^T).  The reference maximum m of a row is fixed after the first block (the only block that needs a separate max
-// pass) and only raised — with a rescale of the TMEM accumulator by tcgen05.ld/st — if a later block's maximum exceeds
-// it by more than 2^kRescaleLog2: f32/bf16 carry an 8-bit exponent, so p up to 2^32 is exact enough and the final
-// O / l division cancels the common factor.  Per block this removes a second pass over S, the per-block read-back of O
-// and the cross-half maximum exchange (two block-wide barriers) of the textbook online softmax.
+// Software pipeline over 64-key blocks with TWO score buffers in TMEM (S0, S1: 64 columns each) and two P tiles:
+//     tensor core : ... P.V_{j-1} | Q.K_{j+1}^T |          P.V_j | Q.K_{j+2}^T | ...
+//     softmax     :        block j (reads S_j, writes P_j)  |  block j+1 (S_{j+1} was issued one block earlier) ...
+// so the MMA -> tcgen05.ld -> exp2 -> P -> MMA dependency chain of a single-buffered loop is broken: while the threads
+// do the softmax of block j+1 the tensor core finishes P.V_j and computes S_{j+2}.
+// The output accumulator O (128x64 f32) stays in TMEM across all blocks (P.V accumulates in place).  A row's reference
+// maximum m is fixed after the first block (the only one that needs a separate max pass) and is only raised — with a
+// tcgen05.ld/st rescale of the accumulator — if a later block exceeds it by more than 2^kRescaleLog2: f32/bf16 carry an
+// 8-bit exponent, so p up to 2^32 loses nothing and the final O / l division cancels the common factor.
+// The kernel is PERSISTENT: 2 CTAs per SM each loop over (image, head, query tile) work items, so barrier set-up, the TMEM
+// allocation and the tensor-map fetch are paid once per CTA (measured: a third of the non-persistent kernel's time was
+// per-CTA fixed cost) and the next item's Q/K/V loads are in flight while the current item finishes.
 // q/k/v are produced in exactly this layout by the QKV GEMM epilogue (gemm.cuh EPI_QKV).
 #pragma once
 #include "ptx.cuh"
@@ -21,17 +25,19 @@
 namespace ovo {
 
 constexpr int kAttnThreads = 256;
-constexpr int kAttnMaxBlocks = 5;  // seq_pad <= 640
+constexpr int kAttnMaxBlocks = 5;  // seq_pad <= 640 (host-side limit of the q/k/v buffers, in 128-query tiles)
+
+constexpr int kAttnKB = 64;        // keys per block
 
 struct AttnSmem {
   static constexpr int kQ = 128 * 64 * 2;       // 16 KB
-  static constexpr int kKBlock = 128 * 64 * 2;  // 16 KB per 128 keys
-  static constexpr int kVBlock = 64 * 64 * 2;   // 8 KB per 64 keys (V rows of 128 B); one 128-key block = 2 of them, one TMA
-  static constexpr int kP = 2 * 128 * 64 * 2;   // 32 KB: P as two K-major 128x64 tiles
+  static constexpr int kKBlock = 64 * 64 * 2;   // 8 KB per 64 keys, 4 slots
+  static constexpr int kVBlock = 64 * 64 * 2;   // 8 KB per 64 keys (V rows of 128 B), 4 slots
+  static constexpr int kP = 128 * 64 * 2;       // 16 KB: P as a K-major 128x64 tile, 2 buffers
   // 112 KB + barriers.  Two CTAs per SM need 2 * (kBytes + 1 KB) <= 228 KB, so there is no room for a dedicated row-exchange
-  // buffer: the rare cross-half exchanges (first block's maximum, a rescale, the final row sum) borrow the P tile while no
+  // buffer: the rare cross-half exchanges (first block's maximum, a rescale, the final row sum) borrow a P tile while no
   // MMA reads it.
-  static constexpr int kBytes = kQ + 2 * kKBlock + 4 * kVBlock + kP + 256;
+  static constexpr int kBytes = kQ + 4 * kKBlock + 4 * kVBlock + 2 * kP + 256;
 };
 
 constexpr float kRescaleLog2 = 32.f;   // raise a row's reference maximum only when a block exceeds it by 2^32
@@ -39,114 +45,128 @@ constexpr float kRescaleLog2 = 32.f;   // raise a row's reference maximum only w
 __global__ void __launch_bounds__(kAttnThreads, 2)
     attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                          const __grid_constant__ CUtensorMap tmV, __nv_bfloat16* __restrict__ out, int seq,
-                         int seq_pad, int heads, int ld_out, float scale_log2e, int causal, int dbg) {
+                         int seq_pad, int heads, int ld_out, float scale_log2e, int causal, int dbg, int qtiles, int n_items) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();  // the 128B swizzle needs 1024-byte aligned tiles
-  const int nblk = seq_pad / 128;
+  const int nblk = seq_pad / kAttnKB;
   uint8_t* sQ = smem;
-  uint8_t* sK = sQ + AttnSmem::kQ;                 // 2 slots
-  uint8_t* sV = sK + 2 * AttnSmem::kKBlock;        // 2 slots x 2 tiles
-  uint8_t* sP = sV + 4 * AttnSmem::kVBlock;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + AttnSmem::kP);
-  uint64_t* bar_k = bars;       // [2]  (bar_k[0] also covers Q on its first use)
-  uint64_t* bar_v = bars + 2;   // [2]
-  uint64_t* bar_s = bars + 4;   // S ready
-  uint64_t* bar_o = bars + 5;   // P.V done
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
-  float* s_x = reinterpret_cast<float*>(sP);   // [half][128] scratch inside the P tile (only while no P.V is in flight)
+  uint8_t* sK = sQ + AttnSmem::kQ;                 // 4 slots
+  uint8_t* sV = sK + 4 * AttnSmem::kKBlock;        // 4 slots
+  uint8_t* sP = sV + 4 * AttnSmem::kVBlock;        // 2 buffers
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * AttnSmem::kP);
+  uint64_t* bar_k = bars;        // [4]  (bar_k[0] also covers Q on its first use)
+  uint64_t* bar_v = bars + 4;    // [4]
+  uint64_t* bar_s = bars + 8;    // [2]  S buffer ready
+  uint64_t* bar_o = bars + 10;   // [2]  P.V of a block with this parity done
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
 
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int qt = blockIdx.x;  // query tile
-  const int bh = blockIdx.y;  // image * heads + head
-  const int b = bh / heads, head = bh - b * heads;
-  const int q0 = qt * 128;
-  // causal: keys beyond the last query of this tile are never needed
-  const int nb = causal ? min(nblk, qt + 1) : nblk;
-
+  uint64_t* bar_q = bars + 13;   // Q tile of the current item landed
   if (tid == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
-    for (int i = 0; i < 6; ++i) mbar_init(&bars[i], 1);
+    for (int i = 0; i < 12; ++i) mbar_init(&bars[i], 1);
+    mbar_init(bar_q, 1);
     fence_barrier_init();
   }
-  if (warp == 0) tmem_alloc<256>(tmem_slot);  // S [0,128)  O [128,192)
+  if (warp == 0) tmem_alloc<256>(tmem_slot);  // S0 [0,64)  S1 [64,128)  O [128,192)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_S = *tmem_slot;
   const uint32_t tmem_O = tmem_S + 128;
 
-  constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128);
+  constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64);
   constexpr uint32_t idesc_o = umma_idesc_bf16_bmn(128, 64);
   const uint64_t qdesc = umma_desc_sw128(smem_u32(sQ));
 
-  auto load_k = [&](int j) {  // K block j -> slot j&1
-    const int s = j & 1;
-    mbar_arrive_expect_tx(&bar_k[s], AttnSmem::kKBlock + (j == 0 ? AttnSmem::kQ : 0));
-    if (j == 0) tma_load_2d(sQ, &tmQ, &bar_k[0], 0, bh * seq_pad + q0);
-    tma_load_2d(sK + s * AttnSmem::kKBlock, &tmK, &bar_k[s], 0, bh * seq_pad + j * 128);
+  // Ring slots and mbarrier parities are driven by `g`, the number of key blocks this CTA has processed so far plus the block
+  // index inside the current item, so the rings keep rolling across work items.
+  int bh = 0, q0 = 0, nb = 0, g0 = 0;   // current item: (image*heads + head), first query, key blocks, global index of its block 0
+  auto load_k = [&](int j) {  // K block j of the item -> slot (g0+j)&3
+    const int s = (g0 + j) & 3;
+    mbar_arrive_expect_tx(&bar_k[s], AttnSmem::kKBlock);
+    tma_load_2d(sK + s * AttnSmem::kKBlock, &tmK, &bar_k[s], 0, bh * seq_pad + j * kAttnKB);
   };
-  auto load_v = [&](int j) {  // V block j (128 keys x 64) -> slot j&1
-    const int s = j & 1;
-    mbar_arrive_expect_tx(&bar_v[s], 2 * AttnSmem::kVBlock);
-    tma_load_2d(sV + (2 * s) * AttnSmem::kVBlock, &tmV, &bar_v[s], 0, bh * seq_pad + j * 128);
+  auto load_v = [&](int j) {  // V block j of the item -> slot (g0+j)&3
+    const int s = (g0 + j) & 3;
+    mbar_arrive_expect_tx(&bar_v[s], AttnSmem::kVBlock);
+    tma_load_2d(sV + s * AttnSmem::kVBlock, &tmV, &bar_v[s], 0, bh * seq_pad + j * kAttnKB);
   };
-  auto issue_qk = [&](int j) {  // S = Q . K_j^T
-    mbar_wait(&bar_k[j & 1], (j >> 1) & 1);
+  auto issue_qk = [&](int j) {  // S_{g&1} = Q . K_j^T
+    const int g = g0 + j;
+    mbar_wait(&bar_k[g & 3], (g >> 2) & 1);
     tc_fence_after();
-    const uint64_t kdesc = umma_desc_sw128(smem_u32(sK + (j & 1) * AttnSmem::kKBlock));
+    const uint64_t kdesc = umma_desc_sw128(smem_u32(sK + (g & 3) * AttnSmem::kKBlock));
+    if (!(dbg & 2)) {
 #pragma unroll
-    for (int k = 0; k < 4; ++k) umma_bf16(tmem_S, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
-    umma_commit(bar_s);
+      for (int k = 0; k < 4; ++k) umma_bf16(tmem_S + (g & 1) * 64, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
+    }
+    umma_commit(&bar_s[g & 1]);
   };
+
+  const int row = tid & 127, half = tid >> 7;
+  const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
+  const int r8 = row & 7;
+  const int p_off = (row >> 3) * 1024 + r8 * 128;  // this row inside a P tile (128-byte rows, 8-row swizzle groups)
+  int n_done = 0;                                   // work items this CTA has finished (parity of bar_q)
+
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n_done) {
+  const int qt = item % qtiles;
+  bh = item / qtiles;
+  const int b = bh / heads, head = bh - b * heads;
+  q0 = qt * 128;
+  // causal: keys beyond the last query of this tile are never needed; blocks of pure padding are skipped
+  // (dbg bits are measurement aids, results are wrong with them: 1 = no softmax math / P stores, 2 = no MMA, 4 = one key block)
+  nb = (dbg & 4) ? 1 : min(causal ? min(nblk, 2 * qt + 2) : nblk, (seq + kAttnKB - 1) / kAttnKB);
 
   if (tid == 0) {
-    load_k(0);
-    if (nb > 1) load_k(1);
-    load_v(0);
-    if (nb > 1) load_v(1);
+    // every MMA of the previous item has completed (its epilogue waited for the last P.V): Q, the K/V rings and S are free
+    mbar_arrive_expect_tx(bar_q, AttnSmem::kQ);
+    tma_load_2d(sQ, &tmQ, bar_q, 0, bh * seq_pad + q0);
+    for (int j = 0; j < 4 && j < nb; ++j) load_k(j);
+    for (int j = 0; j < 4 && j < nb; ++j) load_v(j);
+    mbar_wait(bar_q, n_done & 1);
     issue_qk(0);
+    if (nb > 1) issue_qk(1);
   }
 
-  // thread (row, half) owns query row `row`, keys [64*half, 64*half+64) of every block and output columns
+  // thread (row, half) owns query row `row`, keys [32*half, 32*half+32) of every block and output columns
   // [32*half, 32*half+32) of the accumulator in TMEM
-  const int row = tid & 127, half = tid >> 7;
   const int qrow = q0 + row;
   float m_used = -INFINITY;      // the row's reference maximum (raw score units), identical in both halves
   float l_run = 0.f;             // partial row sum over this thread's keys
   float m_loc = -INFINITY;       // maximum this thread has seen over its keys so far
   int rescale = 0;               // CTA-uniform: some row's maximum outgrew its reference by 2^kRescaleLog2 in the last block
-  const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
-  const int r8 = row & 7;
-  uint8_t* p_row = sP + half * (128 * 128) + (row >> 3) * 1024 + r8 * 128;  // P tile `half` = this thread's 64 keys
 
   for (int j = 0; j < nb; ++j) {
-    mbar_wait(bar_s, j & 1);
+    const int g = g0 + j;                              // global block index of this CTA: ring slots and parities
+    mbar_wait(&bar_s[g & 1], (g >> 1) & 1);
     tc_fence_after();
-    // K slot j&1 has been consumed by Q.K_j^T: refill it with block j+2
-    if (tid == 0 && j + 2 < nb) load_k(j + 2);
+    // K slot g&3 has been consumed by Q.K_j^T: refill it with block j+4
+    if (tid == 0 && j + 4 < nb) load_k(j + 4);
+    const uint32_t s_addr = tmem_S + lane_off + (g & 1) * 64 + half * 32;
+    float* s_x = reinterpret_cast<float*>(sP + (g & 1) * AttnSmem::kP);   // scratch inside the P tile this block will write
 
-    const int kv0 = j * 128 + half * 64;             // first key of this thread's half
+    const int kv0 = j * kAttnKB + half * 32;         // first key of this thread's half
     int kv_hi = seq - kv0;                           // keys >= seq are padding
     if (causal) kv_hi = min(kv_hi, qrow - kv0 + 1);  // keys > query are masked
-    // blocks that are entirely valid (all but the last one, and no causal diagonal) skip the per-element masking
-    const bool full = !causal && (j * 128 + 128 <= seq);   // CTA uniform
+    // blocks that are entirely valid (no padding, no causal diagonal) skip the per-element masking
+    const bool full = !causal && (j * kAttnKB + kAttnKB <= seq);   // CTA uniform
+
+    uint32_t v[32];
+    tmem_ld_32x32(s_addr, v);
+    tmem_ld_wait();
 
     if (j == 0) {
       // first block: the reference maximum of the row = its maximum over block 0 (both halves)
       float mp[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(tmem_S + lane_off + half * 64 + c * 32, v);
-        tmem_ld_wait();
-        if (full) {
+      if (full) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mp[i & 3] = fmaxf(mp[i & 3], __uint_as_float(v[i]));
-        } else {
+        for (int i = 0; i < 32; ++i) mp[i & 3] = fmaxf(mp[i & 3], __uint_as_float(v[i]));
+      } else {
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c * 32 + i < kv_hi) mp[i & 3] = fmaxf(mp[i & 3], __uint_as_float(v[i]));
-        }
+        for (int i = 0; i < 32; ++i)
+          if (i < kv_hi) mp[i & 3] = fmaxf(mp[i & 3], __uint_as_float(v[i]));
       }
       const float mine = fmaxf(fmaxf(mp[0], mp[1]), fmaxf(mp[2], mp[3]));
       s_x[half * 128 + row] = mine;
@@ -155,21 +175,25 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
       m_loc = mine;
       __syncthreads();                               // the scratch lives in the P tile that is written next
     } else {
-      // P.V_{j-1} has completed (it was issued before Q.K_j^T): the P tile, V slot (j-1)&1 and the accumulator are free
-      mbar_wait(bar_o, (j - 1) & 1);
-      tc_fence_after();
-      if (tid == 0 && j + 1 < nb) load_v(j + 1);
+      if (j >= 2) {
+        // P.V_{j-2} has completed: P tile g&1 and V slot (g-2)&3 are free again
+        mbar_wait(&bar_o[g & 1], ((g - 2) >> 1) & 1);
+        tc_fence_after();
+        if (tid == 0 && j + 2 < nb) load_v(j + 2);
+      }
       if (rescale) {   // rare, CTA-uniform (dbg 16: whenever a maximum grows, for the tests)
+        mbar_wait(&bar_o[(g - 1) & 1], ((g - 1) >> 1) & 1);    // every P.V so far has landed: the accumulator is stable
+        tc_fence_after();
         s_x[half * 128 + row] = m_loc;
         __syncthreads();
         const float m_new = fmaxf(m_used, fmaxf(m_loc, s_x[(1 - half) * 128 + row]));   // the same in both halves of the row
         const float alpha = (m_new > m_used) ? fast_ex2((m_used - m_new) * scale_log2e) : 1.f;
-        uint32_t v[32];
-        tmem_ld_32x32(tmem_O + lane_off + half * 32, v);
+        uint32_t o[32];
+        tmem_ld_32x32(tmem_O + lane_off + half * 32, o);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
-        tmem_st_32x32(tmem_O + lane_off + half * 32, v);
+        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+        tmem_st_32x32(tmem_O + lane_off + half * 32, o);
         tmem_st_wait();
         l_run *= alpha;
         m_used = m_new;
@@ -178,70 +202,70 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
     }
     const float m_scaled = (m_used == -INFINITY) ? 0.f : m_used * scale_log2e;
 
-    // single pass: p = exp2(s*scale - m), partial row sum, block maximum, P -> swizzled smem (bf16)
+    // p = exp2(s*scale - m), partial row sum, block maximum, P -> swizzled smem (bf16)
     float lp[4] = {0.f, 0.f, 0.f, 0.f};
     float mp[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll 1
-    for (int c = 0; c < 2; ++c) {
-      uint32_t v[32];
-      tmem_ld_32x32(tmem_S + lane_off + half * 64 + c * 32, v);
-      tmem_ld_wait();
-      float p[32];
-      if (full) {
+    float p[32];
+    if (dbg & 1) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float sv = __uint_as_float(v[i]);
-          p[i] = fast_ex2(fmaf(sv, scale_log2e, -m_scaled));
-          mp[i & 3] = fmaxf(mp[i & 3], sv);
-        }
-      } else {
+      for (int i = 0; i < 32; ++i) p[i] = 0.f;
+    } else if (full) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float sv = __uint_as_float(v[i]);
-          const bool ok = c * 32 + i < kv_hi;
-          p[i] = ok ? fast_ex2(fmaf(sv, scale_log2e, -m_scaled)) : 0.f;
-          if (ok) mp[i & 3] = fmaxf(mp[i & 3], sv);
-        }
+      for (int i = 0; i < 32; ++i) {
+        const float sv = __uint_as_float(v[i]);
+        p[i] = fast_ex2(fmaf(sv, scale_log2e, -m_scaled));
+        mp[i & 3] = fmaxf(mp[i & 3], sv);
       }
+    } else {
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        uint4 u;
-        u.x = pack_bf16(p[8 * g], p[8 * g + 1]); u.y = pack_bf16(p[8 * g + 2], p[8 * g + 3]);
-        u.z = pack_bf16(p[8 * g + 4], p[8 * g + 5]); u.w = pack_bf16(p[8 * g + 6], p[8 * g + 7]);
-        const int chunk = c * 4 + g;  // 16-byte chunk index inside the 128-byte row
-        *reinterpret_cast<uint4*>(p_row + ((chunk ^ r8) << 4)) = u;
+      for (int i = 0; i < 32; ++i) {
+        const float sv = __uint_as_float(v[i]);
+        const bool ok = i < kv_hi;
+        p[i] = ok ? fast_ex2(fmaf(sv, scale_log2e, -m_scaled)) : 0.f;
+        if (ok) mp[i & 3] = fmaxf(mp[i & 3], sv);
       }
-#pragma unroll
-      for (int i = 0; i < 32; ++i) lp[i & 3] += p[i];
     }
+    uint8_t* p_row = sP + (g & 1) * AttnSmem::kP + p_off;
+    if (!(dbg & 1))
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      uint4 u;
+      u.x = pack_bf16(p[8 * g], p[8 * g + 1]); u.y = pack_bf16(p[8 * g + 2], p[8 * g + 3]);
+      u.z = pack_bf16(p[8 * g + 4], p[8 * g + 5]); u.w = pack_bf16(p[8 * g + 6], p[8 * g + 7]);
+      const int chunk = half * 4 + g;  // 16-byte chunk index inside the 128-byte row
+      *reinterpret_cast<uint4*>(p_row + ((chunk ^ r8) << 4)) = u;
+    }
+#pragma unroll
+    for (int i = 0; i < 32; ++i) lp[i & 3] += p[i];
     l_run += (lp[0] + lp[1]) + (lp[2] + lp[3]);
     m_loc = fmaxf(m_loc, fmaxf(fmaxf(mp[0], mp[1]), fmaxf(mp[2], mp[3])));
     const int need = m_loc > m_used + ((dbg & 16) ? 0.f : kRescaleLog2 / scale_log2e);
 
-    // P visible to the async proxy and every thread done reading S; then O += P.V_j and S_{j+1} = Q.K_{j+1}^T
+    // P_j visible to the async proxy and every thread done reading S_j; then O += P_j.V_j and S buffer j&1 <- Q.K_{j+2}^T
     fence_proxy_async_smem();
     tc_fence_before();
     rescale = __syncthreads_or(need);
     if (tid == 0) {
       tc_fence_after();
-      mbar_wait(&bar_v[j & 1], (j >> 1) & 1);
+      mbar_wait(&bar_v[g & 3], (g >> 2) & 1);
       tc_fence_after();
+      const uint64_t pdesc = umma_desc_sw128(smem_u32(sP + (g & 1) * AttnSmem::kP));
+      // keys 16k .. 16k+15 of the block: 16 rows of 128 B = 2048 B per K=16 step
+      const uint64_t vdesc = umma_desc_sw128(smem_u32(sV + (g & 3) * AttnSmem::kVBlock));
+      if (!(dbg & 2)) {
 #pragma unroll
-      for (int t = 0; t < 2; ++t) {
-        const uint64_t pdesc = umma_desc_sw128(smem_u32(sP + t * (128 * 128)));
-        // keys 64t + 16k .. +15 of the block: 16 rows of 128 B = 2048 B per K=16 step
-        const uint64_t vdesc = umma_desc_sw128(smem_u32(sV + (2 * (j & 1) + t) * AttnSmem::kVBlock));
-#pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(tmem_O, pdesc + 2 * k, vdesc + 128 * k, idesc_o, (j | t | k) != 0);
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem_O, pdesc + 2 * k, vdesc + 128 * k, idesc_o, (j | k) != 0);
       }
-      umma_commit(bar_o);
-      if (j + 1 < nb) issue_qk(j + 1);
+      umma_commit(&bar_o[g & 1]);
+      if (j + 2 < nb) issue_qk(j + 2);
     }
   }
 
-  // total row sum = sum of the two halves' partial sums; the accumulator is complete once the last P.V has landed
-  mbar_wait(bar_o, (nb - 1) & 1);                    // ... and the P tile is free to serve as scratch
+  // the accumulator is complete once the last P.V has landed (tcgen05.mma of one thread complete in order);
+  // total row sum = sum of the two halves' partial sums
+  mbar_wait(&bar_o[(g0 + nb - 1) & 1], ((g0 + nb - 1) >> 1) & 1);
   tc_fence_after();
+  float* s_x = reinterpret_cast<float*>(sP);         // every P tile is free now
   s_x[half * 128 + row] = l_run;
   __syncthreads();
   l_run += s_x[(1 - half) * 128 + row];
@@ -261,6 +285,12 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
       *reinterpret_cast<uint4*>(dst + 8 * g) = u;
     }
   }
+  tc_fence_before();
+  __syncthreads();                                   // scratch and accumulator reads done before the next item reuses them
+  tc_fence_after();
+  g0 += nb;
+  }  // work items
+
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {

@@ -388,8 +388,8 @@ int launch_attention(ovo_encoder* e, int n_seq, int seq, int seq_pad, int heads,
   CUtensorMap tq, tk, tv;
   const uint64_t bh = static_cast<uint64_t>(n_seq) * heads;
   OVO_TRY(make_tmap_bf16_2d(&tq, e->q, bh * seq_pad, 64, 64, 128, 64));
-  OVO_TRY(make_tmap_bf16_2d(&tk, e->k, bh * seq_pad, 64, 64, 128, 64));
-  OVO_TRY(make_tmap_bf16_2d(&tv, e->vt, bh * seq_pad, 64, 64, 128, 64));   // V [b,h,seq_pad,64]: MN-major B operand of P.V
+  OVO_TRY(make_tmap_bf16_2d(&tk, e->k, bh * seq_pad, 64, 64, kAttnKB, 64));
+  OVO_TRY(make_tmap_bf16_2d(&tv, e->vt, bh * seq_pad, 64, 64, kAttnKB, 64));   // V [b,h,seq_pad,64]: MN-major B operand of P.V
   const int smem = AttnSmem::kBytes;
   static bool attr_set = false;
   if (!attr_set) {
@@ -399,8 +399,9 @@ int launch_attention(ovo_encoder* e, int n_seq, int seq, int seq_pad, int heads,
   const int qtiles = ceil_div(seq, 128);
   const float scale_log2e = 0.125f * 1.4426950408889634f;  // head_dim 64
   ProfScope prof(s, PROF_ATTN, 4.0 * static_cast<double>(bh) * seq * (causal ? 0.5 * seq : seq) * 64, 4.0 * static_cast<double>(bh) * seq * 64 * 2);
-  attention_fwd_kernel<<<dim3(qtiles, static_cast<unsigned>(bh)), kAttnThreads, smem, s>>>(
-      tq, tk, tv, e->attn, seq, seq_pad, heads, width, scale_log2e, causal ? 1 : 0, g_attn_debug);
+  const int n_items = qtiles * static_cast<int>(bh);
+  attention_fwd_kernel<<<std::min(n_items, 2 * num_sms()), kAttnThreads, smem, s>>>(
+      tq, tk, tv, e->attn, seq, seq_pad, heads, width, scale_log2e, causal ? 1 : 0, g_attn_debug, qtiles, n_items);
   OVO_CHECK_LAUNCH();
   return OVO_OK;
 }

@@ -289,7 +289,7 @@ def stage_attndbg():
     cfg = EncoderConfig(text_layers=0, layers=4)
     enc, sd, ocfg = _enc(cfg, n_img=16, text=False)
     px = torch.randn(16, 3, 336, 336, device=dev)
-    for dbg, name in ((0, "full"), (1, "no softmax (no S loads, no P)"), (2, "no O accumulate"), (4, "no proxy fence"), (8, "no max exchange"), (15, "none of them")):
+    for dbg, name in ((0, "full"), (1, "no softmax math / P stores"), (2, "no MMA"), (3, "neither (barrier skeleton)"), (4, "one key block"), (7, "one block, skeleton")):
         _lib.lib().ovo_set_gemm_cluster((dbg << 24) | 1)
         _lib.profile_begin()
         for _ in range(2):
