@@ -15,6 +15,10 @@
 // maximum m is fixed after the first block (the only one that needs a separate max pass) and is only raised — with a
 // tcgen05.ld/st rescale of the accumulator — if a later block exceeds it by more than 2^kRescaleLog2: f32/bf16 carry an
 // 8-bit exponent, so p up to 2^32 loses nothing and the final O / l division cancels the common factor.
+// Warp specialisation: the 256 softmax threads never issue an MMA — a ninth warp waits on the "P tile ready" mbarrier,
+// issues P.V and the Q.K^T two blocks ahead, and starts the next work item's loads while the softmax threads are still in
+// the current item's epilogue; the softmax threads synchronise among themselves on a named barrier (bar.red.or also carries
+// the rare rescale request).
 // The kernel is PERSISTENT: 2 CTAs per SM each loop over (image, head, query tile) work items, so barrier set-up, the TMEM
 // allocation and the tensor-map fetch are paid once per CTA (measured: a third of the non-persistent kernel's time was
 // per-CTA fixed cost) and the next item's Q/K/V loads are in flight while the current item finishes.
@@ -24,7 +28,7 @@
 
 namespace ovo {
 
-constexpr int kAttnThreads = 256;
+constexpr int kAttnThreads = 288;   // warps 0..7: softmax (two threads per query row); warp 8: TMA + tcgen05.mma issue
 constexpr int kAttnMaxBlocks = 5;  // seq_pad <= 640 (host-side limit of the q/k/v buffers, in 128-query tiles)
 
 constexpr int kAttnKB = 64;        // keys per block
@@ -62,13 +66,16 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
 
   const int tid = threadIdx.x, warp = tid >> 5;
   uint64_t* bar_q = bars + 13;   // Q tile of the current item landed
+  uint64_t* bar_p = bars + 14;   // [2] P tile written and S buffer consumed by every softmax thread
   if (tid == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
     for (int i = 0; i < 12; ++i) mbar_init(&bars[i], 1);
     mbar_init(bar_q, 1);
+    mbar_init(&bar_p[0], 1);
+    mbar_init(&bar_p[1], 1);
     fence_barrier_init();
   }
-  if (warp == 0) tmem_alloc<256>(tmem_slot);  // S0 [0,64)  S1 [64,128)  O [128,192)
+  if (warp == 8) tmem_alloc<256>(tmem_slot);  // S0 [0,64)  S1 [64,128)  O [128,192)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -119,15 +126,41 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
   // (dbg bits are measurement aids, results are wrong with them: 1 = no softmax math / P stores, 2 = no MMA, 4 = one key block)
   nb = (dbg & 4) ? 1 : min(causal ? min(nblk, 2 * qt + 2) : nblk, (seq + kAttnKB - 1) / kAttnKB);
 
-  if (tid == 0) {
-    // every MMA of the previous item has completed (its epilogue waited for the last P.V): Q, the K/V rings and S are free
-    mbar_arrive_expect_tx(bar_q, AttnSmem::kQ);
-    tma_load_2d(sQ, &tmQ, bar_q, 0, bh * seq_pad + q0);
-    for (int j = 0; j < 4 && j < nb; ++j) load_k(j);
-    for (int j = 0; j < 4 && j < nb; ++j) load_v(j);
-    mbar_wait(bar_q, n_done & 1);
-    issue_qk(0);
-    if (nb > 1) issue_qk(1);
+  if (warp == 8) {
+    // ---------------------------------------------------------------- TMA + MMA warp (one elected lane)
+    if (tid == 256) {
+      // every MMA of the previous item has completed (the last P.V was waited for below): Q, the K/V rings are free; the S
+      // buffers were consumed (bar_p of the last two blocks), the accumulator is overwritten only by P.V_0, which waits for
+      // the softmax threads' first bar_p arrival of this item, i.e. for the end of their previous epilogue
+      mbar_arrive_expect_tx(bar_q, AttnSmem::kQ);
+      tma_load_2d(sQ, &tmQ, bar_q, 0, bh * seq_pad + q0);
+      for (int j = 0; j < 4 && j < nb; ++j) load_k(j);
+      for (int j = 0; j < 4 && j < nb; ++j) load_v(j);
+      mbar_wait(bar_q, n_done & 1);
+      issue_qk(0);
+      if (nb > 1) issue_qk(1);
+      for (int j = 0; j < nb; ++j) {
+        const int g = g0 + j;
+        mbar_wait(&bar_p[g & 1], (g >> 1) & 1);      // P_j in smem (async-proxy visible), S buffer g&1 consumed
+        tc_fence_after();
+        mbar_wait(&bar_v[g & 3], (g >> 2) & 1);
+        tc_fence_after();
+        const uint64_t pdesc = umma_desc_sw128(smem_u32(sP + (g & 1) * AttnSmem::kP));
+        // keys 16k .. 16k+15 of the block: 16 rows of 128 B = 2048 B per K=16 step
+        const uint64_t vdesc = umma_desc_sw128(smem_u32(sV + (g & 3) * AttnSmem::kVBlock));
+        if (!(dbg & 2)) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16(tmem_O, pdesc + 2 * k, vdesc + 128 * k, idesc_o, (j | k) != 0);
+        }
+        umma_commit(&bar_o[g & 1]);
+        if (j + 2 < nb) issue_qk(j + 2);
+      }
+      // all tensor work of the item has completed before the next item's loads overwrite Q / the rings
+      mbar_wait(&bar_o[(g0 + nb - 1) & 1], ((g0 + nb - 1) >> 1) & 1);
+    }
+    __syncwarp();
+    g0 += nb;
+    continue;
   }
 
   // thread (row, half) owns query row `row`, keys [32*half, 32*half+32) of every block and output columns
@@ -170,10 +203,10 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
       }
       const float mine = fmaxf(fmaxf(mp[0], mp[1]), fmaxf(mp[2], mp[3]));
       s_x[half * 128 + row] = mine;
-      __syncthreads();
+      named_bar_sync(1, 256);
       m_used = fmaxf(mine, s_x[(1 - half) * 128 + row]);
       m_loc = mine;
-      __syncthreads();                               // the scratch lives in the P tile that is written next
+      named_bar_sync(1, 256);                               // the scratch lives in the P tile that is written next
     } else {
       if (j >= 2) {
         // P.V_{j-2} has completed: P tile g&1 and V slot (g-2)&3 are free again
@@ -185,7 +218,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
         mbar_wait(&bar_o[(g - 1) & 1], ((g - 1) >> 1) & 1);    // every P.V so far has landed: the accumulator is stable
         tc_fence_after();
         s_x[half * 128 + row] = m_loc;
-        __syncthreads();
+        named_bar_sync(1, 256);
         const float m_new = fmaxf(m_used, fmaxf(m_loc, s_x[(1 - half) * 128 + row]));   // the same in both halves of the row
         const float alpha = (m_new > m_used) ? fast_ex2((m_used - m_new) * scale_log2e) : 1.f;
         uint32_t o[32];
@@ -197,7 +230,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
         tmem_st_wait();
         l_run *= alpha;
         m_used = m_new;
-        __syncthreads();                             // scratch reads done before P is written again
+        named_bar_sync(1, 256);                             // scratch reads done before P is written again
       }
     }
     const float m_scaled = (m_used == -INFINITY) ? 0.f : m_used * scale_log2e;
@@ -244,21 +277,8 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
     // P_j visible to the async proxy and every thread done reading S_j; then O += P_j.V_j and S buffer j&1 <- Q.K_{j+2}^T
     fence_proxy_async_smem();
     tc_fence_before();
-    rescale = __syncthreads_or(need);
-    if (tid == 0) {
-      tc_fence_after();
-      mbar_wait(&bar_v[g & 3], (g >> 2) & 1);
-      tc_fence_after();
-      const uint64_t pdesc = umma_desc_sw128(smem_u32(sP + (g & 1) * AttnSmem::kP));
-      // keys 16k .. 16k+15 of the block: 16 rows of 128 B = 2048 B per K=16 step
-      const uint64_t vdesc = umma_desc_sw128(smem_u32(sV + (g & 3) * AttnSmem::kVBlock));
-      if (!(dbg & 2)) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(tmem_O, pdesc + 2 * k, vdesc + 128 * k, idesc_o, (j | k) != 0);
-      }
-      umma_commit(&bar_o[g & 1]);
-      if (j + 2 < nb) issue_qk(j + 2);
-    }
+    rescale = named_bar_or(1, 256, need);
+    if (tid == 0) mbar_arrive(&bar_p[g & 1]);
   }
 
   // the accumulator is complete once the last P.V has landed (tcgen05.mma of one thread complete in order);
@@ -267,7 +287,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
   tc_fence_after();
   float* s_x = reinterpret_cast<float*>(sP);         // every P tile is free now
   s_x[half * 128 + row] = l_run;
-  __syncthreads();
+  named_bar_sync(1, 256);
   l_run += s_x[(1 - half) * 128 + row];
   uint32_t v[32];
   tmem_ld_32x32(tmem_O + lane_off + half * 32, v);   // warp-collective: every lane, also the padding rows
@@ -286,14 +306,14 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
     }
   }
   tc_fence_before();
-  __syncthreads();                                   // scratch and accumulator reads done before the next item reuses them
+  named_bar_sync(1, 256);                                   // scratch and accumulator reads done before the next item reuses them
   tc_fence_after();
   g0 += nb;
   }  // work items
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) {
+  if (warp == 8) {
     tc_fence_after();
     tmem_dealloc<256>(tmem_S);
   }

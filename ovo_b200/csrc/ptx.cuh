@@ -52,6 +52,24 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// named barriers for a subset of the CTA's warps (id 1..15; `threads` = multiple of 32 participating threads)
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(threads) : "memory");
+}
+// barrier + OR-reduction of a predicate over the participating threads
+__device__ __forceinline__ int named_bar_or(int id, int threads, int pred) {
+  int out;
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %3, 0;\n\t"
+      "bar.red.or.pred q, %1, %2, p;\n\t"
+      "selp.b32 %0, 1, 0, q;\n\t}\n"
+      : "=r"(out)
+      : "r"(id), "r"(threads), "r"(pred)
+      : "memory");
+  return out;
+}
+
 // ----------------------------------------------------------------------------- TMA
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];\n" ::"l"(m) : "memory");
