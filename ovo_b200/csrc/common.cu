@@ -115,6 +115,16 @@ static int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N
   return OVO_OK;
 }
 
+void keep_default_mempool_cached() {
+  int dev = 0;
+  cudaMemPool_t pool;
+  if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    unsigned long long thr = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
+  cudaGetLastError();
+}
+
 static int g_gemm_debug = 0;
 static int g_query_cluster = 2;   // cluster size of the wide (Q > 64) dense query: the text tile is multicast (set by tuning)
 static int g_gemm_cluster = -1;   // -1 = auto; OVO_B200_GEMM_CLUSTER=1|2|4 forces a cluster size (tuning aid)

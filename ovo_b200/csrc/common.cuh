@@ -37,6 +37,11 @@ void count_launch(int n = 1);
     if (_r != OVO_OK) return _r; \
   } while (0)
 
+// The stream-ordered temporaries of the mask post-processing come from the device's default memory pool; by default that
+// pool returns memory to the OS at every synchronisation, which makes the next cudaMallocAsync a real allocation
+// (milliseconds).  Keep it cached.
+void keep_default_mempool_cached();
+
 inline int ceil_div(long long a, long long b) { return static_cast<int>((a + b - 1) / b); }
 
 // Optional per-launch timing (ovo_profile_begin / ovo_profile_report): CUDA events recorded on the launching

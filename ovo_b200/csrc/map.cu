@@ -909,6 +909,7 @@ extern "C" {
 
 int ovo_map_create(ovo_map_t** out) {
   OVO_REQUIRE(out != nullptr, "ovo_map_create: null out");
+  ovo::keep_default_mempool_cached();
   ovo_map* m = new ovo_map();
   if (ctl_alloc(m, 256) != OVO_OK) {
     ovo_map_destroy(m);

@@ -924,6 +924,7 @@ int ovo_sam_create(const ovo_sam_cfg* cfg, const ovo_sam_weights* w, int max_h, 
   OVO_REQUIRE(cfg && w && out, "ovo_sam_create: null argument");
   OVO_REQUIRE(cfg->image_size % 64 == 0 && cfg->n_blocks > 0 && cfg->decoder_depth >= 1, "ovo_sam_create: bad config");
   OVO_REQUIRE(w->patch_kpad % 8 == 0 && w->patch_kpad >= 147, "ovo_sam_create: patch_kpad must be a multiple of 8 >= 147");
+  keep_default_mempool_cached();
   ovo_sam* s = new ovo_sam();
   s->cfg = *cfg; s->w = *w;
   s->blocks.assign(w->blocks, w->blocks + cfg->n_blocks);
