@@ -242,6 +242,8 @@ def run_ours(args, rank, world, local_rank):
         out["sam"] = sam
     if not args.no_cpu_baseline and world >= 1:
         out["cpu_baseline"] = cpu_baseline(args, budget_frames=1)
+        if sam is not None:
+            out["sam"]["cpu_baseline"] = sam_cpu_baseline()
     print(json.dumps(out))
 
 
@@ -353,6 +355,16 @@ def run_e2e(args, rank, world, dev, enc, K, xyz, ids, ins, seg, bm, fr, dist):
     for _ in range(max(3, min(args.warmup, 3))):
         step()
     torch.cuda.synchronize()
+    if args.profile_e2e and rank == 0:      # development aid: where the host time of the public-API loop goes
+        import cProfile
+        import pstats
+        pr = cProfile.Profile()
+        pr.enable()
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
+        pr.disable()
+        pstats.Stats(pr, stream=sys.stderr).sort_stats("cumulative").print_stats(35)
     if dist:
         dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -402,6 +414,29 @@ def cpu_frames_per_second(points, n_frames, threads):
     return n_frames / (time.time() - t0)
 
 
+def sam_cpu_baseline():
+    """The reference's SAM-2 algorithm (oracle/sam.py, torch f32) on the host cores: one image through the Hiera-L trunk +
+    neck and ONE batch of 64 point prompts through the decoder (the reference runs 4 such batches per frame)."""
+    from oracle import sam as OS
+    from ovo_b200.sam_config import SamConfig, random_state_dict
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    cfg = SamConfig()
+    sd = random_state_dict(cfg, seed=0)
+    img = np.random.default_rng(5).integers(0, 256, (H, W, 3), dtype=np.uint8)
+    pts = torch.from_numpy(OS.amg_points(16, H, W, cfg.image_size))[:64]
+    with torch.no_grad():
+        t0 = time.time()
+        emb, s0, s1 = OS.forward_image(OS.preprocess(img, cfg.image_size), sd, cfg)
+        t1 = time.time()
+        OS.predict(pts, emb, s0, s1, sd, cfg)
+        t2 = time.time()
+    ms = 1e3 * ((t1 - t0) + 4 * (t2 - t1))
+    return {"value": round(1e3 / ms, 4), "unit": "frames/s", "ms_per_frame": round(ms, 1), "cores": threads, "kind": "port",
+            "sample": f"1 image through the trunk ({t1 - t0:.1f} s) + 1 of the 4 batches of 64 prompts through the decoder "
+                      f"({t2 - t1:.1f} s, scaled x4); AMG post-processing not included"}
+
+
 def cpu_baseline(args, budget_frames=1):
     threads = os.cpu_count() or 1
     fps = cpu_frames_per_second(args.points, budget_frames, threads)
@@ -445,6 +480,7 @@ def main():
     ap.add_argument("--points", type=int, default=2_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sam", action="store_true", help="skip the SAM-2 stage report")
+    ap.add_argument("--profile-e2e", action="store_true", help="cProfile three e2e steps to stderr")
     ap.add_argument("--no-pipeline", action="store_true", help="do not overlap a step's fusion with the next step's encoder")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

@@ -131,3 +131,37 @@ def test_medoid_fusions_pick_a_view(tmp_path, fusion):
     for o in list(ovo.objects.values())[:10]:
         f = o.clip_feature.reshape(-1)
         assert (store - f).abs().sum(1).min().item() == 0.0         # the fused descriptor IS one of the views
+
+
+def test_online_sam_through_the_ovo_api(tmp_path):
+    """`sam.precomputed: False`: MaskGenerator runs SAM-2 (tiny Hiera geometry, seeded weights) on the device
+    (mask_generator.py:37-53,102-120) and OVO consumes its (seg_map, binary_maps) exactly as it consumes precomputed
+    ones; the masks equal a direct `Sam2.generate` call and every mask that won pixels of the seg-map agrees with it."""
+    from ovo_b200 import OVO, CLIPGenerator
+    from ovo_b200.encoder import random_state_dict
+    from ovo_b200.sam_config import random_state_dict as sam_sd, tiny_sam_config
+    K, xyz, ids, ins, frames = GG.ovo_inputs()
+    cfg = GG.tiny_cfg()
+    config = GG.ovo_config(str(tmp_path / "unused"))
+    scfg = tiny_sam_config()
+    config["sam"] = {"precomputed": False, "masks_base_path": "", "sam_version": "2.1", "sam_config": scfg,
+                     "sam_state_dict": sam_sd(scfg, seed=0), "points_per_side": 16, "nms_iou_th": 0.45, "stability_score_th": 0.4,
+                     "box_nms_thresh": 0.9999, "nms_score_th": GG.SAM_OVO_SCORE_THR, "max_h": 480, "max_w": 640}
+    clip = CLIPGenerator(config["clip"], state_dict=random_state_dict(cfg, seed=0), tokenizer=_TokTokenizer(), encoder_config=cfg)
+    ovo = OVO(config, _Logger(), scene_name=None, cam_intrinsics=torch.from_numpy(K), clip_generator=clip)
+    img = GG.sam_image(seed=11)
+    seg, maps = ovo.mask_generator.get_masks(img, 0)
+    assert seg.shape == (480, 640) and seg.dtype == torch.int32 and maps.dtype == torch.bool and maps.shape[0] > 0
+    seg2, maps2 = ovo.mask_generator.mask_generator.generate(torch.from_numpy(img), ovo.mask_generator.amg_params)
+    assert torch.equal(seg, seg2) and torch.equal(maps, maps2)
+    for m in range(maps.shape[0]):
+        assert bool(maps[m][seg == m].all())             # painted pixels belong to their mask (segment_utils.py:12-27)
+    assert int(seg.max()) < maps.shape[0]
+    seg_np, maps_np = ovo.mask_generator.segment(img)    # the numpy-returning form of the reference
+    assert (seg_np == seg.cpu().numpy()).all() and (maps_np == maps.cpu().numpy()).all()
+    pts, pids, pins = (torch.from_numpy(a).cuda() for a in (xyz, ids, ins))
+    f = frames[0]
+    upd = ovo.detect_and_track_objects((0, img, f["depth"], ()), (pts, pids, pins), torch.from_numpy(f["c2w"]))
+    assert upd is not None and upd.shape == pins.shape
+    ovo.compute_semantic_info()
+    ovo.complete_semantic_info()
