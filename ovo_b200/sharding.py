@@ -6,6 +6,10 @@
   shards.  Per keyframe every rank runs pass 1 on its own points (`vote`), the small vote tables
   [n_masks, n_instances+1] are summed with ONE all-reduce, and every rank takes the same decisions and updates its
   own points (`apply`).  The instance registry is therefore replicated deterministically without extra traffic.
+* Map growth: the rank that integrates a frame (`ovo_map_integrate`, VanillaMapper.map) creates points whose voxels may
+  belong to other shards; `route_new_points` sends each new point to its owner with ONE all-to-all per mapped frame
+  (20 B per point: xyz f32x3, id i32, rgb u8x3 — <= 76.8k points ~ 1.5 MB), the only data-path exchange besides the vote
+  table.  The receive order is deterministic (by source rank, then creation order).
 * Query: row parallel, results stay sharded.
 
 `ShardedAssociation` only needs an object with `vote(...) -> table` and `apply(table, ...)`: on the GPU that is
@@ -57,3 +61,37 @@ def gather_descriptors(local_feats: torch.Tensor, counts_per_rank, group=None) -
     out = [torch.empty_like(pad) for _ in counts_per_rank]
     dist.all_gather(out, pad, group=group)
     return torch.cat([o[:c] for o, c in zip(out, counts_per_rank)])
+
+
+def route_new_points(xyz: torch.Tensor, ids: torch.Tensor, colors: torch.Tensor | None = None, group=None, cell: float = 0.25):
+    """All-to-all of freshly created map points to the shards that own their voxels.
+    xyz [n,3] f32, ids [n] i32, colors [n,3] u8 (optional), all on this rank's device (or CPU under gloo).
+    Returns (xyz, ids, colors) of the points this rank now owns, ordered by source rank then by creation order."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return xyz, ids, colors
+    world = dist.get_world_size(group)
+    dst = shard_of_points(xyz, world, cell)
+    order = torch.argsort(dst, stable=True)
+    send_counts = torch.bincount(dst, minlength=world).to(torch.int64)
+    recv_counts = torch.empty_like(send_counts)
+    dist.all_to_all_single(recv_counts, send_counts, group=group)
+    # one 20-byte record per point: 3 x f32 coordinates, the id and the packed colour reinterpreted as f32 lanes
+    rec = torch.empty(xyz.shape[0], 5, dtype=torch.float32, device=xyz.device)
+    rec[:, :3] = xyz
+    rec[:, 3] = ids.to(torch.int32).view(torch.float32)
+    if colors is not None:
+        c = colors.to(torch.int32)
+        rec[:, 4] = (c[:, 0] | (c[:, 1] << 8) | (c[:, 2] << 16)).view(torch.float32)
+    else:
+        rec[:, 4] = 0
+    rec = rec[order].contiguous()
+    n_in, n_out = send_counts.tolist(), recv_counts.tolist()
+    out = torch.empty(sum(n_out), 5, dtype=torch.float32, device=xyz.device)
+    dist.all_to_all_single(out, rec, output_split_sizes=n_out, input_split_sizes=n_in, group=group)
+    oxyz = out[:, :3].contiguous()
+    oids = out[:, 3].contiguous().view(torch.int32)
+    ocol = None
+    if colors is not None:
+        p = out[:, 4].contiguous().view(torch.int32)
+        ocol = torch.stack([p & 255, (p >> 8) & 255, (p >> 16) & 255], dim=1).to(torch.uint8)
+    return oxyz, oids, ocol

@@ -122,3 +122,45 @@ def test_vote_table_decomposition_equals_track():
     n_masks = int(seg.max()) + 1
     rows2, m2 = OF.decide_from_table(OF.vote_table(ins1, sp, n_masks, n1), [r["area"] for r in rows1], 100, n1)
     assert rows1 == rows2 and m1 == m2 and (OF.apply_decisions(ins1, sp, rows2) == ins2).all()
+
+
+def _route_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from ovo_b200.sharding import route_new_points
+    rng = np.random.default_rng(100 + rank)                       # each rank integrated a different frame
+    n = 5000 + 700 * rank
+    xyz = torch.from_numpy(rng.uniform(-4, 4, (n, 3)).astype(np.float32))
+    ids = torch.arange(n, dtype=torch.int32) + 1_000_000 * rank
+    col = torch.from_numpy(rng.integers(0, 256, (n, 3), dtype=np.uint8))
+    oxyz, oids, ocol = route_new_points(xyz, ids, col)
+    q.put((rank, xyz.numpy(), ids.numpy(), col.numpy(), oxyz.numpy(), oids.numpy(), ocol.numpy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_new_points_are_routed_to_their_shard_world2():
+    """The one all-to-all of the map-growth step: every new point ends on the shard its voxel hashes to,
+    nothing is lost or duplicated, payload (xyz bits, id, colour) intact, receive order = (source rank, creation order)."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_route_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=180) for _ in range(world)], key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, *_rest in res:
+        oxyz, oids, ocol = res[rank][4], res[rank][5], res[rank][6]
+        assert (shard_of_points(oxyz, world) == rank).all()
+        exp_xyz, exp_ids, exp_col = [], [], []
+        for src in range(world):                                   # source-rank major, creation order inside
+            sx, si, sc = res[src][1], res[src][2], res[src][3]
+            m = shard_of_points(sx, world) == rank
+            exp_xyz.append(sx[m]); exp_ids.append(si[m]); exp_col.append(sc[m])
+        assert (oxyz.view(np.int32) == np.concatenate(exp_xyz).view(np.int32)).all()      # bit-exact coordinates
+        assert (oids == np.concatenate(exp_ids)).all() and (ocol == np.concatenate(exp_col)).all()
+    assert sum(len(r[5]) for r in res) == sum(len(r[2]) for r in res)

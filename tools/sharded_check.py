@@ -12,7 +12,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from oracle import fusion as OF  # noqa: E402
 from ovo_b200 import synth  # noqa: E402
 from ovo_b200.map import SemanticMap  # noqa: E402
-from ovo_b200.sharding import ShardedAssociation, shard_of_points, gather_descriptors  # noqa: E402
+from ovo_b200.sharding import ShardedAssociation, shard_of_points, gather_descriptors, route_new_points  # noqa: E402
 
 
 def main():
@@ -53,6 +53,24 @@ def main():
     feats = torch.full((2 + rank, 8), float(rank), device=dev)
     allf = gather_descriptors(feats, [2 + r for r in range(world)])
     ok = ok and allf.shape[0] == sum(2 + r for r in range(world))
+    # map growth: every rank "integrated" a different frame; the new points go to their owners with one NCCL all-to-all
+    rng = np.random.default_rng(100 + rank)
+    n_new = 76800
+    nxyz = torch.from_numpy(rng.uniform(-4, 4, (n_new, 3)).astype(np.float32)).to(dev)
+    nids = (torch.arange(n_new, dtype=torch.int32) + 1_000_000 * rank).to(dev)
+    ncol = torch.from_numpy(rng.integers(0, 256, (n_new, 3), dtype=np.uint8)).to(dev)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    oxyz, oids, ocol = route_new_points(nxyz, nids, ncol)
+    e1.record()
+    torch.cuda.synchronize()
+    owned = bool((shard_of_points(oxyz, world) == rank).all())
+    tot = torch.tensor([oxyz.shape[0]], device=dev)
+    dist.all_reduce(tot)
+    ok = ok and owned and int(tot.item()) == n_new * world and bool((oids // 1_000_000 < world).all())
+    if rank == 0:
+        print(f"route_new_points: {n_new} new points per rank, all-to-all {e0.elapsed_time(e1):.3f} ms, owned {owned}, total {int(tot.item())}", flush=True)
     t = torch.tensor([int(ok)], device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     if rank == 0:
