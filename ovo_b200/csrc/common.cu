@@ -184,6 +184,8 @@ int launch_gemm(int epi, const __nv_bfloat16* A, int lda, const __nv_bfloat16* B
     case EPI_QKV: return launch_bn<EPI_QKV>(bn, A, lda, B, ldb, M, N, K, ep, stream);
     case EPI_PATCH: return launch_bn<EPI_PATCH>(bn, A, lda, B, ldb, M, N, K, ep, stream);
     case EPI_BF16_RELU: return launch_bn<EPI_BF16_RELU>(bn, A, lda, B, ldb, M, N, K, ep, stream);
+    case EPI_GELU_DOT: return launch_bn<EPI_GELU_DOT>(bn, A, lda, B, ldb, M, N, K, ep, stream);
+    case EPI_UP_LN: return launch_bn<EPI_UP_LN>(bn >= 128 ? bn : 128, A, lda, B, ldb, M, N, K, ep, stream);
   }
   return set_error(OVO_E_INVALID, "unknown epilogue %d", epi);
 }

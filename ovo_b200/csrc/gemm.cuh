@@ -21,6 +21,12 @@ enum EpiKind : int {
   EPI_QKV = 4,        // split q/k/v head-major [b,h,seq_pad,64], 2D-RoPE on q,k (pe.py:125-143, rope.py:40-62)
   EPI_PATCH = 5,      // out_f32[token row] = acc + pos_emb      (pe.py:509-519)
   EPI_BF16_RELU = 6,  // out_bf16 = relu(acc + bias)            (SAM-2 two-way transformer MLP, sam/transformer.py:161-163)
+  EPI_GELU_DOT = 7,   // SAM-2 mask decoder, second transposed conv fused with the hyper-network product (mask_decoder.py:217,
+                      // 225-226): v = gelu(acc + bias + resid[row % resid_mod]) is one final pixel's 32 channels per 32-column
+                      // chunk; masks[p, m, Y, X] = v . dot_w[p, 1+m, :] for the 3 multimask tokens.  The up-scaled embedding is
+                      // never written.
+  EPI_UP_LN = 8,      // SAM-2 mask decoder, first transposed conv + LayerNorm2d + GELU (mask_decoder.py:214-216): per 64-column
+                      // group (one sub-pixel): out_bf16 = gelu(ln_w * normalize(acc + bias + resid[row % resid_mod]) + ln_b)
 };
 
 struct EpiParams {
@@ -42,6 +48,13 @@ struct EpiParams {
   // EPI_PATCH
   const float* pos = nullptr;  // [1 + patches, width]
   int patches = 0;             // patches per image (576)
+  // EPI_GELU_DOT
+  const float* dot_w = nullptr;   // [P, 4, 32] hyper-network outputs
+  float* dot_out = nullptr;       // [P, 3, 4g, 4g] mask logits
+  int dot_g = 0;                  // image-embedding grid side g (rows are (p, y, x, sub1) over g x g, columns (sub2, 32 channels))
+  // EPI_UP_LN
+  const float* ln_w = nullptr;    // [64]
+  const float* ln_b = nullptr;
   int prof_cls = 0;            // profiling class of this launch (common.cuh ProfClass; host side only)
   int debug = 0;               // tuning experiments: 1 = no epilogue, 2 = no MMA, 4 = no TMA loads, 8 = no GELU math,
                                // 16 = no global stores, 32 = no bias loads, 64 = no residual prefetch
@@ -180,6 +193,41 @@ __device__ __forceinline__ void epilogue_store(const EpiParams& ep, int row, int
   }
 }
 
+// ---- thread-local fused epilogues of the SAM-2 mask decoder -------------------------------------------------------
+// One thread owns `row` and the 32 accumulator columns of chunk `col`: exactly the 32 channels of one output pixel.
+__device__ __forceinline__ void epilogue_gelu_dot(const EpiParams& ep, int row, int col, const uint32_t (&v)[32], int M) {
+  if (row >= M) return;
+  float x[32];
+  const float4* b4 = reinterpret_cast<const float4*>(ep.bias + col);
+  const float4* r4 = reinterpret_cast<const float4*>(ep.resid + static_cast<size_t>(row % ep.resid_mod) * ep.ldr + col);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 b = __ldg(b4 + j), r = __ldg(r4 + j);
+    x[4 * j] = gelu_erf(__uint_as_float(v[4 * j]) + b.x + r.x);
+    x[4 * j + 1] = gelu_erf(__uint_as_float(v[4 * j + 1]) + b.y + r.y);
+    x[4 * j + 2] = gelu_erf(__uint_as_float(v[4 * j + 2]) + b.z + r.z);
+    x[4 * j + 3] = gelu_erf(__uint_as_float(v[4 * j + 3]) + b.w + r.w);
+  }
+  const int g = ep.dot_g, per = 4 * g * g;
+  const int p = row / per, rem = row - p * per;
+  const int t = rem >> 2, sub1 = rem & 3, sub2 = col >> 5;
+  const int y = t / g, xq = t - y * g;
+  const int S = 4 * g;
+  const int Y = 4 * y + 2 * (sub1 >> 1) + (sub2 >> 1), X = 4 * xq + 2 * (sub1 & 1) + (sub2 & 1);
+  const float4* w4 = reinterpret_cast<const float4*>(ep.dot_w + static_cast<size_t>(p) * 128 + 32);   // tokens 1..3 (multimask)
+  float* o = ep.dot_out + (static_cast<size_t>(p) * 3 * S + Y) * S + X;
+#pragma unroll
+  for (int m = 0; m < 3; ++m) {
+    float a = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 w = __ldg(w4 + m * 8 + j);   // the same address for the whole warp: a broadcast
+      a += x[4 * j] * w.x + x[4 * j + 1] * w.y + x[4 * j + 2] * w.z + x[4 * j + 3] * w.w;
+    }
+    o[static_cast<size_t>(m) * S * S] = a;
+  }
+}
+
 // ---- coalesced epilogue -----------------------------------------------------------------------------------------
 // After tcgen05.ld a thread owns one output ROW (32 columns): storing that directly makes every warp instruction
 // touch 32 different cache lines (measured: the epilogue, not the MMA, bounded the GEMM).  Instead each epilogue
@@ -230,6 +278,10 @@ template <int EPI>
 __device__ __forceinline__ void epilogue_chunk(const EpiParams& ep, int row0, int lane, int col, const uint32_t (&v)[32],
                                                int M, int N, const float2* s_rope, uint8_t* st, const ResidPrefetch* pf = nullptr) {
   if (col >= N) return;  // warp uniform
+  if constexpr (EPI == EPI_GELU_DOT) {
+    epilogue_gelu_dot(ep, row0 + lane, col, v, M);
+    return;
+  }
   bool fast = (col + 32 <= N);
   if constexpr (EPI == EPI_F32 || EPI == EPI_F32_RESID)
     fast = fast && (ep.ldo & 3) == 0 && (reinterpret_cast<uintptr_t>(ep.out) & 15) == 0 &&
@@ -363,6 +415,54 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& ep, int row0, in
   }
 }
 
+// EPI_UP_LN: one warp handles rows row0..row0+31 x the 64 columns of chunks `col` and `col`+32 (one sub-pixel's channels).
+__device__ __forceinline__ void epilogue_up_ln(const EpiParams& ep, int row0, int lane, int col, const uint32_t (&v0)[32],
+                                               const uint32_t (&v1)[32], int M, uint8_t* st) {
+  const int row = row0 + lane;
+  float x[64];
+  {
+    const int rr = row < M ? row : M - 1;
+    const float4* b4 = reinterpret_cast<const float4*>(ep.bias + col);
+    const float4* r4 = reinterpret_cast<const float4*>(ep.resid + static_cast<size_t>(ep.resid_mod > 0 ? rr % ep.resid_mod : rr) * ep.ldr + col);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float4 b = __ldg(b4 + j), r = __ldg(r4 + j);
+      const uint32_t* src = j < 8 ? &v0[4 * j] : &v1[4 * (j - 8)];
+      x[4 * j] = __uint_as_float(src[0]) + b.x + r.x; x[4 * j + 1] = __uint_as_float(src[1]) + b.y + r.y;
+      x[4 * j + 2] = __uint_as_float(src[2]) + b.z + r.z; x[4 * j + 3] = __uint_as_float(src[3]) + b.w + r.w;
+    }
+  }
+  float sum = 0.f;
+#pragma unroll
+  for (int j = 0; j < 64; ++j) sum += x[j];
+  const float u = sum * (1.f / 64.f);
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < 64; ++j) { x[j] -= u; q += x[j] * x[j]; }
+  const float r = 1.f / sqrtf(q * (1.f / 64.f) + 1e-6f);   // LayerNorm2d (sam2_utils.py:141-153)
+  const int sub = lane & 3, rsub = lane >> 2;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    uint32_t in[16];
+    const float4* w4 = reinterpret_cast<const float4*>(ep.ln_w + ((col + 32 * h) & 63));
+    const float4* c4 = reinterpret_cast<const float4*>(ep.ln_b + ((col + 32 * h) & 63));
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 w = __ldg(w4 + j), c = __ldg(c4 + j);
+      const float* xs = &x[32 * h + 4 * j];
+      in[2 * j] = pack_bf16(gelu_erf(w.x * (xs[0] * r) + c.x), gelu_erf(w.y * (xs[1] * r) + c.y));
+      in[2 * j + 1] = pack_bf16(gelu_erf(w.z * (xs[2] * r) + c.z), gelu_erf(w.w * (xs[3] * r) + c.w));
+    }
+    uint4 o[4];
+    stage_exchange(st, lane, in, o);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int rw = row0 + 8 * i + rsub;
+      if (rw < M) *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(ep.out) + static_cast<size_t>(rw) * ep.ldo + col + 32 * h + 8 * sub) = o[i];
+    }
+  }
+}
+
 // CS = thread-block cluster size along M.  The CS CTAs of a cluster work on CS consecutive M tiles of the SAME
 // N tile; each loads 1/CS of the B tile and TMA-multicasts it to all of them, so L2 operand traffic per CTA and
 // k-block drops from 16 KB + BN*128 B to 16 KB + BN*128/CS B (the kernel is otherwise L2-bandwidth bound).
@@ -492,6 +592,17 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
           if (pre_ok && c + 2 < BN / 32) resid_prefetch(ep, tm * kBM + quad * 32, lane, tn * BN + (c + 2) * 32, M, N, nxt);
           tmem_ld_wait();
           if (!(ep.debug & 1)) epilogue_chunk<EPI>(ep, tm * kBM + quad * 32, lane, tn * BN + c * 32, v, M, N, s_rope, s_stage + (warp - 2) * 2048, &cur);
+        }
+      } else if constexpr (EPI == EPI_UP_LN) {
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 2 * half; c + 1 < BN / 32; c += 4) {   // adjacent chunk pairs = the 64 channels of one sub-pixel
+          uint32_t v0[32], v1[32];
+          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + c * 32, v0);
+          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + (c + 1) * 32, v1);
+          tmem_ld_wait();
+          if (tn * BN + c * 32 + 64 <= N) epilogue_up_ln(ep, tm * kBM + quad * 32, lane, tn * BN + c * 32, v0, v1, M, s_stage + (warp - 2) * 2048);
         }
       } else {
       mbar_wait(&tmem_full[acc], acc_phase);

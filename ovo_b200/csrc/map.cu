@@ -159,6 +159,9 @@ __global__ void __launch_bounds__(kP1Threads)
   __shared__ float s_xyz[kP1Threads * 3];
   __shared__ FrameGeom s_g;
   __shared__ FrameDev s_f;
+  __shared__ int s_warp_cnt[kP1Threads / 32], s_base, s_matched;
+  int n_matched_local = 0;
+  if (threadIdx.x == 0) s_matched = 0;
   if (threadIdx.x < sizeof(FrameGeom) / 4) reinterpret_cast<int*>(&s_g)[threadIdx.x] = reinterpret_cast<const int*>(geom)[threadIdx.x];
   for (int i = threadIdx.x; i < static_cast<int>(sizeof(FrameDev) / 4); i += blockDim.x)
     reinterpret_cast<int*>(&s_f)[i] = reinterpret_cast<const int*>(fr)[i];
@@ -217,25 +220,36 @@ __global__ void __launch_bounds__(kP1Threads)
         }
       }
     }
-    // bookkeeping, warp aggregated
+    // bookkeeping: warp-aggregated inside the block, ONE global atomic per block and 256 points for the list cursor (every
+    // warp hitting the same two global counters serialised ~60k same-address atomics per pass); the matched count is kept
+    // per thread and added once per block at the end
     const unsigned m_all = __ballot_sync(0xffffffffu, matched);
-    if (lane == 0 && m_all) atomicAdd(&counters[1], __popc(m_all));
+    if (lane == 0) n_matched_local += __popc(m_all);
     const bool listed = matched && seg >= 0;
     const unsigned m_list = __ballot_sync(0xffffffffu, listed);
-    if (m_list) {
-      int pos = 0;
-      if (lane == 0) pos = atomicAdd(&counters[0], __popc(m_list));
-      pos = __shfl_sync(0xffffffffu, pos, 0);
-      if (listed) {
-        match_list[pos + __popc(m_list & ((1u << lane) - 1))] = make_int2(static_cast<int>(idx), seg);
-        int id = ins_ids[idx];
-        if (id >= n_ins) id = -1;  // ids the host does not know about count as unassigned
-        const int key = seg * (n_ins + 1) + (id + 1);
-        const unsigned peers = __match_any_sync(m_list, key);
-        if (lane == __ffs(peers) - 1) atomicAdd(smem_votes ? &s_votes[key] : &votes[key], __popc(peers));
-      }
+    const int warp = threadIdx.x >> 5;
+    if (lane == 0) s_warp_cnt[warp] = __popc(m_list);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int tot = 0;
+#pragma unroll
+      for (int w = 0; w < kP1Threads / 32; ++w) { const int c = s_warp_cnt[w]; s_warp_cnt[w] = tot; tot += c; }
+      s_base = tot ? atomicAdd(&counters[0], tot) : 0;
+    }
+    __syncthreads();
+    if (listed) {
+      const int pos = s_base + s_warp_cnt[warp] + __popc(m_list & ((1u << lane) - 1));
+      match_list[pos] = make_int2(static_cast<int>(idx), seg);
+      int id = ins_ids[idx];
+      if (id >= n_ins) id = -1;  // ids the host does not know about count as unassigned
+      const int key = seg * (n_ins + 1) + (id + 1);
+      const unsigned peers = __match_any_sync(m_list, key);
+      if (lane == __ffs(peers) - 1) atomicAdd(smem_votes ? &s_votes[key] : &votes[key], __popc(peers));
     }
   }
+  if (n_matched_local) atomicAdd(&s_matched, n_matched_local);
+  __syncthreads();
+  if (threadIdx.x == 0 && s_matched) atomicAdd(&counters[1], s_matched);
   if (smem_votes) {
     __syncthreads();
     for (int i = threadIdx.x; i < n_votes; i += blockDim.x)
@@ -747,6 +761,9 @@ __global__ void mark_mapped_pixels_kernel(const float* __restrict__ xyz, long lo
                                           uint8_t* __restrict__ mapped) {
   __shared__ FrameGeom s_g;
   __shared__ FrameDev s_f;
+  __shared__ int s_warp_cnt[kP1Threads / 32], s_base, s_matched;
+  int n_matched_local = 0;
+  if (threadIdx.x == 0) s_matched = 0;
   if (threadIdx.x < sizeof(FrameGeom) / 4) reinterpret_cast<int*>(&s_g)[threadIdx.x] = reinterpret_cast<const int*>(geom)[threadIdx.x];
   for (int i = threadIdx.x; i < static_cast<int>(sizeof(FrameDev) / 4); i += blockDim.x)
     reinterpret_cast<int*>(&s_f)[i] = reinterpret_cast<const int*>(fr)[i];

@@ -975,7 +975,7 @@ int ovo_sam_create(const ovo_sam_cfg* cfg, const ovo_sam_weights* w, int max_h, 
   A(&s->t_q, R * kC); A(&s->t_k, R * kC); A(&s->t_v, R * kC); A(&s->t_o, R * kC); A(&s->t_mlp, R * 2048);
   A(&s->keys, P * HW * kC); A(&s->keys_pre, P * HW * kC); A(&s->keys_bf, P * HW * kC); A(&s->keyspe_bf, P * HW * kC);
   A(&s->big_q, P * HW * kInt); A(&s->big_k, P * HW * kInt); A(&s->big_v, P * HW * kInt);
-  A(&s->up1, P * HW * 4 * 64); A(&s->up2, P * HW * 16 * 32);
+  A(&s->up1, P * HW * 4 * 64);
   A(&s->hyper, P * 4 * 32); A(&s->iou_head, P * 4); A(&s->tok_a, P * kC); A(&s->tok_b, P * kC);
   A(&s->stats, P * 3); A(&s->cand, P * 3); A(&s->sel, P * 3);
   A(&s->low_all, P * 3 * 16 * HW); A(&s->iou_all, P * 3); A(&s->points, P * 2);
@@ -988,7 +988,6 @@ int ovo_sam_create(const ovo_sam_cfg* cfg, const ovo_sam_weights* w, int max_h, 
     ovo_sam_destroy(s);
     return set_error(OVO_E_CUDA, "ovo_sam_create: cudaFuncSetAttribute(shared memory) failed: %s", cudaGetErrorString(cudaGetLastError()));
   }
-  s->dc1 = s->keys_pre;   // [P*HW, 256] f32: the transposed-conv output reuses the pre-LayerNorm key buffer
   *out = s;
   return OVO_OK;
 }
@@ -1122,12 +1121,8 @@ static int sam_predict_impl(ovo_sam_t* s, const float* points_dev, int P, float*
   OVO_TRY(gemm(EPI_BF16, s->keyspe_bf, kC, s->w.final_attn.k_w, kC, static_cast<int>(PHW), kInt, kC, s->w.final_attn.k_b, s->big_k, kInt, nullptr, 0, 0, st));
   OVO_TRY(gemm(EPI_BF16, s->keys_bf, kC, s->w.final_attn.v_w, kC, static_cast<int>(PHW), kInt, kC, s->w.final_attn.v_b, s->big_v, kInt, nullptr, 0, 0, st));
   OVO_TRY(t2i_block(s, s->w.final_attn, s->big_k, s->big_v, static_cast<size_t>(HW) * kInt, P, s->w.norm_final_w, s->w.norm_final_b, st));
-  // hs = s->queries.  Upscaling (mask_decoder.py:210-217): two k2 s2 transposed convs as GEMMs with N = 4*C_out
-  OVO_TRY(gemm(EPI_F32_RESID, s->keys_bf, kC, s->w.up0_w, kC, static_cast<int>(PHW), 256, kC, s->w.up0_b, s->dc1, 256, s->s1_sub, 256, HW, st));
-  sam_up1_kernel<<<num_sms() * 8, 256, 0, st>>>(s->dc1, PHW * 4, s->w.up_ln_w, s->w.up_ln_b, s->up1);
-  OVO_CHECK_LAUNCH();
-  OVO_TRY(gemm(EPI_BF16_GELU, s->up1, 64, s->w.up1_w, 64, static_cast<int>(PHW * 4), 128, 64, s->w.up1_b, s->up2, 128, s->s0_sub, 128, 4 * HW, st));
-  // hypernetwork MLPs on the 4 mask tokens (:219-224) and the IoU head (:229)
+  // hs = s->queries.  Hypernetwork MLPs on the 4 mask tokens (mask_decoder.py:219-224) and the IoU head (:229) first: the
+  // mask product is fused into the last up-scaling GEMM below.
   for (int i = 0; i < 4; ++i) {
     sam_pick_token_kernel<<<ceil_div(P * kC, 256), 256, 0, st>>>(s->queries, P, 2 + i, s->tok_a);
     OVO_CHECK_LAUNCH();
@@ -1142,10 +1137,24 @@ static int sam_predict_impl(ovo_sam_t* s, const float* points_dev, int P, float*
   OVO_TRY(gemm(EPI_F32, s->tok_a, 256, s->w.iou_w[2], 256, P, 4, 256, s->w.iou_b[2], s->iou_head, 4, nullptr, 0, 0, st));
   float* low = low_out ? low_out : s->low_all;
   float* iou = iou_out ? iou_out : s->iou_all;
+  // Up-scaling (mask_decoder.py:210-217): the two k2 s2 transposed convs are GEMMs with N = 4*C_out whose epilogues do the
+  // rest — (1) + feat_s1, LayerNorm2d over each sub-pixel's 64 channels, GELU -> up1 bf16 [P*g*g, (sub1, 64)];
+  // (2) + feat_s0, GELU, and the product with the hyper-network vectors (:225-226) -> mask logits.  Neither the
+  // [P,64,2g,2g] nor the [P,32,4g,4g] up-scaled embedding is ever written to memory.
+  {
+    EpiParams ep;
+    ep.out = s->up1; ep.ldo = 256; ep.bias = s->w.up0_b; ep.resid = s->s1_sub; ep.ldr = 256; ep.resid_mod = HW;
+    ep.ln_w = s->w.up_ln_w; ep.ln_b = s->w.up_ln_b;
+    OVO_TRY(launch_gemm(EPI_UP_LN, s->keys_bf, kC, static_cast<const __nv_bfloat16*>(s->w.up0_w), kC, static_cast<int>(PHW), 256, kC, ep, st));
+  }
+  {
+    EpiParams ep;
+    ep.bias = s->w.up1_b; ep.resid = s->s0_sub; ep.ldr = 128; ep.resid_mod = 4 * HW;
+    ep.dot_w = s->hyper; ep.dot_out = low; ep.dot_g = g;
+    OVO_TRY(launch_gemm(EPI_GELU_DOT, s->up1, 64, static_cast<const __nv_bfloat16*>(s->w.up1_w), 64, static_cast<int>(PHW * 4), 128, 64, ep, st));
+  }
   {
     ProfScope prof(st, PROF_OTHER, 0.0, 0.0);
-    sam_mask_dot_kernel<<<dim3(ceil_div(16 * HW, 256), P), 256, 0, st>>>(s->up2, s->hyper, g, low);
-    OVO_CHECK_LAUNCH();
     sam_iou_kernel<<<ceil_div(P * 3, 256), 256, 0, st>>>(s->iou_head, P, iou);
     OVO_CHECK_LAUNCH();
   }
