@@ -125,6 +125,7 @@ def run_ours(args, rank, world, local_rank):
     state = dict(next_id=0, n_matched=0)
 
     side = torch.cuda.Stream(device=dev)
+    # (a high-priority stream for the encoder was measured: no gain — 813 vs 817 keyframes/s — and it starves the association)
     ident_all = torch.arange(F * M, dtype=torch.int32, device=dev).reshape(F, M)
 
     def step():
@@ -167,6 +168,7 @@ def run_ours(args, rank, world, local_rank):
         e0.record()
         for _ in range(steps):
             fn()
+        torch.cuda.current_stream().wait_stream(side)      # the last step's fusion (side stream) belongs to the timed region
         e1.record()
         torch.cuda.synchronize()
         launches = _lib.lib().ovo_launch_count(0)
@@ -186,6 +188,11 @@ def run_ours(args, rank, world, local_rank):
     clocks = sampler.stop() if sampler else None
     ms_step = ms_total / args.steps
     value = world * F / (ms_step / 1e3)
+
+    # --- the encoder alone (E1..E5 of the same batch, nothing on the side stream): what the step costs beyond it is
+    # association/fusion contention and host gaps
+    enc_ms, _ = timed(lambda: enc.encode_regions(rgb_d, masks_d, masks_per_frame=[M] * F), 10, 3)
+    enc_ms /= 10
 
     # --- per-kernel-class breakdown: same steps, CUDA events around every launch (instrumented pass)
     # The instrumented pass launches eagerly (no graphs) with an event pair per kernel.  A short device-side sleep is queued
@@ -208,7 +215,7 @@ def run_ours(args, rank, world, local_rank):
                 "flops_per_launch": round(g["flops"] / max(g["launches"], 1) / 1e9, 2), "avg_launch_us": round(1e3 * g["ms"] / max(g["launches"], 1), 2),
                 "share_of_step": round(g["ms"] / tot_ms, 3) if tot_ms else None,
                 "how": "CUDA events around every launch in an instrumented pass of the same steps (graphs off, launches queued behind a 30 ms device sleep so host launch latency is not counted)",
-                "step_breakdown_ms": breakdown,
+                "step_breakdown_ms": breakdown, "encoder_only_ms_per_step": round(enc_ms, 4),
                 "encoder_algorithmic_tflops": round(2 * F * GFLOP_PER_IMAGE / (sum(prof[k]["ms"] for k in ("gemm", "attention", "layernorm")) / 2) , 1)}
 
     # --- query: dense cosine of the text bank against the 2M-point map (HBM-bound)
