@@ -50,6 +50,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
     attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                          const __grid_constant__ CUtensorMap tmV, __nv_bfloat16* __restrict__ out, int seq,
                          int seq_pad, int heads, int ld_out, float scale_log2e, int causal, int dbg, int qtiles, int n_items) {
+  griddep_launch();
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();  // the 128B swizzle needs 1024-byte aligned tiles
   const int nblk = seq_pad / kAttnKB;

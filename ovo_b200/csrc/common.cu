@@ -80,6 +80,15 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t
   return OVO_OK;
 }
 
+static bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("OVO_B200_PDL");
+    v = (e && e[0] == '1') ? 1 : 0;   // opt-in: measured 0-1 % on graph-replayed ViT / SAM-2 trunks (launch gaps are not the limit)
+  }
+  return v == 1;
+}
+
 template <int BN, int EPI, int CS>
 static int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const EpiParams& ep,
                       cudaStream_t stream) {
@@ -94,21 +103,28 @@ static int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N
   const int max_clusters = num_sms() / CS;
   const int grid = (ctiles < max_clusters ? ctiles : max_clusters) * CS;
   ProfScope prof(stream, ep.prof_cls, 2.0 * M * N * K, 2.0 * (static_cast<double>(M) * K + static_cast<double>(N) * K) + 4.0 * M * N);
-  if constexpr (CS == 1) {
-    kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, M, N, K, ep);
-  } else {
+  {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(kGemmThreads);
     cfg.dynamicSmemBytes = Cfg::kSmemBytes;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CS;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if constexpr (CS > 1) {
+      attr[na].id = cudaLaunchAttributeClusterDimension;
+      attr[na].val.clusterDim.x = CS;
+      attr[na].val.clusterDim.y = 1;
+      attr[na].val.clusterDim.z = 1;
+      ++na;
+    }
+    if (pdl_enabled()) {   // programmatic dependent launch: our prologue overlaps the previous kernel's tail (ptx.cuh)
+      attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[na].val.programmaticStreamSerializationAllowed = 1;
+      ++na;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = na;
     OVO_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, M, N, K, ep));
   }
   OVO_CHECK_LAUNCH();

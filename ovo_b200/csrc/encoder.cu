@@ -20,6 +20,7 @@ __global__ void __launch_bounds__(256)
     layernorm_kernel(const float* __restrict__ x, int rows, int width, const float* __restrict__ g,
                      const float* __restrict__ b, float eps, __nv_bfloat16* __restrict__ out_bf16,
                      float* __restrict__ out_f32, const int* __restrict__ gather /* optional row indices */) {
+  griddep_launch();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;

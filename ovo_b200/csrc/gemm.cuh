@@ -486,6 +486,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
   float2* s_rope = reinterpret_cast<float2*>(smem + Cfg::kStages * Cfg::kStageBytes + 256);
   uint8_t* s_stage = reinterpret_cast<uint8_t*>(s_rope) + kRopeRowsMax * 17 * 8;
 
+  griddep_launch();   // the next kernel of the stream may be scheduled as SMs free up (it waits for our completion itself)
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int tiles_m = (M + kBM - 1) / kBM;
@@ -521,6 +522,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
   if constexpr (CS > 1) cluster_sync_all();   // peers' barriers are initialised before anyone signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // PDL: everything above (barrier init, TMEM allocation, tensor-map prefetch, the constant RoPE table) overlapped the
+  // previous kernel's tail; operands, residuals and outputs are only touched from here on
+  griddep_wait();
 
   if (warp == 0) {
     if (lane == 0) {

@@ -52,6 +52,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Programmatic dependent launch (PDL): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start
+// while its predecessor in the stream is still draining; it must execute griddep_wait() before it touches anything the
+// predecessor wrote (the wait returns once the predecessor has completed and its writes are visible).  griddep_launch()
+// in the predecessor lets the dependent's CTAs be scheduled as soon as every predecessor CTA has passed it (or exited).
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
+
 // named barriers for a subset of the CTA's warps (id 1..15; `threads` = multiple of 32 participating threads)
 __device__ __forceinline__ void named_bar_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(threads) : "memory");

@@ -30,6 +30,7 @@ __global__ void __launch_bounds__(256)
     sam_ln_kernel(const float* __restrict__ x, int rows, int width, const float* __restrict__ g, const float* __restrict__ b,
                   float eps, float* __restrict__ out32, __nv_bfloat16* __restrict__ out16, __nv_bfloat16* __restrict__ out16b,
                   const float* __restrict__ add, int add_mod) {
+  griddep_launch();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -82,6 +83,7 @@ __global__ void __launch_bounds__(256)
     sam_ln256_kernel(const float* __restrict__ x, int rows, const float* __restrict__ g, const float* __restrict__ b, float eps,
                      float* __restrict__ out32, __nv_bfloat16* __restrict__ out16, __nv_bfloat16* __restrict__ out16b,
                      const float* __restrict__ add, int add_mod) {
+  griddep_launch();
   const int lane = threadIdx.x & 31;
   const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int nwarps = gridDim.x * (blockDim.x >> 5);

@@ -70,6 +70,7 @@ constexpr int hiera_attn_smem_bytes() { return (QB + 4 * kSamKB) * kSamRow * 2; 
 
 template <int QB>
 __global__ void __launch_bounds__(QB * 2) hiera_attention_kernel(WinAttnParams p) {
+  griddep_launch();
   extern __shared__ __align__(16) uint8_t hiera_smem[];
   __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(hiera_smem);
   __nv_bfloat16* sKV = sQ + QB * kSamRow;                 // stage s: K at sKV + s*2*64*row, V right after K
@@ -251,6 +252,7 @@ constexpr int kT2iSmemBytes = 2 * 2 * 64 * kT2iRow * 2;
 __global__ void __launch_bounds__(256) sam_t2i_attn_mma_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k,
                                                                const __nv_bfloat16* __restrict__ v, size_t kv_stride, int n_keys,
                                                                __nv_bfloat16* __restrict__ out) {
+  griddep_launch();
   extern __shared__ __align__(16) uint8_t t2i_smem[];
   __nv_bfloat16* sKV = reinterpret_cast<__nv_bfloat16*>(t2i_smem);
   const int prompt = blockIdx.x, tid = threadIdx.x, head = tid >> 5, lane = tid & 31;
