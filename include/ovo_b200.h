@@ -297,6 +297,7 @@ typedef struct {
   int stage_end[4];        /* block index closing each stage (hieradet.py:193) */
   int decoder_depth;       /* 2 */
   float trunk_ln_eps;      /* 1e-6 */
+  int max_batch;           /* frames one trunk pass may take (ovo_sam_set_images); 0 or 1 = single frame */
 } ovo_sam_cfg;
 
 typedef struct {
@@ -344,6 +345,10 @@ void ovo_sam_destroy(ovo_sam_t* sam);
  * [grid^2, dim] after the last executed block (layer-by-layer parity tests). */
 int ovo_sam_set_image(ovo_sam_t* sam, const uint8_t* rgb_dev, int H, int W, float* pixels_out_dev, float* embed_out_dev,
                       float* feat_s0_out_dev, float* feat_s1_out_dev, int n_blocks, float* block_out_dev, void* stream);
+/* The same for n <= cfg.max_batch frames [n,H,W,3] in ONE trunk pass (replay / MaskGenerator.precompute: the stage-3 GEMMs of
+ * a single frame have only 4096 token rows); the decoder then works on the frame chosen with ovo_sam_select_image. */
+int ovo_sam_set_images(ovo_sam_t* sam, const uint8_t* rgb_dev, int n, int H, int W, void* stream);
+int ovo_sam_select_image(ovo_sam_t* sam, int index);
 /* Test tap: run the trunk from already normalised pixels f32 [3,S,S] instead of the resize. */
 int ovo_sam_set_pixels(ovo_sam_t* sam, const float* pixels_dev, float* embed_out_dev, float* feat_s0_out_dev,
                        float* feat_s1_out_dev, int n_blocks, float* block_out_dev, void* stream);
@@ -364,6 +369,11 @@ int ovo_sam_postprocess(ovo_sam_t* sam, const float* low_res_dev, const float* i
  *   -> seg_map i32 [H,W] (-1 = none), masks_out uint8 [M,H,W] in painted order, M in *n_masks (M <= max_masks). */
 int ovo_sam_generate(ovo_sam_t* sam, const uint8_t* rgb_dev, int H, int W, const ovo_amg_params* prm, int32_t* seg_map_dev,
                      uint8_t* masks_out_dev, int max_masks, int* n_masks, void* stream);
+
+/* ovo_sam_generate for n_frames <= cfg.max_batch frames with one batched trunk pass: seg_maps i32 [n,H,W], masks_out uint8
+ * [n, max_masks, H, W], n_masks_host[n]. */
+int ovo_sam_generate_batch(ovo_sam_t* sam, const uint8_t* rgb_dev, int n_frames, int H, int W, const ovo_amg_params* prm,
+                           int32_t* seg_maps_dev, uint8_t* masks_out_dev, int max_masks, int* n_masks_host, void* stream);
 
 /* OVO.classify_instances (ovo.py:486-491): argmax over queries + threshold. sim f32 [n,Q] ->
  * cls i32 [n] (-1 if max <= th), conf f32 [n] (0 if max <= th). */

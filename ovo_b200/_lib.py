@@ -58,7 +58,7 @@ class SamDecLayer(C.Structure):
 
 class SamCfg(C.Structure):
     _fields_ = [("image_size", c_int), ("n_blocks", c_int), ("embed_dim", c_int), ("stage_end", c_int * 4),
-                ("decoder_depth", c_int), ("trunk_ln_eps", c_float)]
+                ("decoder_depth", c_int), ("trunk_ln_eps", c_float), ("max_batch", c_int)]
 
 
 class SamWeights(C.Structure):
@@ -121,6 +121,10 @@ SIGNATURES = {
     "ovo_sam_create": (c_int, [C.POINTER(SamCfg), C.POINTER(SamWeights), c_int, c_int, c_int, C.POINTER(c_void_p)]),
     "ovo_sam_destroy": (None, [c_void_p]),
     "ovo_sam_set_image": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "ovo_sam_set_images": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "ovo_sam_select_image": (c_int, [c_void_p, c_int]),
+    "ovo_sam_generate_batch": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, C.POINTER(AmgParams), c_void_p, c_void_p, c_int,
+                                       C.POINTER(c_int), c_void_p]),
     "ovo_sam_set_pixels": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "ovo_sam_predict": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "ovo_sam_postprocess": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, C.POINTER(AmgParams), c_void_p,

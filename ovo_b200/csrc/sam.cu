@@ -179,8 +179,10 @@ __global__ void sam_resize_v_kernel(const float* __restrict__ tmp, int H, const 
   px[(static_cast<size_t>(c) * S + oy) * S + ox] = (a - mean) / sd;
 }
 // PatchEmbed conv 7x7 stride 4 pad 3 (backbones/utils.py:65-95) as im2col rows [g*g, kpad] bf16, column = c*49 + ky*7 + kx
-__global__ void sam_im2col_kernel(const float* __restrict__ px, int S, int g, int kpad, __nv_bfloat16* __restrict__ out) {
-  const int t = blockIdx.x;
+__global__ void sam_im2col_kernel(const float* __restrict__ px_all, int S, int g, int kpad, __nv_bfloat16* __restrict__ out_all) {
+  const int img = blockIdx.x / (g * g), t = blockIdx.x - img * g * g;
+  const float* px = px_all + static_cast<size_t>(img) * 3 * S * S;
+  __nv_bfloat16* out = out_all + static_cast<size_t>(img) * g * g * kpad;
   const int ty = t / g, tx = t - ty * g;
   for (int j = threadIdx.x; j < kpad; j += blockDim.x) {
     float v = 0.f;
@@ -193,14 +195,15 @@ __global__ void sam_im2col_kernel(const float* __restrict__ px, int S, int g, in
   }
 }
 // MaxPool2d(2,2) on a [g,g,C] f32 token grid -> [g/2,g/2,C]  (hieradet.py:25-37, the shortcut of a transition block)
-__global__ void sam_maxpool_kernel(const float* __restrict__ in, int g, int C, float* __restrict__ out) {
+__global__ void sam_maxpool_kernel(const float* __restrict__ in, int n_img, int g, int C, float* __restrict__ out) {
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int c4 = C >> 2, go = g >> 1;
-  if (i >= static_cast<size_t>(go) * go * c4) return;
+  if (i >= static_cast<size_t>(n_img) * go * go * c4) return;
   const int c = i % c4;
-  const size_t t = i / c4;
+  const size_t t_all = i / c4;
+  const size_t img = t_all / (static_cast<size_t>(go) * go), t = t_all - img * go * go;
   const int y = t / go, x = t - static_cast<size_t>(y) * go;
-  const float4* p = reinterpret_cast<const float4*>(in);
+  const float4* p = reinterpret_cast<const float4*>(in) + img * g * g * c4;
   const size_t r0 = (static_cast<size_t>(2 * y) * g + 2 * x) * c4 + c;
   const float4 a = p[r0], b = p[r0 + c4], d = p[r0 + static_cast<size_t>(g) * c4], e = p[r0 + static_cast<size_t>(g) * c4 + c4];
   reinterpret_cast<float4*>(out)[i] = make_float4(fmaxf(fmaxf(a.x, b.x), fmaxf(d.x, e.x)), fmaxf(fmaxf(a.y, b.y), fmaxf(d.y, e.y)),
@@ -212,15 +215,16 @@ __global__ void sam_maxpool_kernel(const float* __restrict__ in, int g, int C, f
 __global__ void sam_embed_kernel(const float* __restrict__ lat2, const float* __restrict__ lat3, int g, const float* __restrict__ no_mask,
                                  const float* __restrict__ dense_pe, float* __restrict__ embed, float* __restrict__ src,
                                  __nv_bfloat16* __restrict__ src_bf, __nv_bfloat16* __restrict__ srcpe_bf) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;   // over n_img * g*g * 256 (blockIdx.y = image)
   if (i >= g * g * kC) return;
+  const size_t o = static_cast<size_t>(blockIdx.y) * g * g * kC + i;
   const int c = i % kC, t = i / kC, y = t / g, x = t - y * g;
-  const float e = lat2[i] + lat3[((y >> 1) * (g >> 1) + (x >> 1)) * kC + c];
-  embed[i] = e;
+  const float e = lat2[o] + lat3[(static_cast<size_t>(blockIdx.y) * (g >> 1) * (g >> 1) + (y >> 1) * (g >> 1) + (x >> 1)) * kC + c];
+  embed[o] = e;
   const float s = e + no_mask[c];
-  src[i] = s;
-  src_bf[i] = __float2bfloat16_rn(s);
-  srcpe_bf[i] = __float2bfloat16_rn(s + dense_pe[i]);
+  src[o] = s;
+  src_bf[o] = __float2bfloat16_rn(s);
+  srcpe_bf[o] = __float2bfloat16_rn(s + dense_pe[i]);
 }
 // feature map [2g,2g,C] -> [g*g, (ky*2+kx)*C + c]: the layout in which a k2 s2 transposed conv (a GEMM with N = 4*C_out)
 // meets its high-resolution skip feature (mask_decoder.py:214-217)
@@ -684,6 +688,8 @@ struct ovo_sam {
   std::vector<ovo_hiera_block> blocks;
   std::vector<ovo_sam_dec_layer> layers;
   int S = 0, g = 0;            // image size, embedding grid (S/16)
+  int max_batch = 1;           // images the trunk can take in one pass (activation buffers are sized for it)
+  int n_set = 0, cur = 0;      // images of the last set_image(s) call; the one the decoder works on
   int max_h = 0, max_w = 0, max_p = 0;
   // transform
   int tab_h = -1, tab_w = -1, kx = 0, ky = 0;
@@ -787,21 +793,21 @@ int graphed(ovo_sam* s, long long key, cudaStream_t st, F&& fn) {
 }
 
 // Hiera trunk from the im2col'd patches (hieradet.py:274-291) + neck + decoder-side per-image constants
-int run_trunk(ovo_sam* s, int n_blocks, float* block_out, cudaStream_t st) {
+int run_trunk(ovo_sam* s, int B, int n_blocks, float* block_out, cudaStream_t st) {
   const ovo_sam_cfg& c = s->cfg;
   int grid = s->S / 4;
   const int T0 = grid * grid;
   float* x = s->xa;
   float* xo = s->xb;
   // patch embed + bias + pos embed
-  OVO_TRY(gemm(EPI_F32_RESID, s->patches, s->w.patch_kpad, s->w.patch_w, s->w.patch_kpad, T0, c.embed_dim, s->w.patch_kpad, s->w.patch_b,
-               x, c.embed_dim, s->w.pos, c.embed_dim, 0, st));
+  OVO_TRY(gemm(EPI_F32_RESID, s->patches, s->w.patch_kpad, s->w.patch_w, s->w.patch_kpad, B * T0, c.embed_dim, s->w.patch_kpad, s->w.patch_b,
+               x, c.embed_dim, s->w.pos, c.embed_dim, T0, st));
   const int nb = n_blocks < 0 ? c.n_blocks : std::min(n_blocks, c.n_blocks);
   int stage = 0, last_dim = c.embed_dim;
   for (int i = 0; i < nb; ++i) {
     const ovo_hiera_block& b = s->blocks[i];
     OVO_REQUIRE(b.grid_in == grid, "sam block %d: grid mismatch", i);
-    const int T = grid * grid;
+    const int T = B * grid * grid;               // token rows of all images
     const int ws = b.window > 0 ? b.window : grid;
     OVO_REQUIRE(grid % ws == 0 && (ws * ws) % 16 == 0 && (!b.q_pool || ws % 2 == 0), "sam block %d: unsupported window %d on grid %d", i, ws, grid);
     OVO_REQUIRE(b.dim_out == b.heads * kSamHd, "sam block %d: head_dim must be 72", i);
@@ -813,7 +819,7 @@ int run_trunk(ovo_sam* s, int n_blocks, float* block_out, cudaStream_t st) {
       OVO_TRY(gemm(EPI_F32, s->xn, b.dim, b.short_w, b.dim, T, b.dim_out, b.dim, b.short_b, s->tshort, b.dim_out, nullptr, 0, 0, st));
       if (b.q_pool) {
         grid_out = grid / 2;
-        sam_maxpool_kernel<<<ceil_div(static_cast<long long>(grid_out) * grid_out * (b.dim_out / 4), 256), 256, 0, st>>>(s->tshort, grid, b.dim_out, xo);
+        sam_maxpool_kernel<<<ceil_div(static_cast<long long>(B) * grid_out * grid_out * (b.dim_out / 4), 256), 256, 0, st>>>(s->tshort, B, grid, b.dim_out, xo);
         OVO_CHECK_LAUNCH();
       } else {
         OVO_CUDA(cudaMemcpyAsync(xo, s->tshort, sizeof(float) * T * b.dim_out, cudaMemcpyDeviceToDevice, st));
@@ -827,15 +833,16 @@ int run_trunk(ovo_sam* s, int n_blocks, float* block_out, cudaStream_t st) {
       p.scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(kSamHd));
       const int nq = b.q_pool ? ws * ws / 4 : ws * ws;
       const int wins = (grid / ws) * (grid / ws);
-      ProfScope prof(st, PROF_ATTN, 4.0 * wins * b.heads * static_cast<double>(nq) * ws * ws * kSamHd, 0.0);
+      p.wins2 = wins;
+      ProfScope prof(st, PROF_ATTN, 4.0 * B * wins * b.heads * static_cast<double>(nq) * ws * ws * kSamHd, 0.0);
       if (nq >= 128) {
-        hiera_attention_kernel<128><<<dim3(ceil_div(nq, 128), wins, b.heads), 256, hiera_attn_smem_bytes<128>(), st>>>(p);
+        hiera_attention_kernel<128><<<dim3(ceil_div(nq, 128), B * wins, b.heads), 256, hiera_attn_smem_bytes<128>(), st>>>(p);
       } else {
-        hiera_attention_kernel<64><<<dim3(ceil_div(nq, 64), wins, b.heads), 128, hiera_attn_smem_bytes<64>(), st>>>(p);
+        hiera_attention_kernel<64><<<dim3(ceil_div(nq, 64), B * wins, b.heads), 128, hiera_attn_smem_bytes<64>(), st>>>(p);
       }
       OVO_CHECK_LAUNCH();
     }
-    const int To = grid_out * grid_out;
+    const int To = B * grid_out * grid_out;
     OVO_TRY(gemm(EPI_F32_RESID, s->att, b.dim_out, b.proj_w, b.dim_out, To, b.dim_out, b.dim_out, b.proj_b, dst, b.dim_out, resid, b.dim_out, 0, st));
     if (dst != x) std::swap(x, xo);
     grid = grid_out;
@@ -849,52 +856,57 @@ int run_trunk(ovo_sam* s, int n_blocks, float* block_out, cudaStream_t st) {
       ++stage;
     }
   }
-  if (block_out) OVO_CUDA(cudaMemcpyAsync(block_out, x, sizeof(float) * grid * grid * last_dim, cudaMemcpyDeviceToDevice, st));
+  if (block_out) OVO_CUDA(cudaMemcpyAsync(block_out, x, sizeof(float) * grid * grid * last_dim, cudaMemcpyDeviceToDevice, st));   // image 0
   if (nb < c.n_blocks) return OVO_OK;
   // ---- neck (image_encoder.py:102-134) with conv_s0/conv_s1 folded (sam2_base.py:467-479)
   const int g = s->g;
-  OVO_TRY(gemm(EPI_F32, s->stage_bf[3], s->stage_dim[3], s->w.neck3_w, s->stage_dim[3], (g / 2) * (g / 2), kC, s->stage_dim[3], s->w.neck3_b, s->lat3, kC, nullptr, 0, 0, st));
-  OVO_TRY(gemm(EPI_F32, s->stage_bf[2], s->stage_dim[2], s->w.neck2_w, s->stage_dim[2], g * g, kC, s->stage_dim[2], s->w.neck2_b, s->lat2, kC, nullptr, 0, 0, st));
-  OVO_TRY(gemm(EPI_F32, s->stage_bf[1], s->stage_dim[1], s->w.s1_w, s->stage_dim[1], 4 * g * g, 64, s->stage_dim[1], s->w.s1_b, s->feat_s1, 64, nullptr, 0, 0, st));
-  OVO_TRY(gemm(EPI_F32, s->stage_bf[0], s->stage_dim[0], s->w.s0_w, s->stage_dim[0], 16 * g * g, 32, s->stage_dim[0], s->w.s0_b, s->feat_s0, 32, nullptr, 0, 0, st));
-  sam_embed_kernel<<<ceil_div(g * g * kC, 256), 256, 0, st>>>(s->lat2, s->lat3, g, s->w.no_mask_embed, s->w.dense_pe, s->embed, s->src, s->src_bf, s->srcpe_bf);
+  OVO_TRY(gemm(EPI_F32, s->stage_bf[3], s->stage_dim[3], s->w.neck3_w, s->stage_dim[3], B * (g / 2) * (g / 2), kC, s->stage_dim[3], s->w.neck3_b, s->lat3, kC, nullptr, 0, 0, st));
+  OVO_TRY(gemm(EPI_F32, s->stage_bf[2], s->stage_dim[2], s->w.neck2_w, s->stage_dim[2], B * g * g, kC, s->stage_dim[2], s->w.neck2_b, s->lat2, kC, nullptr, 0, 0, st));
+  OVO_TRY(gemm(EPI_F32, s->stage_bf[1], s->stage_dim[1], s->w.s1_w, s->stage_dim[1], B * 4 * g * g, 64, s->stage_dim[1], s->w.s1_b, s->feat_s1, 64, nullptr, 0, 0, st));
+  OVO_TRY(gemm(EPI_F32, s->stage_bf[0], s->stage_dim[0], s->w.s0_w, s->stage_dim[0], B * 16 * g * g, 32, s->stage_dim[0], s->w.s0_b, s->feat_s0, 32, nullptr, 0, 0, st));
+  sam_embed_kernel<<<dim3(ceil_div(g * g * kC, 256), B), 256, 0, st>>>(s->lat2, s->lat3, g, s->w.no_mask_embed, s->w.dense_pe, s->embed, s->src, s->src_bf, s->srcpe_bf);
   OVO_CHECK_LAUNCH();
-  sam_subpixel_kernel<<<ceil_div(static_cast<long long>(g) * g * 4 * 64, 256), 256, 0, st>>>(s->feat_s1, g, 64, s->s1_sub);
-  OVO_CHECK_LAUNCH();
-  sam_subpixel2_kernel<<<ceil_div(static_cast<long long>(g) * g * 16 * 32, 256), 256, 0, st>>>(s->feat_s0, g, s->s0_sub);
-  OVO_CHECK_LAUNCH();
+  const size_t HWs = static_cast<size_t>(g) * g;
+  for (int b = 0; b < B; ++b) {
+    sam_subpixel_kernel<<<ceil_div(static_cast<long long>(g) * g * 4 * 64, 256), 256, 0, st>>>(s->feat_s1 + b * 4 * HWs * 64, g, 64, s->s1_sub + b * 4 * HWs * 64);
+    OVO_CHECK_LAUNCH();
+    sam_subpixel2_kernel<<<ceil_div(static_cast<long long>(g) * g * 16 * 32, 256), 256, 0, st>>>(s->feat_s0 + b * 16 * HWs * 32, g, s->s0_sub + b * 16 * HWs * 32);
+    OVO_CHECK_LAUNCH();
+  }
   // layer-0 projections of the (prompt independent) image side: k, v of token->image and q of image->token
   const ovo_sam_dec_layer& L0 = s->layers[0];
   const int HW = g * g;
-  OVO_TRY(gemm(EPI_BF16, s->srcpe_bf, kC, L0.t2i.k_w, kC, HW, kInt, kC, L0.t2i.k_b, s->k0, kInt, nullptr, 0, 0, st));
-  OVO_TRY(gemm(EPI_BF16, s->src_bf, kC, L0.t2i.v_w, kC, HW, kInt, kC, L0.t2i.v_b, s->v0, kInt, nullptr, 0, 0, st));
-  OVO_TRY(gemm(EPI_BF16, s->srcpe_bf, kC, L0.i2t.q_w, kC, HW, kInt, kC, L0.i2t.q_b, s->qi0, kInt, nullptr, 0, 0, st));
+  OVO_TRY(gemm(EPI_BF16, s->srcpe_bf, kC, L0.t2i.k_w, kC, B * HW, kInt, kC, L0.t2i.k_b, s->k0, kInt, nullptr, 0, 0, st));
+  OVO_TRY(gemm(EPI_BF16, s->src_bf, kC, L0.t2i.v_w, kC, B * HW, kInt, kC, L0.t2i.v_b, s->v0, kInt, nullptr, 0, 0, st));
+  OVO_TRY(gemm(EPI_BF16, s->srcpe_bf, kC, L0.i2t.q_w, kC, B * HW, kInt, kC, L0.i2t.q_b, s->qi0, kInt, nullptr, 0, 0, st));
   return OVO_OK;
 }
 
 int copy_taps(ovo_sam* s, float* embed, float* s0, float* s1, cudaStream_t st) {
   const int g = s->g;
-  if (embed) OVO_CUDA(cudaMemcpyAsync(embed, s->embed, sizeof(float) * g * g * kC, cudaMemcpyDeviceToDevice, st));
-  if (s0) OVO_CUDA(cudaMemcpyAsync(s0, s->feat_s0, sizeof(float) * 16 * g * g * 32, cudaMemcpyDeviceToDevice, st));
-  if (s1) OVO_CUDA(cudaMemcpyAsync(s1, s->feat_s1, sizeof(float) * 4 * g * g * 64, cudaMemcpyDeviceToDevice, st));
+  const size_t HW = static_cast<size_t>(g) * g, b = s->cur;
+  if (embed) OVO_CUDA(cudaMemcpyAsync(embed, s->embed + b * HW * kC, sizeof(float) * HW * kC, cudaMemcpyDeviceToDevice, st));
+  if (s0) OVO_CUDA(cudaMemcpyAsync(s0, s->feat_s0 + b * 16 * HW * 32, sizeof(float) * 16 * HW * 32, cudaMemcpyDeviceToDevice, st));
+  if (s1) OVO_CUDA(cudaMemcpyAsync(s1, s->feat_s1 + b * 4 * HW * 64, sizeof(float) * 4 * HW * 64, cudaMemcpyDeviceToDevice, st));
   return OVO_OK;
 }
 
-int patches_from_pixels(ovo_sam* s, cudaStream_t st) {
+int patches_from_pixels(ovo_sam* s, int B, cudaStream_t st) {
   ProfScope prof(st, PROF_PRE, 0.0, 0.0);
-  sam_im2col_kernel<<<(s->S / 4) * (s->S / 4), 160, 0, st>>>(s->pixels, s->S, s->S / 4, s->w.patch_kpad, s->patches);
+  sam_im2col_kernel<<<B * (s->S / 4) * (s->S / 4), 160, 0, st>>>(s->pixels, s->S, s->S / 4, s->w.patch_kpad, s->patches);
   OVO_CHECK_LAUNCH();
   return OVO_OK;
 }
 
-int trunk_from_pixels(ovo_sam* s, int n_blocks, float* block_out, cudaStream_t st) {
+int trunk_from_pixels(ovo_sam* s, int B, int n_blocks, float* block_out, cudaStream_t st) {
+  s->n_set = B; s->cur = 0;
   if ((n_blocks < 0 || n_blocks >= s->cfg.n_blocks) && block_out == nullptr)
-    return graphed(s, 1, st, [&](cudaStream_t cs) {
-      OVO_TRY(patches_from_pixels(s, cs));
-      return run_trunk(s, -1, nullptr, cs);
+    return graphed(s, 1 | (static_cast<long long>(B) << 8), st, [&](cudaStream_t cs) {
+      OVO_TRY(patches_from_pixels(s, B, cs));
+      return run_trunk(s, B, -1, nullptr, cs);
     });
-  OVO_TRY(patches_from_pixels(s, st));
-  return run_trunk(s, n_blocks, block_out, st);
+  OVO_TRY(patches_from_pixels(s, B, st));
+  return run_trunk(s, B, n_blocks, block_out, st);
 }
 
 // Attention.forward on the token side: out_proj(attn(...)) handled by the caller; this projects q/k/v of tokens.
@@ -934,6 +946,7 @@ int ovo_sam_create(const ovo_sam_cfg* cfg, const ovo_sam_weights* w, int max_h, 
   s->w.blocks = s->blocks.data(); s->w.layers = s->layers.data();
   s->S = cfg->image_size; s->g = cfg->image_size / 16;
   s->max_h = max_h; s->max_w = max_w; s->max_p = max_prompts;
+  s->max_batch = cfg->max_batch > 1 ? cfg->max_batch : 1;
   {
     const char* env = getenv("OVO_B200_GRAPHS");
     s->use_graphs = !(env && env[0] == '0');
@@ -964,14 +977,15 @@ int ovo_sam_create(const ovo_sam_cfg* cfg, const ovo_sam_weights* w, int max_h, 
   }
   int r = OVO_OK;
   auto A = [&](auto** p, size_t n) { if (r == OVO_OK) r = salloc(s, p, n); };
-  A(&s->tmp, static_cast<size_t>(3) * max_h * S); A(&s->pixels, static_cast<size_t>(3) * S * S);
-  A(&s->patches, static_cast<size_t>(g0) * g0 * w->patch_kpad);
-  A(&s->xa, max_x); A(&s->xb, max_x); A(&s->tshort, max_short); A(&s->xn, max_xn); A(&s->qkv, max_qkv); A(&s->att, max_att); A(&s->hid, max_hid);
-  for (int k = 0; k < 4; ++k) A(&s->stage_bf[k], static_cast<size_t>(s->stage_grid[k]) * s->stage_grid[k] * s->stage_dim[k]);
+  const size_t MB = static_cast<size_t>(s->max_batch);
+  A(&s->tmp, static_cast<size_t>(3) * max_h * S); A(&s->pixels, MB * 3 * S * S);
+  A(&s->patches, MB * g0 * g0 * w->patch_kpad);
+  A(&s->xa, MB * max_x); A(&s->xb, MB * max_x); A(&s->tshort, MB * max_short); A(&s->xn, MB * max_xn); A(&s->qkv, MB * max_qkv); A(&s->att, MB * max_att); A(&s->hid, MB * max_hid);
+  for (int k = 0; k < 4; ++k) A(&s->stage_bf[k], MB * s->stage_grid[k] * s->stage_grid[k] * s->stage_dim[k]);
   const size_t HW = static_cast<size_t>(g) * g;
-  A(&s->lat3, HW / 4 * kC); A(&s->lat2, HW * kC); A(&s->embed, HW * kC); A(&s->feat_s0, 16 * HW * 32); A(&s->feat_s1, 4 * HW * 64);
-  A(&s->s0_sub, 16 * HW * 32); A(&s->s1_sub, 4 * HW * 64); A(&s->src, HW * kC); A(&s->src_bf, HW * kC); A(&s->srcpe_bf, HW * kC);
-  A(&s->k0, HW * kInt); A(&s->v0, HW * kInt); A(&s->qi0, HW * kInt);
+  A(&s->lat3, MB * HW / 4 * kC); A(&s->lat2, MB * HW * kC); A(&s->embed, MB * HW * kC); A(&s->feat_s0, MB * 16 * HW * 32); A(&s->feat_s1, MB * 4 * HW * 64);
+  A(&s->s0_sub, MB * 16 * HW * 32); A(&s->s1_sub, MB * 4 * HW * 64); A(&s->src, MB * HW * kC); A(&s->src_bf, MB * HW * kC); A(&s->srcpe_bf, MB * HW * kC);
+  A(&s->k0, MB * HW * kInt); A(&s->v0, MB * HW * kInt); A(&s->qi0, MB * HW * kInt);
   const size_t P = max_prompts, R = P * kTok;
   A(&s->tokens, R * kC); A(&s->queries, R * kC); A(&s->tq_tmp, R * kC); A(&s->tq_bf, R * kC); A(&s->tqpe_bf, R * kC);
   A(&s->t_q, R * kC); A(&s->t_k, R * kC); A(&s->t_v, R * kC); A(&s->t_o, R * kC); A(&s->t_mlp, R * 2048);
@@ -1010,16 +1024,13 @@ int ovo_sam_set_pixels(ovo_sam_t* s, const float* pixels_dev, float* embed_out, 
   OVO_REQUIRE(s && pixels_dev, "ovo_sam_set_pixels: null argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
   OVO_CUDA(cudaMemcpyAsync(s->pixels, pixels_dev, sizeof(float) * 3 * s->S * s->S, cudaMemcpyDeviceToDevice, st));
-  OVO_TRY(trunk_from_pixels(s, n_blocks, block_out, st));
+  OVO_TRY(trunk_from_pixels(s, 1, n_blocks, block_out, st));
   if (n_blocks < 0 || n_blocks >= s->cfg.n_blocks) OVO_TRY(copy_taps(s, embed_out, s0_out, s1_out, st));
   return OVO_OK;
 }
 
-int ovo_sam_set_image(ovo_sam_t* s, const uint8_t* rgb_dev, int H, int W, float* pixels_out, float* embed_out, float* s0_out,
-                      float* s1_out, int n_blocks, float* block_out, void* stream_) {
-  OVO_REQUIRE(s && rgb_dev, "ovo_sam_set_image: null argument");
-  OVO_REQUIRE(H > 0 && W > 0 && H <= s->max_h && W <= s->max_w, "ovo_sam_set_image: frame %dx%d exceeds the %dx%d the handle was created for", H, W, s->max_h, s->max_w);
-  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+// SAM2Transforms.__call__ for one frame -> s->pixels[slot]
+static int resize_to_pixels(ovo_sam_t* s, const uint8_t* rgb_dev, int H, int W, int slot, cudaStream_t st) {
   const int S = s->S;
   if (s->tab_h != H || s->tab_w != W) {   // resize tables for this frame size (host, once per size)
     OVO_CUDA(cudaStreamSynchronize(st));
@@ -1039,16 +1050,39 @@ int ovo_sam_set_image(ovo_sam_t* s, const uint8_t* rgb_dev, int H, int W, float*
     OVO_CUDA(cudaMemcpy(s->yw, ws.data(), sizeof(float) * ws.size(), cudaMemcpyHostToDevice));
     s->tab_h = H; s->tab_w = W;
   }
-  {
-    ProfScope prof(st, PROF_PRE, 0.0, static_cast<double>(H) * W * 3 + 3.0 * S * S * 4);
-    sam_resize_h_kernel<<<dim3(ceil_div(S, 128), H), 128, 0, st>>>(rgb_dev, H, W, s->xmin, s->xsize, s->xw, s->kx, S, s->tmp);
-    OVO_CHECK_LAUNCH();
-    sam_resize_v_kernel<<<dim3(ceil_div(S, 128), S, 3), 128, 0, st>>>(s->tmp, H, s->ymin, s->ysize, s->yw, s->ky, S, s->pixels);
-    OVO_CHECK_LAUNCH();
-  }
+  ProfScope prof(st, PROF_PRE, 0.0, static_cast<double>(H) * W * 3 + 3.0 * S * S * 4);
+  sam_resize_h_kernel<<<dim3(ceil_div(S, 128), H), 128, 0, st>>>(rgb_dev, H, W, s->xmin, s->xsize, s->xw, s->kx, S, s->tmp);
+  OVO_CHECK_LAUNCH();
+  sam_resize_v_kernel<<<dim3(ceil_div(S, 128), S, 3), 128, 0, st>>>(s->tmp, H, s->ymin, s->ysize, s->yw, s->ky, S, s->pixels + static_cast<size_t>(slot) * 3 * S * S);
+  OVO_CHECK_LAUNCH();
+  return OVO_OK;
+}
+
+int ovo_sam_set_image(ovo_sam_t* s, const uint8_t* rgb_dev, int H, int W, float* pixels_out, float* embed_out, float* s0_out,
+                      float* s1_out, int n_blocks, float* block_out, void* stream_) {
+  OVO_REQUIRE(s && rgb_dev, "ovo_sam_set_image: null argument");
+  OVO_REQUIRE(H > 0 && W > 0 && H <= s->max_h && W <= s->max_w, "ovo_sam_set_image: frame %dx%d exceeds the %dx%d the handle was created for", H, W, s->max_h, s->max_w);
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  const int S = s->S;
+  OVO_TRY(resize_to_pixels(s, rgb_dev, H, W, 0, st));
   if (pixels_out) OVO_CUDA(cudaMemcpyAsync(pixels_out, s->pixels, sizeof(float) * 3 * S * S, cudaMemcpyDeviceToDevice, st));
-  OVO_TRY(trunk_from_pixels(s, n_blocks, block_out, st));
+  OVO_TRY(trunk_from_pixels(s, 1, n_blocks, block_out, st));
   if (n_blocks < 0 || n_blocks >= s->cfg.n_blocks) OVO_TRY(copy_taps(s, embed_out, s0_out, s1_out, st));
+  return OVO_OK;
+}
+
+int ovo_sam_set_images(ovo_sam_t* s, const uint8_t* rgb_dev, int n, int H, int W, void* stream_) {
+  OVO_REQUIRE(s && rgb_dev, "ovo_sam_set_images: null argument");
+  OVO_REQUIRE(n > 0 && n <= s->max_batch, "ovo_sam_set_images: %d frames, handle created for batches of %d", n, s->max_batch);
+  OVO_REQUIRE(H > 0 && W > 0 && H <= s->max_h && W <= s->max_w, "ovo_sam_set_images: frame %dx%d exceeds the %dx%d the handle was created for", H, W, s->max_h, s->max_w);
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  for (int b = 0; b < n; ++b) OVO_TRY(resize_to_pixels(s, rgb_dev + static_cast<size_t>(b) * H * W * 3, H, W, b, st));
+  return trunk_from_pixels(s, n, -1, nullptr, st);
+}
+
+int ovo_sam_select_image(ovo_sam_t* s, int index) {
+  OVO_REQUIRE(s && index >= 0 && index < s->n_set, "ovo_sam_select_image: index %d outside the %d images set", index, s ? s->n_set : 0);
+  s->cur = index;
   return OVO_OK;
 }
 
@@ -1059,13 +1093,22 @@ int ovo_sam_predict(ovo_sam_t* s, const float* points_dev, int P, float* low_out
   OVO_REQUIRE(P > 0 && P <= s->max_p, "ovo_sam_predict: %d prompts, handle sized for %d", P, s->max_p);
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
   if (points_dev == s->points && low_out == s->low_all && iou_out == s->iou_all)   // the handle's own buffers: static launch sequence
-    return graphed(s, (2ll << 32) | P, st, [&](cudaStream_t cs) { return sam_predict_impl(s, points_dev, P, low_out, iou_out, cs); });
+    return graphed(s, (2ll << 32) | (static_cast<long long>(s->cur) << 16) | P, st, [&](cudaStream_t cs) { return sam_predict_impl(s, points_dev, P, low_out, iou_out, cs); });
   return sam_predict_impl(s, points_dev, P, low_out, iou_out, st);
 }
 
 static int sam_predict_impl(ovo_sam_t* s, const float* points_dev, int P, float* low_out, float* iou_out, cudaStream_t st) {
   const int g = s->g, HW = g * g, R = P * kTok;
   const size_t PHW = static_cast<size_t>(P) * HW;
+  OVO_REQUIRE(s->n_set > 0 && s->cur < s->n_set, "ovo_sam_predict: no image set");
+  // per-image features of the selected image (ovo_sam_select_image)
+  const size_t slot = static_cast<size_t>(s->cur);
+  const float* f_src = s->src + slot * HW * kC;
+  const __nv_bfloat16* f_k0 = s->k0 + slot * HW * kInt;
+  const __nv_bfloat16* f_v0 = s->v0 + slot * HW * kInt;
+  const __nv_bfloat16* f_qi0 = s->qi0 + slot * HW * kInt;
+  const float* f_s1_sub = s->s1_sub + slot * 4 * HW * 64;
+  const float* f_s0_sub = s->s0_sub + slot * 16 * HW * 32;
   OVO_REQUIRE(PHW * 4 < (1ull << 31), "ovo_sam_predict: too many prompts for 32-bit GEMM row indices");
   sam_tokens_kernel<<<P, 256, 0, st>>>(points_dev, P, static_cast<float>(s->S), s->w.gauss, s->w.point_embed, s->w.not_a_point, s->w.out_tokens, s->tokens);
   OVO_CHECK_LAUNCH();
@@ -1090,7 +1133,7 @@ static int sam_predict_impl(ovo_sam_t* s, const float* points_dev, int P, float*
     OVO_TRY(ln(s->tq_tmp, R, kC, L.norm_w[0], L.norm_b[0], 1e-5f, s->queries, s->tq_bf, nullptr, nullptr, 1, st));
     // (2) token -> image cross attention (:192-197)
     if (l == 0) {
-      OVO_TRY(t2i_block(s, L.t2i, s->k0, s->v0, 0, P, L.norm_w[1], L.norm_b[1], st));
+      OVO_TRY(t2i_block(s, L.t2i, f_k0, f_v0, 0, P, L.norm_w[1], L.norm_b[1], st));
     } else {
       OVO_TRY(gemm(EPI_BF16, s->keyspe_bf, kC, L.t2i.k_w, kC, static_cast<int>(PHW), kInt, kC, L.t2i.k_b, s->big_k, kInt, nullptr, 0, 0, st));
       OVO_TRY(gemm(EPI_BF16, s->keys_bf, kC, L.t2i.v_w, kC, static_cast<int>(PHW), kInt, kC, L.t2i.v_b, s->big_v, kInt, nullptr, 0, 0, st));
@@ -1104,7 +1147,7 @@ static int sam_predict_impl(ovo_sam_t* s, const float* points_dev, int P, float*
     OVO_TRY(add_cast(s->queries, s->tokens, R, kC, static_cast<size_t>(R) * kC, s->tqpe_bf, nullptr, st));
     OVO_TRY(tok_lin(s, s->tqpe_bf, L.i2t.k_w, L.i2t.k_b, R, kInt, kC, s->t_k, st));
     OVO_TRY(tok_lin(s, s->tq_bf, L.i2t.v_w, L.i2t.v_b, R, kInt, kC, s->t_v, st));
-    const __nv_bfloat16* qsrc = s->qi0;
+    const __nv_bfloat16* qsrc = f_qi0;
     size_t qstride = 0;
     if (l > 0) {
       OVO_TRY(gemm(EPI_BF16, s->keyspe_bf, kC, L.i2t.q_w, kC, static_cast<int>(PHW), kInt, kC, L.i2t.q_b, s->big_q, kInt, nullptr, 0, 0, st));
@@ -1116,7 +1159,7 @@ static int sam_predict_impl(ovo_sam_t* s, const float* points_dev, int P, float*
       OVO_CHECK_LAUNCH();
     }
     OVO_TRY(gemm(EPI_F32_RESID, s->big_k, kInt, L.i2t.o_w, kInt, static_cast<int>(PHW), kC, kInt, L.i2t.o_b, s->keys_pre, kC,
-                 l == 0 ? s->src : s->keys, kC, l == 0 ? HW : 0, st));
+                 l == 0 ? f_src : s->keys, kC, l == 0 ? HW : 0, st));
     OVO_TRY(ln(s->keys_pre, static_cast<int>(PHW), kC, L.norm_w[3], L.norm_b[3], 1e-5f, s->keys, s->keys_bf, s->keyspe_bf, s->w.dense_pe, HW, st));
   }
   // final token -> image attention + norm (sam/transformer.py:124-132)
@@ -1145,13 +1188,13 @@ static int sam_predict_impl(ovo_sam_t* s, const float* points_dev, int P, float*
   // [P,64,2g,2g] nor the [P,32,4g,4g] up-scaled embedding is ever written to memory.
   {
     EpiParams ep;
-    ep.out = s->up1; ep.ldo = 256; ep.bias = s->w.up0_b; ep.resid = s->s1_sub; ep.ldr = 256; ep.resid_mod = HW;
+    ep.out = s->up1; ep.ldo = 256; ep.bias = s->w.up0_b; ep.resid = f_s1_sub; ep.ldr = 256; ep.resid_mod = HW;
     ep.ln_w = s->w.up_ln_w; ep.ln_b = s->w.up_ln_b;
     OVO_TRY(launch_gemm(EPI_UP_LN, s->keys_bf, kC, static_cast<const __nv_bfloat16*>(s->w.up0_w), kC, static_cast<int>(PHW), 256, kC, ep, st));
   }
   {
     EpiParams ep;
-    ep.bias = s->w.up1_b; ep.resid = s->s0_sub; ep.ldr = 128; ep.resid_mod = 4 * HW;
+    ep.bias = s->w.up1_b; ep.resid = f_s0_sub; ep.ldr = 128; ep.resid_mod = 4 * HW;
     ep.dot_w = s->hyper; ep.dot_out = low; ep.dot_g = g;
     OVO_TRY(launch_gemm(EPI_GELU_DOT, s->up1, 64, static_cast<const __nv_bfloat16*>(s->w.up1_w), 64, static_cast<int>(PHW * 4), 128, 64, ep, st));
   }
@@ -1199,14 +1242,13 @@ int ovo_sam_postprocess(ovo_sam_t* s, const float* low_dev, const float* iou_dev
   return OVO_OK;
 }
 
-int ovo_sam_generate(ovo_sam_t* s, const uint8_t* rgb_dev, int H, int W, const ovo_amg_params* prm, int32_t* seg_map_dev,
-                     uint8_t* masks_out_dev, int max_masks, int* n_masks, void* stream_) {
-  OVO_REQUIRE(s && rgb_dev && prm && seg_map_dev && masks_out_dev && n_masks, "ovo_sam_generate: null argument");
+// grid prompts + decoder + AMG filters + OVO's second stage for the image selected in the handle
+static int generate_selected(ovo_sam_t* s, int H, int W, const ovo_amg_params* prm, int32_t* seg_map_dev, uint8_t* masks_out_dev,
+                             int max_masks, int* n_masks, void* stream_) {
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
   const int n = prm->points_per_side, P = n * n;
   OVO_REQUIRE(n > 0 && P <= s->max_p && P * 3 <= 1024, "ovo_sam_generate: points_per_side %d unsupported (handle sized for %d prompts)", n, s->max_p);
   OVO_REQUIRE((static_cast<size_t>(H) * W) % 16 == 0, "ovo_sam_generate: H*W must be a multiple of 16");
-  OVO_TRY(ovo_sam_set_image(s, rgb_dev, H, W, nullptr, nullptr, nullptr, nullptr, -1, nullptr, stream_));
   amg_points_kernel<<<ceil_div(P, 128), 128, 0, st>>>(n, H, W, static_cast<float>(s->S), s->points);
   OVO_CHECK_LAUNCH();
   // every filter of the AMG is per mask, so all prompts go through the decoder in one batch (the reference's batches of 64
@@ -1252,6 +1294,26 @@ int ovo_sam_generate(ovo_sam_t* s, const uint8_t* rgb_dev, int H, int W, const o
   OVO_TRY(ovo_mask2segmap(s->masks_tmp2, s->score_tmp, M, H, W, seg_map_dev, masks_out_dev, s->src_tmp, stream_));
   OVO_CUDA(cudaStreamSynchronize(st));   // idx / stab_kept are host temporaries of this call
   *n_masks = M;
+  return OVO_OK;
+}
+
+int ovo_sam_generate(ovo_sam_t* s, const uint8_t* rgb_dev, int H, int W, const ovo_amg_params* prm, int32_t* seg_map_dev,
+                     uint8_t* masks_out_dev, int max_masks, int* n_masks, void* stream_) {
+  OVO_REQUIRE(s && rgb_dev && prm && seg_map_dev && masks_out_dev && n_masks, "ovo_sam_generate: null argument");
+  OVO_TRY(ovo_sam_set_image(s, rgb_dev, H, W, nullptr, nullptr, nullptr, nullptr, -1, nullptr, stream_));
+  return generate_selected(s, H, W, prm, seg_map_dev, masks_out_dev, max_masks, n_masks, stream_);
+}
+
+int ovo_sam_generate_batch(ovo_sam_t* s, const uint8_t* rgb_dev, int n_frames, int H, int W, const ovo_amg_params* prm,
+                           int32_t* seg_maps_dev, uint8_t* masks_out_dev, int max_masks, int* n_masks_host, void* stream_) {
+  OVO_REQUIRE(s && rgb_dev && prm && seg_maps_dev && masks_out_dev && n_masks_host, "ovo_sam_generate_batch: null argument");
+  OVO_TRY(ovo_sam_set_images(s, rgb_dev, n_frames, H, W, stream_));     // ONE trunk pass over all frames
+  const size_t npix = static_cast<size_t>(H) * W;
+  for (int b = 0; b < n_frames; ++b) {
+    OVO_TRY(ovo_sam_select_image(s, b));
+    OVO_TRY(generate_selected(s, H, W, prm, seg_maps_dev + b * npix, masks_out_dev + static_cast<size_t>(b) * max_masks * npix, max_masks,
+                              n_masks_host + b, stream_));
+  }
   return OVO_OK;
 }
 

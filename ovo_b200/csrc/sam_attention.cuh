@@ -28,6 +28,7 @@ struct WinAttnParams {
   int heads, dim_out;
   int q_pool;                 // 1: queries are 2x2 max-pooled
   float scale_log2e;          // head_dim^-0.5 * log2(e)
+  int wins2;                  // windows per image: blockIdx.y = image * wins2 + window (several images per launch)
 };
 
 __device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const void* p) {
@@ -79,14 +80,15 @@ __global__ void __launch_bounds__(QB * 2) hiera_attention_kernel(WinAttnParams p
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int head = blockIdx.z;
   const int wins = p.grid / p.ws;
-  const int wy = blockIdx.y / wins, wx = blockIdx.y - wy * wins;
+  const int img = blockIdx.y / p.wins2, win = blockIdx.y - img * p.wins2;
+  const int wy = win / wins, wx = win - wy * wins;
   const int nk = p.ws * p.ws;
   const int wsq = p.q_pool ? p.ws >> 1 : p.ws;        // window side on the query / output grid
   const int nq = wsq * wsq;
   const int grid_out = p.q_pool ? p.grid >> 1 : p.grid;
   const int q0 = blockIdx.x * QB;
   const int ld = 3 * p.dim_out;
-  const __nv_bfloat16* qbase = p.qkv + head * kSamHd;
+  const __nv_bfloat16* qbase = p.qkv + static_cast<size_t>(img) * p.grid * p.grid * ld + head * kSamHd;
   const __nv_bfloat16* kbase = qbase + p.dim_out;
   const __nv_bfloat16* vbase = kbase + p.dim_out;
   const int nblocks = (nk + kSamKB - 1) / kSamKB;
@@ -232,7 +234,7 @@ __global__ void __launch_bounds__(QB * 2) hiera_attention_kernel(WinAttnParams p
     if (qi >= nq) continue;
     const int qy = qi / wsq, qx = qi - qy * wsq;
     const size_t row = static_cast<size_t>(wy * wsq + qy) * grid_out + wx * wsq + qx;
-    __nv_bfloat16* dst = p.out + row * p.dim_out + head * kSamHd + 2 * t4;
+    __nv_bfloat16* dst = p.out + (static_cast<size_t>(img) * grid_out * grid_out + row) * p.dim_out + head * kSamHd + 2 * t4;
     const float inv = h ? i1 : i0;
 #pragma unroll
     for (int nt = 0; nt < 9; ++nt)

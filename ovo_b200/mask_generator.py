@@ -54,7 +54,7 @@ class MaskGenerator:
                 raise FileNotFoundError(f"ovo_b200: SAM-2 checkpoint {ckpt} not found (pass sam_state_dict, or sam_random_init for benchmarks)")
         n = int(config.get("points_per_side", 32))
         self.mask_generator = Sam2(cfg, sd, max_h=int(config.get("max_h", 968)), max_w=int(config.get("max_w", 1296)),
-                                   max_prompts=n * n, device=self.device)
+                                   max_prompts=n * n, device=self.device, max_batch=max(1, int(config.get("batch_frames", 4))))
         self.amg_params = Sam2.amg_params(points_per_side=n, pred_iou_thresh=config.get("nms_iou_th", 0.8),
                                           stability_score_thresh=config.get("stability_score_th", 0.95),
                                           box_nms_thresh=config.get("box_nms_thresh", 0.7),
@@ -122,15 +122,48 @@ class MaskGenerator:
         return seg_map, maps
 
     def precompute(self, dataset, segment_every: int) -> None:
-        """With every mask already on disk this is the reference's no-op path (mask_generator.py:141-152)."""
+        """mask_generator.py:122-152: segment every `segment_every`-th frame that has no masks on disk yet and save them as
+        `{frame_id:04d}_seg_map_default.npy` / `_bmap_default.npy`.  Frames are sent through SAM-2 `sam.batch_frames` at a
+        time (default 4): one trunk pass per batch (the results equal frame-by-frame calls, tests/test_gpu_sam.py)."""
+        print("Precomputing segmentation masks.")
+        os.makedirs(self.masks_path, exist_ok=True)
+        todo = []
         for frame_id in range(len(dataset)):
             if frame_id % segment_every:
                 continue
             a = os.path.join(self.masks_path, f"{frame_id:04d}_seg_map_default.npy")
             b = os.path.join(self.masks_path, f"{frame_id:04d}_bmap_default.npy")
-            if not (os.path.exists(a) and os.path.exists(b)):
-                self.segment(dataset[frame_id][1])
+            if os.path.exists(a) and os.path.exists(b):
+                print(f"Frame {frame_id} already compute. Skipping ...")
+            else:
+                todo.append(frame_id)
+        if todo and self.mask_generator is None and getattr(self, "proposal_fn", None) is None:
+            self.load_mask_generator(self.config)
+        B = max(1, min(int(self.config.get("batch_frames", 4)), getattr(self.mask_generator, "max_batch", 1)))
+        i = 0
+        while i < len(todo):
+            chunk = todo[i: i + B]
+            images = [np.ascontiguousarray(dataset[f][1]) for f in chunk]
+            same = all(im.shape == images[0].shape and im.dtype == np.uint8 for im in images)
+            if len(chunk) > 1 and same and getattr(self, "proposal_fn", None) is None:
+                outs = self.mask_generator.generate_batch(torch.from_numpy(np.stack(images)), self.amg_params,
+                                                          max_masks=int(self.config.get("max_masks", 256)))
+                for f, (seg, maps) in zip(chunk, outs):
+                    if maps.shape[0] == 0:
+                        self._save_masks(np.array([]), np.array([]), f)
+                    else:
+                        self._save_masks(seg.cpu().numpy(), maps.cpu().numpy(), f)
+            else:
+                for f, im in zip(chunk, images):
+                    seg, maps = self.segment(im)
+                    self._save_masks(seg, maps, f)
+            i += len(chunk)
         self.precomputed = True
+
+    def _save_masks(self, seg_map: np.ndarray, binary_maps: np.ndarray, frame_id: int) -> None:
+        """mask_generator.py:154-168."""
+        np.save(os.path.join(self.masks_path, f"{frame_id:04d}_seg_map_default"), seg_map)
+        np.save(os.path.join(self.masks_path, f"{frame_id:04d}_bmap_default"), binary_maps)
 
     def _load_masks(self, frame_id: int) -> Tuple[np.ndarray, np.ndarray]:
         map_path = os.path.join(self.masks_path, f"{frame_id:04d}_seg_map_default.npy")

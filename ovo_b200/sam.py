@@ -18,7 +18,8 @@ from .sam_config import SamConfig
 class Sam2:
     """Device-resident SAM-2 image encoder + prompt/mask decoder + automatic mask generator."""
 
-    def __init__(self, cfg: SamConfig, state_dict: dict, max_h: int = 480, max_w: int = 640, max_prompts: int = 256, device="cuda"):
+    def __init__(self, cfg: SamConfig, state_dict: dict, max_h: int = 480, max_w: int = 640, max_prompts: int = 256, device="cuda",
+                 max_batch: int = 1):
         if not torch.cuda.is_available():
             raise RuntimeError("ovo_b200.Sam2 needs a CUDA device (no CPU fallback)")
         self.cfg, self.device = cfg, torch.device(device)
@@ -30,7 +31,8 @@ class Sam2:
         c.image_size, c.n_blocks, c.embed_dim = cfg.image_size, len(cfg.blocks()), cfg.embed_dim
         for i, e in enumerate(cfg.stage_ends()):
             c.stage_end[i] = e
-        c.decoder_depth, c.trunk_ln_eps = cfg.decoder_depth, cfg.trunk_ln_eps
+        c.decoder_depth, c.trunk_ln_eps, c.max_batch = cfg.decoder_depth, cfg.trunk_ln_eps, int(max_batch)
+        self.max_batch = int(max_batch)
         h = C.c_void_p()
         with torch.cuda.device(self.device):
             check(self.lib.ovo_sam_create(C.byref(c), C.byref(w), max_h, max_w, max_prompts, C.byref(h)), "ovo_sam_create")
@@ -189,6 +191,17 @@ class Sam2:
               "ovo_sam_set_pixels")
         return (emb, s0, s1) if n_blocks < 0 else blk
 
+    def set_images(self, rgb_u8: torch.Tensor):
+        """set_image for a batch [n,H,W,3] (n <= max_batch) in ONE trunk pass; `select_image(i)` chooses the frame the
+        decoder (`predict`) works on."""
+        rgb = rgb_u8.to(self.device, torch.uint8).contiguous()
+        n, H, W, _ = rgb.shape
+        check(self.lib.ovo_sam_set_images(self.handle, ptr(rgb), n, H, W, stream_ptr()), "ovo_sam_set_images")
+        self._rgb = rgb
+
+    def select_image(self, index: int):
+        check(self.lib.ovo_sam_select_image(self.handle, int(index)), "ovo_sam_select_image")
+
     def predict(self, points: torch.Tensor):
         """SAM2ImagePredictor._predict (one foreground point per prompt, multimask_output=True, return_logits=True).
         points f32 [P,2] in model-frame pixels -> (low_res_masks [P,3,4g,4g] f32 — NOT clamped —, iou [P,3])."""
@@ -231,3 +244,16 @@ class Sam2:
         check(self.lib.ovo_sam_generate(self.handle, ptr(rgb), H, W, C.byref(prm), ptr(seg), ptr(maps), max_masks, C.byref(m),
                                         stream_ptr()), "ovo_sam_generate")
         return seg, maps[: m.value].bool()
+
+    def generate_batch(self, rgb_u8: torch.Tensor, prm: AmgParams = None, max_masks: int = 256):
+        """`generate` for n <= max_batch frames [n,H,W,3] with one batched trunk pass (MaskGenerator.precompute / replay).
+        -> list of (seg_map int32 [H,W], binary_maps bool [M,H,W])."""
+        prm = prm or self.amg_params()
+        rgb = rgb_u8.to(self.device, torch.uint8).contiguous()
+        n, H, W, _ = rgb.shape
+        seg = torch.full((n, H, W), -1, device=self.device, dtype=torch.int32)
+        maps = torch.empty(n, max_masks, H, W, device=self.device, dtype=torch.uint8)
+        m = (C.c_int * n)()
+        check(self.lib.ovo_sam_generate_batch(self.handle, ptr(rgb), n, H, W, C.byref(prm), ptr(seg), ptr(maps), max_masks, m,
+                                              stream_ptr()), "ovo_sam_generate_batch")
+        return [(seg[i], maps[i, : m[i]].bool()) for i in range(n)]

@@ -165,3 +165,26 @@ def test_online_sam_through_the_ovo_api(tmp_path):
     assert upd is not None and upd.shape == pins.shape
     ovo.compute_semantic_info()
     ovo.complete_semantic_info()
+
+
+def test_precompute_writes_the_reference_mask_files(tmp_path):
+    """MaskGenerator.precompute (mask_generator.py:122-168) with the on-device SAM-2, frames batched through the trunk:
+    the .npy files it writes are what `_load_masks` (the reference's precomputed seam) reads back, and equal segment()."""
+    from ovo_b200.mask_generator import MaskGenerator
+    from ovo_b200.sam_config import random_state_dict as sam_sd, tiny_sam_config
+    scfg = tiny_sam_config()
+    cfg = {"precomputed": False, "precompute": True, "masks_base_path": str(tmp_path), "sam_version": "2.1", "sam_config": scfg,
+           "sam_state_dict": sam_sd(scfg, seed=0), "points_per_side": 16, "nms_iou_th": 0.45, "stability_score_th": 0.4,
+           "box_nms_thresh": 0.9999, "nms_score_th": GG.SAM_OVO_SCORE_THR, "max_h": 240, "max_w": 320, "batch_frames": 2}
+    H, W = GG.SAM_AMG_HW
+    dataset = [(i, GG.sam_image(H, W, seed=30 + i)) for i in range(5)]
+    mg = MaskGenerator(cfg, scene_name="scene", device="cuda")
+    mg.precompute(dataset, segment_every=2)                     # frames 0, 2, 4: one batch of two + a single
+    assert mg.precomputed
+    for f in (0, 2, 4):
+        seg, maps = mg._load_masks(f)
+        seg_ref, maps_ref = mg.segment(dataset[f][1])
+        assert (seg == seg_ref).all() and (maps == maps_ref).all() and maps.shape[0] > 0
+    assert not os.path.exists(os.path.join(mg.masks_path, "0001_seg_map_default.npy"))
+    s2, m2 = mg.get_masks(None, 2)
+    assert s2.is_cuda and s2.dtype == torch.int32 and m2.shape[1:] == (H, W)

@@ -185,3 +185,30 @@ def test_hiera_l_full_size():
         low_ref, iou_ref = OS.predict(pts, emb_ref, s0_ref, s1_ref, sd, cfg)
     assert (iou.cpu() - iou_ref).abs().max().item() < 2e-2
     _check(low.reshape(16 * 3, -1), low_ref.reshape(16 * 3, -1), "low_res_masks (Hiera-L)", rel_tol=5e-2, cos_tol=2e-3)
+
+
+def test_batched_frames_equal_single_frames():
+    """One trunk pass over several frames (ovo_sam_set_images / ovo_sam_generate_batch) gives every frame exactly what a
+    single-frame call gives it: batching only folds the frames into the row dimension of the GEMMs / the window index."""
+    from ovo_b200.sam import Sam2
+    cfg = tiny_sam_config()
+    sd = random_state_dict(cfg, seed=0)
+    sam = Sam2(cfg, sd, max_h=240, max_w=320, max_prompts=256, max_batch=3)
+    H, W = GG.SAM_AMG_HW
+    imgs = torch.from_numpy(np.stack([GG.sam_image(H, W, seed=20 + i) for i in range(3)])).cuda()
+    prm = sam.amg_params(pred_iou_thresh=0.5, stability_score_thresh=0.5, box_nms_thresh=1.0, nms_score_th=GG.SAM_OVO_SCORE_THR)
+    pts = torch.from_numpy(OS.amg_points(16, H, W, cfg.image_size))[:32].cuda()
+    single = []
+    for i in range(3):
+        _, emb, s0, s1 = sam.set_image(imgs[i], taps=True)
+        low, iou = sam.predict(pts)
+        single.append((emb.clone(), low.clone(), iou.clone(), sam.generate(imgs[i], prm)))
+    sam.set_images(imgs)
+    for i in range(3):
+        sam.select_image(i)
+        low, iou = sam.predict(pts)
+        assert torch.equal(low, single[i][1]) and torch.equal(iou, single[i][2]), f"frame {i}"
+    out = sam.generate_batch(imgs, prm)
+    for i in range(3):
+        assert torch.equal(out[i][0], single[i][3][0]) and torch.equal(out[i][1], single[i][3][1]), f"frame {i}"
+    assert len({int(o[1].shape[0]) for o in out}) >= 1

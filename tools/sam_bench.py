@@ -33,9 +33,10 @@ def main():
     ap.add_argument("--tiny", action="store_true")
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--points", type=int, default=16)
+    ap.add_argument("--batch", type=int, default=4, help="frames per batched trunk pass")
     args = ap.parse_args()
     cfg = tiny_sam_config() if args.tiny else SamConfig()
-    sam = Sam2(cfg, random_state_dict(cfg, seed=0), max_h=480, max_w=640, max_prompts=args.points ** 2)
+    sam = Sam2(cfg, random_state_dict(cfg, seed=0), max_h=480, max_w=640, max_prompts=args.points ** 2, max_batch=args.batch)
     img = torch.from_numpy(GG.sam_image()).cuda()
     n = args.points
     from oracle import sam as OS
@@ -47,6 +48,16 @@ def main():
     out["generate_ms"] = timed(lambda: sam.generate(img, prm), args.iters)
     seg, maps = sam.generate(img, prm)
     out["masks"] = int(maps.shape[0])
+    if args.batch > 1:
+        imgs = img[None].repeat(args.batch, 1, 1, 1).contiguous()
+        out["set_images_ms_per_frame"] = timed(lambda: sam.set_images(imgs), args.iters) / args.batch
+        out["generate_batch_ms_per_frame"] = timed(lambda: sam.generate_batch(imgs, prm), args.iters) / args.batch
+        _lib.profile_begin()
+        sam.set_images(imgs)
+        rep = _lib.profile_report()
+        out["set_images_classes_per_frame"] = {k: {"ms": round(v["ms"] / args.batch, 4), "tflops": round(v["flops"] / max(v["ms"], 1e-9) / 1e9, 1), "launches": v["launches"]}
+                                               for k, v in rep.items() if v["launches"]}
+        sam.set_image(img)
     import time
     torch.cuda.synchronize(); t0 = time.time()
     for _ in range(5):
