@@ -266,7 +266,8 @@ def run_sam_stage(args, dev, clip_fusion_ms_per_keyframe, tf_sus, how):
     from ovo_b200.sam import Sam2
     from ovo_b200.sam_config import SamConfig, random_state_dict
     cfg = SamConfig()
-    sam = Sam2(cfg, random_state_dict(cfg, seed=0), max_h=H, max_w=W, max_prompts=256, device=dev)
+    SB = 4          # frames per batched trunk pass (replay / precompute mode)
+    sam = Sam2(cfg, random_state_dict(cfg, seed=0), max_h=H, max_w=W, max_prompts=256, device=dev, max_batch=SB)
     rng = np.random.default_rng(5)
     coarse = rng.integers(0, 256, (H // 40, W // 40, 3))
     img = torch.from_numpy(np.clip(np.kron(coarse, np.ones((40, 40, 1))) + rng.normal(0, 12, (H, W, 3)), 0, 255).astype(np.uint8)).to(dev)
@@ -291,6 +292,8 @@ def run_sam_stage(args, dev, clip_fusion_ms_per_keyframe, tf_sus, how):
     ms_dec = t(lambda: sam.predict(pts))
     ms_gen = t(lambda: sam.generate(img, prm))
     seg, maps = sam.generate(img, prm)
+    imgs = img[None].repeat(SB, 1, 1, 1).contiguous()
+    ms_batch = t(lambda: sam.generate_batch(imgs, prm)) / SB
     _lib.profile_begin()
     sam.generate(img, prm)
     torch.cuda.synchronize()
@@ -307,6 +310,8 @@ def run_sam_stage(args, dev, clip_fusion_ms_per_keyframe, tf_sus, how):
             "roofline": {"bound": "tensor", "achieved": round(gf / ms_gen, 1), "peak": tf_sus, "unit": "TFLOP/s",
                          "frac": round(gf / ms_gen / tf_sus, 4), "peak_source": f"{how} bf16_tflops_sustained",
                          "note": "whole stage (GEMMs + windowed attention + HBM-bound decoder tensors) against the tensor peak"},
+            "batched": {"frames_per_trunk_pass": SB, "ms_per_frame": round(ms_batch, 3), "frames_per_s": round(1e3 / ms_batch, 2),
+                        "note": "replay / MaskGenerator.precompute mode: one Hiera trunk pass over several frames, decoder per frame"},
             "keyframes_per_s_with_online_sam": round(1e3 / (clip_fusion_ms_per_keyframe + ms_gen), 2)}
 
 
