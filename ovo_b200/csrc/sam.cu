@@ -76,6 +76,62 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// Trunk LayerNorm (hieradet.py norm1/norm2, eps 1e-6) -> bf16 GEMM operand.  Rows are short (144..1152 floats), so one warp
+// takes R rows per iteration and issues all of their loads before the first reduction (NV float4 per lane per row).
+template <int NV, int R>
+__global__ void __launch_bounds__(256)
+    sam_ln_rows_kernel(const float* __restrict__ x, int rows, int width, const float* __restrict__ g, const float* __restrict__ b,
+                       float eps, __nv_bfloat16* __restrict__ out16) {
+  griddep_launch();
+  const int lane = threadIdx.x & 31;
+  const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int nwarps = gridDim.x * (blockDim.x >> 5);
+  const int nvec = width >> 2;
+  const float inv_w = 1.f / static_cast<float>(width);
+  for (int r0 = warp * R; r0 < rows; r0 += nwarps * R) {
+    float4 v[R][NV];
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(min(r0 + j, rows - 1)) * width);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int idx = lane + 32 * i;
+        v[j][i] = idx < nvec ? xr[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      float sum = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) sum += (v[j][i].x + v[j][i].y) + (v[j][i].z + v[j][i].w);
+      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      const float mean = sum * inv_w;
+      float var = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        if (lane + 32 * i < nvec) {
+          const float a = v[j][i].x - mean, bb = v[j][i].y - mean, c = v[j][i].z - mean, d = v[j][i].w - mean;
+          var += a * a + bb * bb + c * c + d * d;
+        }
+      }
+      for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+      const float rstd = rsqrtf(var * inv_w + eps);
+      const int r = r0 + j;
+      if (r >= rows) continue;
+      uint2* orow = reinterpret_cast<uint2*>(out16 + static_cast<size_t>(r) * width);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int idx = lane + 32 * i;
+        if (idx < nvec) {
+          const float4 gg = __ldg(reinterpret_cast<const float4*>(g) + idx), bb = __ldg(reinterpret_cast<const float4*>(b) + idx);
+          orow[idx] = make_uint2(pack_bf16((v[j][i].x - mean) * rstd * gg.x + bb.x, (v[j][i].y - mean) * rstd * gg.y + bb.y),
+                                 pack_bf16((v[j][i].z - mean) * rstd * gg.z + bb.z, (v[j][i].w - mean) * rstd * gg.w + bb.w));
+        }
+      }
+    }
+  }
+}
+
 // The decoder's image-side LayerNorm (norm4, sam/transformer.py:209-210) over [prompts*4096, 256] is pure HBM streaming
 // (3 GB per call at 256 prompts): one warp normalises 4 rows per iteration and issues all of their loads (8 float4 per
 // lane + the positional table) before the first reduction, so enough bytes are in flight to cover the DRAM latency.
@@ -752,6 +808,20 @@ int ln(const float* x, int rows, int width, const float* g, const float* b, floa
     OVO_CHECK_LAUNCH();
     return OVO_OK;
   }
+  if (o16 != nullptr && o32 == nullptr && o16b == nullptr && rows >= 1024) {   // the trunk's LayerNorms
+    const int nv = ceil_div(width, 128);
+    const int blocks = std::min(num_sms() * 8, ceil_div(rows, 8));
+    bool done = true;
+    if (nv <= 2) sam_ln_rows_kernel<2, 4><<<std::min(blocks, ceil_div(rows, 32)), 256, 0, st>>>(x, rows, width, g, b, eps, o16);
+    else if (nv <= 3) sam_ln_rows_kernel<3, 2><<<std::min(blocks, ceil_div(rows, 16)), 256, 0, st>>>(x, rows, width, g, b, eps, o16);
+    else if (nv <= 5) sam_ln_rows_kernel<5, 2><<<std::min(blocks, ceil_div(rows, 16)), 256, 0, st>>>(x, rows, width, g, b, eps, o16);
+    else if (nv <= 9) sam_ln_rows_kernel<9, 1><<<blocks, 256, 0, st>>>(x, rows, width, g, b, eps, o16);
+    else done = false;
+    if (done) {
+      OVO_CHECK_LAUNCH();
+      return OVO_OK;
+    }
+  }
   sam_ln_kernel<<<ceil_div(rows, 8), 256, 0, st>>>(x, rows, width, g, b, eps, o32, o16, o16b, add, add_mod);
   OVO_CHECK_LAUNCH();
   return OVO_OK;
@@ -763,6 +833,8 @@ int add_cast(const float* a, const float* b, int b_mod, int width, size_t n, __n
   OVO_CHECK_LAUNCH();
   return OVO_OK;
 }
+
+int g_hiera_qb128_min = 128;   // queries per window from which the 128-query CTA is used (OVO_B200_HIERA_QB128_MIN: tuning)
 
 template <typename F>
 int graphed(ovo_sam* s, long long key, cudaStream_t st, F&& fn) {
@@ -835,7 +907,7 @@ int run_trunk(ovo_sam* s, int B, int n_blocks, float* block_out, cudaStream_t st
       const int wins = (grid / ws) * (grid / ws);
       p.wins2 = wins;
       ProfScope prof(st, PROF_ATTN, 4.0 * B * wins * b.heads * static_cast<double>(nq) * ws * ws * kSamHd, 0.0);
-      if (nq >= 128) {
+      if (nq >= g_hiera_qb128_min) {
         hiera_attention_kernel<128><<<dim3(ceil_div(nq, 128), B * wins, b.heads), 256, hiera_attn_smem_bytes<128>(), st>>>(p);
       } else {
         hiera_attention_kernel<64><<<dim3(ceil_div(nq, 64), B * wins, b.heads), 128, hiera_attn_smem_bytes<64>(), st>>>(p);
@@ -950,6 +1022,8 @@ int ovo_sam_create(const ovo_sam_cfg* cfg, const ovo_sam_weights* w, int max_h, 
   {
     const char* env = getenv("OVO_B200_GRAPHS");
     s->use_graphs = !(env && env[0] == '0');
+    const char* q = getenv("OVO_B200_HIERA_QB128_MIN");
+    if (q) g_hiera_qb128_min = atoi(q);
   }
   const int S = s->S, g = s->g, g0 = S / 4;
   // geometry walk: buffer sizes and the stage outputs
