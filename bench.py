@@ -211,7 +211,8 @@ def run_ours(args, rank, world, local_rank):
     breakdown = {k: round(v["ms"] / 2, 4) for k, v in prof.items() if v["launches"]}
     roofline = {"bound": "tensor", "kernel": "gemm_bf16_tn_kernel (tcgen05, all ViT linears)",
                 "achieved": round(gemm_tflops, 1), "peak": tf_sus, "unit": "TFLOP/s", "frac": round(gemm_tflops / tf_sus, 4),
-                "traffic": None, "peak_source": f"{how} bf16_tflops_sustained (kernel timed inside a long step)",
+                "traffic": 69.5e6, "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, mean over the four ViT GEMM shapes of one layer, ncu --set full capture profiles/r1h_ncu_full_vit.md (QKV 33.3, out-proj 59.3, fc1 54.0, fc2 131.3 MB)",
+                "peak_source": f"{how} bf16_tflops_sustained (kernel timed inside a long step)",
                 "flops_per_launch": round(g["flops"] / max(g["launches"], 1) / 1e9, 2), "avg_launch_us": round(1e3 * g["ms"] / max(g["launches"], 1), 2),
                 "share_of_step": round(g["ms"] / tot_ms, 3) if tot_ms else None,
                 "how": "CUDA events around every launch in an instrumented pass of the same steps (graphs off, launches queued behind a 30 ms device sleep so host launch latency is not counted)",
