@@ -416,68 +416,6 @@ __global__ void __launch_bounds__(256) sam_i2t_attn_kernel(const __nv_bfloat16* 
   op[0] = w[0]; op[1] = w[1];
 }
 
-// ---- output upscaling (mask_decoder.py:214-217): rows of dc1 [P*g*g, 4*64] (transposed conv + bias + feat_s1 already added
-// by the GEMM epilogue) -> LayerNorm2d over the 64 channels of each sub-pixel (eps 1e-6) -> GELU -> up1 bf16
-// [P, (2g)^2 pixels in (y,x,sub) order, 64].  One warp per (row, sub-pixel).
-__global__ void __launch_bounds__(256) sam_up1_kernel(const float* __restrict__ dc1, size_t n_items, const float* __restrict__ lw,
-                                                      const float* __restrict__ lb, __nv_bfloat16* __restrict__ up1) {
-  const int lane = threadIdx.x & 31, sub = lane & 15, hw = lane >> 4;   // 16 lanes x float4 = one item of 64 channels
-  const size_t warp = static_cast<size_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
-  const size_t nwarps = static_cast<size_t>(gridDim.x) * 8;
-  const float4 w = __ldg(reinterpret_cast<const float4*>(lw) + sub), c = __ldg(reinterpret_cast<const float4*>(lb) + sub);
-  for (size_t i0 = warp * 16; i0 < n_items; i0 += nwarps * 16) {   // 16 items per warp iteration: 8 x 16-byte loads in flight per lane
-    float4 v[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = *reinterpret_cast<const float4*>(dc1 + min(i0 + 2 * j + hw, n_items - 1) * 64 + 4 * sub);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float s = (v[j].x + v[j].y) + (v[j].z + v[j].w);
-      for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      const float u = s / 64.f;
-      const float a0 = v[j].x - u, a1 = v[j].y - u, a2 = v[j].z - u, a3 = v[j].w - u;
-      float q = (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
-      for (int o = 8; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-      const float r = 1.f / sqrtf(q / 64.f + 1e-6f);
-      const size_t item = i0 + 2 * j + hw;
-      if (item < n_items)
-        *reinterpret_cast<uint2*>(up1 + item * 64 + 4 * sub) =
-            make_uint2(pack_bf16(gelu_erf(w.x * (a0 * r) + c.x), gelu_erf(w.y * (a1 * r) + c.y)),
-                       pack_bf16(gelu_erf(w.z * (a2 * r) + c.z), gelu_erf(w.w * (a3 * r) + c.w)));
-    }
-  }
-}
-
-// masks = hyper_in @ upscaled (mask_decoder.py:225-226) for mask tokens 1..3 (multimask_output, :141-143):
-// up2 bf16 [P, g*g, sub1, sub2, 32] (nested sub-pixel order, see sam_subpixel2_kernel) -> low_res f32 [P,3,4g,4g].
-// One thread per (prompt, output pixel).
-__global__ void __launch_bounds__(256) sam_mask_dot_kernel(const __nv_bfloat16* __restrict__ up2, const float* __restrict__ hyper /*[P,4,32]*/,
-                                                           int g, float* __restrict__ low) {
-  __shared__ float sh[3][32];
-  const int p = blockIdx.y;
-  if (threadIdx.x < 96) sh[0][threadIdx.x] = hyper[static_cast<size_t>(p) * 128 + 32 + threadIdx.x];
-  __syncthreads();
-  const int S = 4 * g;
-  const int i = blockIdx.x * 256 + threadIdx.x;
-  if (i >= S * S) return;
-  const int y = i / S, x = i - y * S;
-  const int sub2 = (y & 1) * 2 + (x & 1), sub1 = ((y >> 1) & 1) * 2 + ((x >> 1) & 1);
-  const size_t src = (((static_cast<size_t>(p) * g * g + static_cast<size_t>(y >> 2) * g + (x >> 2)) * 4 + sub1) * 4 + sub2) * 32;
-  const uint4* up = reinterpret_cast<const uint4*>(up2 + src);
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f;
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const uint4 raw = up[j];
-    const __nv_bfloat16* e = reinterpret_cast<const __nv_bfloat16*>(&raw);
-#pragma unroll
-    for (int d = 0; d < 8; ++d) {
-      const float f = __bfloat162float(e[d]);
-      a0 += sh[0][8 * j + d] * f; a1 += sh[1][8 * j + d] * f; a2 += sh[2][8 * j + d] * f;
-    }
-  }
-  float* o = low + static_cast<size_t>(p) * 3 * S * S + i;
-  o[0] = a0; o[static_cast<size_t>(S) * S] = a1; o[static_cast<size_t>(2) * S * S] = a2;
-}
-
 // gathers rows (token index `tok` of every prompt) of hs [P,8,256] f32 as bf16 [P,256]
 __global__ void sam_pick_token_kernel(const float* __restrict__ hs, int P, int tok, __nv_bfloat16* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -212,3 +212,24 @@ def test_batched_frames_equal_single_frames():
     for i in range(3):
         assert torch.equal(out[i][0], single[i][3][0]) and torch.equal(out[i][1], single[i][3][1]), f"frame {i}"
     assert len({int(o[1].shape[0]) for o in out}) >= 1
+
+
+def test_edge_cases_and_errors(tiny):
+    """No surviving mask (automatic_mask_generator.py:331-342 filters everything; OVO returns None upstream, ovo.py:141-143),
+    frames larger than the handle was created for, too many prompts: empty results / loud errors, never garbage."""
+    sam, cfg, sd = tiny
+    img = torch.from_numpy(GG.sam_image(seed=12)).cuda()
+    seg, maps = sam.generate(img, sam.amg_params(pred_iou_thresh=0.999, stability_score_thresh=0.999))
+    assert maps.shape[0] == 0 and int(seg.max()) == -1
+    low, iou = sam.predict(torch.from_numpy(OS.amg_points(16, 480, 640, cfg.image_size))[:8].cuda())
+    out = sam.postprocess(low, iou, 480, 640, sam.amg_params(pred_iou_thresh=0.999))
+    assert out["masks"].shape[0] == 0
+    with pytest.raises(RuntimeError, match="exceeds"):
+        sam.set_image(torch.zeros(481, 640, 3, dtype=torch.uint8, device="cuda"))
+    with pytest.raises(RuntimeError, match="prompts"):
+        sam.predict(torch.zeros(sam.max_prompts + 1, 2, device="cuda"))
+    with pytest.raises(RuntimeError, match="frames"):
+        sam.set_images(torch.zeros(2, 480, 640, 3, dtype=torch.uint8, device="cuda"))     # handle created with max_batch 1
+    # the handle still works after the errors
+    seg2, maps2 = sam.generate(img, sam.amg_params(pred_iou_thresh=0.45, stability_score_thresh=0.4, box_nms_thresh=0.9999, nms_score_th=0.2))
+    assert maps2.shape[0] > 0
