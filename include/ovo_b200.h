@@ -47,7 +47,8 @@ long long ovo_launch_count(int reset);
 typedef struct {
   int image_size; /* 336 */
   int patch_size; /* 14 */
-  int width;      /* 1024; head_dim = width/heads must be 64 */
+  int width;      /* 1024; head_dim = width/heads: 64 (tcgen05 attention) or 32 / 80 / 96 (generic mma.sync attention, e.g. the
+                   * ViT-H/14-shaped encoder of BASELINE config 4: 1280 / 16 = 80) */
   int layers;     /* 24 */
   int heads;      /* 16 */
   int mlp_width;  /* 4096 */

@@ -242,6 +242,32 @@ def gen_masks():
     print("masks.npz", {k: v.shape for k, v in out.items()})
 
 
+HD80 = dict(width=160, layers=2, heads=2, mlp_width=640, output_dim=64, text_layers=0)   # head_dim 80, as the ViT-H/14-shaped encoder
+
+
+def gen_encoder_hd80():
+    """Reference PE VisionTransformer with head_dim 80 (BASELINE config 4's ViT-H/14 shape: 1280 / 16 heads): tokens of one image."""
+    from ovo_b200.encoder import EncoderConfig, random_state_dict
+    rh.setup_paths()
+    from core.vision_encoder.config import PEConfig, PETextConfig
+    import core.vision_encoder.pe as pe
+    cfg = EncoderConfig(**HD80)
+    vc = PEConfig(image_size=cfg.image_size, patch_size=cfg.patch_size, width=cfg.width, layers=cfg.layers, heads=cfg.heads,
+                  mlp_ratio=cfg.mlp_width / cfg.width, pool_type="attn", output_dim=cfg.output_dim, use_cls_token=True,
+                  attn_pooler_heads=cfg.heads)
+    torch.manual_seed(123)
+    model = pe.CLIP(vc, PETextConfig(context_length=32, width=128, heads=2, layers=1, output_dim=64, vocab_size=1024)).eval()
+    missing, unexpected = model.load_state_dict(random_state_dict(cfg, seed=0, text=False), strict=False)
+    assert not unexpected, unexpected
+    torch.manual_seed(4)
+    px = torch.randn(2, 3, 336, 336) * 0.5
+    with torch.no_grad():
+        tok = model.visual.forward_features(px, norm=True)
+    out = {"tokens_sub": tok[:, ::9, ::4].numpy()}
+    np.savez_compressed(os.path.join(OUT, "encoder_hd80.npz"), **out)
+    print("encoder_hd80.npz", {k: v.shape for k, v in out.items()})
+
+
 SAM_THR = dict(pred_iou_thresh=0.5, stability_score_thresh=0.5, box_nms_thresh=1.0)
 SAM_AMG_HW = (240, 320)   # the AMG fixture uses a small frame so that the stored masks stay small   # random weights: the stock 0.8 / 0.95 would reject everything
 
@@ -313,6 +339,6 @@ if __name__ == "__main__":
     if not rh.available():
         sys.exit("reference not available: fixtures can only be generated in the build container")
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["encoder", "assoc", "ovo", "masks", "mapper", "sam"]
+    which = sys.argv[1:] or ["encoder", "assoc", "ovo", "masks", "mapper", "sam", "encoder_hd80"]
     for w in which:
         globals()["gen_" + w]()

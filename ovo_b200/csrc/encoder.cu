@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "attention.cuh"
+#include "generic_attention.cuh"
 #include "common.cuh"
 #include "gemm.cuh"
 
@@ -335,6 +336,9 @@ struct ovo_encoder {
   __nv_bfloat16 *patch_buf = nullptr, *xn = nullptr, *q = nullptr, *k = nullptr, *vt = nullptr, *attn = nullptr,
                 *hmid = nullptr, *mean = nullptr, *pooled_in = nullptr;
   float2* rope_tab = nullptr;
+  int hd = 64;                    // vision head_dim; != 64 takes the generic path (generic_attention.cuh)
+  float* qkv_f32 = nullptr;       // [rows, 3*width] f32: QKV GEMM output of the generic path
+  float2* rope_gen = nullptr;     // [grid+1][hd/4] rotary table of the generic path
   float *x = nullptr, *xfinal = nullptr, *canvas = nullptr,
         *resize_tmp = nullptr;
   uint8_t* fmask = nullptr;
@@ -414,12 +418,29 @@ int run_blocks(ovo_encoder* e, const std::vector<ovo_block_weights>& blocks, int
   for (int l = 0; l < n_layers; ++l) {
     const ovo_block_weights& b = blocks[l];
     OVO_TRY(launch_ln(e->x, rows, width, b.ln1_w, b.ln1_b, e->cfg.ln_eps, e->xn, nullptr, nullptr, s));
+    if (rope && e->hd != 64) {
+      // generic head_dim: f32 q|k|v straight from the GEMM, rotary embedding + bf16 rounding while the attention kernel stages
+      EpiParams qe;
+      qe.out = e->qkv_f32; qe.ldo = 3 * width; qe.bias = b.qkv_b;
+      OVO_TRY(launch_gemm(EPI_F32, e->xn, width, static_cast<const __nv_bfloat16*>(b.qkv_w), width, rows, 3 * width, width, qe, s));
+      GenAttnParams gp;
+      gp.qkv = e->qkv_f32; gp.out = e->attn; gp.seq = seq; gp.heads = heads; gp.width = width; gp.causal = causal ? 1 : 0;
+      gp.rope = e->rope_gen; gp.rope_grid = e->grid;
+      gp.scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(e->hd));
+      ProfScope prof(s, PROF_ATTN, 4.0 * n_seq * heads * static_cast<double>(seq) * seq * e->hd, 0.0);
+      if (e->hd == 80) generic_attention_kernel<80><<<dim3(ceil_div(seq, 64), n_seq, heads), 128, 0, s>>>(gp);
+      else if (e->hd == 96) generic_attention_kernel<96><<<dim3(ceil_div(seq, 64), n_seq, heads), 128, 0, s>>>(gp);
+      else if (e->hd == 32) generic_attention_kernel<32><<<dim3(ceil_div(seq, 64), n_seq, heads), 128, 0, s>>>(gp);
+      else return set_error(OVO_E_INVALID, "head_dim %d has no attention kernel (64 fast path; 32, 80, 96 generic)", e->hd);
+      OVO_CHECK_LAUNCH();
+    } else {
     EpiParams qkv;
     qkv.bias = b.qkv_b; qkv.q = e->q; qkv.k = e->k; qkv.vt = e->vt;
     qkv.rope_tab = rope ? e->rope_tab : nullptr; qkv.rope_grid = e->grid;
     qkv.seq = seq; qkv.seq_pad = seq_pad; qkv.heads = heads; qkv.width = width;
     OVO_TRY(launch_gemm(EPI_QKV, e->xn, width, static_cast<const __nv_bfloat16*>(b.qkv_w), width, rows, 3 * width, width, qkv, s));
     OVO_TRY(launch_attention(e, n_seq, seq, seq_pad, heads, width, causal, s));
+    }
     EpiParams op;
     op.out = e->x; op.ldo = width; op.bias = b.out_b; op.resid = e->x; op.ldr = width;
     OVO_TRY(launch_gemm(EPI_F32_RESID, e->attn, width, static_cast<const __nv_bfloat16*>(b.out_w), width, rows, width, width, op, s));
@@ -486,7 +507,12 @@ extern "C" {
 int ovo_encoder_create(const ovo_vit_cfg* cfg, const ovo_vit_weights* w, int max_images, int max_h, int max_w,
                        int max_masks, ovo_encoder_t** out) {
   OVO_REQUIRE(cfg && w && out, "ovo_encoder_create: null argument");
-  OVO_REQUIRE(cfg->width % 64 == 0 && cfg->heads > 0 && cfg->width / cfg->heads == 64, "head_dim must be 64 (width %d, heads %d)", cfg->width, cfg->heads);
+  OVO_REQUIRE(cfg->heads > 0 && cfg->width % cfg->heads == 0, "width %d is not a multiple of heads %d", cfg->width, cfg->heads);
+  {
+    const int hd = cfg->width / cfg->heads;
+    OVO_REQUIRE(cfg->width % 8 == 0 && (hd == 64 || hd == 32 || hd == 80 || hd == 96),
+                "vision head_dim %d unsupported (64 = tcgen05 path; 32, 80, 96 = generic path)", hd);
+  }
   OVO_REQUIRE(cfg->image_size % cfg->patch_size == 0 && cfg->image_size / cfg->patch_size < kRopeRowsMax, "image_size must be a multiple of patch_size (grid < 40)");
   OVO_REQUIRE(max_images > 0 && max_masks > 0 && max_h > 0 && max_w > 0, "ovo_encoder_create: bad limits");
   OVO_REQUIRE(w->patch_kpad % 64 == 0 && w->patch_kpad >= 3 * cfg->patch_size * cfg->patch_size, "patch_kpad must be a multiple of 64");
@@ -500,6 +526,7 @@ int ovo_encoder_create(const ovo_vit_cfg* cfg, const ovo_vit_weights* w, int max
   e->blocks.assign(w->blocks, w->blocks + cfg->layers);
   if (cfg->text_layers > 0) e->text_blocks.assign(w->text_blocks, w->text_blocks + cfg->text_layers);
   e->max_images = max_images; e->max_h = max_h; e->max_w = max_w; e->max_masks = max_masks;
+  e->hd = cfg->width / cfg->heads;
   e->grid = cfg->image_size / cfg->patch_size; e->patches = e->grid * e->grid; e->seq = e->patches + 1;
   e->seq_pad = ceil_div(e->seq, 128) * 128;
   const char* env = getenv("OVO_B200_GRAPHS");
@@ -525,6 +552,10 @@ int ovo_encoder_create(const ovo_vit_cfg* cfg, const ovo_vit_weights* w, int max
   r |= dmalloc(&e->k, qk_elems);
   r |= dmalloc(&e->vt, qk_elems);
   r |= dmalloc(&e->rope_tab, static_cast<size_t>(e->grid + 1) * 16);
+  if (e->hd != 64) {
+    r |= dmalloc(&e->qkv_f32, static_cast<size_t>(max_images) * e->seq * 3 * cfg->width + 64);
+    r |= dmalloc(&e->rope_gen, static_cast<size_t>(e->grid + 1) * (e->hd / 4));
+  }
   r |= dmalloc(&e->canvas, std::max(pmax, static_cast<size_t>(max_images) * e->patches) * cfg->width);
   r |= dmalloc(&e->fmask, static_cast<size_t>(max_masks) * pmax);
   r |= dmalloc(&e->fcnt, static_cast<size_t>(max_masks));
@@ -557,6 +588,20 @@ int ovo_encoder_create(const ovo_vit_cfg* cfg, const ovo_vit_weights* w, int max
       return set_error(OVO_E_CUDA, "rope table upload failed");
     }
   }
+  if (e->hd != 64) {   // rope.py:315-340 for a general head_dim: hd/4 frequencies per axis, theta_i = 10000^(-2i / (hd/2))
+    const int qn = e->hd / 4;
+    std::vector<float2> tab(static_cast<size_t>(e->grid + 1) * qn);
+    for (int r = 0; r <= e->grid; ++r)
+      for (int i = 0; i < qn; ++i) {
+        const float theta = 1.0f / powf(10000.0f, static_cast<float>(2 * i) / static_cast<float>(e->hd / 2));
+        const float ang = static_cast<float>(r) * theta;
+        tab[static_cast<size_t>(r) * qn + i] = make_float2(cosf(ang), sinf(ang));
+      }
+    if (cudaMemcpy(e->rope_gen, tab.data(), tab.size() * sizeof(float2), cudaMemcpyHostToDevice) != cudaSuccess) {
+      ovo_encoder_destroy(e);
+      return set_error(OVO_E_CUDA, "rope table upload failed");
+    }
+  }
   *out = e;
   return OVO_OK;
 }
@@ -566,7 +611,7 @@ void ovo_encoder_destroy(ovo_encoder_t* e) {
   for (auto& g : e->graphs) if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
   if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
   cudaFree(e->patch_buf); cudaFree(e->x); cudaFree(e->xfinal); cudaFree(e->xn); cudaFree(e->attn); cudaFree(e->hmid);
-  cudaFree(e->q); cudaFree(e->k); cudaFree(e->vt); cudaFree(e->rope_tab); cudaFree(e->canvas);
+  cudaFree(e->q); cudaFree(e->k); cudaFree(e->vt); cudaFree(e->rope_tab); cudaFree(e->canvas); cudaFree(e->qkv_f32); cudaFree(e->rope_gen);
   cudaFree(e->fmask); cudaFree(e->mean_acc); cudaFree(e->groups_dev); cudaFree(e->fcnt); cudaFree(e->mean); cudaFree(e->resize_tmp); cudaFree(e->eot_rows);
   cudaFree(e->pooled_in); cudaFree(e->tab_min); cudaFree(e->tab_size); cudaFree(e->tab_w); cudaFree(e->jobs_dev);
   delete e;

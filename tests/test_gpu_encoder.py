@@ -152,3 +152,44 @@ def test_l14_text_vs_oracle(l14):
     with torch.no_grad():
         ref = OE.text_forward(tok, sd, ocfg)
     _check(out, ref, "L14 text")
+
+
+def test_head_dim_80_generic_attention_path(golden_dir):
+    """BASELINE config 4's ViT-H/14 shape has head_dim 80 (1280 / 16): the generic mma.sync attention path
+    (generic_attention.cuh) with the rotary embedding applied while staging, vs the oracle and the reference golden."""
+    from ovo_b200.encoder import EncoderConfig, RegionEncoder, random_state_dict
+    cfg = EncoderConfig(**GG.HD80)
+    sd = random_state_dict(cfg, seed=0, text=False)
+    enc = RegionEncoder(cfg, sd, max_images=8, max_h=968, max_w=1296, max_masks=32)
+    torch.manual_seed(4)
+    px = torch.randn(2, 3, 336, 336) * 0.5
+    ocfg = _ocfg(cfg)
+    for L in (1, 2):
+        out = enc.forward_features_from_pixels(px.cuda(), n_layers=L, ln_post=(L == cfg.layers))
+        with torch.no_grad():
+            ref = OE.vit_forward_features(px, sd, ocfg, n_layers=L, norm=(L == cfg.layers))
+        _check(out, ref, f"hd80 layer {L}")
+    gold = np.load(os.path.join(golden_dir, "encoder_hd80.npz"))
+    sub = out.cpu()[:, ::9, ::4].numpy()
+    assert np.linalg.norm(sub - gold["tokens_sub"]) / np.linalg.norm(gold["tokens_sub"]) < REL_TOL
+    # a 7-image frame (960x1280, config 4's resolution) through the region pipeline
+    img = synth.rgb(960, 1280, seed=2)
+    seg, bm = synth.grid_masks(960, 1280, rows=2, cols=3)
+    feats = enc.encode_regions(torch.from_numpy(img).cuda(), torch.from_numpy(bm).cuda())
+    with torch.no_grad():
+        ref = OE.encode_regions(img, bm, sd, ocfg)
+    _check(feats, ref, "hd80 regions 960x1280")
+
+
+def test_vit_h14_shaped_full_depth_vs_oracle():
+    """The ViT-H/14-shaped encoder of BASELINE config 4 (width 1280, 32 layers, 16 heads, mlp 5120; 652 M parameters)."""
+    from ovo_b200.encoder import EncoderConfig, RegionEncoder, random_state_dict
+    cfg = EncoderConfig(width=1280, layers=32, heads=16, mlp_width=5120, output_dim=1024, text_layers=0)
+    sd = random_state_dict(cfg, seed=3, text=False)
+    enc = RegionEncoder(cfg, sd, max_images=2, max_masks=8)
+    torch.manual_seed(5)
+    px = torch.randn(1, 3, 336, 336) * 0.5
+    out = enc.forward_features_from_pixels(px.cuda())
+    with torch.no_grad():
+        ref = OE.vit_forward_features(px, sd, _ocfg(cfg), n_layers=cfg.layers, norm=True)
+    _check(out, ref, "ViT-H/14-shaped, 32 layers")
