@@ -68,6 +68,24 @@ def test_query_linearity_full_size(sm):
     assert ((a[idx] - bank[idx].float() @ t1.T).abs().max().item()) < 2e-2 * 32   # spot check against f32
 
 
+def test_query_config4_size_5m_points_200_classes(sm):
+    """BASELINE config 4's query: 5M-point dense map (10.2 GB bf16) against a 200-class text bank; spot-checked against f32 and
+    classified (argmax + threshold, ovo.py:486-491) on the device."""
+    N, Q = 5_000_000, 200
+    g = torch.Generator(device="cuda").manual_seed(4)
+    bank = torch.nn.functional.normalize(torch.randn(N, 1024, device="cuda", generator=g), dim=-1).bfloat16()
+    text = torch.nn.functional.normalize(torch.randn(Q, 1024, device="cuda", generator=g), dim=-1)
+    out = sm.query_dense(bank, text)
+    assert out.shape == (N, Q)
+    idx = torch.randint(0, N, (8192,), device="cuda", generator=g)
+    ref = bank[idx].float() @ text.bfloat16().float().T
+    assert (out[idx] - ref).abs().max().item() < 1e-4
+    cls, conf = sm.classify(out, 0.05)
+    mx, am = out.max(1)
+    assert (cls.long() == torch.where(mx > 0.05, am, -1)).all()
+    del bank, out
+
+
 def test_query_instances_and_fuse_views(sm):
     torch.manual_seed(3)
     store = torch.randn(40, 256, device="cuda")
