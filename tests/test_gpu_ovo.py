@@ -9,6 +9,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 from oracle import gen_golden as GG
+from ovo_b200 import synth
 
 
 class _Logger:
@@ -188,3 +189,46 @@ def test_precompute_writes_the_reference_mask_files(tmp_path):
     assert not os.path.exists(os.path.join(mg.masks_path, "0001_seg_map_default.npy"))
     s2, m2 = mg.get_masks(None, 2)
     assert s2.is_cuda and s2.dtype == torch.int32 and m2.shape[1:] == (H, W)
+
+
+def test_streaming_growth_with_online_queries(tmp_path):
+    """BASELINE config 5 in miniature through the public classes: the map grows frame by frame (PointMapper.map =
+    VanillaMapper.map, vanilla_mapper.py:46-85), every 3rd frame is a keyframe (detect_and_track_objects on the map as it
+    is, then the slam's update_pcd_obj_ids, ovomapping.py:180-185), the dense bank follows the growing map and a text
+    query runs on-line after every keyframe (ovomapping.py:200-207)."""
+    from ovo_b200 import OVO, CLIPGenerator
+    from ovo_b200.encoder import random_state_dict
+    from ovo_b200.mapper import PointMapper
+    K, _, _, _, frames = GG.ovo_inputs()
+    mdir = tmp_path / "masks" / "scene"
+    mdir.mkdir(parents=True)
+    cfg = GG.tiny_cfg()
+    config = GG.ovo_config(str(tmp_path / "masks"))
+    config["dense_map"] = True
+    clip = CLIPGenerator(config["clip"], state_dict=random_state_dict(cfg, seed=0), tokenizer=_TokTokenizer(), encoder_config=cfg)
+    ovo = OVO(config, _Logger(), scene_name="scene", cam_intrinsics=torch.from_numpy(K), clip_generator=clip)
+    pm = PointMapper({"device": "cuda", "mapping": {"k_pooling": 3, "reserve_points": 50000}}, torch.from_numpy(K), semmap=ovo.semmap)
+    sizes, n_obj = [], []
+    for fid in range(9):
+        d, c2w, img = synth.depth_map(frame_id=fid), synth.pose(2 * fid, yaw=0.03 * fid), synth.rgb(seed=fid)
+        pm.map([fid, img, d, c2w], torch.from_numpy(c2w))
+        sizes.append(pm.n)
+        if fid % 3:
+            continue
+        seg, bm = synth.grid_masks(rows=3, cols=4)
+        np.save(mdir / f"{fid:04d}_seg_map_default.npy", seg)
+        np.save(mdir / f"{fid:04d}_bmap_default.npy", bm)
+        pts, pids, obj = pm.get_map()
+        upd = ovo.detect_and_track_objects((fid, img, d, ()), (pts, pids, obj.reshape(-1)), torch.from_numpy(c2w))
+        assert upd is not None and upd.shape[0] == pm.n
+        pm.update_pcd_obj_ids(upd)
+        ovo.compute_semantic_info()
+        n_obj.append(len(ovo.objects))
+        sim = ovo.query(["0", "1"])                                  # on-line query against the instance bank
+        assert sim.shape == (len(ovo.objects), 2)                    # one row per instance (ovo.py:513-527)
+        dense = ovo.query_points(["0", "1"], n_points=pm.n)          # and against the dense per-point map
+        assert dense.shape == (pm.n, 2) and not torch.isnan(dense).any()
+    assert sizes == sorted(sizes) and sizes[-1] > sizes[0] > 0 and pm.capacity >= pm.n
+    assert n_obj[-1] >= n_obj[0] > 0
+    labelled = (pm.get_map()[2].reshape(-1) >= 0).sum().item()
+    assert labelled > 0
