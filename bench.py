@@ -367,6 +367,7 @@ def run_e2e(args, rank, world, dev, enc, K, xyz, ids, ins, seg, bm, fr, dist):
             torch.cuda.synchronize()
             ovo._store_n = 0
             ovo.keyframes["ins_descriptors"].clear()
+            ovo._desc_epoch += 1
 
     steps = max(1, min(args.steps, 10))
     for _ in range(max(3, min(args.warmup, 3))):

@@ -215,6 +215,12 @@ int ovo_map_fuse_dense_batch(ovo_map_t* map, const int* kf_slots_host, int n_slo
 int ovo_bank_update_mean(float* bank_dev, int32_t* counts_dev, int D, const float* feats_dev,
                          const int32_t* rows_dev, int n, void* stream);
 
+/* The same fusion when a few views are ADDED to instances whose other views are already fused (the common case of
+ * Instance3D.update_clip with 'avg_pooling': O(new views) per instance instead of re-averaging every stored view):
+ * bank[b] = (n * bank[b] + sum_{i in [i0,i1)} store[idx[i]]) / (n + i1 - i0) for quads_dev i32 [m][4] = (b, n, i0, i1). */
+int ovo_bank_add_views(float* bank_dev, int D, const float* store_dev, const int32_t* quads_dev, const int32_t* idx_dev, int m,
+                       void* stream);
+
 /* clip_cosine_similarity (clip_utils.py:16-19) on the DENSE map: bank bf16 [N,D] x text f32 [Q,D]^T ->
  * out f32 [N,Q].  tcgen05 GEMM streaming the bank once from HBM. */
 int ovo_query_dense(ovo_map_t* map, const void* bank_dev, int64_t N, int D, const float* text_dev, int Q,

@@ -107,6 +107,7 @@ SIGNATURES = {
                                    c_void_p]),
     "ovo_map_fuse_dense_batch": (c_int, [c_void_p, C.POINTER(c_int), c_int, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_int,
                                          c_void_p, c_int, c_void_p]),
+    "ovo_bank_add_views": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "ovo_bank_update_mean": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p]),
     "ovo_query_dense": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     "ovo_query_instances": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),

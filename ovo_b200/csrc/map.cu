@@ -508,6 +508,19 @@ __global__ void bank_update_mean_kernel(float* __restrict__ bank, int32_t* __res
   }
 }
 
+// avg_pooling with k more views (instance3d.py:19-21): mean_{n+k} = (n * mean_n + sum of the k new descriptors) / (n + k).
+// quads [m][4] = (bank row, views already behind the row n, first and one-past-last position in idx); idx = descriptor-store rows.
+__global__ void bank_add_views_kernel(float* __restrict__ bank, int D, const float* __restrict__ store,
+                                      const int32_t* __restrict__ quads, const int32_t* __restrict__ idx) {
+  const int br = quads[4 * blockIdx.x], n = quads[4 * blockIdx.x + 1], i0 = quads[4 * blockIdx.x + 2], i1 = quads[4 * blockIdx.x + 3];
+  const float nf = static_cast<float>(n), inv = __fdiv_rn(1.0f, static_cast<float>(n + (i1 - i0)));
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    float acc = __fmul_rn(bank[static_cast<size_t>(br) * D + d], nf);
+    for (int i = i0; i < i1; ++i) acc = __fadd_rn(acc, store[static_cast<size_t>(idx[i]) * D + d]);
+    bank[static_cast<size_t>(br) * D + d] = __fmul_rn(acc, inv);
+  }
+}
+
 // ------------------------------------------------------------------------------------------ query helpers
 __global__ void f32_to_bf16_pad_kernel(const float* __restrict__ src, int rows, int cols, __nv_bfloat16* __restrict__ dst,
                                        int rows_pad) {
@@ -1144,6 +1157,14 @@ int ovo_map_fuse_dense_batch(ovo_map_t* m, const int* kf_slots_host, int n_slots
     ovo::fuse_dense_batch_kernel<4><<<blocks, 256, 0, stream>>>(m->seg_dense, n_slots, N, static_cast<__nv_bfloat16*>(bank_dev), counts_dev, D, feats_dev, mask_row_dev, n_masks);
   else
     ovo::fuse_dense_batch_kernel<8><<<blocks, 256, 0, stream>>>(m->seg_dense, n_slots, N, static_cast<__nv_bfloat16*>(bank_dev), counts_dev, D, feats_dev, mask_row_dev, n_masks);
+  OVO_CHECK_LAUNCH();
+  return OVO_OK;
+}
+
+int ovo_bank_add_views(float* bank_dev, int D, const float* store_dev, const int32_t* quads_dev, const int32_t* idx_dev, int n, void* stream) {
+  OVO_REQUIRE(bank_dev && store_dev && quads_dev && idx_dev && D > 0 && n >= 0, "ovo_bank_add_views: bad arguments");
+  if (n == 0) return OVO_OK;
+  ovo::bank_add_views_kernel<<<n, 256, 0, static_cast<cudaStream_t>(stream)>>>(bank_dev, D, store_dev, quads_dev, idx_dev);
   OVO_CHECK_LAUNCH();
   return OVO_OK;
 }

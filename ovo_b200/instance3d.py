@@ -29,6 +29,14 @@ class Instance3D:
         self.top_kf: List[tuple] = []      # min-heap of (area, kf_id)
         self.to_update = False
         self.bank_row = -1                 # row of the device instance bank (set by OVO)
+        # host-side indices: membership tests in O(1) (the reference scans its lists, instance3d.py:105-155: per-keyframe cost
+        # grows with the length of the stream) and the bookkeeping of the incremental avg_pooling fusion (ovo_b200/ovo.py)
+        self._kfs_set = set()
+        self._top_area: Dict[int, int] = {}
+        self.pending_rows: List[int] = []  # descriptor-store rows computed for this instance but not yet in the fused feature
+        self.n_fused = 0                   # views behind the current bank row
+        self.evicted = False               # a view left the top-k heap or changed: the next fusion must re-read every view
+        self._desc_epoch = 0               # OVO._desc_epoch at the last full fusion
         if kf_id is not None:
             self.update(points_ids or [], kf_id, mask_area)
 
@@ -50,31 +58,50 @@ class Instance3D:
         self.points_ids.extend(points_ids)
 
     def add_keyframes(self, kf_id: int) -> None:
-        if kf_id not in self.kfs_ids:
+        if len(self._kfs_set) != len(self.kfs_ids):  # the list was assigned from outside (restore, merges)
+            self._kfs_set = set(self.kfs_ids)
+        if kf_id not in self._kfs_set:
+            self._kfs_set.add(kf_id)
             self.kfs_ids.append(kf_id)
 
+    def _sync_top_index(self) -> None:
+        if len(self._top_area) != len(self.top_kf):  # the heap was assigned from outside
+            self._top_area = {k: a for a, k in self.top_kf}
+
     def idx_in_top_kf(self, kf_id: int) -> int:
+        self._sync_top_index()
+        if kf_id not in self._top_area:
+            return -1
         for i, (_, k) in enumerate(self.top_kf):
             if k == kf_id:
                 return i
         return -1
 
     def is_top_kf(self, kf_id: int) -> bool:
-        return self.idx_in_top_kf(kf_id) > -1
+        self._sync_top_index()
+        return kf_id in self._top_area
 
     def add_top_kf(self, kf_id: int, area: int) -> None:
-        i = self.idx_in_top_kf(kf_id)
-        if i > -1:                                   # known keyframe: keep the larger area
-            if area > self.top_kf[i][0]:
+        self._sync_top_index()
+        if kf_id in self._top_area:                  # known keyframe: keep the larger area
+            if area > self._top_area[kf_id]:
+                i = self.idx_in_top_kf(kf_id)
                 self.top_kf[i] = (area, kf_id)
+                self._top_area[kf_id] = area
                 heapq.heapify(self.top_kf)
                 self.to_update = True
+                self.evicted = True                  # the order of the views changed
             return
         if len(self.top_kf) < self.n_top_kf:
             heapq.heappush(self.top_kf, (area, kf_id))
+            self._top_area[kf_id] = area
             self.to_update = True
         else:
             dropped = heapq.heappushpop(self.top_kf, (area, kf_id))
+            if self.n_top_kf > 0:
+                self._top_area[kf_id] = area
+                self._top_area.pop(dropped[1], None)
+                self.evicted = True
             if self.n_top_kf <= 0 or dropped[1] != kf_id:
                 self.to_update = True
 
@@ -94,6 +121,7 @@ class Instance3D:
         if len(views) == 0:
             return None
         self.to_update = False
+        self.n_fused, self.evicted, self.pending_rows = len(views), False, []
         return views
 
     def update_clip(self, keyframes_clips: Dict[int, Dict[int, Any]], force_update: bool = False, fuser=None) -> None:
@@ -119,11 +147,14 @@ class Instance3D:
         self.clip_feature = obj_dict[f"ins3d_{self.id}_clip_feature"]
         self.clip_feature_kf = obj_dict.get(f"ins3d_{self.id}_clip_feature_kf", None)
         self.to_update = self.clip_feature is None
+        self.evicted = True                          # the next fusion re-reads every view
         if debug_info:
             self.kfs_ids = obj_dict[f"ins3d_{self.id}_keyframes_ids"].tolist()
             self.points_ids = obj_dict[f"ins3d_{self.id}_points_ids"].tolist()
             if obj_dict.get(f"ins3d_{self.id}_top_kfs", None) is not None:
                 self.top_kf = [(a, k) for a, k in obj_dict[f"ins3d_{self.id}_top_kfs"]]
+        self._kfs_set = set(self.kfs_ids)
+        self._top_area = {k: a for a, k in self.top_kf}
 
     def purge_points_ids(self, purge_ids: List[int]) -> None:
         drop = set(purge_ids)

@@ -199,6 +199,14 @@ class SemanticMap:
         check(self.lib.ovo_classify(ptr(sim), sim.shape[0], sim.shape[1], float(th), ptr(cls), ptr(conf), stream_ptr()), "ovo_classify")
         return cls, conf
 
+    def bank_add_views(self, bank: torch.Tensor, store: torch.Tensor, quads: torch.Tensor, idx: torch.Tensor):
+        """bank[b] = (n*bank[b] + sum store[idx[i0:i1]]) / (n + i1 - i0) for int32 quads [m,4] = (b, n, i0, i1): a few more
+        views per instance (avg_pooling) without re-reading the views already fused."""
+        assert bank.is_cuda and store.is_cuda and quads.is_cuda and idx.is_cuda
+        assert quads.dtype == torch.int32 and idx.dtype == torch.int32 and quads.is_contiguous() and idx.is_contiguous()
+        check(self.lib.ovo_bank_add_views(ptr(bank), bank.shape[1], ptr(store), ptr(quads), ptr(idx), quads.shape[0], stream_ptr()),
+              "ovo_bank_add_views")
+
     def bank_update_mean(self, bank: torch.Tensor, counts: torch.Tensor, feats: torch.Tensor, rows: torch.Tensor):
         """avg_pooling running mean on the instance bank (instance3d.py:19-21)."""
         assert bank.dtype == torch.float32 and counts.dtype == torch.int32 and rows.dtype == torch.int32

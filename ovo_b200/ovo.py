@@ -49,6 +49,7 @@ class OVO:
         self.clip_generator = clip_generator or CLIPGenerator(config["clip"], device=device)
         self.mask_generator = None if eval else MaskGenerator(config["sam"], scene_name, device=device)
         self.keyframes = {"ins_descriptors": dict(), "frame_id": list(), "ins_maps": list()}
+        self._desc_epoch = 0      # bumped whenever stored descriptors are dropped / rewritten: incremental fusion falls back to a full one
         self.keyframes_queue = deque([])
         self.objects: Dict[int, Instance3D] = dict()
         self._time_cache = []
@@ -346,12 +347,38 @@ class OVO:
         """ovo.py:439-461."""
         ins_embeds = {ins: rows[i] for i, ins in enumerate(matched_ins_ids) if ins != -1}
         self.keyframes["ins_descriptors"][kf_id] = ins_embeds
-        work = []
-        for ins in matched_ins_ids:
-            views = self.objects[ins].views_to_fuse(self.keyframes["ins_descriptors"])
+        work, inc = [], []
+        avg = Instance3D.mv_fusion == "avg_pooling"
+        for i, ins in enumerate(matched_ins_ids):
+            obj = self.objects[ins]
+            obj.pending_rows.append(rows[i])
+            if not obj.to_update:
+                continue                      # instance3d.py:168: nothing is fused until the flag is raised again
+            # avg_pooling, and the only change since the last fusion are descriptors that arrived since: the mean is updated in
+            # place (O(new views)) instead of re-reading every stored view of the instance (the reference re-stacks them all,
+            # instance3d.py:157-189; the same mean up to f32 rounding)
+            if avg and obj.n_fused > 0 and not obj.evicted and obj._desc_epoch == self._desc_epoch:
+                inc.append((obj, obj.n_fused, obj.pending_rows))
+                obj.n_fused += len(obj.pending_rows)
+                obj.pending_rows = []
+                obj.to_update = False
+                continue
+            views = obj.views_to_fuse(self.keyframes["ins_descriptors"])
             if views is not None:
-                work.append((self.objects[ins], views))
+                obj._desc_epoch = self._desc_epoch
+                work.append((obj, views))
         self._fuse(work)
+        if inc:
+            quads, idx = [], []
+            for o, n_before, pend in inc:
+                quads.append((o.bank_row, n_before, len(idx), len(idx) + len(pend)))
+                idx.extend(pend)
+            buf = torch.tensor([v for q in quads for v in q] + idx, dtype=torch.int32).to(self._dev, non_blocking=True)
+            self.semmap.bank_add_views(self._bank, self._store, buf[: 4 * len(quads)].view(-1, 4), buf[4 * len(quads):])
+            for o, _, _ in inc:
+                if o.clip_feature is None or o.clip_feature.dim() == 1:     # instance3d.py:186-187: a fused feature is [1, D]
+                    o.clip_feature = self._bank[o.bank_row][None]
+                o.clip_feature_kf = None
 
     def update_objects_clip(self, force_update: bool = False) -> None:
         """ovo.py:463-470."""
@@ -489,6 +516,7 @@ class OVO:
         test of instance_utils.same_instance (instance_utils.py:5-24), re-fuse descriptors."""
         self.complete_semantic_info()
         self._sync_descriptors()
+        self._desc_epoch += 1
         points_3d, _, points_ins_ids = map_data
         for i, kf in enumerate(self.keyframes["frame_id"]):
             if kf not in kfs:
@@ -573,6 +601,7 @@ class OVO:
                 obj.clip_feature = self._bank[obj.bank_row] if f.dim() == 1 else self._bank[obj.bank_row][None]
             self.objects[obj.id] = obj
         self._rows_cache = None
+        self._desc_epoch += 1
         if debug_info:
             self.keyframes["frame_id"] = list(scene_dict["frame_id"])
             n_kf = len(self.keyframes["frame_id"])
