@@ -334,11 +334,69 @@ def gen_sam():
     np.savez_compressed(os.path.join(OUT, "sam_tiny.npz"), **out)
     print("sam_tiny.npz", {k: v.shape for k, v in out.items()}, "n", len(anns), "kept", len(kept))
 
+CROP_POOL_HEADS = 2          # attn_pooler_heads of the tiny reference model (build_reference_model)
+CROP_CASES = [("vanilla", 336), ("vanilla", 224), ("fixed_weights", 336), ("fixed_weights", 384), ("hovsg", 336),
+              ("adaptive_weights", 336), ("concept_fusion", 336)]
+
+
+def crop_masks(h=480, w=640):
+    """Grid cells (touch every border: the margin box clamps), a disc (masked fill inside its box), a thin
+    horizontal bar (padded square of the `vanilla` type), an L-shape."""
+    from ovo_b200 import synth
+    _, bm = synth.grid_masks(h, w, rows=2, cols=3)
+    yy, xx = np.mgrid[0:h, 0:w]
+    extra = np.zeros((3, h, w), bool)
+    extra[0] = (yy - 200) ** 2 + (xx - 300) ** 2 < 90 ** 2
+    extra[1, 100:112, 40:600] = True
+    extra[2, 300:470, 500:530] = True
+    extra[2, 440:470, 380:530] = True
+    return np.concatenate([bm, extra])
+
+
+def gen_crops():
+    """The reference's crop-based descriptors: UNMODIFIED CLIPGenerator.extract_clip / segmap2segimg / fuse_clips
+    (ovo/entities/clip_generator.py:125-158, ovo/utils/segment_utils.py:29-182, ovo/utils/clip_utils.py:21-48) with the
+    un-vendored open_clip loader (clip_utils.py:51-88) returning the vendored pe.CLIP and its own transform."""
+    from ovo_b200 import synth
+    rh.setup_paths()
+    model, sd, cfg = build_reference_model()
+    import ovo.utils.clip_utils as cu
+    import ovo.utils.segment_utils as su
+    from torchvision.transforms import Resize, Normalize, CenterCrop, Compose
+    import core.vision_encoder.transforms as transforms
+
+    def fake_loader(model_card, use_half):
+        pre = transforms.get_image_transform(model.image_size)
+        keep = [tf for tf in pre.transforms if isinstance(tf, (Resize, CenterCrop, Normalize))]
+        return model, None, Compose(keep), cfg.output_dim
+
+    cu.load_clip_model = fake_loader
+    from ovo.entities.clip_generator import CLIPGenerator
+    img = synth.rgb(480, 640, seed=21)
+    bm = crop_masks()
+    imt = torch.from_numpy(img.transpose(2, 0, 1).copy())           # uint8 [3,H,W], what OVO._extract_clip passes (ovo.py:436)
+    out = {}
+    for et, res in CROP_CASES:
+        gen = CLIPGenerator({"embed_type": et, "model_card": "PE-Core-L-14-336", "mask_res": res}, device="cpu")
+        with torch.no_grad():
+            out[f"{et}_{res}"] = gen.extract_clip(imt, torch.from_numpy(bm)).numpy()
+            if et == "fixed_weights" and res == 336:
+                out["return_all_336"] = gen.extract_clip(imt, torch.from_numpy(bm), return_all=True).numpy()
+                out["encode_image_global"] = gen.encode_image(imt[None] / 255.).numpy()
+    seg = su.segmap2segimg(torch.from_numpy(bm), imt, True, out_l=336)
+    out["segimg_sub"] = seg[:, :, ::6, ::6].numpy()
+    out["segimg_sum"] = seg.long().sum((2, 3)).numpy()
+    segv = su.segmap2segimg(torch.from_numpy(bm), imt, False, out_l=224)
+    out["segimg_vanilla_sub"] = segv[:, :, ::4, ::4].numpy()
+    out["boxes_xywh"] = su.batched_box_xyxy_to_xywh(su.batched_mask_to_box(torch.from_numpy(bm))).numpy()
+    np.savez_compressed(os.path.join(OUT, "crops.npz"), **out)
+    print("crops.npz", {k: v.shape for k, v in out.items()})
+
 
 if __name__ == "__main__":
     if not rh.available():
         sys.exit("reference not available: fixtures can only be generated in the build container")
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["encoder", "assoc", "ovo", "masks", "mapper", "sam", "encoder_hd80"]
+    which = sys.argv[1:] or ["encoder", "assoc", "ovo", "masks", "mapper", "sam", "encoder_hd80", "crops"]
     for w in which:
         globals()["gen_" + w]()

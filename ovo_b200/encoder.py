@@ -80,6 +80,14 @@ def random_state_dict(cfg: EncoderConfig, seed: int = 0, text: bool = True, devi
             block(f"transformer.resblocks.{i}.", TW, TF)
         sd["ln_final.weight"] = 1 + rn(TW, std=0.05); sd["ln_final.bias"] = rn(TW, std=0.02)
         sd["text_projection"] = rn(TW, cfg.text_output_dim, std=TW ** -0.5)
+    # attention-pooling head of `encode_image` (pe.py:44-87), used by the crop-based embed types.  Drawn LAST so the
+    # values of every key above (and the goldens generated from them) do not depend on it.
+    p = "visual.attn_pool."
+    sd[p + "probe"] = rn(1, 1, W)
+    sd[p + "layernorm.weight"] = 1 + rn(W, std=0.05); sd[p + "layernorm.bias"] = rn(W, std=0.02)
+    PF = 4 * W                                          # AttentionPooling's own mlp_ratio = 4 (pe.py:52)
+    sd[p + "mlp.c_fc.weight"] = rn(PF, W, std=W ** -0.5); sd[p + "mlp.c_fc.bias"] = rn(PF, std=0.02)
+    sd[p + "mlp.c_proj.weight"] = rn(W, PF, std=PF ** -0.5); sd[p + "mlp.c_proj.bias"] = rn(W, std=0.02)
     return {k: v.to(device) for k, v in sd.items()}
 
 
