@@ -137,6 +137,66 @@ int ovo_encode_text(ovo_encoder_t* enc, const int32_t* tokens_dev, int T, float*
 int ovo_text_bank(ovo_encoder_t* enc, const int32_t* tokens_dev, int Q, int T, float* out_dev, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Crop-based descriptors (CLIPGenerator.extract_clip's crop branch,
+ * ovo/entities/clip_generator.py:136-158): embed types vanilla / fixed_weights / hovsg / adaptive_weights /
+ * concept_fusion.  Each mask contributes a masked crop and a margin crop (ovo/utils/segment_utils.py:29-182), every
+ * crop goes through the full encode_image = ViT + attention pooling + projection (pe.py:44-87,535-543), and the
+ * frame's global descriptor, the masked-crop descriptor and the margin-crop descriptor are blended by fuse_clips
+ * (ovo/utils/clip_utils.py:21-48).
+ * ---------------------------------------------------------------------------------------------- */
+/* The attention-pooling head of pe.VisionTransformer (`visual.attn_pool.*`, `visual.proj`); device pointers, matrices
+ * bf16 [out,in] as nn.Linear stores them, vectors f32. */
+typedef struct {
+  int heads;                /* attn_pooler_heads (8 for PE-Core-L14-336, config.py:46); width/heads <= 256 */
+  int mlp_width;            /* 4 * width (pe.py:52,70) */
+  const float* q;           /* f32 [width] = (probe @ Wq^T + bq) * head_dim^-0.5: the probe is a parameter, so the query
+                             * projection of pe.py:83-84 does not depend on the image */
+  const void* kv_w;         /* bf16 [2*width, width] = attn.in_proj_weight[width:3*width] (keys | values) */
+  const float* kv_b;        /* f32 [2*width] */
+  const void* out_w; const float* out_b;     /* attn.out_proj */
+  const float* ln_w; const float* ln_b;      /* layernorm */
+  const void* fc_w; const float* fc_b;       /* mlp.c_fc [mlp_width, width] */
+  const void* proj_w; const float* proj_b;   /* mlp.c_proj [width, mlp_width] */
+  const void* vis_proj_w;   /* bf16 [output_dim, width] = visual.proj^T (pe.py:540-541) */
+} ovo_pool_head_weights;
+/* Installs the head (allocates its small workspaces).  Required before ovo_encode_images / ovo_encode_crops. */
+int ovo_encoder_set_pool_head(ovo_encoder_t* enc, const ovo_pool_head_weights* w);
+/* pe.CLIP.encode_image (pe.py:717-719, normalize=False) on already normalised pixels f32 [n,3,S,S]
+ * -> f32 [n, output_dim].  Test tap of the head; n <= max_images. */
+int ovo_encode_images(ovo_encoder_t* enc, const float* pixels_dev, int n, float* out_dev, void* stream);
+
+#define OVO_EMBED_VANILLA 0
+#define OVO_EMBED_FIXED_WEIGHTS 1
+#define OVO_EMBED_HOVSG 2
+#define OVO_EMBED_ADAPTIVE_WEIGHTS 3
+#define OVO_EMBED_CONCEPT_FUSION 4
+typedef struct {
+  int embed_type;   /* OVO_EMBED_* */
+  int return_all;   /* clip_generator.py:151-152: out is [M,3,D] = (global, masked crop, margin crop), no fusion */
+  int mask_res;     /* side of the crops before the encoder's own resize (config `mask_res`, clip_generator.py:16) */
+  int bbox_margin;  /* 50 (segment_utils.py:29) */
+  float w_masked;   /* 0.4418 (clip_generator.py:33) */
+  float w_global;   /* 0.1    (clip_generator.py:34) */
+} ovo_crop_params;
+/* batched_mask_to_box + batched_box_xyxy_to_xywh (segment_utils.py:43-104): masks uint8 [M,H,W] -> int32 [M,4]
+ * (x, y, w, h) with w = right - left, h = bottom - top (the reference's convention); empty mask -> 0,0,0,0. */
+int ovo_mask_boxes(const uint8_t* masks_dev, int M, int H, int W, int32_t* xywh_dev, void* stream);
+/* extract_clip, crop branch, for one frame: rgb uint8 [H,W,3], masks uint8 [M,H,W] -> out f32 [M, output_dim] unit norm
+ * ([M,3,output_dim] with return_all).  crops_out_dev (optional test tap, may be NULL) receives the uint8 crops
+ * [n_crops, mask_res, mask_res, 3] (masked crops first, then margin crops; `vanilla` has masked crops only).
+ * One host synchronisation (the boxes decide the crop geometry).  A mask whose box has zero width or height
+ * (`vanilla`: zero width AND height) makes the reference's F.resize raise; here the call returns OVO_E_INVALID. */
+int ovo_encode_crops(ovo_encoder_t* enc, const uint8_t* rgb_dev, int H, int W, const uint8_t* masks_dev, int M,
+                     const ovo_crop_params* prm, float* out_dev, uint8_t* crops_out_dev, void* stream);
+/* fuse_clips (clip_utils.py:21-48): g f32 [D] (the frame's global descriptor), seg / bbox f32 [M,D], unit norm
+ * -> out f32 [M,D].  embed_type 1..4. */
+int ovo_fuse_clips(const float* g_dev, const float* seg_dev, const float* bbox_dev, int M, int D, int embed_type,
+                   float w_masked, float w_global, float* out_dev, void* stream);
+/* siglip_cosine_similarity (clip_utils.py:10-14) applied in place to a similarity matrix of n entries:
+ * sim <- sigmoid(sim * exp(logit_scale) + logit_bias). */
+int ovo_siglip_similarity(float* sim_dev, int64_t n, float logit_scale, float logit_bias, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Map: 3D association, instance vote, fusion, query
  * ---------------------------------------------------------------------------------------------- */
 typedef struct {

@@ -11,8 +11,10 @@ from . import fusion as OF
 
 class OracleOVO:
     def __init__(self, W: dict, cfg: OE.VitCfg, K: np.ndarray, match_th=0.05, track_th=100, depth_filter=True,
-                 kf_queue_delay=1):
+                 kf_queue_delay=1, encode_fn=None):
         self.W, self.cfg, self.K = W, cfg, K
+        # descriptor rule: TextRegion by default; the crop-based types pass oracle.crops.extract_clip (clip_generator.py:125-158)
+        self.encode_fn = encode_fn or (lambda image, masks: OE.encode_regions(image, masks, W, cfg))
         self.match_th, self.track_th, self.use_df, self.delay = match_th, track_th, depth_filter, kf_queue_delay
         self.next_ins_id, self.kf_id = 0, 0
         self.queue = []
@@ -46,7 +48,7 @@ class OracleOVO:
                     break
                 continue
             with torch.no_grad():
-                feats = OE.encode_regions(image, fused, self.W, self.cfg)
+                feats = self.encode_fn(image, fused)
             self.kf_desc[kf] = {ins: feats[i] for i, ins in enumerate(order)}
             for ins in order:                                   # Instance3D.update_clip, avg_pooling
                 # instance3d.py:157-189: recomputed only while to_update is set.  Because CLIP runs kf_queue_delay

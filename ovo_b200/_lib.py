@@ -29,6 +29,20 @@ class VitWeights(C.Structure):
                 ("ln_final_w", c_void_p), ("ln_final_b", c_void_p), ("text_proj_w", c_void_p)]
 
 
+class PoolHeadWeights(C.Structure):
+    _fields_ = [("heads", c_int), ("mlp_width", c_int)] + \
+               [(n, c_void_p) for n in ("q", "kv_w", "kv_b", "out_w", "out_b", "ln_w", "ln_b", "fc_w", "fc_b", "proj_w", "proj_b",
+                                        "vis_proj_w")]
+
+
+class CropParams(C.Structure):
+    _fields_ = [("embed_type", c_int), ("return_all", c_int), ("mask_res", c_int), ("bbox_margin", c_int),
+                ("w_masked", c_float), ("w_global", c_float)]
+
+
+EMBED_TYPES = {"vanilla": 0, "fixed_weights": 1, "hovsg": 2, "adaptive_weights": 3, "concept_fusion": 4}
+
+
 class VoteRow(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("n_matched", "n_assigned", "n_unassigned", "mode_id", "ins_id",
                                          "is_new", "area", "reserved")]
@@ -95,6 +109,13 @@ SIGNATURES = {
     "ovo_encode_regions": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, C.POINTER(c_int), c_void_p,
                                    c_void_p]),
     "ovo_encode_text": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "ovo_encoder_set_pool_head": (c_int, [c_void_p, C.POINTER(PoolHeadWeights)]),
+    "ovo_encode_images": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "ovo_mask_boxes": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "ovo_encode_crops": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, C.POINTER(CropParams), c_void_p, c_void_p,
+                                 c_void_p]),
+    "ovo_fuse_clips": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_float, c_void_p, c_void_p]),
+    "ovo_siglip_similarity": (c_int, [c_void_p, c_int64, c_float, c_float, c_void_p]),
     "ovo_map_create": (c_int, [C.POINTER(c_void_p)]),
     "ovo_map_destroy": (None, [c_void_p]),
     "ovo_depth_filter": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),

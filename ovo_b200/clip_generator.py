@@ -1,5 +1,9 @@
-"""`CLIPGenerator` with the reference's surface (ovo/entities/clip_generator.py:12-198), TextRegion branch
-(`embed_type: TextRegion`, the default of data/working/configs/ovo.yaml:45) on the sm_100a encoder.
+"""`CLIPGenerator` with the reference's surface (ovo/entities/clip_generator.py:12-198) on the sm_100a encoder:
+the TextRegion branch (`embed_type: TextRegion`, the default of data/working/configs/ovo.yaml:45) and the crop-based
+branch (`vanilla`, `fixed_weights`, `hovsg`, `adaptive_weights`, `concept_fusion`; clip_generator.py:136-158) on the
+Perception-Encoder card (`PE-Core-L-14-336` in the reference's open_clip table, clip_utils.py:61 — the same
+architecture as the vendored `PE-Core-L14-336`).  `embed_type: learned` (a SigLIP-1152 descriptor merger with its own
+checkpoint, clips_merging.py) and the open_clip-only cards are not built.
 
 Weights: `config["ckpt_path"]` may point to a Perception-Encoder checkpoint (`torch.save`d state_dict with the
 reference's key names, what `pe.CLIP.load_ckpt` reads).  Without it — there is no network in the build or
@@ -13,7 +17,8 @@ from . import _lib
 from ._lib import check, ptr, stream_ptr
 from .encoder import EncoderConfig, RegionEncoder, random_state_dict
 
-MODEL_CARDS = {"PE-Core-L14-336": EncoderConfig()}
+MODEL_CARDS = {"PE-Core-L14-336": EncoderConfig(), "PE-Core-L-14-336": EncoderConfig()}
+CROP_EMBED_TYPES = ("vanilla", "fixed_weights", "hovsg", "adaptive_weights", "concept_fusion")
 
 
 class CLIPGenerator:
@@ -23,10 +28,12 @@ class CLIPGenerator:
         self.device = device
         self.embed_type = config.get("embed_type", "vanilla")
         self.mask_res = config.get("mask_res", 384)
-        if self.embed_type != "TextRegion":
+        if self.embed_type != "TextRegion" and self.embed_type not in CROP_EMBED_TYPES:
             raise NotImplementedError(
-                f"ovo_b200: embed_type '{self.embed_type}' (crop-based descriptors, SURVEY §8f rank 2) is not built; "
-                "use embed_type: TextRegion (the reference default)")
+                f"ovo_b200: embed_type '{self.embed_type}' is not built (have TextRegion, {', '.join(CROP_EMBED_TYPES)}); "
+                "`learned` needs the SigLIP-1152 weights-predictor checkpoint of clips_merging.py")
+        self.w_masked = config.get("w_masked", 0.4418)      # clip_generator.py:33-34
+        self.w_global = config.get("w_global", 0.1)
         self.model_card = config.get("model_card", "PE-Core-L14-336")
         cfg = (encoder.cfg if encoder is not None else None) or encoder_config or MODEL_CARDS.get(self.model_card)
         if cfg is None:
@@ -48,9 +55,15 @@ class CLIPGenerator:
                                                 max_masks=config.get("max_masks", 512), device=device)
         self.model = self.encoder                      # attribute the reference exposes
         self._tokenizer = tokenizer
-        if self.model_card.startswith("SigLIP"):
-            raise NotImplementedError("SigLIP similarity is part of the open_clip branch (not built)")
+        if self.embed_type in CROP_EMBED_TYPES and not self.encoder.has_pool_head:
+            self.encoder.install_pool_head(state_dict, pool_heads=getattr(cfg, "pool_heads", 8))
+        # clip_generator.py:54-72: SigLIP cards score with sigmoid(sim * exp(logit_scale) + logit_bias).  No SigLIP
+        # architecture is built in; the rule applies when a caller supplies such an encoder_config under a SigLIP card.
         self.similarity_args = ()
+        if self.model_card.startswith("SigLIP"):
+            if config.get("logit_scale") is None or config.get("logit_bias") is None:
+                raise NotImplementedError("SigLIP cards need `logit_scale` and `logit_bias` in the config")
+            self.similarity_args = (float(config["logit_scale"]), float(config["logit_bias"]))
         self._text_cache = {}
 
     @property
@@ -77,11 +90,16 @@ class CLIPGenerator:
     @torch.no_grad()
     def extract_clip(self, image: torch.Tensor, binary_maps: torch.Tensor, return_all: bool = False) -> torch.Tensor:
         """image [3,H,W] (or [H,W,3] uint8) range 0-255, binary_maps [N,H,W] -> [N, clip_dim] on the device
-        (clip_generator.py:125-135)."""
+        (clip_generator.py:125-158); [N,3,clip_dim] with return_all on the crop-based types."""
         if image.dim() == 3 and image.shape[0] == 3 and image.shape[-1] != 3:
             image = image.permute(1, 2, 0)
         image = image.to(self.encoder.device).round().to(torch.uint8) if image.dtype != torch.uint8 else image
-        return self.encoder.encode_regions(image.contiguous(), binary_maps)
+        if self.embed_type == "TextRegion":
+            return self.encoder.encode_regions(image.contiguous(), binary_maps)
+        if binary_maps.shape[0] == 0:
+            return torch.tensor([], device=self.encoder.device)          # clip_generator.py:141-142
+        return self.encoder.encode_crops(image.contiguous(), binary_maps, self.embed_type, mask_res=self.mask_res,
+                                         w_masked=self.w_masked, w_global=self.w_global, return_all=return_all)
 
     def _tokens(self, phrases: List[str]) -> torch.Tensor:
         return torch.cat([self.tokenizer(p) for p in phrases])
@@ -119,4 +137,7 @@ class CLIPGenerator:
         out = torch.empty(n, txt.shape[0], device=self.encoder.device, dtype=torch.float32)
         check(_lib.lib().ovo_query_instances(ptr(bank), ptr(rows), n, bank.shape[1], ptr(txt), txt.shape[0], ptr(out),
                                              stream_ptr()), "ovo_query_instances")
+        if self.similarity_args and out.numel() > 0:        # clip_utils.py:10-14
+            check(_lib.lib().ovo_siglip_similarity(ptr(out), out.numel(), self.similarity_args[0], self.similarity_args[1],
+                                                   stream_ptr()), "ovo_siglip_similarity")
         return out

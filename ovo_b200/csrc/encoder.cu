@@ -91,7 +91,7 @@ struct ImgJob {  // one 336x336 output image cut from a frame
 // horizontal anti-aliased pass: tmp[img][c][y][ox] = sum_k wx[ox][k] * src[y1+y][x1+xmin[ox]+k][c] / 255
 __global__ void aa_resize_h_kernel(const uint8_t* __restrict__ rgb, int H, int W, const ImgJob* __restrict__ jobs,
                                    const int* __restrict__ tab_min, const int* __restrict__ tab_size,
-                                   const float* __restrict__ tab_w, int S, float* __restrict__ tmp, int tmp_h) {
+                                   const float* __restrict__ tab_w, int S, float* __restrict__ tmp, int tmp_h, int slot0) {
   const ImgJob j = jobs[blockIdx.z];
   const int ox = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y;
@@ -106,7 +106,7 @@ __global__ void aa_resize_h_kernel(const uint8_t* __restrict__ rgb, int H, int W
     a1 += wk * (static_cast<float>(src[3 * k + 1]) / 255.f);
     a2 += wk * (static_cast<float>(src[3 * k + 2]) / 255.f);
   }
-  float* dst = tmp + (static_cast<size_t>(blockIdx.z) * 3 * tmp_h + y) * S + ox;
+  float* dst = tmp + (static_cast<size_t>(blockIdx.z + slot0) * 3 * tmp_h + y) * S + ox;
   dst[0] = a0;
   dst[static_cast<size_t>(tmp_h) * S] = a1;
   dst[static_cast<size_t>(2) * tmp_h * S] = a2;
@@ -116,18 +116,19 @@ __global__ void aa_resize_h_kernel(const uint8_t* __restrict__ rgb, int H, int W
 __global__ void aa_resize_v_patch_kernel(const float* __restrict__ tmp, int tmp_h, const ImgJob* __restrict__ jobs,
                                          const int* __restrict__ tab_min, const int* __restrict__ tab_size,
                                          const float* __restrict__ tab_w, int S, int patch, int kpad,
-                                         __nv_bfloat16* __restrict__ patches) {
+                                         __nv_bfloat16* __restrict__ patches, int slot0) {
   const ImgJob j = jobs[blockIdx.z];
+  const int slot = blockIdx.z + slot0;
   const int ox = blockIdx.x * blockDim.x + threadIdx.x;
   const int oy = blockIdx.y;
   if (ox >= S) return;
   const int ymin = tab_min[j.tab_y + oy], n = tab_size[j.tab_y + oy];
   const float* w = tab_w + static_cast<size_t>(j.tab_y + oy) * j.ky;
   const int grid = S / patch;
-  const int prow = blockIdx.z * grid * grid + (oy / patch) * grid + ox / patch;
+  const int prow = slot * grid * grid + (oy / patch) * grid + ox / patch;
   const int pcol = (oy % patch) * patch + ox % patch;
   for (int c = 0; c < 3; ++c) {
-    const float* src = tmp + ((static_cast<size_t>(blockIdx.z) * 3 + c) * tmp_h + ymin) * S + ox;
+    const float* src = tmp + ((static_cast<size_t>(slot) * 3 + c) * tmp_h + ymin) * S + ox;
     float a = 0.f;
     for (int k = 0; k < n; ++k) a += w[k] * src[static_cast<size_t>(k) * S];
     a = (a - 0.5f) / 0.5f;
@@ -315,6 +316,257 @@ __global__ void text_embed_kernel(const int32_t* __restrict__ tokens, int T, int
   }
 }
 
+// =========================================================================================== crop-based descriptors
+// CLIPGenerator.extract_clip, crop branch (ovo/entities/clip_generator.py:136-158): per mask a masked crop and a margin
+// crop (ovo/utils/segment_utils.py:29-182), each through the full encode_image (pe.py:535-543), then fuse_clips
+// (ovo/utils/clip_utils.py:21-48).
+
+// batched_mask_to_box + batched_box_xyxy_to_xywh (segment_utils.py:43-104): one block per mask; edges are the min / max set
+// row / column INDEX, so w = right - left, h = bottom - top (the reference's convention, kept); empty mask -> 0,0,0,0.
+__global__ void __launch_bounds__(256) mask_boxes_kernel(const uint8_t* __restrict__ masks, int H, int W, int32_t* __restrict__ xywh) {
+  const uint8_t* m = masks + static_cast<size_t>(blockIdx.x) * H * W;
+  int x0 = W, x1 = -1, y0 = H, y1 = -1;
+  const int n = H * W;
+  if ((W & 3) == 0 && (reinterpret_cast<uintptr_t>(m) & 3) == 0) {
+    const uint32_t* m4 = reinterpret_cast<const uint32_t*>(m);
+    for (int i = threadIdx.x; i < n / 4; i += blockDim.x) {
+      const uint32_t v = m4[i];
+      if (v == 0) continue;
+      const int y = (4 * i) / W, x = 4 * i - y * W;
+      const int lo = x + ((v & 0xffu) ? 0 : (v & 0xff00u) ? 1 : (v & 0xff0000u) ? 2 : 3);
+      const int hi = x + ((v & 0xff000000u) ? 3 : (v & 0xff0000u) ? 2 : (v & 0xff00u) ? 1 : 0);
+      x0 = min(x0, lo); x1 = max(x1, hi); y0 = min(y0, y); y1 = max(y1, y);
+    }
+  } else {
+    for (int i = threadIdx.x; i < n; i += blockDim.x)
+      if (m[i]) {
+        const int y = i / W, x = i - y * W;
+        x0 = min(x0, x); x1 = max(x1, x); y0 = min(y0, y); y1 = max(y1, y);
+      }
+  }
+  __shared__ int s[4][8];
+  for (int o = 16; o > 0; o >>= 1) {
+    x0 = min(x0, __shfl_xor_sync(0xffffffffu, x0, o)); x1 = max(x1, __shfl_xor_sync(0xffffffffu, x1, o));
+    y0 = min(y0, __shfl_xor_sync(0xffffffffu, y0, o)); y1 = max(y1, __shfl_xor_sync(0xffffffffu, y1, o));
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { s[0][warp] = x0; s[1][warp] = x1; s[2][warp] = y0; s[3][warp] = y1; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < (blockDim.x >> 5); ++i) {
+      x0 = min(x0, s[0][i]); x1 = max(x1, s[1][i]); y0 = min(y0, s[2][i]); y1 = max(y1, s[3][i]);
+    }
+    int32_t* o = xywh + 4 * blockIdx.x;
+    if (x1 < x0) { o[0] = o[1] = o[2] = o[3] = 0; }
+    else { o[0] = x0; o[1] = y0; o[2] = x1 - x0; o[3] = y1 - y0; }
+  }
+}
+
+// One crop = a virtual source image of vh x vw pixels: inside [oy, oy+h) x [ox, ox+w) it shows the frame rectangle at (x, y)
+// (times the mask when mask >= 0: get_seg_img, segment_utils.py:138-142), zero elsewhere (pad_img, :149-157).
+struct CropJob { int mask, x, y, w, h, ox, oy, vw, vh; };
+
+// torchvision F.resize weights of one crop (ATen _upsample_bilinear2d_aa), both axes: thread per output index
+__global__ void crop_tables_kernel(const CropJob* __restrict__ jobs, int L, int kmax, int* __restrict__ tab_min,
+                                   int* __restrict__ tab_size, float* __restrict__ tab_w) {
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= L) return;
+  const CropJob j = jobs[blockIdx.z];
+  const int axis = blockIdx.y;                              // 0 = x, 1 = y
+  const int n_in = axis == 0 ? j.vw : j.vh;
+  const double scale = static_cast<double>(n_in) / L;
+  const double support = scale > 1.0 ? scale : 1.0, inv = 1.0 / support;
+  const double center = scale * (o + 0.5);
+  const int lo = max(0, static_cast<int>(center - support + 0.5));
+  const int hi = min(n_in, static_cast<int>(center + support + 0.5));
+  const size_t e = (static_cast<size_t>(blockIdx.z) * 2 + axis) * L + o;
+  double total = 0.0;
+  for (int t = lo; t < hi; ++t) total += fmax(0.0, 1.0 - fabs((t - center + 0.5) * inv));
+  tab_min[e] = lo; tab_size[e] = min(hi - lo, kmax);
+  float* w = tab_w + e * kmax;
+  for (int t = lo; t < hi && t - lo < kmax; ++t) w[t - lo] = static_cast<float>(fmax(0.0, 1.0 - fabs((t - center + 0.5) * inv)) / total);
+}
+
+// F.resize(crop uint8, (L, L)) (segment_utils.py:131-135): f32 anti-aliased bilinear (horizontal taps first, like ATen's
+// separable passes), torch.round, uint8.  Output HWC so that the second resize + im2col (E1's kernels) reads it like a frame.
+__global__ void __launch_bounds__(128)
+    crop_resize_kernel(const uint8_t* __restrict__ rgb, int H, int W, const uint8_t* __restrict__ masks, const CropJob* __restrict__ jobs,
+                       int L, int kmax, const int* __restrict__ tab_min, const int* __restrict__ tab_size,
+                       const float* __restrict__ tab_w, uint8_t* __restrict__ out) {
+  const int ox = blockIdx.x * blockDim.x + threadIdx.x;
+  const int oy = blockIdx.y;
+  if (ox >= L) return;
+  const CropJob j = jobs[blockIdx.z];
+  const size_t ex = (static_cast<size_t>(blockIdx.z) * 2) * L + ox, ey = (static_cast<size_t>(blockIdx.z) * 2 + 1) * L + oy;
+  const int xmin = tab_min[ex], nx = tab_size[ex], ymin = tab_min[ey], ny = tab_size[ey];
+  const float* wx = tab_w + ex * kmax;
+  const float* wy = tab_w + ey * kmax;
+  const uint8_t* mk = j.mask >= 0 ? masks + static_cast<size_t>(j.mask) * H * W : nullptr;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+  for (int ky = 0; ky < ny; ++ky) {
+    const int vy = ymin + ky - j.oy;                          // row inside the crop rectangle
+    float h0 = 0.f, h1 = 0.f, h2 = 0.f;
+    if (vy >= 0 && vy < j.h) {
+      const size_t rowbase = static_cast<size_t>(j.y + vy) * W + j.x;
+      for (int kx = 0; kx < nx; ++kx) {
+        const int vx = xmin + kx - j.ox;
+        if (vx < 0 || vx >= j.w) continue;
+        if (mk && !mk[rowbase + vx]) continue;
+        const uint8_t* px = rgb + (rowbase + vx) * 3;
+        const float wk = wx[kx];
+        h0 += wk * static_cast<float>(px[0]);
+        h1 += wk * static_cast<float>(px[1]);
+        h2 += wk * static_cast<float>(px[2]);
+      }
+    }
+    const float wk = wy[ky];
+    a0 += wk * h0; a1 += wk * h1; a2 += wk * h2;
+  }
+  uint8_t* o = out + ((static_cast<size_t>(blockIdx.z) * L + oy) * L + ox) * 3;
+  o[0] = static_cast<uint8_t>(min(max(__float2int_rn(a0), 0), 255));
+  o[1] = static_cast<uint8_t>(min(max(__float2int_rn(a1), 0), 255));
+  o[2] = static_cast<uint8_t>(min(max(__float2int_rn(a2), 0), 255));
+}
+
+__global__ void f32_to_bf16_kernel(const float* __restrict__ x, size_t n4, __nv_bfloat16* __restrict__ o) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const float4 v = reinterpret_cast<const float4*>(x)[i];
+  uint2 u;
+  u.x = pack_bf16(v.x, v.y); u.y = pack_bf16(v.z, v.w);
+  reinterpret_cast<uint2*>(o)[i] = u;
+}
+
+// AttentionPooling's attention (pe.py:81-84): ONE learned query per head against all tokens of an image.
+// kv f32 [n*seq, 2*width] (k | v), q f32 [width] already scaled by head_dim^-0.5.  grid (n_img, heads), 256 threads.
+__global__ void __launch_bounds__(256)
+    pool_attention_kernel(const float* __restrict__ kv, const float* __restrict__ q, int seq, int width, int hd,
+                          __nv_bfloat16* __restrict__ out) {
+  extern __shared__ float sm[];            // [seq] scores, then [256] partial sums
+  float* sc = sm;
+  float* red = sm + seq;
+  __shared__ float s_stat[2];
+  const int img = blockIdx.x, head = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  const float* base = kv + static_cast<size_t>(img) * seq * 2 * width + head * hd;
+  const float* qh = q + head * hd;
+  for (int j = warp; j < seq; j += nwarp) {
+    const float* k = base + static_cast<size_t>(j) * 2 * width;
+    float d = 0.f;
+    for (int i = lane; i < hd; i += 32) d += qh[i] * k[i];
+    for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+    if (lane == 0) sc[j] = d;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    float mx = -INFINITY;
+    for (int j = lane; j < seq; j += 32) mx = fmaxf(mx, sc[j]);
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+    for (int j = lane; j < seq; j += 32) { const float p = expf(sc[j] - mx); sc[j] = p; sum += p; }
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0) { s_stat[0] = mx; s_stat[1] = sum; }
+  }
+  __syncthreads();
+  const float inv = 1.f / s_stat[1];
+  const int slices = static_cast<int>(blockDim.x) / hd;   // hd <= blockDim.x (checked by the host)
+  const int d = static_cast<int>(threadIdx.x) % hd, slice = static_cast<int>(threadIdx.x) / hd;
+  float acc = 0.f;
+  if (slice < slices) {
+    const float* v = base + width + d;
+    for (int j = slice; j < seq; j += slices) acc += sc[j] * v[static_cast<size_t>(j) * 2 * width];
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  if (slice == 0) {
+    for (int sidx = 1; sidx < slices; ++sidx) acc += red[sidx * hd + d];
+    out[static_cast<size_t>(img) * width + head * hd + d] = __float2bfloat16_rn(acc * inv);
+  }
+}
+
+// fuse_clips (clip_utils.py:21-48) for the crops of ONE frame: g [D] (the frame's global descriptor, repeated per mask at
+// clip_generator.py:153), seg / bbox [M, D], all unit norm.  One block; warps stride over the masks; the soft-max of the
+// `hovsg` / `concept_fusion` types runs ACROSS the masks of the frame (dim=0), so the cosines are staged in shared memory.
+// embed_type: 1 fixed_weights, 2 hovsg, 3 adaptive_weights, 4 concept_fusion.
+__device__ __forceinline__ float warp_sum(float v) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__global__ void __launch_bounds__(1024)
+    fuse_clips_kernel(const float* __restrict__ g, const float* __restrict__ seg, const float* __restrict__ bbox, int M, int D,
+                      int embed_type, float w_masked, float w_global, float* __restrict__ out) {
+  extern __shared__ float s_cos[];          // [M]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  const float eps = 1e-6f;                  // torch.nn.CosineSimilarity(eps=1e-6)
+  float gg = 0.f;
+  for (int d = lane; d < D; d += 32) gg += g[d] * g[d];
+  const float gn = fmaxf(sqrtf(warp_sum(gg)), eps);
+  for (int m = warp; m < M; m += nwarp) {
+    const float* s = seg + static_cast<size_t>(m) * D;
+    const float* b = bbox + static_cast<size_t>(m) * D;
+    float* o = out + static_cast<size_t>(m) * D;
+    float wl = w_masked;
+    if (embed_type == 3) {
+      float sb = 0.f, ss = 0.f, bb = 0.f;
+      for (int d = lane; d < D; d += 32) { sb += s[d] * b[d]; ss += s[d] * s[d]; bb += b[d] * b[d]; }
+      sb = warp_sum(sb); ss = warp_sum(ss); bb = warp_sum(bb);
+      wl = sb / (fmaxf(sqrtf(ss), eps) * fmaxf(sqrtf(bb), eps)) * w_masked;
+    }
+    float ll = 0.f, gl = 0.f;
+    for (int d = lane; d < D; d += 32) {
+      const float l = embed_type == 4 ? b[d] : s[d] * wl + b[d] * (1.f - wl);
+      o[d] = l;
+      ll += l * l; gl += g[d] * l;
+    }
+    ll = warp_sum(ll); gl = warp_sum(gl);
+    const float ln = sqrtf(ll);
+    if (embed_type != 4) {                  // clip_l = normalize(...): F.normalize eps 1e-12
+      const float inv = 1.f / fmaxf(ln, 1e-12f);
+      for (int d = lane; d < D; d += 32) o[d] *= inv;
+      gl *= inv; ll = ll * inv * inv;
+    }
+    if (lane == 0) s_cos[m] = gl / (gn * fmaxf(sqrtf(ll), eps));
+  }
+  __syncthreads();
+  float mx = -INFINITY, den = 1.f;
+  if (embed_type == 2 || embed_type == 4) {
+    for (int m = lane; m < M; m += 32) mx = fmaxf(mx, s_cos[m]);
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+    for (int m = lane; m < M; m += 32) sum += expf(s_cos[m] - mx);
+    den = warp_sum(sum);
+  }
+  for (int m = warp; m < M; m += nwarp) {
+    float* o = out + static_cast<size_t>(m) * D;
+    float wg = w_global;
+    if (embed_type == 2 || embed_type == 4) wg = expf(s_cos[m] - mx) / den;
+    else if (embed_type == 3) wg = s_cos[m] * w_global;
+    float ss = 0.f;
+    for (int d = lane; d < D; d += 32) {
+      const float v = g[d] * wg + o[d] * (1.f - wg);
+      o[d] = v; ss += v * v;
+    }
+    const float inv = 1.f / fmaxf(sqrtf(warp_sum(ss)), 1e-12f);
+    for (int d = lane; d < D; d += 32) o[d] *= inv;
+  }
+}
+
+// return_all (clip_generator.py:151-152): out [M,3,D] = (global, masked crop, margin crop)
+__global__ void stack_clips_kernel(const float* __restrict__ g, const float* __restrict__ seg, const float* __restrict__ bbox,
+                                   int M, int D, float* __restrict__ out) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<size_t>(M) * 3 * D) return;
+  const int d = i % D, k = (i / D) % 3;
+  const size_t m = i / (static_cast<size_t>(3) * D);
+  out[i] = k == 0 ? g[d] : k == 1 ? seg[m * D + d] : bbox[m * D + d];
+}
+
+// siglip_cosine_similarity (clip_utils.py:10-14): sim <- sigmoid(sim * exp(logit_scale) + logit_bias), in place
+__global__ void sigmoid_affine_kernel(float* __restrict__ sim, size_t n, float scale, float bias) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) sim[i] = 1.f / (1.f + expf(-(sim[i] * scale + bias)));
+}
+
 }  // namespace ovo
 
 // =============================================================================================== handle
@@ -359,6 +611,19 @@ struct ovo_encoder {
   std::map<long long, GraphEntry> graphs;
   bool use_graphs = true;
   cudaStream_t cap_stream = nullptr;  // capture happens here (the caller's stream may be the legacy stream)
+  // crop-based descriptors (ovo_encoder_set_pool_head / ovo_encode_crops)
+  bool has_head = false;
+  ovo_pool_head_weights head{};
+  float *ph_x1 = nullptr, *ph_x2 = nullptr, *ph_emb = nullptr;
+  __nv_bfloat16 *ph_a = nullptr, *ph_h = nullptr;
+  int32_t* crop_boxes = nullptr;
+  CropJob* crop_jobs = nullptr;
+  std::vector<CropJob> crop_jobs_host;
+  uint8_t* crop_u8 = nullptr;
+  size_t crop_u8_cap = 0;
+  int *ctab_min = nullptr, *ctab_size = nullptr;
+  float* ctab_w = nullptr;
+  size_t ctab_cap = 0, ctab_wcap = 0;
 };
 
 int g_attn_debug = 0;   // tuning experiments (attention.cuh dbg bits), set through ovo_set_gemm_cluster bits 24..31
@@ -569,8 +834,8 @@ int ovo_encoder_create(const ovo_vit_cfg* cfg, const ovo_vit_weights* w, int max
   r |= dmalloc(&e->tab_min, static_cast<size_t>(e->tab_cap));
   r |= dmalloc(&e->tab_size, static_cast<size_t>(e->tab_cap));
   r |= dmalloc(&e->tab_w, static_cast<size_t>(e->tab_wcap));
-  e->jobs_cap = max_images;
-  r |= dmalloc(&e->jobs_dev, static_cast<size_t>(max_images));
+  e->jobs_cap = max_images + 1;   // + the frame's global image of the crop-based path
+  r |= dmalloc(&e->jobs_dev, static_cast<size_t>(max_images) + 1);
   if (r != OVO_OK) { ovo_encoder_destroy(e); return OVO_E_NOMEM; }
 
   // 2D RoPE table (rope.py:315-340): both axes share theta_i = 10000^(-2i/32); row r holds
@@ -614,6 +879,8 @@ void ovo_encoder_destroy(ovo_encoder_t* e) {
   cudaFree(e->q); cudaFree(e->k); cudaFree(e->vt); cudaFree(e->rope_tab); cudaFree(e->canvas); cudaFree(e->qkv_f32); cudaFree(e->rope_gen);
   cudaFree(e->fmask); cudaFree(e->mean_acc); cudaFree(e->groups_dev); cudaFree(e->fcnt); cudaFree(e->mean); cudaFree(e->resize_tmp); cudaFree(e->eot_rows);
   cudaFree(e->pooled_in); cudaFree(e->tab_min); cudaFree(e->tab_size); cudaFree(e->tab_w); cudaFree(e->jobs_dev);
+  cudaFree(e->ph_x1); cudaFree(e->ph_x2); cudaFree(e->ph_emb); cudaFree(e->ph_a); cudaFree(e->ph_h); cudaFree(e->crop_boxes);
+  cudaFree(e->crop_jobs); cudaFree(e->crop_u8); cudaFree(e->ctab_min); cudaFree(e->ctab_size); cudaFree(e->ctab_w);
   delete e;
 }
 
@@ -649,9 +916,9 @@ int ovo_encoder_preprocess(ovo_encoder_t* e, const uint8_t* rgb_dev, int n_frame
     OVO_CUDA(cudaStreamSynchronize(s));
   }
   ProfScope prof(s, PROF_PRE, 0.0, static_cast<double>(n_frames) * H * W * 3 + static_cast<double>(n_img) * e->patches * e->w.patch_kpad * 2);
-  aa_resize_h_kernel<<<dim3(ceil_div(S, 128), H, n_img), 128, 0, s>>>(rgb_dev, H, W, e->jobs_dev, e->tab_min, e->tab_size, e->tab_w, S, e->resize_tmp, e->max_h);
+  aa_resize_h_kernel<<<dim3(ceil_div(S, 128), H, n_img), 128, 0, s>>>(rgb_dev, H, W, e->jobs_dev, e->tab_min, e->tab_size, e->tab_w, S, e->resize_tmp, e->max_h, 0);
   OVO_CHECK_LAUNCH();
-  aa_resize_v_patch_kernel<<<dim3(ceil_div(S, 128), S, n_img), 128, 0, s>>>(e->resize_tmp, e->max_h, e->jobs_dev, e->tab_min, e->tab_size, e->tab_w, S, e->cfg.patch_size, e->w.patch_kpad, e->patch_buf);
+  aa_resize_v_patch_kernel<<<dim3(ceil_div(S, 128), S, n_img), 128, 0, s>>>(e->resize_tmp, e->max_h, e->jobs_dev, e->tab_min, e->tab_size, e->tab_w, S, e->cfg.patch_size, e->w.patch_kpad, e->patch_buf, 0);
   OVO_CHECK_LAUNCH();
   e->loaded_images = n_img;
   if (n_img_per_frame) *n_img_per_frame = per;
@@ -810,6 +1077,249 @@ int ovo_text_bank(ovo_encoder_t* e, const int32_t* tokens_dev, int Q, int T, flo
     const int qn = std::min(qchunk, Q - q0);
     OVO_TRY(ovo_encode_text(e, tokens_dev + static_cast<size_t>(q0) * T * e->cfg.text_ctx, qn * T, emb, stream_));
     text_bank_kernel<<<ceil_div(qn, 8), 256, 0, s>>>(emb, qn, T, D, out_dev + static_cast<size_t>(q0) * D);
+    OVO_CHECK_LAUNCH();
+  }
+  return OVO_OK;
+}
+
+// ------------------------------------------------------------------------------------------- crop-based descriptors
+int ovo_encoder_set_pool_head(ovo_encoder_t* e, const ovo_pool_head_weights* w) {
+  OVO_REQUIRE(e && w, "ovo_encoder_set_pool_head: null argument");
+  const ovo_vit_cfg& c = e->cfg;
+  OVO_REQUIRE(w->heads > 0 && c.width % w->heads == 0 && c.width / w->heads <= 256, "pool head: heads %d unsupported for width %d", w->heads, c.width);
+  OVO_REQUIRE(w->mlp_width > 0 && w->mlp_width % 8 == 0, "pool head: bad mlp_width %d", w->mlp_width);
+  OVO_REQUIRE(w->q && w->kv_w && w->kv_b && w->out_w && w->out_b && w->ln_w && w->ln_b && w->fc_w && w->fc_b && w->proj_w && w->proj_b && w->vis_proj_w,
+              "pool head: null weight pointer");
+  // keys | values of every token live (f32) in the MLP's hidden buffer: [rows, 2*width] f32 <= [rows, mlp] bf16
+  OVO_REQUIRE(std::max(c.mlp_width, c.text_mlp_width) >= 4 * c.width, "pool head: hidden buffer too small for the key/value projections");
+  if (!e->ph_x1) {
+    const size_t rows = static_cast<size_t>(e->max_images) + 128;
+    int r = OVO_OK;
+    r |= dmalloc(&e->ph_x1, rows * c.width);
+    r |= dmalloc(&e->ph_x2, rows * c.width);
+    r |= dmalloc(&e->ph_a, rows * c.width);
+    r |= dmalloc(&e->ph_h, rows * w->mlp_width);
+    r |= dmalloc(&e->ph_emb, (static_cast<size_t>(2) * e->max_masks + 1 + 128) * c.output_dim);
+    r |= dmalloc(&e->crop_boxes, static_cast<size_t>(e->max_masks) * 4);
+    r |= dmalloc(&e->crop_jobs, static_cast<size_t>(2) * e->max_masks);
+    if (r != OVO_OK) return OVO_E_NOMEM;
+  }
+  e->head = *w;
+  e->has_head = true;
+  return OVO_OK;
+}
+
+// pe.py:493 (attn_pool) + :540-541 (@ proj) on the n images of the last forward (tokens after ln_post in xfinal)
+static int pool_head(ovo_encoder* e, int n, float* out, cudaStream_t s) {
+  const ovo_vit_cfg& c = e->cfg;
+  const ovo_pool_head_weights& h = e->head;
+  const int W = c.width, rows = n * e->seq, hd = W / h.heads, mlp = h.mlp_width;
+  typedef const __nv_bfloat16* bfp;
+  {
+    const size_t n4 = static_cast<size_t>(rows) * W / 4;
+    f32_to_bf16_kernel<<<ceil_div(n4, 256), 256, 0, s>>>(e->xfinal, n4, e->xn);
+    OVO_CHECK_LAUNCH();
+  }
+  float* kv = reinterpret_cast<float*>(e->hmid);
+  EpiParams kp;
+  kp.out = kv; kp.ldo = 2 * W; kp.bias = h.kv_b;
+  OVO_TRY(launch_gemm(EPI_F32, e->xn, W, static_cast<bfp>(h.kv_w), W, rows, 2 * W, W, kp, s));
+  {
+    ProfScope prof(s, PROF_POOL, 4.0 * n * e->seq * W, static_cast<double>(rows) * 2 * W * 4);
+    pool_attention_kernel<<<dim3(n, h.heads), 256, (e->seq + 256) * sizeof(float), s>>>(kv, h.q, e->seq, W, hd, e->ph_a);
+    OVO_CHECK_LAUNCH();
+  }
+  EpiParams op;
+  op.out = e->ph_x1; op.ldo = W; op.bias = h.out_b;
+  OVO_TRY(launch_gemm(EPI_F32, e->ph_a, W, static_cast<bfp>(h.out_w), W, n, W, W, op, s));
+  OVO_TRY(launch_ln(e->ph_x1, n, W, h.ln_w, h.ln_b, c.ln_eps, e->ph_a, nullptr, nullptr, s));
+  EpiParams fc;
+  fc.out = e->ph_h; fc.ldo = mlp; fc.bias = h.fc_b;
+  OVO_TRY(launch_gemm(EPI_BF16_GELU, e->ph_a, W, static_cast<bfp>(h.fc_w), W, n, mlp, W, fc, s));
+  EpiParams pj;
+  pj.out = e->ph_x2; pj.ldo = W; pj.bias = h.proj_b; pj.resid = e->ph_x1; pj.ldr = W;
+  OVO_TRY(launch_gemm(EPI_F32_RESID, e->ph_h, mlp, static_cast<bfp>(h.proj_w), mlp, n, W, mlp, pj, s));
+  {
+    const size_t n4 = static_cast<size_t>(n) * W / 4;
+    f32_to_bf16_kernel<<<ceil_div(n4, 256), 256, 0, s>>>(e->ph_x2, n4, e->ph_a);
+    OVO_CHECK_LAUNCH();
+  }
+  EpiParams vp;
+  vp.out = out; vp.ldo = c.output_dim;
+  OVO_TRY(launch_gemm(EPI_F32, e->ph_a, W, static_cast<bfp>(h.vis_proj_w), W, n, c.output_dim, W, vp, s));
+  return OVO_OK;
+}
+
+int ovo_encode_images(ovo_encoder_t* e, const float* pixels_dev, int n, float* out_dev, void* stream) {
+  OVO_REQUIRE(e && pixels_dev && out_dev && n > 0, "ovo_encode_images: bad arguments");
+  OVO_REQUIRE(e->has_head, "ovo_encode_images: call ovo_encoder_set_pool_head first");
+  OVO_TRY(ovo_encoder_load_pixels(e, pixels_dev, n, stream));
+  OVO_TRY(ovo_encoder_forward(e, n, -1, 1, nullptr, stream));
+  return pool_head(e, n, out_dev, static_cast<cudaStream_t>(stream));
+}
+
+int ovo_mask_boxes(const uint8_t* masks_dev, int M, int H, int W, int32_t* xywh_dev, void* stream) {
+  OVO_REQUIRE(masks_dev && xywh_dev && M > 0 && H > 0 && W > 0, "ovo_mask_boxes: bad arguments");
+  mask_boxes_kernel<<<M, 256, 0, static_cast<cudaStream_t>(stream)>>>(masks_dev, H, W, xywh_dev);
+  OVO_CHECK_LAUNCH();
+  return OVO_OK;
+}
+
+int ovo_fuse_clips(const float* g_dev, const float* seg_dev, const float* bbox_dev, int M, int D, int embed_type,
+                   float w_masked, float w_global, float* out_dev, void* stream) {
+  OVO_REQUIRE(g_dev && seg_dev && bbox_dev && out_dev && M > 0 && D > 0, "ovo_fuse_clips: bad arguments");
+  OVO_REQUIRE(embed_type >= OVO_EMBED_FIXED_WEIGHTS && embed_type <= OVO_EMBED_CONCEPT_FUSION, "ovo_fuse_clips: embed_type %d has no fusion rule", embed_type);
+  OVO_REQUIRE(M <= 10000, "ovo_fuse_clips: at most 10000 masks per frame");
+  fuse_clips_kernel<<<1, 1024, M * sizeof(float), static_cast<cudaStream_t>(stream)>>>(g_dev, seg_dev, bbox_dev, M, D, embed_type, w_masked, w_global, out_dev);
+  OVO_CHECK_LAUNCH();
+  return OVO_OK;
+}
+
+int ovo_siglip_similarity(float* sim_dev, int64_t n, float logit_scale, float logit_bias, void* stream) {
+  OVO_REQUIRE(sim_dev && n > 0, "ovo_siglip_similarity: bad arguments");
+  sigmoid_affine_kernel<<<ceil_div(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(sim_dev, static_cast<size_t>(n), expf(logit_scale), logit_bias);
+  OVO_CHECK_LAUNCH();
+  return OVO_OK;
+}
+
+}  // extern "C"
+
+template <typename T>
+static int grow(T** p, size_t* cap, size_t need) {
+  if (*cap >= need) return OVO_OK;
+  cudaDeviceSynchronize();   // the old buffer may still be in use by queued kernels
+  cudaFree(*p);
+  *p = nullptr; *cap = 0;
+  if (cudaMalloc(reinterpret_cast<void**>(p), need * sizeof(T)) != cudaSuccess) {
+    cudaGetLastError();
+    return set_error(OVO_E_NOMEM, "crop workspace allocation of %zu bytes failed", need * sizeof(T));
+  }
+  *cap = need;
+  return OVO_OK;
+}
+
+extern "C" {
+
+int ovo_encode_crops(ovo_encoder_t* e, const uint8_t* rgb_dev, int H, int W, const uint8_t* masks_dev, int M,
+                     const ovo_crop_params* prm, float* out_dev, uint8_t* crops_out_dev, void* stream_) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream_);
+  OVO_REQUIRE(e && rgb_dev && masks_dev && prm && out_dev, "ovo_encode_crops: null argument");
+  OVO_REQUIRE(e->has_head, "ovo_encode_crops: call ovo_encoder_set_pool_head first");
+  OVO_REQUIRE(M > 0 && M <= e->max_masks, "ovo_encode_crops: M=%d outside (0, %d]", M, e->max_masks);
+  OVO_REQUIRE(H > 0 && W > 0 && H <= e->max_h && W <= e->max_w, "frame %dx%d exceeds encoder limits %dx%d", H, W, e->max_h, e->max_w);
+  OVO_REQUIRE(prm->embed_type >= OVO_EMBED_VANILLA && prm->embed_type <= OVO_EMBED_CONCEPT_FUSION, "ovo_encode_crops: unknown embed_type %d", prm->embed_type);
+  const int L = prm->mask_res, S = e->cfg.image_size, D = e->cfg.output_dim;
+  OVO_REQUIRE(L > 0 && L <= e->max_h && L <= 2048, "ovo_encode_crops: mask_res %d outside (0, min(max_h, 2048)]", L);
+  const bool vanilla = prm->embed_type == OVO_EMBED_VANILLA;
+
+  // 1. boxes -> host (they decide the geometry of every crop; the one synchronisation of this path)
+  mask_boxes_kernel<<<M, 256, 0, s>>>(masks_dev, H, W, e->crop_boxes);
+  OVO_CHECK_LAUNCH();
+  std::vector<int32_t> bx(static_cast<size_t>(M) * 4);
+  OVO_CUDA(cudaMemcpyAsync(bx.data(), e->crop_boxes, bx.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  OVO_CUDA(cudaStreamSynchronize(s));
+
+  // 2. crop jobs: masked crops first, then margin crops (clip_generator.py:148)
+  std::vector<CropJob>& jobs = e->crop_jobs_host;
+  jobs.clear();
+  int maxdim = 1;
+  for (int m = 0; m < M; ++m) {
+    const int x = bx[4 * m], y = bx[4 * m + 1], w = bx[4 * m + 2], h = bx[4 * m + 3];
+    if (vanilla) {   // pad_img (segment_utils.py:149-157): centred in a zero square of side max(w, h)
+      const int side = std::max(w, h);
+      OVO_REQUIRE(side > 0, "mask %d: empty crop (box %dx%d); the reference's F.resize raises here", m, w, h);
+      jobs.push_back({m, x, y, w, h, h > w ? (h - w) / 2 : 0, h > w ? 0 : (w - h) / 2, side, side});
+    } else {
+      OVO_REQUIRE(w > 0 && h > 0, "mask %d: empty crop (box %dx%d); the reference's F.resize raises here", m, w, h);
+      jobs.push_back({m, x, y, w, h, 0, 0, w, h});
+    }
+    maxdim = std::max(maxdim, std::max(jobs.back().vw, jobs.back().vh));
+  }
+  if (!vanilla)
+    for (int m = 0; m < M; ++m) {   // increase_bbox_by_margin (segment_utils.py:159-182); slicing clamps right / bottom
+      int x = bx[4 * m] - prm->bbox_margin, y = bx[4 * m + 1] - prm->bbox_margin;
+      int w = bx[4 * m + 2] + 2 * prm->bbox_margin, h = bx[4 * m + 3] + 2 * prm->bbox_margin;
+      if (x < 0) { w += x; x = 0; }
+      if (y < 0) { h += y; y = 0; }
+      w = std::min(x + w, W) - x; h = std::min(y + h, H) - y;
+      OVO_REQUIRE(w > 0 && h > 0, "mask %d: empty margin crop", m);
+      jobs.push_back({-1, x, y, w, h, 0, 0, w, h});
+      maxdim = std::max(maxdim, std::max(w, h));
+    }
+  const int n_crops = static_cast<int>(jobs.size()), has_g = vanilla ? 0 : 1, n_total = n_crops + has_g;
+  const int kmax = static_cast<int>(std::ceil(std::max(static_cast<double>(maxdim) / L, 1.0))) * 2 + 1;
+  const int cmax = e->max_images;
+  OVO_CUDA(cudaMemcpyAsync(e->crop_jobs, jobs.data(), jobs.size() * sizeof(CropJob), cudaMemcpyHostToDevice, s));
+  OVO_TRY(grow(&e->crop_u8, &e->crop_u8_cap, static_cast<size_t>(cmax) * L * L * 3));
+  {
+    size_t cap = e->ctab_cap;
+    OVO_TRY(grow(&e->ctab_min, &cap, static_cast<size_t>(cmax) * 2 * L));
+    cap = e->ctab_cap;
+    OVO_TRY(grow(&e->ctab_size, &cap, static_cast<size_t>(cmax) * 2 * L));
+    e->ctab_cap = cap;
+    OVO_TRY(grow(&e->ctab_w, &e->ctab_wcap, static_cast<size_t>(cmax) * 2 * L * kmax));
+  }
+  // second stage (the encoder's own Resize((S,S)) + Normalize, clip_generator.py:119): E1's kernels read the uint8
+  // crops like frames of L x L pixels; the frame's global image is job 0
+  AaTable tl, tgx, tgy;
+  OVO_TRY(get_table(e, L, &tl, s));
+  OVO_TRY(get_table(e, W, &tgx, s));
+  OVO_TRY(get_table(e, H, &tgy, s));
+  {
+    std::vector<ImgJob>& ij = e->jobs_host;
+    ij.clear();
+    ij.push_back({0, 0, 0, H, W, tgx.offset, tgy.offset, tgx.k, tgy.k});
+    for (int k = 0; k < cmax; ++k) ij.push_back({k, 0, 0, L, L, tl.offset, tl.offset, tl.k, tl.k});
+    OVO_CUDA(cudaMemcpyAsync(e->jobs_dev, ij.data(), ij.size() * sizeof(ImgJob), cudaMemcpyHostToDevice, s));
+    OVO_CUDA(cudaStreamSynchronize(s));
+    ij.clear();   // not the job list ovo_encoder_preprocess caches: force its next upload
+  }
+  const int patch = e->cfg.patch_size, kpad = e->w.patch_kpad;
+  for (int i0 = 0; i0 < n_total;) {
+    const int n = std::min(cmax, n_total - i0);
+    const int g_here = (has_g && i0 == 0) ? 1 : 0;
+    const int nc = n - g_here, c0 = i0 + g_here - has_g;
+    if (nc > 0) {
+      ProfScope prof(s, PROF_PRE, 0.0, static_cast<double>(nc) * L * L * 3 * 2);
+      crop_tables_kernel<<<dim3(ceil_div(L, 128), 2, nc), 128, 0, s>>>(e->crop_jobs + c0, L, kmax, e->ctab_min, e->ctab_size, e->ctab_w);
+      OVO_CHECK_LAUNCH();
+      crop_resize_kernel<<<dim3(ceil_div(L, 128), L, nc), 128, 0, s>>>(rgb_dev, H, W, masks_dev, e->crop_jobs + c0, L, kmax, e->ctab_min,
+                                                                      e->ctab_size, e->ctab_w, e->crop_u8);
+      OVO_CHECK_LAUNCH();
+      if (crops_out_dev)
+        OVO_CUDA(cudaMemcpyAsync(crops_out_dev + static_cast<size_t>(c0) * L * L * 3, e->crop_u8, static_cast<size_t>(nc) * L * L * 3,
+                                 cudaMemcpyDeviceToDevice, s));
+      aa_resize_h_kernel<<<dim3(ceil_div(S, 128), L, nc), 128, 0, s>>>(e->crop_u8, L, L, e->jobs_dev + 1, e->tab_min, e->tab_size, e->tab_w, S,
+                                                                      e->resize_tmp, e->max_h, g_here);
+      OVO_CHECK_LAUNCH();
+      aa_resize_v_patch_kernel<<<dim3(ceil_div(S, 128), S, nc), 128, 0, s>>>(e->resize_tmp, e->max_h, e->jobs_dev + 1, e->tab_min, e->tab_size,
+                                                                            e->tab_w, S, patch, kpad, e->patch_buf, g_here);
+      OVO_CHECK_LAUNCH();
+    }
+    if (g_here) {
+      aa_resize_h_kernel<<<dim3(ceil_div(S, 128), H, 1), 128, 0, s>>>(rgb_dev, H, W, e->jobs_dev, e->tab_min, e->tab_size, e->tab_w, S,
+                                                                     e->resize_tmp, e->max_h, 0);
+      OVO_CHECK_LAUNCH();
+      aa_resize_v_patch_kernel<<<dim3(ceil_div(S, 128), S, 1), 128, 0, s>>>(e->resize_tmp, e->max_h, e->jobs_dev, e->tab_min, e->tab_size,
+                                                                           e->tab_w, S, patch, kpad, e->patch_buf, 0);
+      OVO_CHECK_LAUNCH();
+    }
+    e->loaded_images = n;
+    OVO_TRY(ovo_encoder_forward(e, n, -1, 1, nullptr, stream_));
+    OVO_TRY(pool_head(e, n, e->ph_emb + static_cast<size_t>(i0) * D, s));
+    i0 += n;
+  }
+  l2_normalize_kernel<<<ceil_div(n_total, 8), 256, 0, s>>>(e->ph_emb, n_total, D, nullptr, nullptr);
+  OVO_CHECK_LAUNCH();
+  if (vanilla) {
+    OVO_CUDA(cudaMemcpyAsync(out_dev, e->ph_emb, static_cast<size_t>(M) * D * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  } else if (prm->return_all) {
+    stack_clips_kernel<<<ceil_div(static_cast<long long>(M) * 3 * D, 256), 256, 0, s>>>(e->ph_emb, e->ph_emb + D, e->ph_emb + static_cast<size_t>(1 + M) * D, M, D, out_dev);
+    OVO_CHECK_LAUNCH();
+  } else if (prm->embed_type == OVO_EMBED_VANILLA) {
+  } else {
+    fuse_clips_kernel<<<1, 1024, M * sizeof(float), s>>>(e->ph_emb, e->ph_emb + D, e->ph_emb + static_cast<size_t>(1 + M) * D, M, D, prm->embed_type,
+                                                        prm->w_masked, prm->w_global, out_dev);
     OVO_CHECK_LAUNCH();
   }
   return OVO_OK;

@@ -10,7 +10,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import VitCfg, VitWeights, BlockWeights, check, ptr, stream_ptr
+from ._lib import VitCfg, VitWeights, BlockWeights, PoolHeadWeights, CropParams, EMBED_TYPES, check, ptr, stream_ptr
 
 
 @dataclass
@@ -31,6 +31,7 @@ class EncoderConfig:
     text_mlp_width: int = 4096
     vocab_size: int = 49408
     text_output_dim: int = 1024
+    pool_heads: int = 8          # attn_pooler_heads of the attention-pooling head (config.py:46)
 
     @property
     def grid(self):
@@ -112,6 +113,9 @@ class RegionEncoder:
                   "ovo_encoder_create")
         self.handle = h
         self.max_images, self.max_masks = max_images, max_masks
+        self.has_pool_head = False
+        self._sd_for_head = ({k: v for k, v in state_dict.items() if k.startswith("visual.attn_pool.") or k == "visual.proj"}
+                             if "visual.attn_pool.probe" in state_dict else None)
 
     # ------------------------------------------------------------------ weights
     def _dev(self, t, dtype):
@@ -216,6 +220,64 @@ class RegionEncoder:
         check(self.lib.ovo_encode_regions(self.handle, ptr(rgb_u8), F_, H, W, ptr(m8), arr, ptr(out), stream_ptr()),
               "ovo_encode_regions")
         return out
+
+    # ------------------------------------------------------------------ crop-based descriptors
+    def install_pool_head(self, state_dict: dict | None = None, pool_heads: int = 8) -> None:
+        """Packs `visual.attn_pool.*` + `visual.proj` (pe.py:44-87,540-541) for `encode_image`.  The probe is a
+        parameter, so its query projection (pe.py:83-84) is folded here once, in float64."""
+        sd = state_dict or self._sd_for_head
+        if sd is None or "visual.attn_pool.probe" not in sd:
+            raise RuntimeError("state_dict lacks visual.attn_pool.probe / layernorm / mlp: the crop-based embed types "
+                               "need the full attention-pooling head")
+        f32, bf = torch.float32, torch.bfloat16
+        W = self.cfg.width
+        p = "visual.attn_pool."
+        ipw, ipb = sd[p + "attn.in_proj_weight"].detach().cpu(), sd[p + "attn.in_proj_bias"].detach().cpu()
+        hd = W // pool_heads
+        q = (sd[p + "probe"].detach().double().cpu().reshape(1, W) @ ipw[:W].double().T + ipb[:W].double()) * hd ** -0.5
+        w = PoolHeadWeights()
+        w.heads, w.mlp_width = pool_heads, sd[p + "mlp.c_fc.weight"].shape[0]
+        w.q = ptr(self._dev(q.reshape(W).float(), f32))
+        w.kv_w = ptr(self._dev(ipw[W:], bf)); w.kv_b = ptr(self._dev(ipb[W:], f32))
+        w.out_w = ptr(self._dev(sd[p + "attn.out_proj.weight"], bf)); w.out_b = ptr(self._dev(sd[p + "attn.out_proj.bias"], f32))
+        w.ln_w = ptr(self._dev(sd[p + "layernorm.weight"], f32)); w.ln_b = ptr(self._dev(sd[p + "layernorm.bias"], f32))
+        w.fc_w = ptr(self._dev(sd[p + "mlp.c_fc.weight"], bf)); w.fc_b = ptr(self._dev(sd[p + "mlp.c_fc.bias"], f32))
+        w.proj_w = ptr(self._dev(sd[p + "mlp.c_proj.weight"], bf)); w.proj_b = ptr(self._dev(sd[p + "mlp.c_proj.bias"], f32))
+        w.vis_proj_w = ptr(self._dev(sd["visual.proj"].detach().float().T, bf))
+        with torch.cuda.device(self.device):
+            check(self.lib.ovo_encoder_set_pool_head(self.handle, C.byref(w)), "ovo_encoder_set_pool_head")
+        self.has_pool_head = True
+        self._sd_for_head = None
+
+    def encode_images_from_pixels(self, pixels: torch.Tensor) -> torch.Tensor:
+        """Test tap of pe.CLIP.encode_image: normalised pixels [n,3,S,S] -> [n, output_dim] (not normalised)."""
+        pixels = pixels.to(self.device, torch.float32).contiguous()
+        out = torch.empty(pixels.shape[0], self.cfg.output_dim, device=self.device, dtype=torch.float32)
+        check(self.lib.ovo_encode_images(self.handle, ptr(pixels), pixels.shape[0], ptr(out), stream_ptr()), "ovo_encode_images")
+        return out
+
+    def encode_crops(self, rgb_u8: torch.Tensor, masks: torch.Tensor, embed_type: str, mask_res: int = 384,
+                     w_masked: float = 0.4418, w_global: float = 0.1, return_all: bool = False, bbox_margin: int = 50,
+                     return_crops: bool = False):
+        """CLIPGenerator.extract_clip, crop branch (clip_generator.py:136-158).  rgb uint8 [H,W,3]; masks bool/uint8
+        [M,H,W] -> [M, output_dim] unit norm ([M,3,output_dim] with return_all)."""
+        if not self.has_pool_head:
+            raise RuntimeError("install_pool_head() first: the crop-based embed types use the attention-pooling head")
+        H, W, _ = rgb_u8.shape
+        rgb_u8 = rgb_u8.to(self.device, torch.uint8).contiguous()
+        m8 = masks.to(self.device).to(torch.uint8).contiguous()
+        M, D = m8.shape[0], self.cfg.output_dim
+        vanilla = embed_type == "vanilla"
+        out = torch.empty((M, 3, D) if (return_all and not vanilla) else (M, D), device=self.device, dtype=torch.float32)
+        if M == 0:
+            return out
+        prm = CropParams(EMBED_TYPES[embed_type], int(return_all), mask_res, bbox_margin, w_masked, w_global)
+        crops = None
+        if return_crops:
+            crops = torch.empty((M if vanilla else 2 * M), mask_res, mask_res, 3, device=self.device, dtype=torch.uint8)
+        check(self.lib.ovo_encode_crops(self.handle, ptr(rgb_u8), H, W, ptr(m8), M, C.byref(prm), ptr(out), ptr(crops),
+                                        stream_ptr()), "ovo_encode_crops")
+        return (out, crops) if return_crops else out
 
     def encode_text(self, tokens: torch.Tensor) -> torch.Tensor:
         """CLIP.encode_text: tokens int [T, ctx] -> [T, text_output_dim] f32 (not normalised)."""

@@ -320,7 +320,10 @@ class OVO:
         else:
             img = torch.stack([torch.from_numpy(np.ascontiguousarray(im)) for im in images]).to(self._dev, non_blocking=True)
         masks = maps[0] if len(maps) == 1 else torch.cat(maps)
-        feats = self.clip_generator.encoder.encode_regions(img, masks, masks_per_frame=counts)
+        if self.clip_generator.embed_type == "TextRegion":
+            feats = self.clip_generator.encoder.encode_regions(img, masks, masks_per_frame=counts)
+        else:       # crop-based types: every keyframe is already a batch of 2M+1 images (clip_generator.py:136-158)
+            feats = torch.cat([self.clip_generator.extract_clip(img[f], maps[f]) for f in range(len(images))])
         self._store[self._store_n: self._store_n + M].copy_(feats)
         out, r0 = [], self._store_n
         for c in counts:
