@@ -137,6 +137,21 @@ int ovo_encode_text(ovo_encoder_t* enc, const int32_t* tokens_dev, int T, float*
 int ovo_text_bank(ovo_encoder_t* enc, const int32_t* tokens_dev, int Q, int T, float* out_dev, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Nearest neighbours and label transfer
+ * ---------------------------------------------------------------------------------------------- */
+/* Exact k nearest neighbours (k <= 8) of every query among N points, ascending by distance, ties by point index:
+ * what scipy.spatial.KDTree(points).query(queries, k) returns in match_labels_to_vtx (ovo/utils/eval_utils.py:22-27)
+ * and, with k = 1, Open3D's compute_point_cloud_distance in same_instance (ovo/utils/instance_utils.py:16-22).
+ * points f32 [N,3], queries f32 [Q,3] -> idx int32 [Q,k], dist f64 [Q,k] (optional, may be NULL).
+ * cell_size <= 0 picks the grid cell from the point density.  Needs N >= k.  Two host synchronisations (the
+ * bounding box sizes the grid; the count of far-away queries sizes the exhaustive fallback). */
+int ovo_knn(const float* points_dev, int64_t N, const float* queries_dev, int64_t Q, int k, float cell_size,
+            int32_t* idx_out_dev, double* dist_out_dev, void* stream);
+/* torch.mode over the k labels a query's neighbours carry (eval_utils.py:29-30): labels int32 [N], idx int32 [Q,k]
+ * -> out int32 [Q] = the most frequent label, the smallest one on ties. */
+int ovo_knn_mode(const int32_t* labels_dev, const int32_t* idx_dev, int64_t Q, int k, int32_t* out_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Crop-based descriptors (CLIPGenerator.extract_clip's crop branch,
  * ovo/entities/clip_generator.py:136-158): embed types vanilla / fixed_weights / hovsg / adaptive_weights /
  * concept_fusion.  Each mask contributes a masked crop and a margin crop (ovo/utils/segment_utils.py:29-182), every

@@ -392,11 +392,124 @@ def gen_crops():
     np.savez_compressed(os.path.join(OUT, "crops.npz"), **out)
     print("crops.npz", {k: v.shape for k, v in out.items()})
 
+def gen_labels():
+    """The reference's own match_labels_to_vtx (ovo/utils/eval_utils.py:13-44; SciPy KD-tree + torch.mode)."""
+    rh.setup_paths()
+    import ovo.utils.eval_utils as eu
+    from . import labels as OL
+    out = {}
+    for seed in (0, 1):
+        pts, lab, vtx = OL.synth_scene(seed=seed)
+        ml, masks, ids = eu.match_labels_to_vtx(torch.from_numpy(lab), torch.from_numpy(pts), torch.from_numpy(vtx))
+        out[f"mesh_labels_{seed}"] = ml.numpy().astype(np.int16)
+        out[f"ids_{seed}"] = ids.numpy()
+        out[f"mask_sums_{seed}"] = masks.sum(1).numpy()
+    pts, lab, vtx = OL.synth_scene(seed=0)
+    ml, _, ids = eu.match_labels_to_vtx(torch.from_numpy(lab), torch.from_numpy(pts), torch.from_numpy(vtx), filter_unasigned=False)
+    out["mesh_labels_0_unfiltered"] = ml.numpy().astype(np.int16)
+    out["ids_0_unfiltered"] = ids.numpy()
+    np.savez_compressed(os.path.join(OUT, "labels.npz"), **out)
+    print("labels.npz", {k: v.shape for k, v in out.items()})
+
+UPDATE_MAP = dict(th_centroid=1.5, th_cossim=0.5, th_points=0.5, kfs=[6, 18], drop_instance_rank=2)
+
+
+def update_map_scenario(points_ins_ids: np.ndarray, object_ids):
+    """Loop-closure input shared by the golden generator and the GPU test: the points of one instance lose their id (the SLAM
+    back-end pruned them), keyframes 0 and 12 were culled."""
+    ins = points_ins_ids.copy()
+    drop = list(object_ids)[UPDATE_MAP["drop_instance_rank"]]
+    ins[ins == drop] = -1
+    return ins, UPDATE_MAP["kfs"], drop
+
+
+def gen_update_map():
+    """The reference's OVO.update_map (ovo/entities/ovo.py:366-424) + instance_utils.same_instance / fuse_instances after the
+    4-keyframe replay of gen_ovo; Open3D's nearest-neighbour distance comes from oracle/shims/open3d."""
+    rh.setup_paths()
+    model, sd, cfg = build_reference_model()
+    import ovo.utils.clip_utils as cu
+    import ovo.utils.instance_utils as iu
+    from torchvision.transforms import Resize, Normalize, CenterCrop, Compose
+    import core.vision_encoder.transforms as transforms
+
+    def fake_loader(model_card, ckpt_path=None):
+        pre = transforms.get_image_transform(model.image_size)
+        keep = [tf for tf in pre.transforms if isinstance(tf, (Resize, CenterCrop, Normalize))]
+        return model, None, Compose(keep)
+
+    cu.load_perception_encoder = fake_loader
+    from ovo.entities.ovo import OVO
+    from ovo.entities.logger import Logger
+    K, xyz, ids, ins, frames = ovo_inputs()
+    out, pairs = {}, []
+    orig = iu.same_instance
+
+    def logged(i1, i2, pc1, pc2, thc, ths, thp):
+        r = orig(i1, i2, pc1, pc2, thc, ths, thp)
+        cen = float(((pc1[1] - pc2[1]) ** 2).sum().sqrt())
+        cos = float(torch.nn.functional.cosine_similarity(i1.clip_feature[0], i2.clip_feature[0], dim=0))
+        pd = -1.0
+        if cen <= thc and cos >= ths:
+            import open3d as o3d
+            a, b = o3d.geometry.PointCloud(), o3d.geometry.PointCloud()
+            a.points, b.points = pc1[0].numpy(), pc2[0].numpy()
+            pd = float((a.compute_point_cloud_distance(b) < thp).astype(float).mean())
+        pairs.append((i1.id, i2.id, cen, cos, 1.0 if r else 0.0, pd))
+        return r
+
+    iu.same_instance = logged
+    with tempfile.TemporaryDirectory() as tmp:
+        mdir = os.path.join(tmp, "masks", "scene")
+        os.makedirs(mdir)
+        for f in frames:
+            np.save(os.path.join(mdir, f"{f['frame_id']:04d}_seg_map_default.npy"), f["seg"])
+            np.save(os.path.join(mdir, f"{f['frame_id']:04d}_bmap_default.npy"), f["bm"])
+        logger = Logger(os.path.join(tmp, "log"), os.getpid(), False)
+        config = ovo_config(os.path.join(tmp, "masks"))
+        config.update({k: UPDATE_MAP[k] for k in ("th_centroid", "th_cossim", "th_points")})
+        config["log"] = True         # keyframes["frame_id"] is only filled when logging (ovo.py:152-153): the culled-keyframe branch needs it
+        torch.cuda.synchronize = lambda *a, **k: None     # the reference's profiler (ovo.py:101-118) synchronises CUDA; no GPU here
+        ovo = OVO(config, logger, scene_name="scene", cam_intrinsics=torch.from_numpy(K), device="cpu")
+        ovo.clip_generator.clip_dim = cfg.output_dim
+        pts, pids, pins = torch.from_numpy(xyz), torch.from_numpy(ids), torch.from_numpy(ins)
+        for f in frames:
+            pins = ovo.detect_and_track_objects((f["frame_id"], f["image"], f["depth"], ()), (pts, pids, pins), torch.from_numpy(f["c2w"]))
+            ovo.compute_semantic_info()
+        before = list(ovo.objects.keys())
+        ins_in, kfs, drop = update_map_scenario(pins.numpy(), before)
+        upd = ovo.update_map((pts, pids, torch.from_numpy(ins_in)), kfs)
+        out["ins_ids"] = upd.numpy().astype(np.int16)
+        out["objects_before"] = np.array(before, np.int32)
+        out["object_ids"] = np.array(list(ovo.objects.keys()), np.int32)
+        out["object_clips"] = ovo.get_objs_clips().numpy()
+        out["object_n_kfs"] = np.array([len(o.kfs_ids) for o in ovo.objects.values()], np.int32)
+        out["object_n_points"] = np.array([len(o.points_ids) for o in ovo.objects.values()], np.int32)
+        out["frame_id"] = np.array([str(x) for x in ovo.keyframes["frame_id"]])
+        out["desc_keys"] = np.array(sorted(ovo.keyframes["ins_descriptors"].keys()), np.int32)
+        out["pairs"] = np.array(pairs, np.float64)
+    iu.same_instance = orig
+    p = out["pairs"]
+    # every decision must survive the GPU path's descriptor noise (cos +- 3e-3) and summation order (centroid +- 1e-3, p_dist +- 1e-3)
+    def decide(cen, cos, pd):
+        if cen > UPDATE_MAP["th_centroid"] or cos < UPDATE_MAP["th_cossim"]:
+            return False
+        return pd > 0.5 or (cos > 0.9 and pd > 0.2)
+    fragile = [tuple(r) for r in p if r[5] >= 0 and len({decide(r[2] + a, r[3] + b, r[5] + c) for a in (-1e-3, 1e-3) for b in (-3e-3, 3e-3)
+                                                         for c in (-1e-3, 1e-3)}) > 1]
+    fragile += [tuple(r) for r in p if r[5] < 0 and (abs(r[2] - UPDATE_MAP["th_centroid"]) < 1e-3 and r[3] >= UPDATE_MAP["th_cossim"] - 3e-3
+                                                    or abs(r[3] - UPDATE_MAP["th_cossim"]) < 3e-3 and r[2] <= UPDATE_MAP["th_centroid"] + 1e-3)]
+    print("pairs", len(p), "fused", int(p[:, 4].sum()), "fragile decisions:", fragile)
+    assert not fragile, "pick other thresholds: a decision sits on a threshold"
+    np.savez_compressed(os.path.join(OUT, "update_map.npz"), **out)
+    print("update_map.npz", {k: v.shape for k, v in out.items()})
+    print("before", before, "after", out["object_ids"].tolist(), "dropped", drop)
+
 
 if __name__ == "__main__":
     if not rh.available():
         sys.exit("reference not available: fixtures can only be generated in the build container")
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["encoder", "assoc", "ovo", "masks", "mapper", "sam", "encoder_hd80", "crops"]
+    which = sys.argv[1:] or ["encoder", "assoc", "ovo", "masks", "mapper", "sam", "encoder_hd80", "crops", "labels", "update_map"]
     for w in which:
         globals()["gen_" + w]()

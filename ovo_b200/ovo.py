@@ -569,8 +569,10 @@ class OVO:
         cos = torch.nn.functional.cosine_similarity(fa, fb, dim=0)
         if cos < self.th_cossim:
             return False
-        dmin = torch.cat([torch.cdist(chunk, pb).min(dim=1).values for chunk in pa.split(8192)])
-        p_dist = (dmin < self.th_points).float().mean()
+        # Open3D compute_point_cloud_distance (instance_utils.py:16-22) = nearest-neighbour distance of every point of a in b
+        from .eval_utils import knn
+        dmin, _ = knn(pb, pa, k=1)
+        p_dist = (dmin[:, 0] < self.th_points).float().mean()
         return bool(p_dist > 0.5 or (cos > 0.9 and p_dist > 0.2))
 
     # ------------------------------------------------------------------------------------------ checkpoint

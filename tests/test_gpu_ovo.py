@@ -22,7 +22,7 @@ class _TokTokenizer:            # the fixture's queries are token-id rows (tiny 
         return torch.from_numpy(GG.QUERIES_TOK[int(phrase)][None])
 
 
-def _build(tmp_path, dense=False, fusion="avg_pooling"):
+def _build(tmp_path, dense=False, fusion="avg_pooling", extra=None):
     from ovo_b200 import OVO, CLIPGenerator
     from ovo_b200.encoder import random_state_dict
     K, xyz, ids, ins, frames = GG.ovo_inputs()
@@ -35,6 +35,7 @@ def _build(tmp_path, dense=False, fusion="avg_pooling"):
     config = GG.ovo_config(str(tmp_path / "masks"))
     config["clip"]["fusion"] = fusion
     config["dense_map"] = dense
+    config.update(extra or {})
     clip = CLIPGenerator(config["clip"], state_dict=random_state_dict(cfg, seed=0), tokenizer=_TokTokenizer(), encoder_config=cfg)
     ovo = OVO(config, _Logger(), scene_name="scene", cam_intrinsics=torch.from_numpy(K), clip_generator=clip)
     return ovo, K, xyz, ids, ins, frames
@@ -232,3 +233,30 @@ def test_streaming_growth_with_online_queries(tmp_path):
     assert n_obj[-1] >= n_obj[0] > 0
     labelled = (pm.get_map()[2].reshape(-1) >= 0).sum().item()
     assert labelled > 0
+
+
+def test_update_map_matches_reference_loop_closure(tmp_path, golden_dir):
+    """OVO.update_map (ovo.py:366-424: culled keyframes, pruned instances, pairwise merge by centroid / cosine / nearest-point
+    distance, descriptor re-fusion) against the reference's own run (tests/golden/update_map.npz); the point-distance test runs on
+    ovo_knn instead of Open3D."""
+    g = np.load(os.path.join(golden_dir, "update_map.npz"))
+    U = GG.UPDATE_MAP
+    ovo, K, xyz, ids, ins, frames = _build(tmp_path, extra={"th_centroid": U["th_centroid"], "th_cossim": U["th_cossim"],
+                                                               "th_points": U["th_points"], "log": True})
+    pins = _replay(ovo, xyz, ids, ins, frames)
+    before = list(ovo.objects.keys())
+    assert before == g["objects_before"].tolist()
+    ins_in, kfs, drop = GG.update_map_scenario(pins.cpu().numpy(), before)
+    pts, pids = torch.from_numpy(xyz).cuda(), torch.from_numpy(ids).cuda()
+    upd = ovo.update_map((pts, pids, torch.from_numpy(ins_in).cuda()), kfs)
+    assert (upd.cpu().numpy() == g["ins_ids"]).all()                                # merged ids, bit-exact
+    assert list(ovo.objects.keys()) == g["object_ids"].tolist() and drop not in ovo.objects
+    assert [len(o.kfs_ids) for o in ovo.objects.values()] == g["object_n_kfs"].tolist()
+    assert [len(o.points_ids) for o in ovo.objects.values()] == g["object_n_points"].tolist()
+    assert [str(x) for x in ovo.keyframes["frame_id"]] == g["frame_id"].tolist()    # culled keyframes are marked, not removed
+    assert sorted(ovo.keyframes["ins_descriptors"].keys()) == g["desc_keys"].tolist()
+    clips, ref = ovo.get_objs_clips().cpu(), torch.from_numpy(g["object_clips"])
+    assert (1 - torch.nn.functional.cosine_similarity(clips, ref, dim=-1)).max().item() < 1e-3
+    assert ((clips - ref).norm() / ref.norm()).item() < 1e-2
+    # the map keeps working after the merge: a query over the merged bank
+    assert ovo.query(["0", "1", "2"]).shape == (len(g["object_ids"]), 3)
