@@ -237,6 +237,9 @@ def run_ours(args, rank, world, local_rank):
     # --- e2e through the public OVO API, host inputs, per keyframe
     e2e = run_e2e(args, rank, world, dev, enc, K, xyz, ids, ins, seg, bm, fr, dist)
 
+    # --- SURVEY 8f rows (crop-based descriptors, label transfer): separate stage reports, rank 0 of a single-GPU run only
+    nxt = run_next_rows(args, dev, enc, sd, bm, fr, xyz, tf_sus, how) if (world == 1 and not args.no_next_rows) else None
+
     if rank != 0:
         return
     out = {"metric": "keyframes/s, CLIP-encode (PE-Core-L14-336 TextRegion) + 3D fusion, 640x480 RGB-D into a 2M-point map",
@@ -252,6 +255,8 @@ def run_ours(args, rank, world, local_rank):
            "n_matched_points_per_keyframe": int(state["n_matched"])}
     if sam is not None:
         out["sam"] = sam
+    if nxt is not None:
+        out.update(nxt)
     if not args.no_cpu_baseline and world >= 1:
         out["cpu_baseline"] = cpu_baseline(args, budget_frames=1)
         if sam is not None:
@@ -314,6 +319,65 @@ def run_sam_stage(args, dev, clip_fusion_ms_per_keyframe, tf_sus, how):
             "batched": {"frames_per_trunk_pass": SB, "ms_per_frame": round(ms_batch, 3), "frames_per_s": round(1e3 / ms_batch, 2),
                         "note": "replay / MaskGenerator.precompute mode: one Hiera trunk pass over several frames, decoder per frame"},
             "keyframes_per_s_with_online_sam": round(1e3 / (clip_fusion_ms_per_keyframe + ms_gen), 2)}
+
+
+def run_next_rows(args, dev, enc, sd, bm, fr, xyz, tf_sus, how):
+    """SURVEY 8f rows built after the headline path, timed with CUDA events on resident inputs:
+    crop-based descriptors (rank 2: 2M+1 full encode_image passes per keyframe) and label transfer (rank 4: exact k=5 nearest
+    neighbours of 1M mesh vertices in the 2M-point map + label vote), the latter next to SciPy's KD-tree (what the reference
+    calls) on a bounded sample."""
+    from ovo_b200 import eval_utils as EU
+    out = {}
+    enc.install_pool_head(sd, pool_heads=8)
+    img = torch.from_numpy(fr[0]["image"]).to(dev)
+    masks = torch.from_numpy(bm).to(dev)
+    M = bm.shape[0]
+
+    def t(fn, n):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / n
+
+    ms = t(lambda: enc.encode_crops(img, masks, "fixed_weights", mask_res=336), 5)
+    gf = (2 * M + 1) * GFLOP_PER_IMAGE
+    out["crop_descriptors"] = {"metric": "crop-based descriptors (embed_type fixed_weights, mask_res 336), one 640x480 keyframe",
+                               "masks": M, "images_per_keyframe": 2 * M + 1, "ms_per_keyframe": round(ms, 3),
+                               "keyframes_per_s": round(1e3 / ms, 2), "algorithmic_tflops": round(gf / ms, 1),
+                               "roofline": {"bound": "tensor", "achieved": round(gf / ms, 1), "peak": tf_sus, "unit": "TFLOP/s",
+                                            "frac": round(gf / ms / tf_sus, 4), "peak_source": f"{how} bf16_tflops_sustained"}}
+    rng = np.random.default_rng(3)
+    P = torch.from_numpy(xyz).to(dev)
+    nq = 1_000_000
+    sel = rng.integers(0, xyz.shape[0], nq)
+    vtx_h = (xyz[sel] + rng.normal(0, 0.01, (nq, 3))).astype(np.float32)
+    vtx = torch.from_numpy(vtx_h).to(dev)
+    labels = torch.from_numpy(rng.integers(0, 300, xyz.shape[0]).astype(np.int64)).to(dev)
+    ms_knn = t(lambda: EU.knn(P, vtx, k=5, return_distance=False), 3)
+    ms_lt = t(lambda: EU.match_labels_to_vtx(labels, P, vtx), 3)
+    lt = {"metric": "label transfer: exact 5 nearest map points of every mesh vertex + label vote (match_labels_to_vtx)",
+          "points": int(xyz.shape[0]), "vertices": nq, "knn_ms": round(ms_knn, 2), "match_labels_to_vtx_ms": round(ms_lt, 2),
+          "vertices_per_s": round(nq / ms_lt * 1e3, 0)}
+    if not args.no_cpu_baseline:
+        from scipy.spatial import KDTree
+        t0 = time.perf_counter()
+        tree = KDTree(xyz)
+        t1 = time.perf_counter()
+        ns = 50_000
+        _, idx_ref = tree.query(vtx_h[:ns], k=5)
+        t2 = time.perf_counter()
+        _, idx = EU.knn(P, vtx[:ns], k=5, return_distance=False)
+        lt["cpu_baseline"] = {"kind": "reference", "what": "scipy.spatial.KDTree (eval_utils.py:24-27), 1 core", "build_s": round(t1 - t0, 2),
+                              "vertices_per_s": round(ns / (t2 - t1), 0), "sample": f"{ns} of the {nq} vertices",
+                              "indices_identical": bool((idx.cpu().numpy() == idx_ref).all())}
+    out["label_transfer"] = lt
+    return out
 
 
 def run_e2e(args, rank, world, dev, enc, K, xyz, ids, ins, seg, bm, fr, dist):
@@ -498,6 +562,7 @@ def main():
     ap.add_argument("--points", type=int, default=2_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sam", action="store_true", help="skip the SAM-2 stage report")
+    ap.add_argument("--no-next-rows", action="store_true", help="skip the crop-descriptor / label-transfer stage reports")
     ap.add_argument("--profile-e2e", action="store_true", help="cProfile three e2e steps to stderr")
     ap.add_argument("--no-pipeline", action="store_true", help="do not overlap a step's fusion with the next step's encoder")
     args = ap.parse_args()

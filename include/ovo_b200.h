@@ -147,6 +147,9 @@ int ovo_text_bank(ovo_encoder_t* enc, const int32_t* tokens_dev, int Q, int T, f
  * bounding box sizes the grid; the count of far-away queries sizes the exhaustive fallback). */
 int ovo_knn(const float* points_dev, int64_t N, const float* queries_dev, int64_t Q, int k, float cell_size,
             int32_t* idx_out_dev, double* dist_out_dev, void* stream);
+/* Diagnostics of the calling thread's last ovo_knn: the grid cell it used, the number of cells, and how many queries
+ * went through the exhaustive fallback. */
+void ovo_knn_stats(float* cell_size, int* n_cells, int* n_fallback);
 /* torch.mode over the k labels a query's neighbours carry (eval_utils.py:29-30): labels int32 [N], idx int32 [Q,k]
  * -> out int32 [Q] = the most frequent label, the smallest one on ties. */
 int ovo_knn_mode(const int32_t* labels_dev, const int32_t* idx_dev, int64_t Q, int k, int32_t* out_dev, void* stream);

@@ -117,6 +117,7 @@ SIGNATURES = {
     "ovo_fuse_clips": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_float, c_void_p, c_void_p]),
     "ovo_siglip_similarity": (c_int, [c_void_p, c_int64, c_float, c_float, c_void_p]),
     "ovo_knn": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_float, c_void_p, c_void_p, c_void_p]),
+    "ovo_knn_stats": (None, [C.POINTER(c_float), C.POINTER(c_int), C.POINTER(c_int)]),
     "ovo_knn_mode": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     "ovo_map_create": (c_int, [C.POINTER(c_void_p)]),
     "ovo_map_destroy": (None, [c_void_p]),

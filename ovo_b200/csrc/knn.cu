@@ -13,7 +13,7 @@
 namespace ovo {
 
 constexpr int kKnnMaxK = 8;
-constexpr int kKnnMaxRing = 6;      // shells walked on the grid before a query falls back to the exhaustive scan
+constexpr int kKnnMaxRing = 10;     // shells walked on the grid before a query falls back to the exhaustive scan
 
 struct KnnGrid {
   float ox, oy, oz, cell, inv_cell;
@@ -64,6 +64,17 @@ __global__ void knn_count_kernel(const float* __restrict__ xyz, long long N, Knn
   const int c = cell_index(g, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
   cell_of_pt[i] = c;
   atomicAdd(counts + c, 1);
+}
+
+// sum of count^2 over the cells = (points) x (mean occupancy of the cell a point lives in): the cost a query near the points pays
+__global__ void knn_occupancy_kernel(const int* __restrict__ counts, int n_cells, unsigned long long* __restrict__ sum2) {
+  unsigned long long acc = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_cells; i += gridDim.x * blockDim.x) {
+    const unsigned long long c = static_cast<unsigned long long>(counts[i]);
+    acc += c * c;
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0 && acc) atomicAdd(sum2, acc);
 }
 
 // exclusive scan, three passes: per-block (1024 items) scan + block totals, scan of the totals by one block, offset add
@@ -162,7 +173,37 @@ __device__ __forceinline__ double dist2(const float4& p, float qx, float qy, flo
   return dx * dx + dy * dy + dz * dz;
 }
 
-// One thread per query.  Shell r = the cells at Chebyshev distance r from the query's cell.  After shell r every point inside the
+// Points [p0, p1) of the sorted array against one query, by one WARP: each lane loads one point (coalesced float4) and
+// evaluates its float distance; the few candidates that are not rejected by the current k-th distance are broadcast one by one
+// and pushed by every lane into its own (identical) copy of the top-k list, in double.  The float distance only rejects, and with
+// a margin above its rounding error, so the result is the double-precision one.
+template <int K>
+__device__ __forceinline__ void scan_run(const float4* __restrict__ sorted, int p0, int p1, float qx, float qy, float qz, int k,
+                                         TopK<K>& top, float& kth_f) {
+  const int lane = threadIdx.x & 31;
+  for (int base = p0; base < p1; base += 32) {
+    const int p = base + lane;
+    float4 pt = make_float4(0.f, 0.f, 0.f, 0.f);
+    bool pass = false;
+    if (p < p1) {
+      pt = __ldg(sorted + p);
+      const float fx = pt.x - qx, fy = pt.y - qy, fz = pt.z - qz;
+      pass = fx * fx + fy * fy + fz * fz <= kth_f;
+    }
+    unsigned m = __ballot_sync(0xffffffffu, pass);
+    while (m) {
+      const int src = __ffs(m) - 1;
+      m &= m - 1;
+      float4 c;
+      c.x = __shfl_sync(0xffffffffu, pt.x, src); c.y = __shfl_sync(0xffffffffu, pt.y, src);
+      c.z = __shfl_sync(0xffffffffu, pt.z, src); c.w = __shfl_sync(0xffffffffu, pt.w, src);
+      top.push(dist2(c, qx, qy, qz), __float_as_int(c.w));
+    }
+    kth_f = __double2float_ru(top.kth(k) * 1.000004);
+  }
+}
+
+// One warp per query.  Shell r = the cells at Chebyshev distance r from the query's cell.  After shell r every point inside the
 // cube of (2r+1)^3 cells has been seen; the k-th distance is final once it does not exceed the distance from the query to the
 // nearest face of that cube behind which unseen cells remain.
 template <int K>
@@ -170,41 +211,40 @@ __global__ void __launch_bounds__(128)
     knn_query_kernel(const float4* __restrict__ sorted, const int* __restrict__ starts, KnnGrid g, const float* __restrict__ queries,
                      long long Q, int k, int32_t* __restrict__ idx_out, double* __restrict__ dist_out, int* __restrict__ overflow,
                      int* __restrict__ n_overflow) {
-  const long long q = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const long long q = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;   // uniform over the warp
   if (q >= Q) return;
-  const float qx = queries[3 * q], qy = queries[3 * q + 1], qz = queries[3 * q + 2];
+  const float qx = __ldg(queries + 3 * q), qy = __ldg(queries + 3 * q + 1), qz = __ldg(queries + 3 * q + 2);
   const int cx = axis_cell(qx, g.ox, g.inv_cell, g.nx), cy = axis_cell(qy, g.oy, g.inv_cell, g.ny), cz = axis_cell(qz, g.oz, g.inv_cell, g.nz);
   TopK<K> top;
   top.init();
+  float kth_f = INFINITY;
   bool done = false;
   for (int r = 0; r <= kKnnMaxRing && !done; ++r) {
-    for (int dz = -r; dz <= r; ++dz) {
-      const int z = cz + dz;
-      if (z < 0 || z >= g.nz) continue;
-      for (int dy = -r; dy <= r; ++dy) {
-        const int y = cy + dy;
-        if (y < 0 || y >= g.ny) continue;
-        const bool face = abs(dz) == r || abs(dy) == r;
-        // on a face row every x belongs to the shell (one contiguous run of cells); otherwise only the two end cells
-        const int xa = max(cx - r, 0), xb = min(cx + r, g.nx - 1);
-        const size_t row = (static_cast<size_t>(z) * g.ny + y) * g.nx;
-        if (face) {
-          for (int p = starts[row + xa], pe = starts[row + xb + 1]; p < pe; ++p) {
-            const float4 pt = sorted[p];
-            top.push(dist2(pt, qx, qy, qz), __float_as_int(pt.w));
+    // the shell's runs of cells: a row on a face of the cube contributes one contiguous run of cells, any other row its two end
+    // cells.  Each lane fetches the bounds of one run, then the warp scans the non-empty ones (most are empty in sparse regions).
+    const int w = 2 * r + 1, nslots = 2 * w * w, lane = threadIdx.x & 31;
+    for (int s0 = 0; s0 < nslots; s0 += 32) {
+      const int slot = s0 + lane;
+      int p0 = 0, p1 = 0;
+      if (slot < nslots) {
+        const int idx = slot >> 1, side = slot & 1;
+        const int dz = idx / w - r, dy = idx % w - r;
+        const int z = cz + dz, y = cy + dy;
+        if (z >= 0 && z < g.nz && y >= 0 && y < g.ny) {
+          const size_t row = (static_cast<size_t>(z) * g.ny + y) * g.nx;
+          if (abs(dz) == r || abs(dy) == r) {
+            if (side == 0) { p0 = __ldg(starts + row + max(cx - r, 0)); p1 = __ldg(starts + row + min(cx + r, g.nx - 1) + 1); }
+          } else {
+            const int x = side == 0 ? cx - r : cx + r;
+            if (x >= 0 && x < g.nx) { p0 = __ldg(starts + row + x); p1 = __ldg(starts + row + x + 1); }
           }
-        } else {
-          if (cx - r >= 0)
-            for (int p = starts[row + cx - r], pe = starts[row + cx - r + 1]; p < pe; ++p) {
-              const float4 pt = sorted[p];
-              top.push(dist2(pt, qx, qy, qz), __float_as_int(pt.w));
-            }
-          if (r > 0 && cx + r < g.nx)
-            for (int p = starts[row + cx + r], pe = starts[row + cx + r + 1]; p < pe; ++p) {
-              const float4 pt = sorted[p];
-              top.push(dist2(pt, qx, qy, qz), __float_as_int(pt.w));
-            }
         }
+      }
+      unsigned m = __ballot_sync(0xffffffffu, p1 > p0);
+      while (m) {
+        const int src = __ffs(m) - 1;
+        m &= m - 1;
+        scan_run(sorted, __shfl_sync(0xffffffffu, p0, src), __shfl_sync(0xffffffffu, p1, src), qx, qy, qz, k, top, kth_f);
       }
     }
     // margin to the unseen part of the grid
@@ -221,6 +261,7 @@ __global__ void __launch_bounds__(128)
     if (margin == INFINITY) done = true;                                   // the whole grid has been walked
     else if (margin > 0.0 && top.kth(k) <= margin * margin) done = true;
   }
+  if ((threadIdx.x & 31) != 0) return;
   if (!done) {
     overflow[atomicAdd(n_overflow, 1)] = static_cast<int>(q);
     return;
@@ -243,9 +284,13 @@ __global__ void __launch_bounds__(256)
   const float qx = queries[3 * q], qy = queries[3 * q + 1], qz = queries[3 * q + 2];
   TopK<kKnnMaxK> top;
   top.init();
+  float kth_f = INFINITY;
   for (long long p = threadIdx.x; p < N; p += blockDim.x) {
     const float4 pt = sorted[p];
+    const float fx = pt.x - qx, fy = pt.y - qy, fz = pt.z - qz;
+    if (fx * fx + fy * fy + fz * fz > kth_f) continue;
     top.push(dist2(pt, qx, qy, qz), __float_as_int(pt.w));
+    kth_f = __double2float_ru(top.kth(k) * 1.000004);
   }
   constexpr int K = kKnnMaxK;
 #pragma unroll
@@ -289,7 +334,16 @@ __global__ void knn_mode_kernel(const int32_t* __restrict__ labels, const int32_
 
 }  // namespace ovo
 
+static thread_local float g_knn_cell = 0.f;
+static thread_local int g_knn_cells = 0, g_knn_overflow = 0;
+
 extern "C" {
+
+void ovo_knn_stats(float* cell_size, int* n_cells, int* n_fallback) {
+  if (cell_size) *cell_size = g_knn_cell;
+  if (n_cells) *n_cells = g_knn_cells;
+  if (n_fallback) *n_fallback = g_knn_overflow;
+}
 
 int ovo_knn(const float* points_dev, int64_t N, const float* queries_dev, int64_t Q, int k, float cell_size,
             int32_t* idx_out_dev, double* dist_out_dev, void* stream_) {
@@ -322,35 +376,55 @@ int ovo_knn(const float* points_dev, int64_t N, const float* queries_dev, int64_
     const double surf = std::sqrt(8.0 * 2.0 * (ex * ey + ey * ez + ex * ez) / static_cast<double>(N));
     cell = std::max(vol, std::min(surf, std::max({ex, ey, ez})));
   }
+  constexpr double kMaxCells = static_cast<double>(1 << 25);
+  auto fit = [&](double c, KnnGrid* g) {
+    const double nx = std::floor(ex / c) + 1, ny = std::floor(ey / c) + 1, nz = std::floor(ez / c) + 1;
+    if (!(nx * ny * nz <= kMaxCells && nx <= 4096 && ny <= 4096 && nz <= 4096)) return false;
+    g->nx = static_cast<int>(nx); g->ny = static_cast<int>(ny); g->nz = static_cast<int>(nz);
+    g->ox = lo[0]; g->oy = lo[1]; g->oz = lo[2];
+    g->cell = static_cast<float>(c); g->inv_cell = 1.0f / g->cell;
+    return true;
+  };
   KnnGrid g;
-  for (;;) {
-    const double nx = std::floor(ex / cell) + 1, ny = std::floor(ey / cell) + 1, nz = std::floor(ez / cell) + 1;
-    if (nx * ny * nz <= static_cast<double>(1 << 24) && nx <= 4096 && ny <= 4096 && nz <= 4096) {
-      g.nx = static_cast<int>(nx); g.ny = static_cast<int>(ny); g.nz = static_cast<int>(nz);
-      break;
-    }
-    cell *= 1.26;
-  }
-  g.ox = lo[0]; g.oy = lo[1]; g.oz = lo[2];
-  g.cell = static_cast<float>(cell); g.inv_cell = 1.0f / g.cell;
-  const int n_cells = g.nx * g.ny * g.nz;
+  while (!fit(cell, &g)) cell *= 1.26;
   int *cell_of_pt = nullptr, *starts = nullptr, *cursor = nullptr, *totals = nullptr, *overflow = nullptr, *n_overflow = nullptr;
+  unsigned long long* sum2 = nullptr;
   float4* sorted = nullptr;
-  const int nb = ceil_div(n_cells + 1, 1024);
   OVO_CUDA(cudaMallocAsync(&cell_of_pt, N * sizeof(int), s));
-  OVO_CUDA(cudaMallocAsync(&starts, (static_cast<size_t>(n_cells) + 1) * sizeof(int), s));
+  OVO_CUDA(cudaMallocAsync(&sum2, sizeof(unsigned long long), s));
+  int n_cells = 0;
+  // Count the points per cell; when the density is uneven (a depth-map surface inside a sparse volume) the cells that hold the
+  // points are crowded: halve the cell while a point shares its cell with more than ~16 others on average (auto cell size only).
+  for (int pass = 0;; ++pass) {
+    n_cells = g.nx * g.ny * g.nz;
+    OVO_CUDA(cudaMallocAsync(&starts, (static_cast<size_t>(n_cells) + 1) * sizeof(int), s));
+    OVO_CUDA(cudaMemsetAsync(starts, 0, (static_cast<size_t>(n_cells) + 1) * sizeof(int), s));
+    knn_count_kernel<<<ceil_div(N, 256), 256, 0, s>>>(points_dev, N, g, cell_of_pt, starts);
+    OVO_CHECK_LAUNCH();
+    KnnGrid finer;
+    if (cell_size > 0 || pass >= 5 || !fit(cell * 0.5, &finer)) break;
+    unsigned long long h = 0;
+    OVO_CUDA(cudaMemsetAsync(sum2, 0, sizeof(unsigned long long), s));
+    knn_occupancy_kernel<<<std::min(ceil_div(n_cells, 256), 1184), 256, 0, s>>>(starts, n_cells, sum2);
+    OVO_CHECK_LAUNCH();
+    OVO_CUDA(cudaMemcpyAsync(&h, sum2, sizeof(h), cudaMemcpyDeviceToHost, s));
+    OVO_CUDA(cudaStreamSynchronize(s));
+    if (static_cast<double>(h) / static_cast<double>(N) <= 16.0) break;
+    cudaFreeAsync(starts, s);
+    cell *= 0.5;
+    g = finer;
+  }
+  cudaFreeAsync(sum2, s);
+  const int nb = ceil_div(n_cells + 1, 1024);
   OVO_CUDA(cudaMallocAsync(&cursor, static_cast<size_t>(n_cells) * sizeof(int), s));
   OVO_CUDA(cudaMallocAsync(&totals, static_cast<size_t>(nb) * sizeof(int), s));
   OVO_CUDA(cudaMallocAsync(&sorted, N * sizeof(float4), s));
   OVO_CUDA(cudaMallocAsync(&overflow, Q * sizeof(int), s));
   OVO_CUDA(cudaMallocAsync(&n_overflow, sizeof(int), s));
-  OVO_CUDA(cudaMemsetAsync(starts, 0, (static_cast<size_t>(n_cells) + 1) * sizeof(int), s));
   OVO_CUDA(cudaMemsetAsync(cursor, 0, static_cast<size_t>(n_cells) * sizeof(int), s));
   OVO_CUDA(cudaMemsetAsync(n_overflow, 0, sizeof(int), s));
   {
     ProfScope prof(s, PROF_OTHER, 0.0, static_cast<double>(N) * 36);
-    knn_count_kernel<<<ceil_div(N, 256), 256, 0, s>>>(points_dev, N, g, cell_of_pt, starts);
-    OVO_CHECK_LAUNCH();
     scan_blocks_kernel<<<nb, 256, 0, s>>>(starts, n_cells + 1, totals);
     OVO_CHECK_LAUNCH();
     scan_totals_kernel<<<1, 1024, 0, s>>>(totals, nb);
@@ -362,14 +436,15 @@ int ovo_knn(const float* points_dev, int64_t N, const float* queries_dev, int64_
   }
   {
     ProfScope prof(s, PROF_OTHER, 0.0, static_cast<double>(Q) * (12 + 12.0 * k));
-    if (k == 1) knn_query_kernel<1><<<ceil_div(Q, 128), 128, 0, s>>>(sorted, starts, g, queries_dev, Q, k, idx_out_dev, dist_out_dev, overflow, n_overflow);
-    else if (k <= 5) knn_query_kernel<5><<<ceil_div(Q, 128), 128, 0, s>>>(sorted, starts, g, queries_dev, Q, k, idx_out_dev, dist_out_dev, overflow, n_overflow);
-    else knn_query_kernel<kKnnMaxK><<<ceil_div(Q, 128), 128, 0, s>>>(sorted, starts, g, queries_dev, Q, k, idx_out_dev, dist_out_dev, overflow, n_overflow);
+    if (k == 1) knn_query_kernel<1><<<ceil_div(Q * 32, 128), 128, 0, s>>>(sorted, starts, g, queries_dev, Q, k, idx_out_dev, dist_out_dev, overflow, n_overflow);
+    else if (k <= 5) knn_query_kernel<5><<<ceil_div(Q * 32, 128), 128, 0, s>>>(sorted, starts, g, queries_dev, Q, k, idx_out_dev, dist_out_dev, overflow, n_overflow);
+    else knn_query_kernel<kKnnMaxK><<<ceil_div(Q * 32, 128), 128, 0, s>>>(sorted, starts, g, queries_dev, Q, k, idx_out_dev, dist_out_dev, overflow, n_overflow);
     OVO_CHECK_LAUNCH();
   }
   int n_over = 0;
   OVO_CUDA(cudaMemcpyAsync(&n_over, n_overflow, sizeof(int), cudaMemcpyDeviceToHost, s));
   OVO_CUDA(cudaStreamSynchronize(s));
+  g_knn_cell = g.cell; g_knn_cells = n_cells; g_knn_overflow = n_over;
   if (n_over > 0) {
     knn_brute_kernel<<<n_over, 256, 0, s>>>(sorted, N, queries_dev, overflow, k, idx_out_dev, dist_out_dev);
     OVO_CHECK_LAUNCH();

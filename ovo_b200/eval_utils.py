@@ -28,6 +28,14 @@ def knn(points: torch.Tensor, queries: torch.Tensor, k: int = 5, cell_size: floa
     return dist, idx
 
 
+def knn_stats() -> dict:
+    """Grid cell, cell count and number of exhaustive-fallback queries of the last `knn` call of this thread."""
+    import ctypes as C
+    cell, cells, fb = C.c_float(), C.c_int(), C.c_int()
+    _lib.lib().ovo_knn_stats(C.byref(cell), C.byref(cells), C.byref(fb))
+    return {"cell_size": round(cell.value, 5), "cells": cells.value, "fallback_queries": fb.value}
+
+
 def match_labels_to_vtx(points_3d_labels: torch.Tensor, points_3d: torch.Tensor, mesh_vtx: torch.Tensor,
                         filter_unasigned: bool = True, tree: str = "kd", verbose=False) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     """eval_utils.py:13-44.  `tree` is accepted for compatibility (kd / ball give the same neighbours)."""

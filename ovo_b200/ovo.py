@@ -565,14 +565,15 @@ class OVO:
         pb, cb = pc_b
         if ((ca - cb) ** 2).sum().sqrt() > self.th_centroid:
             return False
-        fa, fb = a.clip_feature.reshape(-1), b.clip_feature.reshape(-1)
-        cos = torch.nn.functional.cosine_similarity(fa, fb, dim=0)
+        # instance_utils.py:13 indexes `clip_feature[0]`: the descriptor row of a fused feature ([1, D]) but the FIRST ELEMENT of a
+        # single-view feature ([D], instance3d.py:184-185), which then broadcasts.  Kept as is (do not "fix").
+        cos = torch.nn.functional.cosine_similarity(a.clip_feature[0], b.clip_feature[0], dim=0)
         if cos < self.th_cossim:
             return False
         # Open3D compute_point_cloud_distance (instance_utils.py:16-22) = nearest-neighbour distance of every point of a in b
         from .eval_utils import knn
         dmin, _ = knn(pb, pa, k=1)
-        p_dist = (dmin[:, 0] < self.th_points).float().mean()
+        p_dist = (dmin[:, 0] < self.th_points).double().mean()     # .astype(float).mean() in the reference
         return bool(p_dist > 0.5 or (cos > 0.9 and p_dist > 0.2))
 
     # ------------------------------------------------------------------------------------------ checkpoint

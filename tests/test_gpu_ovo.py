@@ -242,7 +242,8 @@ def test_update_map_matches_reference_loop_closure(tmp_path, golden_dir):
     g = np.load(os.path.join(golden_dir, "update_map.npz"))
     U = GG.UPDATE_MAP
     ovo, K, xyz, ids, ins, frames = _build(tmp_path, extra={"th_centroid": U["th_centroid"], "th_cossim": U["th_cossim"],
-                                                               "th_points": U["th_points"], "log": True})
+                                                               "th_points": U["th_points"], "log": True,
+                                                               "debug_info": True})   # per-instance point-id lists are only kept for the debug checkpoint
     pins = _replay(ovo, xyz, ids, ins, frames)
     before = list(ovo.objects.keys())
     assert before == g["objects_before"].tolist()
