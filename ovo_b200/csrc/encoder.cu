@@ -323,14 +323,15 @@ __global__ void text_embed_kernel(const int32_t* __restrict__ tokens, int T, int
 
 // batched_mask_to_box + batched_box_xyxy_to_xywh (segment_utils.py:43-104): one block per mask; edges are the min / max set
 // row / column INDEX, so w = right - left, h = bottom - top (the reference's convention, kept); empty mask -> 0,0,0,0.
-__global__ void __launch_bounds__(256) mask_boxes_kernel(const uint8_t* __restrict__ masks, int H, int W, int32_t* __restrict__ xywh) {
+__global__ void __launch_bounds__(1024) mask_boxes_kernel(const uint8_t* __restrict__ masks, int H, int W, int32_t* __restrict__ xywh) {
   const uint8_t* m = masks + static_cast<size_t>(blockIdx.x) * H * W;
   int x0 = W, x1 = -1, y0 = H, y1 = -1;
   const int n = H * W;
   if ((W & 3) == 0 && (reinterpret_cast<uintptr_t>(m) & 3) == 0) {
     const uint32_t* m4 = reinterpret_cast<const uint32_t*>(m);
+#pragma unroll 8
     for (int i = threadIdx.x; i < n / 4; i += blockDim.x) {
-      const uint32_t v = m4[i];
+      const uint32_t v = __ldg(m4 + i);
       if (v == 0) continue;
       const int y = (4 * i) / W, x = 4 * i - y * W;
       const int lo = x + ((v & 0xffu) ? 0 : (v & 0xff00u) ? 1 : (v & 0xff0000u) ? 2 : 3);
@@ -344,7 +345,7 @@ __global__ void __launch_bounds__(256) mask_boxes_kernel(const uint8_t* __restri
         x0 = min(x0, x); x1 = max(x1, x); y0 = min(y0, y); y1 = max(y1, y);
       }
   }
-  __shared__ int s[4][8];
+  __shared__ int s[4][32];
   for (int o = 16; o > 0; o >>= 1) {
     x0 = min(x0, __shfl_xor_sync(0xffffffffu, x0, o)); x1 = max(x1, __shfl_xor_sync(0xffffffffu, x1, o));
     y0 = min(y0, __shfl_xor_sync(0xffffffffu, y0, o)); y1 = max(y1, __shfl_xor_sync(0xffffffffu, y1, o));
@@ -450,12 +451,20 @@ __global__ void __launch_bounds__(256)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
   const float* base = kv + static_cast<size_t>(img) * seq * 2 * width + head * hd;
   const float* qh = q + head * hd;
-  for (int j = warp; j < seq; j += nwarp) {
-    const float* k = base + static_cast<size_t>(j) * 2 * width;
-    float d = 0.f;
-    for (int i = lane; i < hd; i += 32) d += qh[i] * k[i];
-    for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
-    if (lane == 0) sc[j] = d;
+  // four keys per warp iteration: their loads are independent, so they overlap instead of paying one memory latency per key
+  for (int j0 = warp * 4; j0 < seq; j0 += nwarp * 4) {
+    float d[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int i = lane; i < hd; i += 32) {
+      const float qv = qh[i];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (j0 + u < seq) d[u] += qv * __ldg(base + static_cast<size_t>(j0 + u) * 2 * width + i);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      for (int o = 16; o > 0; o >>= 1) d[u] += __shfl_xor_sync(0xffffffffu, d[u], o);
+      if (lane == 0 && j0 + u < seq) sc[j0 + u] = d[u];
+    }
   }
   __syncthreads();
   if (warp == 0) {
@@ -474,7 +483,17 @@ __global__ void __launch_bounds__(256)
   float acc = 0.f;
   if (slice < slices) {
     const float* v = base + width + d;
-    for (int j = slice; j < seq; j += slices) acc += sc[j] * v[static_cast<size_t>(j) * 2 * width];
+    float a4[4] = {0.f, 0.f, 0.f, 0.f};
+    int j = slice;
+    for (; j + 7 * slices < seq; j += 8 * slices) {          // eight independent loads in flight
+      float t[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) t[u] = __ldg(v + static_cast<size_t>(j + u * slices) * 2 * width);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) a4[u & 3] += sc[j + u * slices] * t[u];
+    }
+    for (; j < seq; j += slices) a4[0] += sc[j] * __ldg(v + static_cast<size_t>(j) * 2 * width);
+    acc = (a4[0] + a4[1]) + (a4[2] + a4[3]);
   }
   red[threadIdx.x] = acc;
   __syncthreads();
@@ -1160,7 +1179,7 @@ int ovo_encode_images(ovo_encoder_t* e, const float* pixels_dev, int n, float* o
 
 int ovo_mask_boxes(const uint8_t* masks_dev, int M, int H, int W, int32_t* xywh_dev, void* stream) {
   OVO_REQUIRE(masks_dev && xywh_dev && M > 0 && H > 0 && W > 0, "ovo_mask_boxes: bad arguments");
-  mask_boxes_kernel<<<M, 256, 0, static_cast<cudaStream_t>(stream)>>>(masks_dev, H, W, xywh_dev);
+  mask_boxes_kernel<<<M, 1024, 0, static_cast<cudaStream_t>(stream)>>>(masks_dev, H, W, xywh_dev);
   OVO_CHECK_LAUNCH();
   return OVO_OK;
 }
@@ -1213,7 +1232,7 @@ int ovo_encode_crops(ovo_encoder_t* e, const uint8_t* rgb_dev, int H, int W, con
   const bool vanilla = prm->embed_type == OVO_EMBED_VANILLA;
 
   // 1. boxes -> host (they decide the geometry of every crop; the one synchronisation of this path)
-  mask_boxes_kernel<<<M, 256, 0, s>>>(masks_dev, H, W, e->crop_boxes);
+  mask_boxes_kernel<<<M, 1024, 0, s>>>(masks_dev, H, W, e->crop_boxes);
   OVO_CHECK_LAUNCH();
   std::vector<int32_t> bx(static_cast<size_t>(M) * 4);
   OVO_CUDA(cudaMemcpyAsync(bx.data(), e->crop_boxes, bx.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
