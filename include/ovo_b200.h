@@ -210,6 +210,27 @@ int ovo_encode_crops(ovo_encoder_t* enc, const uint8_t* rgb_dev, int H, int W, c
  * -> out f32 [M,D].  embed_type 1..4. */
 int ovo_fuse_clips(const float* g_dev, const float* seg_dev, const float* bbox_dev, int M, int D, int embed_type,
                    float w_masked, float w_global, float* out_dev, void* stream);
+/* embed_type `learned`: WeightsPredictorMerger (ovo/entities/clips_merging.py:26-56; wired at clip_generator.py:18-29,153).
+ * Device pointers; matrices bf16 [out,in], vectors f32, names as in the module's state_dict. */
+typedef struct {
+  const void* in_w; const float* in_b;      /* att_encoder.layers.{l}.self_attn.in_proj_{weight [3d,d], bias} */
+  const void* out_w; const float* out_b;    /* self_attn.out_proj */
+  const float* ln1_w; const float* ln1_b;   /* norm1 */
+  const void* ff1_w; const float* ff1_b;    /* linear1 [ff,d] */
+  const void* ff2_w; const float* ff2_b;    /* linear2 [d,ff] */
+  const float* ln2_w; const float* ln2_b;   /* norm2 */
+} ovo_merger_layer;
+typedef struct {
+  int d_model, nhead, dim_feedforward, n_layers;
+  const ovo_merger_layer* layers;           /* host array [n_layers] */
+  int n_linear;                             /* linears of `mlp` (hparams n_layers + 2) */
+  const void* const* mlp_w;                 /* host array [n_linear] of device pointers, bf16 [out_j, in_j]; in_0 = 3*d_model */
+  const float* const* mlp_b;                /* host array [n_linear] of device pointers */
+  const int* mlp_out;                       /* host array [n_linear]: out_j; the last is 3*d_model (per-channel weights) or 3 */
+  float ln_eps;                             /* 1e-5 (nn.TransformerEncoderLayer default) */
+} ovo_merger_weights;
+/* clips f32 [B,3,D] (global, masked crop, margin crop; unit norm) -> out f32 [B,D] unit norm. */
+int ovo_merge_clips_learned(const ovo_merger_weights* w, const float* clips_dev, int B, float* out_dev, void* stream);
 /* siglip_cosine_similarity (clip_utils.py:10-14) applied in place to a similarity matrix of n entries:
  * sim <- sigmoid(sim * exp(logit_scale) + logit_bias). */
 int ovo_siglip_similarity(float* sim_dev, int64_t n, float logit_scale, float logit_bias, void* stream);

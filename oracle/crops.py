@@ -169,3 +169,38 @@ def extract_clip(image_u8_hwc: np.ndarray, masks: np.ndarray, W: dict, cfg: OE.V
 def siglip_similarity(txt: torch.Tensor, img: torch.Tensor, logit_scale: float, logit_bias: float) -> torch.Tensor:
     """cu:10-14."""
     return torch.sigmoid(img @ txt.T * float(np.exp(logit_scale)) + logit_bias)
+
+
+# ----------------------------------------------------------------------------------------------
+# embed_type `learned`: WeightsPredictorMerger (ovo/entities/clips_merging.py:26-56)
+# ----------------------------------------------------------------------------------------------
+def weights_predictor_merge(input_clips: torch.Tensor, W: dict, nhead: int = 8, eps: float = 1e-5) -> torch.Tensor:
+    """input_clips [B, 3, D] (global, masked crop, margin crop) -> merged [B, D], unit norm.
+    `att_encoder` = nn.TransformerEncoder of post-norm nn.TransformerEncoderLayer(activation relu) (cm:29-36; eval mode, no dropout);
+    `mlp` = Linear, LeakyReLU, n x (Linear, LeakyReLU), Linear (cm:13-24); the soft-max runs over the three clips, per channel when
+    the MLP emits 3*D weights, per clip when it emits 3 (cm:48-53).  W uses the module's own state_dict keys."""
+    b, n, d = input_clips.shape
+    hd = d // nhead
+    x = input_clips
+    L = 0
+    while f"att_encoder.layers.{L}.self_attn.in_proj_weight" in W:
+        p = f"att_encoder.layers.{L}."
+        qkv = F.linear(x, W[p + "self_attn.in_proj_weight"], W[p + "self_attn.in_proj_bias"])
+        q, k, v = (t.view(b, n, nhead, hd).transpose(1, 2) for t in qkv.split(d, dim=-1))
+        a = torch.softmax(q @ k.transpose(-1, -2) * hd ** -0.5, dim=-1) @ v
+        a = F.linear(a.transpose(1, 2).reshape(b, n, d), W[p + "self_attn.out_proj.weight"], W[p + "self_attn.out_proj.bias"])
+        x = F.layer_norm(x + a, (d,), W[p + "norm1.weight"], W[p + "norm1.bias"], eps)
+        f = F.linear(F.relu(F.linear(x, W[p + "linear1.weight"], W[p + "linear1.bias"])), W[p + "linear2.weight"], W[p + "linear2.bias"])
+        x = F.layer_norm(x + f, (d,), W[p + "norm2.weight"], W[p + "norm2.bias"], eps)
+        L += 1
+    h = x.flatten(-2, -1)
+    idx = sorted(int(k.split(".")[1]) for k in W if k.startswith("mlp.") and k.endswith(".weight"))
+    for j, i in enumerate(idx):
+        h = F.linear(h, W[f"mlp.{i}.weight"], W[f"mlp.{i}.bias"])
+        if j + 1 < len(idx):
+            h = F.leaky_relu(h, 0.01)
+    if h.shape[-1] != 3:
+        w = torch.softmax(h.reshape(b, n, d), dim=-2)
+    else:
+        w = torch.softmax(h, dim=-1).unsqueeze(-1)
+    return F.normalize((input_clips * w).sum(-2), dim=-1)

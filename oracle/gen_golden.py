@@ -505,11 +505,78 @@ def gen_update_map():
     print("update_map.npz", {k: v.shape for k, v in out.items()})
     print("before", before, "after", out["object_ids"].tolist(), "dropped", drop)
 
+MERGER_CFGS = {"per_channel": {"transformer": {"d_model": 64, "nhead": 8, "dim_feedforward": 128, "n_layers": 2},
+                               "mlp": {"i_dim": 192, "h_dim": 256, "o_dim": 192, "n_layers": 2, "act_key": "leaky_relu"}},
+               "per_clip": {"transformer": {"d_model": 64, "nhead": 4, "dim_feedforward": 64, "n_layers": 1},
+                            "mlp": {"i_dim": 192, "h_dim": 128, "o_dim": 3, "n_layers": 1, "act_key": "leaky_relu"}}}
+
+
+def merger_state_dict(cfg, seed=0):
+    """Seeded weights of WeightsPredictorMerger (clips_merging.py:26-56) under its own state_dict keys."""
+    g = torch.Generator().manual_seed(seed)
+    rn = lambda *s, std=1.0: torch.randn(*s, generator=g) * std
+    d, ff, sd = cfg["transformer"]["d_model"], cfg["transformer"]["dim_feedforward"], {}
+    for l in range(cfg["transformer"]["n_layers"]):
+        p = f"att_encoder.layers.{l}."
+        sd[p + "self_attn.in_proj_weight"] = rn(3 * d, d, std=d ** -0.5); sd[p + "self_attn.in_proj_bias"] = rn(3 * d, std=0.02)
+        sd[p + "self_attn.out_proj.weight"] = rn(d, d, std=d ** -0.5); sd[p + "self_attn.out_proj.bias"] = rn(d, std=0.02)
+        sd[p + "linear1.weight"] = rn(ff, d, std=d ** -0.5); sd[p + "linear1.bias"] = rn(ff, std=0.02)
+        sd[p + "linear2.weight"] = rn(d, ff, std=ff ** -0.5); sd[p + "linear2.bias"] = rn(d, std=0.02)
+        for n in ("norm1", "norm2"):
+            sd[p + n + ".weight"] = 1 + rn(d, std=0.05); sd[p + n + ".bias"] = rn(d, std=0.02)
+    m = cfg["mlp"]
+    dims = [m["i_dim"]] + [m["h_dim"]] * (m["n_layers"] + 1) + [m["o_dim"]]
+    for j in range(len(dims) - 1):
+        sd[f"mlp.{2 * j}.weight"] = rn(dims[j + 1], dims[j], std=2.0 * dims[j] ** -0.5); sd[f"mlp.{2 * j}.bias"] = rn(dims[j + 1], std=0.1)
+    return sd
+
+
+def gen_merger():
+    """embed_type `learned`: the UNMODIFIED CLIPGenerator (learned branch, clip_generator.py:18-29,150-154) + WeightsPredictorMerger
+    (clips_merging.py) loading a seeded checkpoint the way the reference loads its own (hparams.yaml + model.pt)."""
+    import yaml
+    from ovo_b200 import synth
+    rh.setup_paths()
+    model, sd, cfg = build_reference_model()
+    import ovo.utils.clip_utils as cu
+    from torchvision.transforms import Resize, Normalize, CenterCrop, Compose
+    import core.vision_encoder.transforms as transforms
+
+    def fake_loader(model_card, use_half):
+        pre = transforms.get_image_transform(model.image_size)
+        keep = [tf for tf in pre.transforms if isinstance(tf, (Resize, CenterCrop, Normalize))]
+        return model, None, Compose(keep), cfg.output_dim
+
+    cu.load_clip_model = fake_loader
+    from ovo.entities.clip_generator import CLIPGenerator
+    from ovo.entities.clips_merging import WeightsPredictorMerger
+    img = synth.rgb(480, 640, seed=21)
+    bm = crop_masks()
+    imt = torch.from_numpy(img.transpose(2, 0, 1).copy())
+    out = {}
+    g = torch.Generator().manual_seed(9)
+    clips = torch.nn.functional.normalize(torch.randn(11, 3, 64, generator=g), dim=-1)
+    for name, mc in MERGER_CFGS.items():
+        msd = merger_state_dict(mc, seed=5)
+        with tempfile.TemporaryDirectory() as tmp:
+            with open(os.path.join(tmp, "hparams.yaml"), "w") as f:
+                yaml.safe_dump({"model": mc}, f)
+            ref = WeightsPredictorMerger(mc).eval()
+            ref.load_state_dict(msd)
+            torch.save(ref.state_dict(), os.path.join(tmp, "model.pt"))
+            gen = CLIPGenerator({"embed_type": "learned", "model_card": "PE-Core-L-14-336", "mask_res": 336,
+                                 "weights_predictor_path": tmp}, device="cpu")
+            with torch.no_grad():
+                out[f"learned_{name}"] = gen.extract_clip(imt, torch.from_numpy(bm)).numpy()
+                out[f"merge_{name}"] = ref(clips).numpy()
+    np.savez_compressed(os.path.join(OUT, "merger.npz"), **out)
+    print("merger.npz", {k: v.shape for k, v in out.items()})
+
 
 if __name__ == "__main__":
     if not rh.available():
         sys.exit("reference not available: fixtures can only be generated in the build container")
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["encoder", "assoc", "ovo", "masks", "mapper", "sam", "encoder_hd80", "crops", "labels", "update_map"]
+    which = sys.argv[1:] or ["encoder", "assoc", "ovo", "masks", "mapper", "sam", "encoder_hd80", "crops", "labels", "update_map", "merger"]
     for w in which:
         globals()["gen_" + w]()

@@ -40,6 +40,17 @@ class CropParams(C.Structure):
                 ("w_masked", c_float), ("w_global", c_float)]
 
 
+class MergerLayer(C.Structure):
+    _fields_ = [(n, c_void_p) for n in ("in_w", "in_b", "out_w", "out_b", "ln1_w", "ln1_b", "ff1_w", "ff1_b", "ff2_w", "ff2_b",
+                                        "ln2_w", "ln2_b")]
+
+
+class MergerWeights(C.Structure):
+    _fields_ = [("d_model", c_int), ("nhead", c_int), ("dim_feedforward", c_int), ("n_layers", c_int),
+                ("layers", C.POINTER(MergerLayer)), ("n_linear", c_int), ("mlp_w", C.POINTER(c_void_p)),
+                ("mlp_b", C.POINTER(c_void_p)), ("mlp_out", C.POINTER(c_int)), ("ln_eps", c_float)]
+
+
 EMBED_TYPES = {"vanilla": 0, "fixed_weights": 1, "hovsg": 2, "adaptive_weights": 3, "concept_fusion": 4}
 
 
@@ -115,6 +126,7 @@ SIGNATURES = {
     "ovo_encode_crops": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, C.POINTER(CropParams), c_void_p, c_void_p,
                                  c_void_p]),
     "ovo_fuse_clips": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_float, c_void_p, c_void_p]),
+    "ovo_merge_clips_learned": (c_int, [C.POINTER(MergerWeights), c_void_p, c_int, c_void_p, c_void_p]),
     "ovo_siglip_similarity": (c_int, [c_void_p, c_int64, c_float, c_float, c_void_p]),
     "ovo_knn": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_float, c_void_p, c_void_p, c_void_p]),
     "ovo_knn_stats": (None, [C.POINTER(c_float), C.POINTER(c_int), C.POINTER(c_int)]),

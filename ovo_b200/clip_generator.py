@@ -17,21 +17,69 @@ from . import _lib
 from ._lib import check, ptr, stream_ptr
 from .encoder import EncoderConfig, RegionEncoder, random_state_dict
 
+
+class LearnedMerger:
+    """`WeightsPredictorMerger` (ovo/entities/clips_merging.py:26-56) on the device: packs the module's state_dict
+    (`att_encoder.layers.{l}.*`, `mlp.{2j}.*`) and calls `ovo_merge_clips_learned`."""
+
+    def __init__(self, model_config: Dict, state_dict: Dict, device):
+        import ctypes as C
+        from ._lib import MergerLayer, MergerWeights
+        self.device = torch.device(device)
+        self._keep = []
+        t = model_config["transformer"]
+        f32, bf = torch.float32, torch.bfloat16
+
+        def dev(x, dt):
+            x = x.detach().to(self.device, dt).contiguous()
+            self._keep.append(x)
+            return ptr(x)
+        n_layers = t["n_layers"]
+        layers = (MergerLayer * max(n_layers, 1))()
+        for l in range(n_layers):
+            p = f"att_encoder.layers.{l}."
+            layers[l] = MergerLayer(dev(state_dict[p + "self_attn.in_proj_weight"], bf), dev(state_dict[p + "self_attn.in_proj_bias"], f32),
+                                    dev(state_dict[p + "self_attn.out_proj.weight"], bf), dev(state_dict[p + "self_attn.out_proj.bias"], f32),
+                                    dev(state_dict[p + "norm1.weight"], f32), dev(state_dict[p + "norm1.bias"], f32),
+                                    dev(state_dict[p + "linear1.weight"], bf), dev(state_dict[p + "linear1.bias"], f32),
+                                    dev(state_dict[p + "linear2.weight"], bf), dev(state_dict[p + "linear2.bias"], f32),
+                                    dev(state_dict[p + "norm2.weight"], f32), dev(state_dict[p + "norm2.bias"], f32))
+        idx = sorted(int(k.split(".")[1]) for k in state_dict if k.startswith("mlp.") and k.endswith(".weight"))
+        n = len(idx)
+        mw, mb, mo = (C.c_void_p * n)(), (C.c_void_p * n)(), (C.c_int * n)()
+        for j, i in enumerate(idx):
+            mw[j], mb[j] = dev(state_dict[f"mlp.{i}.weight"], bf), dev(state_dict[f"mlp.{i}.bias"], f32)
+            mo[j] = state_dict[f"mlp.{i}.weight"].shape[0]
+        self._keep += [layers, mw, mb, mo]
+        self.d_model = t["d_model"]
+        self.w = MergerWeights(t["d_model"], t.get("nhead", 8), t["dim_feedforward"], n_layers, layers, n, mw, mb, mo, 1e-5)
+
+    def __call__(self, clips: torch.Tensor) -> torch.Tensor:
+        """clips [B,3,D] -> [B,D] unit norm."""
+        import ctypes as C
+        clips = clips.to(self.device, torch.float32).contiguous()
+        assert clips.dim() == 3 and clips.shape[1] == 3 and clips.shape[2] == self.d_model, "merger expects [B, 3, d_model] descriptors"
+        out = torch.empty(clips.shape[0], clips.shape[2], device=self.device, dtype=torch.float32)
+        if clips.shape[0]:
+            check(_lib.lib().ovo_merge_clips_learned(C.byref(self.w), ptr(clips), clips.shape[0], ptr(out), stream_ptr()),
+                  "ovo_merge_clips_learned")
+        return out
+
 MODEL_CARDS = {"PE-Core-L14-336": EncoderConfig(), "PE-Core-L-14-336": EncoderConfig()}
-CROP_EMBED_TYPES = ("vanilla", "fixed_weights", "hovsg", "adaptive_weights", "concept_fusion")
+CROP_EMBED_TYPES = ("vanilla", "fixed_weights", "hovsg", "adaptive_weights", "concept_fusion", "learned")
 
 
 class CLIPGenerator:
     def __init__(self, config: Dict, device: str = "cuda", state_dict: dict | None = None, tokenizer=None,
-                 encoder_config: EncoderConfig | None = None, encoder: RegionEncoder | None = None):
+                 encoder_config: EncoderConfig | None = None, encoder: RegionEncoder | None = None,
+                 merger_config: Dict | None = None, merger_state_dict: Dict | None = None):
         self.config = config
         self.device = device
         self.embed_type = config.get("embed_type", "vanilla")
         self.mask_res = config.get("mask_res", 384)
         if self.embed_type != "TextRegion" and self.embed_type not in CROP_EMBED_TYPES:
             raise NotImplementedError(
-                f"ovo_b200: embed_type '{self.embed_type}' is not built (have TextRegion, {', '.join(CROP_EMBED_TYPES)}); "
-                "`learned` needs the SigLIP-1152 weights-predictor checkpoint of clips_merging.py")
+                f"ovo_b200: embed_type '{self.embed_type}' is not built (have TextRegion, {', '.join(CROP_EMBED_TYPES)})")
         self.w_masked = config.get("w_masked", 0.4418)      # clip_generator.py:33-34
         self.w_global = config.get("w_global", 0.1)
         self.model_card = config.get("model_card", "PE-Core-L14-336")
@@ -57,6 +105,18 @@ class CLIPGenerator:
         self._tokenizer = tokenizer
         if self.embed_type in CROP_EMBED_TYPES and not self.encoder.has_pool_head:
             self.encoder.install_pool_head(state_dict, pool_heads=getattr(cfg, "pool_heads", 8))
+        self.clips_fusion_model = None
+        if self.embed_type == "learned":          # clip_generator.py:18-29: hparams.yaml + model.pt under weights_predictor_path
+            import yaml
+            mcfg, msd = merger_config, merger_state_dict
+            if msd is None:
+                with open(os.path.join(config["weights_predictor_path"], "hparams.yaml"), "r") as f:
+                    mcfg = yaml.safe_load(f)["model"]
+                msd = torch.load(os.path.join(config["weights_predictor_path"], "model.pt"), map_location="cpu", weights_only=True)
+            if mcfg["transformer"]["d_model"] != self.clip_dim:
+                raise ValueError(f"weights predictor was trained for {mcfg['transformer']['d_model']}-d descriptors (the reference's SigLIP "
+                                 f"cards), the encoder emits {self.clip_dim}")
+            self.clips_fusion_model = LearnedMerger(mcfg, msd, self.encoder.device)
         # clip_generator.py:54-72: SigLIP cards score with sigmoid(sim * exp(logit_scale) + logit_bias).  No SigLIP
         # architecture is built in; the rule applies when a caller supplies such an encoder_config under a SigLIP card.
         self.similarity_args = ()
@@ -98,6 +158,9 @@ class CLIPGenerator:
             return self.encoder.encode_regions(image.contiguous(), binary_maps)
         if binary_maps.shape[0] == 0:
             return torch.tensor([], device=self.encoder.device)          # clip_generator.py:141-142
+        if self.embed_type == "learned":          # clip_generator.py:150-154: the three descriptors, merged by the predictor
+            allc = self.encoder.encode_crops(image.contiguous(), binary_maps, "fixed_weights", mask_res=self.mask_res, return_all=True)
+            return allc if return_all else self.clips_fusion_model(allc)
         return self.encoder.encode_crops(image.contiguous(), binary_maps, self.embed_type, mask_res=self.mask_res,
                                          w_masked=self.w_masked, w_global=self.w_global, return_all=return_all)
 

@@ -586,6 +586,79 @@ __global__ void sigmoid_affine_kernel(float* __restrict__ sim, size_t n, float s
   if (i < n) sim[i] = 1.f / (1.f + expf(-(sim[i] * scale + bias)));
 }
 
+// ------------------------------------------------------------------------------------------- embed_type `learned`
+// WeightsPredictorMerger (ovo/entities/clips_merging.py:26-56): a small post-norm transformer over the THREE descriptors of a mask
+// (global, masked crop, margin crop), an MLP on the flattened tokens, soft-max weights over the three, weighted sum, L2 norm.
+// Self-attention over 3 tokens: one thread per (mask, head).  qkv f32 [3B, 3d] (q | k | v) -> out bf16 [3B, d].
+__global__ void merger_attention_kernel(const float* __restrict__ qkv, int B, int d, int nhead, __nv_bfloat16* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * nhead) return;
+  const int b = i / nhead, h = i - b * nhead, hd = d / nhead;
+  const float* base = qkv + static_cast<size_t>(b) * 3 * 3 * d + h * hd;
+  float sc[3][3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) sc[a][c] = 0.f;
+  for (int e = 0; e < hd; ++e) {
+    float q[3], k[3];
+#pragma unroll
+    for (int t = 0; t < 3; ++t) { q[t] = base[static_cast<size_t>(t) * 3 * d + e]; k[t] = base[static_cast<size_t>(t) * 3 * d + d + e]; }
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) sc[a][c] += q[a] * k[c];
+  }
+  const float scale = rsqrtf(static_cast<float>(hd));
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const float m = fmaxf(fmaxf(sc[a][0], sc[a][1]), sc[a][2]) * scale;
+    float sum = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { sc[a][c] = expf(sc[a][c] * scale - m); sum += sc[a][c]; }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) sc[a][c] /= sum;
+  }
+  for (int e = 0; e < hd; ++e) {
+    float v[3];
+#pragma unroll
+    for (int t = 0; t < 3; ++t) v[t] = base[static_cast<size_t>(t) * 3 * d + 2 * d + e];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+      out[(static_cast<size_t>(b) * 3 + a) * d + h * hd + e] = __float2bfloat16_rn(sc[a][0] * v[0] + sc[a][1] * v[1] + sc[a][2] * v[2]);
+  }
+}
+
+// nn.LeakyReLU (slope 0.01, clips_merging.py:6-11) on an f32 GEMM output -> bf16 operand of the next linear
+__global__ void leaky_relu_bf16_kernel(const float* __restrict__ x, size_t n, __nv_bfloat16* __restrict__ o) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) { const float v = x[i]; o[i] = __float2bfloat16_rn(v > 0.f ? v : 0.01f * v); }
+}
+
+// clips_merging.py:48-55: soft-max over the three clips (per channel when the MLP emits 3*D weights, per clip when it emits 3),
+// weighted sum, F.normalize.  One warp per mask.
+__global__ void merger_combine_kernel(const float* __restrict__ clips, const float* __restrict__ wts, int B, int D, int o_dim,
+                                      float* __restrict__ out) {
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (b >= B) return;
+  const float* c = clips + static_cast<size_t>(b) * 3 * D;
+  const float* w = wts + static_cast<size_t>(b) * o_dim;
+  float* o = out + static_cast<size_t>(b) * D;
+  float ss = 0.f;
+  for (int d = lane; d < D; d += 32) {
+    float l[3];
+#pragma unroll
+    for (int t = 0; t < 3; ++t) l[t] = o_dim == 3 ? w[t] : w[t * D + d];
+    const float m = fmaxf(fmaxf(l[0], l[1]), l[2]);
+    const float e0 = expf(l[0] - m), e1 = expf(l[1] - m), e2 = expf(l[2] - m);
+    const float v = (c[d] * e0 + c[D + d] * e1 + c[2 * D + d] * e2) / (e0 + e1 + e2);
+    o[d] = v; ss += v * v;
+  }
+  ss = warp_sum(ss);
+  const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+  for (int d = lane; d < D; d += 32) o[d] *= inv;
+}
+
 }  // namespace ovo
 
 // =============================================================================================== handle
@@ -1341,6 +1414,82 @@ int ovo_encode_crops(ovo_encoder_t* e, const uint8_t* rgb_dev, int H, int W, con
                                                         prm->w_masked, prm->w_global, out_dev);
     OVO_CHECK_LAUNCH();
   }
+  return OVO_OK;
+}
+
+int ovo_merge_clips_learned(const ovo_merger_weights* w, const float* clips_dev, int B, float* out_dev, void* stream_) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream_);
+  OVO_REQUIRE(w && clips_dev && out_dev && B > 0, "ovo_merge_clips_learned: bad arguments");
+  const int d = w->d_model, ff = w->dim_feedforward, R = 3 * B;
+  OVO_REQUIRE(d > 0 && w->nhead > 0 && d % w->nhead == 0 && d % 8 == 0 && d <= 2048 && ff > 0 && ff % 8 == 0, "merger: unsupported d_model %d / nhead %d / ff %d", d, w->nhead, ff);
+  OVO_REQUIRE(w->n_layers >= 0 && (w->n_layers == 0 || w->layers) && w->n_linear >= 1 && w->mlp_w && w->mlp_b && w->mlp_out, "merger: missing weights");
+  const int o_dim = w->mlp_out[w->n_linear - 1];
+  OVO_REQUIRE(o_dim == 3 || o_dim == 3 * d, "merger: the MLP must emit 3 or 3*d_model weights (got %d)", o_dim);
+  int maxdim = 3 * d;
+  for (int j = 0; j < w->n_linear; ++j) {
+    OVO_REQUIRE(w->mlp_out[j] > 0 && (j + 1 == w->n_linear || w->mlp_out[j] % 8 == 0), "merger: MLP width %d unsupported", w->mlp_out[j]);
+    maxdim = std::max(maxdim, w->mlp_out[j]);
+  }
+  typedef const __nv_bfloat16* bfp;
+  keep_default_mempool_cached();
+  float *x = nullptr, *x2 = nullptr, *qkv = nullptr, *y = nullptr;
+  __nv_bfloat16 *xb = nullptr, *att = nullptr, *h = nullptr, *a0 = nullptr, *a1 = nullptr;
+  const size_t Rp = static_cast<size_t>(R) + 128, Bp = static_cast<size_t>(B) + 128;
+  OVO_CUDA(cudaMallocAsync(&x, Rp * d * 4, s));
+  OVO_CUDA(cudaMallocAsync(&x2, Rp * d * 4, s));
+  OVO_CUDA(cudaMallocAsync(&qkv, Rp * 3 * d * 4, s));
+  OVO_CUDA(cudaMallocAsync(&xb, Rp * d * 2, s));
+  OVO_CUDA(cudaMallocAsync(&att, Rp * d * 2, s));
+  OVO_CUDA(cudaMallocAsync(&h, Rp * ff * 2, s));
+  OVO_CUDA(cudaMallocAsync(&y, Bp * maxdim * 4, s));
+  OVO_CUDA(cudaMallocAsync(&a0, Bp * maxdim * 2, s));
+  OVO_CUDA(cudaMallocAsync(&a1, Bp * maxdim * 2, s));
+  OVO_CUDA(cudaMemcpyAsync(x, clips_dev, static_cast<size_t>(R) * d * 4, cudaMemcpyDeviceToDevice, s));
+  {
+    const size_t n4 = static_cast<size_t>(R) * d / 4;
+    f32_to_bf16_kernel<<<ceil_div(n4, 256), 256, 0, s>>>(x, n4, xb);
+    OVO_CHECK_LAUNCH();
+  }
+  for (int l = 0; l < w->n_layers; ++l) {   // nn.TransformerEncoderLayer, norm_first=False, relu (clips_merging.py:29-36)
+    const ovo_merger_layer& L = w->layers[l];
+    EpiParams qe;
+    qe.out = qkv; qe.ldo = 3 * d; qe.bias = L.in_b;
+    OVO_TRY(launch_gemm(EPI_F32, xb, d, static_cast<bfp>(L.in_w), d, R, 3 * d, d, qe, s));
+    merger_attention_kernel<<<ceil_div(B * w->nhead, 128), 128, 0, s>>>(qkv, B, d, w->nhead, att);
+    OVO_CHECK_LAUNCH();
+    EpiParams oe;
+    oe.out = x2; oe.ldo = d; oe.bias = L.out_b; oe.resid = x; oe.ldr = d;
+    OVO_TRY(launch_gemm(EPI_F32_RESID, att, d, static_cast<bfp>(L.out_w), d, R, d, d, oe, s));
+    OVO_TRY(launch_ln(x2, R, d, L.ln1_w, L.ln1_b, w->ln_eps, xb, x, nullptr, s));
+    EpiParams f1;
+    f1.out = h; f1.ldo = ff; f1.bias = L.ff1_b;
+    OVO_TRY(launch_gemm(EPI_BF16_RELU, xb, d, static_cast<bfp>(L.ff1_w), d, R, ff, d, f1, s));
+    EpiParams f2;
+    f2.out = x2; f2.ldo = d; f2.bias = L.ff2_b; f2.resid = x; f2.ldr = d;
+    OVO_TRY(launch_gemm(EPI_F32_RESID, h, ff, static_cast<bfp>(L.ff2_w), ff, R, d, ff, f2, s));
+    OVO_TRY(launch_ln(x2, R, d, L.ln2_w, L.ln2_b, w->ln_eps, xb, x, nullptr, s));
+  }
+  // MLP on the flattened tokens: xb [3B, d] row-major IS [B, 3d]
+  const __nv_bfloat16* cur = xb;
+  int in_dim = 3 * d;
+  for (int j = 0; j < w->n_linear; ++j) {
+    const int out_dim = w->mlp_out[j];
+    EpiParams me;
+    me.out = y; me.ldo = out_dim; me.bias = w->mlp_b[j];
+    OVO_TRY(launch_gemm(EPI_F32, cur, in_dim, static_cast<bfp>(w->mlp_w[j]), in_dim, B, out_dim, in_dim, me, s));
+    if (j + 1 < w->n_linear) {
+      __nv_bfloat16* nxt = (j & 1) ? a1 : a0;
+      const size_t n = static_cast<size_t>(B) * out_dim;
+      leaky_relu_bf16_kernel<<<ceil_div(n, 256), 256, 0, s>>>(y, n, nxt);
+      OVO_CHECK_LAUNCH();
+      cur = nxt;
+    }
+    in_dim = out_dim;
+  }
+  merger_combine_kernel<<<ceil_div(B, 8), 256, 0, s>>>(clips_dev, y, B, d, o_dim, out_dev);
+  OVO_CHECK_LAUNCH();
+  cudaFreeAsync(x, s); cudaFreeAsync(x2, s); cudaFreeAsync(qkv, s); cudaFreeAsync(xb, s); cudaFreeAsync(att, s); cudaFreeAsync(h, s);
+  cudaFreeAsync(y, s); cudaFreeAsync(a0, s); cudaFreeAsync(a1, s);
   return OVO_OK;
 }
 

@@ -161,7 +161,7 @@ def test_degenerate_and_error_paths(tiny):
         bare.encode_crops(img, torch.from_numpy(bm[:1]).cuda(), "vanilla")
     from ovo_b200 import CLIPGenerator
     with pytest.raises(NotImplementedError):
-        CLIPGenerator({"embed_type": "learned"}, state_dict=sd, encoder_config=cfg)
+        CLIPGenerator({"embed_type": "no_such_type"}, state_dict=sd, encoder_config=cfg)
     gen = CLIPGenerator({"embed_type": "hovsg", "mask_res": 336, "max_images": 8, "max_h": 480, "max_w": 640, "max_masks": 16},
                         state_dict=sd, encoder_config=EncoderConfig(**{**GG.TINY, "pool_heads": GG.CROP_POOL_HEADS}))
     assert gen.extract_clip(img.permute(2, 0, 1), torch.zeros(0, 480, 640, dtype=torch.bool, device="cuda")).numel() == 0
@@ -216,3 +216,51 @@ def test_ovo_api_with_crop_descriptors(tmp_path):
     assert list(ovo.objects.keys()) == list(orc.objects.keys())
     got, ref = ovo.get_objs_clips().cpu(), orc.bank()
     assert (1 - torch.nn.functional.cosine_similarity(got, ref, dim=-1)).max().item() < 1e-3
+
+
+@pytest.mark.parametrize("name", list(GG.MERGER_CFGS))
+def test_learned_merger_matches_reference(tiny, golden_dir, name):
+    """embed_type `learned` (clips_merging.py:26-56): the merger alone on seeded descriptors, then behind CLIPGenerator.extract_clip,
+    against the reference module / the reference's CLIPGenerator (tests/golden/merger.npz)."""
+    from ovo_b200 import CLIPGenerator
+    from ovo_b200.clip_generator import LearnedMerger
+    g = np.load(os.path.join(golden_dir, "merger.npz"))
+    cfg, ocfg, sd, enc = tiny
+    mc = GG.MERGER_CFGS[name]
+    msd = GG.merger_state_dict(mc, seed=5)
+    gen = torch.Generator().manual_seed(9)
+    clips = torch.nn.functional.normalize(torch.randn(11, 3, 64, generator=gen), dim=-1)
+    merger = LearnedMerger(mc, msd, "cuda:0")
+    got = merger(clips.cuda()).cpu()
+    ref = torch.from_numpy(g[f"merge_{name}"])
+    assert (1 - torch.nn.functional.cosine_similarity(got, ref, dim=-1)).max().item() < 1e-3
+    assert ((got - ref).norm() / ref.norm()).item() < 1e-2
+    with torch.no_grad():
+        orc = OC.weights_predictor_merge(clips, msd, nhead=mc["transformer"]["nhead"])
+    assert (1 - torch.nn.functional.cosine_similarity(got, orc, dim=-1)).max().item() < 1e-3
+    clipgen = CLIPGenerator({"embed_type": "learned", "mask_res": 336}, encoder=enc, merger_config=mc, merger_state_dict=msd)
+    img, bm = synth.rgb(480, 640, seed=21), GG.crop_masks()
+    f = clipgen.extract_clip(torch.from_numpy(img).cuda(), torch.from_numpy(bm).cuda()).cpu()
+    ref = torch.from_numpy(g[f"learned_{name}"])
+    assert f.shape == ref.shape
+    assert (1 - torch.nn.functional.cosine_similarity(f, ref, dim=-1)).max().item() < 1e-3
+    assert ((f - ref).norm() / ref.norm()).item() < 1e-2
+    with pytest.raises(ValueError):          # a predictor trained for another descriptor width (the reference's is SigLIP's 1152)
+        CLIPGenerator({"embed_type": "learned"}, encoder=enc, merger_state_dict=msd,
+                      merger_config={"transformer": {**mc["transformer"], "d_model": 1152}, "mlp": mc["mlp"]})
+
+
+def test_learned_merger_reference_geometry():
+    """The shipped hparams (data/input/weights_predictor/base/hparams.yaml: d_model 1152, 8 heads, 5 layers, MLP 3456 -> 13824 x5 ->
+    3456) with seeded weights, against the oracle."""
+    from ovo_b200.clip_generator import LearnedMerger
+    mc = {"transformer": {"d_model": 1152, "nhead": 8, "dim_feedforward": 1152, "n_layers": 5},
+          "mlp": {"i_dim": 3456, "h_dim": 13824, "o_dim": 3456, "n_layers": 4, "act_key": "leaky_relu"}}
+    msd = GG.merger_state_dict(mc, seed=2)
+    gen = torch.Generator().manual_seed(4)
+    clips = torch.nn.functional.normalize(torch.randn(40, 3, 1152, generator=gen) + torch.randn(40, 1, 1152, generator=gen), dim=-1)
+    got = LearnedMerger(mc, msd, "cuda:0")(clips.cuda()).cpu()
+    with torch.no_grad():
+        orc = OC.weights_predictor_merge(clips, msd, nhead=8)
+    assert (1 - torch.nn.functional.cosine_similarity(got, orc, dim=-1)).max().item() < 1e-3
+    assert (got.norm(dim=-1) - 1).abs().max().item() < 1e-5

@@ -88,3 +88,22 @@ def test_siglip_similarity():
     img, txt = torch.randn(5, 16, generator=g), torch.randn(3, 16, generator=g)
     s = OC.siglip_similarity(txt, img, np.log(10.0), -10.0)
     assert torch.allclose(s, torch.sigmoid(img @ txt.T * 10.0 - 10.0), atol=1e-6)
+
+
+@pytest.mark.parametrize("name", list(GG.MERGER_CFGS))
+def test_learned_merger_matches_reference(setup, golden_dir, name):
+    """embed_type `learned` (clips_merging.py:26-56): the oracle's merger against the reference module, stand-alone and behind the
+    reference's CLIPGenerator."""
+    g = np.load(os.path.join(golden_dir, "merger.npz"))
+    ocfg, sd, img, bm = setup
+    mc = GG.MERGER_CFGS[name]
+    msd = GG.merger_state_dict(mc, seed=5)
+    gen = torch.Generator().manual_seed(9)
+    clips = torch.nn.functional.normalize(torch.randn(11, 3, 64, generator=gen), dim=-1)
+    with torch.no_grad():
+        m = OC.weights_predictor_merge(clips, msd, nhead=mc["transformer"]["nhead"])
+        assert (m - torch.from_numpy(g[f"merge_{name}"])).abs().max().item() < 2e-6
+        allc = OC.extract_clip(img, bm, sd, ocfg, "fixed_weights", mask_res=336, return_all=True, pool_heads=GG.CROP_POOL_HEADS)
+        f = OC.weights_predictor_merge(allc, msd, nhead=mc["transformer"]["nhead"])
+    ref = torch.from_numpy(g[f"learned_{name}"])
+    assert (1 - torch.nn.functional.cosine_similarity(f, ref, dim=-1)).max().item() < 1e-5
