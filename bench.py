@@ -238,7 +238,16 @@ def run_ours(args, rank, world, local_rank):
     e2e = run_e2e(args, rank, world, dev, enc, K, xyz, ids, ins, seg, bm, fr, dist)
 
     # --- SURVEY 8f rows (crop-based descriptors, label transfer): separate stage reports, rank 0 of a single-GPU run only
-    nxt = run_next_rows(args, dev, enc, sd, bm, fr, xyz, tf_sus, how) if (world == 1 and not args.no_next_rows) else None
+    # (stage reports beside the headline: a failure there is reported in place and never costs the headline line)
+    def stage(fn, *a):
+        try:
+            return fn(*a)
+        except Exception as e:  # noqa: BLE001
+            import traceback
+            traceback.print_exc(file=sys.stderr)
+            return {"error": f"{type(e).__name__}: {e}"}
+    nxt = stage(run_next_rows, args, dev, enc, sd, bm, fr, xyz, tf_sus, how) if (world == 1 and not args.no_next_rows) else None
+    stream = stage(run_stream, args, dev, enc, hbm, how) if (world == 1 and not args.no_stream) else None
 
     if rank != 0:
         return
@@ -256,7 +265,9 @@ def run_ours(args, rank, world, local_rank):
     if sam is not None:
         out["sam"] = sam
     if nxt is not None:
-        out.update(nxt)
+        out.update(nxt if "error" not in nxt else {"next_rows": nxt})
+    if stream is not None:
+        out["stream"] = stream
     if not args.no_cpu_baseline and world >= 1:
         out["cpu_baseline"] = cpu_baseline(args, budget_frames=1)
         if sam is not None:
@@ -380,6 +391,83 @@ def run_next_rows(args, dev, enc, sd, bm, fr, xyz, tf_sus, how):
     return out
 
 
+def run_stream(args, dev, enc, hbm, how):
+    """BASELINE config 5 through the public classes: a synthetic 640x480 RGB-D stream whose every frame is mapped
+    (PointMapper.map = VanillaMapper.map) and is a keyframe (OVO.detect_and_track_objects + compute_semantic_info, dense per-point
+    bank on), the camera moving so that each frame sees new surface: the map grows 0 -> 8M points; a Q=20 dense query over the
+    whole map every 10 frames.  Per-frame latency = CUDA events around the frame's calls, host inputs (pinned), one sync per frame."""
+    from ovo_b200 import OVO, CLIPGenerator, synth
+    from ovo_b200.mapper import PointMapper
+    K = synth.intrinsics()
+    seg, bm = synth.grid_masks(rows=6, cols=8)
+    target = 8_000_000
+
+    class _Logger:
+        def log_ovo_stats(self, *a, **k): pass
+
+    class HostMasks:
+        def __init__(self):
+            self.seg, self.bm = torch.from_numpy(seg).pin_memory(), torch.from_numpy(bm).pin_memory()
+        def get_masks(self, image, frame_id=None):
+            return self.seg.to(dev, non_blocking=True), self.bm.to(dev, non_blocking=True)
+        def cpu(self): pass
+        def cuda(self): pass
+
+    config = {"segment_every": 1, "match_distance_th": 0.05, "track_th": 100, "depth_filter": True, "log": False, "kf_queue_delay": 0,
+              "verbose": False, "dense_map": True, "dense_capacity": target + 200_000, "store_capacity": 16384, "bank_capacity": 16384, "sam": {"precomputed": True, "masks_base_path": ""},
+              "clip": {"embed_type": "TextRegion", "model_card": "PE-Core-L14-336", "k_top_views": 10000, "fusion": "avg_pooling"}}
+    ovo = OVO(config, _Logger(), scene_name=None, cam_intrinsics=torch.from_numpy(K), eval=True,
+              clip_generator=CLIPGenerator(config["clip"], encoder=enc), device="cuda")
+    ovo.mask_generator = HostMasks()
+    pm = PointMapper({"device": "cuda", "mapping": {"k_pooling": 3, "reserve_points": target + 200_000}}, torch.from_numpy(K), semmap=ovo.semmap)
+    imgs = [torch.from_numpy(synth.rgb(seed=50 + i)).pin_memory().numpy() for i in range(8)]
+    deps = [torch.from_numpy(synth.depth_map(frame_id=i)).pin_memory().numpy() for i in range(8)]
+    text = torch.nn.functional.normalize(torch.randn(20, enc.cfg.output_dim, device=dev), dim=-1)
+    qout = torch.empty(target + 200_000, 20, device=dev)
+    lat, qlat, sizes = [], [], []
+    fid = 0
+    while pm.n < target and fid < 160:
+        c2w = synth.pose(250 * fid)                       # 2.5 m per frame: every frame looks at unmapped surface
+        c2w_t = torch.from_numpy(c2w)
+        img, d = imgs[fid % 8], deps[fid % 8]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        pm.map([fid, img, d, c2w], c2w_t)
+        pts, pids, obj = pm.get_map()
+        upd = ovo.detect_and_track_objects((fid, img, d, ()), (pts, pids, obj), c2w_t)
+        if upd is not None:
+            pm.update_pcd_obj_ids(upd)
+        ovo.compute_semantic_info()
+        ovo._sync_descriptors()                           # the frame ends when its descriptors and dense fusion are done
+        e1.record()
+        q0 = q1 = None
+        if fid % 10 == 9:
+            q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            q0.record()
+            ovo.semmap.query_dense(ovo._dense_bank[: pm.n], text, qout[: pm.n])
+            q1.record()
+        torch.cuda.synchronize()
+        if fid >= 3:                                      # the first frames pay one-off allocations / graph capture
+            lat.append(e0.elapsed_time(e1) + (q0.elapsed_time(q1) if q0 is not None else 0.0))
+        if q0 is not None:
+            qlat.append((int(pm.n), round(q0.elapsed_time(q1), 3)))
+        sizes.append(int(pm.n))
+        fid += 1
+    a = np.array(lat)
+    D = enc.cfg.output_dim
+    qn, qms = qlat[-1]
+    del ovo, pm
+    torch.cuda.empty_cache()
+    return {"metric": "BASELINE config 5: streaming 640x480 RGB-D, every frame mapped + keyframe, map 0 -> 8M points, dense Q=20 query every 10 frames",
+            "frames": fid, "final_points": sizes[-1], "points_per_frame": int(np.mean(np.diff(sizes))) if len(sizes) > 1 else sizes[-1],
+            "sustained_fps": round(1e3 * len(a) / a.sum(), 1),
+            "frame_ms": {"p50": round(float(np.percentile(a, 50)), 3), "p90": round(float(np.percentile(a, 90)), 3),
+                         "p99": round(float(np.percentile(a, 99)), 3), "max": round(float(a.max()), 3),
+                         "slowest_frames": [[int(i) + 3, round(float(a[i]), 2)] for i in np.argsort(-a)[:4]]},
+            "realtime_30fps_budget_ms": 33.3, "query_ms_vs_points": qlat,
+            "query_gbs_at_final_size": round((qn * D * 2 + qn * 20 * 4) / qms / 1e6, 1), "hbm_peak_gbs": hbm, "peak_source": f"{how} hbm_gbs"}
+
+
 def run_e2e(args, rank, world, dev, enc, K, xyz, ids, ins, seg, bm, fr, dist):
     """The call a user makes: OVO.detect_and_track_objects + compute_semantic_info per keyframe with numpy
     (pinned) image/depth/masks on the host; the new descriptors are read back each keyframe."""
@@ -433,7 +521,9 @@ def run_e2e(args, rank, world, dev, enc, K, xyz, ids, ins, seg, bm, fr, dist):
             ovo.keyframes["ins_descriptors"].clear()
             ovo._desc_epoch += 1
 
-    steps = max(1, min(args.steps, 10))
+    # 30 steps (240 keyframes, ~0.35 s): the loop is host-driven, and on the pool's VMs a single host hiccup of ~100 ms (seen as
+    # isolated slow steps, different ones from run to run) would otherwise decide a 10-step figure
+    steps = max(1, min(3 * args.steps, 30))
     for _ in range(max(3, min(args.warmup, 3))):
         step()
     torch.cuda.synchronize()
@@ -449,13 +539,17 @@ def run_e2e(args, rank, world, dev, enc, K, xyz, ids, ins, seg, bm, fr, dist):
         pstats.Stats(pr, stream=sys.stderr).sort_stats("cumulative").print_stats(35)
     if dist:
         dist.barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(steps):
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    walls = []
+    marks[0].record()
+    for i in range(steps):
+        t0 = time.perf_counter()
         step()
-    e1.record()
+        walls.append((time.perf_counter() - t0) * 1e3)
+        marks[i + 1].record()
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
+    ms = marks[0].elapsed_time(marks[-1])
+    per_step = np.array([marks[i].elapsed_time(marks[i + 1]) for i in range(steps)])
     if dist:
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -465,7 +559,11 @@ def run_e2e(args, rank, world, dev, enc, K, xyz, ids, ins, seg, bm, fr, dist):
     d2h = F * (bm.shape[0] * enc.cfg.output_dim * 4 + bm.shape[0] * 32)
     return {"value": round(world * F * steps / (ms / 1e3), 2), "unit": "keyframes/s", "h2d_bytes_per_step": int(h2d),
             "d2h_bytes_per_step": int(d2h), "api": "ovo_b200.OVO.detect_and_track_objects + compute_semantic_info per keyframe (clip.batch_keyframes = frames/step)",
-            "steps": steps}
+            "steps": steps,
+            "step_ms": {"p50": round(float(np.median(per_step)), 3), "max": round(float(per_step.max()), 3),
+                        "host_p50": round(float(np.median(walls)), 3), "host_max": round(float(np.max(walls)), 3),
+                        "slow_steps": [[int(i), round(float(per_step[i]), 2), round(float(walls[i]), 2)] for i in np.argsort(-per_step)[:3]]},
+            "keyframes_per_s_at_median_step": round(world * F * 1e3 / float(np.median(per_step)), 2)}
 
 
 # ================================================================================================ CPU reference arm
@@ -562,6 +660,7 @@ def main():
     ap.add_argument("--points", type=int, default=2_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sam", action="store_true", help="skip the SAM-2 stage report")
+    ap.add_argument("--no-stream", action="store_true", help="skip the streaming-growth (BASELINE config 5) stage report")
     ap.add_argument("--no-next-rows", action="store_true", help="skip the crop-descriptor / label-transfer stage reports")
     ap.add_argument("--profile-e2e", action="store_true", help="cProfile three e2e steps to stderr")
     ap.add_argument("--no-pipeline", action="store_true", help="do not overlap a step's fusion with the next step's encoder")

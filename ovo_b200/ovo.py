@@ -67,9 +67,11 @@ class OVO:
         # (query, get_objs_clips, capture_dict, ...) first make the current stream wait for this one.
         self._enc_stream = torch.cuda.Stream(device=self._dev)
         D = self.clip_generator.clip_dim
-        self._store = torch.zeros(4096, D, device=self._dev, dtype=torch.float32)   # per-keyframe descriptors
+        # `store_capacity` / `bank_capacity` (optional, new): initial rows; both tables double when full (a pause of a few ms for the
+        # copy and for re-pointing the instances' descriptor views), so a latency-sensitive stream reserves them up front
+        self._store = torch.zeros(int(config.get("store_capacity", 4096)), D, device=self._dev, dtype=torch.float32)   # per-keyframe descriptors
         self._store_n = 0
-        self._bank = torch.zeros(4096, D, device=self._dev, dtype=torch.float32)    # fused instance descriptors
+        self._bank = torch.zeros(int(config.get("bank_capacity", 4096)), D, device=self._dev, dtype=torch.float32)    # fused instance descriptors
         self._bank_n = 0
         self._rows_cache = None
         # dense per-point mode
