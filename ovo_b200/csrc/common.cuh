@@ -42,6 +42,30 @@ void count_launch(int n = 1);
 // (milliseconds).  Keep it cached.
 void keep_default_mempool_cached();
 
+// Stream-ordered temporaries of one call: every pointer handed out is released with cudaFreeAsync on the same stream when the
+// guard goes out of scope, on the success path and on every early error return alike.
+struct AsyncTemps {
+  cudaStream_t s;
+  void* ptrs[32];
+  int n = 0;
+  explicit AsyncTemps(cudaStream_t stream) : s(stream) {}
+  AsyncTemps(const AsyncTemps&) = delete;
+  AsyncTemps& operator=(const AsyncTemps&) = delete;
+  ~AsyncTemps() { for (int i = 0; i < n; ++i) cudaFreeAsync(ptrs[i], s); }
+  template <typename T>
+  cudaError_t alloc(T** p, size_t bytes) {
+    *p = nullptr;
+    if (n >= 32) return cudaErrorMemoryAllocation;
+    const cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(p), bytes ? bytes : 1, s);
+    if (e == cudaSuccess) ptrs[n++] = *p;
+    return e;
+  }
+  void release(void* p) {   // early release of one buffer (e.g. a table that is re-allocated at another size)
+    for (int i = 0; i < n; ++i)
+      if (ptrs[i] == p) { cudaFreeAsync(p, s); ptrs[i] = ptrs[--n]; return; }
+  }
+};
+
 inline int ceil_div(long long a, long long b) { return static_cast<int>((a + b - 1) / b); }
 
 // Optional per-launch timing (ovo_profile_begin / ovo_profile_report): CUDA events recorded on the launching

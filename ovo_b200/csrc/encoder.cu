@@ -1435,15 +1435,16 @@ int ovo_merge_clips_learned(const ovo_merger_weights* w, const float* clips_dev,
   float *x = nullptr, *x2 = nullptr, *qkv = nullptr, *y = nullptr;
   __nv_bfloat16 *xb = nullptr, *att = nullptr, *h = nullptr, *a0 = nullptr, *a1 = nullptr;
   const size_t Rp = static_cast<size_t>(R) + 128, Bp = static_cast<size_t>(B) + 128;
-  OVO_CUDA(cudaMallocAsync(&x, Rp * d * 4, s));
-  OVO_CUDA(cudaMallocAsync(&x2, Rp * d * 4, s));
-  OVO_CUDA(cudaMallocAsync(&qkv, Rp * 3 * d * 4, s));
-  OVO_CUDA(cudaMallocAsync(&xb, Rp * d * 2, s));
-  OVO_CUDA(cudaMallocAsync(&att, Rp * d * 2, s));
-  OVO_CUDA(cudaMallocAsync(&h, Rp * ff * 2, s));
-  OVO_CUDA(cudaMallocAsync(&y, Bp * maxdim * 4, s));
-  OVO_CUDA(cudaMallocAsync(&a0, Bp * maxdim * 2, s));
-  OVO_CUDA(cudaMallocAsync(&a1, Bp * maxdim * 2, s));
+  AsyncTemps tmp(s);
+  OVO_CUDA(tmp.alloc(&x, Rp * d * 4));
+  OVO_CUDA(tmp.alloc(&x2, Rp * d * 4));
+  OVO_CUDA(tmp.alloc(&qkv, Rp * 3 * d * 4));
+  OVO_CUDA(tmp.alloc(&xb, Rp * d * 2));
+  OVO_CUDA(tmp.alloc(&att, Rp * d * 2));
+  OVO_CUDA(tmp.alloc(&h, Rp * ff * 2));
+  OVO_CUDA(tmp.alloc(&y, Bp * maxdim * 4));
+  OVO_CUDA(tmp.alloc(&a0, Bp * maxdim * 2));
+  OVO_CUDA(tmp.alloc(&a1, Bp * maxdim * 2));
   OVO_CUDA(cudaMemcpyAsync(x, clips_dev, static_cast<size_t>(R) * d * 4, cudaMemcpyDeviceToDevice, s));
   {
     const size_t n4 = static_cast<size_t>(R) * d / 4;
@@ -1488,9 +1489,7 @@ int ovo_merge_clips_learned(const ovo_merger_weights* w, const float* clips_dev,
   }
   merger_combine_kernel<<<ceil_div(B, 8), 256, 0, s>>>(clips_dev, y, B, d, o_dim, out_dev);
   OVO_CHECK_LAUNCH();
-  cudaFreeAsync(x, s); cudaFreeAsync(x2, s); cudaFreeAsync(qkv, s); cudaFreeAsync(xb, s); cudaFreeAsync(att, s); cudaFreeAsync(h, s);
-  cudaFreeAsync(y, s); cudaFreeAsync(a0, s); cudaFreeAsync(a1, s);
-  return OVO_OK;
+  return OVO_OK;   // `tmp` releases the temporaries in stream order
 }
 
 }  // extern "C"

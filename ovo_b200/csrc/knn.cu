@@ -354,8 +354,9 @@ int ovo_knn(const float* points_dev, int64_t N, const float* queries_dev, int64_
   OVO_REQUIRE(N >= k && N < (1LL << 31) && Q >= 0 && Q < (1LL << 31), "ovo_knn: need k <= N < 2^31 points (N=%lld, Q=%lld)", (long long)N, (long long)Q);
   if (Q == 0) return OVO_OK;
   keep_default_mempool_cached();
+  AsyncTemps tmp(s);
   unsigned* mm = nullptr;
-  OVO_CUDA(cudaMallocAsync(&mm, 6 * sizeof(unsigned), s));
+  OVO_CUDA(tmp.alloc(&mm, 6 * sizeof(unsigned)));
   const unsigned init[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
   unsigned got[6];
   OVO_CUDA(cudaMemcpyAsync(mm, init, sizeof(init), cudaMemcpyHostToDevice, s));
@@ -363,7 +364,6 @@ int ovo_knn(const float* points_dev, int64_t N, const float* queries_dev, int64_
   OVO_CHECK_LAUNCH();
   OVO_CUDA(cudaMemcpyAsync(got, mm, sizeof(got), cudaMemcpyDeviceToHost, s));
   OVO_CUDA(cudaStreamSynchronize(s));
-  cudaFreeAsync(mm, s);
   float lo[3], hi[3];
   for (int a = 0; a < 3; ++a) { lo[a] = ord2f_host(got[a]); hi[a] = ord2f_host(got[3 + a]); }
   OVO_REQUIRE(std::isfinite(lo[0]) && std::isfinite(lo[1]) && std::isfinite(lo[2]) && std::isfinite(hi[0]) && std::isfinite(hi[1]) && std::isfinite(hi[2]),
@@ -390,14 +390,14 @@ int ovo_knn(const float* points_dev, int64_t N, const float* queries_dev, int64_
   int *cell_of_pt = nullptr, *starts = nullptr, *cursor = nullptr, *totals = nullptr, *overflow = nullptr, *n_overflow = nullptr;
   unsigned long long* sum2 = nullptr;
   float4* sorted = nullptr;
-  OVO_CUDA(cudaMallocAsync(&cell_of_pt, N * sizeof(int), s));
-  OVO_CUDA(cudaMallocAsync(&sum2, sizeof(unsigned long long), s));
+  OVO_CUDA(tmp.alloc(&cell_of_pt, N * sizeof(int)));
+  OVO_CUDA(tmp.alloc(&sum2, sizeof(unsigned long long)));
   int n_cells = 0;
   // Count the points per cell; when the density is uneven (a depth-map surface inside a sparse volume) the cells that hold the
   // points are crowded: halve the cell while a point shares its cell with more than ~16 others on average (auto cell size only).
   for (int pass = 0;; ++pass) {
     n_cells = g.nx * g.ny * g.nz;
-    OVO_CUDA(cudaMallocAsync(&starts, (static_cast<size_t>(n_cells) + 1) * sizeof(int), s));
+    OVO_CUDA(tmp.alloc(&starts, (static_cast<size_t>(n_cells) + 1) * sizeof(int)));
     OVO_CUDA(cudaMemsetAsync(starts, 0, (static_cast<size_t>(n_cells) + 1) * sizeof(int), s));
     knn_count_kernel<<<ceil_div(N, 256), 256, 0, s>>>(points_dev, N, g, cell_of_pt, starts);
     OVO_CHECK_LAUNCH();
@@ -410,17 +410,16 @@ int ovo_knn(const float* points_dev, int64_t N, const float* queries_dev, int64_
     OVO_CUDA(cudaMemcpyAsync(&h, sum2, sizeof(h), cudaMemcpyDeviceToHost, s));
     OVO_CUDA(cudaStreamSynchronize(s));
     if (static_cast<double>(h) / static_cast<double>(N) <= 16.0) break;
-    cudaFreeAsync(starts, s);
+    tmp.release(starts);
     cell *= 0.5;
     g = finer;
   }
-  cudaFreeAsync(sum2, s);
   const int nb = ceil_div(n_cells + 1, 1024);
-  OVO_CUDA(cudaMallocAsync(&cursor, static_cast<size_t>(n_cells) * sizeof(int), s));
-  OVO_CUDA(cudaMallocAsync(&totals, static_cast<size_t>(nb) * sizeof(int), s));
-  OVO_CUDA(cudaMallocAsync(&sorted, N * sizeof(float4), s));
-  OVO_CUDA(cudaMallocAsync(&overflow, Q * sizeof(int), s));
-  OVO_CUDA(cudaMallocAsync(&n_overflow, sizeof(int), s));
+  OVO_CUDA(tmp.alloc(&cursor, static_cast<size_t>(n_cells) * sizeof(int)));
+  OVO_CUDA(tmp.alloc(&totals, static_cast<size_t>(nb) * sizeof(int)));
+  OVO_CUDA(tmp.alloc(&sorted, N * sizeof(float4)));
+  OVO_CUDA(tmp.alloc(&overflow, Q * sizeof(int)));
+  OVO_CUDA(tmp.alloc(&n_overflow, sizeof(int)));
   OVO_CUDA(cudaMemsetAsync(cursor, 0, static_cast<size_t>(n_cells) * sizeof(int), s));
   OVO_CUDA(cudaMemsetAsync(n_overflow, 0, sizeof(int), s));
   {
@@ -449,9 +448,7 @@ int ovo_knn(const float* points_dev, int64_t N, const float* queries_dev, int64_
     knn_brute_kernel<<<n_over, 256, 0, s>>>(sorted, N, queries_dev, overflow, k, idx_out_dev, dist_out_dev);
     OVO_CHECK_LAUNCH();
   }
-  cudaFreeAsync(cell_of_pt, s); cudaFreeAsync(starts, s); cudaFreeAsync(cursor, s); cudaFreeAsync(totals, s);
-  cudaFreeAsync(sorted, s); cudaFreeAsync(overflow, s); cudaFreeAsync(n_overflow, s);
-  return OVO_OK;
+  return OVO_OK;   // `tmp` releases the temporaries in stream order
 }
 
 int ovo_knn_mode(const int32_t* labels_dev, const int32_t* idx_dev, int64_t Q, int k, int32_t* out_dev, void* stream) {

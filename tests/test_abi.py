@@ -34,6 +34,10 @@ def test_struct_sizes():
     assert ctypes.sizeof(_lib.VoteRow) == 32
     assert ctypes.sizeof(_lib.BlockWeights) == 12 * 8
     assert ctypes.sizeof(_lib.VitCfg) == 15 * 4
+    assert ctypes.sizeof(_lib.PoolHeadWeights) == 2 * 4 + 12 * 8         # ovo_pool_head_weights
+    assert ctypes.sizeof(_lib.CropParams) == 6 * 4                        # ovo_crop_params
+    assert ctypes.sizeof(_lib.MergerLayer) == 12 * 8                      # ovo_merger_layer
+    assert ctypes.sizeof(_lib.MergerWeights) == 4 * 4 + 8 + 8 + 3 * 8 + 8  # ovo_merger_weights (int padded to the pointer)
 
 
 def test_fails_loudly_without_gpu(lib_built):
@@ -50,6 +54,26 @@ def test_fails_loudly_without_gpu(lib_built):
     with pytest.raises(RuntimeError):
         from ovo_b200.encoder import RegionEncoder, EncoderConfig
         RegionEncoder(EncoderConfig(), {})
+
+
+def test_new_rows_fail_loudly_without_gpu(lib_built):
+    """Crop-based descriptors, label transfer and the learned merger have no CPU path either."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from ovo_b200 import _lib, eval_utils
+    with pytest.raises(RuntimeError):
+        eval_utils.knn(torch.rand(100, 3), torch.rand(10, 3), k=5)
+    with pytest.raises(RuntimeError):
+        eval_utils.match_labels_to_vtx(torch.zeros(100, dtype=torch.long), torch.rand(100, 3), torch.rand(10, 3))
+    lib = _lib.lib()
+    buf = (ctypes.c_float * 64)()
+    out = (ctypes.c_int32 * 64)()
+    rc = lib.ovo_knn(buf, 8, buf, 2, 1, 0.0, out, None, None)            # host pointers, no device: must not return success
+    assert rc < 0 and len(lib.ovo_last_error()) > 0
+    assert lib.ovo_knn(buf, 2, buf, 2, 5, 0.0, out, None, None) < 0      # fewer points than neighbours: argument check first
+    assert lib.ovo_fuse_clips(buf, buf, buf, 1, 8, 0, 0.4, 0.1, buf, None) < 0     # `vanilla` has no fusion rule
+    assert lib.ovo_encode_crops(None, None, 0, 0, None, 0, None, None, None, None) < 0
 
 
 def test_no_oracle_import_in_product():
