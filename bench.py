@@ -414,7 +414,8 @@ def run_stream(args, dev, enc, hbm, how):
         def cuda(self): pass
 
     config = {"segment_every": 1, "match_distance_th": 0.05, "track_th": 100, "depth_filter": True, "log": False, "kf_queue_delay": 0,
-              "verbose": False, "dense_map": True, "dense_capacity": target + 200_000, "store_capacity": 16384, "bank_capacity": 16384, "sam": {"precomputed": True, "masks_base_path": ""},
+              "verbose": False, "dense_map": True, "dense_capacity": target + 200_000, "store_capacity": 16384, "bank_capacity": 16384,
+              "reserve_points": target + 200_000, "reserve_masks": 64, "reserve_matches": H * W, "sam": {"precomputed": True, "masks_base_path": ""},
               "clip": {"embed_type": "TextRegion", "model_card": "PE-Core-L14-336", "k_top_views": 10000, "fusion": "avg_pooling"}}
     ovo = OVO(config, _Logger(), scene_name=None, cam_intrinsics=torch.from_numpy(K), eval=True,
               clip_generator=CLIPGenerator(config["clip"], encoder=enc), device="cuda")

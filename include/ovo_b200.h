@@ -267,6 +267,12 @@ typedef struct {
 
 int ovo_map_create(ovo_map_t** out);
 void ovo_map_destroy(ovo_map_t* map);
+/* Optional: sizes the handle's workspaces once for a map of up to max_points points, max_instances instances, max_masks masks
+ * per keyframe and max_matches matched points per keyframe (any argument <= 0 leaves that workspace alone).  Without it the
+ * workspaces grow on demand, each growth being a cudaFree + cudaMalloc (a device-wide synchronisation: isolated frames of tens of
+ * milliseconds in a stream whose map keeps growing).  Call it before the first association: match lists of earlier keyframes that
+ * live in a re-allocated slot are dropped. */
+int ovo_map_reserve(ovo_map_t* map, int64_t max_points, int max_instances, int max_masks, int64_t max_matches);
 
 /* geometry_utils.depth_filter (geometry_utils.py:92-96): 7x7 gaussian (sigma 2.5, reflect) high-pass;
  * |d - blur| > 0.05 -> -1. */

@@ -133,6 +133,7 @@ SIGNATURES = {
     "ovo_knn_mode": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     "ovo_map_create": (c_int, [C.POINTER(c_void_p)]),
     "ovo_map_destroy": (None, [c_void_p]),
+    "ovo_map_reserve": (c_int, [c_void_p, c_int64, c_int, c_int, c_int64]),
     "ovo_depth_filter": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "ovo_map_associate": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, C.POINTER(Frame), C.POINTER(c_int),
                                   C.POINTER(VoteRow), C.POINTER(c_int), c_int, c_void_p]),

@@ -949,6 +949,25 @@ int ovo_map_create(ovo_map_t** out) {
   return OVO_OK;
 }
 
+int ovo_map_reserve(ovo_map_t* m, int64_t max_points, int max_instances, int max_masks, int64_t max_matches) {
+  OVO_REQUIRE(m != nullptr, "ovo_map_reserve: null handle");
+  OVO_REQUIRE(!m->pend_valid, "ovo_map_reserve: an association is pending (call before ovo_map_vote / after ovo_map_apply)");
+  if (max_masks > 0 && max_masks + 1 > m->masks_cap) OVO_TRY(ctl_alloc(m, max_masks + 64));
+  if (max_masks > 0 && max_instances > 0) {
+    const size_t need = static_cast<size_t>(max_masks) * (static_cast<size_t>(max_instances) + 1);
+    OVO_REQUIRE(need < (1ull << 28), "ovo_map_reserve: vote table too large (%d masks x %d instances)", max_masks, max_instances);
+    OVO_TRY(grow(&m->votes, &m->votes_cap, need));
+  }
+  if (max_points > 0) OVO_TRY(grow(&m->scratch_list, &m->scratch_cap, static_cast<size_t>(max_points)));
+  if (max_matches > 0)
+    for (int i = 0; i < ovo_map::kSlots; ++i)
+      if (static_cast<size_t>(max_matches) > m->slot_cap[i]) {
+        OVO_TRY(grow(&m->slot_list[i], &m->slot_cap[i], static_cast<size_t>(max_matches)));
+        m->slot_n[i] = 0;   // a re-allocated slot no longer holds its keyframe's match list
+      }
+  return OVO_OK;
+}
+
 void ovo_map_destroy(ovo_map_t* m) {
   if (!m) return;
   cudaFree(m->ctl); cudaFreeHost(m->h_ctl); cudaFree(m->votes); cudaFree(m->area);

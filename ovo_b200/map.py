@@ -34,6 +34,11 @@ class SemanticMap:
             pass
 
     # -------------------------------------------------------------------------------------------
+    def reserve(self, points: int = 0, instances: int = 0, masks: int = 0, matches: int = 0) -> None:
+        """Sizes the association workspaces once (see ovo_map_reserve): no allocation pauses while the map grows."""
+        with torch.cuda.device(self.device):
+            check(self.lib.ovo_map_reserve(self.handle, int(points), int(instances), int(masks), int(matches)), "ovo_map_reserve")
+
     def depth_filter(self, depth: torch.Tensor) -> torch.Tensor:
         """geometry_utils.depth_filter (geometry_utils.py:92-96)."""
         depth = depth.to(self.device, torch.float32).contiguous()

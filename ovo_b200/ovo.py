@@ -62,6 +62,9 @@ class OVO:
         # device-resident tables
         self._dev = self.clip_generator.encoder.device
         self.semmap = SemanticMap(self._dev)
+        if config.get("reserve_points"):      # optional, new: a stream whose map keeps growing sizes the workspaces up front
+            self.semmap.reserve(points=int(config["reserve_points"]), instances=int(config.get("bank_capacity", 4096)),
+                                masks=int(config.get("reserve_masks", 256)), matches=int(config.get("reserve_matches", 0)))
         # Descriptor work (ViT, pooling, fusion) is enqueued on its own stream: association synchronises the host once
         # per keyframe, and that wait must not include the encoder of earlier keyframes.  Readers of descriptors
         # (query, get_objs_clips, capture_dict, ...) first make the current stream wait for this one.

@@ -205,6 +205,29 @@ def test_association_idempotent_at_full_size(sm):
     assert int((ins_d >= 0).sum()) == int(v1["n_matched"][v1["ins_id"] >= 0].sum())
 
 
+def test_reserved_workspaces_give_the_same_association():
+    """ovo_map_reserve only sizes workspaces: same votes / ids / match lists as the grow-on-demand handle."""
+    from ovo_b200.map import SemanticMap
+    K = synth.intrinsics(); d = synth.depth_map(); N = 300_000
+    xyz, ids, ins = synth.point_map(N, d, K, synth.pose(0), seed=4, frac_visible=0.5)
+    seg, _ = synth.grid_masks()
+    outs = []
+    for reserve in (False, True):
+        m = SemanticMap("cuda:0")
+        if reserve:
+            m.reserve(points=1_000_000, instances=5000, masks=300, matches=480 * 640)
+        xyz_d, ins_d, d_d, seg_d = _dev(xyz, ins, d, seg)
+        v, n, nxt = m.associate(xyz_d, ins_d, d_d, seg_d, synth.pose(0), K, 0, kf_slot=3)
+        pairs = m.matches(3, n).cpu().numpy()
+        outs.append((v, n, nxt, ins_d.cpu().numpy(), pairs[np.lexsort((pairs[:, 1], pairs[:, 0]))]))
+    a, b = outs
+    assert a[1] == b[1] and a[2] == b[2] and (a[3] == b[3]).all() and (a[4] == b[4]).all()
+    for k in a[0]:
+        assert (np.asarray(a[0][k]) == np.asarray(b[0][k])).all(), k
+    with pytest.raises(RuntimeError):
+        SemanticMap("cuda:0").reserve(masks=1 << 20, instances=1 << 20)
+
+
 def test_fuse_dense_batch_equals_sequential(sm):
     """One pass over the bank for several keyframes == one pass per keyframe, bit for bit."""
     K = synth.intrinsics(); N, D, F = 120000, 128, 5
