@@ -918,7 +918,7 @@ int grow(T** p, size_t* cap, size_t need) {
 }  // namespace
 
 static int ctl_alloc(ovo_map* m, int masks_cap) {
-  cudaFree(m->ctl); cudaFreeHost(m->h_ctl); cudaFree(m->area); cudaFree(m->mask_ins);
+  cudaFree(m->ctl); cudaFreeHost(m->h_ctl); cudaFree(m->area);   // (mask_ins points INTO the area allocation: not freed on its own)
   m->ctl = nullptr; m->h_ctl = nullptr; m->area = nullptr; m->mask_ins = nullptr;
   const size_t bytes = sizeof(CtlHeader) + static_cast<size_t>(masks_cap) * sizeof(ovo_vote_row);
   if (cudaMalloc(&m->ctl, bytes) != cudaSuccess || cudaMallocHost(&m->h_ctl, bytes) != cudaSuccess ||
