@@ -1,5 +1,5 @@
 """Staged GPU diagnostics (development aid; the judged checks are tests/ -m gpu).
-    python tools/gpu_diag.py <stage> ...      stages: gemm query map enc_tiny enc_full text timing
+    python tests/checks/gpu_diag.py <stage> ...      stages: gemm query map enc_tiny enc_full text timing
 Each stage prints max errors against the CPU oracle; run each under `timeout` on the GPU box."""
 import os
 import sys
@@ -8,7 +8,7 @@ import time
 import numpy as np
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from ovo_b200 import synth  # noqa: E402
 from ovo_b200.encoder import EncoderConfig, RegionEncoder, random_state_dict, gemm_bf16  # noqa: E402
 from ovo_b200.map import SemanticMap  # noqa: E402

@@ -1,6 +1,6 @@
 """SAM-2.1 Hiera-L stage timing on one GPU (development aid): set_image / predict(256 prompts) / generate, CUDA events,
 plus the per-kernel-class breakdown of ovo_profile_begin/report.
-    python tools/sam_bench.py [--tiny] [--iters 10]"""
+    python tests/checks/sam_bench.py [--tiny] [--iters 10]"""
 import argparse
 import json
 import os
@@ -8,7 +8,7 @@ import sys
 
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import gen_golden as GG  # noqa: E402  (image generator only)
 from ovo_b200 import _lib  # noqa: E402
 from ovo_b200.sam import Sam2  # noqa: E402

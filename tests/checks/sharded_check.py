@@ -1,6 +1,6 @@
 """Sharded-map association on N GPUs (NCCL): every rank owns the points whose voxel hashes to it, votes are summed
 with one all-reduce per keyframe, decisions are identical on every rank.  Checked against the unsharded oracle.
-    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/sharded_check.py"""
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/checks/sharded_check.py"""
 import os
 import sys
 
@@ -8,7 +8,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import fusion as OF  # noqa: E402
 from ovo_b200 import synth  # noqa: E402
 from ovo_b200.map import SemanticMap  # noqa: E402
