@@ -85,3 +85,15 @@ def test_no_oracle_import_in_product():
                 txt = open(os.path.join(root, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", txt, flags=re.M), f
                 assert "/root/reference" not in txt or f == "tokenizer.py", f
+
+
+def test_only_tests_smoke_and_bench_import_the_oracle():
+    """oracle/ is test infrastructure: outside tests/ and oracle/ itself only bench.py (CPU legs) and __graft_entry__.py (smoke)
+    may import it."""
+    allowed = {os.path.join(ROOT, "bench.py"), os.path.join(ROOT, "__graft_entry__.py")}
+    for root, dirs, files in os.walk(ROOT):
+        dirs[:] = [d for d in dirs if d not in (".git", "tests", "oracle", "gpurun_out", "baseline", "__pycache__", ".pytest_cache")]
+        for f in files:
+            path = os.path.join(root, f)
+            if f.endswith(".py") and path not in allowed:
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", open(path).read(), flags=re.M), path
