@@ -86,6 +86,8 @@ class CLIPGenerator:
         cfg = (encoder.cfg if encoder is not None else None) or encoder_config or MODEL_CARDS.get(self.model_card)
         if cfg is None:
             raise NotImplementedError(f"ovo_b200: model card '{self.model_card}' is not supported (have {list(MODEL_CARDS)})")
+        if encoder is None and not torch.cuda.is_available():
+            raise RuntimeError("ovo_b200.CLIPGenerator needs a CUDA device (there is no CPU fallback)")
         if state_dict is None and encoder is None:
             ckpt = config.get("ckpt_path")
             if ckpt and os.path.exists(ckpt):

@@ -64,3 +64,25 @@ def test_synth_scene_is_well_formed():
     assert seg.max() + 1 == bm.shape[0] == 48 and (seg == -1).any()
     xyz, ids, ins = synth.point_map(1000, d, K, synth.pose(0))
     assert xyz.shape == (1000, 3) and xyz.dtype == np.float32 and (ins == -1).all()
+
+
+def test_clip_generator_config_validation_needs_no_gpu():
+    """Unknown embed types / model cards are rejected before anything touches the device (clip_generator.py:16,37-52)."""
+    from ovo_b200.clip_generator import CLIPGenerator, CROP_EMBED_TYPES, MODEL_CARDS
+    assert set(CROP_EMBED_TYPES) == {"vanilla", "fixed_weights", "hovsg", "adaptive_weights", "concept_fusion", "learned"}
+    assert "PE-Core-L14-336" in MODEL_CARDS and "PE-Core-L-14-336" in MODEL_CARDS      # the vendored name and its open_clip alias
+    with pytest.raises(NotImplementedError):
+        CLIPGenerator({"embed_type": "no_such_type"})
+    with pytest.raises(NotImplementedError):
+        CLIPGenerator({"embed_type": "TextRegion", "model_card": "SigLIP-384"})         # open_clip-only card: not built
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError):                                                # no CPU fallback
+            CLIPGenerator({"embed_type": "fixed_weights", "model_card": "PE-Core-L14-336", "random_init_seed": 0})
+
+
+def test_embed_type_codes_match_the_header():
+    import os, re
+    from ovo_b200 import _lib
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "ovo_b200.h")).read()
+    codes = {m.group(1).lower(): int(m.group(2)) for m in re.finditer(r"#define OVO_EMBED_([A-Z_]+) (\d+)", hdr)}
+    assert codes == _lib.EMBED_TYPES
