@@ -2,7 +2,7 @@
  * (CLIP/ViT region encoder -> 3D association/fusion into the point map -> text-vs-map cosine query).
  *
  * The reference has no FFI on this path: its seam is the Python class surface of `OVO`,
- * `CLIPGenerator`, `MaskGenerator`, `Instance3D` (ovo/entities/*.py).  ovo_b200/ mirrors those classes in
+ * `CLIPGenerator`, `MaskGenerator`, `Instance3D` (the modules under ovo/entities).  ovo_b200/ mirrors those classes in
  * Python and calls the entry points below through ctypes; INTEGRATION.md shows the binding.
  * Each entry point cites the reference lines it replaces (paths relative to the reference root).
  *

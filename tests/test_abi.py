@@ -97,3 +97,27 @@ def test_only_tests_smoke_and_bench_import_the_oracle():
             path = os.path.join(root, f)
             if f.endswith(".py") and path not in allowed:
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", open(path).read(), flags=re.M), path
+
+
+def test_header_is_plain_c99(tmp_path):
+    """include/ovo_b200.h is the C ABI: it must compile as C99 (no C++ / torch types), and a C program must link against the library."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    src = tmp_path / "abi.c"
+    src.write_text('#include "ovo_b200.h"\n#include <stdio.h>\n'
+                   'int main(void) { ovo_crop_params p; p.embed_type = OVO_EMBED_HOVSG; (void)p;\n'
+                   '  ovo_map_t* m = 0; int rc = ovo_map_create(&m);\n'
+                   '  printf("%d %d %s\\n", ovo_version(), rc, rc < 0 ? ovo_last_error() : "ok"); if (m) ovo_map_destroy(m); return 0; }\n')
+    inc = os.path.join(ROOT, "include")
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-fsyntax-only", "-I", inc, str(src)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    from ovo_b200 import build
+    lib = build.build()
+    exe = tmp_path / "abi"
+    r = subprocess.run([gcc, "-std=c99", "-I", inc, str(src), "-o", str(exe), lib, f"-Wl,-rpath,{os.path.dirname(lib)}"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.split()[0] == "100", r.stdout + r.stderr
