@@ -106,7 +106,8 @@ class PointMapper:
         return {"xyz": self.pcd.clone().cpu(), "obj_ids": self.pcd_obj_ids.clone().cpu(), "ids": self.pcd_ids.clone().cpu(),
                 "max_id": self.max_id, "color": self.pcd_colors.clone().cpu()}
 
-    def set_map_dict(self, d: Dict[str, Any]) -> None:
+    def set_map_dict(self, map_dict: Dict[str, Any]) -> None:
+        d = map_dict
         n = d["xyz"].shape[0]
         if n > self.capacity:
             self._alloc(2 * n)
