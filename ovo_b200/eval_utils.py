@@ -1,7 +1,8 @@
 """Label transfer from the predicted point map to the ground-truth mesh vertices — `match_labels_to_vtx` of the
 reference (ovo/utils/eval_utils.py:13-44, called by run_eval.compute_scene_labels, run_eval.py:50) on the GPU:
 the SciPy KD-tree query (k = 5) is `ovo_knn` (grid hash, exact), `torch.mode` over the five labels is `ovo_knn_mode`.
-Same signature and return values as the reference; tensors live on the device the inputs are moved to."""
+Same signature and return values as the reference; the results are returned on the device the labels came from (CPU tensors in,
+CPU tensors out, as run_eval.py expects)."""
 from typing import Tuple
 
 import torch
@@ -41,6 +42,7 @@ def match_labels_to_vtx(points_3d_labels: torch.Tensor, points_3d: torch.Tensor,
     """eval_utils.py:13-44.  `tree` is accepted for compatibility (kd / ball give the same neighbours)."""
     points_3d_labels = torch.as_tensor(points_3d_labels)
     points_3d, mesh_vtx = torch.as_tensor(points_3d), torch.as_tensor(mesh_vtx)
+    out_dev = points_3d_labels.device        # results go back where the labels came from (run_eval.py:50-53 feeds them to numpy)
     if filter_unasigned:
         assigned_mask = (points_3d_labels > -1).squeeze()
         if verbose:
@@ -53,7 +55,7 @@ def match_labels_to_vtx(points_3d_labels: torch.Tensor, points_3d: torch.Tensor,
     labels = points_3d_labels.to(dev, torch.int32).reshape(-1).contiguous()
     mesh_labels32 = torch.empty(idx.shape[0], device=dev, dtype=torch.int32)
     check(_lib.lib().ovo_knn_mode(ptr(labels), ptr(idx), idx.shape[0], 5, ptr(mesh_labels32), stream_ptr()), "ovo_knn_mode")
-    mesh_labels = mesh_labels32.to(points_3d_labels.dtype)
+    mesh_labels = mesh_labels32.to(out_dev, points_3d_labels.dtype)
     matched_instances_ids = torch.unique(mesh_labels)
     if not filter_unasigned:
         while matched_instances_ids[0] < 0:
