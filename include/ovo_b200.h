@@ -297,23 +297,50 @@ int ovo_map_vote(ovo_map_t* map, const float* xyz_dev, const int32_t* ins_ids_de
                  int n_ins, int32_t* table_out_dev, int kf_slot, void* stream);
 int ovo_map_apply(ovo_map_t* map, const int32_t* table_in_dev, int32_t* ins_ids_dev, int* next_ins_id,
                   ovo_vote_row* votes_host, int* n_matched_host, void* stream);
+/* ovo_map_associate for a BATCH of keyframes (same results as n_frames consecutive calls, ids bit for bit): the map is
+ * streamed ONCE for all keyframes (the geometry of a keyframe does not depend on the instance ids), the votes are then taken
+ * keyframe by keyframe on the device with next_ins_id left there, and the host reads every keyframe's rows back with ONE
+ * synchronisation.  frames / kf_slots host arrays [n_frames] (n_frames <= 64; kf_slots may be NULL: no dense fusion later),
+ * votes_host [n_frames][votes_stride], n_matched_host [n_frames], mask_ins_out_dev (optional) i32 [n_frames][votes_stride]:
+ * the instance id given to every mask (-1 = none), for callers that keep going on the device. */
+int ovo_map_associate_batch(ovo_map_t* map, const float* xyz_dev, int32_t* ins_ids_dev, int64_t N, const ovo_frame* frames,
+                            int n_frames, const int* kf_slots, int* next_ins_id, ovo_vote_row* votes_host, int votes_stride,
+                            int* n_matched_host, int32_t* mask_ins_out_dev, void* stream);
+/* The same batch in stages, for a map SHARDED over several GPUs: every rank runs begin on its own points, then
+ * per keyframe f in order: ovo_map_batch_vote (votes of its points; *table_dev / *table_len = the keyframe's table
+ * [n_masks x (n_ins+1) vote counts | n_matched] inside tables_dev) -> the ranks SUM that table (all-reduce, in place) ->
+ * ovo_map_batch_decide (identical decisions on every rank, next_ins_id stays on the device); ovo_map_batch_end assigns the
+ * last keyframe's ids, reads all rows back and synchronises once.  tables_dev i32 [tables_cap] is caller-owned (NULL: a
+ * workspace of the handle); it needs sum_f (max(n_masks_f,1) * (next_ins_id + sum_{g<f} n_masks_g + 1) + 4) ints. */
+int ovo_map_batch_begin(ovo_map_t* map, const float* xyz_dev, const int32_t* ins_ids_dev, int64_t N, const ovo_frame* frames,
+                        int n_frames, const int* kf_slots, int next_ins_id, int32_t* tables_dev, int64_t tables_cap, void* stream);
+int ovo_map_batch_vote(ovo_map_t* map, int f, int32_t* ins_ids_dev, int32_t** table_dev, int* table_len, void* stream);
+int ovo_map_batch_decide(ovo_map_t* map, int f, void* stream);
+int ovo_map_batch_end(ovo_map_t* map, int32_t* ins_ids_dev, int* next_ins_id, ovo_vote_row* votes_host, int votes_stride,
+                      int* n_matched_host, int32_t* mask_ins_out_dev, void* stream);
 /* Copies the matched list of a slot to the caller: pairs (point index, mask index), n from associate. */
 int ovo_map_get_matches(ovo_map_t* map, int kf_slot, int32_t* pairs_dev, int max_pairs, void* stream);
 
-/* Dense per-point running mean (north-star F6; per-point analogue of instance3d.py:19-21):
- * for every matched point p of slot kf_slot whose mask m has mask_row_dev[m] = r >= 0:
- *   count[p] += 1; bank[p] += (feats[r] - bank[p]) * (1 / count[p])   (f32, result rounded to bf16).
- * bank_dev bf16 [N, D], counts_dev i32 [N], feats_dev f32 [R, D], mask_row_dev i32 [n_masks]. */
-int ovo_map_fuse_dense(ovo_map_t* map, int kf_slot, void* bank_dev, int32_t* counts_dev, int64_t N, int D,
-                       const float* feats_dev, const int32_t* mask_row_dev, int n_masks, void* stream);
+/* Dense per-point running mean (north-star F6; per-point analogue of instance3d.py:19-21).  The bank keeps the mean of the
+ * descriptors of the masks a point fell into as TWO bf16 planes: bank_dev = the mean rounded to bf16 (the operand of
+ * ovo_query_dense), bank_lo_dev = bf16(mean - bank): together 16-17 significant bits, so the increment of a long stream
+ * ((e - f)/count, below half a bf16 ulp of f once count is in the hundreds) is not lost.
+ * For every matched point p of slot kf_slot whose mask m has mask_row_dev[m] = r >= 0 (f32 operations, no FMA contraction):
+ *   f = bank[p] + bank_lo[p];  e = bf16(feats[r]);  count[p] += 1;  f' = f + (e - 1*f) * (1 / count[p]);
+ *   bank[p] = bf16(f');  bank_lo[p] = bf16(f' - bank[p]).
+ * bank_dev, bank_lo_dev bf16 [N, D], counts_dev i32 [N], feats_dev f32 [n_rows, D], mask_row_dev i32 [n_masks]. */
+int ovo_map_fuse_dense(ovo_map_t* map, int kf_slot, void* bank_dev, void* bank_lo_dev, int32_t* counts_dev, int64_t N, int D,
+                       const float* feats_dev, int n_rows, const int32_t* mask_row_dev, int n_masks, void* stream);
 
-/* The same update for SEVERAL keyframes in one pass over the bank (keyframe order preserved, bit-identical to
- * n_slots consecutive ovo_map_fuse_dense calls): a point matched in k keyframes has its row read and written once
- * instead of k times.  feats_dev f32 [R, D] holds the descriptors of all keyframes; mask_row_dev i32
- * [n_slots, n_masks] maps (keyframe, mask) to a row of feats_dev or -1. */
-int ovo_map_fuse_dense_batch(ovo_map_t* map, const int* kf_slots_host, int n_slots, void* bank_dev, int32_t* counts_dev,
-                             int64_t N, int D, const float* feats_dev, int n_rows, const int32_t* mask_row_dev, int n_masks,
-                             void* stream);
+/* The same mean for SEVERAL keyframes in one pass over the bank: a point matched in k keyframes of the batch has its rows
+ * read once and written once, its k descriptors e_1..e_k (keyframe order) summed in f32:
+ *   s = e_1 + ... + e_k;  count += k;  f' = f + (s - k*f) * (1 / count)
+ * (equal to k single updates up to the rounding of the two-plane format).  feats_dev f32 [n_rows, D] holds the descriptors of
+ * all keyframes; mask_row_dev i32 [n_slots, n_masks] maps (keyframe, mask) to a row of feats_dev or -1.  n_slots <= 64.  The
+ * slots are either all filled by ovo_map_associate (match lists) or are consecutive slots of ONE ovo_map_associate_batch. */
+int ovo_map_fuse_dense_batch(ovo_map_t* map, const int* kf_slots_host, int n_slots, void* bank_dev, void* bank_lo_dev,
+                             int32_t* counts_dev, int64_t N, int D, const float* feats_dev, int n_rows,
+                             const int32_t* mask_row_dev, int n_masks, void* stream);
 
 /* Instance-bank running mean, fusion 'avg_pooling' (instance3d.py:19-21,157-189):
  * bank[row[i]] = (bank[row[i]]*cnt + feats[i]) / (cnt+1), not re-normalised. bank f32 [I,D]. */

@@ -194,15 +194,47 @@ def avg_pooling(clips: np.ndarray) -> np.ndarray:
     return clips.astype(f32).mean(axis=0, dtype=f32)
 
 
-def dense_running_mean(bank: np.ndarray, counts: np.ndarray, pt_idx: np.ndarray, feats: np.ndarray):
-    """Dense per-point analogue of i3d:19-21 (north-star F6): c_p += 1; f_p += (e - f_p) * (1/c_p), every operation
-    rounded to f32 (one division per point).  bank [N,D] f32 (the CUDA bank is bf16: compare with bf16 rounding
-    applied after each update)."""
-    for p, e in zip(pt_idx, feats):
-        c = counts[p] + 1
-        bank[p] = bank[p] + ((e - bank[p]).astype(f32) * (f32(1) / f32(c))).astype(f32)
-        counts[p] = c
-    return bank, counts
+def bf16_round(x: np.ndarray) -> np.ndarray:
+    """f32 -> nearest bf16 (ties to even), returned as f32 (what __floats2bfloat162_rn / torch .bfloat16() do)."""
+    u = np.ascontiguousarray(x, dtype=f32).view(np.uint32)
+    r = ((u + np.uint32(0x7FFF) + ((u >> np.uint32(16)) & np.uint32(1))) & np.uint32(0xFFFF0000)).astype(np.uint32)
+    return r.view(f32)
+
+
+def dense_update(hi: np.ndarray, lo: np.ndarray, count: int, descs: np.ndarray):
+    """Dense per-point analogue of i3d:19-21 (north-star F6) on the two-plane bank: `hi` [D] = the running mean rounded to bf16
+    (the query operand), `lo` [D] = bf16(mean - hi).  One update by the k descriptors a pass brings for the point
+    (`descs` [k, D] f32, keyframe order), every operation rounded to f32:
+        f = hi + lo;  s = sum of the bf16-rounded descriptors in order;  c' = c + k;  f' = f + (s - k*f) * (1/c')
+        hi' = bf16(f');  lo' = bf16(f' - hi')
+    With k = 1 this is the running mean f += (e - f)/c' of one keyframe.  Returns (hi', lo', c')."""
+    k = len(descs)
+    f = (hi.astype(f32) + lo.astype(f32)).astype(f32)
+    e = bf16_round(descs)
+    s = e[0].copy()
+    for i in range(1, k):
+        s = (s + e[i]).astype(f32)
+    c1 = count + k
+    inv = f32(1) / f32(c1)
+    t = (f32(k) * f).astype(f32)
+    f1 = (f + ((s - t).astype(f32) * inv).astype(f32)).astype(f32)
+    hi1 = bf16_round(f1)
+    lo1 = bf16_round((f1 - hi1).astype(f32))
+    return hi1, lo1, c1
+
+
+def dense_fuse(hi: np.ndarray, lo: np.ndarray, counts: np.ndarray, seg_of_pt_per_kf, mask_row_per_kf, feats: np.ndarray):
+    """One pass of ovo_map_fuse_dense(_batch): keyframes in order, `seg_of_pt_per_kf[f]` [N] = mask of each point (-1 none),
+    `mask_row_per_kf[f]` [n_masks] = row of `feats` or -1.  Updates hi / lo / counts in place."""
+    N = hi.shape[0]
+    rows = np.full((len(seg_of_pt_per_kf), N), -1, np.int64)
+    for f, (seg, mr) in enumerate(zip(seg_of_pt_per_kf, mask_row_per_kf)):
+        ok = seg >= 0
+        rows[f, ok] = np.asarray(mr)[seg[ok]]
+    for p in np.nonzero((rows >= 0).any(axis=0))[0]:
+        r = rows[:, p]
+        hi[p], lo[p], counts[p] = dense_update(hi[p], lo[p], int(counts[p]), feats[r[r >= 0]])
+    return hi, lo, counts
 
 
 # ---------------------------------------------------------------------------------------------------

@@ -140,10 +140,17 @@ SIGNATURES = {
     "ovo_map_vote": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, C.POINTER(Frame), c_int, c_void_p, c_int, c_void_p]),
     "ovo_map_apply": (c_int, [c_void_p, c_void_p, c_void_p, C.POINTER(c_int), C.POINTER(VoteRow), C.POINTER(c_int), c_void_p]),
     "ovo_map_get_matches": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p]),
-    "ovo_map_fuse_dense": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int,
+    "ovo_map_fuse_dense": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_int, c_void_p, c_int,
                                    c_void_p]),
-    "ovo_map_fuse_dense_batch": (c_int, [c_void_p, C.POINTER(c_int), c_int, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_int,
+    "ovo_map_fuse_dense_batch": (c_int, [c_void_p, C.POINTER(c_int), c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_int,
                                          c_void_p, c_int, c_void_p]),
+    "ovo_map_associate_batch": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, C.POINTER(Frame), c_int, C.POINTER(c_int), C.POINTER(c_int),
+                                        C.POINTER(VoteRow), c_int, C.POINTER(c_int), c_void_p, c_void_p]),
+    "ovo_map_batch_begin": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, C.POINTER(Frame), c_int, C.POINTER(c_int), c_int, c_void_p,
+                                    c_int64, c_void_p]),
+    "ovo_map_batch_vote": (c_int, [c_void_p, c_int, c_void_p, C.POINTER(c_void_p), C.POINTER(c_int), c_void_p]),
+    "ovo_map_batch_decide": (c_int, [c_void_p, c_int, c_void_p]),
+    "ovo_map_batch_end": (c_int, [c_void_p, c_void_p, C.POINTER(c_int), C.POINTER(VoteRow), c_int, C.POINTER(c_int), c_void_p, c_void_p]),
     "ovo_bank_add_views": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "ovo_bank_update_mean": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p]),
     "ovo_query_dense": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_int, c_void_p, c_void_p]),
@@ -208,8 +215,16 @@ def ptr(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
-def stream_ptr():
+def stream_ptr(device=None):
+    """torch's current stream of `device` (default: the current device) as a cudaStream_t.  Kernels launch on the CURRENT
+    device, so a handle that lives on another device is refused instead of being driven on the wrong stream."""
     import torch
+    if device is not None:
+        idx = torch.device(device).index
+        if idx is not None and idx != torch.cuda.current_device():
+            raise RuntimeError(f"ovo_b200: this object lives on cuda:{idx} but the current device is cuda:{torch.cuda.current_device()} "
+                               "(one process per GPU: call torch.cuda.set_device first, or wrap the call in torch.cuda.device(...))")
+        return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 

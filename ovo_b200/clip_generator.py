@@ -5,9 +5,9 @@ Perception-Encoder card (`PE-Core-L-14-336` in the reference's open_clip table, 
 architecture as the vendored `PE-Core-L14-336`).  `embed_type: learned` (a SigLIP-1152 descriptor merger with its own
 checkpoint, clips_merging.py) and the open_clip-only cards are not built.
 
-Weights: `config["ckpt_path"]` may point to a Perception-Encoder checkpoint (`torch.save`d state_dict with the
-reference's key names, what `pe.CLIP.load_ckpt` reads).  Without it — there is no network in the build or
-bench environment — seeded random weights of the same architecture are used and a warning is printed."""
+Weights: `config["ckpt_path"]` points to a Perception-Encoder checkpoint (`torch.save`d state_dict with the
+reference's key names, what `pe.CLIP.load_ckpt` reads).  A missing checkpoint raises; `config["random_init"]: True`
+asks for seeded random weights of the same architecture (benchmarks and tests: there is no network here)."""
 import os
 from typing import Dict, List
 
@@ -65,6 +65,47 @@ class LearnedMerger:
                   "ovo_merge_clips_learned")
         return out
 
+
+def normalize_pe_state_dict(sd: Dict) -> Dict:
+    """The unwrapping `pe.CLIP.load_ckpt` / `pe.VisionTransformer.load_ckpt` do (pe.py:629-638, 407-419): a `state_dict` or
+    `weights` wrapper, DDP's `module.` prefix.  A vision-only checkpoint (keys of `VisionTransformer` itself, which that loader
+    reads after stripping `visual.`) is accepted too: its keys get the `visual.` prefix back, the text tower stays absent."""
+    if "state_dict" in sd:
+        sd = sd["state_dict"]
+    elif "weights" in sd:
+        sd = sd["weights"]
+    sd = {k.replace("module.", ""): v for k, v in sd.items()}
+    if not any(k.startswith("visual.") for k in sd) and "conv1.weight" in sd:
+        sd = {"visual." + k: v for k, v in sd.items()}
+    return sd
+
+
+def load_clip_state_dict(config: Dict, cfg: EncoderConfig, model_card: str) -> Dict:
+    """Weights of the card: `config["ckpt_path"]` (a file, or the reference's root under which
+    `data/input/ckpts/pe/{card}.pt` lives, clip_utils.py:90-93).  A missing checkpoint RAISES, as the reference's loader
+    does; seeded random weights are only used on request (`random_init: True`: benchmarks and tests, no network here)."""
+    ckpt = config.get("ckpt_path")
+    if ckpt:
+        ckpt = str(ckpt)
+        if os.path.isdir(ckpt):
+            ckpt = os.path.join(ckpt, "data", "input", "ckpts", "pe", f"{model_card}.pt")
+        if not os.path.exists(ckpt):
+            raise FileNotFoundError(f"ovo_b200: checkpoint {ckpt} of {model_card} not found")
+        sd = normalize_pe_state_dict(torch.load(ckpt, map_location="cpu", weights_only=True))
+        missing = [k for k in ("visual.conv1.weight", "visual.positional_embedding", "visual.proj",
+                               "visual.attn_pool.attn.in_proj_weight", f"visual.transformer.resblocks.{cfg.layers - 1}.mlp.c_proj.weight")
+                   if k not in sd]
+        if missing:
+            raise KeyError(f"ovo_b200: checkpoint {ckpt} lacks {missing} (expected the key names of pe.CLIP / pe.VisionTransformer)")
+        return sd
+    if config.get("random_init", False):
+        seed = int(config.get("random_init_seed", 0))
+        print(f"[ovo_b200] random_init: seeded RANDOM weights for {model_card} (seed {seed}) — descriptors carry no semantics")
+        return random_state_dict(cfg, seed=seed)
+    raise FileNotFoundError(f"ovo_b200: no checkpoint for {model_card}: set clip.ckpt_path (the reference downloads it, there is no "
+                            "network here) or clip.random_init: True for seeded random weights")
+
+
 MODEL_CARDS = {"PE-Core-L14-336": EncoderConfig(), "PE-Core-L-14-336": EncoderConfig()}
 CROP_EMBED_TYPES = ("vanilla", "fixed_weights", "hovsg", "adaptive_weights", "concept_fusion", "learned")
 
@@ -88,16 +129,9 @@ class CLIPGenerator:
             raise NotImplementedError(f"ovo_b200: model card '{self.model_card}' is not supported (have {list(MODEL_CARDS)})")
         if encoder is None and not torch.cuda.is_available():
             raise RuntimeError("ovo_b200.CLIPGenerator needs a CUDA device (there is no CPU fallback)")
+        self._check_supported_keys(config)
         if state_dict is None and encoder is None:
-            ckpt = config.get("ckpt_path")
-            if ckpt and os.path.exists(ckpt):
-                sd = torch.load(ckpt, map_location="cpu", weights_only=True)
-                sd = sd.get("state_dict", sd.get("weights", sd))
-                state_dict = {k.replace("module.", ""): v for k, v in sd.items()}
-            else:
-                print(f"[ovo_b200] no checkpoint for {self.model_card}: using seeded RANDOM weights (seed "
-                      f"{config.get('random_init_seed', 0)}) — descriptors carry no semantics")
-                state_dict = random_state_dict(cfg, seed=config.get("random_init_seed", 0))
+            state_dict = load_clip_state_dict(config, cfg, self.model_card)
         self.cfg = cfg
         self.clip_dim = cfg.output_dim
         self.encoder = encoder or RegionEncoder(cfg, state_dict, max_images=config.get("max_images", 16),
@@ -127,6 +161,22 @@ class CLIPGenerator:
                 raise NotImplementedError("SigLIP cards need `logit_scale` and `logit_bias` in the config")
             self.similarity_args = (float(config["logit_scale"]), float(config["logit_bias"]))
         self._text_cache = {}
+
+    @staticmethod
+    def _check_supported_keys(config: Dict) -> None:
+        """Reference options that change the descriptors and are not built: refuse them instead of ignoring them
+        (clip_generator.py:30,45-47; ovo.py:437)."""
+        bad = []
+        if config.get("remove_global_patch", False):
+            bad.append("remove_global_patch: True")
+        if config.get("resize_method", "multi_resolution") != "multi_resolution":
+            bad.append(f"resize_method: {config['resize_method']}")
+        if not config.get("project_and_normalize", True):
+            bad.append("project_and_normalize: False")
+        if config.get("use_half", False):
+            bad.append("use_half: True")
+        if bad:
+            raise NotImplementedError("ovo_b200: clip option(s) not built: " + ", ".join(bad))
 
     @property
     def get_clip_dim(self) -> int:

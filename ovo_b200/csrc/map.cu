@@ -61,7 +61,7 @@ __device__ __forceinline__ float dot4_rn(const float* m, float x, float y, float
 }
 
 // corners (geometry_utils.py:110-129), planes (:163-207), AABB (:210-221); one thread, fixed op order.
-__global__ void frustum_setup_kernel(FrameGeom* g, const FrameDev* f) {
+__device__ __forceinline__ void frustum_setup_body(FrameGeom* g, const FrameDev* f) {
   const float dmin = __int_as_float(g->dmin_bits), dmax = __int_as_float(g->dmax_bits);
   const float wf = static_cast<float>(f->w), hf = static_cast<float>(f->h);
   const float px[8] = {0.f, wf, 0.f, wf, 0.f, wf, 0.f, wf};
@@ -97,15 +97,14 @@ __global__ void frustum_setup_kernel(FrameGeom* g, const FrameDev* f) {
     g->planes[i][0] = n0; g->planes[i][1] = n1; g->planes[i][2] = n2; g->planes[i][3] = d;
   }
 }
+__global__ void frustum_setup_kernel(FrameGeom* g, const FrameDev* f) { frustum_setup_body(g, f); }
 
 // ------------------------------------------------------------------------------------------ depth filter
 // torchvision _get_gaussian_kernel1d(7, 2.5, float32) bit patterns (see oracle/fusion.py)
 __constant__ uint32_t kGauss7Bits[7] = {1035802123u, 1041042090u, 1043549328u, 1044527997u,
                                         1043549328u, 1041042090u, 1035802123u};
 
-__global__ void depth_filter_kernel(const float* __restrict__ depth, int h, int w, float* __restrict__ out) {
-  const int x = blockIdx.x * blockDim.x + threadIdx.x;
-  const int y = blockIdx.y * blockDim.y + threadIdx.y;
+__device__ __forceinline__ void depth_filter_body(const float* __restrict__ depth, int h, int w, float* __restrict__ out, int x, int y) {
   if (x >= w || y >= h) return;
   float acc = 0.f;
 #pragma unroll
@@ -123,6 +122,9 @@ __global__ void depth_filter_kernel(const float* __restrict__ depth, int h, int 
   }
   const float d = depth[static_cast<size_t>(y) * w + x];
   out[static_cast<size_t>(y) * w + x] = fabsf(__fsub_rn(d, acc)) > 0.05f ? -1.f : d;
+}
+__global__ void depth_filter_kernel(const float* __restrict__ depth, int h, int w, float* __restrict__ out) {
+  depth_filter_body(depth, h, w, out, blockIdx.x * blockDim.x + threadIdx.x, blockIdx.y * blockDim.y + threadIdx.y);
 }
 
 // ------------------------------------------------------------------------------------------ mask areas
@@ -259,8 +261,8 @@ __global__ void __launch_bounds__(kP1Threads)
 
 // ------------------------------------------------------------------------------------------ vote reduce
 // One block per mask: n_unassigned, n_assigned, mode of assigned ids (ties -> smallest id = torch.mode on CPU).
-__global__ void vote_reduce_kernel(const int32_t* __restrict__ votes, int n_ins, const int32_t* __restrict__ area,
-                                   ovo_vote_row* __restrict__ rows) {
+__device__ __forceinline__ void vote_reduce_body(const int32_t* __restrict__ votes, int n_ins, const int32_t* __restrict__ area,
+                                                 ovo_vote_row* __restrict__ rows) {
   const int m = blockIdx.x;
   const int32_t* row = votes + static_cast<size_t>(m) * (n_ins + 1);
   int best_cnt = 0, best_id = 0x7fffffff, total = 0;
@@ -306,6 +308,10 @@ __global__ void vote_reduce_kernel(const int32_t* __restrict__ votes, int n_ins,
     r.reserved = 0;
     rows[m] = r;
   }
+}
+__global__ void vote_reduce_kernel(const int32_t* __restrict__ votes, int n_ins, const int32_t* __restrict__ area,
+                                   ovo_vote_row* __restrict__ rows) {
+  vote_reduce_body(votes, n_ins, area, rows);
 }
 
 // New ids are allocated in mask order (ovo.py:255,271-273): every mask decides in parallel, then an ordered
@@ -362,17 +368,295 @@ __global__ void associate_pass2_kernel(const int2* __restrict__ match_list, cons
   }
 }
 
+// ------------------------------------------------------------------------------------------ batched association
+// All keyframes of a batch against the map in ONE pass over xyz (ovo_map_associate_batch): the geometry of keyframe f does not
+// depend on the instance ids, only its vote does.  Pass A therefore writes, for every keyframe f and point p, the mask the
+// point was matched into (seg_of_pt[f][p], int16, -1 = none); the votes are then taken keyframe by keyframe over these dense
+// rows (coalesced 2 + 4 B per point) with the id decisions left on the device, and the host reads all rows back once.
+struct BatchFrame {
+  FrameDev fr;
+  FrameGeom geom;
+  const float* depth_raw;     // frustum from the raw depth (ovo.py:209)
+  const float* depth_used;    // matching against the filtered depth (ovo.py:213-216)
+  float* depth_filtered;      // workspace (nullptr: no filter)
+  const int32_t* seg_map;
+  int n_masks, track_th;
+  int votes_off;              // offset of this keyframe's vote table in the batch's table buffer (ints)
+  int pad;
+};
+
+__global__ void batch_depth_minmax_kernel(BatchFrame* __restrict__ fr) {
+  BatchFrame& b = fr[blockIdx.y];
+  const int n = b.fr.h * b.fr.w;
+  int lmin = 0x7f800000, lmax = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float d = b.depth_raw[i];
+    if (d > 0.f) {
+      const int v = __float_as_int(d);
+      lmin = min(lmin, v);
+      lmax = max(lmax, v);
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    lmin = min(lmin, __shfl_xor_sync(0xffffffffu, lmin, o));
+    lmax = max(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMin(&b.geom.dmin_bits, lmin);
+    atomicMax(&b.geom.dmax_bits, lmax);
+  }
+}
+
+__global__ void batch_frustum_setup_kernel(BatchFrame* fr) { frustum_setup_body(&fr[blockIdx.x].geom, &fr[blockIdx.x].fr); }
+
+__global__ void batch_depth_filter_kernel(const BatchFrame* __restrict__ fr) {
+  const BatchFrame& b = fr[blockIdx.z];
+  if (b.depth_filtered == nullptr) return;
+  depth_filter_body(b.depth_raw, b.fr.h, b.fr.w, b.depth_filtered, blockIdx.x * blockDim.x + threadIdx.x, blockIdx.y * blockDim.y + threadIdx.y);
+}
+
+__global__ void batch_seg_area_kernel(const BatchFrame* __restrict__ fr, int32_t* __restrict__ area, int area_stride) {
+  extern __shared__ int32_t hist[];
+  const BatchFrame& b = fr[blockIdx.y];
+  const int n_masks = b.n_masks, n = b.fr.H * b.fr.W;
+  for (int i = threadIdx.x; i < n_masks; i += blockDim.x) hist[i] = 0;
+  __syncthreads();
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int s = b.seg_map[i];
+    if (s >= 0 && s < n_masks) atomicAdd(&hist[s], 1);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n_masks; i += blockDim.x)
+    if (hist[i]) atomicAdd(&area[blockIdx.y * area_stride + i], hist[i]);
+}
+
+// cull + project + depth test + seg lookup of one point against one keyframe (same operations, same order as pass 1 /
+// oracle/fusion.py associate); returns matched, *seg = mask index or -1
+__device__ __forceinline__ bool match_point_seg(float x, float y, float z, const FrameGeom& g, const FrameDev& f,
+                                                const float* __restrict__ depth, const int32_t* __restrict__ seg_map,
+                                                int n_masks, int* seg) {
+  *seg = -1;
+  bool in = x >= g.lo[0] && x <= g.hi[0] && y >= g.lo[1] && y <= g.hi[1] && z >= g.lo[2] && z <= g.hi[2];
+  if (!in) return false;
+#pragma unroll
+  for (int p = 0; p < 6; ++p) in = in && (dot4_rn(g.planes[p], x, y, z) <= 0.f);
+  if (!in) return false;
+  const float lx = dot4_rn(&f.w2c[0], x, y, z), ly = dot4_rn(&f.w2c[4], x, y, z);
+  const float lz = dot4_rn(&f.w2c[8], x, y, z), lw = dot4_rn(&f.w2c[12], x, y, z);
+  const float X = __fdiv_rn(lx, lw), Y = __fdiv_rn(ly, lw), Z = __fdiv_rn(lz, lw);
+  float ph[3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+    ph[r] = __fadd_rn(__fadd_rn(__fmul_rn(f.K[3 * r], X), __fmul_rn(f.K[3 * r + 1], Y)), __fmul_rn(f.K[3 * r + 2], Z));
+  const float uf = rintf(__fdiv_rn(ph[0], ph[2])), vf = rintf(__fdiv_rn(ph[1], ph[2]));
+  if (!(fabsf(uf) < 2e9f && fabsf(vf) < 2e9f)) return false;   // also rejects NaN/Inf
+  int u = static_cast<int>(uf), v = static_cast<int>(vf);
+  if (u < 0 || v < 0 || u >= f.w || v >= f.h) return false;
+  const float d = __ldg(depth + static_cast<size_t>(v) * f.w + u);
+  if (!(fabsf(__fsub_rn(lz, d)) < f.match_th && d != 0.f)) return false;
+  if (f.has_ratio) {  // ovo.py:218-221
+    u += f.crop_edge;
+    v += f.crop_edge;
+    v = static_cast<int>(__fmul_rn(static_cast<float>(v), f.ratio_h));
+    u = static_cast<int>(__fmul_rn(static_cast<float>(u), f.ratio_w));
+  }
+  if (u >= 0 && v >= 0 && u < f.W && v < f.H) {
+    const int s = __ldg(seg_map + static_cast<size_t>(v) * f.W + u);
+    *seg = s < n_masks ? s : -1;
+  }
+  return true;
+}
+
+constexpr int kBatchFramesPerPass = 16;   // keyframes whose constants sit in shared memory at once
+
+__global__ void __launch_bounds__(kP1Threads)
+    associate_batch_pass_kernel(const float* __restrict__ xyz, long long N, const BatchFrame* __restrict__ frames, int f0, int nf,
+                                int16_t* __restrict__ seg_of_pt /* [F][N] */, int32_t* __restrict__ n_matched /* [F] */) {
+  __shared__ float s_xyz[kP1Threads * 3];
+  __shared__ BatchFrame s_fr[kBatchFramesPerPass];
+  __shared__ int s_matched[kBatchFramesPerPass];
+  for (int i = threadIdx.x; i < nf * static_cast<int>(sizeof(BatchFrame) / 4); i += blockDim.x)
+    reinterpret_cast<int*>(s_fr)[i] = reinterpret_cast<const int*>(frames + f0)[i];
+  if (threadIdx.x < kBatchFramesPerPass) s_matched[threadIdx.x] = 0;
+  const int lane = threadIdx.x & 31;
+  for (long long base = static_cast<long long>(blockIdx.x) * kP1Threads; base < N;
+       base += static_cast<long long>(gridDim.x) * kP1Threads) {
+    __syncthreads();
+    const long long fbase = base * 3;
+    const long long fend = min(N * 3, fbase + kP1Threads * 3);
+    if (fend - fbase == kP1Threads * 3) {
+      const float4* src = reinterpret_cast<const float4*>(xyz + fbase);
+      if (threadIdx.x < kP1Threads * 3 / 4) reinterpret_cast<float4*>(s_xyz)[threadIdx.x] = __ldg(src + threadIdx.x);
+    } else {
+      for (int i = threadIdx.x; i < fend - fbase; i += kP1Threads) s_xyz[i] = xyz[fbase + i];
+    }
+    __syncthreads();
+    const long long idx = base + threadIdx.x;
+    const bool live = idx < N;
+    const float x = s_xyz[threadIdx.x * 3], y = s_xyz[threadIdx.x * 3 + 1], z = s_xyz[threadIdx.x * 3 + 2];
+    for (int f = 0; f < nf; ++f) {
+      int seg = -1;
+      const bool matched = live && match_point_seg(x, y, z, s_fr[f].geom, s_fr[f].fr, s_fr[f].depth_used, s_fr[f].seg_map,
+                                                   s_fr[f].n_masks, &seg);
+      if (live) seg_of_pt[static_cast<size_t>(f0 + f) * N + idx] = static_cast<int16_t>(seg);
+      const unsigned bal = __ballot_sync(0xffffffffu, matched);
+      if (lane == 0 && bal) atomicAdd(&s_matched[f], __popc(bal));
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < nf && s_matched[threadIdx.x]) atomicAdd(&n_matched[f0 + threadIdx.x], s_matched[threadIdx.x]);
+}
+
+// Keyframe f of the batch: first give the points keyframe f-1 matched their new ids (its decisions are final), then vote.
+// One coalesced scan of the two dense rows and the ids; votes go to shared memory when the table fits.
+__global__ void __launch_bounds__(256)
+    batch_vote_scan_kernel(const int16_t* __restrict__ seg_prev, const int32_t* __restrict__ mask_ins_prev,
+                           const int16_t* __restrict__ seg_cur, int32_t* __restrict__ ins_ids, long long N,
+                           const int32_t* __restrict__ n_ins_ptr, int n_masks, int32_t* __restrict__ votes, int smem_ints) {
+  extern __shared__ int32_t s_votes[];
+  const int n_ins = *n_ins_ptr;
+  const int n_votes = n_masks * (n_ins + 1);
+  const bool use_smem = seg_cur != nullptr && n_votes <= smem_ints;
+  if (use_smem)
+    for (int i = threadIdx.x; i < n_votes; i += blockDim.x) s_votes[i] = 0;
+  __syncthreads();
+  for (long long p = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; p < N;
+       p += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int sp = seg_prev ? seg_prev[p] : -1;
+    const int sc = seg_cur ? seg_cur[p] : -1;
+    if (sp < 0 && sc < 0) continue;
+    int id = ins_ids[p];
+    if (sp >= 0 && id == -1) {   // assigned points never change (ovo.py:274,280)
+      const int nid = mask_ins_prev[sp];
+      if (nid >= 0) { id = nid; ins_ids[p] = nid; }
+    }
+    if (sc >= 0) {
+      if (id >= n_ins) id = -1;  // ids the decisions do not know about count as unassigned
+      const int key = sc * (n_ins + 1) + (id + 1);
+      atomicAdd(use_smem ? &s_votes[key] : &votes[key], 1);
+    }
+  }
+  if (use_smem) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_votes; i += blockDim.x)
+      if (s_votes[i]) atomicAdd(&votes[i], s_votes[i]);
+  }
+}
+
+// vote_reduce_kernel with the instance count read from the device (the batch never brings it to the host)
+__global__ void batch_vote_reduce_kernel(const int32_t* __restrict__ votes, const int32_t* __restrict__ n_ins_ptr,
+                                         const int32_t* __restrict__ area, ovo_vote_row* __restrict__ rows) {
+  vote_reduce_body(votes, *n_ins_ptr, area, rows);
+}
+
 // ------------------------------------------------------------------------------------------ dense fusion
-// One warp per matched point: 2 KB bf16 row read-modify-write, 16 B per lane per access; every lane issues all
-// of its loads for the row before the arithmetic so several KB per warp are in flight (HBM latency hiding).
+// The dense per-point bank keeps, per map point, the running mean of the descriptors of the masks it fell into, as TWO
+// bf16 planes: `hi` = the mean rounded to bf16 (the operand of the cosine query, read once from HBM by ovo_query_dense) and
+// `lo` = bf16(mean - hi), the part of the mean the first plane cannot hold.  hi + lo carries 16-17 significant bits, so the
+// increment (e - f)/c of a long stream (c in the hundreds: below half a bf16 ulp of f) is not lost.
+// Update of one point by the k descriptors e_1..e_k a pass brings (keyframe order), every operation rounded to f32, no FMA
+// contraction (oracle/fusion.py dense_update restates it):
+//     f = hi + lo;  s = e_1 + ... + e_k  (e_i = the descriptor rounded to bf16);  c' = c + k
+//     f' = f + (s - k*f) * (1/c');  hi' = bf16(f');  lo' = bf16(f' - hi')
+// One warp per touched point: lane l owns elements 8*(l + 32*i) .. +7 of the row (16 B per access).
+template <int kVecPerLane>
+struct DenseRow {
+  uint4 rh[kVecPerLane], rl[kVecPerLane];   // the two planes as loaded (unpacked only in dense_row_finish: 8 registers, not 32)
+  float s[kVecPerLane * 8];                  // sum of this pass's descriptors
+};
+
+__device__ __forceinline__ void unpack_bf16x8(const uint4& u, float* o) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    o[2 * j] = __uint_as_float(w[j] << 16);
+    o[2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u);
+  }
+}
+
+template <int kVecPerLane>
+__device__ __forceinline__ void dense_row_load(DenseRow<kVecPerLane>& r, const __nv_bfloat16* hi, const __nv_bfloat16* lo,
+                                               size_t p, int D, int lane) {
+  const uint4* ph = reinterpret_cast<const uint4*>(hi + p * D);
+  const uint4* pl = reinterpret_cast<const uint4*>(lo + p * D);
+  const int nvec = D >> 3;
+#pragma unroll
+  for (int i = 0; i < kVecPerLane; ++i) {
+    const int v = lane + 32 * i;
+    if (v < nvec) { r.rh[i] = ph[v]; r.rl[i] = pl[v]; }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r.s[8 * i + j] = 0.f;
+  }
+}
+
+// s += e (descriptor row, bf16); `first` = nothing has been added yet (s = e exactly)
+template <int kVecPerLane>
+__device__ __forceinline__ void dense_row_add(DenseRow<kVecPerLane>& r, const uint4 (&e)[kVecPerLane], int D, int lane) {
+  const int nvec = D >> 3;
+#pragma unroll
+  for (int i = 0; i < kVecPerLane; ++i) {
+    const int v = lane + 32 * i;
+    if (v < nvec) {
+      float a[8];
+      unpack_bf16x8(e[i], a);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r.s[8 * i + j] = __fadd_rn(r.s[8 * i + j], a[j]);
+    }
+  }
+}
+
+template <int kVecPerLane>
+__device__ __forceinline__ void dense_row_finish(DenseRow<kVecPerLane>& r, int k, int c_new, __nv_bfloat16* hi,
+                                                 __nv_bfloat16* lo, size_t p, int D, int lane) {
+  const float kf = static_cast<float>(k), inv = __fdiv_rn(1.0f, static_cast<float>(c_new));
+  uint4* ph = reinterpret_cast<uint4*>(hi + p * D);
+  uint4* pl = reinterpret_cast<uint4*>(lo + p * D);
+  const int nvec = D >> 3;
+#pragma unroll
+  for (int i = 0; i < kVecPerLane; ++i) {
+    const int v = lane + 32 * i;
+    if (v < nvec) {
+      float a[8], b[8];
+      unpack_bf16x8(r.rh[i], a);
+      unpack_bf16x8(r.rl[i], b);
+      uint32_t wh[4], wl[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float f1[2];
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          const float f = __fadd_rn(a[2 * j + t], b[2 * j + t]);
+          f1[t] = __fadd_rn(f, __fmul_rn(__fsub_rn(r.s[8 * i + 2 * j + t], __fmul_rn(kf, f)), inv));
+        }
+        wh[j] = pack_bf16(f1[0], f1[1]);
+        const float h0 = __uint_as_float(wh[j] << 16), h1 = __uint_as_float(wh[j] & 0xffff0000u);
+        wl[j] = pack_bf16(__fsub_rn(f1[0], h0), __fsub_rn(f1[1], h1));
+      }
+      ph[v] = make_uint4(wh[0], wh[1], wh[2], wh[3]);
+      pl[v] = make_uint4(wl[0], wl[1], wl[2], wl[3]);
+    }
+  }
+}
+
+template <int kVecPerLane>
+__device__ __forceinline__ void load_desc_row(uint4 (&e)[kVecPerLane], const __nv_bfloat16* feats, int row, int D, int lane) {
+  const uint4* fr = reinterpret_cast<const uint4*>(feats + static_cast<size_t>(row) * D);
+  const int nvec = D >> 3;
+#pragma unroll
+  for (int i = 0; i < kVecPerLane; ++i) {
+    const int v = lane + 32 * i;
+    if (v < nvec) e[i] = __ldg(fr + v);
+  }
+}
+
+// one keyframe, from its match list: one warp per matched point (a point appears once in a keyframe's list)
 template <int kVecPerLane>
 __global__ void __launch_bounds__(256)
-    fuse_dense_kernel(const int2* __restrict__ match_list, int n, __nv_bfloat16* __restrict__ bank,
-                      int32_t* __restrict__ counts, int D, const float* __restrict__ feats,
+    fuse_dense_kernel(const int2* __restrict__ match_list, int n, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                      int32_t* __restrict__ counts, int D, const __nv_bfloat16* __restrict__ feats,
                       const int32_t* __restrict__ mask_row) {
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
-  const int nvec = D >> 3;
   for (int e = blockIdx.x * warps_per_block + (threadIdx.x >> 5); e < n; e += gridDim.x * warps_per_block) {
     const int2 m = match_list[e];
     const int r = mask_row[m.y];
@@ -380,40 +664,20 @@ __global__ void __launch_bounds__(256)
     const int c = counts[m.x] + 1;
     __syncwarp();
     if (lane == 0) counts[m.x] = c;
-    const float inv = __fdiv_rn(1.0f, static_cast<float>(c));   // f += (e - f) * (1/c): one division per point
-    uint4* prow = reinterpret_cast<uint4*>(bank + static_cast<size_t>(m.x) * D);
-    const float4* frow = reinterpret_cast<const float4*>(feats + static_cast<size_t>(r) * D);
-    uint4 raw[kVecPerLane];
-#pragma unroll
-    for (int i = 0; i < kVecPerLane; ++i) {
-      const int v = lane + 32 * i;
-      if (v < nvec) raw[i] = prow[v];
-    }
-#pragma unroll
-    for (int i = 0; i < kVecPerLane; ++i) {
-      const int v = lane + 32 * i;
-      if (v < nvec) {
-        const float4 e0 = __ldg(frow + 2 * v), e1 = __ldg(frow + 2 * v + 1);
-        const float ev[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
-        uint32_t* w = reinterpret_cast<uint32_t*>(&raw[i]);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          __nv_bfloat162 b2 = *reinterpret_cast<__nv_bfloat162*>(&w[j]);
-          float f0 = __bfloat162float(b2.x), f1 = __bfloat162float(b2.y);
-          f0 = __fadd_rn(f0, __fmul_rn(__fsub_rn(ev[2 * j], f0), inv));
-          f1 = __fadd_rn(f1, __fmul_rn(__fsub_rn(ev[2 * j + 1], f1), inv));
-          w[j] = pack_bf16(f0, f1);
-        }
-        prow[v] = raw[i];
-      }
-    }
+    DenseRow<kVecPerLane> row;
+    uint4 ev[kVecPerLane];
+    load_desc_row<kVecPerLane>(ev, feats, r, D, lane);
+    dense_row_load<kVecPerLane>(row, hi, lo, static_cast<size_t>(m.x), D, lane);
+    dense_row_add<kVecPerLane>(row, ev, D, lane);
+    dense_row_finish<kVecPerLane>(row, 1, c, hi, lo, static_cast<size_t>(m.x), D, lane);
   }
 }
 
 // ------------------------------------------------------------------------------------------ batched dense fusion
-// Several keyframes fused in ONE pass over the bank: a point matched in k keyframes of the batch has its 2 KB row
-// read once and written once instead of k times.  The arithmetic per point is the same sequence of updates
-// (keyframe order, bf16 rounding after every update), so the result is bit-identical to k fuse_dense_kernel calls.
+// Several keyframes fused in ONE pass over the bank: a point matched in k keyframes of the batch has its two 2 KB rows
+// read once and written once instead of k times, and its k descriptors are summed in registers (one add per element and
+// keyframe).  Input: seg_of_pt [F][N] int16 = the mask each keyframe matched the point into (-1 = none), written by the
+// batched association or scattered from the keyframes' match lists.
 __global__ void scatter_matches_kernel(const int2* __restrict__ list, int n, int16_t* __restrict__ seg_of_pt) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const int2 e = list[i];
@@ -421,73 +685,63 @@ __global__ void scatter_matches_kernel(const int2* __restrict__ list, int n, int
   }
 }
 
-// One warp per touched point, all keyframes of the batch applied to the row while it sits in registers.  Descriptor
-// rows come from L2 (the batch's descriptors are ~1.5 MB).  (A variant that kept 64-column descriptor slabs in
-// shared memory was 4x slower on B200: 128-byte strided bank accesses waste DRAM pages.)
+// A warp scans 32 consecutive points (lane = point) for "matched by some keyframe", then takes the touched points one at a
+// time: lane f looks up the descriptor row of keyframe f for the point (seg_of_pt -> mask_row: F independent two-step
+// gathers in one round), the rows are broadcast with shuffles and two descriptor rows are in flight per step.
 template <int kVecPerLane>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, kVecPerLane <= 4 ? 2 : 1)
     fuse_dense_batch_kernel(const int16_t* __restrict__ seg_of_pt /* [F][N] */, int F, long long N,
-                            __nv_bfloat16* __restrict__ bank, int32_t* __restrict__ counts, int D,
-                            const float* __restrict__ feats, const int32_t* __restrict__ mask_row /* [F][n_masks] */,
+                            __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int32_t* __restrict__ counts, int D,
+                            const __nv_bfloat16* __restrict__ feats, const int32_t* __restrict__ mask_row /* [F][n_masks] */,
                             int n_masks) {
   const int lane = threadIdx.x & 31;
   const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const long long n_warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
-  const int nvec = D >> 3;
+  const int groups = (F + 31) >> 5;   // keyframes are looked up 32 at a time (lane = keyframe)
   for (long long p0 = warp * 32; p0 < N; p0 += n_warps * 32) {
-    // lane l looks at point p0+l: which keyframes of the batch matched it into a mask that produced a descriptor?
     const long long pl = p0 + lane;
-    unsigned fmask = 0;  // bit f set -> keyframe f updates this point
-    if (pl < N) {
-      for (int f = 0; f < F; ++f) {
-        const int m = seg_of_pt[static_cast<size_t>(f) * N + pl];
-        if (m >= 0 && m < n_masks && mask_row[f * n_masks + m] >= 0) fmask |= 1u << f;
+    bool any = false;
+    if (pl < N)
+      for (int f = 0; f < F; ++f) any = any || (seg_of_pt[static_cast<size_t>(f) * N + pl] >= 0);
+    unsigned todo_pts = __ballot_sync(0xffffffffu, any);
+    while (todo_pts) {
+      const int src = __ffs(todo_pts) - 1;
+      todo_pts &= todo_pts - 1;
+      const size_t p = static_cast<size_t>(p0 + src);
+      int rlane[2] = {-1, -1};   // descriptor row of keyframe 32*g + lane for this point (F <= 64)
+      int k = 0;
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        const int f = 32 * g + lane;
+        if (g < groups && f < F) {
+          const int m = seg_of_pt[static_cast<size_t>(f) * N + p];
+          if (m >= 0 && m < n_masks) rlane[g] = mask_row[f * n_masks + m];
+        }
+        k += __popc(__ballot_sync(0xffffffffu, rlane[g] >= 0));
       }
-    }
-    unsigned todo = __ballot_sync(0xffffffffu, fmask != 0);
-    while (todo) {
-      const int src = __ffs(todo) - 1;
-      todo &= todo - 1;
-      const long long p = p0 + src;
-      const unsigned fm = __shfl_sync(0xffffffffu, fmask, src);
-      int c = counts[p];
-      uint4* prow = reinterpret_cast<uint4*>(bank + static_cast<size_t>(p) * D);
-      uint4 raw[kVecPerLane];
+      if (k == 0) continue;   // matched only into masks that produced no descriptor
+      DenseRow<kVecPerLane> row;
+      dense_row_load<kVecPerLane>(row, hi, lo, p, D, lane);
+      const int c = counts[p];
 #pragma unroll
-      for (int i = 0; i < kVecPerLane; ++i) {
-        const int v = lane + 32 * i;
-        if (v < nvec) raw[i] = prow[v];
-      }
-      for (int f = 0; f < F; ++f) {
-        if (!((fm >> f) & 1u)) continue;
-        const int r = mask_row[f * n_masks + seg_of_pt[static_cast<size_t>(f) * N + p]];
-        ++c;
-        const float inv = __fdiv_rn(1.0f, static_cast<float>(c));
-        const float4* frow = reinterpret_cast<const float4*>(feats + static_cast<size_t>(r) * D);
-#pragma unroll
-        for (int i = 0; i < kVecPerLane; ++i) {
-          const int v = lane + 32 * i;
-          if (v < nvec) {
-            const float4 e0 = __ldg(frow + 2 * v), e1 = __ldg(frow + 2 * v + 1);
-            const float ev[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
-            uint32_t* w = reinterpret_cast<uint32_t*>(&raw[i]);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              __nv_bfloat162 b2 = *reinterpret_cast<__nv_bfloat162*>(&w[j]);
-              float f0 = __bfloat162float(b2.x), f1 = __bfloat162float(b2.y);
-              f0 = __fadd_rn(f0, __fmul_rn(__fsub_rn(ev[2 * j], f0), inv));
-              f1 = __fadd_rn(f1, __fmul_rn(__fsub_rn(ev[2 * j + 1], f1), inv));
-              w[j] = pack_bf16(f0, f1);
-            }
-          }
+      for (int g = 0; g < 2; ++g) {
+        unsigned todo = __ballot_sync(0xffffffffu, rlane[g] >= 0);
+        while (todo) {
+          const int f0 = __ffs(todo) - 1;
+          todo &= todo - 1;
+          const int f1 = todo ? __ffs(todo) - 1 : -1;
+          if (f1 >= 0) todo &= todo - 1;
+          const int r0 = __shfl_sync(0xffffffffu, rlane[g], f0);
+          const int r1 = __shfl_sync(0xffffffffu, rlane[g], f1 >= 0 ? f1 : f0);
+          uint4 e0[kVecPerLane], e1[kVecPerLane];
+          load_desc_row<kVecPerLane>(e0, feats, r0, D, lane);
+          if (f1 >= 0) load_desc_row<kVecPerLane>(e1, feats, r1, D, lane);
+          dense_row_add<kVecPerLane>(row, e0, D, lane);
+          if (f1 >= 0) dense_row_add<kVecPerLane>(row, e1, D, lane);
         }
       }
-#pragma unroll
-      for (int i = 0; i < kVecPerLane; ++i) {
-        const int v = lane + 32 * i;
-        if (v < nvec) prow[v] = raw[i];
-      }
-      if (lane == 0) counts[p] = c;
+      dense_row_finish<kVecPerLane>(row, k, c + k, hi, lo, p, D, lane);
+      if (lane == 0) counts[p] = c + k;
     }
   }
 }
@@ -774,9 +1028,6 @@ __global__ void mark_mapped_pixels_kernel(const float* __restrict__ xyz, long lo
                                           uint8_t* __restrict__ mapped) {
   __shared__ FrameGeom s_g;
   __shared__ FrameDev s_f;
-  __shared__ int s_warp_cnt[kP1Threads / 32], s_base, s_matched;
-  int n_matched_local = 0;
-  if (threadIdx.x == 0) s_matched = 0;
   if (threadIdx.x < sizeof(FrameGeom) / 4) reinterpret_cast<int*>(&s_g)[threadIdx.x] = reinterpret_cast<const int*>(geom)[threadIdx.x];
   for (int i = threadIdx.x; i < static_cast<int>(sizeof(FrameDev) / 4); i += blockDim.x)
     reinterpret_cast<int*>(&s_f)[i] = reinterpret_cast<const int*>(fr)[i];
@@ -896,6 +1147,17 @@ struct ovo_map {
   __nv_bfloat16* text_bf16 = nullptr; size_t text_cap = 0;
   // pinned host staging
   ovo_vote_row* h_rows = nullptr; int32_t* h_counters = nullptr; ovo::FrameDev* h_frame = nullptr;
+  // batched association (ovo_map_associate_batch / ovo_map_batch_*): control block [n_matched[Fcap] | next_ins_id,pad | frames[Fcap] |
+  // rows[Fcap][bt_stride]] on the device and mirrored in pinned host memory, per-keyframe areas / mask->instance tables, filtered
+  // depth maps, the vote tables and the dense rows seg_of_pt [F][N] (shared with ovo_map_fuse_dense_batch)
+  uint8_t* bctl = nullptr; uint8_t* h_bctl = nullptr; int bt_fcap = 0, bt_stride = 0;
+  int32_t* bt_area = nullptr; int32_t* bt_mask_ins = nullptr;
+  float* bt_depth = nullptr; size_t bt_depth_cap = 0;
+  int32_t* bt_tables = nullptr; size_t bt_tables_cap = 0;
+  bool bt_valid = false; int bt_F = 0; int64_t bt_N = 0; int bt_next = 0; int32_t* bt_user_tables = nullptr;
+  std::vector<int> bt_n_masks, bt_track_th, bt_votes_off, bt_table_len, bt_slots;
+  int64_t dense_N = 0; int dense_F = 0; std::vector<int> dense_slots;   // what seg_dense currently holds (from a batched association)
+  __nv_bfloat16* feats_bf16 = nullptr; size_t feats_cap = 0;
   // association split in two calls (ovo_map_vote / ovo_map_apply): state of the pending keyframe
   bool pend_valid = false; int64_t pend_N = 0; int pend_n_ins = 0, pend_n_masks = 0, pend_slot = 0, pend_track_th = 0;
 };
@@ -972,6 +1234,7 @@ void ovo_map_destroy(ovo_map_t* m) {
   if (!m) return;
   cudaFree(m->ctl); cudaFreeHost(m->h_ctl); cudaFree(m->votes); cudaFree(m->area);
   cudaFree(m->scratch_list); cudaFree(m->depth_f); cudaFree(m->seg_dense); cudaFree(m->mapped); cudaFree(m->pix_flags); cudaFree(m->text_bf16);
+  cudaFree(m->bctl); cudaFreeHost(m->h_bctl); cudaFree(m->bt_area); cudaFree(m->bt_depth); cudaFree(m->bt_tables); cudaFree(m->feats_bf16);
   for (int i = 0; i < ovo_map::kSlots; ++i) cudaFree(m->slot_list[i]);
   delete m;
 }
@@ -1080,6 +1343,8 @@ static int associate_apply(ovo_map_t* m, int32_t* ins_ids_dev, int* next_ins_id,
   if (n_list > 0)
     OVO_CUDA(cudaMemcpyAsync(m->slot_list[kf_slot], m->scratch_list, n_list * sizeof(int2), cudaMemcpyDeviceToDevice, stream));
   m->slot_n[kf_slot] = n_list;
+  for (size_t i = 0; i < m->dense_slots.size(); ++i)
+    if (m->dense_slots[i] == kf_slot) m->dense_slots[i] = -1;   // the slot's dense row (of an earlier batch) is stale now
   return OVO_OK;
 }
 
@@ -1115,6 +1380,233 @@ int ovo_map_apply(ovo_map_t* m, const int32_t* table_in_dev, int32_t* ins_ids_de
   return associate_apply(m, ins_ids_dev, next_ins_id, votes_host, n_matched_host, stream);
 }
 
+// ----------------------------------------------------------------------------------------------- batched association
+namespace {
+struct BatchCtl {   // byte offsets inside the batch control block
+  size_t n_matched, next, frames, rows, end;
+  BatchCtl(int fcap, int stride) {
+    n_matched = 0;
+    next = static_cast<size_t>(fcap) * 4;
+    frames = next + 16;
+    rows = frames + static_cast<size_t>(fcap) * sizeof(ovo::BatchFrame);
+    end = rows + static_cast<size_t>(fcap) * stride * sizeof(ovo_vote_row);
+  }
+};
+}  // namespace
+
+static int batch_ctl_alloc(ovo_map* m, int F, int max_masks) {
+  if (F <= m->bt_fcap && max_masks <= m->bt_stride) return OVO_OK;
+  const int fcap = std::max(F, m->bt_fcap), stride = std::max((max_masks + 63) / 64 * 64, m->bt_stride);
+  cudaFree(m->bctl); cudaFreeHost(m->h_bctl); cudaFree(m->bt_area);
+  m->bctl = nullptr; m->h_bctl = nullptr; m->bt_area = nullptr; m->bt_fcap = 0; m->bt_stride = 0;
+  const BatchCtl L(fcap, stride);
+  if (cudaMalloc(&m->bctl, L.end) != cudaSuccess || cudaMallocHost(&m->h_bctl, L.end) != cudaSuccess ||
+      cudaMalloc(&m->bt_area, 2 * static_cast<size_t>(fcap) * stride * sizeof(int32_t)) != cudaSuccess)
+    return ovo::set_error(OVO_E_CUDA, "ovo_map: batch control block allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+  m->bt_mask_ins = m->bt_area + static_cast<size_t>(fcap) * stride;
+  m->bt_fcap = fcap; m->bt_stride = stride;
+  return OVO_OK;
+}
+
+int ovo_map_batch_begin(ovo_map_t* m, const float* xyz_dev, const int32_t* ins_ids_dev, int64_t N, const ovo_frame* frames, int F,
+                        const int* kf_slots, int next_ins_id, int32_t* tables_dev, int64_t tables_cap, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  OVO_REQUIRE(m && frames && F > 0 && F <= 64, "ovo_map_batch_begin: 1..64 keyframes per batch (got %d)", F);
+  OVO_REQUIRE(N >= 0 && N < (1LL << 31) && next_ins_id >= 0, "ovo_map_batch_begin: N / next_ins_id out of range");
+  OVO_REQUIRE(N == 0 || (xyz_dev && ins_ids_dev), "ovo_map_batch_begin: null map");
+  OVO_REQUIRE(!m->pend_valid && !m->bt_valid, "ovo_map_batch_begin: another association is pending on this handle");
+  int max_masks = 1;
+  size_t npix_max = 0;
+  for (int f = 0; f < F; ++f) {
+    const ovo_frame& fr = frames[f];
+    OVO_REQUIRE(fr.n_masks >= 0 && fr.n_masks <= 8192, "ovo_map_batch_begin: n_masks out of range (keyframe %d)", f);
+    OVO_REQUIRE(fr.depth_dev && fr.seg_map_dev && fr.h > 0 && fr.w > 0 && fr.H > 0 && fr.W > 0, "ovo_map_batch_begin: bad frame %d", f);
+    OVO_REQUIRE(!kf_slots || (kf_slots[f] >= 0 && kf_slots[f] < ovo_map::kSlots), "ovo_map_batch_begin: kf_slot out of range");
+    max_masks = std::max(max_masks, fr.n_masks);
+    npix_max = std::max(npix_max, static_cast<size_t>(fr.h) * fr.w);
+  }
+  OVO_TRY(batch_ctl_alloc(m, F, max_masks));
+  OVO_TRY(grow(&m->bt_depth, &m->bt_depth_cap, static_cast<size_t>(F) * npix_max));
+  OVO_TRY(grow(&m->seg_dense, &m->seg_dense_cap, static_cast<size_t>(F) * static_cast<size_t>(N > 0 ? N : 1)));
+  // vote tables: keyframe f may see up to next_ins_id + (masks of the keyframes before it) instances; each table is followed by
+  // one counter (the keyframe's n_matched) so that a sharded map sums both with one exchange
+  m->bt_n_masks.assign(F, 0); m->bt_track_th.assign(F, 0); m->bt_votes_off.assign(F, 0); m->bt_table_len.assign(F, 0);
+  m->bt_slots.assign(F, -1);
+  size_t off = 0;
+  int bound = next_ins_id;
+  for (int f = 0; f < F; ++f) {
+    const int nm = frames[f].n_masks;
+    const size_t len = static_cast<size_t>(nm > 0 ? nm : 1) * (bound + 1) + 1;
+    OVO_REQUIRE(len < (1ull << 28), "ovo_map_batch_begin: vote table too large (%d masks x %d instances)", nm, bound);
+    m->bt_n_masks[f] = nm; m->bt_track_th[f] = frames[f].track_th; m->bt_votes_off[f] = static_cast<int>(off);
+    m->bt_table_len[f] = static_cast<int>(len);
+    if (kf_slots) m->bt_slots[f] = kf_slots[f];
+    off += (len + 3) & ~size_t(3);
+    OVO_REQUIRE(off < (1ull << 30), "ovo_map_batch_begin: vote tables of the batch too large");
+    bound += nm;
+  }
+  int32_t* tables = tables_dev;
+  if (tables_dev) {
+    OVO_REQUIRE(static_cast<size_t>(tables_cap) >= off, "ovo_map_batch_begin: tables buffer too small (%lld < %zu ints)", (long long)tables_cap, off);
+  } else {
+    OVO_TRY(grow(&m->bt_tables, &m->bt_tables_cap, off));
+    tables = m->bt_tables;
+  }
+  m->bt_user_tables = tables;
+
+  const BatchCtl L(m->bt_fcap, m->bt_stride);
+  int32_t* h_nm = reinterpret_cast<int32_t*>(m->h_bctl + L.n_matched);
+  int32_t* h_next = reinterpret_cast<int32_t*>(m->h_bctl + L.next);
+  ovo::BatchFrame* hf = reinterpret_cast<ovo::BatchFrame*>(m->h_bctl + L.frames);
+  for (int f = 0; f < F; ++f) {
+    const ovo_frame& fr = frames[f];
+    ovo::BatchFrame& b = hf[f];
+    memset(&b, 0, sizeof(b));
+    memcpy(b.fr.c2w, fr.c2w, sizeof(b.fr.c2w)); memcpy(b.fr.w2c, fr.w2c, sizeof(b.fr.w2c)); memcpy(b.fr.K, fr.K, sizeof(b.fr.K));
+    b.fr.match_th = fr.match_th; b.fr.h = fr.h; b.fr.w = fr.w; b.fr.H = fr.H; b.fr.W = fr.W;
+    b.fr.has_ratio = fr.has_ratio; b.fr.ratio_h = fr.ratio_h; b.fr.ratio_w = fr.ratio_w; b.fr.crop_edge = fr.crop_edge;
+    b.geom.dmin_bits = 0x7f800000; b.geom.dmax_bits = 0;
+    b.depth_raw = fr.depth_dev;
+    b.depth_filtered = fr.depth_filter ? m->bt_depth + static_cast<size_t>(f) * npix_max : nullptr;
+    b.depth_used = fr.depth_filter ? b.depth_filtered : fr.depth_dev;
+    b.seg_map = fr.seg_map_dev; b.n_masks = fr.n_masks; b.track_th = fr.track_th; b.votes_off = m->bt_votes_off[f];
+    h_nm[f] = 0;
+  }
+  h_next[0] = next_ins_id; h_next[1] = h_next[2] = h_next[3] = 0;
+  OVO_CUDA(cudaMemcpyAsync(m->bctl, m->h_bctl, L.frames + static_cast<size_t>(F) * sizeof(ovo::BatchFrame), cudaMemcpyHostToDevice, stream));
+  OVO_CUDA(cudaMemsetAsync(tables, 0, off * sizeof(int32_t), stream));
+  OVO_CUDA(cudaMemsetAsync(m->bt_area, 0, static_cast<size_t>(m->bt_fcap) * m->bt_stride * sizeof(int32_t), stream));
+  ovo::BatchFrame* dfr = reinterpret_cast<ovo::BatchFrame*>(m->bctl + L.frames);
+  int32_t* d_nm = reinterpret_cast<int32_t*>(m->bctl + L.n_matched);
+  const int sms = ovo::num_sms();
+  int hmax = 0, wmax = 0;
+  for (int f = 0; f < F; ++f) { hmax = std::max(hmax, frames[f].h); wmax = std::max(wmax, frames[f].w); }
+  ovo::batch_depth_minmax_kernel<<<dim3(32, F), 256, 0, stream>>>(dfr);
+  OVO_CHECK_LAUNCH();
+  ovo::batch_frustum_setup_kernel<<<F, 1, 0, stream>>>(dfr);
+  OVO_CHECK_LAUNCH();
+  ovo::batch_depth_filter_kernel<<<dim3(ovo::ceil_div(wmax, 32), ovo::ceil_div(hmax, 8), F), dim3(32, 8), 0, stream>>>(dfr);
+  OVO_CHECK_LAUNCH();
+  ovo::batch_seg_area_kernel<<<dim3(32, F), 256, max_masks * sizeof(int32_t), stream>>>(dfr, m->bt_area, m->bt_stride);
+  OVO_CHECK_LAUNCH();
+  if (N > 0) {
+    const int blocks = static_cast<int>(std::min<long long>((N + ovo::kP1Threads - 1) / ovo::kP1Threads, sms * 8LL));
+    for (int f0 = 0; f0 < F; f0 += ovo::kBatchFramesPerPass) {
+      ovo::associate_batch_pass_kernel<<<blocks, ovo::kP1Threads, 0, stream>>>(xyz_dev, N, dfr, f0, std::min(ovo::kBatchFramesPerPass, F - f0),
+                                                                                m->seg_dense, d_nm);
+      OVO_CHECK_LAUNCH();
+    }
+  }
+  m->bt_valid = true; m->bt_F = F; m->bt_N = N; m->bt_next = next_ins_id;
+  m->dense_slots.assign(m->bt_slots.begin(), m->bt_slots.end()); m->dense_N = N; m->dense_F = F;
+  for (int f = 0; f < F; ++f)
+    if (m->bt_slots[f] >= 0) m->slot_n[m->bt_slots[f]] = 0;   // these slots hold dense rows now, not lists
+  return OVO_OK;
+}
+
+// votes of keyframe f on this handle's points (after applying the decisions of keyframe f-1); *table_dev / *table_len = the
+// keyframe's vote table [n_masks x (n_ins+1) | n_matched] inside the batch's table buffer, to be summed over shards
+int ovo_map_batch_vote(ovo_map_t* m, int f, int32_t* ins_ids_dev, int32_t** table_dev, int* table_len, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  OVO_REQUIRE(m && m->bt_valid && f >= 0 && f < m->bt_F, "ovo_map_batch_vote: no batch pending or keyframe %d out of range", f);
+  const BatchCtl L(m->bt_fcap, m->bt_stride);
+  const int64_t N = m->bt_N;
+  int32_t* table = m->bt_user_tables + m->bt_votes_off[f];
+  const int len = m->bt_table_len[f];
+  const int32_t* d_next = reinterpret_cast<const int32_t*>(m->bctl + L.next);
+  if (N > 0) {
+    const int16_t* prev = f > 0 ? m->seg_dense + static_cast<size_t>(f - 1) * N : nullptr;
+    const int32_t* mi_prev = f > 0 ? m->bt_mask_ins + static_cast<size_t>(f - 1) * m->bt_stride : nullptr;
+    const int smem_ints = std::min(len - 1, 10 * 1024);   // up to 40 KB of shared-memory votes
+    const int blocks = static_cast<int>(std::min<long long>((N + 255) / 256, ovo::num_sms() * 4LL));
+    ovo::batch_vote_scan_kernel<<<blocks, 256, smem_ints * sizeof(int32_t), stream>>>(prev, mi_prev, m->seg_dense + static_cast<size_t>(f) * N,
+                                                                                    ins_ids_dev, N, d_next, m->bt_n_masks[f], table, smem_ints);
+    OVO_CHECK_LAUNCH();
+  }
+  // the keyframe's n_matched rides behind its table
+  OVO_CUDA(cudaMemcpyAsync(table + len - 1, m->bctl + L.n_matched + 4 * static_cast<size_t>(f), sizeof(int32_t), cudaMemcpyDeviceToDevice, stream));
+  if (table_dev) *table_dev = table;
+  if (table_len) *table_len = len;
+  return OVO_OK;
+}
+
+// decisions of keyframe f from its (summed) table: per-mask reduce, ordered id allocation; next_ins_id stays on the device
+int ovo_map_batch_decide(ovo_map_t* m, int f, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  OVO_REQUIRE(m && m->bt_valid && f >= 0 && f < m->bt_F, "ovo_map_batch_decide: no batch pending or keyframe %d out of range", f);
+  const BatchCtl L(m->bt_fcap, m->bt_stride);
+  const int nm = m->bt_n_masks[f];
+  int32_t* table = m->bt_user_tables + m->bt_votes_off[f];
+  int32_t* d_next = reinterpret_cast<int32_t*>(m->bctl + L.next);
+  ovo_vote_row* rows = reinterpret_cast<ovo_vote_row*>(m->bctl + L.rows) + static_cast<size_t>(f) * m->bt_stride;
+  int32_t* mask_ins = m->bt_mask_ins + static_cast<size_t>(f) * m->bt_stride;
+  OVO_CUDA(cudaMemcpyAsync(m->bctl + L.n_matched + 4 * static_cast<size_t>(f), table + m->bt_table_len[f] - 1, sizeof(int32_t), cudaMemcpyDeviceToDevice, stream));
+  if (nm > 0) {
+    ovo::batch_vote_reduce_kernel<<<nm, 128, 0, stream>>>(table, d_next, m->bt_area + static_cast<size_t>(f) * m->bt_stride, rows);
+    OVO_CHECK_LAUNCH();
+    ovo::vote_decide_kernel<<<1, 256, 0, stream>>>(rows, nm, m->bt_track_th[f], mask_ins, d_next);
+    OVO_CHECK_LAUNCH();
+  }
+  return OVO_OK;
+}
+
+// ids of the last keyframe's matches, then ONE read-back of every keyframe's rows and ONE host synchronisation
+int ovo_map_batch_end(ovo_map_t* m, int32_t* ins_ids_dev, int* next_ins_id, ovo_vote_row* votes_host, int votes_stride,
+                      int* n_matched_host, int32_t* mask_ins_out_dev, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  OVO_REQUIRE(m && m->bt_valid, "ovo_map_batch_end: no batch pending");
+  OVO_REQUIRE(next_ins_id && votes_host && n_matched_host && votes_stride > 0, "ovo_map_batch_end: null argument");
+  m->bt_valid = false;
+  const BatchCtl L(m->bt_fcap, m->bt_stride);
+  const int F = m->bt_F;
+  const int64_t N = m->bt_N;
+  for (int f = 0; f < F; ++f) OVO_REQUIRE(m->bt_n_masks[f] <= votes_stride, "ovo_map_batch_end: votes_stride %d < n_masks %d", votes_stride, m->bt_n_masks[f]);
+  if (N > 0 && m->bt_n_masks[F - 1] > 0) {
+    const int blocks = static_cast<int>(std::min<long long>((N + 255) / 256, ovo::num_sms() * 4LL));
+    ovo::batch_vote_scan_kernel<<<blocks, 256, 0, stream>>>(m->seg_dense + static_cast<size_t>(F - 1) * N,
+                                                           m->bt_mask_ins + static_cast<size_t>(F - 1) * m->bt_stride, nullptr, ins_ids_dev, N,
+                                                           reinterpret_cast<const int32_t*>(m->bctl + L.next), 0, nullptr, 0);
+    OVO_CHECK_LAUNCH();
+  }
+  if (mask_ins_out_dev)
+    for (int f = 0; f < F; ++f) {
+      if (m->bt_n_masks[f] < votes_stride)
+        OVO_CUDA(cudaMemsetAsync(mask_ins_out_dev + static_cast<size_t>(f) * votes_stride, 0xff, static_cast<size_t>(votes_stride) * 4, stream));
+      if (m->bt_n_masks[f] > 0)
+        OVO_CUDA(cudaMemcpyAsync(mask_ins_out_dev + static_cast<size_t>(f) * votes_stride, m->bt_mask_ins + static_cast<size_t>(f) * m->bt_stride,
+                                 static_cast<size_t>(m->bt_n_masks[f]) * 4, cudaMemcpyDeviceToDevice, stream));
+    }
+  const size_t bytes = L.rows + static_cast<size_t>(F) * m->bt_stride * sizeof(ovo_vote_row);
+  OVO_CUDA(cudaMemcpyAsync(m->h_bctl, m->bctl, bytes, cudaMemcpyDeviceToHost, stream));
+  OVO_CUDA(cudaStreamSynchronize(stream));   // the one host sync of the batch
+  const int32_t* h_nm = reinterpret_cast<const int32_t*>(m->h_bctl + L.n_matched);
+  const ovo_vote_row* h_rows = reinterpret_cast<const ovo_vote_row*>(m->h_bctl + L.rows);
+  for (int f = 0; f < F; ++f) {
+    n_matched_host[f] = h_nm[f];
+    if (m->bt_n_masks[f] > 0)
+      memcpy(votes_host + static_cast<size_t>(f) * votes_stride, h_rows + static_cast<size_t>(f) * m->bt_stride, m->bt_n_masks[f] * sizeof(ovo_vote_row));
+  }
+  *next_ins_id = *reinterpret_cast<const int32_t*>(m->h_bctl + L.next);
+  return OVO_OK;
+}
+
+int ovo_map_associate_batch(ovo_map_t* m, const float* xyz_dev, int32_t* ins_ids_dev, int64_t N, const ovo_frame* frames, int F,
+                            const int* kf_slots, int* next_ins_id, ovo_vote_row* votes_host, int votes_stride, int* n_matched_host,
+                            int32_t* mask_ins_out_dev, void* stream_) {
+  OVO_REQUIRE(next_ins_id && votes_host && n_matched_host, "ovo_map_associate_batch: null argument");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  double px = 0;
+  for (int f = 0; frames && f < F; ++f) px += static_cast<double>(frames[f].h) * frames[f].w * 8;
+  ovo::ProfScope prof(stream, ovo::PROF_ASSOC, 0.0, static_cast<double>(N) * (12.0 + F * 14.0) + px);
+  OVO_TRY(ovo_map_batch_begin(m, xyz_dev, ins_ids_dev, N, frames, F, kf_slots, *next_ins_id, nullptr, 0, stream_));
+  for (int f = 0; f < F; ++f) {
+    int r = ovo_map_batch_vote(m, f, ins_ids_dev, nullptr, nullptr, stream_);
+    if (r == OVO_OK) r = ovo_map_batch_decide(m, f, stream_);
+    if (r != OVO_OK) { m->bt_valid = false; return r; }
+  }
+  return ovo_map_batch_end(m, ins_ids_dev, next_ins_id, votes_host, votes_stride, n_matched_host, mask_ins_out_dev, stream_);
+}
+
 int ovo_map_get_matches(ovo_map_t* m, int kf_slot, int32_t* pairs_dev, int max_pairs, void* stream) {
   OVO_REQUIRE(m && kf_slot >= 0 && kf_slot < ovo_map::kSlots, "ovo_map_get_matches: bad slot");
   const int n = m->slot_n[kf_slot];
@@ -1125,57 +1617,97 @@ int ovo_map_get_matches(ovo_map_t* m, int kf_slot, int32_t* pairs_dev, int max_p
   return n;
 }
 
-int ovo_map_fuse_dense(ovo_map_t* m, int kf_slot, void* bank_dev, int32_t* counts_dev, int64_t N, int D,
-                       const float* feats_dev, const int32_t* mask_row_dev, int n_masks, void* stream) {
-  OVO_REQUIRE(m && kf_slot >= 0 && kf_slot < ovo_map::kSlots, "ovo_map_fuse_dense: bad slot");
-  OVO_REQUIRE(bank_dev && counts_dev && feats_dev && mask_row_dev, "ovo_map_fuse_dense: null argument");
-  OVO_REQUIRE(D > 0 && D % 8 == 0, "ovo_map_fuse_dense: D must be a multiple of 8");
-  (void)N; (void)n_masks;
-  const int n = m->slot_n[kf_slot];
-  if (n == 0) return OVO_OK;
-  OVO_REQUIRE(D <= 8 * 32 * 8, "ovo_map_fuse_dense: D > 2048 unsupported");
-  const int blocks = std::min(ovo::ceil_div(n, 8), ovo::num_sms() * 8);
-  ovo::ProfScope prof(static_cast<cudaStream_t>(stream), ovo::PROF_FUSE, 0.0, static_cast<double>(n) * (4.0 * D + 12));
-  if (D <= 1024)
-    ovo::fuse_dense_kernel<4><<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        m->slot_list[kf_slot], n, static_cast<__nv_bfloat16*>(bank_dev), counts_dev, D, feats_dev, mask_row_dev);
-  else
-    ovo::fuse_dense_kernel<8><<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        m->slot_list[kf_slot], n, static_cast<__nv_bfloat16*>(bank_dev), counts_dev, D, feats_dev, mask_row_dev);
+// descriptors f32 [R,D] -> the handle's bf16 staging copy (the update rule adds bf16-rounded descriptors)
+static int stage_feats(ovo_map_t* m, const float* feats_dev, int R, int D, cudaStream_t stream) {
+  const size_t n = static_cast<size_t>(R) * D;
+  OVO_TRY(grow(&m->feats_bf16, &m->feats_cap, n));
+  ovo::f32_to_bf16_pad_kernel<<<ovo::ceil_div(static_cast<long long>(n), 256), 256, 0, stream>>>(feats_dev, R, D, m->feats_bf16, R);
   OVO_CHECK_LAUNCH();
   return OVO_OK;
 }
 
-int ovo_map_fuse_dense_batch(ovo_map_t* m, const int* kf_slots_host, int n_slots, void* bank_dev, int32_t* counts_dev,
-                             int64_t N, int D, const float* feats_dev, int n_rows, const int32_t* mask_row_dev, int n_masks,
-                             void* stream_) {
+int ovo_map_fuse_dense(ovo_map_t* m, int kf_slot, void* bank_dev, void* bank_lo_dev, int32_t* counts_dev, int64_t N, int D,
+                       const float* feats_dev, int n_rows, const int32_t* mask_row_dev, int n_masks, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  OVO_REQUIRE(m && kf_slots_host && bank_dev && counts_dev && feats_dev && mask_row_dev, "ovo_map_fuse_dense_batch: null argument");
-  OVO_REQUIRE(n_slots > 0 && n_slots <= 32 && N > 0 && N < (1LL << 31) && D > 0 && D % 8 == 0 && D <= 2048 && n_masks > 0 && n_masks < 32768,
-              "ovo_map_fuse_dense_batch: bad shape (slots %d, N %lld, D %d, masks %d)", n_slots, (long long)N, D, n_masks);
-  long long total = 0;
-  for (int i = 0; i < n_slots; ++i) {
-    OVO_REQUIRE(kf_slots_host[i] >= 0 && kf_slots_host[i] < ovo_map::kSlots, "ovo_map_fuse_dense_batch: bad slot");
-    total += m->slot_n[kf_slots_host[i]];
+  OVO_REQUIRE(m && kf_slot >= 0 && kf_slot < ovo_map::kSlots, "ovo_map_fuse_dense: bad slot");
+  OVO_REQUIRE(bank_dev && bank_lo_dev && counts_dev && feats_dev && mask_row_dev, "ovo_map_fuse_dense: null argument");
+  OVO_REQUIRE(D > 0 && D % 8 == 0 && n_rows > 0, "ovo_map_fuse_dense: D must be a multiple of 8, n_rows > 0");
+  (void)N; (void)n_masks;
+  bool dense_only = false;
+  for (size_t i = 0; i < m->dense_slots.size(); ++i) dense_only = dense_only || (m->dense_slots[i] == kf_slot);
+  if (dense_only) {   // the slot was filled by a batched association: it has a dense row, not a list
+    const int slot1[1] = {kf_slot};
+    return ovo_map_fuse_dense_batch(m, slot1, 1, bank_dev, bank_lo_dev, counts_dev, N, D, feats_dev, n_rows, mask_row_dev, n_masks, stream_);
   }
-  if (total == 0) return OVO_OK;
-  const size_t need = static_cast<size_t>(n_slots) * N;
-  OVO_TRY(grow(&m->seg_dense, &m->seg_dense_cap, need));
-  ovo::ProfScope prof(stream, ovo::PROF_FUSE, 0.0, static_cast<double>(total) * (4.0 * D + 12));
-  OVO_CUDA(cudaMemsetAsync(m->seg_dense, 0xff, need * sizeof(int16_t), stream));   // -1 everywhere
-  const int sms = ovo::num_sms();
-  for (int i = 0; i < n_slots; ++i) {
-    const int s = kf_slots_host[i], n = m->slot_n[s];
-    if (n == 0) continue;
-    ovo::scatter_matches_kernel<<<std::min(ovo::ceil_div(n, 256), sms * 4), 256, 0, stream>>>(m->slot_list[s], n, m->seg_dense + static_cast<size_t>(i) * N);
-    OVO_CHECK_LAUNCH();
-  }
-  (void)n_rows;
-  const int blocks = static_cast<int>(std::min<long long>((N + 255) / 256, sms * 8LL));
+  const int n = m->slot_n[kf_slot];
+  if (n == 0) return OVO_OK;
+  OVO_REQUIRE(D <= 8 * 32 * 8, "ovo_map_fuse_dense: D > 2048 unsupported");
+  const int blocks = std::min(ovo::ceil_div(n, 8), ovo::num_sms() * 8);
+  ovo::ProfScope prof(stream, ovo::PROF_FUSE, 0.0, static_cast<double>(n) * (8.0 * D + 8));
+  OVO_TRY(stage_feats(m, feats_dev, n_rows, D, stream));
+  auto* hi = static_cast<__nv_bfloat16*>(bank_dev);
+  auto* lo = static_cast<__nv_bfloat16*>(bank_lo_dev);
   if (D <= 1024)
-    ovo::fuse_dense_batch_kernel<4><<<blocks, 256, 0, stream>>>(m->seg_dense, n_slots, N, static_cast<__nv_bfloat16*>(bank_dev), counts_dev, D, feats_dev, mask_row_dev, n_masks);
+    ovo::fuse_dense_kernel<4><<<blocks, 256, 0, stream>>>(m->slot_list[kf_slot], n, hi, lo, counts_dev, D, m->feats_bf16, mask_row_dev);
   else
-    ovo::fuse_dense_batch_kernel<8><<<blocks, 256, 0, stream>>>(m->seg_dense, n_slots, N, static_cast<__nv_bfloat16*>(bank_dev), counts_dev, D, feats_dev, mask_row_dev, n_masks);
+    ovo::fuse_dense_kernel<8><<<blocks, 256, 0, stream>>>(m->slot_list[kf_slot], n, hi, lo, counts_dev, D, m->feats_bf16, mask_row_dev);
+  OVO_CHECK_LAUNCH();
+  return OVO_OK;
+}
+
+int ovo_map_fuse_dense_batch(ovo_map_t* m, const int* kf_slots_host, int n_slots, void* bank_dev, void* bank_lo_dev,
+                             int32_t* counts_dev, int64_t N, int D, const float* feats_dev, int n_rows,
+                             const int32_t* mask_row_dev, int n_masks, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  OVO_REQUIRE(m && kf_slots_host && bank_dev && bank_lo_dev && counts_dev && feats_dev && mask_row_dev, "ovo_map_fuse_dense_batch: null argument");
+  OVO_REQUIRE(n_slots > 0 && n_slots <= 64 && N > 0 && N < (1LL << 31) && D > 0 && D % 8 == 0 && D <= 2048 && n_masks > 0 && n_masks < 32768 && n_rows > 0,
+              "ovo_map_fuse_dense_batch: bad shape (slots %d, N %lld, D %d, masks %d)", n_slots, (long long)N, D, n_masks);
+  // the dense rows a batched association left in the handle are used as they are when they cover exactly these slots in order
+  bool direct = m->dense_N == N && m->dense_F >= n_slots && static_cast<int>(m->dense_slots.size()) >= n_slots;
+  int first = -1;
+  if (direct) {
+    for (size_t i = 0; i < m->dense_slots.size() && first < 0; ++i)
+      if (m->dense_slots[i] == kf_slots_host[0]) first = static_cast<int>(i);
+    direct = first >= 0 && first + n_slots <= static_cast<int>(m->dense_slots.size());
+    for (int i = 0; direct && i < n_slots; ++i) direct = m->dense_slots[first + i] == kf_slots_host[i];
+  }
+  const int16_t* rows = nullptr;
+  double touched = 0;
+  if (direct) {
+    rows = m->seg_dense + static_cast<size_t>(first) * N;
+    touched = static_cast<double>(N) * 0.25;   // profiling estimate only
+  } else {
+    long long total = 0;
+    for (int i = 0; i < n_slots; ++i) {
+      OVO_REQUIRE(kf_slots_host[i] >= 0 && kf_slots_host[i] < ovo_map::kSlots, "ovo_map_fuse_dense_batch: bad slot");
+      for (size_t j = 0; j < m->dense_slots.size(); ++j)
+        OVO_REQUIRE(m->dense_slots[j] != kf_slots_host[i], "ovo_map_fuse_dense_batch: slot %d was filled by a batched association; pass that batch's slots in its order", kf_slots_host[i]);
+      total += m->slot_n[kf_slots_host[i]];
+    }
+    if (total == 0) return OVO_OK;
+    const size_t need = static_cast<size_t>(n_slots) * N;
+    OVO_TRY(grow(&m->seg_dense, &m->seg_dense_cap, need));
+    m->dense_slots.clear(); m->dense_N = 0; m->dense_F = 0;
+    OVO_CUDA(cudaMemsetAsync(m->seg_dense, 0xff, need * sizeof(int16_t), stream));   // -1 everywhere
+    const int sms = ovo::num_sms();
+    for (int i = 0; i < n_slots; ++i) {
+      const int sl = kf_slots_host[i], n = m->slot_n[sl];
+      if (n == 0) continue;
+      ovo::scatter_matches_kernel<<<std::min(ovo::ceil_div(n, 256), sms * 4), 256, 0, stream>>>(m->slot_list[sl], n, m->seg_dense + static_cast<size_t>(i) * N);
+      OVO_CHECK_LAUNCH();
+    }
+    rows = m->seg_dense;
+    touched = static_cast<double>(total);
+  }
+  ovo::ProfScope prof(stream, ovo::PROF_FUSE, 0.0, touched * (8.0 * D + 8));
+  OVO_TRY(stage_feats(m, feats_dev, n_rows, D, stream));
+  const int blocks = static_cast<int>(std::min<long long>((N + 255) / 256, ovo::num_sms() * 8LL));
+  auto* hi = static_cast<__nv_bfloat16*>(bank_dev);
+  auto* lo = static_cast<__nv_bfloat16*>(bank_lo_dev);
+  if (D <= 1024)
+    ovo::fuse_dense_batch_kernel<4><<<blocks, 256, 0, stream>>>(rows, n_slots, N, hi, lo, counts_dev, D, m->feats_bf16, mask_row_dev, n_masks);
+  else
+    ovo::fuse_dense_batch_kernel<8><<<blocks, 256, 0, stream>>>(rows, n_slots, N, hi, lo, counts_dev, D, m->feats_bf16, mask_row_dev, n_masks);
   OVO_CHECK_LAUNCH();
   return OVO_OK;
 }

@@ -188,18 +188,18 @@ class RegionEncoder:
         n = pixels.shape[0]
         pixels = pixels.to(self.device, torch.float32).contiguous()
         out = torch.empty(n, self.cfg.seq, self.cfg.width, device=self.device, dtype=torch.float32)
-        check(self.lib.ovo_encoder_load_pixels(self.handle, ptr(pixels), n, stream_ptr()), "load_pixels")
-        check(self.lib.ovo_encoder_forward(self.handle, n, n_layers, int(ln_post), ptr(out), stream_ptr()), "forward")
+        check(self.lib.ovo_encoder_load_pixels(self.handle, ptr(pixels), n, stream_ptr(self.device)), "load_pixels")
+        check(self.lib.ovo_encoder_forward(self.handle, n, n_layers, int(ln_post), ptr(out), stream_ptr(self.device)), "forward")
         return out
 
     def forward_features(self, rgb_u8: torch.Tensor):
         """E1+E2: rgb uint8 [F,H,W,3] (device) -> tokens [F*n_img, seq, width]."""
         F_, H, W, _ = rgb_u8.shape
         per = C.c_int(0)
-        check(self.lib.ovo_encoder_preprocess(self.handle, ptr(rgb_u8), F_, H, W, C.byref(per), stream_ptr()), "preprocess")
+        check(self.lib.ovo_encoder_preprocess(self.handle, ptr(rgb_u8), F_, H, W, C.byref(per), stream_ptr(self.device)), "preprocess")
         n = F_ * per.value
         out = torch.empty(n, self.cfg.seq, self.cfg.width, device=self.device, dtype=torch.float32)
-        check(self.lib.ovo_encoder_forward(self.handle, n, -1, 1, ptr(out), stream_ptr()), "forward")
+        check(self.lib.ovo_encoder_forward(self.handle, n, -1, 1, ptr(out), stream_ptr(self.device)), "forward")
         return out
 
     def encode_regions(self, rgb_u8: torch.Tensor, masks: torch.Tensor, masks_per_frame=None) -> torch.Tensor:
@@ -217,7 +217,7 @@ class RegionEncoder:
         if M == 0:
             return out
         arr = (C.c_int * F_)(*counts)
-        check(self.lib.ovo_encode_regions(self.handle, ptr(rgb_u8), F_, H, W, ptr(m8), arr, ptr(out), stream_ptr()),
+        check(self.lib.ovo_encode_regions(self.handle, ptr(rgb_u8), F_, H, W, ptr(m8), arr, ptr(out), stream_ptr(self.device)),
               "ovo_encode_regions")
         return out
 
@@ -253,7 +253,7 @@ class RegionEncoder:
         """Test tap of pe.CLIP.encode_image: normalised pixels [n,3,S,S] -> [n, output_dim] (not normalised)."""
         pixels = pixels.to(self.device, torch.float32).contiguous()
         out = torch.empty(pixels.shape[0], self.cfg.output_dim, device=self.device, dtype=torch.float32)
-        check(self.lib.ovo_encode_images(self.handle, ptr(pixels), pixels.shape[0], ptr(out), stream_ptr()), "ovo_encode_images")
+        check(self.lib.ovo_encode_images(self.handle, ptr(pixels), pixels.shape[0], ptr(out), stream_ptr(self.device)), "ovo_encode_images")
         return out
 
     def encode_crops(self, rgb_u8: torch.Tensor, masks: torch.Tensor, embed_type: str, mask_res: int = 384,
@@ -276,7 +276,7 @@ class RegionEncoder:
         if return_crops:
             crops = torch.empty((M if vanilla else 2 * M), mask_res, mask_res, 3, device=self.device, dtype=torch.uint8)
         check(self.lib.ovo_encode_crops(self.handle, ptr(rgb_u8), H, W, ptr(m8), M, C.byref(prm), ptr(out), ptr(crops),
-                                        stream_ptr()), "ovo_encode_crops")
+                                        stream_ptr(self.device)), "ovo_encode_crops")
         return (out, crops) if return_crops else out
 
     def encode_text(self, tokens: torch.Tensor) -> torch.Tensor:
@@ -285,7 +285,7 @@ class RegionEncoder:
             raise RuntimeError("encoder was built without a text tower")
         tok = tokens.to(self.device, torch.int32).contiguous()
         out = torch.empty(tok.shape[0], self.cfg.text_output_dim, device=self.device, dtype=torch.float32)
-        check(self.lib.ovo_encode_text(self.handle, ptr(tok), tok.shape[0], ptr(out), stream_ptr()), "ovo_encode_text")
+        check(self.lib.ovo_encode_text(self.handle, ptr(tok), tok.shape[0], ptr(out), stream_ptr(self.device)), "ovo_encode_text")
         return out
 
 
@@ -295,5 +295,5 @@ def gemm_bf16(A: torch.Tensor, B: torch.Tensor, bias: torch.Tensor | None = None
     N = B.shape[0]
     out = torch.empty(M, N, device=A.device, dtype=torch.float32)
     check(_lib.lib().ovo_gemm_bf16(ptr(A), A.stride(0), ptr(B), B.stride(0), M, N, K, ptr(bias), ptr(out), N, force_bn,
-                                   stream_ptr()), "ovo_gemm_bf16")
+                                   stream_ptr(A.device)), "ovo_gemm_bf16")
     return out

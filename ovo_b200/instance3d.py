@@ -20,6 +20,19 @@ class Instance3D:
     n_top_kf: int = 0
     mv_fusion: str = "l1_medoid"          # reference default (instance3d.py:51)
 
+    @property
+    def clip_feature_kf(self):
+        """Index of the view a medoid fusion picked (instance3d.py:185-187).  The fusion kernel leaves it on the device; it is
+        read back on first use (export) instead of blocking the host behind the encoder at every keyframe."""
+        v = self._clip_feature_kf
+        if isinstance(v, tuple):           # (device tensor of one launch's picks, position)
+            v = self._clip_feature_kf = int(v[0][v[1]].item())
+        return v
+
+    @clip_feature_kf.setter
+    def clip_feature_kf(self, v) -> None:
+        self._clip_feature_kf = v
+
     def __init__(self, id: int, kf_id: int | None = None, points_ids: List[int] | None = None, mask_area: int = 0):
         self.id = id
         self.clip_feature = None           # torch view of the bank row: [D] (one view) or [1,D] (fused), instance3d.py:184-187

@@ -24,6 +24,7 @@ class SemanticMap:
         with torch.cuda.device(self.device):
             check(self.lib.ovo_map_create(C.byref(h)), "ovo_map_create")
         self.handle = h
+        self.n_slots = 64          # per-keyframe match-list slots of the handle (ovo_map::kSlots)
 
     def __del__(self):
         try:
@@ -43,7 +44,7 @@ class SemanticMap:
         """geometry_utils.depth_filter (geometry_utils.py:92-96)."""
         depth = depth.to(self.device, torch.float32).contiguous()
         out = torch.empty_like(depth)
-        check(self.lib.ovo_depth_filter(ptr(depth), depth.shape[0], depth.shape[1], ptr(out), stream_ptr()), "ovo_depth_filter")
+        check(self.lib.ovo_depth_filter(ptr(depth), depth.shape[0], depth.shape[1], ptr(out), stream_ptr(self.device)), "ovo_depth_filter")
         return out
 
     def associate(self, xyz: torch.Tensor, ins_ids: torch.Tensor, depth: torch.Tensor, seg_map: torch.Tensor,
@@ -73,7 +74,7 @@ class SemanticMap:
         rows = (VoteRow * max(n_masks, 1))()
         nxt, nm = C.c_int(next_ins_id), C.c_int(0)
         check(self.lib.ovo_map_associate(self.handle, ptr(xyz), ptr(ins_ids), xyz.shape[0], C.byref(f), C.byref(nxt), rows,
-                                         C.byref(nm), kf_slot, stream_ptr()), "ovo_map_associate")
+                                         C.byref(nm), kf_slot, stream_ptr(self.device)), "ovo_map_associate")
         arr = np.frombuffer(rows, dtype=np.int32).reshape(-1, 8)[:n_masks]
         votes = {k: arr[:, i].copy() for i, k in enumerate(VOTE_FIELDS)}
         return votes, nm.value, nxt.value
@@ -102,7 +103,7 @@ class SemanticMap:
         table = torch.empty(max(n_masks, 1) * (n_ins + 1) + 1, device=self.device, dtype=torch.int32)
         self._pending = (ins_ids, n_masks)
         check(self.lib.ovo_map_vote(self.handle, ptr(xyz), ptr(ins_ids), xyz.shape[0], C.byref(f), n_ins, ptr(table), kf_slot,
-                                    stream_ptr()), "ovo_map_vote")
+                                    stream_ptr(self.device)), "ovo_map_vote")
         return table
 
     def apply(self, table: torch.Tensor, next_ins_id: int):
@@ -110,33 +111,116 @@ class SemanticMap:
         ins_ids, n_masks = self._pending
         rows = (VoteRow * max(n_masks, 1))()
         nxt, nm = C.c_int(next_ins_id), C.c_int(0)
-        check(self.lib.ovo_map_apply(self.handle, ptr(table), ptr(ins_ids), C.byref(nxt), rows, C.byref(nm), stream_ptr()), "ovo_map_apply")
+        check(self.lib.ovo_map_apply(self.handle, ptr(table), ptr(ins_ids), C.byref(nxt), rows, C.byref(nm), stream_ptr(self.device)), "ovo_map_apply")
         arr = np.frombuffer(rows, dtype=np.int32).reshape(-1, 8)[:n_masks]
         return {k: arr[:, i].copy() for i, k in enumerate(VOTE_FIELDS)}, nm.value, nxt.value
 
     def matches(self, kf_slot: int, n_max: int) -> torch.Tensor:
         """(point index, mask index) pairs of a keyframe slot, [n,2] i32 on the device (unordered)."""
         buf = torch.empty(max(n_max, 1), 2, device=self.device, dtype=torch.int32)
-        n = check(self.lib.ovo_map_get_matches(self.handle, kf_slot, ptr(buf), n_max, stream_ptr()), "ovo_map_get_matches")
+        n = check(self.lib.ovo_map_get_matches(self.handle, kf_slot, ptr(buf), n_max, stream_ptr(self.device)), "ovo_map_get_matches")
         return buf[:n]
 
-    def fuse_dense(self, kf_slot: int, bank: torch.Tensor, counts: torch.Tensor, feats: torch.Tensor, mask_row: torch.Tensor):
-        """Per-point running mean: bank [N,D] bf16, counts [N] i32, feats [R,D] f32, mask_row [n_masks] i32."""
-        assert bank.dtype == torch.bfloat16 and counts.dtype == torch.int32 and feats.dtype == torch.float32
-        assert mask_row.dtype == torch.int32 and bank.is_contiguous() and feats.is_contiguous()
-        check(self.lib.ovo_map_fuse_dense(self.handle, kf_slot, ptr(bank), ptr(counts), bank.shape[0], bank.shape[1],
-                                          ptr(feats), ptr(mask_row), mask_row.shape[0], stream_ptr()), "ovo_map_fuse_dense")
+    # ---- several keyframes in one pass over the map (ovo_map_associate_batch)
+    def _frames(self, depths, seg_maps, c2ws, K, n_masks, match_th, track_th, depth_filter, rgb_depth_ratio, w2cs):
+        F = len(depths)
+        arr = (Frame * F)()
+        for i in range(F):
+            assert depths[i].is_cuda and seg_maps[i].is_cuda and depths[i].dtype == torch.float32 and seg_maps[i].dtype == torch.int32
+            assert depths[i].is_contiguous() and seg_maps[i].is_contiguous()
+            nm = n_masks[i] if not isinstance(n_masks, int) else n_masks
+            arr[i] = self._frame(depths[i], seg_maps[i], c2ws[i], K, match_th, track_th, depth_filter, rgb_depth_ratio, int(nm),
+                                 None if w2cs is None else w2cs[i])
+        return arr
 
-    def fuse_dense_batch(self, kf_slots, bank: torch.Tensor, counts: torch.Tensor, feats: torch.Tensor, mask_row: torch.Tensor):
-        """Several keyframes in one pass over the bank (bit-identical to consecutive fuse_dense calls in that order).
+    def associate_batch(self, xyz: torch.Tensor, ins_ids: torch.Tensor, depths, seg_maps, c2ws, K, next_ins_id: int, n_masks,
+                        match_th: float = 0.05, track_th: int = 100, depth_filter: bool = True, rgb_depth_ratio=(), kf_slots=None,
+                        w2cs=None, mask_ins_out: torch.Tensor | None = None):
+        """F keyframes against the map in one pass over xyz, id decisions on the device, ONE host synchronisation; the same
+        results as F consecutive `associate` calls.  depths / seg_maps / c2ws: lists of F; n_masks: int or list.
+        Returns (list of F votes dicts, list of F n_matched, next_ins_id); `mask_ins_out` i32 [F, stride] (optional, device)
+        receives the instance id of every mask."""
+        assert xyz.is_cuda and ins_ids.is_cuda and xyz.dtype == torch.float32 and ins_ids.dtype == torch.int32
+        assert xyz.is_contiguous() and ins_ids.is_contiguous()
+        F = len(depths)
+        frames = self._frames(depths, seg_maps, c2ws, K, n_masks, match_th, track_th, depth_filter, rgb_depth_ratio, w2cs)
+        nms = [int(frames[i].n_masks) for i in range(F)]
+        stride = max(max(nms), 1) if mask_ins_out is None else int(mask_ins_out.shape[1])
+        assert mask_ins_out is None or (mask_ins_out.dtype == torch.int32 and mask_ins_out.shape[0] >= F and mask_ins_out.is_contiguous() and stride >= max(nms))
+        rows = (VoteRow * (F * stride))()
+        nxt, nm = C.c_int(next_ins_id), (C.c_int * F)()
+        slots = None if kf_slots is None else (C.c_int * F)(*[int(x) for x in kf_slots])
+        check(self.lib.ovo_map_associate_batch(self.handle, ptr(xyz), ptr(ins_ids), xyz.shape[0], frames, F, slots, C.byref(nxt), rows,
+                                               stride, nm, ptr(mask_ins_out), stream_ptr(self.device)), "ovo_map_associate_batch")
+        arr = np.frombuffer(rows, dtype=np.int32).reshape(F, stride, 8)
+        votes = [{k: arr[f, :nms[f], i].copy() for i, k in enumerate(VOTE_FIELDS)} for f in range(F)]
+        return votes, [int(x) for x in nm], nxt.value
+
+    # the same batch in stages, for a map sharded over ranks: begin -> per keyframe (vote -> all-reduce of the table -> decide) -> end
+    def batch_begin(self, xyz, ins_ids, depths, seg_maps, c2ws, K, next_ins_id: int, n_masks, tables: torch.Tensor, match_th=0.05,
+                    track_th=100, depth_filter=True, rgb_depth_ratio=(), kf_slots=None, w2cs=None):
+        F = len(depths)
+        frames = self._frames(depths, seg_maps, c2ws, K, n_masks, match_th, track_th, depth_filter, rgb_depth_ratio, w2cs)
+        assert tables.is_cuda and tables.dtype == torch.int32 and tables.is_contiguous()
+        slots = None if kf_slots is None else (C.c_int * F)(*[int(x) for x in kf_slots])
+        check(self.lib.ovo_map_batch_begin(self.handle, ptr(xyz), ptr(ins_ids), xyz.shape[0], frames, F, slots, int(next_ins_id),
+                                           ptr(tables), tables.numel(), stream_ptr(self.device)), "ovo_map_batch_begin")
+        self._batch = (ins_ids, [int(frames[i].n_masks) for i in range(F)], tables)
+
+    def batch_vote(self, f: int) -> torch.Tensor:
+        """Votes of keyframe f on this rank's points -> the view of `tables` that holds its table (sum it over the ranks in place)."""
+        ins_ids, _, tables = self._batch
+        p, n = C.c_void_p(), C.c_int(0)
+        check(self.lib.ovo_map_batch_vote(self.handle, f, ptr(ins_ids), C.byref(p), C.byref(n), stream_ptr(self.device)), "ovo_map_batch_vote")
+        off = (p.value - tables.data_ptr()) // 4
+        return tables[off: off + n.value]
+
+    def batch_decide(self, f: int) -> None:
+        check(self.lib.ovo_map_batch_decide(self.handle, f, stream_ptr(self.device)), "ovo_map_batch_decide")
+
+    def batch_end(self, mask_ins_out: torch.Tensor | None = None):
+        ins_ids, nms, _ = self._batch
+        F = len(nms)
+        stride = max(max(nms), 1) if mask_ins_out is None else int(mask_ins_out.shape[1])
+        rows = (VoteRow * (F * stride))()
+        nxt, nm = C.c_int(0), (C.c_int * F)()
+        check(self.lib.ovo_map_batch_end(self.handle, ptr(ins_ids), C.byref(nxt), rows, stride, nm, ptr(mask_ins_out),
+                                         stream_ptr(self.device)), "ovo_map_batch_end")
+        arr = np.frombuffer(rows, dtype=np.int32).reshape(F, stride, 8)
+        votes = [{k: arr[f, :nms[f], i].copy() for i, k in enumerate(VOTE_FIELDS)} for f in range(F)]
+        return votes, [int(x) for x in nm], nxt.value
+
+    @staticmethod
+    def batch_tables_size(next_ins_id: int, n_masks) -> int:
+        """ints `tables` needs for a batch whose keyframes have n_masks[f] masks (ovo_map_batch_begin)."""
+        n, bound = 0, int(next_ins_id)
+        for nm in n_masks:
+            n += (max(int(nm), 1) * (bound + 1) + 1 + 3) // 4 * 4
+            bound += int(nm)
+        return n
+
+    def fuse_dense(self, kf_slot: int, bank: torch.Tensor, bank_lo: torch.Tensor, counts: torch.Tensor, feats: torch.Tensor,
+                   mask_row: torch.Tensor):
+        """Per-point running mean in the two-plane bank: bank / bank_lo [N,D] bf16 (mean = bank + bank_lo; `bank` alone is the
+        query operand), counts [N] i32, feats [R,D] f32, mask_row [n_masks] i32."""
+        assert bank.dtype == torch.bfloat16 and bank_lo.dtype == torch.bfloat16 and counts.dtype == torch.int32 and feats.dtype == torch.float32
+        assert mask_row.dtype == torch.int32 and bank.is_contiguous() and bank_lo.is_contiguous() and feats.is_contiguous()
+        assert bank_lo.shape == bank.shape and feats.shape[1] == bank.shape[1]
+        check(self.lib.ovo_map_fuse_dense(self.handle, kf_slot, ptr(bank), ptr(bank_lo), ptr(counts), bank.shape[0], bank.shape[1],
+                                          ptr(feats), feats.shape[0], ptr(mask_row), mask_row.shape[0], stream_ptr(self.device)),
+              "ovo_map_fuse_dense")
+
+    def fuse_dense_batch(self, kf_slots, bank: torch.Tensor, bank_lo: torch.Tensor, counts: torch.Tensor, feats: torch.Tensor,
+                         mask_row: torch.Tensor):
+        """Several keyframes in one pass over the bank (a point's descriptors are summed in f32, then ONE mean update).
         feats [R,D] f32 = descriptors of all keyframes, mask_row [len(kf_slots), n_masks] i32 -> row of feats or -1."""
-        assert bank.dtype == torch.bfloat16 and counts.dtype == torch.int32 and feats.dtype == torch.float32
+        assert bank.dtype == torch.bfloat16 and bank_lo.dtype == torch.bfloat16 and counts.dtype == torch.int32 and feats.dtype == torch.float32
         assert mask_row.dtype == torch.int32 and mask_row.dim() == 2 and mask_row.shape[0] == len(kf_slots) and mask_row.is_contiguous()
         arr = (C.c_int * len(kf_slots))(*[int(s) for s in kf_slots])
-        assert feats.is_contiguous() and feats.shape[1] == bank.shape[1]
-        check(self.lib.ovo_map_fuse_dense_batch(self.handle, arr, len(kf_slots), ptr(bank), ptr(counts), bank.shape[0], bank.shape[1],
-                                                ptr(feats), feats.shape[0], ptr(mask_row), mask_row.shape[1], stream_ptr()),
-              "ovo_map_fuse_dense_batch")
+        assert feats.is_contiguous() and feats.shape[1] == bank.shape[1] and bank_lo.shape == bank.shape and bank.is_contiguous() and bank_lo.is_contiguous()
+        check(self.lib.ovo_map_fuse_dense_batch(self.handle, arr, len(kf_slots), ptr(bank), ptr(bank_lo), ptr(counts), bank.shape[0],
+                                                bank.shape[1], ptr(feats), feats.shape[0], ptr(mask_row), mask_row.shape[1],
+                                                stream_ptr(self.device)), "ovo_map_fuse_dense_batch")
 
     def query_dense(self, bank: torch.Tensor, text: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
         """clip_cosine_similarity over the dense bank: [N,D] bf16 x [Q,D] f32 -> [N,Q] f32."""
@@ -146,7 +230,7 @@ class SemanticMap:
         Q = text.shape[0]
         if out is None:
             out = torch.empty(N, Q, device=self.device, dtype=torch.float32)
-        check(self.lib.ovo_query_dense(self.handle, ptr(bank), N, D, ptr(text), Q, ptr(out), stream_ptr()), "ovo_query_dense")
+        check(self.lib.ovo_query_dense(self.handle, ptr(bank), N, D, ptr(text), Q, ptr(out), stream_ptr(self.device)), "ovo_query_dense")
         return out
 
     def query_instances(self, bank: torch.Tensor, text: torch.Tensor, rows: torch.Tensor | None = None) -> torch.Tensor:
@@ -156,7 +240,7 @@ class SemanticMap:
         n = bank.shape[0] if rows is None else rows.shape[0]
         out = torch.empty(n, text.shape[0], device=self.device, dtype=torch.float32)
         check(self.lib.ovo_query_instances(ptr(bank), ptr(rows), n, bank.shape[1], ptr(text), text.shape[0], ptr(out),
-                                           stream_ptr()), "ovo_query_instances")
+                                           stream_ptr(self.device)), "ovo_query_instances")
         return out
 
     def merge_masks(self, masks: torch.Tensor, group: torch.Tensor, n_out: int):
@@ -165,7 +249,7 @@ class SemanticMap:
         M, H, W = masks.shape
         out = torch.empty(n_out, H, W, device=self.device, dtype=torch.uint8)
         areas = torch.empty(n_out, device=self.device, dtype=torch.int32)
-        check(self.lib.ovo_merge_masks(ptr(masks), M, H, W, ptr(group), n_out, ptr(out), ptr(areas), stream_ptr()), "ovo_merge_masks")
+        check(self.lib.ovo_merge_masks(ptr(masks), M, H, W, ptr(group), n_out, ptr(out), ptr(areas), stream_ptr(self.device)), "ovo_merge_masks")
         return out, areas
 
     def fuse_views(self, store: torch.Tensor, idx: torch.Tensor, off: torch.Tensor, mode: int, bank: torch.Tensor,
@@ -173,7 +257,7 @@ class SemanticMap:
         """Instance3D.update_clip batched: see ovo_fuse_views in include/ovo_b200.h."""
         assert store.dtype == torch.float32 and bank.dtype == torch.float32 and idx.dtype == torch.int32
         check(self.lib.ovo_fuse_views(ptr(store), store.shape[1], ptr(idx), ptr(off), out_rows.shape[0], mode, ptr(bank),
-                                      ptr(out_rows), ptr(chosen), stream_ptr()), "ovo_fuse_views")
+                                      ptr(out_rows), ptr(chosen), stream_ptr(self.device)), "ovo_fuse_views")
 
     def mask_nms(self, masks: torch.Tensor, scores: torch.Tensor, iou_thr=0.8, score_thr=0.7, inner_thr=0.5) -> torch.Tensor:
         """masks_update/mask_nms/filter (segment_utils.py:173-259): masks [M,H,W] bool/uint8, scores [M] f32 ->
@@ -182,7 +266,7 @@ class SemanticMap:
         sc = scores.to(self.device, torch.float32).contiguous()
         keep = torch.empty(m8.shape[0], device=self.device, dtype=torch.uint8)
         check(self.lib.ovo_mask_nms(ptr(m8), ptr(sc), m8.shape[0], m8.shape[1], m8.shape[2], float(iou_thr), float(score_thr),
-                                    float(inner_thr), ptr(keep), stream_ptr()), "ovo_mask_nms")
+                                    float(inner_thr), ptr(keep), stream_ptr(self.device)), "ovo_mask_nms")
         return keep.bool()
 
     def mask2segmap(self, masks: torch.Tensor, stability: torch.Tensor):
@@ -193,7 +277,7 @@ class SemanticMap:
         seg = torch.empty(H, W, device=self.device, dtype=torch.int32)
         maps = torch.empty_like(m8)
         order = torch.empty(M, device=self.device, dtype=torch.int32)
-        check(self.lib.ovo_mask2segmap(ptr(m8), ptr(st), M, H, W, ptr(seg), ptr(maps), ptr(order), stream_ptr()), "ovo_mask2segmap")
+        check(self.lib.ovo_mask2segmap(ptr(m8), ptr(st), M, H, W, ptr(seg), ptr(maps), ptr(order), stream_ptr(self.device)), "ovo_mask2segmap")
         return seg, maps.bool(), order
 
     def classify(self, sim: torch.Tensor, th: float = 0.0):
@@ -201,7 +285,7 @@ class SemanticMap:
         sim = sim.contiguous()
         cls = torch.empty(sim.shape[0], device=self.device, dtype=torch.int32)
         conf = torch.empty(sim.shape[0], device=self.device, dtype=torch.float32)
-        check(self.lib.ovo_classify(ptr(sim), sim.shape[0], sim.shape[1], float(th), ptr(cls), ptr(conf), stream_ptr()), "ovo_classify")
+        check(self.lib.ovo_classify(ptr(sim), sim.shape[0], sim.shape[1], float(th), ptr(cls), ptr(conf), stream_ptr(self.device)), "ovo_classify")
         return cls, conf
 
     def bank_add_views(self, bank: torch.Tensor, store: torch.Tensor, quads: torch.Tensor, idx: torch.Tensor):
@@ -209,7 +293,7 @@ class SemanticMap:
         views per instance (avg_pooling) without re-reading the views already fused."""
         assert bank.is_cuda and store.is_cuda and quads.is_cuda and idx.is_cuda
         assert quads.dtype == torch.int32 and idx.dtype == torch.int32 and quads.is_contiguous() and idx.is_contiguous()
-        check(self.lib.ovo_bank_add_views(ptr(bank), bank.shape[1], ptr(store), ptr(quads), ptr(idx), quads.shape[0], stream_ptr()),
+        check(self.lib.ovo_bank_add_views(ptr(bank), bank.shape[1], ptr(store), ptr(quads), ptr(idx), quads.shape[0], stream_ptr(self.device)),
               "ovo_bank_add_views")
 
     def bank_update_mean(self, bank: torch.Tensor, counts: torch.Tensor, feats: torch.Tensor, rows: torch.Tensor):
@@ -217,4 +301,4 @@ class SemanticMap:
         assert bank.dtype == torch.float32 and counts.dtype == torch.int32 and rows.dtype == torch.int32
         feats = feats.to(self.device, torch.float32).contiguous()
         check(self.lib.ovo_bank_update_mean(ptr(bank), ptr(counts), bank.shape[1], ptr(feats), ptr(rows), rows.shape[0],
-                                            stream_ptr()), "ovo_bank_update_mean")
+                                            stream_ptr(self.device)), "ovo_bank_update_mean")

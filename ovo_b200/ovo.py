@@ -79,7 +79,8 @@ class OVO:
         self._rows_cache = None
         # dense per-point mode
         self.dense = bool(config.get("dense_map", False))
-        self._dense_bank = None
+        self._dense_bank = None        # [N, D] bf16: the running mean rounded to bf16 (the operand of the dense query)
+        self._dense_bank_lo = None     # [N, D] bf16: mean - _dense_bank (the bits the first plane cannot hold)
         self._dense_counts = None
         if config.get("verbose", True):
             print('Semantic config')
@@ -124,6 +125,10 @@ class OVO:
         if len(seg_maps) == 0:
             print(f"No mask segmented in {frame_id}!")
             return None
+        if self.dense and len(self.keyframes_queue) >= self.semmap.n_slots - 1:
+            # the match list of a queued keyframe lives in one of the map handle's slots (kf_id % n_slots) until its dense fusion ran
+            raise RuntimeError(f"ovo_b200: {len(self.keyframes_queue)} keyframes are queued for descriptors; dense_map keeps at most "
+                               f"{self.semmap.n_slots - 1} (lower kf_queue_delay or call compute_semantic_info more often)")
         last_id = self.next_ins_id
         matched_ins_ids, binary_maps, n_matched_points, updated, extra = self._match_and_track_instances(
             frame_data[1:], map_data, c2w, seg_maps, binary_maps)
@@ -155,7 +160,7 @@ class OVO:
         updated = points_ins_ids.to(dev, torch.int32).reshape(-1).clone()        # ovo.py:228
         c2w_np = c2w.detach().float().cpu().numpy() if torch.is_tensor(c2w) else np.asarray(c2w, np.float32)
         K_np = self.cam_intrinsics.detach().float().cpu().numpy()
-        slot = kf_id % 64
+        slot = kf_id % self.semmap.n_slots
         votes, n_matched, self.next_ins_id = self.semmap.associate(
             xyz, updated, depth_d, seg_d, c2w_np, K_np, self.next_ins_id, match_th=self.config["match_distance_th"],
             track_th=int(self.config["track_th"]), depth_filter=self.config.get("depth_filter", False),
@@ -198,15 +203,16 @@ class OVO:
         """ids of the points that were unassigned before this keyframe, grouped by the mask they matched
         (what ovo.py:261 builds with a per-mask `.cpu().tolist()`): one D2H of the match list instead."""
         n = int(votes["n_matched"].sum())
-        pairs = self.semmap.matches(slot, n).cpu().numpy()
-        ids = points_ids.reshape(-1).cpu().numpy()
-        before = ins_before.reshape(-1).cpu().numpy()
-        out = [[] for _ in range(len(votes["ins_id"]))]
-        order = np.argsort(pairs[:, 0], kind="stable")            # point order, as boolean indexing yields it
-        for p, m in pairs[order]:
-            if before[p] == -1:
-                out[m].append(int(ids[p]))
-        return out
+        n_masks = len(votes["ins_id"])
+        pairs = self.semmap.matches(slot, n)
+        before = ins_before.reshape(-1).to(self._dev)
+        fresh = pairs[before[pairs[:, 0].long()] == -1]                      # only points without an id count (ovo.py:261,274)
+        ids = points_ids.reshape(-1).to(self._dev)[fresh[:, 0].long()].cpu().numpy()
+        fresh = fresh.cpu().numpy()
+        order = np.lexsort((fresh[:, 0], fresh[:, 1]))                        # by mask, then point order (as boolean indexing yields it)
+        bounds = np.searchsorted(fresh[order, 1], np.arange(n_masks + 1))
+        ids = ids[order]
+        return [ids[bounds[m]: bounds[m + 1]].tolist() for m in range(n_masks)]
 
     def _fuse_masks_with_same_ins_id(self, binary_maps, matched_ins_info, kf_id, n_masks):
         """ovo.py:284-324.  Masks voted to the same instance are OR-ed (one kernel for all groups); returns
@@ -289,8 +295,9 @@ class OVO:
 
     def _compute_groups(self, groups) -> None:
         for group in groups:
-            for it in group:
+            for it in group:                # allocated on the caller's stream, read (and released) under the descriptor stream
                 it[1].record_stream(self._enc_stream)
+                it[5].record_stream(self._enc_stream)
             rows_per_kf = self._extract_clip_batch([it[2] for it in group], [it[1] for it in group])
             if self.dense and len(group) > 1:
                 # all keyframes of the batch in ONE pass over the dense bank (bit-identical to one pass per keyframe)
@@ -300,12 +307,12 @@ class OVO:
                 for k, (it, rows) in enumerate(zip(group, rows_per_kf)):
                     loc = it[5]
                     mr[k, : loc.shape[0]] = torch.where(loc >= 0, loc + (rows[0] - base), loc)
-                self.semmap.fuse_dense_batch([it[4] for it in group], self._dense_bank, self._dense_counts,
+                self.semmap.fuse_dense_batch([it[4] for it in group], self._dense_bank, self._dense_bank_lo, self._dense_counts,
                                              self._store[base: base + total], mr)
             for (ids, _, _, kf_id, slot, mask_row), rows in zip(group, rows_per_kf):
                 self._update_matched_objects_clip(rows, ids, kf_id)
                 if self.dense and len(group) == 1:
-                    self.semmap.fuse_dense(slot, self._dense_bank, self._dense_counts,
+                    self.semmap.fuse_dense(slot, self._dense_bank, self._dense_bank_lo, self._dense_counts,
                                            self._store[rows[0]: rows[0] + len(ids)], mask_row.contiguous())
                 if self.config.get("log", False):
                     frame_id = self.keyframes["frame_id"][kf_id]
@@ -412,20 +419,20 @@ class OVO:
         self.semmap.fuse_views(self._store, torch.tensor(idx, dtype=torch.int32, device=dev),
                                torch.tensor(off, dtype=torch.int32, device=dev), mode, self._bank,
                                torch.tensor(out_rows, dtype=torch.int32, device=dev), chosen)
-        chosen_h = chosen.cpu().tolist() if chosen is not None else None
         for j, (obj, views) in enumerate(work):
             row = self._bank[obj.bank_row]
             if len(views) == 1:                                  # instance3d.py:184-185
                 obj.clip_feature, obj.clip_feature_kf = row, 0
             else:                                                # instance3d.py:186-187: fused shape is [1, D]
                 obj.clip_feature = row[None]
-                obj.clip_feature_kf = None if chosen_h is None else chosen_h[j]
+                obj.clip_feature_kf = None if chosen is None else (chosen, j)      # read back lazily (Instance3D.clip_feature_kf)
 
     # ------------------------------------------------------------------------------------------ tables
     def _grow_store(self, need: int) -> None:
         if need > self._store.shape[0]:
             new = torch.zeros(max(need, 2 * self._store.shape[0]), self._store.shape[1], device=self._dev)
             new[: self._store_n] = self._store[: self._store_n]
+            self._store.record_stream(torch.cuda.current_stream(self._dev))   # the old table may belong to another stream's pool
             self._store = new
 
     def _alloc_bank_row(self) -> int:
@@ -445,14 +452,21 @@ class OVO:
         if self._dense_bank is None:
             D = self.clip_generator.clip_dim
             self._dense_bank = torch.zeros(max(cap, n_points), D, device=self._dev, dtype=torch.bfloat16)
+            self._dense_bank_lo = torch.zeros(max(cap, n_points), D, device=self._dev, dtype=torch.bfloat16)
             self._dense_counts = torch.zeros(max(cap, n_points), device=self._dev, dtype=torch.int32)
         elif n_points > self._dense_bank.shape[0]:
+            # fusions of earlier keyframes may still be queued on the descriptor stream with pointers into the old bank: the copy
+            # (and the release of the old tensors, which belong to this stream's pool) must come after them
+            self._sync_descriptors()
             grow = max(n_points, int(1.5 * self._dense_bank.shape[0]))
+            n_old = self._dense_bank.shape[0]
             nb = torch.zeros(grow, self._dense_bank.shape[1], device=self._dev, dtype=torch.bfloat16)
+            nl = torch.zeros(grow, self._dense_bank.shape[1], device=self._dev, dtype=torch.bfloat16)
             nc = torch.zeros(grow, device=self._dev, dtype=torch.int32)
-            nb[: self._dense_bank.shape[0]] = self._dense_bank
-            nc[: self._dense_counts.shape[0]] = self._dense_counts
-            self._dense_bank, self._dense_counts = nb, nc
+            nb[:n_old] = self._dense_bank
+            nl[:n_old] = self._dense_bank_lo
+            nc[:n_old] = self._dense_counts
+            self._dense_bank, self._dense_bank_lo, self._dense_counts = nb, nl, nc
 
     def _sync_descriptors(self) -> None:
         """Make the current stream wait for the descriptor stream (no host sync)."""

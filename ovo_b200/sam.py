@@ -173,7 +173,7 @@ class Sam2:
             gsz, dim = (spec.grid_out, spec.dim_out) if spec else (S // 4, self.cfg.embed_dim)
             blk = torch.empty(gsz * gsz, dim, device=self.device)
         check(self.lib.ovo_sam_set_image(self.handle, ptr(rgb), H, W, ptr(px), ptr(emb), ptr(s0), ptr(s1), n_blocks, ptr(blk),
-                                         stream_ptr()), "ovo_sam_set_image")
+                                         stream_ptr(self.device)), "ovo_sam_set_image")
         self._rgb = rgb
         return (px, emb, s0, s1) if n_blocks < 0 else blk
 
@@ -187,7 +187,7 @@ class Sam2:
             spec = self.cfg.blocks()[n_blocks - 1] if n_blocks > 0 else None
             gsz, dim = (spec.grid_out, spec.dim_out) if spec else (S // 4, self.cfg.embed_dim)
             blk = torch.empty(gsz * gsz, dim, device=self.device)
-        check(self.lib.ovo_sam_set_pixels(self.handle, ptr(pixels), ptr(emb), ptr(s0), ptr(s1), n_blocks, ptr(blk), stream_ptr()),
+        check(self.lib.ovo_sam_set_pixels(self.handle, ptr(pixels), ptr(emb), ptr(s0), ptr(s1), n_blocks, ptr(blk), stream_ptr(self.device)),
               "ovo_sam_set_pixels")
         return (emb, s0, s1) if n_blocks < 0 else blk
 
@@ -196,7 +196,7 @@ class Sam2:
         decoder (`predict`) works on."""
         rgb = rgb_u8.to(self.device, torch.uint8).contiguous()
         n, H, W, _ = rgb.shape
-        check(self.lib.ovo_sam_set_images(self.handle, ptr(rgb), n, H, W, stream_ptr()), "ovo_sam_set_images")
+        check(self.lib.ovo_sam_set_images(self.handle, ptr(rgb), n, H, W, stream_ptr(self.device)), "ovo_sam_set_images")
         self._rgb = rgb
 
     def select_image(self, index: int):
@@ -209,7 +209,7 @@ class Sam2:
         P = pts.shape[0]
         low = torch.empty(P, 3, 4 * self.g, 4 * self.g, device=self.device)
         iou = torch.empty(P, 3, device=self.device)
-        check(self.lib.ovo_sam_predict(self.handle, ptr(pts), P, ptr(low), ptr(iou), stream_ptr()), "ovo_sam_predict")
+        check(self.lib.ovo_sam_predict(self.handle, ptr(pts), P, ptr(low), ptr(iou), stream_ptr(self.device)), "ovo_sam_predict")
         return low, iou
 
     @staticmethod
@@ -228,7 +228,7 @@ class Sam2:
         boxes = torch.empty(n, 4, device=self.device, dtype=torch.int32); src = torch.empty(n, device=self.device, dtype=torch.int32)
         k = C.c_int(0)
         check(self.lib.ovo_sam_postprocess(self.handle, ptr(low.contiguous()), ptr(iou.contiguous()), P, h, w, H, W, C.byref(prm),
-                                           ptr(masks), ptr(io), ptr(st), ptr(boxes), ptr(src), n, C.byref(k), stream_ptr()),
+                                           ptr(masks), ptr(io), ptr(st), ptr(boxes), ptr(src), n, C.byref(k), stream_ptr(self.device)),
               "ovo_sam_postprocess")
         K = k.value
         return dict(masks=masks[:K], iou=io[:K], stability=st[:K], boxes=boxes[:K], src=src[:K])
@@ -242,7 +242,7 @@ class Sam2:
         maps = torch.empty(max_masks, H, W, device=self.device, dtype=torch.uint8)
         m = C.c_int(0)
         check(self.lib.ovo_sam_generate(self.handle, ptr(rgb), H, W, C.byref(prm), ptr(seg), ptr(maps), max_masks, C.byref(m),
-                                        stream_ptr()), "ovo_sam_generate")
+                                        stream_ptr(self.device)), "ovo_sam_generate")
         return seg, maps[: m.value].bool()
 
     def generate_batch(self, rgb_u8: torch.Tensor, prm: AmgParams = None, max_masks: int = 256):
@@ -255,5 +255,5 @@ class Sam2:
         maps = torch.empty(n, max_masks, H, W, device=self.device, dtype=torch.uint8)
         m = (C.c_int * n)()
         check(self.lib.ovo_sam_generate_batch(self.handle, ptr(rgb), n, H, W, C.byref(prm), ptr(seg), ptr(maps), max_masks, m,
-                                              stream_ptr()), "ovo_sam_generate_batch")
+                                              stream_ptr(self.device)), "ovo_sam_generate_batch")
         return [(seg[i], maps[i, : m[i]].bool()) for i in range(n)]

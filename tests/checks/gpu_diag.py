@@ -76,8 +76,9 @@ def stage_map():
     seg, bm = synth.grid_masks()
     seg_d = torch.from_numpy(seg).to(dev)
     bank = torch.zeros(N, 256, device=dev, dtype=torch.bfloat16)
+    bank_lo = torch.zeros_like(bank)
     counts = torch.zeros(N, device=dev, dtype=torch.int32)
-    bank_o = np.zeros((N, 256), np.float32); counts_o = np.zeros(N, np.int32)
+    bank_o = np.zeros((N, 256), np.float32); lo_o = np.zeros_like(bank_o); counts_o = np.zeros(N, np.int32)
     for fid in range(4):
         c2w = synth.pose(fid * 5)
         d = synth.depth_map(frame_id=fid)
@@ -97,16 +98,10 @@ def stage_map():
         order, fused, mask_row = OF.fuse_masks(bm, rows)
         R = max(len(order), 1)
         feats = torch.randn(R, 256)
-        sm.fuse_dense(fid, bank, counts, feats.to(dev), torch.from_numpy(mask_row).to(dev))
-        pts = np.nonzero(seg_of_pt >= 0)[0]
-        rr = mask_row[seg_of_pt[pts]]
-        sel = rr >= 0
-        for p, r_ in zip(pts[sel], rr[sel]):
-            c = counts_o[p] + 1
-            bank_o[p] = (torch.from_numpy(bank_o[p] + (feats[r_].numpy() - bank_o[p]) * (np.float32(1) / np.float32(c))).bfloat16().float().numpy())
-            counts_o[p] = c
-        print("  dense bank mismatches", int((bank.float().cpu().numpy() != bank_o).sum()), "count mismatches",
-              int((counts.cpu().numpy() != counts_o).sum()), flush=True)
+        sm.fuse_dense(fid, bank, bank_lo, counts, feats.to(dev), torch.from_numpy(mask_row).to(dev))
+        OF.dense_fuse(bank_o, lo_o, counts_o, [np.where(seg_of_pt >= 0, seg_of_pt, -1)], [mask_row], feats.numpy())
+        print("  dense bank mismatches", int((bank.float().cpu().numpy() != bank_o).sum()) + int((bank_lo.float().cpu().numpy() != lo_o).sum()),
+              "count mismatches", int((counts.cpu().numpy() != counts_o).sum()), flush=True)
         ins_o, next_id = ins_new, nxt_o
 
 

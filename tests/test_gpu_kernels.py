@@ -157,8 +157,9 @@ def test_association_multi_keyframe_vs_oracle(sm, N, track_th, ratio):
     xyz_d, ins_d = _dev(xyz, ins)
     D = 64
     bank = torch.zeros(max(N, 1), D, device="cuda", dtype=torch.bfloat16)
+    bank_lo = torch.zeros_like(bank)
     counts = torch.zeros(max(N, 1), device="cuda", dtype=torch.int32)
-    bank_o = np.zeros((max(N, 1), D), np.float32); counts_o = np.zeros(max(N, 1), np.int32)
+    hi_o = np.zeros((max(N, 1), D), np.float32); lo_o = np.zeros_like(hi_o); counts_o = np.zeros(max(N, 1), np.int32)
     next_id = 0
     for i in range(4):
         fid = 4 * i
@@ -176,16 +177,11 @@ def test_association_multi_keyframe_vs_oracle(sm, N, track_th, ratio):
             assert (votes[k] == np.array([r[k] for r in rows])).all(), (i, k)
         order, fused, mask_row = OF.fuse_masks(bm, rows)
         feats = torch.randn(max(len(order), 1), D, generator=torch.Generator().manual_seed(i))
-        sm.fuse_dense(i, bank, counts, feats.cuda(), torch.from_numpy(mask_row).cuda())
-        pts = np.nonzero(seg_of_pt >= 0)[0]
-        rr = mask_row[seg_of_pt[pts]]
-        for p, r_ in zip(pts[rr >= 0], rr[rr >= 0]):
-            c = counts_o[p] + 1
-            upd = bank_o[p] + (feats[r_].numpy() - bank_o[p]) * (np.float32(1) / np.float32(c))
-            bank_o[p] = torch.from_numpy(upd).bfloat16().float().numpy()
-            counts_o[p] = c
+        sm.fuse_dense(i, bank, bank_lo, counts, feats.cuda(), torch.from_numpy(mask_row).cuda())
+        if N:
+            OF.dense_fuse(hi_o, lo_o, counts_o, [np.where(seg_of_pt >= 0, seg_of_pt, -1)], [mask_row], feats.numpy())
         assert (counts.cpu().numpy() == counts_o).all()
-        assert (bank.float().cpu().numpy() == bank_o).all()
+        assert (bank.float().cpu().numpy() == hi_o).all() and (bank_lo.float().cpu().numpy() == lo_o).all()
         ins, next_id = new, nxt_o
 
 
@@ -228,18 +224,72 @@ def test_reserved_workspaces_give_the_same_association():
         SemanticMap("cuda:0").reserve(masks=1 << 20, instances=1 << 20)
 
 
-def test_fuse_dense_batch_equals_sequential(sm):
-    """One pass over the bank for several keyframes == one pass per keyframe, bit for bit."""
-    K = synth.intrinsics(); N, D, F = 120000, 128, 5
+def _batch_scene(N, F, seed=9):
+    K = synth.intrinsics()
     d0 = synth.depth_map(frame_id=0)
-    xyz, ids, ins = synth.point_map(N, d0, K, synth.pose(0), seed=9, frac_visible=0.6)
-    xyz_d, ins_d = _dev(xyz, ins)
-    feats_all, rows_all, nm = [], [], 48
-    base = 0
+    xyz, ids, ins = synth.point_map(N, d0, K, synth.pose(0), seed=seed, frac_visible=0.6)
+    frames = []
     for i in range(F):
         seg, bm = synth.grid_masks(rows=(6 if i % 2 == 0 else 3), cols=(8 if i % 2 == 0 else 5))
-        d_d, seg_d = _dev(synth.depth_map(frame_id=3 * i), seg)
-        votes, _, _ = sm.associate(xyz_d, ins_d, d_d, seg_d, synth.pose(3 * i), K, 0 if i == 0 else 48, kf_slot=i)
+        frames.append(dict(depth=synth.depth_map(frame_id=3 * i), seg=seg, bm=bm, c2w=synth.pose(3 * i)))
+    return K, xyz, ins, frames
+
+
+@pytest.mark.parametrize("N,F,track_th", [(120000, 5, 100), (0, 2, 100), (300, 3, 2), (70000, 19, 60)])
+def test_associate_batch_equals_sequential_and_oracle(sm, N, F, track_th):
+    """One pass over the map for F keyframes (id decisions on the device, one host sync) == F single-keyframe associations ==
+    oracle/fusion.py: votes, n_matched, next_ins_id, the per-point ids and the mask -> instance table, bit for bit; 19 keyframes
+    exercise the second shared-memory group of the pass (16 keyframes at a time)."""
+    K, xyz, ins, frames = _batch_scene(max(N, 1), F)
+    xyz, ins = xyz[:N], ins[:N]
+    xyz_d, ins_a = _dev(xyz, ins)
+    ins_b = ins_a.clone()
+    dd = [torch.from_numpy(f["depth"]).cuda() for f in frames]
+    sd = [torch.from_numpy(f["seg"]).cuda() for f in frames]
+    nms = [int(f["bm"].shape[0]) for f in frames]
+    seq, nxt = [], 0
+    for i in range(F):
+        v, nm, nxt = sm.associate(xyz_d, ins_a, dd[i], sd[i], frames[i]["c2w"], K, nxt, track_th=track_th, kf_slot=i, n_masks=nms[i])
+        seq.append((v, nm))
+    mask_ins = torch.full((F, 64), -7, dtype=torch.int32, device="cuda")
+    votes, nmb, nxt_b = sm.associate_batch(xyz_d, ins_b, dd, sd, [f["c2w"] for f in frames], K, 0, nms, track_th=track_th,
+                                           kf_slots=list(range(F)), mask_ins_out=mask_ins)
+    assert nxt_b == nxt and torch.equal(ins_a, ins_b)
+    for i in range(F):
+        assert nmb[i] == seq[i][1]
+        for k in votes[i]:
+            assert (votes[i][k] == seq[i][0][k]).all(), (i, k)
+        got = mask_ins[i].cpu().numpy()
+        assert (got[: nms[i]] == votes[i]["ins_id"]).all() and (got[nms[i]:] == -1).all()
+    # and the oracle, keyframe by keyframe
+    ins_o, nxt_o = ins.copy(), 0
+    for i, f in enumerate(frames):
+        w2c = torch.linalg.inv(torch.from_numpy(f["c2w"])).numpy()
+        seg_of_pt, _ = OF.associate(xyz, ins_o, f["depth"], f["seg"], f["c2w"], w2c, K, 0.05, True) if N else (np.zeros(0, np.int32), None)
+        ins_o, rows, nxt_o = OF.track(ins_o, seg_of_pt, f["seg"], track_th, nxt_o)
+        for k in votes[i]:
+            assert (votes[i][k] == np.array([r[k] for r in rows])).all(), (i, k)
+    assert nxt_o == nxt_b and (ins_b.cpu().numpy() == ins_o).all()
+
+
+def test_fuse_dense_batch_vs_oracle_and_sequential(sm):
+    """One pass over the two-plane bank for several keyframes: bit-exact against oracle/fusion.py dense_fuse (descriptors of a
+    point summed in f32, one mean update), from match lists and from the dense rows of a batched association alike; equal to
+    one pass per keyframe up to the rounding of the 16-bit mean (2^-15 relative)."""
+    N, D, F = 120000, 128, 5
+    K, xyz, ins, frames = _batch_scene(N, F)
+    xyz_d, ins_d = _dev(xyz, ins)
+    dd = [torch.from_numpy(f["depth"]).cuda() for f in frames]
+    sd = [torch.from_numpy(f["seg"]).cuda() for f in frames]
+    feats_all, rows_all, nm = [], [], 48
+    base, nxt = 0, 0
+    ins_o = ins.copy()
+    segs_o = []
+    for i in range(F):
+        votes, _, nxt = sm.associate(xyz_d, ins_d, dd[i], sd[i], frames[i]["c2w"], K, nxt, kf_slot=i)
+        w2c = torch.linalg.inv(torch.from_numpy(frames[i]["c2w"])).numpy()
+        seg_of_pt, _ = OF.associate(xyz, ins_o, frames[i]["depth"], frames[i]["seg"], frames[i]["c2w"], w2c, K, 0.05, True)
+        segs_o.append(np.where(seg_of_pt >= 0, seg_of_pt, -1))
         n_m = len(votes["ins_id"])
         local = np.where(votes["ins_id"] >= 0, np.arange(n_m), -1).astype(np.int32)
         local[::7] = -1                                   # some masks produce no descriptor
@@ -247,16 +297,64 @@ def test_fuse_dense_batch_equals_sequential(sm):
         row = np.full(nm, -1, np.int32); row[:n_m] = np.where(local >= 0, local + base, -1)
         rows_all.append((local, row)); base += n_m
     feats = torch.cat(feats_all).cuda()
-    bank_a = torch.zeros(N, D, device="cuda", dtype=torch.bfloat16); cnt_a = torch.zeros(N, device="cuda", dtype=torch.int32)
-    bank_b, cnt_b = bank_a.clone(), cnt_a.clone()
+    mk = lambda: (torch.zeros(N, D, device="cuda", dtype=torch.bfloat16), torch.zeros(N, D, device="cuda", dtype=torch.bfloat16),
+                  torch.zeros(N, device="cuda", dtype=torch.int32))
+    hi_a, lo_a, cnt_a = mk()
+    hi_b, lo_b, cnt_b = mk()
+    hi_c, lo_c, cnt_c = mk()
     off = 0
     for i in range(F):
         n_m = feats_all[i].shape[0]
-        sm.fuse_dense(i, bank_a, cnt_a, feats[off:off + n_m].contiguous(), torch.from_numpy(rows_all[i][0]).cuda())
+        sm.fuse_dense(i, hi_a, lo_a, cnt_a, feats[off:off + n_m].contiguous(), torch.from_numpy(rows_all[i][0]).cuda())
         off += n_m
-    sm.fuse_dense_batch(list(range(F)), bank_b, cnt_b, feats, torch.from_numpy(np.stack([r[1] for r in rows_all])).cuda())
-    assert torch.equal(cnt_a, cnt_b) and int(cnt_a.max()) >= 3
-    assert torch.equal(bank_a, bank_b)
+    mr = torch.from_numpy(np.stack([r[1] for r in rows_all])).cuda()
+    sm.fuse_dense_batch(list(range(F)), hi_b, lo_b, cnt_b, feats, mr)
+    # the same keyframes through the batched association (dense rows instead of lists)
+    ins_e = torch.from_numpy(ins).cuda()
+    sm.associate_batch(xyz_d, ins_e, dd, sd, [f["c2w"] for f in frames], K, 0, [int(f["bm"].shape[0]) for f in frames], kf_slots=list(range(F)))
+    sm.fuse_dense_batch(list(range(F)), hi_c, lo_c, cnt_c, feats, mr)
+    assert torch.equal(ins_e, ins_d)
+    hi_o = np.zeros((N, D), np.float32); lo_o = np.zeros_like(hi_o); cnt_o = np.zeros(N, np.int32)
+    OF.dense_fuse(hi_o, lo_o, cnt_o, segs_o, [r[1] for r in rows_all], feats.cpu().numpy())
+    for hi, lo, cnt in ((hi_b, lo_b, cnt_b), (hi_c, lo_c, cnt_c)):
+        assert (cnt.cpu().numpy() == cnt_o).all() and int(cnt.max()) >= 3
+        assert (hi.float().cpu().numpy() == hi_o).all() and (lo.float().cpu().numpy() == lo_o).all()
+    assert torch.equal(cnt_a, cnt_b)
+    fa, fb = hi_a.float() + lo_a.float(), hi_b.float() + lo_b.float()
+    assert (fa - fb).abs().max().item() <= 2.0 ** -14 * fb.abs().max().item()
+
+
+def test_dense_bank_keeps_the_mean_over_500_views(sm):
+    """a bf16 running mean re-rounded at every update freezes once the increment (e - f)/c drops below half
+    an ulp.  The two-plane bank must not: 500 updates of the same points against the f64 mean, 1 - cos <= 1e-6 (hi + lo) and
+    <= 1e-4 for the bf16 query plane alone."""
+    N, D, V = 512, 1024, 500
+    K = synth.intrinsics(); d = synth.depth_map()
+    xyz, ids, ins = synth.point_map(N, d, K, synth.pose(0), seed=1, frac_visible=1.0)
+    seg, bm = synth.grid_masks()
+    xyz_d, ins_d, d_d, seg_d = _dev(xyz, ins, d, seg)
+    votes, nm, nxt = sm.associate(xyz_d, ins_d, d_d, seg_d, synth.pose(0), K, 0, track_th=0, kf_slot=0)
+    pairs = sm.matches(0, nm).cpu().numpy()
+    assert len(pairs) > 100
+    M = bm.shape[0]
+    g = torch.Generator().manual_seed(0)
+    base = torch.nn.functional.normalize(torch.randn(M, D, generator=g), dim=-1)
+    hi = torch.zeros(N, D, device="cuda", dtype=torch.bfloat16); lo = torch.zeros_like(hi)
+    cnt = torch.zeros(N, device="cuda", dtype=torch.int32)
+    mask_row = torch.arange(M, dtype=torch.int32, device="cuda")
+    acc = torch.zeros(M, D, dtype=torch.float64)
+    for v in range(V):
+        e = torch.nn.functional.normalize(0.8 * base + 0.6 * torch.nn.functional.normalize(torch.randn(M, D, generator=g), dim=-1), dim=-1)
+        acc += e.double()
+        sm.fuse_dense(0, hi, lo, cnt, e.cuda(), mask_row)
+    pts, msk = pairs[:, 0], pairs[:, 1]
+    assert (cnt.cpu().numpy()[pts] == V).all()
+    ref = (acc / V)[msk]
+    full = (hi.double() + lo.double()).cpu()[pts]
+    cos = torch.nn.functional.cosine_similarity
+    assert (1 - cos(full, ref, dim=-1)).max().item() <= 1e-6
+    assert (1 - cos(hi.double().cpu()[pts], ref, dim=-1)).max().item() <= 1e-4
+    assert ((full - ref).norm(dim=-1) / ref.norm(dim=-1)).max().item() <= 3e-3     # descriptors enter rounded to bf16
 
 
 @pytest.mark.parametrize("seed", [0, 1, 2, 3])

@@ -33,11 +33,12 @@ if what in ("fuse", "assoc", "all"):
     seg, bm = synth.grid_masks()
     xyz_d, ins_d, dd, seg_d = (torch.from_numpy(a).to(dev) for a in (xyz, ins, d, seg))
     bank = torch.zeros(N, 1024, device=dev, dtype=torch.bfloat16)
+    bank_lo = torch.zeros_like(bank)
     counts = torch.zeros(N, device=dev, dtype=torch.int32)
     feats = torch.randn(48, 1024, device=dev)
     mask_row = torch.arange(48, dtype=torch.int32, device=dev)
     for i in range(3):
         sm.associate(xyz_d, ins_d, dd, seg_d, synth.pose(0), K, 0 if i == 0 else 48, kf_slot=0)
-        sm.fuse_dense(0, bank, counts, feats, mask_row)
+        sm.fuse_dense(0, bank, bank_lo, counts, feats, mask_row)
 torch.cuda.synchronize()
 print("done")
