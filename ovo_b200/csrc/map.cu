@@ -382,7 +382,7 @@ struct BatchFrame {
   const int32_t* seg_map;
   int n_masks, track_th;
   int votes_off;              // offset of this keyframe's vote table in the batch's table buffer (ints)
-  int pad;
+  int nm_off;                 // offset of its n_matched counter (the int behind the table)
 };
 
 __global__ void batch_depth_minmax_kernel(BatchFrame* __restrict__ fr) {
@@ -471,7 +471,8 @@ constexpr int kBatchFramesPerPass = 16;   // keyframes whose constants sit in sh
 
 __global__ void __launch_bounds__(kP1Threads)
     associate_batch_pass_kernel(const float* __restrict__ xyz, long long N, const BatchFrame* __restrict__ frames, int f0, int nf,
-                                int16_t* __restrict__ seg_of_pt /* [F][N] */, int32_t* __restrict__ n_matched /* [F] */) {
+                                int16_t* __restrict__ seg_of_pt /* [F][stride] */, long long stride,
+                                int32_t* __restrict__ tables /* n_matched of keyframe f at frames[f].nm_off */) {
   __shared__ float s_xyz[kP1Threads * 3];
   __shared__ BatchFrame s_fr[kBatchFramesPerPass];
   __shared__ int s_matched[kBatchFramesPerPass];
@@ -498,17 +499,18 @@ __global__ void __launch_bounds__(kP1Threads)
       int seg = -1;
       const bool matched = live && match_point_seg(x, y, z, s_fr[f].geom, s_fr[f].fr, s_fr[f].depth_used, s_fr[f].seg_map,
                                                    s_fr[f].n_masks, &seg);
-      if (live) seg_of_pt[static_cast<size_t>(f0 + f) * N + idx] = static_cast<int16_t>(seg);
+      if (live) seg_of_pt[static_cast<size_t>(f0 + f) * stride + idx] = static_cast<int16_t>(seg);
       const unsigned bal = __ballot_sync(0xffffffffu, matched);
       if (lane == 0 && bal) atomicAdd(&s_matched[f], __popc(bal));
     }
   }
   __syncthreads();
-  if (threadIdx.x < nf && s_matched[threadIdx.x]) atomicAdd(&n_matched[f0 + threadIdx.x], s_matched[threadIdx.x]);
+  if (threadIdx.x < nf && s_matched[threadIdx.x]) atomicAdd(&tables[s_fr[threadIdx.x].nm_off], s_matched[threadIdx.x]);
 }
 
 // Keyframe f of the batch: first give the points keyframe f-1 matched their new ids (its decisions are final), then vote.
-// One coalesced scan of the two dense rows and the ids; votes go to shared memory when the table fits.
+// One coalesced scan of the two dense rows and the ids, 8 points per thread (16-byte loads of the int16 rows: the rows are
+// padded to a multiple of 8 points); votes go to shared memory when the table fits.
 __global__ void __launch_bounds__(256)
     batch_vote_scan_kernel(const int16_t* __restrict__ seg_prev, const int32_t* __restrict__ mask_ins_prev,
                            const int16_t* __restrict__ seg_cur, int32_t* __restrict__ ins_ids, long long N,
@@ -520,20 +522,32 @@ __global__ void __launch_bounds__(256)
   if (use_smem)
     for (int i = threadIdx.x; i < n_votes; i += blockDim.x) s_votes[i] = 0;
   __syncthreads();
-  for (long long p = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; p < N;
-       p += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int sp = seg_prev ? seg_prev[p] : -1;
-    const int sc = seg_cur ? seg_cur[p] : -1;
-    if (sp < 0 && sc < 0) continue;
-    int id = ins_ids[p];
-    if (sp >= 0 && id == -1) {   // assigned points never change (ovo.py:274,280)
-      const int nid = mask_ins_prev[sp];
-      if (nid >= 0) { id = nid; ins_ids[p] = nid; }
-    }
-    if (sc >= 0) {
-      if (id >= n_ins) id = -1;  // ids the decisions do not know about count as unassigned
-      const int key = sc * (n_ins + 1) + (id + 1);
-      atomicAdd(use_smem ? &s_votes[key] : &votes[key], 1);
+  const long long n8 = (N + 7) >> 3;
+  for (long long q = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; q < n8;
+       q += static_cast<long long>(gridDim.x) * blockDim.x) {
+    uint4 vp = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu), vc = vp;
+    if (seg_prev) vp = *reinterpret_cast<const uint4*>(seg_prev + 8 * q);
+    if (seg_cur) vc = *reinterpret_cast<const uint4*>(seg_cur + 8 * q);
+    // any point of the eight matched by either keyframe?  (int16 -1 = 0xffff; mask indices are < 0x8000)
+    const uint32_t neg = (vp.x & vp.y & vp.z & vp.w & vc.x & vc.y & vc.z & vc.w & 0x80008000u);
+    if (neg == 0x80008000u) continue;
+    const int16_t* sp8 = reinterpret_cast<const int16_t*>(&vp);
+    const int16_t* sc8 = reinterpret_cast<const int16_t*>(&vc);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const long long p = 8 * q + j;
+      const int sp = sp8[j], sc = sc8[j];
+      if ((sp < 0 && sc < 0) || p >= N) continue;
+      int id = ins_ids[p];
+      if (sp >= 0 && id == -1) {   // assigned points never change (ovo.py:274,280)
+        const int nid = mask_ins_prev[sp];
+        if (nid >= 0) { id = nid; ins_ids[p] = nid; }
+      }
+      if (sc >= 0) {
+        if (id >= n_ins) id = -1;  // ids the decisions do not know about count as unassigned
+        const int key = sc * (n_ins + 1) + (id + 1);
+        atomicAdd(use_smem ? &s_votes[key] : &votes[key], 1);
+      }
     }
   }
   if (use_smem) {
@@ -545,7 +559,9 @@ __global__ void __launch_bounds__(256)
 
 // vote_reduce_kernel with the instance count read from the device (the batch never brings it to the host)
 __global__ void batch_vote_reduce_kernel(const int32_t* __restrict__ votes, const int32_t* __restrict__ n_ins_ptr,
-                                         const int32_t* __restrict__ area, ovo_vote_row* __restrict__ rows) {
+                                         const int32_t* __restrict__ area, ovo_vote_row* __restrict__ rows,
+                                         const int32_t* __restrict__ n_matched_in, int32_t* __restrict__ n_matched_out) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) *n_matched_out = *n_matched_in;   // the (summed) counter behind the table
   vote_reduce_body(votes, *n_ins_ptr, area, rows);
 }
 
@@ -574,29 +590,34 @@ __device__ __forceinline__ void unpack_bf16x8(const uint4& u, float* o) {
   }
 }
 
-template <int kVecPerLane>
+// kFull: the part is exactly kVecPerLane * 256 columns wide (no per-vector guards: straight-line code)
+template <int kVecPerLane, bool kFull = false>
 __device__ __forceinline__ void dense_row_load(DenseRow<kVecPerLane>& r, const __nv_bfloat16* hi, const __nv_bfloat16* lo,
-                                               size_t p, int D, int lane) {
+                                               size_t p, int D, int Dp, int lane) {
   const uint4* ph = reinterpret_cast<const uint4*>(hi + p * D);
   const uint4* pl = reinterpret_cast<const uint4*>(lo + p * D);
-  const int nvec = D >> 3;
+  const int nvec = Dp >> 3;
 #pragma unroll
   for (int i = 0; i < kVecPerLane; ++i) {
     const int v = lane + 32 * i;
-    if (v < nvec) { r.rh[i] = ph[v]; r.rl[i] = pl[v]; }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) r.s[8 * i + j] = 0.f;
+    if (kFull || v < nvec) { r.rh[i] = ph[v]; r.rl[i] = pl[v]; }
   }
 }
 
-// s += e (descriptor row, bf16); `first` = nothing has been added yet (s = e exactly)
-template <int kVecPerLane>
-__device__ __forceinline__ void dense_row_add(DenseRow<kVecPerLane>& r, const uint4 (&e)[kVecPerLane], int D, int lane) {
-  const int nvec = D >> 3;
+// s = e (first descriptor of the pass) / s += e, descriptor rows in bf16
+template <int kVecPerLane, bool kFull = false>
+__device__ __forceinline__ void dense_row_set(DenseRow<kVecPerLane>& r, const uint4 (&e)[kVecPerLane], int Dp, int lane) {
+  const int nvec = Dp >> 3;
+#pragma unroll
+  for (int i = 0; i < kVecPerLane; ++i)
+    if (kFull || lane + 32 * i < nvec) unpack_bf16x8(e[i], &r.s[8 * i]);
+}
+template <int kVecPerLane, bool kFull = false>
+__device__ __forceinline__ void dense_row_add(DenseRow<kVecPerLane>& r, const uint4 (&e)[kVecPerLane], int Dp, int lane) {
+  const int nvec = Dp >> 3;
 #pragma unroll
   for (int i = 0; i < kVecPerLane; ++i) {
-    const int v = lane + 32 * i;
-    if (v < nvec) {
+    if (kFull || lane + 32 * i < nvec) {
       float a[8];
       unpack_bf16x8(e[i], a);
 #pragma unroll
@@ -605,17 +626,17 @@ __device__ __forceinline__ void dense_row_add(DenseRow<kVecPerLane>& r, const ui
   }
 }
 
-template <int kVecPerLane>
+template <int kVecPerLane, bool kFull = false>
 __device__ __forceinline__ void dense_row_finish(DenseRow<kVecPerLane>& r, int k, int c_new, __nv_bfloat16* hi,
-                                                 __nv_bfloat16* lo, size_t p, int D, int lane) {
+                                                 __nv_bfloat16* lo, size_t p, int D, int Dp, int lane) {
   const float kf = static_cast<float>(k), inv = __fdiv_rn(1.0f, static_cast<float>(c_new));
   uint4* ph = reinterpret_cast<uint4*>(hi + p * D);
   uint4* pl = reinterpret_cast<uint4*>(lo + p * D);
-  const int nvec = D >> 3;
+  const int nvec = Dp >> 3;
 #pragma unroll
   for (int i = 0; i < kVecPerLane; ++i) {
     const int v = lane + 32 * i;
-    if (v < nvec) {
+    if (kFull || v < nvec) {
       float a[8], b[8];
       unpack_bf16x8(r.rh[i], a);
       unpack_bf16x8(r.rl[i], b);
@@ -638,14 +659,14 @@ __device__ __forceinline__ void dense_row_finish(DenseRow<kVecPerLane>& r, int k
   }
 }
 
-template <int kVecPerLane>
-__device__ __forceinline__ void load_desc_row(uint4 (&e)[kVecPerLane], const __nv_bfloat16* feats, int row, int D, int lane) {
+template <int kVecPerLane, bool kFull = false>
+__device__ __forceinline__ void load_desc_row(uint4 (&e)[kVecPerLane], const __nv_bfloat16* feats, int row, int D, int Dp, int lane) {
   const uint4* fr = reinterpret_cast<const uint4*>(feats + static_cast<size_t>(row) * D);
-  const int nvec = D >> 3;
+  const int nvec = Dp >> 3;
 #pragma unroll
   for (int i = 0; i < kVecPerLane; ++i) {
     const int v = lane + 32 * i;
-    if (v < nvec) e[i] = __ldg(fr + v);
+    if (kFull || v < nvec) e[i] = __ldg(fr + v);
   }
 }
 
@@ -666,10 +687,10 @@ __global__ void __launch_bounds__(256)
     if (lane == 0) counts[m.x] = c;
     DenseRow<kVecPerLane> row;
     uint4 ev[kVecPerLane];
-    load_desc_row<kVecPerLane>(ev, feats, r, D, lane);
-    dense_row_load<kVecPerLane>(row, hi, lo, static_cast<size_t>(m.x), D, lane);
-    dense_row_add<kVecPerLane>(row, ev, D, lane);
-    dense_row_finish<kVecPerLane>(row, 1, c, hi, lo, static_cast<size_t>(m.x), D, lane);
+    load_desc_row<kVecPerLane>(ev, feats, r, D, D, lane);
+    dense_row_load<kVecPerLane>(row, hi, lo, static_cast<size_t>(m.x), D, D, lane);
+    dense_row_set<kVecPerLane>(row, ev, D, lane);
+    dense_row_finish<kVecPerLane>(row, 1, c, hi, lo, static_cast<size_t>(m.x), D, D, lane);
   }
 }
 
@@ -688,21 +709,26 @@ __global__ void scatter_matches_kernel(const int2* __restrict__ list, int n, int
 // A warp scans 32 consecutive points (lane = point) for "matched by some keyframe", then takes the touched points one at a
 // time: lane f looks up the descriptor row of keyframe f for the point (seg_of_pt -> mask_row: F independent two-step
 // gathers in one round), the rows are broadcast with shuffles and two descriptor rows are in flight per step.
-template <int kVecPerLane>
-__global__ void __launch_bounds__(256, kVecPerLane <= 4 ? 2 : 1)
-    fuse_dense_batch_kernel(const int16_t* __restrict__ seg_of_pt /* [F][N] */, int F, long long N,
-                            __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int32_t* __restrict__ counts, int D,
-                            const __nv_bfloat16* __restrict__ feats, const int32_t* __restrict__ mask_row /* [F][n_masks] */,
+// A warp owns kVecPerLane * 256 COLUMNS of the rows (blockIdx.y = which part): with 512 columns per warp the kernel needs
+// ~80 registers, so 24 warps per SM are resident instead of 16 (the pass is latency-bound: ncu long_scoreboard).  The
+// counts are therefore not written here (another part's warp may still need the old value): fuse_counts_kernel follows.
+template <int kVecPerLane, bool kFull>
+__global__ void __launch_bounds__(256, kVecPerLane <= 2 ? 3 : 1)
+    fuse_dense_batch_kernel(const int16_t* __restrict__ seg_of_pt /* [F][stride] */, long long stride, int F, long long N,
+                            __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, const int32_t* __restrict__ counts,
+                            int D, const __nv_bfloat16* __restrict__ feats, const int32_t* __restrict__ mask_row /* [F][n_masks] */,
                             int n_masks) {
   const int lane = threadIdx.x & 31;
   const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const long long n_warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
   const int groups = (F + 31) >> 5;   // keyframes are looked up 32 at a time (lane = keyframe)
+  const int col0 = blockIdx.y * kVecPerLane * 256;   // first column of this warp's part
+  const int Dp = min(D - col0, kVecPerLane * 256);   // columns of this part
   for (long long p0 = warp * 32; p0 < N; p0 += n_warps * 32) {
     const long long pl = p0 + lane;
     bool any = false;
     if (pl < N)
-      for (int f = 0; f < F; ++f) any = any || (seg_of_pt[static_cast<size_t>(f) * N + pl] >= 0);
+      for (int f = 0; f < F; ++f) any = any || (seg_of_pt[static_cast<size_t>(f) * stride + pl] >= 0);
     unsigned todo_pts = __ballot_sync(0xffffffffu, any);
     while (todo_pts) {
       const int src = __ffs(todo_pts) - 1;
@@ -714,15 +740,16 @@ __global__ void __launch_bounds__(256, kVecPerLane <= 4 ? 2 : 1)
       for (int g = 0; g < 2; ++g) {
         const int f = 32 * g + lane;
         if (g < groups && f < F) {
-          const int m = seg_of_pt[static_cast<size_t>(f) * N + p];
+          const int m = seg_of_pt[static_cast<size_t>(f) * stride + p];
           if (m >= 0 && m < n_masks) rlane[g] = mask_row[f * n_masks + m];
         }
         k += __popc(__ballot_sync(0xffffffffu, rlane[g] >= 0));
       }
       if (k == 0) continue;   // matched only into masks that produced no descriptor
       DenseRow<kVecPerLane> row;
-      dense_row_load<kVecPerLane>(row, hi, lo, p, D, lane);
+      dense_row_load<kVecPerLane, kFull>(row, hi + col0, lo + col0, p, D, Dp, lane);
       const int c = counts[p];
+      bool have = false;
 #pragma unroll
       for (int g = 0; g < 2; ++g) {
         unsigned todo = __ballot_sync(0xffffffffu, rlane[g] >= 0);
@@ -734,15 +761,30 @@ __global__ void __launch_bounds__(256, kVecPerLane <= 4 ? 2 : 1)
           const int r0 = __shfl_sync(0xffffffffu, rlane[g], f0);
           const int r1 = __shfl_sync(0xffffffffu, rlane[g], f1 >= 0 ? f1 : f0);
           uint4 e0[kVecPerLane], e1[kVecPerLane];
-          load_desc_row<kVecPerLane>(e0, feats, r0, D, lane);
-          if (f1 >= 0) load_desc_row<kVecPerLane>(e1, feats, r1, D, lane);
-          dense_row_add<kVecPerLane>(row, e0, D, lane);
-          if (f1 >= 0) dense_row_add<kVecPerLane>(row, e1, D, lane);
+          load_desc_row<kVecPerLane, kFull>(e0, feats + col0, r0, D, Dp, lane);
+          if (f1 >= 0) load_desc_row<kVecPerLane, kFull>(e1, feats + col0, r1, D, Dp, lane);
+          if (have) dense_row_add<kVecPerLane, kFull>(row, e0, Dp, lane);
+          else dense_row_set<kVecPerLane, kFull>(row, e0, Dp, lane);
+          have = true;
+          if (f1 >= 0) dense_row_add<kVecPerLane, kFull>(row, e1, Dp, lane);
         }
       }
-      dense_row_finish<kVecPerLane>(row, k, c + k, hi, lo, p, D, lane);
-      if (lane == 0) counts[p] = c + k;
+      dense_row_finish<kVecPerLane, kFull>(row, k, c + k, hi + col0, lo + col0, p, D, Dp, lane);
     }
+  }
+}
+
+// counts[p] += number of keyframes of the pass that brought a descriptor for p (the k of fuse_dense_batch_kernel)
+__global__ void fuse_counts_kernel(const int16_t* __restrict__ seg_of_pt, long long stride, int F, long long N,
+                                   int32_t* __restrict__ counts, const int32_t* __restrict__ mask_row, int n_masks) {
+  for (long long p = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; p < N;
+       p += static_cast<long long>(gridDim.x) * blockDim.x) {
+    int k = 0;
+    for (int f = 0; f < F; ++f) {
+      const int m = seg_of_pt[static_cast<size_t>(f) * stride + p];
+      if (m >= 0 && m < n_masks && mask_row[f * n_masks + m] >= 0) ++k;
+    }
+    if (k) counts[p] += k;
   }
 }
 
@@ -1156,7 +1198,7 @@ struct ovo_map {
   int32_t* bt_tables = nullptr; size_t bt_tables_cap = 0;
   bool bt_valid = false; int bt_F = 0; int64_t bt_N = 0; int bt_next = 0; int32_t* bt_user_tables = nullptr;
   std::vector<int> bt_n_masks, bt_track_th, bt_votes_off, bt_table_len, bt_slots;
-  int64_t dense_N = 0; int dense_F = 0; std::vector<int> dense_slots;   // what seg_dense currently holds (from a batched association)
+  int64_t dense_N = 0, dense_stride = 0; int dense_F = 0; std::vector<int> dense_slots;   // what seg_dense currently holds (from a batched association)
   __nv_bfloat16* feats_bf16 = nullptr; size_t feats_cap = 0;
   // association split in two calls (ovo_map_vote / ovo_map_apply): state of the pending keyframe
   bool pend_valid = false; int64_t pend_N = 0; int pend_n_ins = 0, pend_n_masks = 0, pend_slot = 0, pend_track_th = 0;
@@ -1386,9 +1428,9 @@ struct BatchCtl {   // byte offsets inside the batch control block
   size_t n_matched, next, frames, rows, end;
   BatchCtl(int fcap, int stride) {
     n_matched = 0;
-    next = static_cast<size_t>(fcap) * 4;
-    frames = next + 16;
-    rows = frames + static_cast<size_t>(fcap) * sizeof(ovo::BatchFrame);
+    next = (static_cast<size_t>(fcap) * 4 + 15) & ~size_t(15);
+    frames = next + 16;                                                      // 16-byte aligned: BatchFrame holds pointers
+    rows = (frames + static_cast<size_t>(fcap) * sizeof(ovo::BatchFrame) + 15) & ~size_t(15);
     end = rows + static_cast<size_t>(fcap) * stride * sizeof(ovo_vote_row);
   }
 };
@@ -1427,7 +1469,8 @@ int ovo_map_batch_begin(ovo_map_t* m, const float* xyz_dev, const int32_t* ins_i
   }
   OVO_TRY(batch_ctl_alloc(m, F, max_masks));
   OVO_TRY(grow(&m->bt_depth, &m->bt_depth_cap, static_cast<size_t>(F) * npix_max));
-  OVO_TRY(grow(&m->seg_dense, &m->seg_dense_cap, static_cast<size_t>(F) * static_cast<size_t>(N > 0 ? N : 1)));
+  const int64_t stride = ((N > 0 ? N : 1) + 7) & ~int64_t(7);   // rows padded to 8 points: 16-byte loads in the vote scan
+  OVO_TRY(grow(&m->seg_dense, &m->seg_dense_cap, static_cast<size_t>(F) * static_cast<size_t>(stride)));
   // vote tables: keyframe f may see up to next_ins_id + (masks of the keyframes before it) instances; each table is followed by
   // one counter (the keyframe's n_matched) so that a sharded map sums both with one exchange
   m->bt_n_masks.assign(F, 0); m->bt_track_th.assign(F, 0); m->bt_votes_off.assign(F, 0); m->bt_table_len.assign(F, 0);
@@ -1470,6 +1513,7 @@ int ovo_map_batch_begin(ovo_map_t* m, const float* xyz_dev, const int32_t* ins_i
     b.depth_filtered = fr.depth_filter ? m->bt_depth + static_cast<size_t>(f) * npix_max : nullptr;
     b.depth_used = fr.depth_filter ? b.depth_filtered : fr.depth_dev;
     b.seg_map = fr.seg_map_dev; b.n_masks = fr.n_masks; b.track_th = fr.track_th; b.votes_off = m->bt_votes_off[f];
+    b.nm_off = m->bt_votes_off[f] + m->bt_table_len[f] - 1;
     h_nm[f] = 0;
   }
   h_next[0] = next_ins_id; h_next[1] = h_next[2] = h_next[3] = 0;
@@ -1477,7 +1521,6 @@ int ovo_map_batch_begin(ovo_map_t* m, const float* xyz_dev, const int32_t* ins_i
   OVO_CUDA(cudaMemsetAsync(tables, 0, off * sizeof(int32_t), stream));
   OVO_CUDA(cudaMemsetAsync(m->bt_area, 0, static_cast<size_t>(m->bt_fcap) * m->bt_stride * sizeof(int32_t), stream));
   ovo::BatchFrame* dfr = reinterpret_cast<ovo::BatchFrame*>(m->bctl + L.frames);
-  int32_t* d_nm = reinterpret_cast<int32_t*>(m->bctl + L.n_matched);
   const int sms = ovo::num_sms();
   int hmax = 0, wmax = 0;
   for (int f = 0; f < F; ++f) { hmax = std::max(hmax, frames[f].h); wmax = std::max(wmax, frames[f].w); }
@@ -1493,12 +1536,12 @@ int ovo_map_batch_begin(ovo_map_t* m, const float* xyz_dev, const int32_t* ins_i
     const int blocks = static_cast<int>(std::min<long long>((N + ovo::kP1Threads - 1) / ovo::kP1Threads, sms * 8LL));
     for (int f0 = 0; f0 < F; f0 += ovo::kBatchFramesPerPass) {
       ovo::associate_batch_pass_kernel<<<blocks, ovo::kP1Threads, 0, stream>>>(xyz_dev, N, dfr, f0, std::min(ovo::kBatchFramesPerPass, F - f0),
-                                                                                m->seg_dense, d_nm);
+                                                                                m->seg_dense, stride, tables);
       OVO_CHECK_LAUNCH();
     }
   }
   m->bt_valid = true; m->bt_F = F; m->bt_N = N; m->bt_next = next_ins_id;
-  m->dense_slots.assign(m->bt_slots.begin(), m->bt_slots.end()); m->dense_N = N; m->dense_F = F;
+  m->dense_slots.assign(m->bt_slots.begin(), m->bt_slots.end()); m->dense_N = N; m->dense_F = F; m->dense_stride = stride;
   for (int f = 0; f < F; ++f)
     if (m->bt_slots[f] >= 0) m->slot_n[m->bt_slots[f]] = 0;   // these slots hold dense rows now, not lists
   return OVO_OK;
@@ -1515,16 +1558,15 @@ int ovo_map_batch_vote(ovo_map_t* m, int f, int32_t* ins_ids_dev, int32_t** tabl
   const int len = m->bt_table_len[f];
   const int32_t* d_next = reinterpret_cast<const int32_t*>(m->bctl + L.next);
   if (N > 0) {
-    const int16_t* prev = f > 0 ? m->seg_dense + static_cast<size_t>(f - 1) * N : nullptr;
+    const size_t st = static_cast<size_t>(m->dense_stride);
+    const int16_t* prev = f > 0 ? m->seg_dense + static_cast<size_t>(f - 1) * st : nullptr;
     const int32_t* mi_prev = f > 0 ? m->bt_mask_ins + static_cast<size_t>(f - 1) * m->bt_stride : nullptr;
     const int smem_ints = std::min(len - 1, 10 * 1024);   // up to 40 KB of shared-memory votes
-    const int blocks = static_cast<int>(std::min<long long>((N + 255) / 256, ovo::num_sms() * 4LL));
-    ovo::batch_vote_scan_kernel<<<blocks, 256, smem_ints * sizeof(int32_t), stream>>>(prev, mi_prev, m->seg_dense + static_cast<size_t>(f) * N,
+    const int blocks = static_cast<int>(std::min<long long>(((N + 7) / 8 + 255) / 256, ovo::num_sms() * 8LL));
+    ovo::batch_vote_scan_kernel<<<blocks, 256, smem_ints * sizeof(int32_t), stream>>>(prev, mi_prev, m->seg_dense + static_cast<size_t>(f) * st,
                                                                                     ins_ids_dev, N, d_next, m->bt_n_masks[f], table, smem_ints);
     OVO_CHECK_LAUNCH();
   }
-  // the keyframe's n_matched rides behind its table
-  OVO_CUDA(cudaMemcpyAsync(table + len - 1, m->bctl + L.n_matched + 4 * static_cast<size_t>(f), sizeof(int32_t), cudaMemcpyDeviceToDevice, stream));
   if (table_dev) *table_dev = table;
   if (table_len) *table_len = len;
   return OVO_OK;
@@ -1540,12 +1582,15 @@ int ovo_map_batch_decide(ovo_map_t* m, int f, void* stream_) {
   int32_t* d_next = reinterpret_cast<int32_t*>(m->bctl + L.next);
   ovo_vote_row* rows = reinterpret_cast<ovo_vote_row*>(m->bctl + L.rows) + static_cast<size_t>(f) * m->bt_stride;
   int32_t* mask_ins = m->bt_mask_ins + static_cast<size_t>(f) * m->bt_stride;
-  OVO_CUDA(cudaMemcpyAsync(m->bctl + L.n_matched + 4 * static_cast<size_t>(f), table + m->bt_table_len[f] - 1, sizeof(int32_t), cudaMemcpyDeviceToDevice, stream));
+  int32_t* nm_out = reinterpret_cast<int32_t*>(m->bctl + L.n_matched) + f;
   if (nm > 0) {
-    ovo::batch_vote_reduce_kernel<<<nm, 128, 0, stream>>>(table, d_next, m->bt_area + static_cast<size_t>(f) * m->bt_stride, rows);
+    ovo::batch_vote_reduce_kernel<<<nm, 128, 0, stream>>>(table, d_next, m->bt_area + static_cast<size_t>(f) * m->bt_stride, rows,
+                                                         table + m->bt_table_len[f] - 1, nm_out);
     OVO_CHECK_LAUNCH();
     ovo::vote_decide_kernel<<<1, 256, 0, stream>>>(rows, nm, m->bt_track_th[f], mask_ins, d_next);
     OVO_CHECK_LAUNCH();
+  } else {
+    OVO_CUDA(cudaMemcpyAsync(nm_out, table + m->bt_table_len[f] - 1, sizeof(int32_t), cudaMemcpyDeviceToDevice, stream));
   }
   return OVO_OK;
 }
@@ -1562,8 +1607,8 @@ int ovo_map_batch_end(ovo_map_t* m, int32_t* ins_ids_dev, int* next_ins_id, ovo_
   const int64_t N = m->bt_N;
   for (int f = 0; f < F; ++f) OVO_REQUIRE(m->bt_n_masks[f] <= votes_stride, "ovo_map_batch_end: votes_stride %d < n_masks %d", votes_stride, m->bt_n_masks[f]);
   if (N > 0 && m->bt_n_masks[F - 1] > 0) {
-    const int blocks = static_cast<int>(std::min<long long>((N + 255) / 256, ovo::num_sms() * 4LL));
-    ovo::batch_vote_scan_kernel<<<blocks, 256, 0, stream>>>(m->seg_dense + static_cast<size_t>(F - 1) * N,
+    const int blocks = static_cast<int>(std::min<long long>(((N + 7) / 8 + 255) / 256, ovo::num_sms() * 8LL));
+    ovo::batch_vote_scan_kernel<<<blocks, 256, 0, stream>>>(m->seg_dense + static_cast<size_t>(F - 1) * static_cast<size_t>(m->dense_stride),
                                                            m->bt_mask_ins + static_cast<size_t>(F - 1) * m->bt_stride, nullptr, ins_ids_dev, N,
                                                            reinterpret_cast<const int32_t*>(m->bctl + L.next), 0, nullptr, 0);
     OVO_CHECK_LAUNCH();
@@ -1672,9 +1717,11 @@ int ovo_map_fuse_dense_batch(ovo_map_t* m, const int* kf_slots_host, int n_slots
     for (int i = 0; direct && i < n_slots; ++i) direct = m->dense_slots[first + i] == kf_slots_host[i];
   }
   const int16_t* rows = nullptr;
+  int64_t stride = 0;
   double touched = 0;
   if (direct) {
-    rows = m->seg_dense + static_cast<size_t>(first) * N;
+    stride = m->dense_stride;
+    rows = m->seg_dense + static_cast<size_t>(first) * stride;
     touched = static_cast<double>(N) * 0.25;   // profiling estimate only
   } else {
     long long total = 0;
@@ -1685,7 +1732,8 @@ int ovo_map_fuse_dense_batch(ovo_map_t* m, const int* kf_slots_host, int n_slots
       total += m->slot_n[kf_slots_host[i]];
     }
     if (total == 0) return OVO_OK;
-    const size_t need = static_cast<size_t>(n_slots) * N;
+    stride = (N + 7) & ~int64_t(7);
+    const size_t need = static_cast<size_t>(n_slots) * stride;
     OVO_TRY(grow(&m->seg_dense, &m->seg_dense_cap, need));
     m->dense_slots.clear(); m->dense_N = 0; m->dense_F = 0;
     OVO_CUDA(cudaMemsetAsync(m->seg_dense, 0xff, need * sizeof(int16_t), stream));   // -1 everywhere
@@ -1693,7 +1741,7 @@ int ovo_map_fuse_dense_batch(ovo_map_t* m, const int* kf_slots_host, int n_slots
     for (int i = 0; i < n_slots; ++i) {
       const int sl = kf_slots_host[i], n = m->slot_n[sl];
       if (n == 0) continue;
-      ovo::scatter_matches_kernel<<<std::min(ovo::ceil_div(n, 256), sms * 4), 256, 0, stream>>>(m->slot_list[sl], n, m->seg_dense + static_cast<size_t>(i) * N);
+      ovo::scatter_matches_kernel<<<std::min(ovo::ceil_div(n, 256), sms * 4), 256, 0, stream>>>(m->slot_list[sl], n, m->seg_dense + static_cast<size_t>(i) * stride);
       OVO_CHECK_LAUNCH();
     }
     rows = m->seg_dense;
@@ -1701,13 +1749,16 @@ int ovo_map_fuse_dense_batch(ovo_map_t* m, const int* kf_slots_host, int n_slots
   }
   ovo::ProfScope prof(stream, ovo::PROF_FUSE, 0.0, touched * (8.0 * D + 8));
   OVO_TRY(stage_feats(m, feats_dev, n_rows, D, stream));
-  const int blocks = static_cast<int>(std::min<long long>((N + 255) / 256, ovo::num_sms() * 8LL));
   auto* hi = static_cast<__nv_bfloat16*>(bank_dev);
   auto* lo = static_cast<__nv_bfloat16*>(bank_lo_dev);
-  if (D <= 1024)
-    ovo::fuse_dense_batch_kernel<4><<<blocks, 256, 0, stream>>>(rows, n_slots, N, hi, lo, counts_dev, D, m->feats_bf16, mask_row_dev, n_masks);
+  const int parts = ovo::ceil_div(D, 512);   // a warp owns 512 columns of a row
+  const int blocks = static_cast<int>(std::min<long long>((N + 255) / 256, std::max(1, ovo::num_sms() * 12 / parts)));
+  if (D % 512 == 0)
+    ovo::fuse_dense_batch_kernel<2, true><<<dim3(blocks, parts), 256, 0, stream>>>(rows, stride, n_slots, N, hi, lo, counts_dev, D, m->feats_bf16, mask_row_dev, n_masks);
   else
-    ovo::fuse_dense_batch_kernel<8><<<blocks, 256, 0, stream>>>(rows, n_slots, N, hi, lo, counts_dev, D, m->feats_bf16, mask_row_dev, n_masks);
+    ovo::fuse_dense_batch_kernel<2, false><<<dim3(blocks, parts), 256, 0, stream>>>(rows, stride, n_slots, N, hi, lo, counts_dev, D, m->feats_bf16, mask_row_dev, n_masks);
+  OVO_CHECK_LAUNCH();
+  ovo::fuse_counts_kernel<<<static_cast<int>(std::min<long long>((N + 255) / 256, ovo::num_sms() * 8LL)), 256, 0, stream>>>(rows, stride, n_slots, N, counts_dev, mask_row_dev, n_masks);
   OVO_CHECK_LAUNCH();
   return OVO_OK;
 }
