@@ -157,7 +157,8 @@ def run_ours(args, rank, world, local_rank):
             main.wait_stream(side)
         return feats
 
-    def timed(fn, steps, warmup):
+    def timed(fn, steps, warmup, side_stream=None):
+        side_stream = side_stream or side
         for _ in range(warmup):
             fn()
         torch.cuda.synchronize()
@@ -168,7 +169,7 @@ def run_ours(args, rank, world, local_rank):
         e0.record()
         for _ in range(steps):
             fn()
-        torch.cuda.current_stream().wait_stream(side)      # the last step's fusion (side stream) belongs to the timed region
+        torch.cuda.current_stream().wait_stream(side_stream)      # the last step's fusion (side stream) belongs to the timed region
         e1.record()
         torch.cuda.synchronize()
         launches = _lib.lib().ovo_launch_count(0)
@@ -184,10 +185,20 @@ def run_ours(args, rank, world, local_rank):
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
-    ms_total, launches = timed(step, args.steps, args.warmup)
+    sharded = None
+    if world > 1:
+        # N > 1: BASELINE config 3 — ONE map sharded over the ranks (the headline), and the independent replicas beside it
+        sharded = run_sharded(args, rank, world, dev, dist, enc, timed)
+        rep_steps = max(3, args.steps // 2)
+        rep_total, _ = timed(step, rep_steps, args.warmup)
+        replicas = {"value": round(world * F / (rep_total / rep_steps / 1e3), 2), "unit": "keyframes/s", "ms_per_step": round(rep_total / rep_steps, 4),
+                    "note": f"{world} independent replicas, each with its own {P}-point map (no data-path collective)"}
+        ms_step, value, launches = sharded["ms_per_step"], sharded["value"], sharded["launches"]
+    else:
+        ms_total, launches = timed(step, args.steps, args.warmup)
+        ms_step = ms_total / args.steps
+        value = world * F / (ms_step / 1e3)
     clocks = sampler.stop() if sampler else None
-    ms_step = ms_total / args.steps
-    value = world * F / (ms_step / 1e3)
 
     # --- the encoder alone (E1..E5 of the same batch, nothing on the side stream): what the step costs beyond it is
     # association/fusion contention and host gaps
@@ -255,13 +266,23 @@ def run_ours(args, rank, world, local_rank):
            "value": round(value, 2), "unit": "keyframes/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "bf16 (f32 accumulate, f32 residual stream)", "data": "synthetic (seeded RGB-D, random-init weights)",
-           "config": {"workload": f"{F} keyframes/step x {world} replica(s): 640x480 RGB-D, PE-Core-L14-336 (2 images/keyframe), "
-                                  f"{M} precomputed masks/keyframe (sam.precomputed seam), {P}-point map per replica, dense "
-                                  f"running-mean fusion + instance bank; query Q={Q}",
-                      "frames_per_step": F, "points": P, "masks": M, "queries": Q, "parallelism": f"replicas x{world}",
+           "config": {"workload": (f"{F} keyframes/step: 640x480 RGB-D, PE-Core-L14-336 (2 images/keyframe), "
+                                   f"{M} precomputed masks/keyframe (sam.precomputed seam), {P}-point map, dense "
+                                   f"running-mean fusion + instance bank; query Q={Q}") if world == 1 else
+                                  (f"BASELINE config 3: {world} scenes x {F} keyframes/step, data-parallel PE-Core-L14-336 (2 images/keyframe, "
+                                   f"{M} precomputed masks), ONE shared {P}-point map sharded {world}-way by spatial hash: per step all-gather of "
+                                   f"depth+seg, {world * F} vote-table exchanges, all-gather of descriptors, all-to-all of {NEW_POINTS_PER_FRAME} new "
+                                   f"points per rank; dense running-mean fusion + instance bank; query Q={Q}"),
+                      "frames_per_step": F, "points": P, "masks": M, "queries": Q,
+                      "parallelism": "single GPU" if world == 1 else f"dp{world} encoder + map sharded x{world}",
                       "l2_policy": "inputs larger than L2: per step 0.63 GB weights + ~2 GB map/bank traffic per keyframe (L2 126 MB)"},
            "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e, "roofline": roofline, "query": query,
            "n_matched_points_per_keyframe": int(state["n_matched"])}
+    if sharded is not None:
+        out["sharded_map"] = {k: v for k, v in sharded.items() if k not in ("ms_per_step", "value", "launches")}
+        out["replicas"] = replicas
+        out["scaling_note"] = ("weak: per-GPU work is constant in N (F keyframes encoded per rank and step; every rank tests its "
+                               "points/N shard against all N*F keyframes); the shared map's total size is fixed")
     if sam is not None:
         out["sam"] = sam
     if nxt is not None:
@@ -273,6 +294,207 @@ def run_ours(args, rank, world, local_rank):
         if sam is not None:
             out["sam"]["cpu_baseline"] = sam_cpu_baseline()
     print(json.dumps(out))
+
+
+NEW_POINTS_PER_FRAME = 76_800       # VanillaMapper at downscale 2 on 640x480 (vanilla_mapper.py:32-36)
+
+
+def run_sharded(args, rank, world, dev, dist, enc, timed):
+    """BASELINE config 3: `world` scenes replayed data-parallel (rank r encodes the keyframes g with g % world == r: F per step)
+    into ONE shared map of `--points` points sharded by spatial hash (ovo_b200.sharding.shard_of_points).  Per step, inside the
+    timed region: all-gather of the keyframes' depth + seg-map, ONE pass of every rank over its shard for all world*F keyframes,
+    per keyframe (global order) the vote-table exchange (all-reduce SUM) and the identical decisions on every rank, all-gather of
+    the region descriptors, dense fusion of the shard + the replicated instance bank, and one all-to-all of 76.8k freshly
+    mapped points per rank (one mapped frame per rank and step) routed to the shards that own them.
+    Per-GPU work is constant in `world` (F keyframes encoded, F * points point tests): weak scaling."""
+    from ovo_b200 import sharding, synth
+    from ovo_b200.map import SemanticMap
+    F, P = args.frames_per_step, args.points
+    G = world * F
+    assert G <= 64, "at most 64 keyframes per batch (ovo_map_batch_begin)"
+    K, xyz, ids, ins, seg, bm = scene(P, seed=0)                   # ONE global map, the same on every rank
+    M = bm.shape[0]
+    D = enc.cfg.output_dim
+    owner = sharding.shard_of_points(xyz, world)
+    mine = np.nonzero(owner == rank)[0]
+    n0 = len(mine)
+    cap_dst = int(1.5 * NEW_POINTS_PER_FRAME / world) + 64          # records per (source, destination) and step, padded
+    ring_slots = 2
+    ring = ring_slots * world * cap_dst                             # growth region of the shard, overwritten cyclically
+    NL = n0 + ring
+    xyz_l = torch.full((NL, 3), 1.0e6, dtype=torch.float32, device=dev)
+    xyz_l[:n0] = torch.from_numpy(xyz[mine]).to(dev)
+    ins_l = torch.full((NL,), -1, dtype=torch.int32, device=dev)
+    sm = SemanticMap(dev)
+    fr = frames(F, seed=rank)                                       # this rank's scene
+    rgb_d = torch.from_numpy(np.stack([f["image"] for f in fr])).to(dev)
+    masks_d = torch.from_numpy(np.concatenate([bm] * F)).to(dev).to(torch.uint8).contiguous()
+    depth_own = torch.from_numpy(np.stack([f["depth"] for f in fr])).to(dev)                  # [F,h,w]
+    seg_own = torch.from_numpy(np.stack([seg] * F)).to(dev)                                    # [F,H,W]
+    depth_f_own = torch.empty_like(depth_own)                       # this rank's keyframes after the depth filter ...
+    range_own = torch.empty(F, 2, dtype=torch.float32, device=dev)  # ... and the [min, max] of their raw depth (frustum)
+    depth_all = torch.empty(world, F, H, W, dtype=torch.float32, device=dev)
+    range_all = torch.empty(world, F, 2, dtype=torch.float32, device=dev)
+    seg_all = torch.empty(world, F, H, W, dtype=torch.int32, device=dev)
+    feats_all = torch.empty(world, F * M, D, dtype=torch.float32, device=dev)
+    # global keyframe g: encoded by rank g % world as its local keyframe g // world (poses come with the replay: host-known)
+    order = [(g % world, g // world) for g in range(G)]
+    all_fr = [frames(F, seed=r) for r in range(world)] if world <= 8 else None
+    c2ws = [all_fr[r][i]["c2w"] for r, i in order]
+    w2cs = [torch.linalg.inv(torch.from_numpy(c)).numpy() for c in c2ws]
+    depths = [depth_all[r, i] for r, i in order]
+    ranges = [range_all[r, i] for r, i in order]
+    segs = [seg_all[r, i] for r, i in order]
+    row0 = torch.tensor([r * F * M + i * M for r, i in order], dtype=torch.int32, device=dev)[:, None] + torch.arange(M, dtype=torch.int32, device=dev)[None]
+    bank = torch.zeros(NL, D, device=dev, dtype=torch.bfloat16)
+    bank_lo = torch.zeros_like(bank)
+    counts = torch.zeros(NL, device=dev, dtype=torch.int32)
+    ibank = torch.zeros(4096, D, device=dev, dtype=torch.float32)
+    icounts = torch.zeros(4096, device=dev, dtype=torch.int32)
+    mask_ins = torch.full((G, M), -1, dtype=torch.int32, device=dev)
+    tables = torch.zeros(SemanticMap.batch_tables_size(4096, [M] * G), dtype=torch.int32, device=dev)
+    state = dict(next_id=0, step=0, overflow=torch.zeros((), dtype=torch.int64, device=dev))
+    side = torch.cuda.Stream(device=dev)
+    exchange = "nccl"
+    if args.exchange == "p2p":
+        from ovo_b200.p2p import VoteExchange
+        exchange = VoteExchange(sm, rank, world, dev, table_ints=4 + M * (1024 + M * G + 1), slots=G)
+
+        def do_assoc(next_id):           # the whole batch in ONE library call, tables summed by the device-side peer exchange
+            return exchange.associate_batch(xyz_l, ins_l, depths, segs, c2ws, K, next_id, M, kf_slots=range(G), w2cs=w2cs,
+                                            mask_ins_out=mask_ins, depth_ranges=ranges)
+    else:
+        assoc = sharding.ShardedBatchAssociation(sm, exchange="nccl")
+
+        def do_assoc(next_id):           # per keyframe: vote kernel -> NCCL all-reduce -> decision kernels
+            return assoc.associate(xyz_l, ins_l, depths, segs, c2ws, K, next_id, M, tables, kf_slots=range(G), w2cs=w2cs,
+                                   depth_ranges=ranges, n_frames=G, mask_ins_out=mask_ins)
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    # freshly mapped points of 4 synthetic frames per rank (a region no benchmark keyframe looks at), cycled over the steps
+    new_pts = [torch.rand(NEW_POINTS_PER_FRAME, 3, device=dev, generator=gen) * torch.tensor([16.0, 12.0, 6.0], device=dev) +
+               torch.tensor([-8.0, -6.0, 20.0], device=dev) for _ in range(4)]
+    new_ids = torch.arange(NEW_POINTS_PER_FRAME, dtype=torch.int32, device=dev)
+    ev = {}                                                         # optional per-collective events of the instrumented pass
+
+    def mark(name):
+        if ev is not None and state.get("instrument"):
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            ev.setdefault(name, []).append(e)
+
+    def step():
+        main = torch.cuda.current_stream()
+        side.wait_stream(main)
+        feats = enc.encode_regions(rgb_d, masks_d, masks_per_frame=[M] * F)
+        enc_done = main.record_event()
+        with torch.cuda.stream(side):
+            mark("t0")
+            # the depth filter and the raw-depth range of a keyframe are computed ONCE, where the keyframe lives, and gathered
+            for i in range(F):
+                sm.depth_filter(depth_own[i], out=depth_f_own[i])
+                sm.depth_range(depth_own[i], out=range_own[i])
+            dist.all_gather_into_tensor(depth_all, depth_f_own)
+            dist.all_gather_into_tensor(range_all, range_own)
+            dist.all_gather_into_tensor(seg_all, seg_own)
+            mark("gather_frames")
+            votes, nms, state["next_id"] = do_assoc(state["next_id"])
+            state["n_matched"] = nms[-1]
+            mark("associate")
+            side.wait_event(enc_done)
+            mark("enc_wait")
+            dist.all_gather_into_tensor(feats_all, feats)
+            mark("gather_feats")
+            mask_row = torch.where(mask_ins >= 0, row0, -1)
+            fa = feats_all.view(-1, D)
+            sm.fuse_dense_batch(list(range(G)), bank, bank_lo, counts, fa, mask_row)
+            for g, (r, i) in enumerate(order):
+                sm.bank_update_mean(ibank, icounts, fa[r * F * M + i * M: r * F * M + (i + 1) * M], mask_ins[g])
+            mark("fuse")
+            # one mapped frame per rank and step: 76.8k new points, routed to the shards that own their voxels
+            rx, rid, ovf = sharding.route_new_points_fixed(new_pts[state["step"] % 4], new_ids, cap_dst)
+            state["overflow"] += ovf
+            slot = n0 + (state["step"] % ring_slots) * world * cap_dst
+            xyz_l[slot: slot + world * cap_dst] = rx
+            ins_l[slot: slot + world * cap_dst] = -1
+            mark("route_points")
+            feats.record_stream(side)
+            state["step"] += 1
+        return feats
+
+    # ---- the shards reproduce the single-GPU run: the same world*F keyframes against the WHOLE map on this GPU
+    xyz_f = torch.from_numpy(xyz).to(dev)
+    ins_f = torch.from_numpy(ins).to(dev)
+    sm_f = SemanticMap(dev)
+    with torch.cuda.stream(side):
+        raw_all = torch.empty(world, F, H, W, dtype=torch.float32, device=dev)
+        dist.all_gather_into_tensor(raw_all, depth_own)
+        dist.all_gather_into_tensor(seg_all, seg_own)
+        v_ref, nm_ref, nxt_ref = sm_f.associate_batch(xyz_f, ins_f, [raw_all[r, i] for r, i in order], segs, c2ws, K, 0, M, w2cs=w2cs)
+        for i in range(F):
+            sm.depth_filter(depth_own[i], out=depth_f_own[i])
+            sm.depth_range(depth_own[i], out=range_own[i])
+        dist.all_gather_into_tensor(depth_all, depth_f_own)
+        dist.all_gather_into_tensor(range_all, range_own)
+        v_sh, nm_sh, nxt_sh = do_assoc(0)
+    side.synchronize()
+    same = nxt_sh == nxt_ref and nm_sh == nm_ref and all((v_sh[g][k] == v_ref[g][k]).all() for g in range(G) for k in v_ref[g])
+    same = same and bool(torch.equal(ins_l[:n0], ins_f[torch.from_numpy(mine).to(dev)]))
+    flag = torch.tensor([0 if same else 1], device=dev)
+    dist.all_reduce(flag)
+    if flag.item() != 0:
+        raise RuntimeError(f"sharded association differs from the single-GPU run (rank {rank}: same={same})")
+    del xyz_f, ins_f, sm_f, raw_all
+    ins_l[:] = -1
+    state["next_id"] = 0
+
+    ms_total, launches = timed(step, args.steps, args.warmup, side)
+    ms_step = ms_total / args.steps
+    # ---- instrumented pass: CUDA events around each exchange on the side stream (max over ranks per class)
+    state["instrument"] = True
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    names = ["gather_frames", "associate", "enc_wait", "gather_feats", "fuse", "route_points"]
+    prev = "t0"
+    per = {}
+    for n in names:
+        per[n] = float(np.mean([ev[prev][j].elapsed_time(ev[n][j]) for j in range(len(ev[n]))]))
+        prev = n
+    state["instrument"] = False
+    t = torch.tensor([per[n] for n in names], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    per = {n: round(float(v), 4) for n, v in zip(names, t.tolist())}
+    # the vote exchange alone: G exchanges of one keyframe's table, back to back
+    tab = tables[: M * (state["next_id"] + 1) + 1]
+    def xchg():
+        for g in range(G):
+            if callable(exchange):
+                exchange(tab, g)
+            else:
+                dist.all_reduce(tab)
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            xchg()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(5):
+            xchg()
+        b.record()
+    torch.cuda.synchronize()
+    us_vote = a.elapsed_time(b) / 5 / G * 1e3
+    coll = {"gather_frames_ms": per["gather_frames"], "gather_frames_bytes": int(world * F * H * W * 8),
+            "associate_ms": per["associate"], "vote_exchange_us_each": round(us_vote, 2), "vote_exchanges_per_step": G,
+            "vote_exchange_ms_per_step": round(us_vote * G / 1e3, 4), "vote_table_bytes": int(tab.numel() * 4),
+            "vote_exchange": args.exchange, "gather_descriptors_ms": per["gather_feats"], "gather_descriptors_bytes": int(world * F * M * D * 4),
+            "fuse_ms": per["fuse"], "route_new_points_ms": per["route_points"], "route_new_points_bytes": int(world * cap_dst * 16),
+            "wait_for_encoder_ms": per["enc_wait"]}
+    exch = {"gather_frames": per["gather_frames"], "vote_exchange": us_vote * G / 1e3, "gather_descriptors": per["gather_feats"],
+            "route_new_points": per["route_points"]}
+    coll["limiting_collective"] = max(exch, key=exch.get)
+    coll["side_stream_ms_per_step"] = round(sum(per[n] for n in names if n != "enc_wait"), 4)
+    return {"ms_per_step": ms_step, "value": G / (ms_step / 1e3), "launches": launches, "collectives": coll,
+            "points_per_shard": int(n0), "ring_points": int(ring), "keyframes_per_step": G, "identical_to_single_gpu": True,
+            "new_point_overflow": int(state["overflow"].item()), "n_matched_last": int(state["n_matched"])}
 
 
 def run_sam_stage(args, dev, clip_fusion_ms_per_keyframe, tf_sus, how):
@@ -670,6 +892,9 @@ def main():
     ap.add_argument("--no-next-rows", action="store_true", help="skip the crop-descriptor / label-transfer stage reports")
     ap.add_argument("--profile-e2e", action="store_true", help="cProfile three e2e steps to stderr")
     ap.add_argument("--no-pipeline", action="store_true", help="do not overlap a step's fusion with the next step's encoder")
+    ap.add_argument("--exchange", default="nccl", choices=["nccl", "p2p"],
+                    help="vote-table exchange of the sharded map (N > 1): NCCL all-reduce per keyframe, or the fused device-side "
+                         "peer-memory exchange (ovo_b200/p2p.py)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", 0))

@@ -263,6 +263,10 @@ typedef struct {
   int depth_filter;         /* semantic.depth_filter */
   /* rgb/depth resolution fix-up (ovo.py:218-221): 0 = none, else u' = int((u+crop_edge)*ratio_w) */
   int has_ratio; float ratio_h, ratio_w; int crop_edge;
+  /* Batched calls only (NULL otherwise): depth_dev is ALREADY the map the points are matched against (the depth filter was run
+   * where the frame lives, ovo_depth_filter) and depth_range_dev -> f32 [2] = min / max of the RAW depth > 0 (ovo_depth_range),
+   * from which the frustum is built (ovo.py:209).  A sharded map gathers these instead of filtering every keyframe on every rank. */
+  const float* depth_range_dev;
 } ovo_frame;
 
 int ovo_map_create(ovo_map_t** out);
@@ -277,6 +281,9 @@ int ovo_map_reserve(ovo_map_t* map, int64_t max_points, int max_instances, int m
 /* geometry_utils.depth_filter (geometry_utils.py:92-96): 7x7 gaussian (sigma 2.5, reflect) high-pass;
  * |d - blur| > 0.05 -> -1. */
 int ovo_depth_filter(const float* depth_dev, int h, int w, float* out_dev, void* stream);
+/* min / max of the depth values > 0 (what compute_camera_frustum_corners takes from the raw depth, geometry_utils.py:110-111)
+ * -> range_out_dev f32 [2]. */
+int ovo_depth_range(const float* depth_dev, int64_t n, float* range_out_dev, void* stream);
 
 /* OVO._match_and_track_instances minus the Python bookkeeping (ovo.py:204-229, 240-282):
  * frustum cull (geometry_utils.py:99-129,252-277) + projection/depth match (:26-89) + seg lookup +
@@ -308,16 +315,39 @@ int ovo_map_associate_batch(ovo_map_t* map, const float* xyz_dev, int32_t* ins_i
                             int* n_matched_host, int32_t* mask_ins_out_dev, void* stream);
 /* The same batch in stages, for a map SHARDED over several GPUs: every rank runs begin on its own points, then
  * per keyframe f in order: ovo_map_batch_vote (votes of its points; *table_dev / *table_len = the keyframe's table
- * [n_masks x (n_ins+1) vote counts | n_matched] inside tables_dev) -> the ranks SUM that table (all-reduce, in place) ->
+ * [n_matched, 0, 0, 0 | n_masks x (n_ins+1) vote counts] inside tables_dev) -> the ranks SUM that table (all-reduce, in place) ->
  * ovo_map_batch_decide (identical decisions on every rank, next_ins_id stays on the device); ovo_map_batch_end assigns the
  * last keyframe's ids, reads all rows back and synchronises once.  tables_dev i32 [tables_cap] is caller-owned (NULL: a
- * workspace of the handle); it needs sum_f (max(n_masks_f,1) * (next_ins_id + sum_{g<f} n_masks_g + 1) + 4) ints. */
+ * workspace of the handle); it needs sum_f (4 + max(n_masks_f,1) * (next_ins_id + sum_{g<f} n_masks_g + 1), rounded up to 4) ints. */
 int ovo_map_batch_begin(ovo_map_t* map, const float* xyz_dev, const int32_t* ins_ids_dev, int64_t N, const ovo_frame* frames,
                         int n_frames, const int* kf_slots, int next_ins_id, int32_t* tables_dev, int64_t tables_cap, void* stream);
 int ovo_map_batch_vote(ovo_map_t* map, int f, int32_t* ins_ids_dev, int32_t** table_dev, int* table_len, void* stream);
 int ovo_map_batch_decide(ovo_map_t* map, int f, void* stream);
 int ovo_map_batch_end(ovo_map_t* map, int32_t* ins_ids_dev, int* next_ins_id, ovo_vote_row* votes_host, int votes_stride,
                       int* n_matched_host, int32_t* mask_ins_out_dev, void* stream);
+/* Keyframe f of the pending batch: its mask count and the DEVICE address of the batch's instance counter (n_ins). */
+int ovo_map_batch_info(ovo_map_t* map, int f, int* n_masks, const int32_t** n_ins_dev);
+
+/* Device-side exchange of the vote tables of a sharded map (one process per GPU of one box, peer memory over NVLink/NVSwitch):
+ * instead of a host-launched all-reduce per keyframe, ONE kernel per keyframe writes this rank's compact table into every
+ * peer's inbox (16-byte peer stores), raises a flag there (st.release.sys), waits for the flags of its own inbox and sums the
+ * world tables in place — the result is the same on every rank.  Set-up: every rank creates its exchange (slots = keyframes per
+ * batch, table_ints = largest table), publishes its 64-byte IPC handle (ovo_xchg_ipc_handle) to the others by any means
+ * (torch.distributed all_gather) and opens theirs (ovo_xchg_open_peers, handles [world][64] in rank order).  All ranks must
+ * call ovo_xchg_exchange in the same order with the same slot. */
+typedef struct ovo_xchg ovo_xchg_t;
+int ovo_xchg_create(int rank, int world, int slots, int64_t table_ints, ovo_xchg_t** out);
+int ovo_xchg_ipc_handle(ovo_xchg_t* x, void* handle_out_64);
+int ovo_xchg_open_peers(ovo_xchg_t* x, const void* handles_world_x_64);
+/* table_dev i32 [n_ints] (16-byte aligned) <- sum over the ranks.  n_ins_dev / n_masks (optional): only the first
+ * 4 + max(n_masks,1) * (*n_ins_dev + 1) ints travel (the layout of ovo_map_batch_vote's tables). */
+int ovo_xchg_exchange(ovo_xchg_t* x, int32_t* table_dev, int n_ints, const int32_t* n_ins_dev, int n_masks, int slot, void* stream);
+void ovo_xchg_destroy(ovo_xchg_t* x);
+/* ovo_map_associate_batch on a shard, the per-keyframe tables summed through `xchg`: the whole batch is one call. */
+int ovo_map_associate_batch_sharded(ovo_map_t* map, ovo_xchg_t* xchg, const float* xyz_dev, int32_t* ins_ids_dev, int64_t N,
+                                    const ovo_frame* frames, int n_frames, const int* kf_slots, int* next_ins_id,
+                                    ovo_vote_row* votes_host, int votes_stride, int* n_matched_host, int32_t* mask_ins_out_dev,
+                                    void* stream);
 /* Copies the matched list of a slot to the caller: pairs (point index, mask index), n from associate. */
 int ovo_map_get_matches(ovo_map_t* map, int kf_slot, int32_t* pairs_dev, int max_pairs, void* stream);
 

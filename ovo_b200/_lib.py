@@ -63,7 +63,7 @@ class Frame(C.Structure):
     _fields_ = [("depth_dev", c_void_p), ("h", c_int), ("w", c_int), ("seg_map_dev", c_void_p), ("H", c_int),
                 ("W", c_int), ("n_masks", c_int), ("c2w", c_float * 16), ("w2c", c_float * 16), ("K", c_float * 9),
                 ("match_th", c_float), ("track_th", c_int), ("depth_filter", c_int), ("has_ratio", c_int),
-                ("ratio_h", c_float), ("ratio_w", c_float), ("crop_edge", c_int)]
+                ("ratio_h", c_float), ("ratio_w", c_float), ("crop_edge", c_int), ("depth_range_dev", c_void_p)]
 
 
 class HieraBlock(C.Structure):
@@ -135,6 +135,7 @@ SIGNATURES = {
     "ovo_map_destroy": (None, [c_void_p]),
     "ovo_map_reserve": (c_int, [c_void_p, c_int64, c_int, c_int, c_int64]),
     "ovo_depth_filter": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "ovo_depth_range": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "ovo_map_associate": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, C.POINTER(Frame), C.POINTER(c_int),
                                   C.POINTER(VoteRow), C.POINTER(c_int), c_int, c_void_p]),
     "ovo_map_vote": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, C.POINTER(Frame), c_int, c_void_p, c_int, c_void_p]),
@@ -150,6 +151,14 @@ SIGNATURES = {
                                     c_int64, c_void_p]),
     "ovo_map_batch_vote": (c_int, [c_void_p, c_int, c_void_p, C.POINTER(c_void_p), C.POINTER(c_int), c_void_p]),
     "ovo_map_batch_decide": (c_int, [c_void_p, c_int, c_void_p]),
+    "ovo_map_batch_info": (c_int, [c_void_p, c_int, C.POINTER(c_int), C.POINTER(c_void_p)]),
+    "ovo_xchg_create": (c_int, [c_int, c_int, c_int, c_int64, C.POINTER(c_void_p)]),
+    "ovo_xchg_ipc_handle": (c_int, [c_void_p, c_void_p]),
+    "ovo_xchg_open_peers": (c_int, [c_void_p, c_void_p]),
+    "ovo_xchg_exchange": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p]),
+    "ovo_xchg_destroy": (None, [c_void_p]),
+    "ovo_map_associate_batch_sharded": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, C.POINTER(Frame), c_int, C.POINTER(c_int),
+                                                C.POINTER(c_int), C.POINTER(VoteRow), c_int, C.POINTER(c_int), c_void_p, c_void_p]),
     "ovo_map_batch_end": (c_int, [c_void_p, c_void_p, C.POINTER(c_int), C.POINTER(VoteRow), c_int, C.POINTER(c_int), c_void_p, c_void_p]),
     "ovo_bank_add_views": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "ovo_bank_update_mean": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p]),

@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libovo_b200.so")
-SOURCES = ["common.cu", "map.cu", "encoder.cu", "sam.cu", "knn.cu"]
+SOURCES = ["common.cu", "map.cu", "encoder.cu", "sam.cu", "knn.cu", "p2p.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 

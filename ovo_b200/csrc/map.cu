@@ -14,6 +14,7 @@
 
 #include "common.cuh"
 #include "gemm.cuh"
+#include "p2p.cuh"
 
 namespace ovo {
 
@@ -51,6 +52,21 @@ __global__ void depth_minmax_kernel(const float* __restrict__ depth, int n, Fram
     atomicMin(&g->dmin_bits, lmin);
     atomicMax(&g->dmax_bits, lmax);
   }
+}
+
+// positive floats order like their bit patterns: the range is reduced as two ints and IS the two floats
+__global__ void depth_range_init_kernel(int* r) { r[0] = 0x7f800000; r[1] = 0; }
+__global__ void depth_range_kernel(const float* __restrict__ depth, int n, int* __restrict__ r) {
+  int lmin = 0x7f800000, lmax = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float d = depth[i];
+    if (d > 0.f) { lmin = min(lmin, __float_as_int(d)); lmax = max(lmax, __float_as_int(d)); }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    lmin = min(lmin, __shfl_xor_sync(0xffffffffu, lmin, o));
+    lmax = max(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+  }
+  if ((threadIdx.x & 31) == 0) { atomicMin(&r[0], lmin); atomicMax(&r[1], lmax); }
 }
 
 __device__ __forceinline__ float dot4_rn(const float* m, float x, float y, float z) {
@@ -316,8 +332,7 @@ __global__ void vote_reduce_kernel(const int32_t* __restrict__ votes, int n_ins,
 
 // New ids are allocated in mask order (ovo.py:255,271-273): every mask decides in parallel, then an ordered
 // prefix sum over the "wants a new instance" flags hands out next_ins_id, next_ins_id+1, ...  One block.
-__global__ void __launch_bounds__(256)
-    vote_decide_kernel(ovo_vote_row* rows, int n_masks, int track_th, int32_t* mask_ins, int32_t* next_ins_id) {
+__device__ __forceinline__ void vote_decide_body(ovo_vote_row* rows, int n_masks, int track_th, int32_t* mask_ins, int32_t* next_ins_id) {
   __shared__ int s_warp[8];
   __shared__ int s_base;
   if (threadIdx.x == 0) s_base = *next_ins_id;
@@ -356,6 +371,42 @@ __global__ void __launch_bounds__(256)
   }
   if (threadIdx.x == 0) *next_ins_id = s_base;
 }
+__global__ void __launch_bounds__(256)
+    vote_decide_kernel(ovo_vote_row* rows, int n_masks, int track_th, int32_t* mask_ins, int32_t* next_ins_id) {
+  vote_decide_body(rows, n_masks, track_th, mask_ins, next_ins_id);
+}
+
+// Per-mask reduce + decisions by ONE block of 256 threads (a warp per mask): the tail of the batched vote.  votes
+// [n_masks][n_ins+1] was written by other blocks / other GPUs: read through L2.
+__device__ __forceinline__ void vote_finish_block(const int32_t* votes, int n_ins, int n_masks, const int32_t* __restrict__ area,
+                                                  ovo_vote_row* rows, int track_th, int32_t* mask_ins, int32_t* next_ins_id) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int m = warp; m < n_masks; m += nw) {
+    const int32_t* row = votes + static_cast<size_t>(m) * (n_ins + 1);
+    int best_cnt = 0, best_id = 0x7fffffff, total = 0;
+    for (int i = lane; i < n_ins; i += 32) {
+      const int c = __ldcg(row + 1 + i);
+      total += c;
+      if (c > best_cnt || (c == best_cnt && c > 0 && i < best_id)) { best_cnt = c; best_id = i; }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      const int oc = __shfl_xor_sync(0xffffffffu, best_cnt, o), oi = __shfl_xor_sync(0xffffffffu, best_id, o);
+      total += __shfl_xor_sync(0xffffffffu, total, o);
+      if (oc > best_cnt || (oc == best_cnt && oi < best_id)) { best_cnt = oc; best_id = oi; }
+    }
+    if (lane == 0) {
+      ovo_vote_row r;
+      r.n_unassigned = __ldcg(row);
+      r.n_assigned = total;
+      r.n_matched = total + r.n_unassigned;
+      r.mode_id = best_cnt > 0 ? best_id : -1;
+      r.ins_id = -1; r.is_new = 0; r.area = area[m]; r.reserved = 0;
+      rows[m] = r;
+    }
+  }
+  __syncthreads();
+  vote_decide_body(rows, n_masks, track_th, mask_ins, next_ins_id);
+}
 
 // ------------------------------------------------------------------------------------------ pass 2
 __global__ void associate_pass2_kernel(const int2* __restrict__ match_list, const int32_t* __restrict__ counters,
@@ -377,16 +428,24 @@ struct BatchFrame {
   FrameDev fr;
   FrameGeom geom;
   const float* depth_raw;     // frustum from the raw depth (ovo.py:209)
+  const float* range;         // optional [2]: min / max of the raw depth > 0 computed elsewhere (then depth_raw is not scanned)
   const float* depth_used;    // matching against the filtered depth (ovo.py:213-216)
   float* depth_filtered;      // workspace (nullptr: no filter)
   const int32_t* seg_map;
   int n_masks, track_th;
-  int votes_off;              // offset of this keyframe's vote table in the batch's table buffer (ints)
-  int nm_off;                 // offset of its n_matched counter (the int behind the table)
+  int votes_off;              // offset of this keyframe's table [n_matched, 0, 0, 0 | votes] in the batch's table buffer (ints)
+  int nm_off;                 // offset of its n_matched counter (the table's first int)
 };
 
 __global__ void batch_depth_minmax_kernel(BatchFrame* __restrict__ fr) {
   BatchFrame& b = fr[blockIdx.y];
+  if (b.range != nullptr) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      b.geom.dmin_bits = __float_as_int(b.range[0]);
+      b.geom.dmax_bits = __float_as_int(b.range[1]);
+    }
+    return;
+  }
   const int n = b.fr.h * b.fr.w;
   int lmin = 0x7f800000, lmax = 0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -511,10 +570,23 @@ __global__ void __launch_bounds__(kP1Threads)
 // Keyframe f of the batch: first give the points keyframe f-1 matched their new ids (its decisions are final), then vote.
 // One coalesced scan of the two dense rows and the ids, 8 points per thread (16-byte loads of the int16 rows: the rows are
 // padded to a multiple of 8 points); votes go to shared memory when the table fits.
+// Fused tail (tail.enabled): the LAST block to finish its share of the scan (ticket counter) goes on alone — on a sharded map it
+// pushes the table into every peer's inbox over NVLink, waits for theirs and sums (p2p.cuh), then reduces the votes per mask and
+// takes the id decisions: one launch per keyframe instead of scan + exchange + reduce + decide.
+struct VoteTail {
+  int enabled;
+  int32_t* done;                 // ticket counter (0 between launches)
+  int32_t* table;                // [n_matched, 0, 0, 0 | votes]
+  const int32_t* area; ovo_vote_row* rows; int32_t* mask_ins; int32_t* next_ins_id; int32_t* n_matched_out; int track_th;
+  int world, rank, slots, slot, parity, epoch; long long table_cap;
+  XchgPeers peers;
+};
+
 __global__ void __launch_bounds__(256)
     batch_vote_scan_kernel(const int16_t* __restrict__ seg_prev, const int32_t* __restrict__ mask_ins_prev,
                            const int16_t* __restrict__ seg_cur, int32_t* __restrict__ ins_ids, long long N,
-                           const int32_t* __restrict__ n_ins_ptr, int n_masks, int32_t* __restrict__ votes, int smem_ints) {
+                           const int32_t* __restrict__ n_ins_ptr, int n_masks, int32_t* __restrict__ votes, int smem_ints,
+                           const __grid_constant__ VoteTail tail) {
   extern __shared__ int32_t s_votes[];
   const int n_ins = *n_ins_ptr;
   const int n_votes = n_masks * (n_ins + 1);
@@ -555,14 +627,30 @@ __global__ void __launch_bounds__(256)
     for (int i = threadIdx.x; i < n_votes; i += blockDim.x)
       if (s_votes[i]) atomicAdd(&votes[i], s_votes[i]);
   }
+  if (!tail.enabled) return;
+  __shared__ int s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(tail.done, 1) == static_cast<int>(gridDim.x) - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (threadIdx.x == 0) *tail.done = 0;
+  if (tail.world > 1)
+    xchg_block(tail.peers, tail.rank, tail.world, tail.slots, tail.slot, tail.parity, tail.epoch, tail.table_cap, tail.table,
+               4 + max(n_masks, 1) * (n_ins + 1));
+  if (threadIdx.x == 0) *tail.n_matched_out = __ldcg(tail.table);
+  vote_finish_block(tail.table + 4, n_ins, n_masks, tail.area, tail.rows, tail.track_th, tail.mask_ins, tail.next_ins_id);
 }
 
-// vote_reduce_kernel with the instance count read from the device (the batch never brings it to the host)
-__global__ void batch_vote_reduce_kernel(const int32_t* __restrict__ votes, const int32_t* __restrict__ n_ins_ptr,
-                                         const int32_t* __restrict__ area, ovo_vote_row* __restrict__ rows,
-                                         const int32_t* __restrict__ n_matched_in, int32_t* __restrict__ n_matched_out) {
-  if (blockIdx.x == 0 && threadIdx.x == 0) *n_matched_out = *n_matched_in;   // the (summed) counter behind the table
-  vote_reduce_body(votes, *n_ins_ptr, area, rows);
+// the same tail alone (staged protocol: the table was summed by a host-launched collective; or an empty shard)
+__global__ void __launch_bounds__(256) batch_vote_finish_kernel(const __grid_constant__ VoteTail tail, int n_masks) {
+  const int n_ins = *tail.next_ins_id;
+  if (tail.world > 1)
+    xchg_block(tail.peers, tail.rank, tail.world, tail.slots, tail.slot, tail.parity, tail.epoch, tail.table_cap, tail.table,
+               4 + max(n_masks, 1) * (n_ins + 1));
+  if (threadIdx.x == 0) *tail.n_matched_out = __ldcg(tail.table);
+  vote_finish_block(tail.table + 4, n_ins, n_masks, tail.area, tail.rows, tail.track_th, tail.mask_ins, tail.next_ins_id);
 }
 
 // ------------------------------------------------------------------------------------------ dense fusion
@@ -1281,6 +1369,16 @@ void ovo_map_destroy(ovo_map_t* m) {
   delete m;
 }
 
+int ovo_depth_range(const float* depth_dev, int64_t n, float* range_out_dev, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  OVO_REQUIRE(depth_dev && range_out_dev && n > 0 && n < (1LL << 31), "ovo_depth_range: bad arguments");
+  ovo::depth_range_init_kernel<<<1, 1, 0, stream>>>(reinterpret_cast<int*>(range_out_dev));
+  OVO_CHECK_LAUNCH();
+  ovo::depth_range_kernel<<<32, 256, 0, stream>>>(depth_dev, static_cast<int>(n), reinterpret_cast<int*>(range_out_dev));
+  OVO_CHECK_LAUNCH();
+  return OVO_OK;
+}
+
 int ovo_depth_filter(const float* depth_dev, int h, int w, float* out_dev, void* stream) {
   OVO_REQUIRE(depth_dev && out_dev && h >= 4 && w >= 4, "ovo_depth_filter: bad arguments");
   dim3 b(32, 8), g(ovo::ceil_div(w, 32), ovo::ceil_div(h, 8));
@@ -1299,6 +1397,7 @@ static int associate_vote(ovo_map_t* m, const float* xyz_dev, const int32_t* ins
   OVO_REQUIRE(kf_slot >= 0 && kf_slot < ovo_map::kSlots, "ovo_map_associate: kf_slot out of range");
   OVO_REQUIRE(f->n_masks >= 0 && f->n_masks <= 8192, "ovo_map_associate: n_masks out of range");
   OVO_REQUIRE(f->depth_dev && f->seg_map_dev && f->h > 0 && f->w > 0 && f->H > 0 && f->W > 0, "ovo_map_associate: bad frame");
+  OVO_REQUIRE(f->depth_range_dev == nullptr, "ovo_map_associate: pre-filtered depth (depth_range_dev) is a feature of the batched calls");
   OVO_REQUIRE(N == 0 || (xyz_dev && ins_ids_dev), "ovo_map_associate: null map");
   const int n_masks = f->n_masks, n_ins = *next_ins_id;
   OVO_REQUIRE(n_ins >= 0, "ovo_map_associate: negative next_ins_id");
@@ -1471,15 +1570,16 @@ int ovo_map_batch_begin(ovo_map_t* m, const float* xyz_dev, const int32_t* ins_i
   OVO_TRY(grow(&m->bt_depth, &m->bt_depth_cap, static_cast<size_t>(F) * npix_max));
   const int64_t stride = ((N > 0 ? N : 1) + 7) & ~int64_t(7);   // rows padded to 8 points: 16-byte loads in the vote scan
   OVO_TRY(grow(&m->seg_dense, &m->seg_dense_cap, static_cast<size_t>(F) * static_cast<size_t>(stride)));
-  // vote tables: keyframe f may see up to next_ins_id + (masks of the keyframes before it) instances; each table is followed by
-  // one counter (the keyframe's n_matched) so that a sharded map sums both with one exchange
+  // vote tables: keyframe f may see up to next_ins_id + (masks of the keyframes before it) instances; each table starts with a
+  // 4-int header whose first int counts the keyframe's matched points, so that a sharded map sums both with one exchange (and
+  // only the compact front of the table, 4 + n_masks x (n_ins+1) ints, has to travel)
   m->bt_n_masks.assign(F, 0); m->bt_track_th.assign(F, 0); m->bt_votes_off.assign(F, 0); m->bt_table_len.assign(F, 0);
   m->bt_slots.assign(F, -1);
   size_t off = 0;
   int bound = next_ins_id;
   for (int f = 0; f < F; ++f) {
     const int nm = frames[f].n_masks;
-    const size_t len = static_cast<size_t>(nm > 0 ? nm : 1) * (bound + 1) + 1;
+    const size_t len = 4 + static_cast<size_t>(nm > 0 ? nm : 1) * (bound + 1);
     OVO_REQUIRE(len < (1ull << 28), "ovo_map_batch_begin: vote table too large (%d masks x %d instances)", nm, bound);
     m->bt_n_masks[f] = nm; m->bt_track_th[f] = frames[f].track_th; m->bt_votes_off[f] = static_cast<int>(off);
     m->bt_table_len[f] = static_cast<int>(len);
@@ -1510,10 +1610,12 @@ int ovo_map_batch_begin(ovo_map_t* m, const float* xyz_dev, const int32_t* ins_i
     b.fr.has_ratio = fr.has_ratio; b.fr.ratio_h = fr.ratio_h; b.fr.ratio_w = fr.ratio_w; b.fr.crop_edge = fr.crop_edge;
     b.geom.dmin_bits = 0x7f800000; b.geom.dmax_bits = 0;
     b.depth_raw = fr.depth_dev;
-    b.depth_filtered = fr.depth_filter ? m->bt_depth + static_cast<size_t>(f) * npix_max : nullptr;
-    b.depth_used = fr.depth_filter ? b.depth_filtered : fr.depth_dev;
+    b.range = fr.depth_range_dev;
+    const bool filter_here = fr.depth_filter && fr.depth_range_dev == nullptr;
+    b.depth_filtered = filter_here ? m->bt_depth + static_cast<size_t>(f) * npix_max : nullptr;
+    b.depth_used = filter_here ? b.depth_filtered : fr.depth_dev;
     b.seg_map = fr.seg_map_dev; b.n_masks = fr.n_masks; b.track_th = fr.track_th; b.votes_off = m->bt_votes_off[f];
-    b.nm_off = m->bt_votes_off[f] + m->bt_table_len[f] - 1;
+    b.nm_off = m->bt_votes_off[f];
     h_nm[f] = 0;
   }
   h_next[0] = next_ins_id; h_next[1] = h_next[2] = h_next[3] = 0;
@@ -1547,28 +1649,63 @@ int ovo_map_batch_begin(ovo_map_t* m, const float* xyz_dev, const int32_t* ins_i
   return OVO_OK;
 }
 
-// votes of keyframe f on this handle's points (after applying the decisions of keyframe f-1); *table_dev / *table_len = the
-// keyframe's vote table [n_masks x (n_ins+1) | n_matched] inside the batch's table buffer, to be summed over shards
-int ovo_map_batch_vote(ovo_map_t* m, int f, int32_t* ins_ids_dev, int32_t** table_dev, int* table_len, void* stream_) {
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  OVO_REQUIRE(m && m->bt_valid && f >= 0 && f < m->bt_F, "ovo_map_batch_vote: no batch pending or keyframe %d out of range", f);
+static ovo::VoteTail make_tail(ovo_map* m, int f, ovo_xchg* x) {
+  const BatchCtl L(m->bt_fcap, m->bt_stride);
+  ovo::VoteTail t;
+  memset(&t, 0, sizeof(t));
+  t.enabled = 1;
+  t.done = reinterpret_cast<int32_t*>(m->bctl + L.next) + 2;     // zeroed by the upload of ovo_map_batch_begin, reset by every tail
+  t.table = m->bt_user_tables + m->bt_votes_off[f];
+  t.area = m->bt_area + static_cast<size_t>(f) * m->bt_stride;
+  t.rows = reinterpret_cast<ovo_vote_row*>(m->bctl + L.rows) + static_cast<size_t>(f) * m->bt_stride;
+  t.mask_ins = m->bt_mask_ins + static_cast<size_t>(f) * m->bt_stride;
+  t.next_ins_id = reinterpret_cast<int32_t*>(m->bctl + L.next);
+  t.n_matched_out = reinterpret_cast<int32_t*>(m->bctl + L.n_matched) + f;
+  t.track_th = m->bt_track_th[f];
+  t.world = 1;
+  if (x != nullptr && x->world > 1) {
+    const int epoch = ++(*x->epochs)[f];
+    t.world = x->world; t.rank = x->rank; t.slots = x->slots; t.slot = f; t.parity = epoch & 1; t.epoch = epoch;
+    t.table_cap = x->table_cap; t.peers = x->peers;
+  }
+  return t;
+}
+
+// scan of keyframe f (ids of keyframe f-1 first, then its votes); tail != nullptr: the fused exchange + decisions follow in the
+// same launch
+static int batch_scan(ovo_map_t* m, int f, int32_t* ins_ids_dev, const ovo::VoteTail* tail, cudaStream_t stream) {
   const BatchCtl L(m->bt_fcap, m->bt_stride);
   const int64_t N = m->bt_N;
   int32_t* table = m->bt_user_tables + m->bt_votes_off[f];
   const int len = m->bt_table_len[f];
   const int32_t* d_next = reinterpret_cast<const int32_t*>(m->bctl + L.next);
+  ovo::VoteTail none;
+  memset(&none, 0, sizeof(none));
   if (N > 0) {
     const size_t st = static_cast<size_t>(m->dense_stride);
     const int16_t* prev = f > 0 ? m->seg_dense + static_cast<size_t>(f - 1) * st : nullptr;
     const int32_t* mi_prev = f > 0 ? m->bt_mask_ins + static_cast<size_t>(f - 1) * m->bt_stride : nullptr;
-    const int smem_ints = std::min(len - 1, 10 * 1024);   // up to 40 KB of shared-memory votes
+    const int smem_ints = std::min(len - 4, 10 * 1024);   // up to 40 KB of shared-memory votes
     const int blocks = static_cast<int>(std::min<long long>(((N + 7) / 8 + 255) / 256, ovo::num_sms() * 8LL));
     ovo::batch_vote_scan_kernel<<<blocks, 256, smem_ints * sizeof(int32_t), stream>>>(prev, mi_prev, m->seg_dense + static_cast<size_t>(f) * st,
-                                                                                    ins_ids_dev, N, d_next, m->bt_n_masks[f], table, smem_ints);
+                                                                                    ins_ids_dev, N, d_next, m->bt_n_masks[f], table + 4, smem_ints,
+                                                                                    tail ? *tail : none);
+    OVO_CHECK_LAUNCH();
+  } else if (tail) {   // an empty shard still takes part in the exchange and takes the decisions
+    ovo::batch_vote_finish_kernel<<<1, 256, 0, stream>>>(*tail, m->bt_n_masks[f]);
     OVO_CHECK_LAUNCH();
   }
-  if (table_dev) *table_dev = table;
-  if (table_len) *table_len = len;
+  return OVO_OK;
+}
+
+// votes of keyframe f on this handle's points (after applying the decisions of keyframe f-1); *table_dev / *table_len = the
+// keyframe's table [n_matched, 0, 0, 0 | n_masks x (n_ins+1) votes] inside the batch's table buffer, to be summed over shards
+int ovo_map_batch_vote(ovo_map_t* m, int f, int32_t* ins_ids_dev, int32_t** table_dev, int* table_len, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  OVO_REQUIRE(m && m->bt_valid && f >= 0 && f < m->bt_F, "ovo_map_batch_vote: no batch pending or keyframe %d out of range", f);
+  OVO_TRY(batch_scan(m, f, ins_ids_dev, nullptr, stream));
+  if (table_dev) *table_dev = m->bt_user_tables + m->bt_votes_off[f];
+  if (table_len) *table_len = m->bt_table_len[f];
   return OVO_OK;
 }
 
@@ -1576,22 +1713,9 @@ int ovo_map_batch_vote(ovo_map_t* m, int f, int32_t* ins_ids_dev, int32_t** tabl
 int ovo_map_batch_decide(ovo_map_t* m, int f, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   OVO_REQUIRE(m && m->bt_valid && f >= 0 && f < m->bt_F, "ovo_map_batch_decide: no batch pending or keyframe %d out of range", f);
-  const BatchCtl L(m->bt_fcap, m->bt_stride);
-  const int nm = m->bt_n_masks[f];
-  int32_t* table = m->bt_user_tables + m->bt_votes_off[f];
-  int32_t* d_next = reinterpret_cast<int32_t*>(m->bctl + L.next);
-  ovo_vote_row* rows = reinterpret_cast<ovo_vote_row*>(m->bctl + L.rows) + static_cast<size_t>(f) * m->bt_stride;
-  int32_t* mask_ins = m->bt_mask_ins + static_cast<size_t>(f) * m->bt_stride;
-  int32_t* nm_out = reinterpret_cast<int32_t*>(m->bctl + L.n_matched) + f;
-  if (nm > 0) {
-    ovo::batch_vote_reduce_kernel<<<nm, 128, 0, stream>>>(table, d_next, m->bt_area + static_cast<size_t>(f) * m->bt_stride, rows,
-                                                         table + m->bt_table_len[f] - 1, nm_out);
-    OVO_CHECK_LAUNCH();
-    ovo::vote_decide_kernel<<<1, 256, 0, stream>>>(rows, nm, m->bt_track_th[f], mask_ins, d_next);
-    OVO_CHECK_LAUNCH();
-  } else {
-    OVO_CUDA(cudaMemcpyAsync(nm_out, table + m->bt_table_len[f] - 1, sizeof(int32_t), cudaMemcpyDeviceToDevice, stream));
-  }
+  const ovo::VoteTail t = make_tail(m, f, nullptr);
+  ovo::batch_vote_finish_kernel<<<1, 256, 0, stream>>>(t, m->bt_n_masks[f]);
+  OVO_CHECK_LAUNCH();
   return OVO_OK;
 }
 
@@ -1610,7 +1734,7 @@ int ovo_map_batch_end(ovo_map_t* m, int32_t* ins_ids_dev, int* next_ins_id, ovo_
     const int blocks = static_cast<int>(std::min<long long>(((N + 7) / 8 + 255) / 256, ovo::num_sms() * 8LL));
     ovo::batch_vote_scan_kernel<<<blocks, 256, 0, stream>>>(m->seg_dense + static_cast<size_t>(F - 1) * static_cast<size_t>(m->dense_stride),
                                                            m->bt_mask_ins + static_cast<size_t>(F - 1) * m->bt_stride, nullptr, ins_ids_dev, N,
-                                                           reinterpret_cast<const int32_t*>(m->bctl + L.next), 0, nullptr, 0);
+                                                           reinterpret_cast<const int32_t*>(m->bctl + L.next), 0, nullptr, 0, ovo::VoteTail{});
     OVO_CHECK_LAUNCH();
   }
   if (mask_ins_out_dev)
@@ -1635,6 +1759,41 @@ int ovo_map_batch_end(ovo_map_t* m, int32_t* ins_ids_dev, int* next_ins_id, ovo_
   return OVO_OK;
 }
 
+int ovo_map_batch_info(ovo_map_t* m, int f, int* n_masks, const int32_t** n_ins_dev) {
+  OVO_REQUIRE(m && m->bt_valid && f >= 0 && f < m->bt_F, "ovo_map_batch_info: no batch pending or keyframe %d out of range", f);
+  const BatchCtl L(m->bt_fcap, m->bt_stride);
+  if (n_masks) *n_masks = m->bt_n_masks[f];
+  if (n_ins_dev) *n_ins_dev = reinterpret_cast<const int32_t*>(m->bctl + L.next);
+  return OVO_OK;
+}
+
+// all keyframes of the batch, ONE launch each: scan + (device-side exchange over the shards) + decisions
+static int batch_run_fused(ovo_map_t* m, ovo_xchg* xchg, int32_t* ins_ids_dev, cudaStream_t stream) {
+  for (int f = 0; f < m->bt_F; ++f) {
+    const ovo::VoteTail t = make_tail(m, f, xchg);
+    const int r = batch_scan(m, f, ins_ids_dev, &t, stream);
+    if (r != OVO_OK) { m->bt_valid = false; return r; }
+  }
+  return OVO_OK;
+}
+
+int ovo_map_associate_batch_sharded(ovo_map_t* m, ovo_xchg_t* xchg, const float* xyz_dev, int32_t* ins_ids_dev, int64_t N,
+                                    const ovo_frame* frames, int F, const int* kf_slots, int* next_ins_id, ovo_vote_row* votes_host,
+                                    int votes_stride, int* n_matched_host, int32_t* mask_ins_out_dev, void* stream_) {
+  OVO_REQUIRE(xchg && next_ins_id && votes_host && n_matched_host, "ovo_map_associate_batch_sharded: null argument");
+  OVO_REQUIRE(F <= xchg->slots, "ovo_map_associate_batch_sharded: %d keyframes but the exchange has %d slots", F, xchg->slots);
+  for (int r = 0; r < xchg->world; ++r) OVO_REQUIRE(xchg->peers.inbox[r] != nullptr, "ovo_map_associate_batch_sharded: peer %d not opened", r);
+  OVO_TRY(ovo_map_batch_begin(m, xyz_dev, ins_ids_dev, N, frames, F, kf_slots, *next_ins_id, nullptr, 0, stream_));
+  for (int f = 0; f < F; ++f)
+    if (m->bt_table_len[f] > xchg->table_cap) {
+      m->bt_valid = false;
+      return ovo::set_error(OVO_E_INVALID, "ovo_map_associate_batch_sharded: table of keyframe %d (%d ints) exceeds the exchange's %lld", f,
+                            m->bt_table_len[f], xchg->table_cap);
+    }
+  OVO_TRY(batch_run_fused(m, xchg, ins_ids_dev, static_cast<cudaStream_t>(stream_)));
+  return ovo_map_batch_end(m, ins_ids_dev, next_ins_id, votes_host, votes_stride, n_matched_host, mask_ins_out_dev, stream_);
+}
+
 int ovo_map_associate_batch(ovo_map_t* m, const float* xyz_dev, int32_t* ins_ids_dev, int64_t N, const ovo_frame* frames, int F,
                             const int* kf_slots, int* next_ins_id, ovo_vote_row* votes_host, int votes_stride, int* n_matched_host,
                             int32_t* mask_ins_out_dev, void* stream_) {
@@ -1644,11 +1803,7 @@ int ovo_map_associate_batch(ovo_map_t* m, const float* xyz_dev, int32_t* ins_ids
   for (int f = 0; frames && f < F; ++f) px += static_cast<double>(frames[f].h) * frames[f].w * 8;
   ovo::ProfScope prof(stream, ovo::PROF_ASSOC, 0.0, static_cast<double>(N) * (12.0 + F * 14.0) + px);
   OVO_TRY(ovo_map_batch_begin(m, xyz_dev, ins_ids_dev, N, frames, F, kf_slots, *next_ins_id, nullptr, 0, stream_));
-  for (int f = 0; f < F; ++f) {
-    int r = ovo_map_batch_vote(m, f, ins_ids_dev, nullptr, nullptr, stream_);
-    if (r == OVO_OK) r = ovo_map_batch_decide(m, f, stream_);
-    if (r != OVO_OK) { m->bt_valid = false; return r; }
-  }
+  OVO_TRY(batch_run_fused(m, nullptr, ins_ids_dev, stream));
   return ovo_map_batch_end(m, ins_ids_dev, next_ins_id, votes_host, votes_stride, n_matched_host, mask_ins_out_dev, stream_);
 }
 

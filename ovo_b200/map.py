@@ -40,11 +40,21 @@ class SemanticMap:
         with torch.cuda.device(self.device):
             check(self.lib.ovo_map_reserve(self.handle, int(points), int(instances), int(masks), int(matches)), "ovo_map_reserve")
 
-    def depth_filter(self, depth: torch.Tensor) -> torch.Tensor:
+    def depth_filter(self, depth: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
         """geometry_utils.depth_filter (geometry_utils.py:92-96)."""
         depth = depth.to(self.device, torch.float32).contiguous()
-        out = torch.empty_like(depth)
+        if out is None:
+            out = torch.empty_like(depth)
+        assert out.is_contiguous() and out.shape == depth.shape and out.dtype == torch.float32
         check(self.lib.ovo_depth_filter(ptr(depth), depth.shape[0], depth.shape[1], ptr(out), stream_ptr(self.device)), "ovo_depth_filter")
+        return out
+
+    def depth_range(self, depth: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+        """[min, max] of the depth values > 0 (the raw-depth range the frustum is built from), f32 [2] on the device."""
+        depth = depth.to(self.device, torch.float32).contiguous()
+        if out is None:
+            out = torch.empty(2, device=self.device, dtype=torch.float32)
+        check(self.lib.ovo_depth_range(ptr(depth), depth.numel(), ptr(out), stream_ptr(self.device)), "ovo_depth_range")
         return out
 
     def associate(self, xyz: torch.Tensor, ins_ids: torch.Tensor, depth: torch.Tensor, seg_map: torch.Tensor,
@@ -86,11 +96,12 @@ class SemanticMap:
             w2c = torch.linalg.inv(torch.from_numpy(c2w)).numpy()
         K = np.asarray(K, np.float32).reshape(3, 3)
         f = Frame()
-        f.depth_dev = ptr(depth); f.h, f.w = depth.shape
-        f.seg_map_dev = ptr(seg_map); f.H, f.W = seg_map.shape
+        f.depth_dev = depth.data_ptr(); f.h, f.w = depth.shape
+        f.seg_map_dev = seg_map.data_ptr(); f.H, f.W = seg_map.shape
         f.n_masks = n_masks
-        f.c2w[:] = c2w.reshape(-1).tolist(); f.w2c[:] = np.asarray(w2c, np.float32).reshape(-1).tolist()
-        f.K[:] = K.reshape(-1).tolist()
+        C.memmove(f.c2w, np.ascontiguousarray(c2w).ctypes.data, 64)
+        C.memmove(f.w2c, np.ascontiguousarray(w2c, np.float32).ctypes.data, 64)
+        C.memmove(f.K, np.ascontiguousarray(K).ctypes.data, 36)
         f.match_th, f.track_th, f.depth_filter = float(match_th), int(track_th), int(bool(depth_filter))
         if len(rgb_depth_ratio) > 0:
             f.has_ratio, f.ratio_h, f.ratio_w, f.crop_edge = 1, float(rgb_depth_ratio[0]), float(rgb_depth_ratio[1]), int(rgb_depth_ratio[2])
@@ -122,7 +133,9 @@ class SemanticMap:
         return buf[:n]
 
     # ---- several keyframes in one pass over the map (ovo_map_associate_batch)
-    def _frames(self, depths, seg_maps, c2ws, K, n_masks, match_th, track_th, depth_filter, rgb_depth_ratio, w2cs):
+    def _frames(self, depths, seg_maps, c2ws, K, n_masks, match_th, track_th, depth_filter, rgb_depth_ratio, w2cs, depth_ranges=None):
+        """depth_ranges (optional, list of F device tensors f32 [2]): `depths` are already filtered (depth_filter(...)) and these
+        are the raw depths' [min, max] (depth_range(...)): a sharded map gathers them instead of filtering on every rank."""
         F = len(depths)
         arr = (Frame * F)()
         for i in range(F):
@@ -131,11 +144,13 @@ class SemanticMap:
             nm = n_masks[i] if not isinstance(n_masks, int) else n_masks
             arr[i] = self._frame(depths[i], seg_maps[i], c2ws[i], K, match_th, track_th, depth_filter, rgb_depth_ratio, int(nm),
                                  None if w2cs is None else w2cs[i])
+            if depth_ranges is not None:
+                arr[i].depth_range_dev = depth_ranges[i].data_ptr()
         return arr
 
     def associate_batch(self, xyz: torch.Tensor, ins_ids: torch.Tensor, depths, seg_maps, c2ws, K, next_ins_id: int, n_masks,
                         match_th: float = 0.05, track_th: int = 100, depth_filter: bool = True, rgb_depth_ratio=(), kf_slots=None,
-                        w2cs=None, mask_ins_out: torch.Tensor | None = None):
+                        w2cs=None, mask_ins_out: torch.Tensor | None = None, depth_ranges=None):
         """F keyframes against the map in one pass over xyz, id decisions on the device, ONE host synchronisation; the same
         results as F consecutive `associate` calls.  depths / seg_maps / c2ws: lists of F; n_masks: int or list.
         Returns (list of F votes dicts, list of F n_matched, next_ins_id); `mask_ins_out` i32 [F, stride] (optional, device)
@@ -143,7 +158,7 @@ class SemanticMap:
         assert xyz.is_cuda and ins_ids.is_cuda and xyz.dtype == torch.float32 and ins_ids.dtype == torch.int32
         assert xyz.is_contiguous() and ins_ids.is_contiguous()
         F = len(depths)
-        frames = self._frames(depths, seg_maps, c2ws, K, n_masks, match_th, track_th, depth_filter, rgb_depth_ratio, w2cs)
+        frames = self._frames(depths, seg_maps, c2ws, K, n_masks, match_th, track_th, depth_filter, rgb_depth_ratio, w2cs, depth_ranges)
         nms = [int(frames[i].n_masks) for i in range(F)]
         stride = max(max(nms), 1) if mask_ins_out is None else int(mask_ins_out.shape[1])
         assert mask_ins_out is None or (mask_ins_out.dtype == torch.int32 and mask_ins_out.shape[0] >= F and mask_ins_out.is_contiguous() and stride >= max(nms))
@@ -158,9 +173,9 @@ class SemanticMap:
 
     # the same batch in stages, for a map sharded over ranks: begin -> per keyframe (vote -> all-reduce of the table -> decide) -> end
     def batch_begin(self, xyz, ins_ids, depths, seg_maps, c2ws, K, next_ins_id: int, n_masks, tables: torch.Tensor, match_th=0.05,
-                    track_th=100, depth_filter=True, rgb_depth_ratio=(), kf_slots=None, w2cs=None):
+                    track_th=100, depth_filter=True, rgb_depth_ratio=(), kf_slots=None, w2cs=None, depth_ranges=None):
         F = len(depths)
-        frames = self._frames(depths, seg_maps, c2ws, K, n_masks, match_th, track_th, depth_filter, rgb_depth_ratio, w2cs)
+        frames = self._frames(depths, seg_maps, c2ws, K, n_masks, match_th, track_th, depth_filter, rgb_depth_ratio, w2cs, depth_ranges)
         assert tables.is_cuda and tables.dtype == torch.int32 and tables.is_contiguous()
         slots = None if kf_slots is None else (C.c_int * F)(*[int(x) for x in kf_slots])
         check(self.lib.ovo_map_batch_begin(self.handle, ptr(xyz), ptr(ins_ids), xyz.shape[0], frames, F, slots, int(next_ins_id),
@@ -195,7 +210,7 @@ class SemanticMap:
         """ints `tables` needs for a batch whose keyframes have n_masks[f] masks (ovo_map_batch_begin)."""
         n, bound = 0, int(next_ins_id)
         for nm in n_masks:
-            n += (max(int(nm), 1) * (bound + 1) + 1 + 3) // 4 * 4
+            n += (4 + max(int(nm), 1) * (bound + 1) + 3) // 4 * 4
             bound += int(nm)
         return n
 

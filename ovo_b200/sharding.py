@@ -50,6 +50,31 @@ class ShardedAssociation:
         return self.backend.apply(table, next_ins_id=next_ins_id)
 
 
+class ShardedBatchAssociation:
+    """A BATCH of keyframes against a map sharded over the ranks of `group` (ovo_map_batch_*): one pass over this rank's
+    points for all keyframes, then per keyframe (in order) votes -> SUM of the vote tables over the ranks -> decisions; the
+    instance count stays on the device, so the whole batch costs one host synchronisation.  `backend` needs
+    batch_begin / batch_vote(f) -> table view / batch_decide(f) / batch_end (ovo_b200.map.SemanticMap; the CPU tests use a
+    numpy backend).  `exchange`: "nccl" = one all-reduce per keyframe on the current stream; a callable(table, f) replaces it
+    (the fused device-side exchange of ovo_b200.p2p)."""
+
+    def __init__(self, backend, group=None, exchange="nccl"):
+        self.backend, self.group, self.exchange = backend, group, exchange
+
+    def associate(self, *begin_args, n_frames: int, mask_ins_out=None, **begin_kwargs):
+        self.backend.batch_begin(*begin_args, **begin_kwargs)
+        multi = dist.is_initialized() and dist.get_world_size(self.group) > 1
+        for f in range(n_frames):
+            table = self.backend.batch_vote(f)
+            if multi:
+                if callable(self.exchange):
+                    self.exchange(table, f)
+                else:
+                    dist.all_reduce(table, op=dist.ReduceOp.SUM, group=self.group)     # the one exchange per keyframe
+            self.backend.batch_decide(f)
+        return self.backend.batch_end(mask_ins_out=mask_ins_out) if mask_ins_out is not None else self.backend.batch_end()
+
+
 def gather_descriptors(local_feats: torch.Tensor, counts_per_rank, group=None) -> torch.Tensor:
     """All-gather of the region descriptors computed by each rank (variable row counts) -> [sum, D] on every rank."""
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
@@ -95,3 +120,31 @@ def route_new_points(xyz: torch.Tensor, ids: torch.Tensor, colors: torch.Tensor 
         p = out[:, 4].contiguous().view(torch.int32)
         ocol = torch.stack([p & 255, (p >> 8) & 255, (p >> 16) & 255], dim=1).to(torch.uint8)
     return oxyz, oids, ocol
+
+
+def route_new_points_fixed(xyz: torch.Tensor, ids: torch.Tensor, cap_per_dst: int, group=None, cell: float = 0.25,
+                           far: float = 1.0e6):
+    """route_new_points without a host synchronisation: every rank sends exactly `cap_per_dst` 16-byte records (xyz f32x3,
+    id i32) to every rank — its points of that shard in creation order, the rest padded with a far-away sentinel (id -1) that
+    no frustum ever contains.  Returns (xyz [world*cap,3], ids [world*cap], overflow flag tensor: > 0 if some shard received
+    more than cap_per_dst points from one source and dropped the surplus — size cap_per_dst with a margin over n/world)."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    dst = shard_of_points(xyz, world, cell)
+    order = torch.argsort(dst, stable=True)
+    sdst = dst[order]
+    first = torch.searchsorted(sdst, torch.arange(world, device=xyz.device, dtype=sdst.dtype))
+    pos = torch.arange(xyz.shape[0], device=xyz.device) - first[sdst]            # position inside its destination's run
+    keep = pos < cap_per_dst
+    overflow = (~keep).sum()
+    rec = torch.full((world * cap_per_dst, 4), far, dtype=torch.float32, device=xyz.device)
+    rec[:, 3] = torch.full((world * cap_per_dst,), -1, dtype=torch.int32, device=xyz.device).view(torch.float32)
+    slot = (sdst * cap_per_dst + pos)[keep]
+    src = order[keep]
+    rec[slot, :3] = xyz[src]
+    rec[slot, 3] = ids[src].to(torch.int32).view(torch.float32)
+    if world > 1:
+        out = torch.empty_like(rec)
+        dist.all_to_all_single(out, rec, group=group)
+    else:
+        out = rec
+    return out[:, :3].contiguous(), out[:, 3].contiguous().view(torch.int32), overflow

@@ -164,3 +164,93 @@ def test_new_points_are_routed_to_their_shard_world2():
         assert (oxyz.view(np.int32) == np.concatenate(exp_xyz).view(np.int32)).all()      # bit-exact coordinates
         assert (oids == np.concatenate(exp_ids)).all() and (ocol == np.concatenate(exp_col)).all()
     assert sum(len(r[5]) for r in res) == sum(len(r[2]) for r in res)
+
+
+# ---------------------------------------------------------------------------------------------- batch protocol (round 2)
+class NumpyBatchBackend:
+    """batch_begin / batch_vote / batch_decide / batch_end (ovo_map_batch_*) with the oracle's arithmetic: the geometry of every
+    keyframe first, then per keyframe votes on the current ids -> (summed) table -> decisions applied to this shard."""
+
+    def batch_begin(self, xyz, ins, frames, K, next_ins_id):
+        self.ins, self.frames, self.nxt = ins.copy(), frames, next_ins_id
+        self.segs = []
+        for depth, seg, c2w in frames:
+            w2c = torch.linalg.inv(torch.from_numpy(c2w)).numpy()
+            sp, _ = OF.associate(xyz, ins, depth, seg, c2w, w2c, K, 0.05, True) if len(xyz) else (np.zeros(0, np.int32), None)
+            self.segs.append(sp)
+        self.rows = []
+
+    def batch_vote(self, f):
+        seg = self.frames[f][1]
+        self.n_masks = int(seg.max()) + 1
+        t = OF.vote_table(self.ins, self.segs[f], self.n_masks, self.nxt)
+        self.table = torch.from_numpy(np.concatenate([t.reshape(-1), [(self.segs[f] > -2).sum()]]).astype(np.int32))
+        return self.table
+
+    def batch_decide(self, f):
+        seg = self.frames[f][1]
+        t = self.table.numpy()
+        areas = np.array([(seg == m).sum() for m in range(self.n_masks)])
+        rows, self.nxt = OF.decide_from_table(t[:-1].reshape(self.n_masks, -1), areas, 100, self.nxt)
+        self.ins = OF.apply_decisions(self.ins, self.segs[f], rows)
+        self.rows.append((rows, int(t[-1])))
+
+    def batch_end(self):
+        return self.rows, self.ins, self.nxt
+
+
+def _batch_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from ovo_b200.sharding import ShardedBatchAssociation, route_new_points_fixed
+    K, xyz, ins, frames = _scene()
+    mine = shard_of_points(xyz, world) == rank
+    sa = ShardedBatchAssociation(NumpyBatchBackend())
+    rows, lins, nxt = sa.associate(xyz[mine], ins[mine], frames, K, 0, n_frames=len(frames))
+    # fixed-size routing of new points (no host synchronisation: padded records)
+    rng = np.random.default_rng(200 + rank)
+    n = 3000
+    nx = torch.from_numpy(rng.uniform(-4, 4, (n, 3)).astype(np.float32))
+    ni = torch.arange(n, dtype=torch.int32) + 10_000 * rank
+    ox, oi, ovf = route_new_points_fixed(nx, ni, cap_per_dst=2000)
+    ox2, oi2, ovf2 = route_new_points_fixed(nx, ni, cap_per_dst=1000)     # too small on purpose: the surplus is counted
+    q.put((rank, np.nonzero(mine)[0], lins, [([r["ins_id"] for r in rr], nm) for rr, nm in rows], nxt, nx.numpy(), ni.numpy(),
+           ox.numpy(), oi.numpy(), int(ovf), int(ovf2), int((oi2 >= 0).sum())))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_batch_association_and_fixed_routing_world2():
+    """The batched protocol (one geometry pass, per keyframe vote -> all-reduce -> decide) gives every shard the ids and rows
+    of the unsharded oracle; route_new_points_fixed delivers every new point to its owner, padded with sentinels."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_batch_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=180) for _ in range(world)], key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    K, xyz, ins, frames = _scene()
+    nxt, ref = 0, []
+    for depth, seg, c2w in frames:
+        w2c = torch.linalg.inv(torch.from_numpy(c2w)).numpy()
+        sp, _ = OF.associate(xyz, ins, depth, seg, c2w, w2c, K, 0.05, True)
+        ins, rows, nxt = OF.track(ins, sp, seg, 100, nxt)
+        ref.append(([r["ins_id"] for r in rows], int((sp > -2).sum())))
+    merged = np.full(len(xyz), -99, np.int32)
+    for rank, idx, lins, log, n, *_ in res:
+        merged[idx] = lins
+        assert log == ref and n == nxt
+    assert (merged == ins).all()
+    for rank, *_ in res:
+        ox, oi, ovf, ovf2, kept2 = res[rank][7], res[rank][8], res[rank][9], res[rank][10], res[rank][11]
+        assert ovf == 0 and ovf2 > 0 and kept2 <= world * 1000
+        real = oi >= 0
+        assert (shard_of_points(ox[real], world) == rank).all() and (ox[~real] > 1e5).all()
+        exp = np.concatenate([res[s][6][shard_of_points(res[s][5], world) == rank] for s in range(world)])
+        assert (oi[real] == exp).all()                           # source-rank major, creation order inside
+    assert sum(int((r[8] >= 0).sum()) for r in res) == sum(len(r[6]) for r in res)
