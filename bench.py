@@ -143,15 +143,17 @@ def run_ours(args, rank, world, local_rank):
         feats = enc.encode_regions(rgb_d, masks_d, masks_per_frame=[M] * F)
         enc_done = main.record_event()
         with torch.cuda.stream(side):
-            votes, nms, state["next_id"] = sm.associate_batch(xyz_d, ins_d, depth_d, segs, c2ws, K, state["next_id"], M,
-                                                              kf_slots=range(F), w2cs=w2cs, mask_ins_out=mask_ins)
-            state["n_matched"] = nms[-1]
+            if args.side in ("all", "assoc") or state["next_id"] == 0:
+                votes, nms, state["next_id"] = sm.associate_batch(xyz_d, ins_d, depth_d, segs, c2ws, K, state["next_id"], M,
+                                                                  kf_slots=range(F), w2cs=w2cs, mask_ins_out=mask_ins)
+                state["n_matched"] = nms[-1]
             side.wait_event(enc_done)
             # dense per-point fusion of all F keyframes in one pass over the bank, then the instance bank
-            mask_row = torch.where(mask_ins >= 0, ident_all, -1)
-            sm.fuse_dense_batch(list(range(F)), bank, bank_lo, counts, feats, mask_row)
-            for i in range(F):
-                sm.bank_update_mean(ibank, icounts, feats[i * M:(i + 1) * M], mask_ins[i])
+            if args.side in ("all", "fuse"):
+                mask_row = torch.where(mask_ins >= 0, ident_all, -1)
+                sm.fuse_dense_batch(list(range(F)), bank, bank_lo, counts, feats, mask_row)
+                for i in range(F):
+                    sm.bank_update_mean(ibank, icounts, feats[i * M:(i + 1) * M], mask_ins[i])
             feats.record_stream(side)
         if args.no_pipeline:
             main.wait_stream(side)
@@ -199,6 +201,10 @@ def run_ours(args, rank, world, local_rank):
         ms_step = ms_total / args.steps
         value = world * F / (ms_step / 1e3)
     clocks = sampler.stop() if sampler else None
+    if args.only_value:
+        if rank == 0:
+            print(json.dumps({"diagnostic": True, "side": args.side, "ms_per_step": round(ms_step, 4), "value": round(value, 2)}))
+        return
 
     # --- the encoder alone (E1..E5 of the same batch, nothing on the side stream): what the step costs beyond it is
     # association/fusion contention and host gaps
@@ -482,10 +488,21 @@ def run_sharded(args, rank, world, dev, dist, enc, timed):
         b.record()
     torch.cuda.synchronize()
     us_vote = a.elapsed_time(b) / 5 / G * 1e3
+    # the host-launched NCCL all-reduce of the same table, for comparison (what exchange="nccl" pays per keyframe)
+    with torch.cuda.stream(side):
+        for _ in range(20):
+            dist.all_reduce(tab)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(5 * G):
+            dist.all_reduce(tab)
+        b.record()
+    torch.cuda.synchronize()
+    us_nccl = a.elapsed_time(b) / 5 / G * 1e3
     coll = {"gather_frames_ms": per["gather_frames"], "gather_frames_bytes": int(world * F * H * W * 8),
             "associate_ms": per["associate"], "vote_exchange_us_each": round(us_vote, 2), "vote_exchanges_per_step": G,
             "vote_exchange_ms_per_step": round(us_vote * G / 1e3, 4), "vote_table_bytes": int(tab.numel() * 4),
-            "vote_exchange": args.exchange, "gather_descriptors_ms": per["gather_feats"], "gather_descriptors_bytes": int(world * F * M * D * 4),
+            "vote_exchange": args.exchange, "nccl_all_reduce_us_each_same_table": round(us_nccl, 2), "gather_descriptors_ms": per["gather_feats"], "gather_descriptors_bytes": int(world * F * M * D * 4),
             "fuse_ms": per["fuse"], "route_new_points_ms": per["route_points"], "route_new_points_bytes": int(world * cap_dst * 16),
             "wait_for_encoder_ms": per["enc_wait"]}
     exch = {"gather_frames": per["gather_frames"], "vote_exchange": us_vote * G / 1e3, "gather_descriptors": per["gather_feats"],
@@ -892,7 +909,10 @@ def main():
     ap.add_argument("--no-next-rows", action="store_true", help="skip the crop-descriptor / label-transfer stage reports")
     ap.add_argument("--profile-e2e", action="store_true", help="cProfile three e2e steps to stderr")
     ap.add_argument("--no-pipeline", action="store_true", help="do not overlap a step's fusion with the next step's encoder")
-    ap.add_argument("--exchange", default="nccl", choices=["nccl", "p2p"],
+    ap.add_argument("--side", default="all", choices=["all", "assoc", "fuse", "none"],
+                    help="diagnostic: which part of the map work runs beside the encoder (anything but `all` is NOT the benchmark)")
+    ap.add_argument("--only-value", action="store_true", help="diagnostic: print the device-resident step time and stop")
+    ap.add_argument("--exchange", default="p2p", choices=["nccl", "p2p"],
                     help="vote-table exchange of the sharded map (N > 1): NCCL all-reduce per keyframe, or the fused device-side "
                          "peer-memory exchange (ovo_b200/p2p.py)")
     args = ap.parse_args()

@@ -1062,7 +1062,14 @@ int ovo_encoder_forward(ovo_encoder_t* e, int n_img, int n_layers, int apply_ln_
     if (ge.exec == nullptr) {
       const long long before = ovo_launch_count(0);
       cudaGraph_t graph = nullptr;
-      if (!e->cap_stream) OVO_CUDA(cudaStreamCreateWithFlags(&e->cap_stream, cudaStreamNonBlocking));
+      if (!e->cap_stream) {
+        // captured kernel nodes inherit the capture stream's priority: the encoder's (resource-hungry, one CTA per SM) kernels get the
+        // highest one, so that map kernels running beside them on another stream only take what the encoder leaves (OVO_B200_ENC_PRIO=0: off)
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        const char* pe = getenv("OVO_B200_ENC_PRIO");
+        OVO_CUDA(cudaStreamCreateWithPriority(&e->cap_stream, cudaStreamNonBlocking, (pe && pe[0] == '0') ? lo : hi));
+      }
       OVO_CUDA(cudaStreamBeginCapture(e->cap_stream, cudaStreamCaptureModeThreadLocal));
       const int r = forward_eager(e, n_img, n_layers, apply_ln_post, e->cap_stream);
       const cudaError_t ce = cudaStreamEndCapture(e->cap_stream, &graph);

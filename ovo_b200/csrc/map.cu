@@ -800,8 +800,10 @@ __global__ void scatter_matches_kernel(const int2* __restrict__ list, int n, int
 // A warp owns kVecPerLane * 256 COLUMNS of the rows (blockIdx.y = which part): with 512 columns per warp the kernel needs
 // ~80 registers, so 24 warps per SM are resident instead of 16 (the pass is latency-bound: ncu long_scoreboard).  The
 // counts are therefore not written here (another part's warp may still need the old value): fuse_counts_kernel follows.
+// 128-thread blocks of <= 80 registers: one of them fits on an SM beside a resident encoder GEMM CTA (see batch_scan), seven when
+// the SM is free.
 template <int kVecPerLane, bool kFull>
-__global__ void __launch_bounds__(256, kVecPerLane <= 2 ? 3 : 1)
+__global__ void __launch_bounds__(128, kVecPerLane <= 2 ? 6 : 1)
     fuse_dense_batch_kernel(const int16_t* __restrict__ seg_of_pt /* [F][stride] */, long long stride, int F, long long N,
                             __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, const int32_t* __restrict__ counts,
                             int D, const __nv_bfloat16* __restrict__ feats, const int32_t* __restrict__ mask_row /* [F][n_masks] */,
@@ -1630,12 +1632,12 @@ int ovo_map_batch_begin(ovo_map_t* m, const float* xyz_dev, const int32_t* ins_i
   OVO_CHECK_LAUNCH();
   ovo::batch_frustum_setup_kernel<<<F, 1, 0, stream>>>(dfr);
   OVO_CHECK_LAUNCH();
-  ovo::batch_depth_filter_kernel<<<dim3(ovo::ceil_div(wmax, 32), ovo::ceil_div(hmax, 8), F), dim3(32, 8), 0, stream>>>(dfr);
+  ovo::batch_depth_filter_kernel<<<dim3(ovo::ceil_div(wmax, 32), ovo::ceil_div(hmax, 4), F), dim3(32, 4), 0, stream>>>(dfr);   // 128-thread blocks: co-resident with the encoder's GEMM CTAs
   OVO_CHECK_LAUNCH();
   ovo::batch_seg_area_kernel<<<dim3(32, F), 256, max_masks * sizeof(int32_t), stream>>>(dfr, m->bt_area, m->bt_stride);
   OVO_CHECK_LAUNCH();
   if (N > 0) {
-    const int blocks = static_cast<int>(std::min<long long>((N + ovo::kP1Threads - 1) / ovo::kP1Threads, sms * 8LL));
+    const int blocks = static_cast<int>(std::min<long long>((N + ovo::kP1Threads - 1) / ovo::kP1Threads, sms * 64LL));   // short-lived blocks
     for (int f0 = 0; f0 < F; f0 += ovo::kBatchFramesPerPass) {
       ovo::associate_batch_pass_kernel<<<blocks, ovo::kP1Threads, 0, stream>>>(xyz_dev, N, dfr, f0, std::min(ovo::kBatchFramesPerPass, F - f0),
                                                                                 m->seg_dense, stride, tables);
@@ -1685,11 +1687,17 @@ static int batch_scan(ovo_map_t* m, int f, int32_t* ins_ids_dev, const ovo::Vote
     const size_t st = static_cast<size_t>(m->dense_stride);
     const int16_t* prev = f > 0 ? m->seg_dense + static_cast<size_t>(f - 1) * st : nullptr;
     const int32_t* mi_prev = f > 0 ? m->bt_mask_ins + static_cast<size_t>(f - 1) * m->bt_stride : nullptr;
-    const int smem_ints = std::min(len - 4, 10 * 1024);   // up to 40 KB of shared-memory votes
+    // No shared-memory vote table here: the batch runs on a side stream UNDER the encoder, whose persistent GEMM CTAs leave ~12 KB
+    // of shared memory and ~11k registers per SM — a 256-thread block with <= 40 registers and no dynamic shared memory is
+    // co-resident with them, one that asks for 40 KB only runs in the gaps between GEMM launches (measured: ~100 us per
+    // keyframe of scheduling delay, the whole association chain of a 64-keyframe batch serialised behind the encoder).  The
+    // votes go to L2 as RED.ADD (a few 10^4 - 10^5 per keyframe over ~100 addresses: microseconds).
+    const int smem_ints = 0;
+    (void)len;
     const int blocks = static_cast<int>(std::min<long long>(((N + 7) / 8 + 255) / 256, ovo::num_sms() * 8LL));
-    ovo::batch_vote_scan_kernel<<<blocks, 256, smem_ints * sizeof(int32_t), stream>>>(prev, mi_prev, m->seg_dense + static_cast<size_t>(f) * st,
-                                                                                    ins_ids_dev, N, d_next, m->bt_n_masks[f], table + 4, smem_ints,
-                                                                                    tail ? *tail : none);
+    ovo::batch_vote_scan_kernel<<<blocks, 256, 0, stream>>>(prev, mi_prev, m->seg_dense + static_cast<size_t>(f) * st,
+                                                           ins_ids_dev, N, d_next, m->bt_n_masks[f], table + 4, smem_ints,
+                                                           tail ? *tail : none);
     OVO_CHECK_LAUNCH();
   } else if (tail) {   // an empty shard still takes part in the exchange and takes the decisions
     ovo::batch_vote_finish_kernel<<<1, 256, 0, stream>>>(*tail, m->bt_n_masks[f]);
@@ -1907,13 +1915,15 @@ int ovo_map_fuse_dense_batch(ovo_map_t* m, const int* kf_slots_host, int n_slots
   auto* hi = static_cast<__nv_bfloat16*>(bank_dev);
   auto* lo = static_cast<__nv_bfloat16*>(bank_lo_dev);
   const int parts = ovo::ceil_div(D, 512);   // a warp owns 512 columns of a row
-  const int blocks = static_cast<int>(std::min<long long>((N + 255) / 256, std::max(1, ovo::num_sms() * 12 / parts)));
+  // short-lived blocks (a warp = ONE chunk of 32 points): a block that squats on an SM for the whole pass keeps the encoder's next
+  // GEMM CTA (215 KB of shared memory, 54k registers) off that SM; blocks of a few microseconds give the SM back at once
+  const int blocks = static_cast<int>((N + 127) / 128);
   if (D % 512 == 0)
-    ovo::fuse_dense_batch_kernel<2, true><<<dim3(blocks, parts), 256, 0, stream>>>(rows, stride, n_slots, N, hi, lo, counts_dev, D, m->feats_bf16, mask_row_dev, n_masks);
+    ovo::fuse_dense_batch_kernel<2, true><<<dim3(blocks, parts), 128, 0, stream>>>(rows, stride, n_slots, N, hi, lo, counts_dev, D, m->feats_bf16, mask_row_dev, n_masks);
   else
-    ovo::fuse_dense_batch_kernel<2, false><<<dim3(blocks, parts), 256, 0, stream>>>(rows, stride, n_slots, N, hi, lo, counts_dev, D, m->feats_bf16, mask_row_dev, n_masks);
+    ovo::fuse_dense_batch_kernel<2, false><<<dim3(blocks, parts), 128, 0, stream>>>(rows, stride, n_slots, N, hi, lo, counts_dev, D, m->feats_bf16, mask_row_dev, n_masks);
   OVO_CHECK_LAUNCH();
-  ovo::fuse_counts_kernel<<<static_cast<int>(std::min<long long>((N + 255) / 256, ovo::num_sms() * 8LL)), 256, 0, stream>>>(rows, stride, n_slots, N, counts_dev, mask_row_dev, n_masks);
+  ovo::fuse_counts_kernel<<<static_cast<int>((N + 255) / 256), 256, 0, stream>>>(rows, stride, n_slots, N, counts_dev, mask_row_dev, n_masks);
   OVO_CHECK_LAUNCH();
   return OVO_OK;
 }
