@@ -184,6 +184,18 @@ def run_ours(args, rank, world, local_rank):
             ms = t.item()
         return ms, launches
 
+    def timed_plain(fn, n, warm):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a_.record()
+        for _ in range(n):
+            fn()
+        b_.record()
+        torch.cuda.synchronize()
+        return a_.elapsed_time(b_) / n
+
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
@@ -248,6 +260,20 @@ def run_ours(args, rank, world, local_rank):
              "roofline": {"bound": "hbm", "achieved": round(qgbs, 1), "peak": hbm, "unit": "GB/s", "frac": round(qgbs / hbm, 4),
                           "traffic": None, "peak_source": f"{how} hbm_gbs", "algorithmic_bytes": qbytes}}
 
+    # --- the reference's deployment path (PyTorch, bf16 autocast) on this same GPU, kernel by kernel
+    gpu_base = None
+    if world == 1 and not args.no_gpu_baseline:
+        def _gb():
+            assoc_ms = timed_plain(lambda: sm.associate_batch(xyz_d, ins_d, depth_d, segs, c2ws, K, state["next_id"], M, kf_slots=range(F),
+                                                              w2cs=w2cs, mask_ins_out=mask_ins), 5, 2) / F
+            return run_gpu_baseline(args, dev, enc, sd, cfg, sm, F, xyz, ins, fr[0], seg, K, bank, qms, assoc_ms)
+        try:
+            gpu_base = _gb()
+        except Exception as e:  # noqa: BLE001
+            import traceback
+            traceback.print_exc(file=sys.stderr)
+            gpu_base = {"error": f"{type(e).__name__}: {e}"}
+
     # --- SAM-2 mask proposal stage (reported as a separate stage; the headline uses the precomputed-mask seam)
     sam = None if args.no_sam else run_sam_stage(args, dev, ms_step / F, tf_sus, how)
 
@@ -284,6 +310,8 @@ def run_ours(args, rank, world, local_rank):
                       "l2_policy": "inputs larger than L2: per step 0.63 GB weights + ~2 GB map/bank traffic per keyframe (L2 126 MB)"},
            "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e, "roofline": roofline, "query": query,
            "n_matched_points_per_keyframe": int(state["n_matched"])}
+    if gpu_base is not None:
+        out["gpu_baseline"] = gpu_base
     if sharded is not None:
         out["sharded_map"] = {k: v for k, v in sharded.items() if k not in ("ms_per_step", "value", "launches")}
         out["replicas"] = replicas
@@ -300,6 +328,104 @@ def run_ours(args, rank, world, local_rank):
         if sam is not None:
             out["sam"]["cpu_baseline"] = sam_cpu_baseline()
     print(json.dumps(out))
+
+
+def run_gpu_baseline(args, dev, enc, sd, cfg, sm, F, xyz, ins, frame0, seg, K, bank, qms_ours, assoc_ms_ours_per_kf):
+    """The GPU-vs-GPU bar: the reference's deployment path — plain PyTorch on the SAME B200 under bf16 autocast
+    (ovomapping.py:166): the ViT with cuDNN/flash SDPA + cuBLASLt linears (oracle/torch_gpu.py restates pe.py), SDPA alone, the four
+    GEMM shapes of a layer (F.linear), the association as torch ops + the reference's per-mask Python loop, the cosine query as
+    torch.mm (clip_utils.py:16-19) — each timed with CUDA events beside this repo's kernel for the same work."""
+    import ctypes as C
+    import torch.nn.functional as Fn
+    from oracle import torch_gpu as TG
+    from ovo_b200 import _lib
+    lib = _lib.lib()
+
+    def t(fn, n=10, warm=3):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / n
+
+    out = {"what": "PyTorch (cuBLASLt, SDPA, ATen) on the same GPU under torch.autocast(bfloat16) vs this repo's kernels, CUDA events, "
+                   "same shapes; ratio = torch_ms / ours_ms (> 1: the hand-written kernel is faster)"}
+    n_img = 2 * F
+    W = {k: v.to(dev) for k, v in sd.items() if k.startswith("visual.")}
+    px = torch.randn(n_img, 3, cfg.image_size, cfg.image_size, device=dev)
+    with torch.no_grad():
+        def torch_enc():
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                return TG.vit_forward_features(px, W, cfg)
+        ms_t = t(torch_enc, 5, 2)
+        ms_o = t(lambda: enc.forward_features_from_pixels(px), 10, 3)
+        ref = torch_enc().float()
+        got = enc.forward_features_from_pixels(px)
+        cos = torch.nn.functional.cosine_similarity(got.flatten(1), ref.flatten(1), dim=1).min().item()
+    out["encoder"] = {"images": n_img, "torch_ms": round(ms_t, 3), "ours_ms": round(ms_o, 3), "ratio": round(ms_t / ms_o, 3),
+                      "min_cosine_vs_torch_bf16": round(cos, 6)}
+    # attention alone: one layer, 16 images x 16 heads x 577 tokens x 64
+    H_ = cfg.heads
+    q, k, v = (torch.randn(n_img, H_, cfg.seq, cfg.width // H_, device=dev, dtype=torch.bfloat16) for _ in range(3))
+    ms_sdpa = t(lambda: Fn.scaled_dot_product_attention(q, k, v), 20, 5)
+    _lib.profile_begin()
+    enc.forward_features_from_pixels(px)
+    torch.cuda.synchronize()
+    prof = _lib.profile_report()
+    ms_attn = prof["attention"]["ms"] / max(prof["attention"]["launches"], 1)
+    fl = 4.0 * n_img * H_ * cfg.seq * cfg.seq * (cfg.width // H_)
+    out["attention"] = {"shape": [n_img, H_, cfg.seq, cfg.width // H_], "torch_sdpa_ms": round(ms_sdpa, 4), "ours_ms": round(ms_attn, 4),
+                        "ratio": round(ms_sdpa / ms_attn, 3), "torch_tflops": round(fl / ms_sdpa / 1e9, 1), "ours_tflops": round(fl / ms_attn / 1e9, 1)}
+    # the four GEMMs of a layer (M = images * 577)
+    M_ = n_img * cfg.seq
+    gem = {}
+    for name, epi, N_, K_ in (("qkv", 4, 3 * cfg.width, cfg.width), ("out_proj+residual", 3, cfg.width, cfg.width),
+                              ("fc1+gelu", 2, cfg.mlp_width, cfg.width), ("fc2+residual", 3, cfg.width, cfg.mlp_width)):
+        a_ = torch.randn(M_, K_, device=dev, dtype=torch.bfloat16)
+        w_ = torch.randn(N_, K_, device=dev, dtype=torch.bfloat16)
+        b_ = torch.randn(N_, device=dev, dtype=torch.bfloat16)
+        r_ = torch.randn(M_, N_, device=dev, dtype=torch.float32)
+        if "gelu" in name:
+            fn = lambda: Fn.gelu(Fn.linear(a_, w_, b_))
+        elif "residual" in name:
+            fn = lambda: r_ + Fn.linear(a_, w_, b_)
+        else:
+            fn = lambda: Fn.linear(a_, w_, b_)
+        ms_lin = t(lambda: Fn.linear(a_, w_, b_), 20, 5)
+        ms_full = t(fn, 20, 5)
+        mo = C.c_float(0)
+        _lib.check(lib.ovo_gemm_bench(epi, M_, N_, K_, 0, 20, C.byref(mo), _lib.stream_ptr(dev)), "ovo_gemm_bench")
+        fl = 2.0 * M_ * N_ * K_
+        gem[name] = {"M": M_, "N": N_, "K": K_, "torch_linear_ms": round(ms_lin, 4), "torch_linear_plus_epilogue_ms": round(ms_full, 4),
+                     "ours_fused_ms": round(mo.value, 4), "ratio_vs_linear_alone": round(ms_lin / mo.value, 3),
+                     "ratio_vs_linear_plus_epilogue": round(ms_full / mo.value, 3), "torch_linear_tflops": round(fl / ms_lin / 1e9, 1),
+                     "ours_tflops": round(fl / mo.value / 1e9, 1)}
+        del a_, w_, b_, r_
+    out["gemm"] = gem
+    # association of one keyframe against the 2M-point map: torch ops + the per-mask loop of the reference
+    xyz_t, ins_t = torch.from_numpy(xyz).to(dev), torch.from_numpy(ins).to(dev)
+    d_t, seg_t = torch.from_numpy(frame0["depth"]).to(dev), torch.from_numpy(seg).to(dev)
+    c2w_t, K_t = torch.from_numpy(frame0["c2w"]).to(dev), torch.from_numpy(K).to(dev)
+    warm, _, nxt = TG.associate(xyz_t, ins_t, d_t, seg_t, c2w_t, K_t, 0.05, 100, 0)     # creates the instances
+    ms_assoc = t(lambda: TG.associate(xyz_t, warm, d_t, seg_t, c2w_t, K_t, 0.05, 100, nxt), 5, 1)
+    out["associate"] = {"points": int(xyz.shape[0]), "torch_ms_per_keyframe": round(ms_assoc, 3), "ours_ms_per_keyframe": round(assoc_ms_ours_per_kf, 4),
+                        "ratio": round(ms_assoc / assoc_ms_ours_per_kf, 2), "note": "torch: ~25 ATen kernels + a host sync per mask (ovo.py:255-280); "
+                        "ours: one pass over the map per BATCH of keyframes, decisions on the device"}
+    # cosine query: bank [N, D] bf16 x text [Q, D]
+    text = torch.nn.functional.normalize(torch.randn(Q, bank.shape[1], device=dev), dim=-1)
+    tb = text.bfloat16()
+    ms_mm = t(lambda: torch.mm(bank, tb.T), 20, 3)
+    out["query"] = {"points": int(bank.shape[0]), "queries": Q, "torch_mm_ms": round(ms_mm, 4), "ours_ms": round(qms_ours, 4),
+                    "ratio": round(ms_mm / qms_ours, 3), "note": "torch.mm writes bf16 [N, Q] (half the output bytes of our f32 result)"}
+    worst = min([out["encoder"]["ratio"], out["attention"]["ratio"], out["associate"]["ratio"], out["query"]["ratio"]] +
+                [g["ratio_vs_linear_plus_epilogue"] for g in gem.values()])
+    out["vs_torch_gpu"] = {"encoder": out["encoder"]["ratio"], "min_over_kernels": round(worst, 3)}
+    return out
 
 
 NEW_POINTS_PER_FRAME = 76_800       # VanillaMapper at downscale 2 on 640x480 (vanilla_mapper.py:32-36, SURVEY 8d)
@@ -905,6 +1031,7 @@ def main():
     ap.add_argument("--points", type=int, default=2_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sam", action="store_true", help="skip the SAM-2 stage report")
+    ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the PyTorch-on-the-same-GPU comparison")
     ap.add_argument("--no-stream", action="store_true", help="skip the streaming-growth (BASELINE config 5) stage report")
     ap.add_argument("--no-next-rows", action="store_true", help="skip the crop-descriptor / label-transfer stage reports")
     ap.add_argument("--profile-e2e", action="store_true", help="cProfile three e2e steps to stderr")

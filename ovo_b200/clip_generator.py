@@ -121,6 +121,7 @@ class CLIPGenerator:
         if self.embed_type != "TextRegion" and self.embed_type not in CROP_EMBED_TYPES:
             raise NotImplementedError(
                 f"ovo_b200: embed_type '{self.embed_type}' is not built (have TextRegion, {', '.join(CROP_EMBED_TYPES)})")
+        self._check_supported_keys(config)
         self.w_masked = config.get("w_masked", 0.4418)      # clip_generator.py:33-34
         self.w_global = config.get("w_global", 0.1)
         self.model_card = config.get("model_card", "PE-Core-L14-336")
@@ -129,7 +130,6 @@ class CLIPGenerator:
             raise NotImplementedError(f"ovo_b200: model card '{self.model_card}' is not supported (have {list(MODEL_CARDS)})")
         if encoder is None and not torch.cuda.is_available():
             raise RuntimeError("ovo_b200.CLIPGenerator needs a CUDA device (there is no CPU fallback)")
-        self._check_supported_keys(config)
         if state_dict is None and encoder is None:
             state_dict = load_clip_state_dict(config, cfg, self.model_card)
         self.cfg = cfg

@@ -77,6 +77,19 @@ class OVO:
         self._bank = torch.zeros(int(config.get("bank_capacity", 4096)), D, device=self._dev, dtype=torch.float32)    # fused instance descriptors
         self._bank_n = 0
         self._rows_cache = None
+        # map sharded over the ranks of a torch.distributed group (new, `semantic.shard_map: True`): `map_data` is then
+        # THIS rank's shard (points whose voxel hashes to it, ovo_b200.sharding.shard_of_points), every rank makes the same calls
+        # with the same frames; per keyframe the vote tables are summed over the ranks (one all-reduce), every rank takes the same
+        # decisions, keyframe k's descriptors are computed by rank k % world and broadcast, the instance registry / bank are
+        # replicated, the dense bank is sharded like the map
+        self.sharded = bool(config.get("shard_map", False))
+        self._group = config.get("shard_group", None)
+        self._rank, self._world = 0, 1
+        if self.sharded:
+            import torch.distributed as dist
+            if not dist.is_initialized():
+                raise RuntimeError("ovo_b200: semantic.shard_map needs an initialised torch.distributed process group (one process per GPU)")
+            self._rank, self._world = dist.get_rank(self._group), dist.get_world_size(self._group)
         # dense per-point mode
         self.dense = bool(config.get("dense_map", False))
         self._dense_bank = None        # [N, D] bf16: the running mean rounded to bf16 (the operand of the dense query)
@@ -161,10 +174,19 @@ class OVO:
         c2w_np = c2w.detach().float().cpu().numpy() if torch.is_tensor(c2w) else np.asarray(c2w, np.float32)
         K_np = self.cam_intrinsics.detach().float().cpu().numpy()
         slot = kf_id % self.semmap.n_slots
-        votes, n_matched, self.next_ins_id = self.semmap.associate(
-            xyz, updated, depth_d, seg_d, c2w_np, K_np, self.next_ins_id, match_th=self.config["match_distance_th"],
-            track_th=int(self.config["track_th"]), depth_filter=self.config.get("depth_filter", False),
-            rgb_depth_ratio=rgb_depth_ratio, kf_slot=slot, n_masks=int(binary_maps.shape[0]))
+        if self.sharded and self._world > 1:
+            # this rank's points vote, the tables are summed over the shards, every rank decides alike (ovo_map_vote / ovo_map_apply)
+            import torch.distributed as dist
+            table = self.semmap.vote(xyz, updated, depth_d, seg_d, c2w_np, K_np, n_ins=self.next_ins_id, n_masks=int(binary_maps.shape[0]),
+                                     match_th=self.config["match_distance_th"], track_th=int(self.config["track_th"]),
+                                     depth_filter=self.config.get("depth_filter", False), rgb_depth_ratio=rgb_depth_ratio, kf_slot=slot)
+            dist.all_reduce(table, op=dist.ReduceOp.SUM, group=self._group)
+            votes, n_matched, self.next_ins_id = self.semmap.apply(table, self.next_ins_id)
+        else:
+            votes, n_matched, self.next_ins_id = self.semmap.associate(
+                xyz, updated, depth_d, seg_d, c2w_np, K_np, self.next_ins_id, match_th=self.config["match_distance_th"],
+                track_th=int(self.config["track_th"]), depth_filter=self.config.get("depth_filter", False),
+                rgb_depth_ratio=rgb_depth_ratio, kf_slot=slot, n_masks=int(binary_maps.shape[0]))
         # (the reference loops to seg_map.max()+1 <= len(binary_maps); masks absent from seg_map get no votes, so
         # using the mask count instead saves a device->host sync without changing any result)
         n_masks = len(votes["ins_id"])
@@ -298,7 +320,7 @@ class OVO:
             for it in group:                # allocated on the caller's stream, read (and released) under the descriptor stream
                 it[1].record_stream(self._enc_stream)
                 it[5].record_stream(self._enc_stream)
-            rows_per_kf = self._extract_clip_batch([it[2] for it in group], [it[1] for it in group])
+            rows_per_kf = self._extract_clip_batch([it[2] for it in group], [it[1] for it in group], [it[3] for it in group])
             if self.dense and len(group) > 1:
                 # all keyframes of the batch in ONE pass over the dense bank (bit-identical to one pass per keyframe)
                 base, total = rows_per_kf[0][0], sum(len(r) for r in rows_per_kf)
@@ -320,13 +342,45 @@ class OVO:
                                                "t_up": round(self._time_cache[-1], 3)}, print_output=True)
             self._time_cache = []
 
+    def _extract_clip_batch_sharded(self, images, maps, counts, kf_ids) -> List[List[int]]:
+        """Keyframe k's descriptors are computed by rank k % world (the encoder is replicated, frames are data parallel) and
+        broadcast to the other ranks (<= 0.2 MB per keyframe); every rank appends them to its replica of the descriptor store."""
+        import torch.distributed as dist
+        D = self._store.shape[1]
+        mine = [j for j, k in enumerate(kf_ids) if k % self._world == self._rank and counts[j] > 0]
+        feats = [torch.empty(c, D, device=self._dev, dtype=torch.float32) for c in counts]
+        if mine:
+            if self.clip_generator.embed_type == "TextRegion" and all(images[j].shape == images[mine[0]].shape for j in mine):
+                img = torch.stack([torch.from_numpy(np.ascontiguousarray(images[j])) for j in mine]).to(self._dev, non_blocking=True)
+                out = self.clip_generator.encoder.encode_regions(img, torch.cat([maps[j] for j in mine]), masks_per_frame=[counts[j] for j in mine])
+                off = 0
+                for j in mine:
+                    feats[j] = out[off: off + counts[j]].contiguous()
+                    off += counts[j]
+            else:
+                for j in mine:
+                    im = torch.from_numpy(np.ascontiguousarray(images[j])).to(self._dev)
+                    feats[j] = self.clip_generator.extract_clip(im, maps[j]).contiguous()
+        out_rows, r0 = [], self._store_n
+        for j, k in enumerate(kf_ids):
+            if counts[j] > 0:
+                dist.broadcast(feats[j], src=dist.get_global_rank(self._group, k % self._world) if self._group is not None else k % self._world,
+                               group=self._group)
+                self._store[r0: r0 + counts[j]].copy_(feats[j])
+            out_rows.append(list(range(r0, r0 + counts[j])))
+            r0 += counts[j]
+        self._store_n = r0
+        return out_rows
+
     @profil
-    def _extract_clip_batch(self, images: List[np.ndarray], maps: List[torch.Tensor]) -> List[List[int]]:
+    def _extract_clip_batch(self, images: List[np.ndarray], maps: List[torch.Tensor], kf_ids: List[int] | None = None) -> List[List[int]]:
         """ovo.py:426-437 for a batch of keyframes: descriptors are written straight into the device descriptor
         store; returns the store rows per keyframe."""
         counts = [int(m.shape[0]) for m in maps]
         M = sum(counts)
         self._grow_store(self._store_n + M)
+        if self.sharded and self._world > 1:
+            return self._extract_clip_batch_sharded(images, maps, counts, kf_ids)
         if len(images) == 1:
             img = torch.from_numpy(np.ascontiguousarray(images[0])).to(self._dev, non_blocking=True)[None]
         else:

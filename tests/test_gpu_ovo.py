@@ -261,3 +261,77 @@ def test_update_map_matches_reference_loop_closure(tmp_path, golden_dir):
     assert ((clips - ref).norm() / ref.norm()).item() < 1e-2
     # the map keeps working after the merge: a query over the merged bank
     assert ovo.query(["0", "1", "2"]).shape == (len(g["object_ids"]), 3)
+
+
+def test_weights_load_from_checkpoint_files_like_the_reference(tmp_path):
+    """`clip.ckpt_path` reads a `pe.CLIP.load_ckpt`-format file (wrapper + `module.` prefix, pe.py:629-638) and a
+    vision-only one (pe.py:407-419); `sam.sam_ckpt_path` reads `sam2.1_hiera_large.pt` = {"model": state_dict}
+    (build_sam.py:159, segment_utils.py:269-276).  The descriptors / masks equal those of the same weights passed in memory; a
+    missing CLIP checkpoint raises (random weights only with `random_init: True`)."""
+    from ovo_b200 import CLIPGenerator
+    from ovo_b200.encoder import random_state_dict
+    from ovo_b200.mask_generator import MaskGenerator
+    from ovo_b200.sam_config import random_state_dict as sam_sd, tiny_sam_config
+    cfg = GG.tiny_cfg()
+    sd = random_state_dict(cfg, seed=0)
+    base = {"embed_type": "TextRegion", "model_card": "PE-Core-L14-336", "max_images": 4, "max_h": 480, "max_w": 640, "max_masks": 32}
+    torch.save({"state_dict": {"module." + k: v for k, v in sd.items()}}, tmp_path / "clip.pt")
+    torch.save({k[len("visual."):]: v for k, v in sd.items() if k.startswith("visual.")}, tmp_path / "vision_only.pt")
+    img = torch.from_numpy(synth.rgb(seed=3)).cuda()
+    _, bm = synth.grid_masks(rows=2, cols=3)
+    masks = torch.from_numpy(bm).cuda()
+    ref = CLIPGenerator(dict(base), state_dict=sd, encoder_config=cfg).extract_clip(img, masks)
+    for name in ("clip.pt", "vision_only.pt"):
+        gen = CLIPGenerator({**base, "ckpt_path": str(tmp_path / name)}, encoder_config=cfg)
+        assert torch.equal(gen.extract_clip(img, masks), ref), name
+        assert gen.encoder.has_text == (name == "clip.pt")
+    with pytest.raises(FileNotFoundError):
+        CLIPGenerator(dict(base), encoder_config=cfg)
+    with pytest.raises(FileNotFoundError):
+        CLIPGenerator({**base, "ckpt_path": str(tmp_path / "missing.pt")}, encoder_config=cfg)
+    rnd = CLIPGenerator({**base, "random_init": True, "random_init_seed": 0}, encoder_config=cfg)
+    assert torch.equal(rnd.extract_clip(img, masks), ref)
+    # SAM-2: the reference's file name and {"model": ...} wrapper
+    scfg = tiny_sam_config()
+    ssd = sam_sd(scfg, seed=0)
+    torch.save({"model": ssd}, tmp_path / "sam2.1_hiera_large.pt")
+    sam_cfg = {"precomputed": False, "masks_base_path": "", "sam_version": "2.1", "sam_config": scfg, "points_per_side": 16,
+               "nms_iou_th": 0.45, "stability_score_th": 0.4, "box_nms_thresh": 0.9999, "nms_score_th": GG.SAM_OVO_SCORE_THR,
+               "max_h": 480, "max_w": 640}
+    simg = GG.sam_image(seed=11)
+    a = MaskGenerator({**sam_cfg, "sam_state_dict": ssd}).get_masks(simg, 0)
+    b = MaskGenerator({**sam_cfg, "sam_ckpt_path": str(tmp_path)}).get_masks(simg, 0)
+    assert a[1].shape[0] > 0 and torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    with pytest.raises(FileNotFoundError):
+        MaskGenerator({**sam_cfg, "sam_ckpt_path": str(tmp_path / "nowhere")})
+
+
+def test_dense_bank_grows_between_keyframes_without_losing_queued_fusions(tmp_path):
+    """`_ensure_dense` grows the bank while fusions of earlier keyframes may still be queued on the
+    descriptor stream (log off, no reserved capacity): nothing may be lost or written into freed memory.  The map doubles between
+    keyframes; the final bank equals the one of a run whose capacity was reserved up front."""
+    banks = []
+    for reserve in (True, False):
+        ovo, K, xyz, ids, ins, frames = _build(tmp_path / f"r{int(reserve)}", dense=True,
+                                               extra={"dense_capacity": 4 * xyz_len()} if reserve else None)
+        n0 = xyz.shape[0] // 2
+        pts_all = torch.from_numpy(xyz).cuda(); pids_all = torch.from_numpy(ids).cuda()
+        pins = torch.from_numpy(ins).cuda()
+        for i, f in enumerate(frames):
+            n = n0 if i < 2 else xyz.shape[0]                      # the map grows after the second keyframe
+            cur = pins[:n].clone()
+            upd = ovo.detect_and_track_objects((f["frame_id"], f["image"], f["depth"], ()), (pts_all[:n], pids_all[:n], cur), torch.from_numpy(f["c2w"]))
+            if upd is not None:
+                pins[:n] = upd
+            ovo.compute_semantic_info()
+        ovo.complete_semantic_info()
+        ovo._sync_descriptors()
+        torch.cuda.synchronize()
+        N = xyz.shape[0]
+        banks.append((ovo._dense_bank[:N].clone(), ovo._dense_bank_lo[:N].clone(), ovo._dense_counts[:N].clone()))
+    assert torch.equal(banks[0][2], banks[1][2]) and int(banks[0][2].max()) >= 2
+    assert torch.equal(banks[0][0], banks[1][0]) and torch.equal(banks[0][1], banks[1][1])
+
+
+def xyz_len():
+    return GG.ovo_inputs()[1].shape[0]

@@ -77,7 +77,52 @@ def test_clip_generator_config_validation_needs_no_gpu():
         CLIPGenerator({"embed_type": "TextRegion", "model_card": "SigLIP-384"})         # open_clip-only card: not built
     if not torch.cuda.is_available():
         with pytest.raises(RuntimeError):                                                # no CPU fallback
-            CLIPGenerator({"embed_type": "fixed_weights", "model_card": "PE-Core-L14-336", "random_init_seed": 0})
+            CLIPGenerator({"embed_type": "fixed_weights", "model_card": "PE-Core-L14-336", "random_init": True, "random_init_seed": 0})
+    for bad in ({"remove_global_patch": True}, {"resize_method": "resize"}, {"project_and_normalize": False}, {"use_half": True}):
+        with pytest.raises(NotImplementedError):      # reference options that are not built are refused (before the device is touched), not ignored
+            CLIPGenerator({"embed_type": "TextRegion", "random_init": True, **bad})
+    CLIPGenerator._check_supported_keys({"remove_global_patch": False, "resize_method": "multi_resolution", "project_and_normalize": True})
+
+
+def test_clip_checkpoint_loading_rules(tmp_path):
+    """`clip.ckpt_path`: the unwrapping of pe.CLIP.load_ckpt / pe.VisionTransformer.load_ckpt (pe.py:629-638, 407-419) — `state_dict`
+    / `weights` wrappers, DDP's `module.` prefix, a vision-only checkpoint without the `visual.` prefix; the reference's root
+    directory layout (clip_utils.py:90-93); a missing file or a missing key RAISES; random weights only with `random_init`."""
+    from ovo_b200.clip_generator import load_clip_state_dict, normalize_pe_state_dict
+    from ovo_b200.encoder import EncoderConfig, random_state_dict
+    cfg = EncoderConfig(width=64, layers=2, heads=1, mlp_width=128, output_dim=32, text_width=64, text_heads=1, text_layers=1,
+                        text_mlp_width=128, vocab_size=100, text_output_dim=32, image_size=28)
+    sd = random_state_dict(cfg, seed=3)
+    card = "PE-Core-L14-336"
+    # 1. plain state_dict, 2. {"state_dict": ...} with module. prefixes, 3. {"weights": ...}
+    torch.save(sd, tmp_path / "a.pt")
+    torch.save({"state_dict": {"module." + k: v for k, v in sd.items()}}, tmp_path / "b.pt")
+    torch.save({"weights": sd}, tmp_path / "c.pt")
+    for name in ("a.pt", "b.pt", "c.pt"):
+        got = load_clip_state_dict({"ckpt_path": str(tmp_path / name)}, cfg, card)
+        assert set(got) == set(sd) and all(torch.equal(got[k], sd[k]) for k in sd)
+    # 4. vision-only checkpoint (VisionTransformer's own keys): gets its `visual.` prefix back, no text tower
+    vis = {k[len("visual."):]: v for k, v in sd.items() if k.startswith("visual.")}
+    torch.save(vis, tmp_path / "v.pt")
+    got = load_clip_state_dict({"ckpt_path": str(tmp_path / "v.pt")}, cfg, card)
+    assert set(got) == {k for k in sd if k.startswith("visual.")} and "token_embedding.weight" not in got
+    assert normalize_pe_state_dict({"state_dict": {"module.visual.proj": 1}}) == {"visual.proj": 1}
+    # 5. the reference's directory layout: <root>/data/input/ckpts/pe/<card>.pt
+    d = tmp_path / "root" / "data" / "input" / "ckpts" / "pe"
+    d.mkdir(parents=True)
+    torch.save(sd, d / f"{card}.pt")
+    assert set(load_clip_state_dict({"ckpt_path": str(tmp_path / "root")}, cfg, card)) == set(sd)
+    # 6. loud failures
+    with pytest.raises(FileNotFoundError):
+        load_clip_state_dict({"ckpt_path": str(tmp_path / "nope.pt")}, cfg, card)
+    with pytest.raises(FileNotFoundError):
+        load_clip_state_dict({}, cfg, card)                                # the reference would fail to download: so do we
+    torch.save({k: v for k, v in sd.items() if k != "visual.proj"}, tmp_path / "broken.pt")
+    with pytest.raises(KeyError):
+        load_clip_state_dict({"ckpt_path": str(tmp_path / "broken.pt")}, cfg, card)
+    rnd = load_clip_state_dict({"random_init": True, "random_init_seed": 3}, cfg, card)
+    assert all(torch.equal(rnd[k], sd[k]) for k in sd)
+
 
 
 def test_embed_type_codes_match_the_header():
