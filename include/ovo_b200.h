@@ -533,6 +533,11 @@ int ovo_sam_predict(ovo_sam_t* sam, const float* points_dev, int P, float* low_r
 int ovo_sam_postprocess(ovo_sam_t* sam, const float* low_res_dev, const float* iou_dev, int P, int h, int w, int H, int W,
                         const ovo_amg_params* prm, uint8_t* masks_out_dev, float* iou_out_dev, float* stab_out_dev,
                         int32_t* boxes_out_dev, int32_t* src_out_dev, int max_out, int* n_out, void* stream);
+/* Measurement / test aid: after this call ovo_sam_generate(_batch) still runs the whole network but hands low_dev f32
+ * [n_prompts,3,4g,4g] / iou_dev f32 [n_prompts,3] (caller-owned, kept alive) to the AMG post-processing instead of the decoder's
+ * own logits — with random-init weights the stock thresholds reject every proposal, so a benchmark without checkpoints would
+ * time an empty NMS / seg-map stage.  NULL, NULL, 0 removes the override. */
+int ovo_sam_override_logits(ovo_sam_t* sam, const float* low_dev, const float* iou_dev, int n_prompts);
 /* MaskGenerator.segment (ovo/entities/mask_generator.py:102-120) end to end: set_image, grid prompts, decoder, AMG filters,
  * OVO's masks_update (segment_utils.py:173-259) and mask2segmap (:12-27).
  *   -> seg_map i32 [H,W] (-1 = none), masks_out uint8 [M,H,W] in painted order, M in *n_masks (M <= max_masks). */

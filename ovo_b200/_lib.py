@@ -183,6 +183,7 @@ SIGNATURES = {
     "ovo_sam_predict": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "ovo_sam_postprocess": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, C.POINTER(AmgParams), c_void_p,
                                     c_void_p, c_void_p, c_void_p, c_void_p, c_int, C.POINTER(c_int), c_void_p]),
+    "ovo_sam_override_logits": (c_int, [c_void_p, c_void_p, c_void_p, c_int]),
     "ovo_sam_generate": (c_int, [c_void_p, c_void_p, c_int, c_int, C.POINTER(AmgParams), c_void_p, c_void_p, c_int, C.POINTER(c_int),
                                  c_void_p]),
     "ovo_classify": (c_int, [c_void_p, c_int64, c_int, c_float, c_void_p, c_void_p, c_void_p]),

@@ -708,6 +708,7 @@ struct ovo_sam {
   MaskStat* stats = nullptr;
   int *cand = nullptr, *sel = nullptr;
   float* low_all = nullptr; float* iou_all = nullptr; float* points = nullptr;
+  const float* low_override = nullptr; const float* iou_override = nullptr; int override_p = 0;   // measurement aid, see ovo_sam_override_logits
   uint8_t* masks_tmp = nullptr; float* score_tmp = nullptr; uint8_t* keep_tmp = nullptr; float* stab_tmp = nullptr; float* iou_tmp = nullptr;
   int32_t* box_tmp = nullptr; int32_t* src_tmp = nullptr; int32_t* order_tmp = nullptr;
   int* counters = nullptr;
@@ -1268,6 +1269,12 @@ static int generate_selected(ovo_sam_t* s, int H, int W, const ovo_amg_params* p
   // every filter of the AMG is per mask, so all prompts go through the decoder in one batch (the reference's batches of 64
   // only bound its memory, automatic_mask_generator.py:270-276)
   OVO_TRY(ovo_sam_predict(s, s->points, P, s->low_all, s->iou_all, stream_));
+  if (s->low_override != nullptr) {   // the network ran; its (random-weight) logits are replaced before the AMG post-processing
+    OVO_REQUIRE(s->override_p == P, "ovo_sam_generate: logit override holds %d prompts, the grid has %d", s->override_p, P);
+    const size_t per = static_cast<size_t>(16) * s->g * s->g;
+    OVO_CUDA(cudaMemcpyAsync(s->low_all, s->low_override, static_cast<size_t>(P) * 3 * per * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    OVO_CUDA(cudaMemcpyAsync(s->iou_all, s->iou_override, static_cast<size_t>(P) * 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  }
   const size_t need = static_cast<size_t>(P) * 3 * H * W;
   if (s->masks_tmp_bytes < need) {
     OVO_CUDA(cudaStreamSynchronize(st));
@@ -1308,6 +1315,12 @@ static int generate_selected(ovo_sam_t* s, int H, int W, const ovo_amg_params* p
   OVO_TRY(ovo_mask2segmap(s->masks_tmp2, s->score_tmp, M, H, W, seg_map_dev, masks_out_dev, s->src_tmp, stream_));
   OVO_CUDA(cudaStreamSynchronize(st));   // idx / stab_kept are host temporaries of this call
   *n_masks = M;
+  return OVO_OK;
+}
+
+int ovo_sam_override_logits(ovo_sam_t* s, const float* low_dev, const float* iou_dev, int n_prompts) {
+  OVO_REQUIRE(s && ((low_dev && iou_dev && n_prompts > 0) || (!low_dev && !iou_dev)), "ovo_sam_override_logits: bad arguments");
+  s->low_override = low_dev; s->iou_override = iou_dev; s->override_p = low_dev ? n_prompts : 0;
   return OVO_OK;
 }
 

@@ -233,6 +233,42 @@ class Sam2:
         K = k.value
         return dict(masks=masks[:K], iou=io[:K], stability=st[:K], boxes=boxes[:K], src=src[:K])
 
+    def override_logits(self, low: torch.Tensor | None, iou: torch.Tensor | None = None) -> None:
+        """Measurement / test aid (ovo_sam_override_logits): `generate` keeps running the network but post-processes these
+        logits [P,3,4g,4g] / predicted IoUs [P,3] instead (None removes the override).  See `synthetic_logits`."""
+        if low is None:
+            self._override = None
+            check(self.lib.ovo_sam_override_logits(self.handle, None, None, 0), "ovo_sam_override_logits")
+            return
+        low = low.to(self.device, torch.float32).contiguous()
+        iou = iou.to(self.device, torch.float32).contiguous()
+        assert low.dim() == 4 and low.shape[1] == 3 and low.shape[2] == 4 * self.g and iou.shape == (low.shape[0], 3)
+        self._override = (low, iou)
+        check(self.lib.ovo_sam_override_logits(self.handle, ptr(low), ptr(iou), low.shape[0]), "ovo_sam_override_logits")
+
+    def synthetic_logits(self, points_per_side: int = 16, keep_frac: float = 0.55, seed: int = 0):
+        """Plausible decoder outputs for a benchmark without checkpoints: every grid prompt proposes three nested elliptical
+        masks around its point (logit +-8 with a soft edge, like a confident SAM-2), a seeded `keep_frac` of the prompts gets a
+        high predicted IoU for ONE of its scales, the rest are rejected by the stock pred_iou threshold.  With the stock AMG /
+        OVO thresholds (0.8 / 0.95 / box-NMS 0.7, mask NMS 0.8 / 0.7 / 0.5) 50-150 masks survive."""
+        gen = torch.Generator().manual_seed(seed)
+        n, S = points_per_side, 4 * self.g
+        c = (torch.arange(n, dtype=torch.float32) + 0.5) / n * S
+        cy, cx = torch.meshgrid(c, c, indexing="ij")
+        yy, xx = torch.meshgrid(torch.arange(S, dtype=torch.float32), torch.arange(S, dtype=torch.float32), indexing="ij")
+        P = n * n
+        low = torch.empty(P, 3, S, S)
+        rad = torch.tensor([0.45, 0.8, 1.35]) * (S / n)
+        ecc = 0.6 + 0.8 * torch.rand(P, generator=gen)
+        for k in range(3):
+            d = torch.sqrt(((xx[None] - cx.reshape(-1, 1, 1)) * ecc[:, None, None]) ** 2 + ((yy[None] - cy.reshape(-1, 1, 1)) / ecc[:, None, None]) ** 2)
+            low[:, k] = ((rad[k] - d) * 20.0).clamp(-8, 8)
+        iou = torch.full((P, 3), 0.3)
+        chosen = torch.rand(P, generator=gen) < keep_frac
+        scale = torch.randint(0, 3, (P,), generator=gen)
+        iou[torch.nonzero(chosen).squeeze(1), scale[chosen]] = 0.93
+        return low, iou
+
     def generate(self, rgb_u8: torch.Tensor, prm: AmgParams = None, max_masks: int = 256):
         """MaskGenerator.segment: rgb uint8 [H,W,3] -> (seg_map int32 [H,W], binary_maps bool [M,H,W])."""
         prm = prm or self.amg_params()
