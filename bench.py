@@ -42,6 +42,28 @@ def peaks():
     return 6650.0, 1400.0, 1590.0, "fallback"
 
 
+def captured_traffic():
+    """DRAM traffic per launch of the dominant kernels from the committed ncu capture of this round (profiles/r2_traffic.json,
+    written by tools/traffic_from_captures.py from `ncu --set full` reports of tools/r2_capture.sh), with the hash of the kernel
+    sources it was taken on next to the hash of the sources this run uses."""
+    import hashlib
+    p = os.path.join(ROOT, "profiles", "r2_traffic.json")
+    if not os.path.exists(p):
+        return None
+    d = json.load(open(p))
+    h = hashlib.sha256()
+    cs = os.path.join(ROOT, "ovo_b200", "csrc")
+    for f in sorted(os.listdir(cs)):
+        h.update(open(os.path.join(cs, f), "rb").read())
+    d["same_sources"] = d.get("csrc_sha16") == h.hexdigest()[:16]
+
+    def mean(pred):
+        v = [k["dram_bytes"] for k in d["kernels"] if pred(k) and k.get("dram_bytes")]
+        return (sum(v) / len(v), len(v)) if v else (None, 0)
+    d["mean"] = mean
+    return d
+
+
 class ClockSampler:
     """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
@@ -218,6 +240,7 @@ def run_ours(args, rank, world, local_rank):
             print(json.dumps({"diagnostic": True, "side": args.side, "ms_per_step": round(ms_step, 4), "value": round(value, 2)}))
         return
 
+    feats_last = enc.encode_regions(rgb_d, masks_d, masks_per_frame=[M] * F).clone()
     # --- the encoder alone (E1..E5 of the same batch, nothing on the side stream): what the step costs beyond it is
     # association/fusion contention and host gaps
     enc_ms, _ = timed(lambda: enc.encode_regions(rgb_d, masks_d, masks_per_frame=[M] * F), 10, 3)
@@ -234,13 +257,22 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.synchronize()
     prof = _lib.profile_report()
     hbm, tf_sus, tf_burst, how = peaks()
+    cap = captured_traffic()
+    gemm_traffic, gemm_traffic_src, query_traffic, fuse_traffic = None, "no capture (profiles/r2_traffic.json absent)", None, None
+    if cap is not None:
+        tail = (f"ncu --set full capture of this round (profiles/r2_traffic.json, kernel sources {cap['csrc_sha16']}"
+                f"{' = the sources of this run' if cap['same_sources'] else ', NOT the sources of this run'})")
+        gemm_traffic, n = cap["mean"](lambda k: k["capture"] == "gemm" and "gemm_bf16_tn_kernel" in k["kernel"] and (k.get("grid") or 0) >= 100)
+        gemm_traffic_src = f"dram__bytes_read.sum + dram__bytes_write.sum per launch, mean over {n} ViT-layer GEMM launches (16 images); " + tail
+        query_traffic, _ = cap["mean"](lambda k: k["capture"] == "query")
+        fuse_traffic, _ = cap["mean"](lambda k: k["capture"] == "map" and "fuse_dense_batch" in k["kernel"])
     g = prof["gemm"]
     gemm_tflops = g["flops"] / (g["ms"] * 1e-3) / 1e12 if g["ms"] > 0 else 0.0
     tot_ms = sum(v["ms"] for v in prof.values())
     breakdown = {k: round(v["ms"] / 2, 4) for k, v in prof.items() if v["launches"]}
     roofline = {"bound": "tensor", "kernel": "gemm_bf16_tn_kernel (tcgen05, all ViT linears)",
                 "achieved": round(gemm_tflops, 1), "peak": tf_sus, "unit": "TFLOP/s", "frac": round(gemm_tflops / tf_sus, 4),
-                "traffic": 69.5e6, "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, mean over the four ViT GEMM shapes of one layer, ncu --set full capture profiles/r1h_ncu_full_vit.md (QKV 33.3, out-proj 59.3, fc1 54.0, fc2 131.3 MB)",
+                "traffic": gemm_traffic, "traffic_source": gemm_traffic_src,
                 "peak_source": f"{how} bf16_tflops_sustained (kernel timed inside a long step)",
                 "flops_per_launch": round(g["flops"] / max(g["launches"], 1) / 1e9, 2), "avg_launch_us": round(1e3 * g["ms"] / max(g["launches"], 1), 2),
                 "share_of_step": round(g["ms"] / tot_ms, 3) if tot_ms else None,
@@ -258,15 +290,31 @@ def run_ours(args, rank, world, local_rank):
     query = {"metric": "dense text-vs-map cosine query", "value": round(qgbs, 1), "unit": "GB/s", "ms": round(qms, 4),
              "points": P, "queries": Q, "l2": "bank 4.1 GB >> 126 MB L2",
              "roofline": {"bound": "hbm", "achieved": round(qgbs, 1), "peak": hbm, "unit": "GB/s", "frac": round(qgbs / hbm, 4),
-                          "traffic": None, "peak_source": f"{how} hbm_gbs", "algorithmic_bytes": qbytes}}
+                          "traffic": query_traffic, "peak_source": f"{how} hbm_gbs", "algorithmic_bytes": qbytes}}
+
+    # --- the two map kernels' own rooflines, timed alone (CUDA events, the 2M-point map and its 8 GB of bank planes >> L2)
+    assoc_ms_batch = timed_plain(lambda: sm.associate_batch(xyz_d, ins_d, depth_d, segs, c2ws, K, state["next_id"], M, kf_slots=range(F),
+                                                            w2cs=w2cs, mask_ins_out=mask_ins), 10, 3)
+    mask_row_all = torch.where(mask_ins >= 0, ident_all, -1)
+    fuse_ms = timed_plain(lambda: sm.fuse_dense_batch(list(range(F)), bank, bank_lo, counts, feats_last, mask_row_all), 10, 3)
+    n_touched = int((counts > 0).sum())
+    fuse_bytes = n_touched * (8.0 * D + 8)                 # two bf16 planes read + written, count read + written
+    assoc_bytes = F * (P * 20.0 + H * W * 8.0)             # SURVEY 8d's per-keyframe figure x F (the batch reads xyz once, so it moves less)
+    map_roof = {"fuse_dense_batch": {"bound": "hbm", "ms": round(fuse_ms, 4), "points_touched": n_touched, "keyframes": F,
+                                     "algorithmic_bytes": fuse_bytes, "achieved": round(fuse_bytes / fuse_ms / 1e6, 1), "peak": hbm, "unit": "GB/s",
+                                     "frac": round(fuse_bytes / fuse_ms / 1e6 / hbm, 4), "traffic": fuse_traffic, "peak_source": f"{how} hbm_gbs",
+                                     "note": "two-plane bank (bf16 mean + bf16 compensation): 8 KB per touched point and pass"},
+                "associate_batch": {"bound": "latency / issue (the pass over xyz is ALU-bound: ncu issue-active 75 %; the per-keyframe vote chain is dependent launches)",
+                                    "ms_per_batch": round(assoc_ms_batch, 4), "ms_per_keyframe": round(assoc_ms_batch / F, 4), "keyframes": F,
+                                    "algorithmic_bytes_survey_formula": assoc_bytes, "achieved": round(assoc_bytes / assoc_ms_batch / 1e6, 1),
+                                    "peak": hbm, "unit": "GB/s", "frac": round(assoc_bytes / assoc_ms_batch / 1e6 / hbm, 4),
+                                    "includes": "frustum + depth filter + seg areas of every keyframe, the pass, F vote/decision kernels, one D2H + host sync"}}
 
     # --- the reference's deployment path (PyTorch, bf16 autocast) on this same GPU, kernel by kernel
     gpu_base = None
     if world == 1 and not args.no_gpu_baseline:
         def _gb():
-            assoc_ms = timed_plain(lambda: sm.associate_batch(xyz_d, ins_d, depth_d, segs, c2ws, K, state["next_id"], M, kf_slots=range(F),
-                                                              w2cs=w2cs, mask_ins_out=mask_ins), 5, 2) / F
-            return run_gpu_baseline(args, dev, enc, sd, cfg, sm, F, xyz, ins, fr[0], seg, K, bank, qms, assoc_ms)
+            return run_gpu_baseline(args, dev, enc, sd, cfg, sm, F, xyz, ins, fr[0], seg, K, bank, qms, assoc_ms_batch / F)
         try:
             gpu_base = _gb()
         except Exception as e:  # noqa: BLE001
@@ -313,7 +361,7 @@ def run_ours(args, rank, world, local_rank):
                       "frames_per_step": F, "points": P, "masks": M, "queries": Q,
                       "parallelism": "single GPU" if world == 1 else f"dp{world} encoder + map sharded x{world}",
                       "l2_policy": "inputs larger than L2: per step 0.63 GB weights + ~2 GB map/bank traffic per keyframe (L2 126 MB)"},
-           "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e, "roofline": roofline, "query": query,
+           "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e, "roofline": roofline, "query": query, "map_kernels": map_roof,
            "n_matched_points_per_keyframe": int(state["n_matched"])}
     if gpu_base is not None:
         out["gpu_baseline"] = gpu_base

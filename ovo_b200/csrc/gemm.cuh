@@ -234,17 +234,28 @@ __device__ __forceinline__ void epilogue_gelu_dot(const EpiParams& ep, int row, 
 // warp exchanges 32 rows x 64 B through a private, XOR-swizzled (bank-conflict-free) shared-memory tile so that
 // afterwards lane l holds, for i = 0..3, the 16-byte piece (l & 3) of row 8*i + (l >> 2): a warp store instruction
 // then writes 8 rows x 64 contiguous bytes (full 32-byte sectors).
+// (explicit st.shared / ld.shared: through the generic `uint8_t*` the compiler emitted generic ST.E / LD.E, which take the
+// slower generic-to-shared path of the LSU)
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
 __device__ __forceinline__ void stage_exchange(uint8_t* st, int lane, const uint32_t (&in)[16], uint4 (&out)[4]) {
   __syncwarp();  // the previous exchange has been read by everyone
+  const uint32_t base = smem_u32(st);
   const int sw = (lane >> 1) & 3;
 #pragma unroll
   for (int j = 0; j < 4; ++j)
-    *reinterpret_cast<uint4*>(st + lane * 64 + ((j ^ sw) << 4)) = make_uint4(in[4 * j], in[4 * j + 1], in[4 * j + 2], in[4 * j + 3]);
+    sts128(base + lane * 64 + ((j ^ sw) << 4), in[4 * j], in[4 * j + 1], in[4 * j + 2], in[4 * j + 3]);
   __syncwarp();
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int r = 8 * i + (lane >> 2);
-    out[i] = *reinterpret_cast<const uint4*>(st + r * 64 + (((lane & 3) ^ ((r >> 1) & 3)) << 4));
+    out[i] = lds128(base + r * 64 + (((lane & 3) ^ ((r >> 1) & 3)) << 4));
   }
 }
 

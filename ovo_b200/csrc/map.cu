@@ -587,10 +587,15 @@ __global__ void __launch_bounds__(256)
                            const int16_t* __restrict__ seg_cur, int32_t* __restrict__ ins_ids, long long N,
                            const int32_t* __restrict__ n_ins_ptr, int n_masks, int32_t* __restrict__ votes, int smem_ints,
                            const __grid_constant__ VoteTail tail) {
-  extern __shared__ int32_t s_votes[];
+  // votes of a block are gathered in a STATIC 12 KB table when the keyframe's compact table fits (the instance count is only known
+  // on the device, so the size cannot be a launch parameter); larger tables take RED.ADD straight to L2 (500k votes of a 2M-point
+  // keyframe over ~100 hot addresses cost ~25 us that way)
+  constexpr int kSmemVotes = 3072;
+  __shared__ int32_t s_votes[kSmemVotes];
+  (void)smem_ints;
   const int n_ins = *n_ins_ptr;
   const int n_votes = n_masks * (n_ins + 1);
-  const bool use_smem = seg_cur != nullptr && n_votes <= smem_ints;
+  const bool use_smem = seg_cur != nullptr && n_votes <= kSmemVotes;
   if (use_smem)
     for (int i = threadIdx.x; i < n_votes; i += blockDim.x) s_votes[i] = 0;
   __syncthreads();
@@ -1687,11 +1692,6 @@ static int batch_scan(ovo_map_t* m, int f, int32_t* ins_ids_dev, const ovo::Vote
     const size_t st = static_cast<size_t>(m->dense_stride);
     const int16_t* prev = f > 0 ? m->seg_dense + static_cast<size_t>(f - 1) * st : nullptr;
     const int32_t* mi_prev = f > 0 ? m->bt_mask_ins + static_cast<size_t>(f - 1) * m->bt_stride : nullptr;
-    // No shared-memory vote table here: the batch runs on a side stream UNDER the encoder, whose persistent GEMM CTAs leave ~12 KB
-    // of shared memory and ~11k registers per SM — a 256-thread block with <= 40 registers and no dynamic shared memory is
-    // co-resident with them, one that asks for 40 KB only runs in the gaps between GEMM launches (measured: ~100 us per
-    // keyframe of scheduling delay, the whole association chain of a 64-keyframe batch serialised behind the encoder).  The
-    // votes go to L2 as RED.ADD (a few 10^4 - 10^5 per keyframe over ~100 addresses: microseconds).
     const int smem_ints = 0;
     (void)len;
     const int blocks = static_cast<int>(std::min<long long>(((N + 7) / 8 + 255) / 256, ovo::num_sms() * 8LL));
