@@ -579,9 +579,7 @@ def run_sharded(args, rank, world, dev, dist, enc, timed):
         with torch.cuda.stream(side):
             mark("t0")
             # the depth filter and the raw-depth range of a keyframe are computed ONCE, where the keyframe lives, and gathered
-            for i in range(F):
-                sm.depth_filter(depth_own[i], out=depth_f_own[i])
-                sm.depth_range(depth_own[i], out=range_own[i])
+            sm.depth_filter_batch(depth_own, out=depth_f_own, ranges=range_own)
             dist.all_gather_into_tensor(depth_all, depth_f_own)
             dist.all_gather_into_tensor(range_all, range_own)
             dist.all_gather_into_tensor(seg_all, seg_own)
@@ -619,9 +617,7 @@ def run_sharded(args, rank, world, dev, dist, enc, timed):
         dist.all_gather_into_tensor(raw_all, depth_own)
         dist.all_gather_into_tensor(seg_all, seg_own)
         v_ref, nm_ref, nxt_ref = sm_f.associate_batch(xyz_f, ins_f, [raw_all[r, i] for r, i in order], segs, c2ws, K, 0, M, w2cs=w2cs)
-        for i in range(F):
-            sm.depth_filter(depth_own[i], out=depth_f_own[i])
-            sm.depth_range(depth_own[i], out=range_own[i])
+        sm.depth_filter_batch(depth_own, out=depth_f_own, ranges=range_own)
         dist.all_gather_into_tensor(depth_all, depth_f_own)
         dist.all_gather_into_tensor(range_all, range_own)
         v_sh, nm_sh, nxt_sh = do_assoc(0)

@@ -281,6 +281,10 @@ int ovo_map_reserve(ovo_map_t* map, int64_t max_points, int max_instances, int m
 /* geometry_utils.depth_filter (geometry_utils.py:92-96): 7x7 gaussian (sigma 2.5, reflect) high-pass;
  * |d - blur| > 0.05 -> -1. */
 int ovo_depth_filter(const float* depth_dev, int h, int w, float* out_dev, void* stream);
+/* Both for n_frames depth maps [n_frames,h,w] in ONE launch: out_dev [n_frames,h,w] = the filtered maps (NULL: skip),
+ * ranges_out_dev f32 [n_frames,2] = min / max of every map's values > 0 (NULL: skip) — what a rank of a sharded map computes for
+ * its own keyframes before they are gathered (ovo_frame.depth_range_dev). */
+int ovo_depth_filter_batch(const float* depth_dev, int n_frames, int h, int w, float* out_dev, float* ranges_out_dev, void* stream);
 /* min / max of the depth values > 0 (what compute_camera_frustum_corners takes from the raw depth, geometry_utils.py:110-111)
  * -> range_out_dev f32 [2]. */
 int ovo_depth_range(const float* depth_dev, int64_t n, float* range_out_dev, void* stream);
@@ -296,6 +300,13 @@ int ovo_depth_range(const float* depth_dev, int64_t n, float* range_out_dev, voi
  * (0 <= kf_slot < 64) for a later ovo_map_fuse_dense. */
 int ovo_map_associate(ovo_map_t* map, const float* xyz_dev, int32_t* ins_ids_dev, int64_t N, const ovo_frame* frame,
                       int* next_ins_id, ovo_vote_row* votes_host, int* n_matched_host, int kf_slot, void* stream);
+/* ovo_map_associate in two halves: `launch` enqueues everything (kernels + the read-back of the rows) and returns at once,
+ * `wait` is the one host synchronisation and fills votes_host / n_matched / next_ins_id.  Between the two the caller does its own
+ * host work (the drop-in's per-keyframe bookkeeping of the PREVIOUS keyframe overlaps the GPU's association of this one).  One
+ * association in flight per handle. */
+int ovo_map_associate_launch(ovo_map_t* map, const float* xyz_dev, int32_t* ins_ids_dev, int64_t N, const ovo_frame* frame,
+                             int next_ins_id, int kf_slot, void* stream);
+int ovo_map_associate_wait(ovo_map_t* map, int* next_ins_id, ovo_vote_row* votes_host, int* n_matched_host);
 /* The same association split in two for a map SHARDED over several GPUs: every rank calls
  * ovo_map_vote on its own points (no host sync), the ranks sum the returned table (n_masks*(n_ins+1) vote counts
  * followed by one n_matched counter; the call returns that length) with an all-reduce, then every rank calls
@@ -343,6 +354,12 @@ int ovo_xchg_open_peers(ovo_xchg_t* x, const void* handles_world_x_64);
  * 4 + max(n_masks,1) * (*n_ins_dev + 1) ints travel (the layout of ovo_map_batch_vote's tables). */
 int ovo_xchg_exchange(ovo_xchg_t* x, int32_t* table_dev, int n_ints, const int32_t* n_ins_dev, int n_masks, int slot, void* stream);
 void ovo_xchg_destroy(ovo_xchg_t* x);
+/* Map growth of a sharded map: packs n freshly mapped points (xyz f32 [n,3], ids i32 [n]) into fixed-size per-shard runs for ONE
+ * all-to-all without a host synchronisation: records_out_dev f32 [world * cap_per_dst][4] = (x, y, z, id bits); slot
+ * dst * cap_per_dst + k holds this rank's k-th point (creation order) of shard dst = hash of its voxel (cell metres, the rule of
+ * ovo_b200.sharding.shard_of_points); unused slots hold (far, far, far, id -1); *overflow_dev += points that did not fit. */
+int ovo_route_pack(const float* xyz_dev, const int32_t* ids_dev, int n, int world, float cell, int cap_per_dst, float far_value,
+                   float* records_out_dev, int32_t* overflow_dev, void* stream);
 /* ovo_map_associate_batch on a shard, the per-keyframe tables summed through `xchg`: the whole batch is one call. */
 int ovo_map_associate_batch_sharded(ovo_map_t* map, ovo_xchg_t* xchg, const float* xyz_dev, int32_t* ins_ids_dev, int64_t N,
                                     const ovo_frame* frames, int n_frames, const int* kf_slots, int* next_ins_id,

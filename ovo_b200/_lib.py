@@ -135,9 +135,12 @@ SIGNATURES = {
     "ovo_map_destroy": (None, [c_void_p]),
     "ovo_map_reserve": (c_int, [c_void_p, c_int64, c_int, c_int, c_int64]),
     "ovo_depth_filter": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "ovo_depth_filter_batch": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "ovo_depth_range": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "ovo_map_associate": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, C.POINTER(Frame), C.POINTER(c_int),
                                   C.POINTER(VoteRow), C.POINTER(c_int), c_int, c_void_p]),
+    "ovo_map_associate_launch": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, C.POINTER(Frame), c_int, c_int, c_void_p]),
+    "ovo_map_associate_wait": (c_int, [c_void_p, C.POINTER(c_int), C.POINTER(VoteRow), C.POINTER(c_int)]),
     "ovo_map_vote": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, C.POINTER(Frame), c_int, c_void_p, c_int, c_void_p]),
     "ovo_map_apply": (c_int, [c_void_p, c_void_p, c_void_p, C.POINTER(c_int), C.POINTER(VoteRow), C.POINTER(c_int), c_void_p]),
     "ovo_map_get_matches": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p]),
@@ -157,6 +160,7 @@ SIGNATURES = {
     "ovo_xchg_open_peers": (c_int, [c_void_p, c_void_p]),
     "ovo_xchg_exchange": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p]),
     "ovo_xchg_destroy": (None, [c_void_p]),
+    "ovo_route_pack": (c_int, [c_void_p, c_void_p, c_int, c_int, c_float, c_int, c_float, c_void_p, c_void_p, c_void_p]),
     "ovo_map_associate_batch_sharded": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, C.POINTER(Frame), c_int, C.POINTER(c_int),
                                                 C.POINTER(c_int), C.POINTER(VoteRow), c_int, C.POINTER(c_int), c_void_p, c_void_p]),
     "ovo_map_batch_end": (c_int, [c_void_p, c_void_p, C.POINTER(c_int), C.POINTER(VoteRow), c_int, C.POINTER(c_int), c_void_p, c_void_p]),

@@ -69,7 +69,15 @@ __global__ void depth_range_kernel(const float* __restrict__ depth, int n, int* 
   if ((threadIdx.x & 31) == 0) { atomicMin(&r[0], lmin); atomicMax(&r[1], lmax); }
 }
 
+// F depth maps [F][h][w] in ONE launch: the high-pass filter of every map (out, may be null) and the [min, max] of its values > 0
+// (ranges [F][2] as int bit patterns, initialised by depth_range_init_batch_kernel)
+__global__ void depth_range_init_batch_kernel(int* r, int F) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < F) { r[2 * i] = 0x7f800000; r[2 * i + 1] = 0; }
+}
+
 __device__ __forceinline__ float dot4_rn(const float* m, float x, float y, float z) {
+
   float acc = __fmul_rn(m[0], x);
   acc = __fadd_rn(acc, __fmul_rn(m[1], y));
   acc = __fadd_rn(acc, __fmul_rn(m[2], z));
@@ -141,6 +149,26 @@ __device__ __forceinline__ void depth_filter_body(const float* __restrict__ dept
 }
 __global__ void depth_filter_kernel(const float* __restrict__ depth, int h, int w, float* __restrict__ out) {
   depth_filter_body(depth, h, w, out, blockIdx.x * blockDim.x + threadIdx.x, blockIdx.y * blockDim.y + threadIdx.y);
+}
+__global__ void depth_filter_range_batch_kernel(const float* __restrict__ depth, int h, int w, float* __restrict__ out, int* __restrict__ ranges) {
+  const size_t off = static_cast<size_t>(blockIdx.z) * h * w;
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (out != nullptr) depth_filter_body(depth + off, h, w, out + off, x, y);
+  if (ranges != nullptr) {
+    int lmin = 0x7f800000, lmax = 0;
+    if (x < w && y < h) {
+      const float d = depth[off + static_cast<size_t>(y) * w + x];
+      if (d > 0.f) { lmin = __float_as_int(d); lmax = lmin; }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      lmin = min(lmin, __shfl_xor_sync(0xffffffffu, lmin, o));
+      lmax = max(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+    }
+    if (((threadIdx.y * blockDim.x + threadIdx.x) & 31) == 0 && lmax != 0) {
+      atomicMin(&ranges[2 * blockIdx.z], lmin);
+      atomicMax(&ranges[2 * blockIdx.z + 1], lmax);
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------ mask areas
@@ -587,10 +615,12 @@ __global__ void __launch_bounds__(256)
                            const int16_t* __restrict__ seg_cur, int32_t* __restrict__ ins_ids, long long N,
                            const int32_t* __restrict__ n_ins_ptr, int n_masks, int32_t* __restrict__ votes, int smem_ints,
                            const __grid_constant__ VoteTail tail) {
-  // votes of a block are gathered in a STATIC 12 KB table when the keyframe's compact table fits (the instance count is only known
+  // votes of a block are gathered in a STATIC 10 KB table when the keyframe's compact table fits (the instance count is only known
   // on the device, so the size cannot be a launch parameter); larger tables take RED.ADD straight to L2 (500k votes of a 2M-point
-  // keyframe over ~100 hot addresses cost ~25 us that way)
-  constexpr int kSmemVotes = 3072;
+  // keyframe over ~100 hot addresses cost ~25 us that way).  10 KB + the 1 KB the driver reserves per block is what fits on an SM
+  // BESIDE a resident encoder GEMM CTA (214.6 KB of the 228 KB, 53.7k of the 64k registers; this kernel: 256 threads x 40): the
+  // per-keyframe chain of a batch then advances while the encoder runs instead of waiting for the gaps between its launches.
+  constexpr int kSmemVotes = 2560;
   __shared__ int32_t s_votes[kSmemVotes];
   (void)smem_ints;
   const int n_ins = *n_ins_ptr;
@@ -646,6 +676,116 @@ __global__ void __launch_bounds__(256)
                4 + max(n_masks, 1) * (n_ins + 1));
   if (threadIdx.x == 0) *tail.n_matched_out = __ldcg(tail.table);
   vote_finish_block(tail.table + 4, n_ins, n_masks, tail.area, tail.rows, tail.track_th, tail.mask_ins, tail.next_ins_id);
+}
+
+// ------------------------------------------------------------------------------------------ persistent batch votes
+// ALL keyframes of a batch in ONE launch (sharded maps: 64 dependent per-keyframe launches, each waiting for the slowest of 8
+// GPUs under a busy encoder, made the vote chain the critical path).  One 256-thread block per SM at most, resident for the
+// whole batch; per keyframe f:
+//   every block : ids of keyframe f-1 -> its points, votes of keyframe f of its slice of the map (static shared-memory table,
+//                 flushed to the keyframe's table in L2), then a ticket on `sync[0]`;
+//   block 0     : waits until every block's ticket for f is in, pushes the table into the peers' inboxes / waits for theirs /
+//                 sums (p2p.cuh), reduces the votes per mask, takes the id decisions, releases `sync[1] = f + 1`;
+//   every block : waits for that release (ld.acquire.gpu) before touching keyframe f+1.
+// The blocks of a batch need not all be resident at once for progress: a waiting block only polls, and the ones not yet
+// scheduled are ahead of every later kernel in the block scheduler's queue.
+struct VotePersist {
+  const BatchFrame* frames;      // n_masks, track_th, votes_off per keyframe
+  int F;
+  const int16_t* seg; long long stride;      // dense rows [F][stride]
+  int32_t* ins_ids; long long N;
+  int32_t* tables;
+  const int32_t* area; ovo_vote_row* rows; int32_t* mask_ins; int rows_stride;     // [F][rows_stride]
+  int32_t* next_ins_id; int32_t* n_matched_out;                                   // device counter, [F]
+  int32_t* sync;                 // [0] block tickets, [1] released keyframes (both zero at launch)
+  int world, rank, slots; long long table_cap;
+  XchgPeers peers;
+  int epoch[64];                 // the exchange's epoch of every keyframe slot
+};
+
+__device__ __forceinline__ int ld_acquire_gpu(const int32_t* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// kSmem: gather a block's votes in a static 10 KB table first (single GPU: 500k votes per keyframe); without it (sharded maps: a
+// few 10^4 votes per keyframe and rank, RED.ADD to L2) the resident block leaves the SM's shared memory to the encoder — two
+// attention CTAs need 226.5 of the 228 KB.
+// (<= 40 registers, forced: 256 threads x 40 is what fits beside a resident encoder GEMM CTA; at 60 the block kept the next GEMM's
+// CTA off its SM for the whole batch and the step got SLOWER)
+template <bool kSmem>
+__global__ void __launch_bounds__(256, 6) batch_vote_persistent_kernel(const __grid_constant__ VotePersist P) {
+  constexpr int kSmemVotes = kSmem ? 2560 : 1;
+  __shared__ int32_t s_votes[kSmemVotes];
+  const long long n8 = (P.N + 7) >> 3;
+  for (int f = 0; f <= P.F; ++f) {          // f == F: only the ids of the last keyframe
+    const int n_ins = ld_acquire_gpu(P.next_ins_id);
+    const bool vote = f < P.F;
+    const int n_masks = vote ? P.frames[f].n_masks : 0;
+    int32_t* table = vote ? P.tables + P.frames[f].votes_off : nullptr;
+    int32_t* votes = vote ? table + 4 : nullptr;
+    const int n_votes = n_masks * (n_ins + 1);
+    const bool use_smem = kSmem && vote && n_votes <= kSmemVotes;
+    if (use_smem)
+      for (int i = threadIdx.x; i < n_votes; i += blockDim.x) s_votes[i] = 0;
+    __syncthreads();
+    const int16_t* seg_prev = f > 0 ? P.seg + static_cast<size_t>(f - 1) * P.stride : nullptr;
+    const int16_t* seg_cur = vote ? P.seg + static_cast<size_t>(f) * P.stride : nullptr;
+    const int32_t* mask_ins_prev = f > 0 ? P.mask_ins + static_cast<size_t>(f - 1) * P.rows_stride : nullptr;
+    for (long long q = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; q < n8;
+         q += static_cast<long long>(gridDim.x) * blockDim.x) {
+      uint4 vp = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu), vc = vp;
+      if (seg_prev) vp = *reinterpret_cast<const uint4*>(seg_prev + 8 * q);
+      if (seg_cur) vc = *reinterpret_cast<const uint4*>(seg_cur + 8 * q);
+      const uint32_t neg = (vp.x & vp.y & vp.z & vp.w & vc.x & vc.y & vc.z & vc.w & 0x80008000u);
+      if (neg == 0x80008000u) continue;
+      const int16_t* sp8 = reinterpret_cast<const int16_t*>(&vp);
+      const int16_t* sc8 = reinterpret_cast<const int16_t*>(&vc);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const long long p = 8 * q + j;
+        const int sp = sp8[j], sc = sc8[j];
+        if ((sp < 0 && sc < 0) || p >= P.N) continue;
+        int id = P.ins_ids[p];
+        if (sp >= 0 && id == -1) {
+          const int nid = __ldcg(mask_ins_prev + sp);     // written by block 0 during this launch: L2, not a stale L1 line
+          if (nid >= 0) { id = nid; P.ins_ids[p] = nid; }
+        }
+        if (sc >= 0) {
+          if (id >= n_ins) id = -1;
+          const int key = sc * (n_ins + 1) + (id + 1);
+          atomicAdd(use_smem ? &s_votes[key] : &votes[key], 1);
+        }
+      }
+    }
+    if (!vote) break;
+    if (use_smem) {
+      __syncthreads();
+      for (int i = threadIdx.x; i < n_votes; i += blockDim.x)
+        if (s_votes[i]) atomicAdd(&votes[i], s_votes[i]);
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) atomicAdd(&P.sync[0], 1);
+    if (blockIdx.x == 0) {
+      if (threadIdx.x == 0)
+        while (ld_acquire_gpu(&P.sync[0]) < static_cast<int>(gridDim.x) * (f + 1)) __nanosleep(100);
+      __syncthreads();
+      if (P.world > 1)
+        xchg_block(P.peers, P.rank, P.world, P.slots, f, P.epoch[f] & 1, P.epoch[f], P.table_cap, table, 4 + max(n_masks, 1) * (n_ins + 1));
+      if (threadIdx.x == 0) P.n_matched_out[f] = __ldcg(table);
+      vote_finish_block(votes, n_ins, n_masks, P.area + static_cast<size_t>(f) * P.rows_stride, P.rows + static_cast<size_t>(f) * P.rows_stride,
+                        P.frames[f].track_th, P.mask_ins + static_cast<size_t>(f) * P.rows_stride, P.next_ins_id);
+      __threadfence();
+      __syncthreads();
+      if (threadIdx.x == 0) atomicExch(&P.sync[1], f + 1);
+    } else {
+      if (threadIdx.x == 0)
+        while (ld_acquire_gpu(&P.sync[1]) < f + 1) __nanosleep(500);   // (the exchange takes microseconds: poll gently, the SM is shared)
+      __syncthreads();
+    }
+  }
 }
 
 // the same tail alone (staged protocol: the table was summed by a host-launched collective; or an empty shard)
@@ -1291,11 +1431,13 @@ struct ovo_map {
   int32_t* bt_area = nullptr; int32_t* bt_mask_ins = nullptr;
   float* bt_depth = nullptr; size_t bt_depth_cap = 0;
   int32_t* bt_tables = nullptr; size_t bt_tables_cap = 0;
+  bool bt_last_applied = false;   // the persistent vote kernel already gave the last keyframe's points their ids
   bool bt_valid = false; int bt_F = 0; int64_t bt_N = 0; int bt_next = 0; int32_t* bt_user_tables = nullptr;
   std::vector<int> bt_n_masks, bt_track_th, bt_votes_off, bt_table_len, bt_slots;
   int64_t dense_N = 0, dense_stride = 0; int dense_F = 0; std::vector<int> dense_slots;   // what seg_dense currently holds (from a batched association)
   __nv_bfloat16* feats_bf16 = nullptr; size_t feats_cap = 0;
   // association split in two calls (ovo_map_vote / ovo_map_apply): state of the pending keyframe
+  bool pend_launched = false; cudaEvent_t pend_event = nullptr; cudaStream_t pend_stream = nullptr;
   bool pend_valid = false; int64_t pend_N = 0; int pend_n_ins = 0, pend_n_masks = 0, pend_slot = 0, pend_track_th = 0;
 };
 
@@ -1373,6 +1515,7 @@ void ovo_map_destroy(ovo_map_t* m) {
   cudaFree(m->scratch_list); cudaFree(m->depth_f); cudaFree(m->seg_dense); cudaFree(m->mapped); cudaFree(m->pix_flags); cudaFree(m->text_bf16);
   cudaFree(m->bctl); cudaFreeHost(m->h_bctl); cudaFree(m->bt_area); cudaFree(m->bt_depth); cudaFree(m->bt_tables); cudaFree(m->feats_bf16);
   for (int i = 0; i < ovo_map::kSlots; ++i) cudaFree(m->slot_list[i]);
+  if (m->pend_event) cudaEventDestroy(m->pend_event);
   delete m;
 }
 
@@ -1382,6 +1525,19 @@ int ovo_depth_range(const float* depth_dev, int64_t n, float* range_out_dev, voi
   ovo::depth_range_init_kernel<<<1, 1, 0, stream>>>(reinterpret_cast<int*>(range_out_dev));
   OVO_CHECK_LAUNCH();
   ovo::depth_range_kernel<<<32, 256, 0, stream>>>(depth_dev, static_cast<int>(n), reinterpret_cast<int*>(range_out_dev));
+  OVO_CHECK_LAUNCH();
+  return OVO_OK;
+}
+
+int ovo_depth_filter_batch(const float* depth_dev, int n_frames, int h, int w, float* out_dev, float* ranges_out_dev, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  OVO_REQUIRE(depth_dev && (out_dev || ranges_out_dev) && n_frames > 0 && h >= 4 && w >= 4, "ovo_depth_filter_batch: bad arguments");
+  if (ranges_out_dev) {
+    ovo::depth_range_init_batch_kernel<<<ovo::ceil_div(n_frames, 128), 128, 0, stream>>>(reinterpret_cast<int*>(ranges_out_dev), n_frames);
+    OVO_CHECK_LAUNCH();
+  }
+  ovo::depth_filter_range_batch_kernel<<<dim3(ovo::ceil_div(w, 32), ovo::ceil_div(h, 4), n_frames), dim3(32, 4), 0, stream>>>(
+      depth_dev, h, w, out_dev, reinterpret_cast<int*>(ranges_out_dev));
   OVO_CHECK_LAUNCH();
   return OVO_OK;
 }
@@ -1460,14 +1616,12 @@ static int associate_vote(ovo_map_t* m, const float* xyz_dev, const int32_t* ins
   return OVO_OK;
 }
 
-// Phase 2: per-mask reduce of the (possibly all-reduced) vote table, id decisions, pass 2, one host sync.
-static int associate_apply(ovo_map_t* m, int32_t* ins_ids_dev, int* next_ins_id, ovo_vote_row* votes_host,
-                           int* n_matched_host, cudaStream_t stream) {
-  OVO_REQUIRE(m && next_ins_id && votes_host && n_matched_host, "ovo_map_associate: null argument");
+// Phase 2: per-mask reduce of the (possibly all-reduced) vote table, id decisions, pass 2 and the read-back ENQUEUED (no host
+// sync): associate_finish waits for it.
+static int associate_apply_launch(ovo_map_t* m, int32_t* ins_ids_dev, cudaStream_t stream) {
   if (!m->pend_valid) return ovo::set_error(OVO_E_STATE, "ovo_map_apply called without a pending ovo_map_vote");
-  m->pend_valid = false;
   const int64_t N = m->pend_N;
-  const int n_masks = m->pend_n_masks, n_ins = m->pend_n_ins, kf_slot = m->pend_slot, track_th = m->pend_track_th;
+  const int n_masks = m->pend_n_masks, n_ins = m->pend_n_ins, track_th = m->pend_track_th;
   const int sms = ovo::num_sms();
   if (n_masks > 0) {
     ovo::vote_reduce_kernel<<<n_masks, 128, 0, stream>>>(m->votes, n_ins, m->area, m->rows);
@@ -1481,7 +1635,21 @@ static int associate_apply(ovo_map_t* m, int32_t* ins_ids_dev, int* next_ins_id,
   }
   OVO_CUDA(cudaMemcpyAsync(m->h_counters, m->counters, 4 * sizeof(int32_t) + static_cast<size_t>(n_masks) * sizeof(ovo_vote_row),
                            cudaMemcpyDeviceToHost, stream));   // counters + rows are contiguous: one read-back
-  OVO_CUDA(cudaStreamSynchronize(stream));  // the one host sync of the association step
+  if (!m->pend_event) OVO_CUDA(cudaEventCreateWithFlags(&m->pend_event, cudaEventDisableTiming));
+  OVO_CUDA(cudaEventRecord(m->pend_event, stream));
+  m->pend_stream = stream;
+  m->pend_launched = true;
+  return OVO_OK;
+}
+
+// The one host synchronisation of an association: waits for the read-back, hands the rows to the caller, keeps the match list.
+static int associate_finish(ovo_map_t* m, int* next_ins_id, ovo_vote_row* votes_host, int* n_matched_host) {
+  OVO_REQUIRE(m && next_ins_id && votes_host && n_matched_host, "ovo_map_associate: null argument");
+  if (!m->pend_valid || !m->pend_launched) return ovo::set_error(OVO_E_STATE, "no association is in flight on this handle");
+  m->pend_valid = false; m->pend_launched = false;
+  cudaStream_t stream = m->pend_stream;
+  const int n_masks = m->pend_n_masks, kf_slot = m->pend_slot;
+  OVO_CUDA(cudaEventSynchronize(m->pend_event));
   if (n_masks > 0) memcpy(votes_host, m->h_rows, n_masks * sizeof(ovo_vote_row));
   *n_matched_host = m->h_counters[1];
   *next_ins_id = m->h_counters[2];
@@ -1494,6 +1662,30 @@ static int associate_apply(ovo_map_t* m, int32_t* ins_ids_dev, int* next_ins_id,
   for (size_t i = 0; i < m->dense_slots.size(); ++i)
     if (m->dense_slots[i] == kf_slot) m->dense_slots[i] = -1;   // the slot's dense row (of an earlier batch) is stale now
   return OVO_OK;
+}
+
+static int associate_apply(ovo_map_t* m, int32_t* ins_ids_dev, int* next_ins_id, ovo_vote_row* votes_host,
+                           int* n_matched_host, cudaStream_t stream) {
+  OVO_REQUIRE(m && next_ins_id && votes_host && n_matched_host, "ovo_map_associate: null argument");
+  OVO_TRY(associate_apply_launch(m, ins_ids_dev, stream));
+  return associate_finish(m, next_ins_id, votes_host, n_matched_host);
+}
+
+// ovo_map_associate in two halves: everything enqueued, nothing waited for (the caller goes on with its own work while the
+// GPU runs the association) ...
+int ovo_map_associate_launch(ovo_map_t* m, const float* xyz_dev, int32_t* ins_ids_dev, int64_t N, const ovo_frame* f, int next_ins_id,
+                             int kf_slot, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  OVO_REQUIRE(m && !m->pend_valid, "ovo_map_associate_launch: an association is already in flight on this handle (ovo_map_associate_wait first)");
+  ovo::ProfScope prof(stream, ovo::PROF_ASSOC, 0.0, static_cast<double>(N) * 20 + (f ? static_cast<double>(f->h) * f->w * 8 : 0.0));
+  OVO_TRY(associate_vote(m, xyz_dev, ins_ids_dev, N, f, next_ins_id, kf_slot, stream));
+  const int r = associate_apply_launch(m, ins_ids_dev, stream);
+  if (r != OVO_OK) m->pend_valid = false;
+  return r;
+}
+// ... and the one host synchronisation, whenever the caller needs the rows (votes_host [n_masks of the launch]).
+int ovo_map_associate_wait(ovo_map_t* m, int* next_ins_id, ovo_vote_row* votes_host, int* n_matched_host) {
+  return associate_finish(m, next_ins_id, votes_host, n_matched_host);
 }
 
 
@@ -1649,7 +1841,7 @@ int ovo_map_batch_begin(ovo_map_t* m, const float* xyz_dev, const int32_t* ins_i
       OVO_CHECK_LAUNCH();
     }
   }
-  m->bt_valid = true; m->bt_F = F; m->bt_N = N; m->bt_next = next_ins_id;
+  m->bt_valid = true; m->bt_F = F; m->bt_N = N; m->bt_next = next_ins_id; m->bt_last_applied = false;
   m->dense_slots.assign(m->bt_slots.begin(), m->bt_slots.end()); m->dense_N = N; m->dense_F = F; m->dense_stride = stride;
   for (int f = 0; f < F; ++f)
     if (m->bt_slots[f] >= 0) m->slot_n[m->bt_slots[f]] = 0;   // these slots hold dense rows now, not lists
@@ -1738,7 +1930,7 @@ int ovo_map_batch_end(ovo_map_t* m, int32_t* ins_ids_dev, int* next_ins_id, ovo_
   const int F = m->bt_F;
   const int64_t N = m->bt_N;
   for (int f = 0; f < F; ++f) OVO_REQUIRE(m->bt_n_masks[f] <= votes_stride, "ovo_map_batch_end: votes_stride %d < n_masks %d", votes_stride, m->bt_n_masks[f]);
-  if (N > 0 && m->bt_n_masks[F - 1] > 0) {
+  if (N > 0 && m->bt_n_masks[F - 1] > 0 && !m->bt_last_applied) {
     const int blocks = static_cast<int>(std::min<long long>(((N + 7) / 8 + 255) / 256, ovo::num_sms() * 8LL));
     ovo::batch_vote_scan_kernel<<<blocks, 256, 0, stream>>>(m->seg_dense + static_cast<size_t>(F - 1) * static_cast<size_t>(m->dense_stride),
                                                            m->bt_mask_ins + static_cast<size_t>(F - 1) * m->bt_stride, nullptr, ins_ids_dev, N,
@@ -1785,6 +1977,34 @@ static int batch_run_fused(ovo_map_t* m, ovo_xchg* xchg, int32_t* ins_ids_dev, c
   return OVO_OK;
 }
 
+// all keyframes of the batch in ONE persistent launch (batch_vote_persistent_kernel); the ids of the last keyframe included
+static int batch_run_persistent(ovo_map_t* m, ovo_xchg* xchg, int32_t* ins_ids_dev, cudaStream_t stream) {
+  const BatchCtl L(m->bt_fcap, m->bt_stride);
+  ovo::VotePersist P;
+  memset(&P, 0, sizeof(P));
+  P.frames = reinterpret_cast<const ovo::BatchFrame*>(m->bctl + L.frames);
+  P.F = m->bt_F;
+  P.seg = m->seg_dense; P.stride = m->dense_stride;
+  P.ins_ids = ins_ids_dev; P.N = m->bt_N;
+  P.tables = m->bt_user_tables;
+  P.area = m->bt_area; P.rows = reinterpret_cast<ovo_vote_row*>(m->bctl + L.rows); P.mask_ins = m->bt_mask_ins; P.rows_stride = m->bt_stride;
+  P.next_ins_id = reinterpret_cast<int32_t*>(m->bctl + L.next);
+  P.n_matched_out = reinterpret_cast<int32_t*>(m->bctl + L.n_matched);
+  P.sync = reinterpret_cast<int32_t*>(m->bctl + L.next) + 2;          // [2], [3] of the 4-int state: zeroed by the upload of batch_begin
+  P.world = 1;
+  if (xchg != nullptr && xchg->world > 1) {
+    P.world = xchg->world; P.rank = xchg->rank; P.slots = xchg->slots; P.table_cap = xchg->table_cap; P.peers = xchg->peers;
+    for (int f = 0; f < m->bt_F; ++f) P.epoch[f] = ++(*xchg->epochs)[f];
+  }
+  const long long n8 = (m->bt_N + 7) / 8;
+  const int blocks = static_cast<int>(std::max<long long>(1, std::min<long long>((n8 + 255) / 256, ovo::num_sms())));
+  if (P.world > 1) ovo::batch_vote_persistent_kernel<false><<<blocks, 256, 0, stream>>>(P);
+  else ovo::batch_vote_persistent_kernel<true><<<blocks, 256, 0, stream>>>(P);
+  OVO_CHECK_LAUNCH();
+  m->bt_last_applied = true;
+  return OVO_OK;
+}
+
 int ovo_map_associate_batch_sharded(ovo_map_t* m, ovo_xchg_t* xchg, const float* xyz_dev, int32_t* ins_ids_dev, int64_t N,
                                     const ovo_frame* frames, int F, const int* kf_slots, int* next_ins_id, ovo_vote_row* votes_host,
                                     int votes_stride, int* n_matched_host, int32_t* mask_ins_out_dev, void* stream_) {
@@ -1798,7 +2018,10 @@ int ovo_map_associate_batch_sharded(ovo_map_t* m, ovo_xchg_t* xchg, const float*
       return ovo::set_error(OVO_E_INVALID, "ovo_map_associate_batch_sharded: table of keyframe %d (%d ints) exceeds the exchange's %lld", f,
                             m->bt_table_len[f], xchg->table_cap);
     }
-  OVO_TRY(batch_run_fused(m, xchg, ins_ids_dev, static_cast<cudaStream_t>(stream_)));
+  // one persistent launch for the whole batch (OVO_B200_VOTE=launches: one launch per keyframe, the A/B alternative)
+  const char* mode = getenv("OVO_B200_VOTE");
+  if (mode && mode[0] == 'l') OVO_TRY(batch_run_fused(m, xchg, ins_ids_dev, static_cast<cudaStream_t>(stream_)));
+  else OVO_TRY(batch_run_persistent(m, xchg, ins_ids_dev, static_cast<cudaStream_t>(stream_)));
   return ovo_map_batch_end(m, ins_ids_dev, next_ins_id, votes_host, votes_stride, n_matched_host, mask_ins_out_dev, stream_);
 }
 
@@ -1811,7 +2034,11 @@ int ovo_map_associate_batch(ovo_map_t* m, const float* xyz_dev, int32_t* ins_ids
   for (int f = 0; frames && f < F; ++f) px += static_cast<double>(frames[f].h) * frames[f].w * 8;
   ovo::ProfScope prof(stream, ovo::PROF_ASSOC, 0.0, static_cast<double>(N) * (12.0 + F * 14.0) + px);
   OVO_TRY(ovo_map_batch_begin(m, xyz_dev, ins_ids_dev, N, frames, F, kf_slots, *next_ins_id, nullptr, 0, stream_));
-  OVO_TRY(batch_run_fused(m, nullptr, ins_ids_dev, stream));
+  {
+    const char* mode = getenv("OVO_B200_VOTE");
+    if (N == 0 || (mode && mode[0] == 'l')) OVO_TRY(batch_run_fused(m, nullptr, ins_ids_dev, stream));
+    else OVO_TRY(batch_run_persistent(m, nullptr, ins_ids_dev, stream));
+  }
   return ovo_map_batch_end(m, ins_ids_dev, next_ins_id, votes_host, votes_stride, n_matched_host, mask_ins_out_dev, stream_);
 }
 

@@ -69,6 +69,60 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// Packing of freshly mapped points for the fixed-size all-to-all of a sharded map (ovo_b200/sharding.py route_new_points_fixed):
+// record slot dst * cap + (position of the point among this rank's points of shard dst, creation order) <- (x, y, z, id); unused
+// slots keep a far-away sentinel (id -1).  ONE block: every thread takes a contiguous run of points, counts them per shard, the
+// per-shard counts are scanned over the threads (stable order, deterministic), then the records are scattered.
+__device__ __forceinline__ int shard_of(float x, float y, float z, float cell, int world) {
+  const long long vx = static_cast<long long>(floorf(__fdiv_rn(x, cell))), vy = static_cast<long long>(floorf(__fdiv_rn(y, cell))),
+                  vz = static_cast<long long>(floorf(__fdiv_rn(z, cell)));
+  const long long h = (vx * 73856093LL) ^ (vy * 19349663LL) ^ (vz * 83492791LL);
+  return static_cast<int>(((h % world) + world) % world);
+}
+
+__global__ void __launch_bounds__(1024)
+    route_pack_kernel(const float* __restrict__ xyz, const int32_t* __restrict__ ids, int n, int world, float cell, int cap, float far,
+                      float4* __restrict__ rec, int32_t* __restrict__ overflow) {
+  // tiles of 1024 consecutive points (coalesced reads); inside a tile a point's position in its shard's run = the shard's running
+  // base + the points of that shard in lower warps of the tile + those in lower lanes of its warp (stable: creation order)
+  __shared__ int s_wcnt[16][32];     // per shard, per warp: points of the tile
+  __shared__ int s_base[16];         // per shard: points of the earlier tiles
+  const int t = threadIdx.x, T = blockDim.x, warp = t >> 5, lane = t & 31;
+  const float4 sentinel = make_float4(far, far, far, __int_as_float(-1));
+  for (int i = t; i < world * cap; i += T) rec[i] = sentinel;
+  if (t < 16) s_base[t] = 0;
+  __syncthreads();
+  for (int base = 0; base < n; base += T) {
+    const int i = base + t;
+    float x = 0.f, y = 0.f, z = 0.f;
+    int d = -1;
+    if (i < n) {
+      x = xyz[3 * i]; y = xyz[3 * i + 1]; z = xyz[3 * i + 2];
+      d = shard_of(x, y, z, cell, world);
+    }
+    int rank = 0;
+    for (int k = 0; k < world; ++k) {
+      const unsigned bal = __ballot_sync(0xffffffffu, d == k);
+      if (d == k) rank = __popc(bal & ((1u << lane) - 1));
+      if (lane == 0) s_wcnt[k][warp] = __popc(bal);
+    }
+    __syncthreads();
+    int before = 0;
+    if (d >= 0)
+      for (int w = 0; w < warp; ++w) before += s_wcnt[d][w];
+    const int p = d >= 0 ? s_base[d] + before + rank : 0;
+    if (d >= 0 && p < cap) rec[static_cast<size_t>(d) * cap + p] = make_float4(x, y, z, __int_as_float(ids[i]));
+    __syncthreads();
+    if (t < world) {
+      int tot = 0;
+      for (int w = 0; w < 32; ++w) tot += s_wcnt[t][w];
+      s_base[t] += tot;
+    }
+    __syncthreads();
+  }
+  if (t < world && s_base[t] > cap) atomicAdd(overflow, s_base[t] - cap);
+}
+
 }  // namespace ovo
 
 extern "C" {
@@ -139,6 +193,17 @@ int ovo_xchg_exchange(ovo_xchg_t* x, int32_t* table_dev, int n_ints, const int32
                                                                                     epoch, x->table_cap, table_dev, n_ints, n_ins_dev, n_masks);
     OVO_CHECK_LAUNCH();
   }
+  return OVO_OK;
+}
+
+int ovo_route_pack(const float* xyz_dev, const int32_t* ids_dev, int n, int world, float cell, int cap_per_dst, float far_value,
+                   float* records_out_dev, int32_t* overflow_dev, void* stream) {
+  OVO_REQUIRE(xyz_dev && ids_dev && records_out_dev && overflow_dev && n >= 0 && world >= 1 && world <= 16 && cap_per_dst > 0 && cell > 0.f,
+              "ovo_route_pack: bad arguments (world <= 16)");
+  OVO_REQUIRE((reinterpret_cast<uintptr_t>(records_out_dev) & 15) == 0, "ovo_route_pack: records must be 16-byte aligned");
+  ovo::route_pack_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(
+      xyz_dev, ids_dev, n, world, cell, cap_per_dst, far_value, reinterpret_cast<float4*>(records_out_dev), overflow_dev);
+  OVO_CHECK_LAUNCH();
   return OVO_OK;
 }
 

@@ -49,6 +49,18 @@ class SemanticMap:
         check(self.lib.ovo_depth_filter(ptr(depth), depth.shape[0], depth.shape[1], ptr(out), stream_ptr(self.device)), "ovo_depth_filter")
         return out
 
+    def depth_filter_batch(self, depths: torch.Tensor, out: torch.Tensor | None = None, ranges: torch.Tensor | None = None):
+        """F depth maps [F,h,w] in one launch -> (filtered maps [F,h,w], raw-depth ranges [F,2]); see depth_filter / depth_range."""
+        assert depths.is_cuda and depths.dtype == torch.float32 and depths.is_contiguous() and depths.dim() == 3
+        if out is None:
+            out = torch.empty_like(depths)
+        if ranges is None:
+            ranges = torch.empty(depths.shape[0], 2, device=self.device, dtype=torch.float32)
+        assert out.is_contiguous() and ranges.is_contiguous() and out.shape == depths.shape
+        check(self.lib.ovo_depth_filter_batch(ptr(depths), depths.shape[0], depths.shape[1], depths.shape[2], ptr(out), ptr(ranges),
+                                              stream_ptr(self.device)), "ovo_depth_filter_batch")
+        return out, ranges
+
     def depth_range(self, depth: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
         """[min, max] of the depth values > 0 (the raw-depth range the frustum is built from), f32 [2] on the device."""
         depth = depth.to(self.device, torch.float32).contiguous()
@@ -66,21 +78,9 @@ class SemanticMap:
         assert xyz.is_cuda and ins_ids.is_cuda and depth.is_cuda and seg_map.is_cuda
         assert xyz.dtype == torch.float32 and ins_ids.dtype == torch.int32 and seg_map.dtype == torch.int32
         assert xyz.is_contiguous() and ins_ids.is_contiguous() and depth.is_contiguous() and seg_map.is_contiguous()
-        c2w = np.asarray(c2w, np.float32).reshape(4, 4)
-        if w2c is None:
-            w2c = torch.linalg.inv(torch.from_numpy(c2w)).numpy()      # ovo.py:216
-        K = np.asarray(K, np.float32).reshape(3, 3)
         if n_masks is None:
             n_masks = int(seg_map.max().item()) + 1                     # ovo.py:255
-        f = Frame()
-        f.depth_dev = ptr(depth); f.h, f.w = depth.shape
-        f.seg_map_dev = ptr(seg_map); f.H, f.W = seg_map.shape
-        f.n_masks = n_masks
-        f.c2w[:] = c2w.reshape(-1).tolist(); f.w2c[:] = np.asarray(w2c, np.float32).reshape(-1).tolist()
-        f.K[:] = K.reshape(-1).tolist()
-        f.match_th, f.track_th, f.depth_filter = float(match_th), int(track_th), int(bool(depth_filter))
-        if len(rgb_depth_ratio) > 0:
-            f.has_ratio, f.ratio_h, f.ratio_w, f.crop_edge = 1, float(rgb_depth_ratio[0]), float(rgb_depth_ratio[1]), int(rgb_depth_ratio[2])
+        f = self._frame(depth, seg_map, c2w, K, match_th, track_th, depth_filter, rgb_depth_ratio, n_masks, w2c)
         rows = (VoteRow * max(n_masks, 1))()
         nxt, nm = C.c_int(next_ins_id), C.c_int(0)
         check(self.lib.ovo_map_associate(self.handle, ptr(xyz), ptr(ins_ids), xyz.shape[0], C.byref(f), C.byref(nxt), rows,
@@ -88,6 +88,27 @@ class SemanticMap:
         arr = np.frombuffer(rows, dtype=np.int32).reshape(-1, 8)[:n_masks]
         votes = {k: arr[:, i].copy() for i, k in enumerate(VOTE_FIELDS)}
         return votes, nm.value, nxt.value
+
+    def associate_launch(self, xyz, ins_ids, depth, seg_map, c2w, K, next_ins_id: int, match_th=0.05, track_th=100, depth_filter=True,
+                         rgb_depth_ratio=(), kf_slot: int = 0, n_masks: int | None = None, w2c=None) -> None:
+        """`associate` without the host synchronisation: everything is enqueued, `associate_wait()` returns the results."""
+        assert xyz.is_cuda and ins_ids.is_cuda and xyz.dtype == torch.float32 and ins_ids.dtype == torch.int32
+        assert xyz.is_contiguous() and ins_ids.is_contiguous() and depth.is_contiguous() and seg_map.is_contiguous()
+        if n_masks is None:
+            n_masks = int(seg_map.max().item()) + 1
+        f = self._frame(depth, seg_map, c2w, K, match_th, track_th, depth_filter, rgb_depth_ratio, n_masks, w2c)
+        check(self.lib.ovo_map_associate_launch(self.handle, ptr(xyz), ptr(ins_ids), xyz.shape[0], C.byref(f), int(next_ins_id), kf_slot,
+                                                stream_ptr(self.device)), "ovo_map_associate_launch")
+        self._launched = (n_masks, (xyz, ins_ids, depth, seg_map))        # keep the operands alive until the wait
+
+    def associate_wait(self):
+        n_masks, _ = self._launched
+        self._launched = None
+        rows = (VoteRow * max(n_masks, 1))()
+        nxt, nm = C.c_int(0), C.c_int(0)
+        check(self.lib.ovo_map_associate_wait(self.handle, C.byref(nxt), rows, C.byref(nm)), "ovo_map_associate_wait")
+        arr = np.frombuffer(rows, dtype=np.int32).reshape(-1, 8)[:n_masks]
+        return {k: arr[:, i].copy() for i, k in enumerate(VOTE_FIELDS)}, nm.value, nxt.value
 
     # ---- the same association in two halves, for a map sharded over ranks (ovo_b200/sharding.py)
     def _frame(self, depth, seg_map, c2w, K, match_th, track_th, depth_filter, rgb_depth_ratio, n_masks, w2c):

@@ -129,19 +129,28 @@ def route_new_points_fixed(xyz: torch.Tensor, ids: torch.Tensor, cap_per_dst: in
     no frustum ever contains.  Returns (xyz [world*cap,3], ids [world*cap], overflow flag tensor: > 0 if some shard received
     more than cap_per_dst points from one source and dropped the surplus — size cap_per_dst with a margin over n/world)."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
-    dst = shard_of_points(xyz, world, cell)
-    order = torch.argsort(dst, stable=True)
-    sdst = dst[order]
-    first = torch.searchsorted(sdst, torch.arange(world, device=xyz.device, dtype=sdst.dtype))
-    pos = torch.arange(xyz.shape[0], device=xyz.device) - first[sdst]            # position inside its destination's run
-    keep = pos < cap_per_dst
-    overflow = (~keep).sum()
-    rec = torch.full((world * cap_per_dst, 4), far, dtype=torch.float32, device=xyz.device)
-    rec[:, 3] = torch.full((world * cap_per_dst,), -1, dtype=torch.int32, device=xyz.device).view(torch.float32)
-    slot = (sdst * cap_per_dst + pos)[keep]
-    src = order[keep]
-    rec[slot, :3] = xyz[src]
-    rec[slot, 3] = ids[src].to(torch.int32).view(torch.float32)
+    if xyz.is_cuda and world <= 16:
+        # one kernel (ovo_route_pack): hash, stable per-shard positions, records — instead of ~15 torch launches
+        from . import _lib
+        xyz_c, ids_c = xyz.to(torch.float32).contiguous(), ids.to(torch.int32).contiguous()
+        rec = torch.empty(world * cap_per_dst, 4, dtype=torch.float32, device=xyz.device)
+        overflow = torch.zeros((), dtype=torch.int32, device=xyz.device)
+        _lib.check(_lib.lib().ovo_route_pack(_lib.ptr(xyz_c), _lib.ptr(ids_c), xyz_c.shape[0], world, float(cell), int(cap_per_dst), float(far),
+                                             _lib.ptr(rec), _lib.ptr(overflow), _lib.stream_ptr(xyz.device)), "ovo_route_pack")
+    else:
+        dst = shard_of_points(xyz, world, cell)
+        order = torch.argsort(dst, stable=True)
+        sdst = dst[order]
+        first = torch.searchsorted(sdst, torch.arange(world, device=xyz.device, dtype=sdst.dtype))
+        pos = torch.arange(xyz.shape[0], device=xyz.device) - first[sdst]            # position inside its destination's run
+        keep = pos < cap_per_dst
+        overflow = (~keep).sum()
+        rec = torch.full((world * cap_per_dst, 4), far, dtype=torch.float32, device=xyz.device)
+        rec[:, 3] = torch.full((world * cap_per_dst,), -1, dtype=torch.int32, device=xyz.device).view(torch.float32)
+        slot = (sdst * cap_per_dst + pos)[keep]
+        src = order[keep]
+        rec[slot, :3] = xyz[src]
+        rec[slot, 3] = ids[src].to(torch.int32).view(torch.float32)
     if world > 1:
         out = torch.empty_like(rec)
         dist.all_to_all_single(out, rec, group=group)

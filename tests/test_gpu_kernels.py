@@ -393,3 +393,55 @@ def test_map_producer_matches_oracle(sm):
     pts, pids, obj = pm.get_map()
     assert pts.shape[0] == len(xyz) and (pids.reshape(-1).cpu().numpy() == np.arange(len(xyz))).all() and int(obj.max()) == -1
     assert pm.capacity >= len(xyz) > 100000          # grew past the initial reservation
+
+
+def test_associate_launch_wait_equals_associate(sm):
+    """ovo_map_associate in two halves (everything enqueued, then ONE host synchronisation whenever the caller needs the rows):
+    the same rows, ids and match list as the one-call form; a second launch before the wait is refused."""
+    K = synth.intrinsics(); d = synth.depth_map(); N = 200_000
+    xyz, ids, ins = synth.point_map(N, d, K, synth.pose(0), seed=2, frac_visible=0.5)
+    seg, _ = synth.grid_masks()
+    xyz_d, ins_a, d_d, seg_d = _dev(xyz, ins, d, seg)
+    ins_b = ins_a.clone()
+    va, na, xa = sm.associate(xyz_d, ins_a, d_d, seg_d, synth.pose(0), K, 0, kf_slot=5)
+    pa = sm.matches(5, na).cpu().numpy()
+    sm.associate_launch(xyz_d, ins_b, d_d, seg_d, synth.pose(0), K, 0, kf_slot=6)
+    with pytest.raises(RuntimeError):
+        sm.associate_launch(xyz_d, ins_b, d_d, seg_d, synth.pose(0), K, 0, kf_slot=7)
+    host_work = sum(i * i for i in range(10000))                  # (the caller's own work overlaps the GPU here)
+    vb, nb, xb = sm.associate_wait()
+    pb = sm.matches(6, nb).cpu().numpy()
+    assert host_work > 0 and na == nb and xa == xb and torch.equal(ins_a, ins_b)
+    for k in va:
+        assert (va[k] == vb[k]).all(), k
+    assert (pa[np.lexsort((pa[:, 1], pa[:, 0]))] == pb[np.lexsort((pb[:, 1], pb[:, 0]))]).all()
+
+
+@pytest.mark.parametrize("world,n,cap", [(8, 76800, 14464), (2, 5000, 4000), (5, 3000, 500), (16, 1000, 200)])
+def test_route_pack_kernel_matches_the_torch_rule(world, n, cap):
+    """ovo_route_pack (one kernel) == the torch formulation of route_new_points_fixed: shard of every point = shard_of_points,
+    slot = its rank among this rank's points of that shard in creation order, sentinels elsewhere, surplus counted."""
+    from ovo_b200 import _lib
+    from ovo_b200.sharding import shard_of_points
+    rng = np.random.default_rng(world)
+    xyz = rng.uniform(-8, 8, (n, 3)).astype(np.float32)
+    xyz[::97] = np.round(xyz[::97] * 4) / 4                      # points exactly on voxel faces
+    ids = (np.arange(n) + 1000).astype(np.int32)
+    xd, idd = torch.from_numpy(xyz).cuda(), torch.from_numpy(ids).cuda()
+    rec = torch.empty(world * cap, 4, device="cuda")
+    ovf = torch.zeros((), dtype=torch.int32, device="cuda")
+    _lib.check(_lib.lib().ovo_route_pack(_lib.ptr(xd), _lib.ptr(idd), n, world, 0.25, cap, 1.0e6, _lib.ptr(rec), _lib.ptr(ovf),
+                                         _lib.stream_ptr()), "ovo_route_pack")
+    got = rec.cpu().numpy()
+    dst = shard_of_points(xyz, world)
+    exp = np.full((world * cap, 4), 1.0e6, np.float32)
+    exp[:, 3] = np.int32(-1).view(np.float32)
+    surplus = 0
+    for d in range(world):
+        sel = np.nonzero(dst == d)[0]
+        surplus += max(0, len(sel) - cap)
+        sel = sel[:cap]
+        exp[d * cap: d * cap + len(sel), :3] = xyz[sel]
+        exp[d * cap: d * cap + len(sel), 3] = ids[sel].view(np.float32)
+    assert (got.view(np.int32) == exp.view(np.int32)).all() and int(ovf) == surplus
+    assert (surplus > 0) == (world == 5)
