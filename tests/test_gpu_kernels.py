@@ -235,11 +235,14 @@ def _batch_scene(N, F, seed=9):
     return K, xyz, ins, frames
 
 
+@pytest.mark.parametrize("vote_mode", ["launches", "persistent"])
 @pytest.mark.parametrize("N,F,track_th", [(120000, 5, 100), (0, 2, 100), (300, 3, 2), (70000, 19, 60)])
-def test_associate_batch_equals_sequential_and_oracle(sm, N, F, track_th):
-    """One pass over the map for F keyframes (id decisions on the device, one host sync) == F single-keyframe associations ==
+def test_associate_batch_equals_sequential_and_oracle(sm, monkeypatch, N, F, track_th, vote_mode):
+    """Both vote schedules of the batch (one launch per keyframe — the default — and the single persistent launch,
+    OVO_B200_VOTE=persistent).  One pass over the map for F keyframes (id decisions on the device, one host sync) == F single-keyframe associations ==
     oracle/fusion.py: votes, n_matched, next_ins_id, the per-point ids and the mask -> instance table, bit for bit; 19 keyframes
     exercise the second shared-memory group of the pass (16 keyframes at a time)."""
+    monkeypatch.setenv("OVO_B200_VOTE", vote_mode)
     K, xyz, ins, frames = _batch_scene(max(N, 1), F)
     xyz, ins = xyz[:N], ins[:N]
     xyz_d, ins_a = _dev(xyz, ins)

@@ -125,7 +125,10 @@ def _run_batch(rank, world, port, q):
     v_ref, nm_ref, nxt_ref = sm_full.associate_batch(xf, inf_, dd, sd, c2ws, K, 0, nms, track_th=60)
     mine = np.nonzero(shard_of_points(xyz, world) == rank)[0]
     out = {}
-    for mode in ("nccl", "p2p"):
+    for mode in ("nccl", "p2p", "p2p_persistent"):   # the last: the whole batch in one persistent launch (OVO_B200_VOTE)
+        os.environ["OVO_B200_VOTE"] = "persistent" if mode == "p2p_persistent" else "launches"
+        inf_ = torch.from_numpy(ins).to(dev)
+        sm_full.associate_batch(xf, inf_, dd, sd, c2ws, K, 0, nms, track_th=60)
         xl, il = torch.from_numpy(xyz[mine]).to(dev), torch.from_numpy(ins[mine]).to(dev)
         if mode == "nccl":
             tables = torch.zeros(SemanticMap.batch_tables_size(0, nms), dtype=torch.int32, device=dev)
@@ -135,7 +138,7 @@ def _run_batch(rank, world, port, q):
             v, nm, nxt = x.associate_batch(xl, il, dd, sd, c2ws, K, 0, nms, track_th=60)
             v2, nm2, nxt2 = x.associate_batch(xl, il, dd, sd, c2ws, K, nxt, nms, track_th=60)   # a second batch re-uses the inbox (parities)
             r2 = sm_full.associate_batch(xf, inf_, dd, sd, c2ws, K, nxt_ref, nms, track_th=60)
-            out["second"] = nxt2 == r2[2] and nm2 == r2[1] and all((v2[f][k] == r2[0][f][k]).all() for f in range(F) for k in v2[f]) \
+            out["second_" + mode] = nxt2 == r2[2] and nm2 == r2[1] and all((v2[f][k] == r2[0][f][k]).all() for f in range(F) for k in v2[f]) \
                 and bool(torch.equal(il, inf_[torch.from_numpy(mine).to(dev)]))
             inf_ = torch.from_numpy(ins).to(dev)
             sm_full.associate_batch(xf, inf_, dd, sd, c2ws, K, 0, nms, track_th=60)
@@ -152,4 +155,4 @@ def _run_batch(rank, world, port, q):
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
 def test_sharded_batch_association_nccl_and_fused_peer_exchange():
     for r in _spawn(_run_batch, 2):
-        assert r["nccl"] and r["p2p"] and r["second"], r
+        assert r["nccl"] and r["p2p"] and r["p2p_persistent"] and r["second_p2p"] and r["second_p2p_persistent"], r

@@ -1,0 +1,15 @@
+#!/bin/bash
+# same-box A/B of tuning switches on the device-resident step
+cd /root/repo
+run() { # label, env...
+  local l=$1; shift
+  env "$@" python bench.py --only-value --steps 40 --warmup 5 2>&1 | tail -1 | python -c "
+import sys, json
+d = json.loads(sys.stdin.read()); print('$l', d['value'], d['ms_per_step'])"
+}
+python -m pytest tests/test_gpu_kernels.py -m gpu -x -q -k "associate_batch" 2>&1 | tail -2
+run default X=1
+run resid-bn128 OVO_B200_RESID_BN=128
+run default X=1
+run resid-bn128 OVO_B200_RESID_BN=128
+run persistent OVO_B200_VOTE=persistent
