@@ -49,7 +49,8 @@ constexpr float kRescaleLog2 = 32.f;   // raise a row's reference maximum only w
 __global__ void __launch_bounds__(kAttnThreads, 2)
     attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                          const __grid_constant__ CUtensorMap tmV, __nv_bfloat16* __restrict__ out, int seq,
-                         int seq_pad, int heads, int ld_out, float scale_log2e, int causal, int dbg, int qtiles, int n_items) {
+                         int seq_pad, int heads, int ld_out, float scale_log2e, int causal, int dbg, int qtiles, int n_items,
+                         const __nv_bfloat16* __restrict__ k_glob, const __nv_bfloat16* __restrict__ v_glob, int tail1) {
   griddep_launch();
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();  // the 128B swizzle needs 1024-byte aligned tiles
@@ -125,7 +126,10 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
   q0 = qt * 128;
   // causal: keys beyond the last query of this tile are never needed; blocks of pure padding are skipped
   // (dbg bits are measurement aids, results are wrong with them: 1 = no softmax math / P stores, 2 = no MMA, 4 = one key block)
-  nb = (dbg & 4) ? 1 : min(causal ? min(nblk, 2 * qt + 2) : nblk, (seq + kAttnKB - 1) / kAttnKB);
+  // tail1 (seq % 64 == 1, e.g. 24*24 patches + the class token = 577): the single key of the last block does not get a
+  // 64-key block of its own — the softmax threads take it as a rank-1 term (q.k_last on the FMA pipe, p_last * v_last added
+  // to the accumulator in the epilogue), which removes one of ten block iterations of every work item.
+  nb = (dbg & 4) ? 1 : min(causal ? min(nblk, 2 * qt + 2) : nblk, (seq - tail1 + kAttnKB - 1) / kAttnKB);
 
   if (warp == 8) {
     // ---------------------------------------------------------------- TMA + MMA warp (one elected lane)
@@ -171,6 +175,14 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
   float l_run = 0.f;             // partial row sum over this thread's keys
   float m_loc = -INFINITY;       // maximum this thread has seen over its keys so far
   int rescale = 0;               // CTA-uniform: some row's maximum outgrew its reference by 2^kRescaleLog2 in the last block
+  float s_tail = -INFINITY;      // raw score of the tail key (tail1), identical in both halves
+  // this half's 32 dims of the tail key / 32 output columns of its V row (bf16, 64 B each): pulled into L1 now, read when used
+  const uint4* kt_ptr = reinterpret_cast<const uint4*>(k_glob + (static_cast<size_t>(bh) * seq_pad + (seq - 1)) * 64 + half * 32);
+  const uint4* vt_ptr = reinterpret_cast<const uint4*>(v_glob + (static_cast<size_t>(bh) * seq_pad + (seq - 1)) * 64 + half * 32);
+  if (tail1 && (tid & 31) == 0) {
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(kt_ptr));
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(vt_ptr));
+  }
 
   for (int j = 0; j < nb; ++j) {
     const int g = g0 + j;                              // global block index of this CTA: ring slots and parities
@@ -204,8 +216,31 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
       }
       const float mine = fmaxf(fmaxf(mp[0], mp[1]), fmaxf(mp[2], mp[3]));
       s_x[half * 128 + row] = mine;
+      float dot = 0.f;
+      if (tail1) {
+        // Q landed before S_0 was computed; the wait (already complete) orders this thread's generic-proxy reads after the TMA
+        mbar_wait(bar_q, n_done & 1);
+        float d4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const uint4 qv = *reinterpret_cast<const uint4*>(sQ + row * 128 + (((half * 4 + c) ^ r8) << 4));
+          const uint4 kv = __ldg(kt_ptr + c);
+          const uint32_t qa[4] = {qv.x, qv.y, qv.z, qv.w}, ka[4] = {kv.x, kv.y, kv.z, kv.w};
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            d4[w] = fmaf(__uint_as_float(qa[w] << 16), __uint_as_float(ka[w] << 16), d4[w]);
+            d4[w] = fmaf(__uint_as_float(qa[w] & 0xffff0000u), __uint_as_float(ka[w] & 0xffff0000u), d4[w]);
+          }
+        }
+        dot = (d4[0] + d4[1]) + (d4[2] + d4[3]);
+        s_x[256 + half * 128 + row] = dot;
+      }
       named_bar_sync(1, 256);
       m_used = fmaxf(mine, s_x[(1 - half) * 128 + row]);
+      if (tail1) {
+        s_tail = dot + s_x[256 + (1 - half) * 128 + row];   // a + b == b + a: the same value in both halves
+        m_used = fmaxf(m_used, s_tail);
+      }
       m_loc = mine;
       named_bar_sync(1, 256);                               // the scratch lives in the P tile that is written next
     } else {
@@ -293,6 +328,20 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
   uint32_t v[32];
   tmem_ld_32x32(tmem_O + lane_off + half * 32, v);   // warp-collective: every lane, also the padding rows
   tmem_ld_wait();
+  if (tail1) {   // the tail key against the row's FINAL reference maximum: l += p, O += p * v_last
+    const float pt = fast_ex2(fmaf(s_tail, scale_log2e, -m_used * scale_log2e));
+    l_run += pt;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const uint4 vv = __ldg(vt_ptr + c);
+      const uint32_t va[4] = {vv.x, vv.y, vv.z, vv.w};
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        v[8 * c + 2 * w] = __float_as_uint(fmaf(pt, __uint_as_float(va[w] << 16), __uint_as_float(v[8 * c + 2 * w])));
+        v[8 * c + 2 * w + 1] = __float_as_uint(fmaf(pt, __uint_as_float(va[w] & 0xffff0000u), __uint_as_float(v[8 * c + 2 * w + 1])));
+      }
+    }
+  }
   if (qrow < seq) {
     const float inv = 1.f / l_run;
     __nv_bfloat16* dst = out + (static_cast<size_t>(b) * seq + qrow) * ld_out + head * 64 + half * 32;

@@ -762,8 +762,11 @@ int launch_attention(ovo_encoder* e, int n_seq, int seq, int seq_pad, int heads,
   const float scale_log2e = 0.125f * 1.4426950408889634f;  // head_dim 64
   ProfScope prof(s, PROF_ATTN, 4.0 * static_cast<double>(bh) * seq * (causal ? 0.5 * seq : seq) * 64, 4.0 * static_cast<double>(bh) * seq * 64 * 2);
   const int n_items = qtiles * static_cast<int>(bh);
+  // one key left over after the 64-key blocks (577 = 9 * 64 + 1): folded into the epilogue instead of a tenth block
+  static const bool tail_off = getenv("OVO_B200_ATTN_TAIL") && getenv("OVO_B200_ATTN_TAIL")[0] == '0';   // A/B measurement aid
+  const int tail1 = (!causal && seq > 64 && seq % kAttnKB == 1 && !tail_off) ? 1 : 0;
   attention_fwd_kernel<<<std::min(n_items, 2 * num_sms()), kAttnThreads, smem, s>>>(
-      tq, tk, tv, e->attn, seq, seq_pad, heads, width, scale_log2e, causal ? 1 : 0, g_attn_debug, qtiles, n_items);
+      tq, tk, tv, e->attn, seq, seq_pad, heads, width, scale_log2e, causal ? 1 : 0, g_attn_debug, qtiles, n_items, e->k, e->vt, tail1);
   OVO_CHECK_LAUNCH();
   return OVO_OK;
 }

@@ -7,9 +7,8 @@ run() { # label, env...
 import sys, json
 d = json.loads(sys.stdin.read()); print('$l', d['value'], d['ms_per_step'])"
 }
-python -m pytest tests/test_gpu_kernels.py -m gpu -x -q -k "associate_batch" 2>&1 | tail -2
-run default X=1
-run resid-bn128 OVO_B200_RESID_BN=128
-run default X=1
-run resid-bn128 OVO_B200_RESID_BN=128
-run persistent OVO_B200_VOTE=persistent
+python -m pytest tests/test_gpu_encoder.py tests/test_gpu_crops.py -m gpu -x -q 2>&1 | tail -2
+run tail-on X=1
+run tail-off OVO_B200_ATTN_TAIL=0
+run tail-on X=1
+run tail-off OVO_B200_ATTN_TAIL=0
