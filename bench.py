@@ -265,7 +265,7 @@ def run_ours(args, rank, world, local_rank):
         gemm_traffic, n = cap["mean"](lambda k: k["capture"] == "gemm" and "gemm_bf16_tn_kernel" in k["kernel"] and (k.get("grid") or 0) >= 100)
         gemm_traffic_src = f"dram__bytes_read.sum + dram__bytes_write.sum per launch, mean over {n} ViT-layer GEMM launches (16 images); " + tail
         query_traffic, _ = cap["mean"](lambda k: k["capture"] == "query")
-        fuse_traffic, _ = cap["mean"](lambda k: k["capture"] == "map" and "fuse_dense_batch" in k["kernel"])
+        fuse_traffic, _ = cap["mean"](lambda k: k["capture"] in ("map", "fuse") and "fuse_dense_batch" in k["kernel"])
     g = prof["gemm"]
     gemm_tflops = g["flops"] / (g["ms"] * 1e-3) / 1e12 if g["ms"] > 0 else 0.0
     tot_ms = sum(v["ms"] for v in prof.values())

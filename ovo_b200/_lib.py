@@ -194,6 +194,7 @@ SIGNATURES = {
     "ovo_profile_begin": (None, []),
     "ovo_profile_report": (c_int, [c_int, C.POINTER(c_float), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(c_int)]),
     "ovo_set_gemm_cluster": (None, [c_int]),
+    "ovo_attn_trace": (None, [c_void_p]),
     "ovo_gemm_bench": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, C.POINTER(c_float), c_void_p]),
     "ovo_gemm_bf16": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int,
                               c_int, c_void_p]),

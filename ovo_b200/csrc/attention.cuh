@@ -1,8 +1,8 @@
 // Flash-style softmax attention forward for head_dim 64 on tcgen05 (reference: F.scaled_dot_product_attention
 // at pe.py:145-147 for the vision tower, nn.MultiheadAttention with the causal mask pe.py:621-627 for text).
 //
-// One CTA = one (image, head, 128-query tile), 256 threads: two threads per query row, each owning half of the keys
-// of a block and half of the output columns.  TWO CTAs are resident per SM (112 KB smem, 256 TMEM columns each).
+// One CTA = one (image, head, 128-query tile), 256 softmax threads: two threads per query row, each owning half of the keys
+// of a block and half of the output columns (+ one MMA warp and one TMA producer warp, below).  TWO CTAs are resident per SM (112 KB smem, 256 TMEM columns each).
 // Q (128x64) is TMA-loaded once; K and V stream in 64-key blocks through 4-slot rings of 128B-swizzled shared memory
 // (V is consumed as an MN-major B operand: no transposed copy of V is ever made).
 //
@@ -15,10 +15,13 @@
 // maximum m is fixed after the first block (the only one that needs a separate max pass) and is only raised — with a
 // tcgen05.ld/st rescale of the accumulator — if a later block exceeds it by more than 2^kRescaleLog2: f32/bf16 carry an
 // 8-bit exponent, so p up to 2^32 loses nothing and the final O / l division cancels the common factor.
-// Warp specialisation: the 256 softmax threads never issue an MMA — a ninth warp waits on the "P tile ready" mbarrier,
-// issues P.V and the Q.K^T two blocks ahead, and starts the next work item's loads while the softmax threads are still in
-// the current item's epilogue; the softmax threads synchronise among themselves on a named barrier (bar.red.or also carries
-// the rare rescale request).
+// Warp specialisation: the 256 softmax threads issue neither MMAs nor loads — a ninth warp waits on the "P tile ready"
+// mbarrier and issues P.V and the Q.K^T two blocks ahead; a tenth warp is the TMA producer: it refills a K / V ring slot as soon
+// as the MMA that read it has completed (full/empty mbarrier pairs per slot) and starts the next work item's loads while the
+// softmax threads are still in the current item's epilogue.  (A clock64 trace of one CTA, tools/attn_trace.py, showed that a
+// TMA issue costs the issuing thread 150-200 cycles; with softmax thread 0 doing them, 350 of the ~1850 cycles of every block
+// were spent there while the other 255 threads waited at the block's barrier.)  The softmax threads synchronise among
+// themselves on a named barrier (bar.red.or also carries the rare rescale request).
 // The kernel is PERSISTENT: 2 CTAs per SM each loop over (image, head, query tile) work items, so barrier set-up, the TMEM
 // allocation and the tensor-map fetch are paid once per CTA (measured: a third of the non-persistent kernel's time was
 // per-CTA fixed cost) and the next item's Q/K/V loads are in flight while the current item finishes.
@@ -28,7 +31,7 @@
 
 namespace ovo {
 
-constexpr int kAttnThreads = 288;   // warps 0..7: softmax (two threads per query row); warp 8: TMA + tcgen05.mma issue
+constexpr int kAttnThreads = 320;   // warps 0..7: softmax (two threads per query row); warp 8: tcgen05.mma issue; warp 9: TMA producer
 constexpr int kAttnMaxBlocks = 5;  // seq_pad <= 640 (host-side limit of the q/k/v buffers, in 128-query tiles)
 
 constexpr int kAttnKB = 64;        // keys per block
@@ -41,7 +44,7 @@ struct AttnSmem {
   // 112 KB + barriers.  Two CTAs per SM need 2 * (kBytes + 1 KB) <= 228 KB, so there is no room for a dedicated row-exchange
   // buffer: the rare cross-half exchanges (first block's maximum, a rescale, the final row sum) borrow a P tile while no
   // MMA reads it.
-  static constexpr int kBytes = kQ + 4 * kKBlock + 4 * kVBlock + 2 * kP + 256;
+  static constexpr int kBytes = kQ + 4 * kKBlock + 4 * kVBlock + 2 * kP + 256;   // 24 mbarriers + the TMEM slot in the last 256 B
 };
 
 constexpr float kRescaleLog2 = 32.f;   // raise a row's reference maximum only when a block exceeds it by 2^32
@@ -50,7 +53,8 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
     attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                          const __grid_constant__ CUtensorMap tmV, __nv_bfloat16* __restrict__ out, int seq,
                          int seq_pad, int heads, int ld_out, float scale_log2e, int causal, int dbg, int qtiles, int n_items,
-                         const __nv_bfloat16* __restrict__ k_glob, const __nv_bfloat16* __restrict__ v_glob, int tail1) {
+                         const __nv_bfloat16* __restrict__ k_glob, const __nv_bfloat16* __restrict__ v_glob, int tail1,
+                         long long* __restrict__ trace /* measurement tap (ovo_attn_trace): clock64 stamps of CTA 0, else null */) {
   griddep_launch();
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();  // the 128B swizzle needs 1024-byte aligned tiles
@@ -67,14 +71,20 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
 
   const int tid = threadIdx.x, warp = tid >> 5;
+  // trace[(item * 16 + block) * 8 + phase]: softmax thread 0 writes phases 0..5, the MMA thread 6..7; block 15 = item level
+  const bool tr0 = trace != nullptr && blockIdx.x == 0 && tid == 0, tr8 = trace != nullptr && blockIdx.x == 0 && tid == 256;
+#define ATTN_STAMP(on, blk, ph) do { if (on) trace[((n_done & 7) * 16 + (blk)) * 8 + (ph)] = clock64(); } while (0)
   uint64_t* bar_q = bars + 13;   // Q tile of the current item landed
   uint64_t* bar_p = bars + 14;   // [2] P tile written and S buffer consumed by every softmax thread
+  uint64_t* bar_kfree = bars + 16;   // [4] K slot consumed by its Q.K^T (tcgen05.commit): the producer may refill it
+  uint64_t* bar_vfree = bars + 20;   // [4] V slot consumed by its P.V
   if (tid == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
     for (int i = 0; i < 12; ++i) mbar_init(&bars[i], 1);
     mbar_init(bar_q, 1);
     mbar_init(&bar_p[0], 1);
     mbar_init(&bar_p[1], 1);
+    for (int i = 0; i < 4; ++i) { mbar_init(&bar_kfree[i], 1); mbar_init(&bar_vfree[i], 1); }
     fence_barrier_init();
   }
   if (warp == 8) tmem_alloc<256>(tmem_slot);  // S0 [0,64)  S1 [64,128)  O [128,192)
@@ -111,6 +121,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
       for (int k = 0; k < 4; ++k) umma_bf16(tmem_S + (g & 1) * 64, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
     }
     umma_commit(&bar_s[g & 1]);
+    umma_commit(&bar_kfree[g & 3]);
   };
 
   const int row = tid & 127, half = tid >> 7;
@@ -131,22 +142,44 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
   // to the accumulator in the epilogue), which removes one of ten block iterations of every work item.
   nb = (dbg & 4) ? 1 : min(causal ? min(nblk, 2 * qt + 2) : nblk, (seq - tail1 + kAttnKB - 1) / kAttnKB);
 
-  if (warp == 8) {
-    // ---------------------------------------------------------------- TMA + MMA warp (one elected lane)
-    if (tid == 256) {
-      // every MMA of the previous item has completed (the last P.V was waited for below): Q, the K/V rings are free; the S
-      // buffers were consumed (bar_p of the last two blocks), the accumulator is overwritten only by P.V_0, which waits for
-      // the softmax threads' first bar_p arrival of this item, i.e. for the end of their previous epilogue
+  if (warp == 9) {
+    // ---------------------------------------------------------------- TMA producer warp (one lane)
+    // Full/empty rings: a slot's "free" barrier completes once per use (committed by the MMA thread behind the MMAs that read
+    // it) and cannot complete again before this thread has refilled the slot, so a parity wait can never fall a phase behind.
+    if (tid == 288) {
+      if (n_done > 0) {
+        // the previous item's last P.V (hence every MMA of that item: one thread's MMAs complete in order) has read Q and the rings
+        const int gl = g0 - 1;
+        mbar_wait(&bar_vfree[gl & 3], (gl >> 2) & 1);
+      }
       mbar_arrive_expect_tx(bar_q, AttnSmem::kQ);
       tma_load_2d(sQ, &tmQ, bar_q, 0, bh * seq_pad + q0);
       for (int j = 0; j < 4 && j < nb; ++j) load_k(j);
       for (int j = 0; j < 4 && j < nb; ++j) load_v(j);
+      for (int j = 0; j + 4 < nb; ++j) {
+        const int g = g0 + j;
+        mbar_wait(&bar_kfree[g & 3], (g >> 2) & 1);
+        load_k(j + 4);
+        mbar_wait(&bar_vfree[g & 3], (g >> 2) & 1);
+        load_v(j + 4);
+      }
+    }
+    __syncwarp();
+    g0 += nb;
+    continue;
+  }
+  if (warp == 8) {
+    // ---------------------------------------------------------------- MMA warp (one elected lane)
+    if (tid == 256) {
+      // S buffers: consumed (bar_p of the previous item's last two blocks was waited for); the accumulator is overwritten only
+      // by P.V_0, which waits for the softmax threads' first bar_p arrival of this item, i.e. for the end of their previous epilogue
       mbar_wait(bar_q, n_done & 1);
       issue_qk(0);
       if (nb > 1) issue_qk(1);
       for (int j = 0; j < nb; ++j) {
         const int g = g0 + j;
         mbar_wait(&bar_p[g & 1], (g >> 1) & 1);      // P_j in smem (async-proxy visible), S buffer g&1 consumed
+        ATTN_STAMP(tr8, j, 6);
         tc_fence_after();
         mbar_wait(&bar_v[g & 3], (g >> 2) & 1);
         tc_fence_after();
@@ -158,10 +191,10 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
           for (int k = 0; k < 4; ++k) umma_bf16(tmem_O, pdesc + 2 * k, vdesc + 128 * k, idesc_o, (j | k) != 0);
         }
         umma_commit(&bar_o[g & 1]);
+        umma_commit(&bar_vfree[g & 3]);
         if (j + 2 < nb) issue_qk(j + 2);
+        ATTN_STAMP(tr8, j, 7);
       }
-      // all tensor work of the item has completed before the next item's loads overwrite Q / the rings
-      mbar_wait(&bar_o[(g0 + nb - 1) & 1], ((g0 + nb - 1) >> 1) & 1);
     }
     __syncwarp();
     g0 += nb;
@@ -184,12 +217,13 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
     asm volatile("prefetch.global.L1 [%0];" ::"l"(vt_ptr));
   }
 
+  ATTN_STAMP(tr0, 15, 0);
   for (int j = 0; j < nb; ++j) {
     const int g = g0 + j;                              // global block index of this CTA: ring slots and parities
+    ATTN_STAMP(tr0, j, 0);
     mbar_wait(&bar_s[g & 1], (g >> 1) & 1);
+    ATTN_STAMP(tr0, j, 1);
     tc_fence_after();
-    // K slot g&3 has been consumed by Q.K_j^T: refill it with block j+4
-    if (tid == 0 && j + 4 < nb) load_k(j + 4);
     const uint32_t s_addr = tmem_S + lane_off + (g & 1) * 64 + half * 32;
     float* s_x = reinterpret_cast<float*>(sP + (g & 1) * AttnSmem::kP);   // scratch inside the P tile this block will write
 
@@ -202,6 +236,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
     uint32_t v[32];
     tmem_ld_32x32(s_addr, v);
     tmem_ld_wait();
+    ATTN_STAMP(tr0, j, 2);
 
     if (j == 0) {
       // first block: the reference maximum of the row = its maximum over block 0 (both halves)
@@ -245,10 +280,9 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
       named_bar_sync(1, 256);                               // the scratch lives in the P tile that is written next
     } else {
       if (j >= 2) {
-        // P.V_{j-2} has completed: P tile g&1 and V slot (g-2)&3 are free again
+        // P.V_{j-2} has completed: P tile g&1 is free again
         mbar_wait(&bar_o[g & 1], ((g - 2) >> 1) & 1);
         tc_fence_after();
-        if (tid == 0 && j + 2 < nb) load_v(j + 2);
       }
       if (rescale) {   // rare, CTA-uniform (dbg 16: whenever a maximum grows, for the tests)
         mbar_wait(&bar_o[(g - 1) & 1], ((g - 1) >> 1) & 1);    // every P.V so far has landed: the accumulator is stable
@@ -270,6 +304,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
       }
     }
     const float m_scaled = (m_used == -INFINITY) ? 0.f : m_used * scale_log2e;
+    ATTN_STAMP(tr0, j, 3);
 
     // p = exp2(s*scale - m), partial row sum, block maximum, P -> swizzled smem (bf16)
     float lp[4] = {0.f, 0.f, 0.f, 0.f};
@@ -311,16 +346,20 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
     const int need = m_loc > m_used + ((dbg & 16) ? 0.f : kRescaleLog2 / scale_log2e);
 
     // P_j visible to the async proxy and every thread done reading S_j; then O += P_j.V_j and S buffer j&1 <- Q.K_{j+2}^T
+    ATTN_STAMP(tr0, j, 4);
     fence_proxy_async_smem();
     tc_fence_before();
     rescale = named_bar_or(1, 256, need);
     if (tid == 0) mbar_arrive(&bar_p[g & 1]);
+    ATTN_STAMP(tr0, j, 5);
   }
+  ATTN_STAMP(tr0, 15, 1);
 
   // the accumulator is complete once the last P.V has landed (tcgen05.mma of one thread complete in order);
   // total row sum = sum of the two halves' partial sums
   mbar_wait(&bar_o[(g0 + nb - 1) & 1], ((g0 + nb - 1) >> 1) & 1);
   tc_fence_after();
+  ATTN_STAMP(tr0, 15, 2);
   float* s_x = reinterpret_cast<float*>(sP);         // every P tile is free now
   s_x[half * 128 + row] = l_run;
   named_bar_sync(1, 256);
@@ -358,8 +397,10 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
   tc_fence_before();
   named_bar_sync(1, 256);                                   // scratch and accumulator reads done before the next item reuses them
   tc_fence_after();
+  ATTN_STAMP(tr0, 15, 3);
   g0 += nb;
   }  // work items
+#undef ATTN_STAMP
 
   tc_fence_before();
   __syncthreads();

@@ -718,6 +718,7 @@ struct ovo_encoder {
   size_t ctab_cap = 0, ctab_wcap = 0;
 };
 
+long long* g_attn_trace = nullptr;   // ovo_attn_trace: device buffer [8 items][16 blocks][8 phases] of clock64 stamps, or null
 int g_attn_debug = 0;   // tuning experiments (attention.cuh dbg bits), set through ovo_set_gemm_cluster bits 24..31
 
 namespace {
@@ -766,7 +767,7 @@ int launch_attention(ovo_encoder* e, int n_seq, int seq, int seq_pad, int heads,
   static const bool tail_off = getenv("OVO_B200_ATTN_TAIL") && getenv("OVO_B200_ATTN_TAIL")[0] == '0';   // A/B measurement aid
   const int tail1 = (!causal && seq > 64 && seq % kAttnKB == 1 && !tail_off) ? 1 : 0;
   attention_fwd_kernel<<<std::min(n_items, 2 * num_sms()), kAttnThreads, smem, s>>>(
-      tq, tk, tv, e->attn, seq, seq_pad, heads, width, scale_log2e, causal ? 1 : 0, g_attn_debug, qtiles, n_items, e->k, e->vt, tail1);
+      tq, tk, tv, e->attn, seq, seq_pad, heads, width, scale_log2e, causal ? 1 : 0, g_attn_debug, qtiles, n_items, e->k, e->vt, tail1, g_attn_trace);
   OVO_CHECK_LAUNCH();
   return OVO_OK;
 }
@@ -863,6 +864,9 @@ int get_table(ovo_encoder* e, int n_in, AaTable* out, cudaStream_t s) {
 }  // namespace
 
 extern "C" {
+
+void ovo_attn_trace(long long* buf_dev) { g_attn_trace = buf_dev; }
+
 
 int ovo_encoder_create(const ovo_vit_cfg* cfg, const ovo_vit_weights* w, int max_images, int max_h, int max_w,
                        int max_masks, ovo_encoder_t** out) {

@@ -70,9 +70,11 @@ class OVO:
         # (query, get_objs_clips, capture_dict, ...) first make the current stream wait for this one.
         self._enc_stream = torch.cuda.Stream(device=self._dev)
         D = self.clip_generator.clip_dim
-        # `store_capacity` / `bank_capacity` (optional, new): initial rows; both tables double when full (a pause of a few ms for the
-        # copy and for re-pointing the instances' descriptor views), so a latency-sensitive stream reserves them up front
-        self._store = torch.zeros(int(config.get("store_capacity", 4096)), D, device=self._dev, dtype=torch.float32)   # per-keyframe descriptors
+        # `store_capacity` / `bank_capacity` (optional, new): initial rows; both tables double when full (a pause for the allocation,
+        # the copy and re-pointing the instances' descriptor views: up to ~100 ms when keyframes are processed one at a time,
+        # bench.py e2e.batch_keyframes_1), so a latency-sensitive stream reserves them up front.  32768 rows = 128 MB = 680
+        # keyframes of 48 masks before the first doubling
+        self._store = torch.zeros(int(config.get("store_capacity", 32768)), D, device=self._dev, dtype=torch.float32)   # per-keyframe descriptors
         self._store_n = 0
         self._bank = torch.zeros(int(config.get("bank_capacity", 4096)), D, device=self._dev, dtype=torch.float32)    # fused instance descriptors
         self._bank_n = 0

@@ -96,6 +96,20 @@ def test_capture_restore_roundtrip(tmp_path):
     assert torch.equal(other.query(["0", "1"]).cpu(), q0)
 
 
+def test_store_and_bank_growth_keep_the_results(tmp_path):
+    """The descriptor store and the instance bank double when full (default 32768 / 4096 rows: never in the other tests).
+    Starting from 8 rows forces several doublings inside the 4-keyframe replay; ids, descriptors and queries are unchanged."""
+    ovo, K, xyz, ids, ins, frames = _build(tmp_path)
+    small, *_ = _build(tmp_path / "b", extra={"store_capacity": 8, "bank_capacity": 2})
+    a = _replay(ovo, xyz, ids, ins, frames)
+    b = _replay(small, xyz, ids, ins, frames)
+    assert small._store.shape[0] > 8 and small._bank.shape[0] > 2
+    assert torch.equal(a, b) and list(ovo.objects.keys()) == list(small.objects.keys())
+    assert torch.equal(ovo._store[: ovo._store_n], small._store[: small._store_n])
+    assert torch.equal(ovo.get_objs_clips(), small.get_objs_clips())
+    assert torch.equal(ovo.query(["0", "1", "2"]), small.query(["0", "1", "2"]))
+
+
 def test_dense_mode_consistent_with_instance_mode(tmp_path):
     """SURVEY §0 consistency rule: a point's dense feature is the running mean of the descriptors of the masks it
     fell into; for a point seen in exactly the keyframes that formed its instance's descriptor, the two agree."""

@@ -1,4 +1,4 @@
-"""profiles/<tag>_traffic.json from `ncu --set full` captures (gpurun_out/<tag>_{gemm,attn,query,map}.ncu-rep, tools/r2_capture.sh):
+"""profiles/<tag>_traffic.json from `ncu --set full` captures (gpurun_out/<tag>_{gemm,attn,query,map,fuse}.ncu-rep, tools/r2_capture.sh):
 per kernel the DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) per launch, duration, tensor-pipe %, L2 bytes.  bench.py
 reads this file for `roofline.traffic` (a capture of the build whose source hash is recorded here, not a literal).
     python tools/traffic_from_captures.py r2"""
@@ -33,7 +33,7 @@ def to_us(v, u):
 
 
 out = {"tag": tag, "csrc_sha16": src_hash(), "how": "ncu --set full --clock-control none (cold caches, one replayed launch at a time)", "kernels": []}
-for part in ("gemm", "attn", "query", "map"):
+for part in ("gemm", "attn", "query", "map", "fuse"):
     rep = os.path.join(ROOT, "gpurun_out", f"{tag}_{part}.ncu-rep")
     if not os.path.exists(rep):
         continue
