@@ -581,9 +581,9 @@ int ovo_profile_report(int n_classes, float* ms_host, double* flops_host, double
  * 0 = automatic (default), 1, 2 or 4. */
 void ovo_set_gemm_cluster(int cluster_size);
 
-/* Measurement tap: while `buf_dev` (device memory, 8 x 16 x 8 int64, zeroed by the caller) is set, CTA 0 of every
+/* Measurement tap: while `buf_dev` (device memory, 8 x 16 x 16 int64, zeroed by the caller) is set, CTA 0 of every
  * attention_fwd_kernel launch writes clock64() stamps of its softmax thread 0 and of its MMA thread:
- * buf[(item % 8) * 128 + block * 8 + phase]; null switches it off (tools/attn_trace.py reads it). */
+ * buf[(item % 8) * 256 + block * 16 + phase]; null switches it off (tools/attn_trace.py reads it). */
 void ovo_attn_trace(long long* buf_dev);
 
 /* Test tap for the GEMM machinery: C[M,N] f32 = A[M,K] bf16 . B[N,K]^T bf16 (+bias f32 [N]). */

@@ -2,11 +2,13 @@
 // at pe.py:145-147 for the vision tower, nn.MultiheadAttention with the causal mask pe.py:621-627 for text).
 //
 // One CTA = one (image, head, 128-query tile), 256 softmax threads: two threads per query row, each owning half of the keys
-// of a block and half of the output columns (+ one MMA warp and one TMA producer warp, below).  TWO CTAs are resident per SM (112 KB smem, 256 TMEM columns each).
+// of a block and half of the output columns (+ one MMA warp and one TMA producer warp, below).  TWO CTAs are resident per SM (84 KB smem, 256 TMEM columns each).
 // Q (128x64) is TMA-loaded once; K and V stream in 64-key blocks through 4-slot rings of 128B-swizzled shared memory
-// (V is consumed as an MN-major B operand: no transposed copy of V is ever made).
+// (V is consumed as an MN-major B operand: no transposed copy of V is ever made).  P never touches shared memory: the softmax
+// threads store it as bf16 pairs into tensor memory (tcgen05.st, 16 columns per thread) and P.V takes its A operand from there
+// (tcgen05.mma with a tensor-memory A operand).
 //
-// Software pipeline over 64-key blocks with TWO score buffers in TMEM (S0, S1: 64 columns each) and two P tiles:
+// Software pipeline over 64-key blocks with TWO score buffers in TMEM (S0, S1: 64 columns each) and two P buffers (32 columns each):
 //     tensor core : ... P.V_{j-1} | Q.K_{j+1}^T |          P.V_j | Q.K_{j+2}^T | ...
 //     softmax     :        block j (reads S_j, writes P_j)  |  block j+1 (S_{j+1} was issued one block earlier) ...
 // so the MMA -> tcgen05.ld -> exp2 -> P -> MMA dependency chain of a single-buffered loop is broken: while the threads
@@ -40,10 +42,9 @@ struct AttnSmem {
   static constexpr int kQ = 128 * 64 * 2;       // 16 KB
   static constexpr int kKBlock = 64 * 64 * 2;   // 8 KB per 64 keys, 4 slots
   static constexpr int kVBlock = 64 * 64 * 2;   // 8 KB per 64 keys (V rows of 128 B), 4 slots
-  static constexpr int kP = 128 * 64 * 2;       // 16 KB: P as a K-major 128x64 tile, 2 buffers
-  // 112 KB + barriers.  Two CTAs per SM need 2 * (kBytes + 1 KB) <= 228 KB, so there is no room for a dedicated row-exchange
-  // buffer: the rare cross-half exchanges (first block's maximum, a rescale, the final row sum) borrow a P tile while no
-  // MMA reads it.
+  static constexpr int kP = 2048;               // 2 KB of exchange scratch (2 x 256 floats), 2 buffers.  P itself lives in tensor memory
+  // 84 KB + barriers; two CTAs per SM (tensor memory: 2 x 256 columns).  The scratch carries the rare cross-half exchanges (first
+  // block's maximum and tail-key dot product, a rescale, the final row sum).
   static constexpr int kBytes = kQ + 4 * kKBlock + 4 * kVBlock + 2 * kP + 256;   // 24 mbarriers + the TMEM slot in the last 256 B
 };
 
@@ -70,10 +71,12 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
   uint64_t* bar_o = bars + 10;   // [2]  P.V of a block with this parity done
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
 
-  const int tid = threadIdx.x, warp = tid >> 5;
-  // trace[(item * 16 + block) * 8 + phase]: softmax thread 0 writes phases 0..5, the MMA thread 6..7; block 15 = item level
+  const int tid = threadIdx.x;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform: the MMA warp's control flow and descriptors stay
+                                                            // on the uniform datapath (see the MMA warp below)
+  // trace[(item * 16 + block) * 16 + phase]: softmax thread 0 writes phases 0..5, the MMA thread 6..12; block 15 = item level
   const bool tr0 = trace != nullptr && blockIdx.x == 0 && tid == 0, tr8 = trace != nullptr && blockIdx.x == 0 && tid == 256;
-#define ATTN_STAMP(on, blk, ph) do { if (on) trace[((n_done & 7) * 16 + (blk)) * 8 + (ph)] = clock64(); } while (0)
+#define ATTN_STAMP(on, blk, ph) do { if (on) trace[((n_done & 7) * 16 + (blk)) * 16 + (ph)] = clock64(); } while (0)
   uint64_t* bar_q = bars + 13;   // Q tile of the current item landed
   uint64_t* bar_p = bars + 14;   // [2] P tile written and S buffer consumed by every softmax thread
   uint64_t* bar_kfree = bars + 16;   // [4] K slot consumed by its Q.K^T (tcgen05.commit): the producer may refill it
@@ -87,12 +90,13 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
     for (int i = 0; i < 4; ++i) { mbar_init(&bar_kfree[i], 1); mbar_init(&bar_vfree[i], 1); }
     fence_barrier_init();
   }
-  if (warp == 8) tmem_alloc<256>(tmem_slot);  // S0 [0,64)  S1 [64,128)  O [128,192)
+  if (warp == 8) tmem_alloc<256>(tmem_slot);  // S0 [0,64)  S1 [64,128)  O [128,192)  P0 [192,224)  P1 [224,256)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_S = *tmem_slot;
   const uint32_t tmem_O = tmem_S + 128;
+  const uint32_t tmem_P = tmem_S + 192;   // P0 [192,224)  P1 [224,256): bf16 pairs, the A operand of P.V (never in shared memory)
 
   constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64);
   constexpr uint32_t idesc_o = umma_idesc_bf16_bmn(128, 64);
@@ -100,6 +104,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
 
   // Ring slots and mbarrier parities are driven by `g`, the number of key blocks this CTA has processed so far plus the block
   // index inside the current item, so the rings keep rolling across work items.
+  int n_done = 0;                       // work items this CTA has finished (parity of bar_q)
   int bh = 0, q0 = 0, nb = 0, g0 = 0;   // current item: (image*heads + head), first query, key blocks, global index of its block 0
   auto load_k = [&](int j) {  // K block j of the item -> slot (g0+j)&3
     const int s = (g0 + j) & 3;
@@ -111,24 +116,27 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
     mbar_arrive_expect_tx(&bar_v[s], AttnSmem::kVBlock);
     tma_load_2d(sV + s * AttnSmem::kVBlock, &tmV, &bar_v[s], 0, bh * seq_pad + j * kAttnKB);
   };
-  auto issue_qk = [&](int j) {  // S_{g&1} = Q . K_j^T
+  auto issue_qk = [&](int j) {  // S_{g&1} = Q . K_j^T   (called by every lane of the MMA warp; one elected lane issues)
     const int g = g0 + j;
     mbar_wait(&bar_k[g & 3], (g >> 2) & 1);
     tc_fence_after();
+    ATTN_STAMP(tr8, j - 2 >= 0 ? j - 2 : 14, 11);
     const uint64_t kdesc = umma_desc_sw128(smem_u32(sK + (g & 3) * AttnSmem::kKBlock));
-    if (!(dbg & 2)) {
+    if (elect_one()) {
+      if (!(dbg & 2)) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) umma_bf16(tmem_S + (g & 1) * 64, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem_S + (g & 1) * 64, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
+      }
+      umma_commit(&bar_s[g & 1]);
+      umma_commit(&bar_kfree[g & 3]);
     }
-    umma_commit(&bar_s[g & 1]);
-    umma_commit(&bar_kfree[g & 3]);
+    __syncwarp();
+    ATTN_STAMP(tr8, j - 2 >= 0 ? j - 2 : 14, 12);
   };
 
   const int row = tid & 127, half = tid >> 7;
   const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
-  const int r8 = row & 7;
-  const int p_off = (row >> 3) * 1024 + r8 * 128;  // this row inside a P tile (128-byte rows, 8-row swizzle groups)
-  int n_done = 0;                                   // work items this CTA has finished (parity of bar_q)
+  const int r8 = row & 7;                           // position inside an 8-row swizzle group of the Q tile (tail-key dot product)
 
   for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n_done) {
   const int qt = item % qtiles;
@@ -169,34 +177,39 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
     continue;
   }
   if (warp == 8) {
-    // ---------------------------------------------------------------- MMA warp (one elected lane)
-    if (tid == 256) {
-      // S buffers: consumed (bar_p of the previous item's last two blocks was waited for); the accumulator is overwritten only
-      // by P.V_0, which waits for the softmax threads' first bar_p arrival of this item, i.e. for the end of their previous epilogue
-      mbar_wait(bar_q, n_done & 1);
-      issue_qk(0);
-      if (nb > 1) issue_qk(1);
-      for (int j = 0; j < nb; ++j) {
-        const int g = g0 + j;
-        mbar_wait(&bar_p[g & 1], (g >> 1) & 1);      // P_j in smem (async-proxy visible), S buffer g&1 consumed
-        ATTN_STAMP(tr8, j, 6);
-        tc_fence_after();
-        mbar_wait(&bar_v[g & 3], (g >> 2) & 1);
-        tc_fence_after();
-        const uint64_t pdesc = umma_desc_sw128(smem_u32(sP + (g & 1) * AttnSmem::kP));
-        // keys 16k .. 16k+15 of the block: 16 rows of 128 B = 2048 B per K=16 step
-        const uint64_t vdesc = umma_desc_sw128(smem_u32(sV + (g & 3) * AttnSmem::kVBlock));
-        if (!(dbg & 2)) {
+    // ---------------------------------------------------------------- MMA warp
+    // Every lane runs the (warp-uniform) control flow and the barrier waits; ONE elected lane issues the tcgen05 instructions.
+    // With the whole section under `if (tid == 256)` the compiler could not prove the descriptors uniform and moved each one
+    // into the uniform registers through an ELECT / R2UR.BROADCAST loop: ~100 cycles per tcgen05.mma, 1300-1500 cycles of
+    // issue per key block (clock64 trace, tools/attn_trace.py) — as long as the softmax of a block.
+    // S buffers: consumed (bar_p of the previous item's last two blocks was waited for); the accumulator is overwritten only
+    // by P.V_0, which waits for the softmax threads' first bar_p arrival of this item, i.e. for the end of their previous epilogue
+    mbar_wait(bar_q, n_done & 1);
+    issue_qk(0);
+    if (nb > 1) issue_qk(1);
+    for (int j = 0; j < nb; ++j) {
+      const int g = g0 + j;
+      mbar_wait(&bar_p[g & 1], (g >> 1) & 1);      // P_j written (tensor memory), S buffer g&1 consumed
+      ATTN_STAMP(tr8, j, 6);
+      tc_fence_after();
+      mbar_wait(&bar_v[g & 3], (g >> 2) & 1);
+      tc_fence_after();
+      ATTN_STAMP(tr8, j, 8);
+      // keys 16k .. 16k+15 of the block: 16 rows of 128 B = 2048 B per K=16 step
+      const uint64_t vdesc = umma_desc_sw128(smem_u32(sV + (g & 3) * AttnSmem::kVBlock));
+      if (elect_one()) {
+        if (!(dbg & 2)) {              // P from tensor memory: 8 columns (16 keys) per K step
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16(tmem_O, pdesc + 2 * k, vdesc + 128 * k, idesc_o, (j | k) != 0);
+          for (int k = 0; k < 4; ++k) umma_bf16_ts(tmem_O, tmem_P + (g & 1) * 32 + 8 * k, vdesc + 128 * k, idesc_o, (j | k) != 0);
         }
         umma_commit(&bar_o[g & 1]);
         umma_commit(&bar_vfree[g & 3]);
-        if (j + 2 < nb) issue_qk(j + 2);
-        ATTN_STAMP(tr8, j, 7);
       }
+      __syncwarp();
+      ATTN_STAMP(tr8, j, 10);
+      if (j + 2 < nb) issue_qk(j + 2);
+      ATTN_STAMP(tr8, j, 7);
     }
-    __syncwarp();
     g0 += nb;
     continue;
   }
@@ -225,7 +238,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
     ATTN_STAMP(tr0, j, 1);
     tc_fence_after();
     const uint32_t s_addr = tmem_S + lane_off + (g & 1) * 64 + half * 32;
-    float* s_x = reinterpret_cast<float*>(sP + (g & 1) * AttnSmem::kP);   // scratch inside the P tile this block will write
+    float* s_x = reinterpret_cast<float*>(sP + (g & 1) * AttnSmem::kP);   // exchange scratch
 
     const int kv0 = j * kAttnKB + half * 32;         // first key of this thread's half
     int kv_hi = seq - kv0;                           // keys >= seq are padding
@@ -276,8 +289,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
         s_tail = dot + s_x[256 + (1 - half) * 128 + row];   // a + b == b + a: the same value in both halves
         m_used = fmaxf(m_used, s_tail);
       }
-      m_loc = mine;
-      named_bar_sync(1, 256);                               // the scratch lives in the P tile that is written next
+      m_loc = mine;   // (a thread's scratch slot is next written in a rescale or in the epilogue: a CTA barrier of a later block lies between)
     } else {
       if (j >= 2) {
         // P.V_{j-2} has completed: P tile g&1 is free again
@@ -329,15 +341,13 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
         if (ok) mp[i & 3] = fmaxf(mp[i & 3], sv);
       }
     }
-    uint8_t* p_row = sP + (g & 1) * AttnSmem::kP + p_off;
-    if (!(dbg & 1))
+    if (dbg & 1) {
+    } else {                // P -> tensor memory: this thread's 32 keys = 16 columns of bf16 pairs in its own lane
+      uint32_t pw[16];
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      uint4 u;
-      u.x = pack_bf16(p[8 * g], p[8 * g + 1]); u.y = pack_bf16(p[8 * g + 2], p[8 * g + 3]);
-      u.z = pack_bf16(p[8 * g + 4], p[8 * g + 5]); u.w = pack_bf16(p[8 * g + 6], p[8 * g + 7]);
-      const int chunk = half * 4 + g;  // 16-byte chunk index inside the 128-byte row
-      *reinterpret_cast<uint4*>(p_row + ((chunk ^ r8) << 4)) = u;
+      for (int w = 0; w < 16; ++w) pw[w] = pack_bf16(p[2 * w], p[2 * w + 1]);
+      tmem_st_32x16(tmem_P + lane_off + (g & 1) * 32 + half * 16, pw);
+      tmem_st_wait();
     }
 #pragma unroll
     for (int i = 0; i < 32; ++i) lp[i & 3] += p[i];
@@ -345,9 +355,8 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
     m_loc = fmaxf(m_loc, fmaxf(fmaxf(mp[0], mp[1]), fmaxf(mp[2], mp[3])));
     const int need = m_loc > m_used + ((dbg & 16) ? 0.f : kRescaleLog2 / scale_log2e);
 
-    // P_j visible to the async proxy and every thread done reading S_j; then O += P_j.V_j and S buffer j&1 <- Q.K_{j+2}^T
+    // P_j stored to tensor memory (tcgen05.wait::st above) and every thread done reading S_j; then O += P_j.V_j and S buffer j&1 <- Q.K_{j+2}^T
     ATTN_STAMP(tr0, j, 4);
-    fence_proxy_async_smem();
     tc_fence_before();
     rescale = named_bar_or(1, 256, need);
     if (tid == 0) mbar_arrive(&bar_p[g & 1]);
@@ -360,7 +369,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
   mbar_wait(&bar_o[(g0 + nb - 1) & 1], ((g0 + nb - 1) >> 1) & 1);
   tc_fence_after();
   ATTN_STAMP(tr0, 15, 2);
-  float* s_x = reinterpret_cast<float*>(sP);         // every P tile is free now
+  float* s_x = reinterpret_cast<float*>(sP);
   s_x[half * 128 + row] = l_run;
   named_bar_sync(1, 256);
   l_run += s_x[(1 - half) * 128 + row];

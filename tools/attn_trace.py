@@ -16,13 +16,13 @@ enc = RegionEncoder(cfg, random_state_dict(cfg, text=False), max_images=16, max_
 px = torch.randn(16, 3, 336, 336, device="cuda")
 for _ in range(3):
     enc.forward_features_from_pixels(px)
-buf = torch.zeros(8 * 16 * 8, dtype=torch.int64, device="cuda")
+buf = torch.zeros(8 * 16 * 16, dtype=torch.int64, device="cuda")
 lib = _lib.lib()
 lib.ovo_attn_trace(_lib.ptr(buf))
 enc.forward_features_from_pixels(px)
 torch.cuda.synchronize()
 lib.ovo_attn_trace(None)
-t = buf.cpu().numpy().reshape(8, 16, 8)
+t = buf.cpu().numpy().reshape(8, 16, 16)
 names = ["top", "S ready", "tmem_ld done", "max/rescale done", "exp+P stored", "barrier done"]
 for it in range(5):
     if t[it, 15, 0] == 0:
@@ -34,5 +34,6 @@ for it in range(5):
             continue
         d = [int(t[it, j, k + 1] - t[it, j, k]) for k in range(5)]
         mma = (int(t[it, j, 6] - t[it, j, 5]), int(t[it, j, 7] - t[it, j, 6])) if t[it, j, 6] else None
+        fine = [int(t[it, j, b] - t[it, j, a]) if t[it, j, b] and t[it, j, a] else -1 for a, b in ((6, 8), (8, 10), (10, 11), (11, 12))]
         print(f"  block {j}: start +{int(t[it, j, 0] - base):6d} | wait S {d[0]:5d} | tmem_ld {d[1]:5d} | max/rescale {d[2]:5d} | exp+store {d[3]:5d} | fence+barrier {d[4]:5d}"
-              f" | MMA thread: woke {mma[0]:5d} after the arrive, issue took {mma[1]:5d}" if mma else "")
+              f" | MMA thread: woke {mma[0]:5d} after the arrive, issue took {mma[1]:5d} = V wait {fine[0]} | 4 P.V + 2 commits {fine[1]} | K wait {fine[2]} | 4 Q.K + 2 commits {fine[3]}" if mma else "")
