@@ -291,11 +291,9 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
       }
       m_loc = mine;   // (a thread's scratch slot is next written in a rescale or in the epilogue: a CTA barrier of a later block lies between)
     } else {
-      if (j >= 2) {
-        // P.V_{j-2} has completed: P tile g&1 is free again
-        mbar_wait(&bar_o[g & 1], ((g - 2) >> 1) & 1);
-        tc_fence_after();
-      }
+      // P buffer g&1 is free again without a wait of its own: S_j is ready (waited for above), so Q.K_j^T has completed, and
+      // with it every MMA its thread issued earlier (tcgen05.mma execute in issue order) — P.V_{j-2}, the buffer's last reader,
+      // was issued before Q.K_j^T.
       if (rescale) {   // rare, CTA-uniform (dbg 16: whenever a maximum grows, for the tests)
         mbar_wait(&bar_o[(g - 1) & 1], ((g - 1) >> 1) & 1);    // every P.V so far has landed: the accumulator is stable
         tc_fence_after();
