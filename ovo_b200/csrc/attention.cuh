@@ -81,12 +81,16 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
   uint64_t* bar_p = bars + 14;   // [2] P tile written and S buffer consumed by every softmax thread
   uint64_t* bar_kfree = bars + 16;   // [4] K slot consumed by its Q.K^T (tcgen05.commit): the producer may refill it
   uint64_t* bar_vfree = bars + 20;   // [4] V slot consumed by its P.V
+  // rescale requests, per warp pair and block (4 slots): the global index of the block in which some row of the pair outgrew
+  // its reference maximum; read two blocks later (block indices never repeat, so the slots are never cleared)
+  volatile int* s_flag = reinterpret_cast<volatile int*>(bars + 24) + (warp & 3) * 4;
   if (tid == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
     for (int i = 0; i < 12; ++i) mbar_init(&bars[i], 1);
     mbar_init(bar_q, 1);
-    mbar_init(&bar_p[0], 1);
-    mbar_init(&bar_p[1], 1);
+    mbar_init(&bar_p[0], 8);      // one arrival per softmax warp
+    mbar_init(&bar_p[1], 8);
+    for (int i = 0; i < 16; ++i) reinterpret_cast<volatile int*>(bars + 24)[i] = -1;
     for (int i = 0; i < 4; ++i) { mbar_init(&bar_kfree[i], 1); mbar_init(&bar_vfree[i], 1); }
     fence_barrier_init();
   }
@@ -220,7 +224,11 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
   float m_used = -INFINITY;      // the row's reference maximum (raw score units), identical in both halves
   float l_run = 0.f;             // partial row sum over this thread's keys
   float m_loc = -INFINITY;       // maximum this thread has seen over its keys so far
-  int rescale = 0;               // CTA-uniform: some row's maximum outgrew its reference by 2^kRescaleLog2 in the last block
+  int rescale = 0;               // uniform over the warp pair: some row of the pair outgrew its reference by 2^kRescaleLog2 two blocks ago
+  // The two threads of a row sit in warps w and w + 4 (same TMEM lane quarter).  They synchronise only with each other (a 64-thread
+  // named barrier for the first block's maximum, the final row sum and the rare rescale); no barrier spans the CTA: every warp
+  // arrives on the "P ready" mbarrier by itself, so the eight softmax warps are free to drift apart.
+  const int pair_bar = 1 + (warp & 3);
   float s_tail = -INFINITY;      // raw score of the tail key (tail1), identical in both halves
   // this half's 32 dims of the tail key / 32 output columns of its V row (bf16, 64 B each): pulled into L1 now, read when used
   const uint4* kt_ptr = reinterpret_cast<const uint4*>(k_glob + (static_cast<size_t>(bh) * seq_pad + (seq - 1)) * 64 + half * 32);
@@ -283,22 +291,26 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
         dot = (d4[0] + d4[1]) + (d4[2] + d4[3]);
         s_x[256 + half * 128 + row] = dot;
       }
-      named_bar_sync(1, 256);
+      named_bar_sync(pair_bar, 64);
       m_used = fmaxf(mine, s_x[(1 - half) * 128 + row]);
       if (tail1) {
         s_tail = dot + s_x[256 + (1 - half) * 128 + row];   // a + b == b + a: the same value in both halves
         m_used = fmaxf(m_used, s_tail);
       }
-      m_loc = mine;   // (a thread's scratch slot is next written in a rescale or in the epilogue: a CTA barrier of a later block lies between)
+      m_loc = mine;   // (a thread's scratch slot is next written in a rescale at block >= 2 or in the epilogue: S of that block exists
+                      // only after every warp arrived for block 0, i.e. after the partner's read above)
     } else {
       // P buffer g&1 is free again without a wait of its own: S_j is ready (waited for above), so Q.K_j^T has completed, and
       // with it every MMA its thread issued earlier (tcgen05.mma execute in issue order) — P.V_{j-2}, the buffer's last reader,
-      // was issued before Q.K_j^T.
-      if (rescale) {   // rare, CTA-uniform (dbg 16: whenever a maximum grows, for the tests)
+      // was issued before Q.K_j^T.  The same chain (the pair's writes of block j-2 -> bar_p -> MMA warp -> commit -> bar_s) makes the
+      // pair's rescale request of block j-2 visible here.
+      if (j >= 2) rescale = (s_flag[(g - 2) & 3] == g - 2);
+      if (rescale) {   // rare, uniform over the warp pair (dbg 16: whenever a maximum grows, for the tests)
+        rescale = 0;
         mbar_wait(&bar_o[(g - 1) & 1], ((g - 1) >> 1) & 1);    // every P.V so far has landed: the accumulator is stable
-        tc_fence_after();
+        tc_fence_after();                                     // (P.V_j cannot start before this warp has arrived for block j)
         s_x[half * 128 + row] = m_loc;
-        named_bar_sync(1, 256);
+        named_bar_sync(pair_bar, 64);
         const float m_new = fmaxf(m_used, fmaxf(m_loc, s_x[(1 - half) * 128 + row]));   // the same in both halves of the row
         const float alpha = (m_new > m_used) ? fast_ex2((m_used - m_new) * scale_log2e) : 1.f;
         uint32_t o[32];
@@ -310,7 +322,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
         tmem_st_wait();
         l_run *= alpha;
         m_used = m_new;
-        named_bar_sync(1, 256);                             // scratch reads done before P is written again
+        named_bar_sync(pair_bar, 64);                       // scratch reads done before the slot can be written again
       }
     }
     const float m_scaled = (m_used == -INFINITY) ? 0.f : m_used * scale_log2e;
@@ -355,9 +367,10 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
 
     // P_j stored to tensor memory (tcgen05.wait::st above) and every thread done reading S_j; then O += P_j.V_j and S buffer j&1 <- Q.K_{j+2}^T
     ATTN_STAMP(tr0, j, 4);
+    if (need) s_flag[g & 3] = g;      // picked up by both warps of the pair at block j + 2
     tc_fence_before();
-    rescale = named_bar_or(1, 256, need);
-    if (tid == 0) mbar_arrive(&bar_p[g & 1]);
+    __syncwarp();
+    if ((tid & 31) == 0) mbar_arrive(&bar_p[g & 1]);   // one of 8 arrivals: this warp's P rows are stored, its S rows consumed
     ATTN_STAMP(tr0, j, 5);
   }
   ATTN_STAMP(tr0, 15, 1);
@@ -369,7 +382,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
   ATTN_STAMP(tr0, 15, 2);
   float* s_x = reinterpret_cast<float*>(sP);
   s_x[half * 128 + row] = l_run;
-  named_bar_sync(1, 256);
+  named_bar_sync(pair_bar, 64);
   l_run += s_x[(1 - half) * 128 + row];
   uint32_t v[32];
   tmem_ld_32x32(tmem_O + lane_off + half * 32, v);   // warp-collective: every lane, also the padding rows
@@ -401,8 +414,10 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
       *reinterpret_cast<uint4*>(dst + 8 * g) = u;
     }
   }
+  // the partner has read this thread's scratch slot before it is written again (next item's block 0); this warp's accumulator
+  // reads precede its first bar_p arrival of the next item, which P.V_0 (the first MMA to overwrite the accumulator) waits for
   tc_fence_before();
-  named_bar_sync(1, 256);                                   // scratch and accumulator reads done before the next item reuses them
+  named_bar_sync(pair_bar, 64);
   tc_fence_after();
   ATTN_STAMP(tr0, 15, 3);
   g0 += nb;
