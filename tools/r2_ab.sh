@@ -1,14 +1,11 @@
 #!/bin/bash
-# same-box A/B of tuning switches on the device-resident step
+# Same-box A/B (run under gpurun): the working tree's library against a previous build of it.
+#   1. build the older commit in a git worktree and copy its ovo_b200/libovo_b200.so to tools/_ab/libovo_prev.so (git-ignored)
+#   2. gpurun -- bash tools/r2_ab.sh [bench flags]
+# Boxes of the pool differ by +-2 % on the same build, so only runs of ONE call are compared; the pairs alternate to expose drift.
 cd /root/repo
-run() { # label, env...
-  local l=$1; shift
-  env "$@" python bench.py --only-value --steps 40 --warmup 5 2>&1 | tail -1 | python -c "
-import sys, json
-d = json.loads(sys.stdin.read()); print('$l', d['value'], d['ms_per_step'])"
-}
-python -m pytest tests/test_gpu_encoder.py tests/test_gpu_crops.py -m gpu -x -q 2>&1 | tail -2
-run tail-on X=1
-run tail-off OVO_B200_ATTN_TAIL=0
-run tail-on X=1
-run tail-off OVO_B200_ATTN_TAIL=0
+FLAGS=${@:---only-value --side none --steps 40 --warmup 5}
+for i in 1 2 3; do
+  echo -n "new   "; timeout 200 python bench.py $FLAGS 2>&1 | tail -1
+  echo -n "prev  "; OVO_B200_LIB=/root/repo/tools/_ab/libovo_prev.so timeout 200 python bench.py $FLAGS 2>&1 | tail -1
+done
